@@ -1,0 +1,314 @@
+/*
+ * pxf.h -- C ABI of libpxf.so, the B200 (sm_100a) ray-trace engine that replaces
+ * PyXFocus's four f2py Fortran extension modules (transformationsf, surfacesf,
+ * woltsurf, zernsurf) plus the numpy analyses on the trace hot path.
+ *
+ * Conventions
+ *   - Every ray array is a DEVICE pointer to `num` contiguous IEEE fp64 values
+ *     (one row of the structure-of-arrays bundle [opd,x,y,z,l,m,n,ux,uy,uz],
+ *     reference sources.py:1-15).  Arrays are mutated in place, exactly like the
+ *     Fortran `intent(inout)` arguments they replace.  Rows may be independent
+ *     allocations; when every row is 16-byte aligned the kernels use double2
+ *     loads/stores.
+ *   - Scalars have the meaning and order of the Fortran dummy arguments
+ *     (file:line cited at each entry).  The array-length argument `num` that
+ *     f2py hides is explicit here.
+ *   - `mask` (nullable) is a device uint8 array of length num: ray i is
+ *     processed iff mask[i] != 0.  It replaces the reference's ind= gather ->
+ *     Fortran -> scatter idiom (transformations.py:20-27, surfaces.py:17-24).
+ *   - `stream` is a cudaStream_t (CUstream); work is enqueued asynchronously.
+ *     Entry points that return scalars to host memory synchronise the stream.
+ *   - Return value: PXF_OK or an error code; pxf_last_error() gives text.
+ *     Per-ray failures stay in-band exactly as in the reference (zeroed
+ *     direction cosines, NaN, restored positions).
+ *   - No CPU fallback exists: without a CUDA device every entry point that
+ *     touches rays returns PXF_ERR_CUDA.
+ */
+#ifndef PXF_H
+#define PXF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *pxf_stream_t;
+
+enum {
+    PXF_OK = 0,
+    PXF_ERR_INVALID = 1, /* bad argument (null pointer, negative size, bad table) */
+    PXF_ERR_CUDA = 2,    /* CUDA runtime/launch failure                           */
+    PXF_ERR_NOMEM = 3,   /* workspace allocation failed                           */
+    PXF_ERR_UNSUPPORTED = 4
+};
+
+int pxf_version(void);
+const char *pxf_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t pxf_launch_count(void);
+/* Iteration cap applied to the reference's uncapped Newton loops (oracle uses the same). */
+int pxf_newton_cap(void);
+
+/* ======================= transformationsf =============================== */
+/* transformationsf.f95:134-163  transform(x,y,z,l,m,n,ux,uy,uz,num,tx,ty,tz,rx,ry,rz) */
+int pxf_transform(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num,
+                  double tx, double ty, double tz, double rx, double ry, double rz,
+                  const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:168-201 */
+int pxf_itransform(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num,
+                   double tx, double ty, double tz, double rx, double ry, double rz,
+                   const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:60-79 */
+int pxf_reflect(double *l, double *m, double *n, double *ux, double *uy, double *uz, int64_t num,
+                const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:82-130 */
+int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double *uz, int64_t num,
+                double n1, double n2, const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:205-238 (scalar wavelength; sign of n kept) */
+int pxf_radgrat(const double *x, const double *y, double *l, double *m, double *n, double wave,
+                int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:242-272 (per-ray wavelength; sign taken from y) */
+int pxf_radgratw(const double *x, const double *y, double *l, double *m, double *n, const double *wave,
+                 int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream);
+/* transformationsf.f95:277-305 (linear grating, per-ray order and wavelength) */
+int pxf_grat(const double *x, const double *y, double *l, double *m, double *n, int64_t num, double d,
+             const double *order, const double *wave, const uint8_t *mask, pxf_stream_t stream);
+
+/* ======================= surfacesf ====================================== */
+/* surfacesf.f95:4-29 (REAL*4 delta) */
+int pxf_flat(double *x, double *y, double *z, const double *l, const double *m, const double *n,
+             double *ux, double *uy, double *uz, int64_t num, const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:32-53 */
+int pxf_flatopd(double *x, double *y, double *z, const double *l, const double *m, const double *n,
+                double *ux, double *uy, double *uz, double *opd, int64_t num, double nr,
+                const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:302-360 */
+int pxf_conic(double *x, double *y, double *z, double *l, double *m, double *n,
+              double *ux, double *uy, double *uz, int64_t num, double R, double K,
+              const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:366-420 */
+int pxf_conicopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double R, double K, double nr,
+                 const uint8_t *mask, pxf_stream_t stream);
+
+/* ======================= woltsurf ======================================= */
+/* woltsurf.f95:7-54 */
+int pxf_wolterprimary(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                      const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:60-108 */
+int pxf_wolterprimaryopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                         double *ux, double *uy, double *uz, int64_t num,
+                         double r0, double z0, double psi, double nr,
+                         const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:114-161 */
+int pxf_woltersecondary(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                        const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:167-215 */
+int pxf_woltersine(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num,
+                   double r0, double z0, double amp, double freq,
+                   const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:387-476 */
+int pxf_wsprimary(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                  const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:484-588 */
+int pxf_wssecondary(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                    const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:591-638 */
+int pxf_spocone(double *x, double *y, double *z, double *l, double *m, double *n,
+                double *ux, double *uy, double *uz, int64_t num, double R0, double tg,
+                const uint8_t *mask, pxf_stream_t stream);
+
+/* ======================= zernsurf ======================================= */
+/* zernsurf.f95:8-101.  coeff/rorder/aorder are HOST pointers (arrsize entries; the f2py
+ * wrapper receives them as small numpy arrays, surfaces.py:39-43).  rorder[i] <= 15. */
+int pxf_tracezern(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num,
+                  const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                  double rad, const uint8_t *mask, pxf_stream_t stream);
+/* zernsurf.f95:108-203 */
+int pxf_tracezernopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num,
+                     const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                     double rad, double nr, const uint8_t *mask, pxf_stream_t stream);
+
+/* ======================= fused per-ray program ========================== */
+/* One kernel: load a ray once, run a list of the operations above in registers,
+ * store once.  Arithmetic is the same device code as the per-op entry points, so
+ * results are bit-identical to calling them one by one. */
+enum {
+    PXF_OP_TRANSFORM = 1,      /* p: tx,ty,tz,rx,ry,rz                 */
+    PXF_OP_ITRANSFORM = 2,     /* p: tx,ty,tz,rx,ry,rz                 */
+    PXF_OP_REFLECT = 3,
+    PXF_OP_REFRACT = 4,        /* p: n1,n2                             */
+    PXF_OP_RADGRAT = 5,        /* p: wave,dpermm,order                 */
+    PXF_OP_FLAT = 6,
+    PXF_OP_FLATOPD = 7,        /* p: nr                                */
+    PXF_OP_CONIC = 8,          /* p: R,K                               */
+    PXF_OP_CONICOPD = 9,       /* p: R,K,nr                            */
+    PXF_OP_WOLTERPRIMARY = 10, /* p: r0,z0,psi                         */
+    PXF_OP_WOLTERPRIMARYOPD = 11, /* p: r0,z0,psi,nr                   */
+    PXF_OP_WOLTERSECONDARY = 12,  /* p: r0,z0,psi                      */
+    PXF_OP_WOLTERSINE = 13,    /* p: r0,z0,amp,freq                    */
+    PXF_OP_WSPRIMARY = 14,     /* p: alpha,z0,psi                      */
+    PXF_OP_WSSECONDARY = 15,   /* p: alpha,z0,psi                      */
+    PXF_OP_SPOCONE = 16,       /* p: R0,tg                             */
+    PXF_OP_VIGNETTE_MAG = 17,  /* kill ray unless l^2+m^2+n^2 > .1 (transformations.py:220-223) */
+    PXF_OP_VIGNETTE_BOX = 18,  /* p: row(1..9),lo,hi ; kill ray unless lo < row < hi             */
+    PXF_OP_VIGNETTE_ABS = 19,  /* p: row(1..9),hi    ; kill ray unless |row| < hi                */
+    PXF_OP_KICK = 20           /* p: dl,dm,sn ; l+=dl, m+=dm, n=sn*sqrt(1-l^2-m^2) (field angle,
+                                  examples/axro/axialHeights.py:94-95 with dm=0 uses l only)   */
+};
+typedef struct pxf_op {
+    int32_t code;
+    int32_t reserved;
+    double p[6];
+} pxf_op;
+#define PXF_MAX_OPS 24
+/* rays[10] = device pointers in bundle order [opd,x,y,z,l,m,n,ux,uy,uz] (opd may be NULL when
+ * no OPD op is in the program).  alive (nullable): device uint8[num], set to 0 for rays killed
+ * by a VIGNETTE op (they stop executing at that op; their state at that point is stored), 1
+ * otherwise.  Required when the program contains a VIGNETTE op. */
+int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
+                      uint8_t *alive, pxf_stream_t stream);
+
+/* ======================= vignetting / compaction ======================== */
+/* flags[i] = (l^2+m^2+n^2 > .1), the default predicate of transformations.vignette
+ * (transformations.py:220-223; NaN compares false). */
+int pxf_vignette_flags(const double *l, const double *m, const double *n, int64_t num,
+                       uint8_t *flags, pxf_stream_t stream);
+/* Order-preserving stream compaction of nrows arrays by a uint8 flag array (replaces the
+ * ten numpy fancy-index copies of transformations.py:225).  Step 1 counts survivors
+ * (synchronises, returns the count in *count_host); step 2 scatters.  `scratch` is a device
+ * buffer of pxf_compact_scratch_bytes(num) bytes shared by both steps. */
+size_t pxf_compact_scratch_bytes(int64_t num);
+int pxf_compact_count(const uint8_t *flags, int64_t num, void *scratch, int64_t *count_host,
+                      pxf_stream_t stream);
+int pxf_compact_scatter(const double *const *rows_in, double *const *rows_out, int32_t nrows,
+                        const uint8_t *flags, int64_t num, const void *scratch, pxf_stream_t stream);
+/* int64 indices of the surviving rays (np.where(flags)[0]); same scratch as above. */
+int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, int64_t *idx_out,
+                        pxf_stream_t stream);
+
+/* ======================= analyses ======================================= */
+/* Weighted sums for analyses.centroid / rmsCentroid / analyticImagePlane
+ * (analyses.py:16-30,118-133).  w may be NULL (unit weights).  out_dev: device double[16].
+ *   PXF_SUMS_CENTROID   : [0]=sum w, [1]=sum w x, [2]=sum w y, [3]=count of rays
+ *   PXF_SUMS_RMS        : [0]=sum w, [1]=sum w ((x-cx)^2+(y-cy)^2)        (a=cx, b=cy)
+ *   PXF_SUMS_IMAGEPLANE : [0]=sum w, [1]=sum w x, [2]=sum w y, [3]=sum w l/n, [4]=sum w m/n,
+ *                         [5]=sum w x l/n, [6]=sum w y m/n, [7]=sum w (l/n)^2, [8]=sum w (m/n)^2
+ * Deterministic (fixed-shape tree, no atomics).  scratch: pxf_sums_scratch_bytes() bytes. */
+enum { PXF_SUMS_CENTROID = 0, PXF_SUMS_RMS = 1, PXF_SUMS_IMAGEPLANE = 2 };
+size_t pxf_sums_scratch_bytes(void);
+int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, const double *m,
+             const double *n, const double *w, int64_t num, double a, double b,
+             double *out_dev, void *scratch, pxf_stream_t stream);
+
+/* rho[i] = sqrt((x-cx)^2+(y-cy)^2)  (analyses.py:60-71) */
+int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy, double *rho_out,
+            pxf_stream_t stream);
+
+/* Exact radix select of the two middle order statistics of r = sqrt((x-cx)^2+(y-cy)^2)
+ * (keys==NULL) or of keys[i] (keys!=NULL), i.e. np.median in analyses.hpd (analyses.py:96),
+ * with DEVICE-RESIDENT state so no pass needs a host round trip and so that a sharded
+ * bundle can all-reduce the per-pass histogram between pxf_select_hist and
+ * pxf_select_narrow.  `state` is a device buffer of pxf_select_state_bytes()
+ * bytes laid out [chain state 48 B][nan count u64][pad][histogram u64 x 2*8192]; the two
+ * accessors return device pointers into it (for the collective).
+ *   pxf_select_begin   : ranks k0 <= k1 (0-based, over the GLOBAL ray count) to resolve
+ *   pxf_select_hist    : add this shard's histogram of digit (key>>shift)&(2^bits-1) for the
+ *                        keys that match the prefix of each still-unresolved chain; NaN
+ *                        keys are counted separately.  cxy_dev = device double[2] centroid.
+ *   pxf_select_narrow  : pick the bin holding each rank, extend the prefixes, clear hist
+ *   pxf_select_finish  : out_dev[0] = 2*median (mean of the two order statistics; NaN if
+ *                        any key is NaN or num_total == 0 -- numpy semantics),
+ *                        out_dev[1], out_dev[2] = the two order statistics
+ *   pxf_select_schedule: digit schedule (shift,bits) of pass `pass`; returns #passes (5). */
+size_t pxf_select_state_bytes(void);
+int pxf_select_begin(void *state, int64_t k0, int64_t k1, pxf_stream_t stream);
+int pxf_select_hist(const double *x, const double *y, const double *keys, int64_t num,
+                    const double *cxy_dev, int32_t shift, int32_t bits, void *state,
+                    pxf_stream_t stream);
+uint64_t *pxf_select_hist_ptr(void *state);
+uint64_t *pxf_select_nan_ptr(void *state);
+int pxf_select_narrow(int32_t bits, void *state, pxf_stream_t stream);
+int pxf_select_finish(void *state, int64_t num_total, double *out_dev, pxf_stream_t stream);
+int pxf_select_schedule(int32_t pass, int32_t *shift, int32_t *bits);
+/* cxy_dev[0] = sums[1]/sums[0], cxy_dev[1] = sums[2]/sums[0] (np.average) */
+int pxf_centroid_from_sums(const double *sums_dev, double *cxy_dev, pxf_stream_t stream);
+/* Unweighted HPD entirely on the device: centroid sums -> centroid -> 5 select passes.
+ * out_dev: device double[3] as pxf_select_finish; workspace: pxf_hpd_workspace_bytes(). */
+size_t pxf_hpd_workspace_bytes(void);
+int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev,
+                           void *workspace, pxf_stream_t stream);
+/* rows_out[r][i] = rows_in[r][idx[i]] for nrows <= 16 rows (vignette with an index array,
+ * transformations.py:225).  rows_in/rows_out are HOST arrays of device pointers;
+ * table_scratch: >= 256 B device. */
+int pxf_gather_rows(const double *const *rows_in, double *const *rows_out, int32_t nrows,
+                    const int64_t *idx, int64_t count, void *table_scratch, pxf_stream_t stream);
+
+/* Convenience, single GPU: analyses.hpd / rmsCentroid / centroid / analyticImagePlane end to
+ * end, result in host memory (synchronises).  weights may be NULL.
+ *   pxf_hpd unweighted: 2*median(r) (exact order statistics; mean of the two middle values for
+ *   even num, NaN if any r is NaN -- numpy semantics).  Weighted: radix sort by r, cumulative
+ *   weights, r[argmin|cdf-.75|]-r[argmin|cdf-.25|] (analyses.py:91-94). */
+int pxf_centroid(const double *x, const double *y, const double *w, int64_t num,
+                 double *cx_host, double *cy_host, pxf_stream_t stream);
+int pxf_rmscentroid(const double *x, const double *y, const double *w, int64_t num,
+                    double *rms_host, pxf_stream_t stream);
+int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+            pxf_stream_t stream);
+int pxf_analyticimageplane(const double *x, const double *y, const double *l, const double *m,
+                           const double *n, const double *w, int64_t num, double *dz_host,
+                           pxf_stream_t stream);
+
+/* Stable LSD radix sort of fp64 keys (ascending by IEEE total order of non-negative values;
+ * negative keys and NaNs are ordered by their raw bit pattern after sign fix-up as in
+ * np.sort) with the permutation (np.argsort equivalent, stable).  keys_out / idx_out device
+ * arrays of length num.  scratch: pxf_sort_scratch_bytes(num). */
+size_t pxf_sort_scratch_bytes(int64_t num);
+int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
+                void *scratch, pxf_stream_t stream);
+/* out[i] = inclusive prefix sum of (w ? w[idx[i]] : 1.0)  (np.cumsum(weights[ind]),
+ * analyses.py:83-85).  scratch: pxf_scan_scratch_bytes(num). */
+size_t pxf_scan_scratch_bytes(int64_t num);
+int pxf_cumsum_gather(const double *w, const int64_t *idx, int64_t num, double *out,
+                      void *scratch, pxf_stream_t stream);
+
+/* ======================= sources ======================================== */
+/* Device-side ray generation for bundles too large for host MT19937 (SURVEY 7 "RNG parity").
+ * Counter-based Philox4x32-10, key=(seed lo,hi), counter=(global ray index, stream id);
+ * u1,u2 are 53-bit uniforms built as numpy does ((a>>5)*2^26+(b>>6))/2^53.  Same formulas as
+ * sources.py:130-170 / :56-88 / :20-53 / :91-127.  `first` is the global index of ray 0 of
+ * this shard so that sharded generation reproduces the single-GPU stream.
+ * kind: 0=subannulus(a=rin,b=rout,c=dphi,d=zhat) 1=circularbeam(a=rad) 2=pointsource(a=ang)
+ *       3=annulus(a=rin,b=rout,d=zhat) */
+int pxf_source(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+               double a, double b, double c, double d, pxf_stream_t stream);
+/* The same formulas applied to caller-supplied uniforms u1,u2 (device arrays, e.g. uploaded
+ * from numpy's legacy MT19937 for bit-identical seeds). */
+int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, const double *u1,
+                            const double *u2, double a, double b, double c, double d,
+                            pxf_stream_t stream);
+
+/* ======================= host-buffer entry points ======================= */
+/* The call an f2py user makes: HOST arrays in, HOST arrays mutated in place.  The ten host rows
+ * are streamed through the device in chunks on internal streams (H2D, fused program, D2H
+ * overlap); rows_host[k] may be NULL for rows the program neither reads nor writes.  When
+ * hpd_host != NULL the unweighted HPD of the final bundle is also returned (the bundle then has to
+ * fit on the device).  write_back=0 skips the D2H copy of the rays (analysis-only callers). */
+int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
+                           int32_t write_back, double *hpd_host, int64_t *alive_count_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PXF_H */

@@ -1,0 +1,265 @@
+"""f2py-shaped Python bindings over ``liboracle.so`` (TEST INFRASTRUCTURE ONLY).
+
+Each function mirrors the signature f2py generates for the corresponding
+Fortran subroutine (array-length arguments dropped, names lower-cased;
+call sites ``surfaces.py:21-43,110-112,224-226,242,269,342,378,413`` and
+``transformations.py:24,29,58,63,108,111,120,163,170``).  ``intent(inout)``
+arrays must be 1-D contiguous float64 and are mutated in place; anything else
+raises ``ValueError`` like the f2py wrapper would.
+"""
+import ctypes
+import os
+import subprocess
+from types import SimpleNamespace
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_SRC = os.path.join(_HERE, "pxf_oracle.c")
+_lib = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_d = ctypes.c_double
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile if it is stale."""
+    stale = force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    nine = [_dp] * 9
+    L.pxfo_reflect.argtypes = [_dp] * 6 + [_i64]
+    L.pxfo_refract.argtypes = [_dp] * 6 + [_i64, _d, _d]
+    L.pxfo_transform.argtypes = nine + [_i64] + [_d] * 6
+    L.pxfo_itransform.argtypes = nine + [_i64] + [_d] * 6
+    L.pxfo_radgrat.argtypes = [_dp] * 5 + [_d, _i64, _d, _d]
+    L.pxfo_radgratw.argtypes = [_dp] * 6 + [_i64, _d, _d]
+    L.pxfo_grat.argtypes = [_dp] * 5 + [_i64, _d, _dp, _dp]
+    L.pxfo_flat.argtypes = nine + [_i64]
+    L.pxfo_flatopd.argtypes = nine + [_dp, _i64, _d]
+    L.pxfo_conic.argtypes = nine + [_i64, _d, _d]
+    L.pxfo_conicopd.argtypes = [_dp] * 10 + [_i64, _d, _d, _d]
+    L.pxfo_wolterprimary.argtypes = nine + [_i64, _d, _d, _d]
+    L.pxfo_wolterprimaryopd.argtypes = [_dp] * 10 + [_i64, _d, _d, _d, _d]
+    L.pxfo_woltersecondary.argtypes = nine + [_i64, _d, _d, _d]
+    L.pxfo_woltersine.argtypes = nine + [_i64, _d, _d, _d, _d]
+    L.pxfo_wsprimary.argtypes = nine + [_i64, _d, _d, _d]
+    L.pxfo_wssecondary.argtypes = nine + [_i64, _d, _d, _d]
+    L.pxfo_spocone.argtypes = nine + [_i64, _d, _d]
+    L.pxfo_zernset.argtypes = [_d, _d, _ip, _ip, _i32, _dp, _dp, _dp]
+    L.pxfo_tracezern.argtypes = nine + [_i64, _dp, _ip, _ip, _i32, _d]
+    L.pxfo_tracezernopd.argtypes = [_dp] * 10 + [_i64, _dp, _ip, _ip, _i32, _d, _d]
+    L.pxfo_radialpoly.argtypes = [_d, _i32, _i32]
+    L.pxfo_radialpoly.restype = _d
+    L.pxfo_legendre.argtypes = [_d, _i32]
+    L.pxfo_legendre.restype = _d
+    L.pxfo_legendrep.argtypes = [_d, _i32]
+    L.pxfo_legendrep.restype = _d
+    L.pxfo_woltersecondary_steps.argtypes = [_d] * 9
+    L.pxfo_woltersecondary_steps.restype = _i32
+
+
+def _io(*arrs):
+    """Validate intent(inout) arrays the way f2py does and return pointers."""
+    n = None
+    out = []
+    for a in arrs:
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.ndim != 1 or not a.flags.c_contiguous:
+            raise ValueError("failed in converting argument to C/Fortran array: "
+                             "intent(inout) array must be a contiguous 1-D float64 ndarray")
+        if n is None:
+            n = a.shape[0]
+        elif a.shape[0] != n:
+            raise ValueError("shape mismatch against num")
+        out.append(a.ctypes.data_as(_dp))
+    return n, out
+
+
+def _in(a, n=None):
+    """intent(in) array: f2py silently copies/casts."""
+    b = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and b.shape[0] != n:
+        raise ValueError("shape mismatch against num")
+    return b, b.ctypes.data_as(_dp)
+
+
+def _orders(rorder, aorder, arrsize):
+    r = np.ascontiguousarray(rorder, dtype=np.int32)
+    a = np.ascontiguousarray(aorder, dtype=np.int32)
+    if r.shape[0] != arrsize or a.shape[0] != arrsize:
+        raise ValueError("shape mismatch against arrsize")
+    return r, a
+
+
+# ---------------------------------------------------------------- transformationsf
+def _transform(x, y, z, l, m, n, ux, uy, uz, tx, ty, tz, rx, ry, rz):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_transform(*p, num, tx, ty, tz, rx, ry, rz)
+
+
+def _itransform(x, y, z, l, m, n, ux, uy, uz, tx, ty, tz, rx, ry, rz):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_itransform(*p, num, tx, ty, tz, rx, ry, rz)
+
+
+def _reflect(l, m, n, ux, uy, uz):
+    num, p = _io(l, m, n, ux, uy, uz)
+    lib().pxfo_reflect(*p, num)
+
+
+def _refract(l, m, n, ux, uy, uz, n1, n2):
+    num, p = _io(l, m, n, ux, uy, uz)
+    lib().pxfo_refract(*p, num, n1, n2)
+
+
+def _radgrat(x, y, l, m, n, wave, dpermm, order):
+    num, p = _io(l, m, n)
+    xb, xp = _in(x, num)
+    yb, yp = _in(y, num)
+    lib().pxfo_radgrat(xp, yp, *p, float(wave), num, dpermm, order)
+
+
+def _radgratw(x, y, l, m, n, wave, dpermm, order):
+    num, p = _io(l, m, n)
+    xb, xp = _in(x, num)
+    yb, yp = _in(y, num)
+    wb, wp = _in(wave, num)
+    lib().pxfo_radgratw(xp, yp, *p, wp, num, dpermm, order)
+
+
+def _grat(x, y, l, m, n, d, order, wave):
+    num, p = _io(l, m, n)
+    xb, xp = _in(x, num)
+    yb, yp = _in(y, num)
+    ob, op = _in(order, num)
+    wb, wp = _in(wave, num)
+    lib().pxfo_grat(xp, yp, *p, num, d, op, wp)
+
+
+transformationsf = SimpleNamespace(transform=_transform, itransform=_itransform, reflect=_reflect,
+                                   refract=_refract, radgrat=_radgrat, radgratw=_radgratw, grat=_grat)
+
+
+# ---------------------------------------------------------------- surfacesf
+def _flat(x, y, z, l, m, n, ux, uy, uz):
+    num, p = _io(x, y, z, ux, uy, uz)
+    lb, lp = _in(l, num)
+    mb, mp = _in(m, num)
+    nb, np_ = _in(n, num)
+    lib().pxfo_flat(p[0], p[1], p[2], lp, mp, np_, p[3], p[4], p[5], num)
+
+
+def _flatopd(x, y, z, l, m, n, ux, uy, uz, opd, nr):
+    num, p = _io(x, y, z, ux, uy, uz, opd)
+    lb, lp = _in(l, num)
+    mb, mp = _in(m, num)
+    nb, np_ = _in(n, num)
+    lib().pxfo_flatopd(p[0], p[1], p[2], lp, mp, np_, p[3], p[4], p[5], p[6], num, nr)
+
+
+def _conic(x, y, z, l, m, n, ux, uy, uz, r, k):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_conic(*p, num, r, k)
+
+
+def _conicopd(opd, x, y, z, l, m, n, ux, uy, uz, r, k, nr):
+    num, p = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_conicopd(*p, num, r, k, nr)
+
+
+surfacesf = SimpleNamespace(flat=_flat, flatopd=_flatopd, conic=_conic, conicopd=_conicopd)
+
+
+# ---------------------------------------------------------------- woltsurf
+def _wolterprimary(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_wolterprimary(*p, num, r0, z0, psi)
+
+
+def _wolterprimaryopd(opd, x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, nr):
+    num, p = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_wolterprimaryopd(*p, num, r0, z0, psi, nr)
+
+
+def _woltersecondary(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_woltersecondary(*p, num, r0, z0, psi)
+
+
+def _woltersine(x, y, z, l, m, n, ux, uy, uz, r0, z0, amp, freq):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_woltersine(*p, num, r0, z0, amp, freq)
+
+
+def _wsprimary(x, y, z, l, m, n, ux, uy, uz, alpha, z0, psi):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_wsprimary(*p, num, alpha, z0, psi)
+
+
+def _wssecondary(x, y, z, l, m, n, ux, uy, uz, alpha, z0, psi):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_wssecondary(*p, num, alpha, z0, psi)
+
+
+def _spocone(x, y, z, l, m, n, ux, uy, uz, r0, tg):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    lib().pxfo_spocone(*p, num, r0, tg)
+
+
+woltsurf = SimpleNamespace(wolterprimary=_wolterprimary, wolterprimaryopd=_wolterprimaryopd,
+                           woltersecondary=_woltersecondary, woltersine=_woltersine,
+                           wsprimary=_wsprimary, wssecondary=_wssecondary, spocone=_spocone)
+
+
+# ---------------------------------------------------------------- zernsurf
+def _tracezern(x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    cb, cp = _in(coeff)
+    r, a = _orders(rorder, aorder, cb.shape[0])
+    lib().pxfo_tracezern(*p, num, cp, r.ctypes.data_as(_ip), a.ctypes.data_as(_ip), cb.shape[0], rad)
+
+
+def _tracezernopd(opd, x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad, nr):
+    num, p = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+    cb, cp = _in(coeff)
+    r, a = _orders(rorder, aorder, cb.shape[0])
+    lib().pxfo_tracezernopd(*p, num, cp, r.ctypes.data_as(_ip), a.ctypes.data_as(_ip), cb.shape[0], rad, nr)
+
+
+zernsurf = SimpleNamespace(tracezern=_tracezern, tracezernopd=_tracezernopd)
+
+
+# ---------------------------------------------------------------- specialfunctions
+def _zernset(rho, theta, rorder, aorder):
+    r = np.ascontiguousarray(rorder, dtype=np.int32)
+    a = np.ascontiguousarray(aorder, dtype=np.int32)
+    znum = r.shape[0]
+    po, dr, dt = (np.zeros(znum) for _ in range(3))
+    lib().pxfo_zernset(float(rho), float(theta), r.ctypes.data_as(_ip), a.ctypes.data_as(_ip), znum,
+                       po.ctypes.data_as(_dp), dr.ctypes.data_as(_dp), dt.ctypes.data_as(_dp))
+    return po, dr, dt
+
+
+specialfunctions = SimpleNamespace(
+    zernset=_zernset,
+    radialpoly=lambda rho, n, m: lib().pxfo_radialpoly(float(rho), int(n), int(m)),
+    legendre=lambda x, n: lib().pxfo_legendre(float(x), int(n)),
+    legendrep=lambda x, n: lib().pxfo_legendrep(float(x), int(n)),
+)

@@ -1,0 +1,815 @@
+// Analyses on the trace hot path (analyses.py:16-30,60-97,118-133) and order-preserving
+// vignetting compaction (transformations.py:214-225).  All kernels are HBM-streaming:
+// persistent grids, double2 loads, warp-shuffle + shared-memory block reductions, a
+// fixed-shape two-level tree (deterministic, no floating-point atomics).
+#include "pxf_internal.h"
+#include "pxf_ray.cuh"
+
+namespace pxf {
+
+#define NSUM 9
+#define SUM_BLOCKS_MAX 2048   // >= SM count x resident CTAs
+
+// ------------------------------------------------------------------ sums
+template <int MODE>
+PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m, double n, double w,
+                        bool has_w, double a, double b)
+{
+    if (MODE == PXF_SUMS_CENTROID) {
+        acc[0] += w;
+        acc[1] += has_w ? x * w : x;
+        acc[2] += has_w ? y * w : y;
+        acc[3] += 1.;
+    } else if (MODE == PXF_SUMS_RMS) {
+        double rho = sq(x - a) + sq(y - b);
+        acc[0] += w;
+        acc[1] += has_w ? rho * w : rho;
+    } else {
+        double ln = l / n, mn = m / n;
+        double t1 = x * l / n, t2 = y * m / n, t3 = sq(ln), t4 = sq(mn);
+        acc[0] += w;
+        acc[1] += has_w ? x * w : x;
+        acc[2] += has_w ? y * w : y;
+        acc[3] += has_w ? ln * w : ln;
+        acc[4] += has_w ? mn * w : mn;
+        acc[5] += has_w ? t1 * w : t1;
+        acc[6] += has_w ? t2 * w : t2;
+        acc[7] += has_w ? t3 * w : t3;
+        acc[8] += has_w ? t4 * w : t4;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_sums(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ l,
+       const double *__restrict__ m, const double *__restrict__ n, const double *__restrict__ w,
+       int64_t num, double a, double b, const double *__restrict__ ab_dev, double *__restrict__ partial)
+{
+    constexpr int NS = MODE == PXF_SUMS_CENTROID ? 4 : (MODE == PXF_SUMS_RMS ? 2 : 9);
+    if (ab_dev) { a = ab_dev[0]; b = ab_dev[1]; }
+    double acc[NSUM];
+#pragma unroll
+    for (int k = 0; k < NSUM; k++) acc[k] = 0.;
+    const bool has_w = w != nullptr;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < num; i += nthr) {
+        double xv = x[i], yv = y[i];
+        double lv = 0., mv = 0., nv = 1.;
+        if (MODE == PXF_SUMS_IMAGEPLANE) { lv = l[i]; mv = m[i]; nv = n[i]; }
+        double wv = has_w ? w[i] : 1.;
+        sums_accum<MODE>(acc, xv, yv, lv, mv, nv, wv, has_w, a, b);
+    }
+    __shared__ double sh[NSUM][PXF_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            double v = lane < PXF_BLOCK / 32 ? sh[k][lane] : 0.;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) partial[(int64_t)blockIdx.x * NSUM + k] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_sums_final(const double *__restrict__ partial, int nblocks, int ns, double *__restrict__ out)
+{
+    __shared__ double sh[PXF_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < ns; k++) {
+        double v = 0.;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(int64_t)b * NSUM + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            v = lane < PXF_BLOCK / 32 ? sh[lane] : 0.;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) out[k] = v;
+        }
+        __syncthreads();
+    }
+}
+
+static int sums_launch(int mode, const double *x, const double *y, const double *l, const double *m,
+                       const double *n, const double *w, int64_t num, double a, double b,
+                       const double *ab_dev, double *out_dev, void *scratch, cudaStream_t s)
+{
+    if (num < 0 || !x || !y || !out_dev || !scratch) { set_error("pxf_sums: bad argument"); return PXF_ERR_INVALID; }
+    if (mode == PXF_SUMS_IMAGEPLANE && (!l || !m || !n)) { set_error("pxf_sums: l,m,n required"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    int grid = grid_for(num, PXF_BLOCK * 4, 8);
+    if (grid > SUM_BLOCKS_MAX) grid = SUM_BLOCKS_MAX;
+    double *partial = static_cast<double *>(scratch);
+    int ns;
+    if (mode == PXF_SUMS_CENTROID) {
+        ns = 4;
+        k_sums<PXF_SUMS_CENTROID><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
+    } else if (mode == PXF_SUMS_RMS) {
+        ns = 2;
+        k_sums<PXF_SUMS_RMS><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
+    } else if (mode == PXF_SUMS_IMAGEPLANE) {
+        ns = 9;
+        k_sums<PXF_SUMS_IMAGEPLANE><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
+    } else {
+        set_error("pxf_sums: bad mode");
+        return PXF_ERR_INVALID;
+    }
+    k_sums_final<<<1, PXF_BLOCK, 0, s>>>(partial, grid, ns, out_dev);
+    count_launch(2);
+    return check_launch("k_sums");
+}
+
+// cxy[0] = S1/S0, cxy[1] = S2/S0 (np.average: sum(w*x)/sum(w); unweighted: sum(x)/N)
+__global__ void k_centroid_from_sums(const double *__restrict__ sums, double *__restrict__ cxy)
+{
+    cxy[0] = sums[1] / sums[0];
+    cxy[1] = sums[2] / sums[0];
+}
+
+// ------------------------------------------------------------------ rho
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_rho(const double *__restrict__ x, const double *__restrict__ y, int64_t num, double cx, double cy,
+      const double *__restrict__ cxy_dev, double *__restrict__ out)
+{
+    if (cxy_dev) { cx = cxy_dev[0]; cy = cxy_dev[1]; }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < num; i += nthr) out[i] = sqrt(sq(x[i] - cx) + sq(y[i] - cy));
+}
+
+// ------------------------------------------------------------------ exact radix select
+// Device-resident state so that no pass needs a host round trip.
+struct SelectState {
+    unsigned long long prefix[2];   // resolved high bits of each chain (right aligned)
+    unsigned long long rank[2];     // 0-based rank still to resolve inside the prefix group
+    int nprefix;                    // 1 while both order statistics share a prefix, else 2
+    int pad;
+};
+
+PXF_DEV unsigned long long key_of(double r) { return (unsigned long long)__double_as_longlong(r); }
+
+template <bool FROM_KEYS>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_select_hist(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ keys,
+              int64_t num, const unsigned long long *__restrict__ count_dev,
+              const double *__restrict__ cxy, int shift, int bits,
+              const SelectState *__restrict__ st, unsigned long long *__restrict__ hist,
+              unsigned long long *__restrict__ nan_count)
+{
+    extern __shared__ unsigned int sh[];
+    const int nbins = 1 << bits;
+    const int np = st->nprefix;
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
+    const int hi = shift + bits;
+    for (int t = threadIdx.x; t < np * nbins; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    double cx = 0., cy = 0.;
+    if (!FROM_KEYS) { cx = cxy[0]; cy = cxy[1]; }
+    if (FROM_KEYS && count_dev) {
+        unsigned long long c = *count_dev;
+        if ((unsigned long long)num > c) num = (int64_t)c;
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    unsigned int nans = 0;
+    // whole warps iterate together so that __match_any_sync sees a full mask
+    const int64_t nround = (num + nthr - 1) / nthr;
+    for (int64_t it = 0; it < nround; it++) {
+        const int64_t i = tid + it * nthr;
+        int bin = -1;
+        if (i < num) {
+            double r = FROM_KEYS ? keys[i] : sqrt(sq(x[i] - cx) + sq(y[i] - cy));
+            if (r != r) {
+                nans++;
+            } else {
+                unsigned long long k = key_of(r);
+                unsigned long long top = hi >= 64 ? 0ull : (k >> hi);
+                int d = (int)((k >> shift) & (unsigned long long)(nbins - 1));
+                if (top == p0) bin = d;
+                else if (np == 2 && top == p1) bin = nbins + d;
+            }
+        }
+        // warp-aggregated shared-memory histogram: one atomic per distinct bin per warp
+        unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[bin], __popc(peers));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < np * nbins; t += blockDim.x) {
+        unsigned int v = sh[t];
+        if (v) atomicAdd(&hist[t], (unsigned long long)v);
+    }
+    if (nan_count) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nans += __shfl_down_sync(0xffffffffu, nans, o);
+        if ((threadIdx.x & 31) == 0 && nans) atomicAdd(nan_count, (unsigned long long)nans);
+    }
+}
+
+// One CTA walks the (all-reduced) histogram and narrows each chain by `bits` bits.
+__global__ void __launch_bounds__(1024)
+k_select_scan(unsigned long long *__restrict__ hist, int bits, SelectState *__restrict__ st)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ int found_bin[2];
+    __shared__ unsigned long long found_base[2];
+    const int nbins = 1 << bits;
+    const int np = st->nprefix;
+    const int per = (nbins + blockDim.x - 1) / blockDim.x;
+    if (threadIdx.x < 2) { found_bin[threadIdx.x] = 0; found_base[threadIdx.x] = 0ull; }
+    __syncthreads();
+    for (int j = 0; j < 2; j++) {
+        const int hsel = (np == 2) ? j : 0;
+        const unsigned long long *h = hist + (size_t)hsel * nbins;
+        const unsigned long long rank = st->rank[j];
+        // block-wide exclusive scan over contiguous chunks of `per` bins per thread
+        const int b0 = threadIdx.x * per;
+        unsigned long long local = 0;
+        for (int b = b0; b < b0 + per && b < nbins; b++) local += h[b];
+        unsigned long long incl = local;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0ull;
+            unsigned long long iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+                if (lane >= o) iv += t;
+            }
+            wsum[lane] = iv - v;
+        }
+        __syncthreads();
+        unsigned long long excl = wsum[warp] + incl - local;
+        if (rank >= excl && rank < excl + local) {
+            unsigned long long c = excl;
+            for (int b = b0; b < b0 + per && b < nbins; b++) {
+                unsigned long long hb = h[b];
+                if (rank < c + hb) { found_bin[j] = b; found_base[j] = c; break; }
+                c += hb;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long pa = st->prefix[0], pb = (np == 2) ? st->prefix[1] : st->prefix[0];
+        st->prefix[0] = (pa << bits) | (unsigned long long)found_bin[0];
+        st->prefix[1] = (pb << bits) | (unsigned long long)found_bin[1];
+        st->rank[0] -= found_base[0];
+        st->rank[1] -= found_base[1];
+        st->nprefix = (st->prefix[0] == st->prefix[1]) ? 1 : 2;
+    }
+    __syncthreads();
+    // zero the histogram for the next pass
+    for (int t = threadIdx.x; t < 2 * nbins; t += blockDim.x) hist[t] = 0ull;
+}
+
+__global__ void k_select_init(SelectState *st, unsigned long long k0, unsigned long long k1,
+                              unsigned long long *hist, int nh, unsigned long long *nan_count)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        st->prefix[0] = 0; st->prefix[1] = 0; st->rank[0] = k0; st->rank[1] = k1; st->nprefix = 1; st->pad = 0;
+        if (nan_count) *nan_count = 0;
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nh; t += gridDim.x * blockDim.x) hist[t] = 0ull;
+}
+
+// out[0] = 2*median (np.median(r)*2., analyses.py:96); out[1], out[2] = the two middle order statistics
+__global__ void k_select_result(const SelectState *st, const unsigned long long *nan_count, int64_t num,
+                                double *out)
+{
+    double a = __longlong_as_double((long long)st->prefix[0]);
+    double b = __longlong_as_double((long long)st->prefix[1]);
+    double med = (a + b) / 2.;
+    if (num == 0 || (nan_count && *nan_count > 0)) med = __longlong_as_double(0x7ff8000000000000ll);
+    out[0] = med * 2.;
+    out[1] = a;
+    out[2] = b;
+}
+
+// ------------------------------------------------------------------ compaction
+#define CTILE 2048   // rays per CTA tile: 8 warps x 8 chunks x 32 lanes
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_vignette_flags(const double *__restrict__ l, const double *__restrict__ m, const double *__restrict__ n,
+                 int64_t num, uint8_t *__restrict__ flags)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < num; i += nthr) {
+        double mag = sq(l[i]) + sq(m[i]) + sq(n[i]);
+        flags[i] = mag > .1 ? 1 : 0;
+    }
+}
+
+// per-tile survivor counts
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_compact_count(const uint8_t *__restrict__ flags, int64_t num, unsigned int *__restrict__ tile_count)
+{
+    __shared__ unsigned int sh[PXF_BLOCK / 32];
+    const int64_t base = (int64_t)blockIdx.x * CTILE;
+    unsigned int c = 0;
+#pragma unroll
+    for (int j = 0; j < CTILE / PXF_BLOCK; j++) {
+        int64_t i = base + j * PXF_BLOCK + threadIdx.x;
+        if (i < num && flags[i]) c++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < PXF_BLOCK / 32; w++) t += sh[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts into 64-bit offsets; total at offsets[ntiles]
+__global__ void __launch_bounds__(1024)
+k_compact_scan(const unsigned int *__restrict__ tile_count, int64_t ntiles, long long *__restrict__ offsets)
+{
+    __shared__ long long wsum[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < ntiles; b0 += blockDim.x) {
+        int64_t b = b0 + threadIdx.x;
+        long long v = b < ntiles ? (long long)tile_count[b] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane];
+            long long iw = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, iw, o);
+                if (lane >= o) iw += t;
+            }
+            wsum[lane] = iw - w;
+        }
+        __syncthreads();
+        long long excl = carry + wsum[warp] + incl - v;
+        if (b < ntiles) offsets[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[ntiles] = carry;
+}
+
+// Each warp owns 8 consecutive 32-ray chunks of the tile; ballot + popc give the rank inside a
+// chunk, a 64-entry shared scan gives the chunk base, the tile offset comes from k_compact_scan.
+template <int MODE>   // 0: scatter rows, 1: write indices
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_compact_scatter(const double *const *__restrict__ rows_in, double *const *__restrict__ rows_out, int nrows,
+                  const uint8_t *__restrict__ flags, int64_t num, const long long *__restrict__ offsets,
+                  long long *__restrict__ idx_out)
+{
+    __shared__ unsigned int chunk_cnt[CTILE / 32];
+    __shared__ unsigned int chunk_base[CTILE / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * CTILE;
+    unsigned int ballots[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int chunk = warp * 8 + j;
+        const int64_t i = base + chunk * 32 + lane;
+        const bool f = i < num && flags[i] != 0;
+        ballots[j] = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) chunk_cnt[chunk] = __popc(ballots[j]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int a = chunk_cnt[lane], b = chunk_cnt[lane + 32];
+        unsigned int ia = a, ib = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int ta = __shfl_up_sync(0xffffffffu, ia, o);
+            unsigned int tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+        }
+        unsigned int total_a = __shfl_sync(0xffffffffu, ia, 31);
+        chunk_base[lane] = ia - a;
+        chunk_base[lane + 32] = total_a + ib - b;
+    }
+    __syncthreads();
+    const long long tile_off = offsets[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int chunk = warp * 8 + j;
+        const int64_t i = base + chunk * 32 + lane;
+        if ((ballots[j] >> lane) & 1u) {
+            const long long dst = tile_off + chunk_base[chunk] + __popc(ballots[j] & ((1u << lane) - 1));
+            if (MODE == 0) {
+                for (int r = 0; r < nrows; r++) rows_out[r][dst] = rows_in[r][i];
+            } else {
+                idx_out[dst] = i;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_gather_rows(const double *const *__restrict__ rows_in, double *const *__restrict__ rows_out, int nrows,
+              const long long *__restrict__ idx, int64_t count)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < count; i += nthr) {
+        const long long s = idx[i];
+        for (int r = 0; r < nrows; r++) rows_out[r][i] = rows_in[r][s];
+    }
+}
+
+struct RowTable { const double *in[16]; double *out[16]; };
+
+static int need_device()
+{
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    return PXF_OK;
+}
+
+static int select_smem_bytes(int bits) { return 2 * (1 << bits) * (int)sizeof(unsigned int); }
+
+static int select_pass(const double *x, const double *y, const double *keys, int64_t num,
+                       const unsigned long long *count_dev, const double *cxy, int shift, int bits,
+                       SelectState *st, unsigned long long *hist, unsigned long long *nan_count, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_select_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes(13));
+        cudaFuncSetAttribute(k_select_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes(13));
+        attr_set = true;
+    }
+    int grid = grid_for(num, PXF_BLOCK * 8, 3);
+    if (keys)
+        k_select_hist<true><<<grid, PXF_BLOCK, select_smem_bytes(bits), s>>>(x, y, keys, num, count_dev, cxy, shift,
+                                                                           bits, st, hist, nan_count);
+    else
+        k_select_hist<false><<<grid, PXF_BLOCK, select_smem_bytes(bits), s>>>(x, y, keys, num, count_dev, cxy, shift,
+                                                                            bits, st, hist, nan_count);
+    count_launch();
+    return check_launch("k_select_hist");
+}
+
+}  // namespace pxf
+
+using namespace pxf;
+
+extern "C" {
+
+int pxf_hpd_weighted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+                     pxf_stream_t stream);   // pxf_sort.cu
+
+size_t pxf_sums_scratch_bytes(void) { return (size_t)SUM_BLOCKS_MAX * NSUM * sizeof(double); }
+
+int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, const double *m,
+             const double *n, const double *w, int64_t num, double a, double b,
+             double *out_dev, void *scratch, pxf_stream_t stream)
+{
+    return sums_launch(mode, x, y, l, m, n, w, num, a, b, nullptr, out_dev, scratch,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy, double *rho_out,
+            pxf_stream_t stream)
+{
+    if (num < 0 || !x || !y || !rho_out) { set_error("pxf_rho: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    if (num == 0) return PXF_OK;
+    k_rho<<<grid_for(num, PXF_BLOCK * 2, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, y, num, cx, cy, nullptr, rho_out);
+    count_launch();
+    return check_launch("k_rho");
+}
+
+// ---- radix-select primitives (device-resident state; used directly by the sharded path) ----
+size_t pxf_select_state_bytes(void) { return sizeof(SelectState) + 8 /*nan*/ + 2 * 8192 * 8 /*hist*/ + 64; }
+
+/* state layout inside the caller's buffer: [SelectState][nan u64][pad][hist u64 x 2*8192] */
+static inline SelectState *st_of(void *buf) { return reinterpret_cast<SelectState *>(buf); }
+static inline unsigned long long *nan_of(void *buf) { return reinterpret_cast<unsigned long long *>((char *)buf + 48); }
+static inline unsigned long long *hist_of(void *buf) { return reinterpret_cast<unsigned long long *>((char *)buf + 64); }
+
+int pxf_select_begin(void *state, int64_t k0, int64_t k1, pxf_stream_t stream)
+{
+    if (!state || k0 < 0 || k1 < k0) { set_error("pxf_select_begin: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_select_init<<<16, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        st_of(state), (unsigned long long)k0, (unsigned long long)k1, hist_of(state), 2 * 8192, nan_of(state));
+    count_launch();
+    return check_launch("k_select_init");
+}
+
+/* histogram of one digit of the local shard into the state's histogram (device uint64[2<<13]) */
+int pxf_select_hist(const double *x, const double *y, const double *keys, int64_t num, const double *cxy_dev,
+                    int32_t shift, int32_t bits, void *state, pxf_stream_t stream)
+{
+    if (!state || bits < 1 || bits > 13 || shift < 0 || shift + bits > 64 || num < 0 ||
+        (!keys && (!x || !y || !cxy_dev))) {
+        set_error("pxf_select_hist: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    int rc = need_device();
+    if (rc) return rc;
+    if (num == 0) return PXF_OK;
+    return select_pass(x, y, keys, num, nullptr, cxy_dev, shift, bits, st_of(state), hist_of(state), nan_of(state),
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t *pxf_select_hist_ptr(void *state) { return reinterpret_cast<uint64_t *>(hist_of(state)); }
+uint64_t *pxf_select_nan_ptr(void *state) { return reinterpret_cast<uint64_t *>(nan_of(state)); }
+
+/* narrow both chains by `bits` using the (possibly all-reduced) histogram, then clear it */
+int pxf_select_narrow(int32_t bits, void *state, pxf_stream_t stream)
+{
+    if (!state || bits < 1 || bits > 13) { set_error("pxf_select_narrow: bad argument"); return PXF_ERR_INVALID; }
+    k_select_scan<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hist_of(state), bits, st_of(state));
+    count_launch();
+    return check_launch("k_select_scan");
+}
+
+/* out_dev[0] = 2*median, out_dev[1..2] = the two middle order statistics */
+int pxf_select_finish(void *state, int64_t num_total, double *out_dev, pxf_stream_t stream)
+{
+    if (!state || !out_dev) { set_error("pxf_select_finish: bad argument"); return PXF_ERR_INVALID; }
+    k_select_result<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(st_of(state), nan_of(state), num_total, out_dev);
+    count_launch();
+    return check_launch("k_select_result");
+}
+
+int pxf_centroid_from_sums(const double *sums_dev, double *cxy_dev, pxf_stream_t stream)
+{
+    if (!sums_dev || !cxy_dev) { set_error("pxf_centroid_from_sums: bad argument"); return PXF_ERR_INVALID; }
+    k_centroid_from_sums<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums_dev, cxy_dev);
+    count_launch();
+    return check_launch("k_centroid_from_sums");
+}
+
+// The digit schedule of the 64-bit key: 13+13+13+13+12.
+static const int kShift[5] = {51, 38, 25, 12, 0};
+static const int kBits[5] = {13, 13, 13, 13, 12};
+
+int pxf_select_schedule(int32_t pass, int32_t *shift, int32_t *bits)
+{
+    if (pass < 0 || pass >= 5) return 0;
+    *shift = kShift[pass]; *bits = kBits[pass];
+    return 5;
+}
+
+// ---- single-GPU convenience entry points --------------------------------------------------
+int pxf_centroid(const double *x, const double *y, const double *w, int64_t num,
+                 double *cx_host, double *cy_host, pxf_stream_t stream)
+{
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    Scratch sc;
+    if ((rc = sc.alloc(pxf_sums_scratch_bytes() + 16 * sizeof(double), s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_sums_scratch_bytes());
+    if ((rc = sums_launch(PXF_SUMS_CENTROID, x, y, nullptr, nullptr, nullptr, w, num, 0., 0., nullptr, out, sc.p, s)))
+        return rc;
+    double h[4];
+    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    *cx_host = h[1] / h[0];
+    *cy_host = h[2] / h[0];
+    return PXF_OK;
+}
+
+int pxf_rmscentroid(const double *x, const double *y, const double *w, int64_t num,
+                    double *rms_host, pxf_stream_t stream)
+{
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    Scratch sc;
+    if ((rc = sc.alloc(pxf_sums_scratch_bytes() + 32 * sizeof(double), s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_sums_scratch_bytes());
+    double *cxy = out + 16;
+    if ((rc = sums_launch(PXF_SUMS_CENTROID, x, y, nullptr, nullptr, nullptr, w, num, 0., 0., nullptr, out, sc.p, s)))
+        return rc;
+    k_centroid_from_sums<<<1, 1, 0, s>>>(out, cxy);
+    count_launch();
+    if ((rc = sums_launch(PXF_SUMS_RMS, x, y, nullptr, nullptr, nullptr, w, num, 0., 0., cxy, out, sc.p, s)))
+        return rc;
+    double h[2];
+    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    *rms_host = sqrt(h[1] / h[0]);
+    return PXF_OK;
+}
+
+int pxf_analyticimageplane(const double *x, const double *y, const double *l, const double *m,
+                           const double *n, const double *w, int64_t num, double *dz_host,
+                           pxf_stream_t stream)
+{
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    Scratch sc;
+    if ((rc = sc.alloc(pxf_sums_scratch_bytes() + 16 * sizeof(double), s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_sums_scratch_bytes());
+    if ((rc = sums_launch(PXF_SUMS_IMAGEPLANE, x, y, l, m, n, w, num, 0., 0., nullptr, out, sc.p, s))) return rc;
+    double h[9];
+    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    // analyses.py:123-131 with <q> = S_q/S_0
+    const double W = h[0];
+    double ax_ = h[1] / W, ay_ = h[2] / W, aln = h[3] / W, amn = h[4] / W;
+    double bx = h[5] / W - ax_ * aln;
+    double ax = h[7] / W - aln * aln;
+    double by = h[6] / W - ay_ * amn;
+    double ay = h[8] / W - amn * amn;
+    *dz_host = -(bx + by) / (ax + ay);
+    return PXF_OK;
+}
+
+int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev /*[3]*/,
+                           void *workspace, pxf_stream_t stream)
+{
+    // workspace: pxf_hpd_workspace_bytes()
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    char *ws = static_cast<char *>(workspace);
+    double *sums = reinterpret_cast<double *>(ws + pxf_sums_scratch_bytes());
+    double *cxy = sums + 16;
+    void *state = ws + pxf_sums_scratch_bytes() + 32 * sizeof(double);
+    if ((rc = sums_launch(PXF_SUMS_CENTROID, x, y, nullptr, nullptr, nullptr, nullptr, num, 0., 0., nullptr, sums, ws, s)))
+        return rc;
+    k_centroid_from_sums<<<1, 1, 0, s>>>(sums, cxy);
+    count_launch();
+    int64_t k0 = num > 0 ? (num - 1) / 2 : 0, k1 = num > 0 ? num / 2 : 0;
+    if ((rc = pxf_select_begin(state, k0, k1, stream))) return rc;
+    for (int p = 0; p < 5 && num > 0; p++) {
+        if ((rc = pxf_select_hist(x, y, nullptr, num, cxy, kShift[p], kBits[p], state, stream))) return rc;
+        if ((rc = pxf_select_narrow(kBits[p], state, stream))) return rc;
+    }
+    return pxf_select_finish(state, num, out_dev, stream);
+}
+
+size_t pxf_hpd_workspace_bytes(void)
+{
+    return pxf_sums_scratch_bytes() + 32 * sizeof(double) + pxf_select_state_bytes();
+}
+
+int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+            pxf_stream_t stream)
+{
+    if (num < 0 || !x || !y || !hpd_host) { set_error("pxf_hpd: bad argument"); return PXF_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    if (w) return pxf_hpd_weighted(x, y, w, num, hpd_host, stream);
+    Scratch sc;
+    if ((rc = sc.alloc(pxf_hpd_workspace_bytes() + 64, s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_hpd_workspace_bytes());
+    if ((rc = pxf_hpd_unweighted_dev(x, y, num, out, sc.p, stream))) return rc;
+    double h[3];
+    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    *hpd_host = h[0];
+    return PXF_OK;
+}
+
+// ---- compaction ---------------------------------------------------------------------------
+size_t pxf_compact_scratch_bytes(int64_t num)
+{
+    int64_t ntiles = (num + CTILE - 1) / CTILE;
+    if (ntiles < 1) ntiles = 1;
+    // [offsets int64 x (ntiles+1)] [tile_count u32 x ntiles] [row table]
+    return (size_t)(ntiles + 1) * 8 + (size_t)ntiles * 4 + 16 + sizeof(RowTable);
+}
+
+static inline long long *coff(const void *scratch) { return (long long *)scratch; }
+static inline unsigned int *ccnt(const void *scratch, int64_t ntiles)
+{
+    return (unsigned int *)((char *)scratch + (size_t)(ntiles + 1) * 8);
+}
+static inline RowTable *ctab(const void *scratch, int64_t ntiles)
+{
+    size_t off = (size_t)(ntiles + 1) * 8 + (size_t)ntiles * 4;
+    off = (off + 15) & ~(size_t)15;
+    return (RowTable *)((char *)scratch + off);
+}
+
+int pxf_vignette_flags(const double *l, const double *m, const double *n, int64_t num,
+                       uint8_t *flags, pxf_stream_t stream)
+{
+    if (num < 0 || !l || !m || !n || !flags) { set_error("pxf_vignette_flags: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    if (num == 0) return PXF_OK;
+    k_vignette_flags<<<grid_for(num, PXF_BLOCK * 2, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        l, m, n, num, flags);
+    count_launch();
+    return check_launch("k_vignette_flags");
+}
+
+int pxf_compact_count(const uint8_t *flags, int64_t num, void *scratch, int64_t *count_host,
+                      pxf_stream_t stream)
+{
+    if (num < 0 || !flags || !scratch || !count_host) { set_error("pxf_compact_count: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (num == 0) { *count_host = 0; return PXF_OK; }
+    int64_t ntiles = (num + CTILE - 1) / CTILE;
+    k_compact_count<<<(unsigned)ntiles, PXF_BLOCK, 0, s>>>(flags, num, ccnt(scratch, ntiles));
+    k_compact_scan<<<1, 1024, 0, s>>>(ccnt(scratch, ntiles), ntiles, coff(scratch));
+    count_launch(2);
+    if ((rc = check_launch("k_compact_count"))) return rc;
+    long long total = 0;
+    PXF_CUDA(cudaMemcpyAsync(&total, coff(scratch) + ntiles, 8, cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    *count_host = total;
+    return PXF_OK;
+}
+
+int pxf_compact_scatter(const double *const *rows_in, double *const *rows_out, int32_t nrows,
+                        const uint8_t *flags, int64_t num, const void *scratch, pxf_stream_t stream)
+{
+    if (num < 0 || !rows_in || !rows_out || nrows < 1 || nrows > 16 || !flags || !scratch) {
+        set_error("pxf_compact_scatter: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    int rc = need_device();
+    if (rc) return rc;
+    if (num == 0) return PXF_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int64_t ntiles = (num + CTILE - 1) / CTILE;
+    RowTable h;
+    for (int r = 0; r < nrows; r++) { h.in[r] = rows_in[r]; h.out[r] = rows_out[r]; }
+    RowTable *d = ctab(scratch, ntiles);
+    PXF_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    k_compact_scatter<0><<<(unsigned)ntiles, PXF_BLOCK, 0, s>>>(d->in, d->out, nrows, flags, num, coff(scratch), nullptr);
+    count_launch();
+    return check_launch("k_compact_scatter");
+}
+
+int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, int64_t *idx_out,
+                        pxf_stream_t stream)
+{
+    if (num < 0 || !flags || !scratch || !idx_out) { set_error("pxf_compact_indices: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    if (num == 0) return PXF_OK;
+    int64_t ntiles = (num + CTILE - 1) / CTILE;
+    k_compact_scatter<1><<<(unsigned)ntiles, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        nullptr, nullptr, 0, flags, num, coff(scratch), reinterpret_cast<long long *>(idx_out));
+    count_launch();
+    return check_launch("k_compact_indices");
+}
+
+int pxf_gather_rows(const double *const *rows_in, double *const *rows_out, int32_t nrows,
+                    const int64_t *idx, int64_t count, void *table_scratch /* >= 256 B device */,
+                    pxf_stream_t stream)
+{
+    if (count < 0 || !rows_in || !rows_out || nrows < 1 || nrows > 16 || !idx || !table_scratch) {
+        set_error("pxf_gather_rows: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    int rc = need_device();
+    if (rc) return rc;
+    if (count == 0) return PXF_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    RowTable h;
+    for (int r = 0; r < nrows; r++) { h.in[r] = rows_in[r]; h.out[r] = rows_out[r]; }
+    RowTable *d = static_cast<RowTable *>(table_scratch);
+    PXF_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    k_gather_rows<<<grid_for(count, PXF_BLOCK, 8), PXF_BLOCK, 0, s>>>(d->in, d->out, nrows,
+                                                                     reinterpret_cast<const long long *>(idx), count);
+    count_launch();
+    return check_launch("k_gather_rows");
+}
+
+}  // extern "C"

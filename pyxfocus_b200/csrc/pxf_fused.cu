@@ -1,0 +1,307 @@
+// Fused per-ray program: one kernel loads a ray once, runs a whole op list in registers and
+// stores once -- no HBM round trip per optical element.  The per-op arithmetic is the same
+// device code as the per-routine kernels (pxf_ray.cuh), so the result is bit-identical to
+// issuing the routines one by one.  Every ray runs the same program, so the opcode switch is
+// warp-uniform; only Newton trip counts and vignetting diverge.
+#include "pxf_internal.h"
+#include "pxf_params.h"
+
+namespace pxf {
+
+#define FOP_PARAM_DOUBLES 28   // sizeof(WSP)/8 is the largest folded parameter block
+
+struct FusedOp {
+    int code;
+    int row;                 // VIGNETTE_BOX / ABS: bundle row index
+    double q[FOP_PARAM_DOUBLES];
+};
+struct FusedProgram {
+    int nops;
+    unsigned load_mask, store_mask;
+    int has_vignette;
+    FusedOp ops[PXF_MAX_OPS];
+};
+
+static_assert(sizeof(WSP) <= FOP_PARAM_DOUBLES * 8, "WSP does not fit a fused op slot");
+static_assert(sizeof(ConicP) <= FOP_PARAM_DOUBLES * 8, "ConicP does not fit");
+static_assert(sizeof(WolterSineP) <= FOP_PARAM_DOUBLES * 8, "WolterSineP does not fit");
+
+PXF_DEV double ray_row(const Ray &r, int row)
+{
+    switch (row) {
+        case 0: return r.opd; case 1: return r.x; case 2: return r.y; case 3: return r.z;
+        case 4: return r.l; case 5: return r.m; case 6: return r.n; case 7: return r.ux;
+        case 8: return r.uy; default: return r.uz;
+    }
+}
+
+// returns false when the ray is vignetted at this op
+PXF_DEV bool run_op(Ray &r, const FusedOp &op)
+{
+    switch (op.code) {
+        case PXF_OP_TRANSFORM: op_transform(r, *reinterpret_cast<const TransformP *>(op.q)); break;
+        case PXF_OP_ITRANSFORM: op_itransform(r, *reinterpret_cast<const TransformP *>(op.q)); break;
+        case PXF_OP_REFLECT: op_reflect(r); break;
+        case PXF_OP_REFRACT: op_refract(r, *reinterpret_cast<const RefractP *>(op.q)); break;
+        case PXF_OP_RADGRAT: {
+            const RadgratP &p = *reinterpret_cast<const RadgratP *>(op.q);
+            op_radgrat(r, p, p.wave, false);
+            break;
+        }
+        case PXF_OP_FLAT: op_flat(r, false, 0.); break;
+        case PXF_OP_FLATOPD: op_flat(r, true, op.q[0]); break;
+        case PXF_OP_CONIC:
+        case PXF_OP_CONICOPD: op_conic(r, *reinterpret_cast<const ConicP *>(op.q)); break;
+        case PXF_OP_WOLTERPRIMARY:
+        case PXF_OP_WOLTERPRIMARYOPD: op_wolterprimary(r, *reinterpret_cast<const WolterP *>(op.q)); break;
+        case PXF_OP_WOLTERSECONDARY: op_woltersecondary(r, *reinterpret_cast<const WolterP *>(op.q)); break;
+        case PXF_OP_WOLTERSINE: op_woltersine(r, *reinterpret_cast<const WolterSineP *>(op.q)); break;
+        case PXF_OP_WSPRIMARY: op_wsprimary(r, *reinterpret_cast<const WSP *>(op.q)); break;
+        case PXF_OP_WSSECONDARY: op_wssecondary(r, *reinterpret_cast<const WSP *>(op.q)); break;
+        case PXF_OP_SPOCONE: op_spocone(r, *reinterpret_cast<const SpoP *>(op.q)); break;
+        case PXF_OP_VIGNETTE_MAG: {
+            double mag = sq(r.l) + sq(r.m) + sq(r.n);
+            return mag > .1;
+        }
+        case PXF_OP_VIGNETTE_BOX: {
+            double v = ray_row(r, op.row);
+            return (v > op.q[0]) && (v < op.q[1]);
+        }
+        case PXF_OP_VIGNETTE_ABS: {
+            double v = ray_row(r, op.row);
+            return fabs(v) < op.q[0];
+        }
+        case PXF_OP_KICK: {
+            r.l = r.l + op.q[0];
+            r.m = r.m + op.q[1];
+            r.n = op.q[2] * sqrt(1. - sq(r.l) - sq(r.m));
+            break;
+        }
+        default: break;
+    }
+    return true;
+}
+
+PXF_DEV bool run_program(Ray &r, const FusedProgram &prog)
+{
+    for (int k = 0; k < prog.nops; k++)
+        if (!run_op(r, prog.ops[k])) return false;
+    return true;
+}
+
+struct RowPtrs { double *p[10]; };
+
+PXF_DEV void fload1(Ray &r, const RowPtrs &P, unsigned M, int64_t i)
+{
+    r.opd = (M & R_OPD) ? P.p[0][i] : 0.;
+    r.x = (M & R_X) ? P.p[1][i] : 0.;  r.y = (M & R_Y) ? P.p[2][i] : 0.;  r.z = (M & R_Z) ? P.p[3][i] : 0.;
+    r.l = (M & R_L) ? P.p[4][i] : 0.;  r.m = (M & R_M) ? P.p[5][i] : 0.;  r.n = (M & R_N) ? P.p[6][i] : 0.;
+    r.ux = (M & R_UX) ? P.p[7][i] : 0.; r.uy = (M & R_UY) ? P.p[8][i] : 0.; r.uz = (M & R_UZ) ? P.p[9][i] : 0.;
+}
+PXF_DEV void fstore1(const Ray &r, const RowPtrs &P, unsigned M, int64_t i)
+{
+    if (M & R_OPD) P.p[0][i] = r.opd;
+    if (M & R_X) P.p[1][i] = r.x;   if (M & R_Y) P.p[2][i] = r.y;   if (M & R_Z) P.p[3][i] = r.z;
+    if (M & R_L) P.p[4][i] = r.l;   if (M & R_M) P.p[5][i] = r.m;   if (M & R_N) P.p[6][i] = r.n;
+    if (M & R_UX) P.p[7][i] = r.ux; if (M & R_UY) P.p[8][i] = r.uy; if (M & R_UZ) P.p[9][i] = r.uz;
+}
+#define FLD2(bit, k, f)                                                               \
+    if (M & bit) { double2 v = *reinterpret_cast<const double2 *>(P.p[k] + i); a.f = v.x; b.f = v.y; } \
+    else { a.f = 0.; b.f = 0.; }
+#define FST2(bit, k, f) if (M & bit) *reinterpret_cast<double2 *>(P.p[k] + i) = make_double2(a.f, b.f);
+PXF_DEV void fload2(Ray &a, Ray &b, const RowPtrs &P, unsigned M, int64_t i)
+{
+    FLD2(R_OPD, 0, opd) FLD2(R_X, 1, x) FLD2(R_Y, 2, y) FLD2(R_Z, 3, z) FLD2(R_L, 4, l)
+    FLD2(R_M, 5, m) FLD2(R_N, 6, n) FLD2(R_UX, 7, ux) FLD2(R_UY, 8, uy) FLD2(R_UZ, 9, uz)
+}
+PXF_DEV void fstore2(const Ray &a, const Ray &b, const RowPtrs &P, unsigned M, int64_t i)
+{
+    FST2(R_OPD, 0, opd) FST2(R_X, 1, x) FST2(R_Y, 2, y) FST2(R_Z, 3, z) FST2(R_L, 4, l)
+    FST2(R_M, 5, m) FST2(R_N, 6, n) FST2(R_UX, 7, ux) FST2(R_UY, 8, uy) FST2(R_UZ, 9, uz)
+}
+
+template <bool VEC2>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_program(const RowPtrs P, const int64_t num, uint8_t *__restrict__ alive,
+          const __grid_constant__ FusedProgram prog)
+{
+    const unsigned LM = prog.load_mask, SM = prog.store_mask;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    if (VEC2) {
+        const int64_t npair = num >> 1;
+        for (int64_t q = tid; q < npair; q += nthr) {
+            const int64_t i = q << 1;
+            Ray a, b;
+            fload2(a, b, P, LM, i);
+            const bool ka = run_program(a, prog);
+            const bool kb = run_program(b, prog);
+            fstore2(a, b, P, SM, i);
+            if (alive) { alive[i] = ka ? 1 : 0; alive[i + 1] = kb ? 1 : 0; }
+        }
+        if ((num & 1) && tid == 0) {
+            const int64_t i = num - 1;
+            Ray a;
+            fload1(a, P, LM, i);
+            const bool ka = run_program(a, prog);
+            fstore1(a, P, SM, i);
+            if (alive) alive[i] = ka ? 1 : 0;
+        }
+    } else {
+        for (int64_t i = tid; i < num; i += nthr) {
+            Ray a;
+            fload1(a, P, LM, i);
+            const bool ka = run_program(a, prog);
+            fstore1(a, P, SM, i);
+            if (alive) alive[i] = ka ? 1 : 0;
+        }
+    }
+}
+
+// rows read (use) / possibly written (st) / unconditionally overwritten (kill) by each op
+static void op_masks(int code, int row, unsigned &use, unsigned &st, unsigned &kill)
+{
+    switch (code) {
+        case PXF_OP_TRANSFORM: case PXF_OP_ITRANSFORM: use = R_NINE; st = R_NINE; kill = R_NINE; break;
+        case PXF_OP_REFLECT: use = R_DIR | R_NRM; st = R_DIR; kill = R_DIR; break;
+        case PXF_OP_REFRACT: use = R_DIR | R_NRM; st = R_DIR | R_NRM; kill = 0; break;
+        case PXF_OP_RADGRAT: use = R_X | R_Y | R_DIR; st = R_DIR; kill = R_DIR; break;
+        case PXF_OP_FLAT: use = R_POS | R_DIR; st = R_POS | R_NRM; kill = R_POS | R_NRM; break;
+        case PXF_OP_FLATOPD: use = R_POS | R_DIR | R_OPD; st = R_POS | R_NRM | R_OPD; kill = R_POS | R_NRM; break;
+        case PXF_OP_CONIC: case PXF_OP_SPOCONE: use = R_NINE; st = R_NINE; kill = 0; break;
+        case PXF_OP_CONICOPD: use = R_ALL; st = R_ALL; kill = 0; break;
+        case PXF_OP_WOLTERPRIMARY: case PXF_OP_WOLTERSECONDARY: case PXF_OP_WOLTERSINE:
+            use = R_POS | R_DIR; st = R_POS | R_NRM; kill = R_POS | R_NRM; break;
+        case PXF_OP_WOLTERPRIMARYOPD:
+            use = R_POS | R_DIR | R_OPD; st = R_POS | R_NRM | R_OPD; kill = R_POS | R_NRM; break;
+        case PXF_OP_WSPRIMARY: case PXF_OP_WSSECONDARY: use = R_NINE; st = R_POS | R_NRM; kill = R_POS; break;
+        case PXF_OP_VIGNETTE_MAG: use = R_DIR; st = 0; kill = 0; break;
+        case PXF_OP_VIGNETTE_BOX: case PXF_OP_VIGNETTE_ABS: use = 1u << row; st = 0; kill = 0; break;
+        case PXF_OP_KICK: use = R_L | R_M; st = R_DIR; kill = R_N; break;
+        default: use = 0; st = 0; kill = 0; break;
+    }
+}
+
+int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
+{
+    if (!ops || nops < 1 || nops > PXF_MAX_OPS) { set_error("program: need 1..%d ops", PXF_MAX_OPS); return PXF_ERR_INVALID; }
+    memset(&fp, 0, sizeof(fp));
+    fp.nops = nops;
+    unsigned store = 0;
+    for (int k = 0; k < nops; k++) {
+        const pxf_op &o = ops[k];
+        FusedOp &f = fp.ops[k];
+        f.code = o.code;
+        f.row = 0;
+        const double *p = o.p;
+        switch (o.code) {
+            case PXF_OP_TRANSFORM: { TransformP t = make_transform(p[0], p[1], p[2], p[3], p[4], p[5]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_ITRANSFORM: { TransformP t = make_itransform(p[0], p[1], p[2], p[3], p[4], p[5]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_REFLECT: case PXF_OP_FLAT: case PXF_OP_VIGNETTE_MAG: break;
+            case PXF_OP_REFRACT: { RefractP t; t.ratio = p[0] / p[1]; memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_RADGRAT: { RadgratP t = make_radgrat(p[0], p[1], p[2]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_FLATOPD: f.q[0] = p[0]; break;
+            case PXF_OP_CONIC: { ConicP t = make_conic(p[0], p[1], false, 0.); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_CONICOPD: { ConicP t = make_conic(p[0], p[1], true, p[2]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_WOLTERPRIMARY: { WolterP t = make_wolter(p[0], p[1], p[2], false, 0.); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_WOLTERPRIMARYOPD: { WolterP t = make_wolter(p[0], p[1], p[2], true, p[3]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_WOLTERSECONDARY: { WolterP t = make_wolter(p[0], p[1], p[2], false, 0.); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_WOLTERSINE: { WolterSineP t = make_woltersine(p[0], p[1], p[2], p[3]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_WSPRIMARY: case PXF_OP_WSSECONDARY: { WSP t = make_ws(p[0], p[1], p[2]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_SPOCONE: { SpoP t = make_spo(p[0], p[1]); memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_VIGNETTE_BOX:
+                f.row = (int)p[0];
+                if (f.row < 0 || f.row > 9) { set_error("program: bad row in VIGNETTE_BOX"); return PXF_ERR_INVALID; }
+                f.q[0] = p[1]; f.q[1] = p[2];
+                break;
+            case PXF_OP_VIGNETTE_ABS:
+                f.row = (int)p[0];
+                if (f.row < 0 || f.row > 9) { set_error("program: bad row in VIGNETTE_ABS"); return PXF_ERR_INVALID; }
+                f.q[0] = p[1];
+                break;
+            case PXF_OP_KICK: f.q[0] = p[0]; f.q[1] = p[1]; f.q[2] = p[2]; break;
+            default: set_error("program: unknown opcode %d", o.code); return PXF_ERR_INVALID;
+        }
+        if (o.code == PXF_OP_VIGNETTE_MAG || o.code == PXF_OP_VIGNETTE_BOX || o.code == PXF_OP_VIGNETTE_ABS)
+            fp.has_vignette = 1;
+        unsigned use, st, kill;
+        op_masks(o.code, f.row, use, st, kill);
+        store |= st;
+    }
+    // Backward liveness: a row is read from HBM only if some op consumes its incoming value
+    // before an op overwrites it unconditionally (e.g. the normals entering a transform that is
+    // followed by a surface are dead: never loaded, never rotated).  Every row any op may write
+    // is live at the end (it is stored).
+    unsigned live = store;
+    for (int k = nops - 1; k >= 0; k--) {
+        FusedOp &f = fp.ops[k];
+        unsigned use, st, kill;
+        op_masks(f.code, f.row, use, st, kill);
+        if (f.code == PXF_OP_TRANSFORM || f.code == PXF_OP_ITRANSFORM) {
+            // position / direction / normal triplets transform independently
+            unsigned groups = 0, in = live & ~R_NINE;
+            if (live & R_POS) { groups |= 1; in |= R_POS; }
+            if (live & R_DIR) { groups |= 2; in |= R_DIR; }
+            if (live & R_NRM) { groups |= 4; in |= R_NRM; }
+            reinterpret_cast<TransformP *>(f.q)->groups = (int)groups;
+            live = in;
+        } else {
+            const bool side_effect = (st == 0);   // vignette predicates
+            unsigned in = live & ~kill;
+            if ((st & live) || side_effect) in |= use;
+            live = in;
+        }
+    }
+    fp.load_mask = live;
+    fp.store_mask = store;
+    return PXF_OK;
+}
+
+int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s)
+{
+    if (num < 0 || !rays) { set_error("program: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    if (fp.has_vignette && !alive) { set_error("program with a VIGNETTE op needs an alive array"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    RowPtrs P;
+    bool aligned = true;
+    const unsigned used = fp.load_mask | fp.store_mask;
+    for (int k = 0; k < 10; k++) {
+        P.p[k] = rays[k];
+        if (used & (1u << k)) {
+            if (!rays[k]) { set_error("program: null row pointer (row %d)", k); return PXF_ERR_INVALID; }
+            if (reinterpret_cast<uintptr_t>(rays[k]) & 15) aligned = false;
+        }
+    }
+    static int ctas[2] = {0, 0};
+    const int v = aligned ? 1 : 0;
+    if (ctas[v] == 0) {
+        int nb = 0;
+        cudaError_t e = aligned ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program<true>, PXF_BLOCK, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program<false>, PXF_BLOCK, 0);
+        if (e != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
+        ctas[v] = nb;
+    }
+    if (aligned) {
+        int grid = grid_for((num + 1) >> 1, PXF_BLOCK, ctas[v]);
+        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, num, alive, fp);
+    } else {
+        int grid = grid_for(num, PXF_BLOCK, ctas[v]);
+        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, num, alive, fp);
+    }
+    count_launch();
+    return check_launch("k_program");
+}
+
+}  // namespace pxf
+
+using namespace pxf;
+
+extern "C" int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
+                                 uint8_t *alive, pxf_stream_t stream)
+{
+    FusedProgram fp;
+    int rc = build_program(fp, ops, nops);
+    if (rc) return rc;
+    return launch_program(rays, num, fp, alive, reinterpret_cast<cudaStream_t>(stream));
+}

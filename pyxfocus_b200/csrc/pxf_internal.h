@@ -1,0 +1,47 @@
+// Internal helpers shared by the libpxf translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/pxf.h"
+
+#define PXF_NEWTON_CAP 1000
+#define PXF_BLOCK 256
+
+namespace pxf {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+// Persistent grid: SM count x resident CTAs, capped by the work available.
+int grid_for(int64_t work_items, int per_block, int ctas_per_sm);
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return PXF_ERR_CUDA;
+    }
+    return PXF_OK;
+}
+
+#define PXF_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) {                                             \
+            pxf::set_error("%s: %s", #call, cudaGetErrorString(e__));         \
+            return PXF_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+// Stream-ordered scratch allocation for the convenience entry points.
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    int alloc(size_t bytes, cudaStream_t stream);
+    ~Scratch();
+};
+
+}  // namespace pxf

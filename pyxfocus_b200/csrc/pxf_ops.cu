@@ -1,0 +1,565 @@
+// Per-routine kernels: one launch per f2py routine, one pass over the rows it touches.
+// HBM-bound streaming kernels (SURVEY 8a "B/ray"): rows are read and written with double2
+// accesses (two rays per thread) when every row is 16-byte aligned, by a persistent grid
+// of SM-count x resident-CTA blocks striding over ray pairs.
+#include <stdarg.h>
+#include <atomic>
+#include "pxf_internal.h"
+#include "pxf_params.h"
+
+namespace pxf {
+
+// ------------------------------------------------------------------ library state
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static int g_sms = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count()
+{
+    if (g_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            return 0;
+        }
+        g_sms = n;
+    }
+    return g_sms;
+}
+int grid_for(int64_t work_items, int per_block, int ctas_per_sm)
+{
+    int64_t need = (work_items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (cap <= 0) cap = 1;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+int Scratch::alloc(size_t bytes, cudaStream_t stream)
+{
+    s = stream;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, stream);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PXF_ERR_NOMEM : PXF_ERR_CUDA;
+    }
+    return PXF_OK;
+}
+Scratch::~Scratch()
+{
+    if (p) cudaFreeAsync(p, s);
+}
+
+// ------------------------------------------------------------------ row access
+struct RowPtrs { double *p[10]; };
+
+template <unsigned M>
+PXF_DEV void load1(Ray &r, const RowPtrs &P, int64_t i)
+{
+    if (M & R_OPD) r.opd = P.p[0][i];
+    if (M & R_X) r.x = P.p[1][i];
+    if (M & R_Y) r.y = P.p[2][i];
+    if (M & R_Z) r.z = P.p[3][i];
+    if (M & R_L) r.l = P.p[4][i];
+    if (M & R_M) r.m = P.p[5][i];
+    if (M & R_N) r.n = P.p[6][i];
+    if (M & R_UX) r.ux = P.p[7][i];
+    if (M & R_UY) r.uy = P.p[8][i];
+    if (M & R_UZ) r.uz = P.p[9][i];
+}
+template <unsigned M>
+PXF_DEV void store1(const Ray &r, const RowPtrs &P, int64_t i)
+{
+    if (M & R_OPD) P.p[0][i] = r.opd;
+    if (M & R_X) P.p[1][i] = r.x;
+    if (M & R_Y) P.p[2][i] = r.y;
+    if (M & R_Z) P.p[3][i] = r.z;
+    if (M & R_L) P.p[4][i] = r.l;
+    if (M & R_M) P.p[5][i] = r.m;
+    if (M & R_N) P.p[6][i] = r.n;
+    if (M & R_UX) P.p[7][i] = r.ux;
+    if (M & R_UY) P.p[8][i] = r.uy;
+    if (M & R_UZ) P.p[9][i] = r.uz;
+}
+#define PXF_LD2(bit, k, f)                                                          \
+    if (M & bit) {                                                                  \
+        double2 v = *reinterpret_cast<const double2 *>(P.p[k] + i);                 \
+        a.f = v.x; b.f = v.y;                                                       \
+    }
+#define PXF_ST2(bit, k, f)                                                          \
+    if (M & bit) *reinterpret_cast<double2 *>(P.p[k] + i) = make_double2(a.f, b.f);
+template <unsigned M>
+PXF_DEV void load2(Ray &a, Ray &b, const RowPtrs &P, int64_t i)
+{
+    PXF_LD2(R_OPD, 0, opd) PXF_LD2(R_X, 1, x) PXF_LD2(R_Y, 2, y) PXF_LD2(R_Z, 3, z) PXF_LD2(R_L, 4, l)
+    PXF_LD2(R_M, 5, m) PXF_LD2(R_N, 6, n) PXF_LD2(R_UX, 7, ux) PXF_LD2(R_UY, 8, uy) PXF_LD2(R_UZ, 9, uz)
+}
+template <unsigned M>
+PXF_DEV void store2(const Ray &a, const Ray &b, const RowPtrs &P, int64_t i)
+{
+    PXF_ST2(R_OPD, 0, opd) PXF_ST2(R_X, 1, x) PXF_ST2(R_Y, 2, y) PXF_ST2(R_Z, 3, z) PXF_ST2(R_L, 4, l)
+    PXF_ST2(R_M, 5, m) PXF_ST2(R_N, 6, n) PXF_ST2(R_UX, 7, ux) PXF_ST2(R_UY, 8, uy) PXF_ST2(R_UZ, 9, uz)
+}
+
+// ------------------------------------------------------------------ op functors
+// LOAD: rows the loop body reads; STORE: rows it may write.  Rows that are written only
+// conditionally are also in LOAD so that the unconditional row store is a no-op for them.
+struct NoParams { int unused; };
+
+struct OpTransform {
+    using Params = TransformP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_transform(r, p); }
+};
+struct OpITransform {
+    using Params = TransformP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_itransform(r, p); }
+};
+struct OpReflect {
+    using Params = NoParams;
+    static constexpr unsigned LOAD = R_DIR | R_NRM, STORE = R_DIR;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &, const double *, double, double) { op_reflect(r); }
+};
+struct OpRefract {
+    using Params = RefractP;
+    static constexpr unsigned LOAD = R_DIR | R_NRM, STORE = R_DIR | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_refract(r, p); }
+};
+struct OpRadgrat {
+    using Params = RadgratP;
+    static constexpr unsigned LOAD = R_X | R_Y | R_DIR, STORE = R_DIR;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        op_radgrat(r, p, p.wave, false);
+    }
+};
+struct OpRadgratW {
+    using Params = RadgratP;
+    static constexpr unsigned LOAD = R_X | R_Y | R_DIR, STORE = R_DIR;
+    static constexpr int AUX = 1, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double wave, double)
+    {
+        op_radgrat(r, p, wave, true);
+    }
+};
+struct GratP { double d; };
+struct OpGrat {
+    using Params = GratP;
+    static constexpr unsigned LOAD = R_DIR, STORE = R_DIR;
+    static constexpr int AUX = 2, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double order, double wave)
+    {
+        op_grat(r, p.d, order, wave);
+    }
+};
+struct FlatP { double nr; };
+struct OpFlat {
+    using Params = FlatP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &, const double *, double, double) { op_flat(r, false, 0.); }
+};
+struct OpFlatOpd {
+    using Params = FlatP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | R_OPD, STORE = R_POS | R_NRM | R_OPD;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_flat(r, true, p.nr); }
+};
+struct OpConic {
+    using Params = ConicP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_conic(r, p); }
+};
+struct OpConicOpd {
+    using Params = ConicP;
+    static constexpr unsigned LOAD = R_ALL, STORE = R_ALL;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_conic(r, p); }
+};
+struct OpWolterPrimary {
+    using Params = WolterP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wolterprimary(r, p); }
+};
+struct OpWolterPrimaryOpd {
+    using Params = WolterP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | R_OPD, STORE = R_POS | R_NRM | R_OPD;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wolterprimary(r, p); }
+};
+struct OpWolterSecondary {
+    using Params = WolterP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_woltersecondary(r, p); }
+};
+struct OpWolterSine {
+    using Params = WolterSineP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_woltersine(r, p); }
+};
+struct OpWsPrimary {
+    using Params = WSP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wsprimary(r, p); }
+};
+struct OpWsSecondary {
+    using Params = WSP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wssecondary(r, p); }
+};
+struct OpSpoCone {
+    using Params = SpoP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_spocone(r, p); }
+};
+template <int NMAX, bool OPD>
+struct OpZern {
+    using Params = ZernP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | (OPD ? R_OPD : 0u);
+    static constexpr unsigned STORE = R_POS | R_NRM | (OPD ? R_OPD : 0u);
+    static constexpr int AUX = 0, SMEM = PXF_ZERN_SMEM_DOUBLES;
+    PXF_DEV static const double *table(const Params &p) { return reinterpret_cast<const double *>(p.e); }
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *smem, double, double)
+    {
+        op_tracezern<NMAX>(r, p.rad, p.nr, p.tol, p.nmax, OPD ? 1 : 0, smem);
+    }
+};
+
+// ------------------------------------------------------------------ the kernel
+template <class Op, bool MASKED, bool VEC2>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_op(const RowPtrs P, const int64_t num, const uint8_t *__restrict__ mask,
+     const double *__restrict__ aux0, const double *__restrict__ aux1,
+     const __grid_constant__ typename Op::Params prm)
+{
+    constexpr unsigned LD = MASKED ? (Op::LOAD | Op::STORE) : Op::LOAD;
+    constexpr unsigned ST = Op::STORE;
+    __shared__ double smem[Op::SMEM > 0 ? Op::SMEM : 1];
+    if constexpr (Op::SMEM > 0) {
+        // stage the coefficient table (Zernike) once per CTA
+        const double *src = Op::table(prm);
+        for (int t = threadIdx.x; t < Op::SMEM; t += blockDim.x) smem[t] = src[t];
+        __syncthreads();
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    if (VEC2) {
+        const int64_t npair = num >> 1;
+        for (int64_t q = tid; q < npair; q += nthr) {
+            const int64_t i = q << 1;
+            bool do0 = true, do1 = true;
+            if (MASKED) {
+                do0 = mask[i] != 0; do1 = mask[i + 1] != 0;
+                if (!do0 && !do1) continue;
+            }
+            Ray a, b;
+            load2<LD>(a, b, P, i);
+            double w0a = 0., w0b = 0., w1a = 0., w1b = 0.;
+            if (Op::AUX >= 1) { w0a = aux0[i]; w0b = aux0[i + 1]; }
+            if (Op::AUX >= 2) { w1a = aux1[i]; w1b = aux1[i + 1]; }
+            if (do0) Op::apply(a, prm, smem, w0a, w1a);
+            if (do1) Op::apply(b, prm, smem, w0b, w1b);
+            store2<ST>(a, b, P, i);
+        }
+        if ((num & 1) && tid == 0) {
+            const int64_t i = num - 1;
+            if (!MASKED || mask[i] != 0) {
+                Ray a;
+                load1<LD>(a, P, i);
+                Op::apply(a, prm, smem, Op::AUX >= 1 ? aux0[i] : 0., Op::AUX >= 2 ? aux1[i] : 0.);
+                store1<ST>(a, P, i);
+            }
+        }
+    } else {
+        for (int64_t i = tid; i < num; i += nthr) {
+            if (MASKED && mask[i] == 0) continue;
+            Ray a;
+            load1<LD>(a, P, i);
+            Op::apply(a, prm, smem, Op::AUX >= 1 ? aux0[i] : 0., Op::AUX >= 2 ? aux1[i] : 0.);
+            store1<ST>(a, P, i);
+        }
+    }
+}
+
+template <class Op, bool MASKED, bool VEC2>
+static int launch3(const RowPtrs &P, int64_t num, const uint8_t *mask, const double *aux0,
+                   const double *aux1, const typename Op::Params &prm, cudaStream_t s)
+{
+    static int ctas = 0;
+    if (ctas == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_op<Op, MASKED, VEC2>, PXF_BLOCK, 0) !=
+                cudaSuccess || nb <= 0) {
+            cudaGetLastError();
+            nb = 4;
+        }
+        ctas = nb;
+    }
+    int64_t items = VEC2 ? ((num + 1) >> 1) : num;
+    int grid = grid_for(items, PXF_BLOCK, ctas);
+    k_op<Op, MASKED, VEC2><<<grid, PXF_BLOCK, 0, s>>>(P, num, mask, aux0, aux1, prm);
+    count_launch();
+    return check_launch("k_op");
+}
+
+template <class Op>
+static int launch_op(RowPtrs P, int64_t num, const uint8_t *mask, const double *aux0, const double *aux1,
+                     const typename Op::Params &prm, pxf_stream_t stream)
+{
+    if (num < 0) { set_error("num < 0"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    if (num == 0) return PXF_OK;
+    const unsigned used = Op::LOAD | Op::STORE;
+    bool aligned = true;
+    for (int k = 0; k < 10; k++) {
+        if (used & (1u << k)) {
+            if (!P.p[k]) { set_error("null row pointer (row %d)", k); return PXF_ERR_INVALID; }
+            if (reinterpret_cast<uintptr_t>(P.p[k]) & 15) aligned = false;
+        } else {
+            P.p[k] = nullptr;
+        }
+    }
+    if (Op::AUX >= 1 && !aux0) { set_error("null per-ray argument"); return PXF_ERR_INVALID; }
+    if (Op::AUX >= 2 && !aux1) { set_error("null per-ray argument"); return PXF_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (mask) {
+        if (aligned) return launch3<Op, true, true>(P, num, mask, aux0, aux1, prm, s);
+        return launch3<Op, true, false>(P, num, mask, aux0, aux1, prm, s);
+    }
+    if (aligned) return launch3<Op, false, true>(P, num, mask, aux0, aux1, prm, s);
+    return launch3<Op, false, false>(P, num, mask, aux0, aux1, prm, s);
+}
+
+static RowPtrs rows9(double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, double *opd = nullptr)
+{
+    RowPtrs P;
+    P.p[0] = opd; P.p[1] = x; P.p[2] = y; P.p[3] = z; P.p[4] = l; P.p[5] = m; P.p[6] = n;
+    P.p[7] = ux; P.p[8] = uy; P.p[9] = uz;
+    return P;
+}
+
+template <bool OPD>
+static int launch_zern(RowPtrs P, int64_t num, const uint8_t *mask, const ZernP &z, pxf_stream_t stream)
+{
+    if (z.nmax <= 7) return launch_op<OpZern<7, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+    if (z.nmax <= 11) return launch_op<OpZern<11, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+    return launch_op<OpZern<15, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+}
+
+}  // namespace pxf
+
+using namespace pxf;
+
+// =================================================================== C ABI
+extern "C" {
+
+int pxf_version(void) { return 100; }
+const char *pxf_last_error(void) { return g_err; }
+int64_t pxf_launch_count(void) { return g_launches.load(); }
+int pxf_newton_cap(void) { return PXF_NEWTON_CAP; }
+
+int pxf_transform(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num,
+                  double tx, double ty, double tz, double rx, double ry, double rz,
+                  const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpTransform>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_transform(tx, ty, tz, rx, ry, rz), stream);
+}
+
+int pxf_itransform(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num,
+                   double tx, double ty, double tz, double rx, double ry, double rz,
+                   const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpITransform>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                   make_itransform(tx, ty, tz, rx, ry, rz), stream);
+}
+
+int pxf_reflect(double *l, double *m, double *n, double *ux, double *uy, double *uz, int64_t num,
+                const uint8_t *mask, pxf_stream_t stream)
+{
+    NoParams np{0};
+    return launch_op<OpReflect>(rows9(nullptr, nullptr, nullptr, l, m, n, ux, uy, uz), num, mask, nullptr,
+                                nullptr, np, stream);
+}
+
+int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double *uz, int64_t num,
+                double n1, double n2, const uint8_t *mask, pxf_stream_t stream)
+{
+    RefractP p;
+    p.ratio = n1 / n2;
+    return launch_op<OpRefract>(rows9(nullptr, nullptr, nullptr, l, m, n, ux, uy, uz), num, mask, nullptr,
+                                nullptr, p, stream);
+}
+
+int pxf_radgrat(const double *x, const double *y, double *l, double *m, double *n, double wave,
+                int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpRadgrat>(rows9(const_cast<double *>(x), const_cast<double *>(y), nullptr, l, m, n,
+                                      nullptr, nullptr, nullptr),
+                                num, mask, nullptr, nullptr, make_radgrat(wave, dpermm, order), stream);
+}
+
+int pxf_radgratw(const double *x, const double *y, double *l, double *m, double *n, const double *wave,
+                 int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpRadgratW>(rows9(const_cast<double *>(x), const_cast<double *>(y), nullptr, l, m, n,
+                                       nullptr, nullptr, nullptr),
+                                 num, mask, wave, nullptr, make_radgrat(0., dpermm, order), stream);
+}
+
+int pxf_grat(const double *x, const double *y, double *l, double *m, double *n, int64_t num, double d,
+             const double *order, const double *wave, const uint8_t *mask, pxf_stream_t stream)
+{
+    (void)x; (void)y;
+    GratP p{d};
+    return launch_op<OpGrat>(rows9(nullptr, nullptr, nullptr, l, m, n, nullptr, nullptr, nullptr), num, mask,
+                             order, wave, p, stream);
+}
+
+int pxf_flat(double *x, double *y, double *z, const double *l, const double *m, const double *n,
+             double *ux, double *uy, double *uz, int64_t num, const uint8_t *mask, pxf_stream_t stream)
+{
+    FlatP p{0.};
+    return launch_op<OpFlat>(rows9(x, y, z, const_cast<double *>(l), const_cast<double *>(m),
+                                   const_cast<double *>(n), ux, uy, uz),
+                             num, mask, nullptr, nullptr, p, stream);
+}
+
+int pxf_flatopd(double *x, double *y, double *z, const double *l, const double *m, const double *n,
+                double *ux, double *uy, double *uz, double *opd, int64_t num, double nr,
+                const uint8_t *mask, pxf_stream_t stream)
+{
+    FlatP p{nr};
+    return launch_op<OpFlatOpd>(rows9(x, y, z, const_cast<double *>(l), const_cast<double *>(m),
+                                      const_cast<double *>(n), ux, uy, uz, opd),
+                                num, mask, nullptr, nullptr, p, stream);
+}
+
+int pxf_conic(double *x, double *y, double *z, double *l, double *m, double *n,
+              double *ux, double *uy, double *uz, int64_t num, double R, double K,
+              const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpConic>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                              make_conic(R, K, false, 0.), stream);
+}
+
+int pxf_conicopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double R, double K, double nr,
+                 const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpConicOpd>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, nullptr, nullptr,
+                                 make_conic(R, K, true, nr), stream);
+}
+
+int pxf_wolterprimary(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                      const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWolterPrimary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                      make_wolter(r0, z0, psi, false, 0.), stream);
+}
+
+int pxf_wolterprimaryopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                         double *ux, double *uy, double *uz, int64_t num,
+                         double r0, double z0, double psi, double nr,
+                         const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWolterPrimaryOpd>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, nullptr,
+                                         nullptr, make_wolter(r0, z0, psi, true, nr), stream);
+}
+
+int pxf_woltersecondary(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                        const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWolterSecondary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                        make_wolter(r0, z0, psi, false, 0.), stream);
+}
+
+int pxf_woltersine(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num,
+                   double r0, double z0, double amp, double freq,
+                   const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWolterSine>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                   make_woltersine(r0, z0, amp, freq), stream);
+}
+
+int pxf_wsprimary(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                  const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWsPrimary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_ws(alpha, z0, psi), stream);
+}
+
+int pxf_wssecondary(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                    const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWsSecondary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                    make_ws(alpha, z0, psi), stream);
+}
+
+int pxf_spocone(double *x, double *y, double *z, double *l, double *m, double *n,
+                double *ux, double *uy, double *uz, int64_t num, double R0, double tg,
+                const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpSpoCone>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                make_spo(R0, tg), stream);
+}
+
+int pxf_tracezern(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num,
+                  const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                  double rad, const uint8_t *mask, pxf_stream_t stream)
+{
+    if (!coeff || !rorder || !aorder || arrsize <= 0) { set_error("bad Zernike table"); return PXF_ERR_INVALID; }
+    ZernP zp;
+    if (make_zern(zp, coeff, rorder, aorder, arrsize, rad, false, 0.) < 0) {
+        set_error("invalid Zernike orders (need 0<=n<=15, |m|<=n, n-|m| even, n < radnum(arrsize))");
+        return PXF_ERR_INVALID;
+    }
+    return launch_zern<false>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, zp, stream);
+}
+
+int pxf_tracezernopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num,
+                     const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                     double rad, double nr, const uint8_t *mask, pxf_stream_t stream)
+{
+    if (!coeff || !rorder || !aorder || arrsize <= 0) { set_error("bad Zernike table"); return PXF_ERR_INVALID; }
+    ZernP zp;
+    if (make_zern(zp, coeff, rorder, aorder, arrsize, rad, true, nr) < 0) {
+        set_error("invalid Zernike orders (need 0<=n<=15, |m|<=n, n-|m| even, n < radnum(arrsize))");
+        return PXF_ERR_INVALID;
+    }
+    return launch_zern<true>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, zp, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// Host-side folding of the scalar arguments of each routine into the *P structs the
+// device code consumes.  Every expression keeps the Fortran's evaluation order and is
+// evaluated with the host libm, so the folded constants are the values the reference
+// (and the CPU oracle) compute once per call or once per ray from the same scalars.
+// Compiled with -ffp-contract=off.
+#pragma once
+#include <math.h>
+#include <string.h>
+#include "pxf_ray.cuh"
+
+namespace pxf {
+
+inline double h_sq(double a) { return a * a; }
+inline double h_pow4(double a) { double t = a * a; return t * t; }
+inline double h_pi32() { return (double)acosf(-1.0f); }   // REAL*4 acos(-1.)
+inline double h_tol8() { return (double)1.e-8f; }
+inline double h_tol10() { return (double)1.e-10f; }
+
+// transformationsf.f95:134-163: rotatevector(…,rx,1) etc.
+inline TransformP make_transform(double tx, double ty, double tz, double rx, double ry, double rz)
+{
+    TransformP p;
+    p.tx = tx; p.ty = ty; p.tz = tz;
+    p.cx = cos(rx); p.sx = sin(rx);
+    p.cy = cos(ry); p.sy = sin(ry);
+    p.cz = cos(rz); p.sz = sin(rz);
+    p.groups = 7; p.pad = 0;
+    return p;
+}
+// transformationsf.f95:168-201: tmp = -rz; rotatevector(…,tmp,3) …
+inline TransformP make_itransform(double tx, double ty, double tz, double rx, double ry, double rz)
+{
+    return make_transform(tx, ty, tz, -rx, -ry, -rz);
+}
+
+// woltsurf.f95:18-25
+inline void vanspeybroeck(double r0, double z0, double psi, double &p, double &d, double &e)
+{
+    double alpha = .25 * atan(r0 / z0);
+    double thetah = 2 * (1 + 2 * psi) / (1 + psi) * alpha;
+    double thetap = 2 * psi / (1 + psi) * alpha;
+    p = z0 * tan(4 * alpha) * tan(thetap);
+    d = z0 * tan(4 * alpha) * tan(4 * alpha - thetah);
+    e = cos(4 * alpha) * (1 + tan(4 * alpha) * tan(thetah));
+}
+
+inline WolterP make_wolter(double r0, double z0, double psi, bool opd, double nr)
+{
+    double p, d, e;
+    vanspeybroeck(r0, z0, psi, p, d, e);
+    WolterP w;
+    w.twop = 2 * p;
+    w.p2 = h_sq(p);
+    w.c1 = 4 * h_sq(e) * p * d / (h_sq(e) - 1);
+    w.e2 = h_sq(e);
+    w.two_e2 = 2 * h_sq(e);
+    w.d = d;
+    w.tol = opd ? h_tol10() : h_tol8();
+    w.nr = nr;
+    w.opd = opd ? 1 : 0;
+    return w;
+}
+
+// woltsurf.f95:178-183 (psi fixed: thetah = 3.*alpha, thetap = alpha)
+inline WolterSineP make_woltersine(double r0, double z0, double amp, double freq)
+{
+    double alpha = .25 * atan(r0 / z0);
+    double thetah = 3. * alpha;
+    double thetap = alpha;
+    double p = z0 * tan(4 * alpha) * tan(thetap);
+    double d = z0 * tan(4 * alpha) * tan(4 * alpha - thetah);
+    double e = cos(4 * alpha) * (1 + tan(4 * alpha) * tan(thetah));
+    WolterSineP w;
+    w.twop = 2 * p;            // also 2.*p at :194
+    w.p2 = h_sq(p);
+    w.c1 = 4 * h_sq(e) * p * d / (h_sq(e) - 1);
+    w.amp = amp;
+    w.freq = freq;
+    w.twopi32 = (double)(2 * acosf(-1.0f));
+    w.pi32 = h_pi32();
+    w.tol = h_tol10();
+    return w;
+}
+
+inline WSP make_ws(double alpha, double z0, double psi)
+{
+    WSP p;
+    memset(&p, 0, sizeof(p));
+    p.betas = 4 * alpha;
+    p.ff = z0 / cos(p.betas);
+    p.g = p.ff / psi;
+    p.k = h_sq(tan(p.betas / 2));
+    p.tol = h_tol8();
+    const double betas = p.betas, ff = p.ff, g = p.g, k = p.k;
+    p.invk = 1 / k;
+    p.omk = 1 - k;
+    p.opk = 1 + k;
+    p.ff2 = h_sq(ff);
+    const double sh2 = h_sq(sin(betas / 2));
+    p.A0 = ff * sh2;
+    p.denF = 4 * ff * sh2;
+    p.denFb = 2 * ff * sh2;
+    p.twog = 2 * g;
+    p.gomk = g * (1 - k);
+    p.Cs = h_sq(ff) * h_sq(sin(betas)) / (4 * ff * sh2);
+    p.Ds = g * h_pow4(cos(betas / 2)) * pow(0., 1 - k);
+    p.FbS = h_sq(ff) * sin(betas) * cos(betas) / (2 * ff * sh2) +
+            g * (1 - k) * cos(betas / 2) * sin(betas / 2) * (1 / k);
+    p.ffsinbs = ff * sin(betas);
+    p.a_s = 1 / ff;
+    p.F0s = cos(betas) / p.a_s;
+    p.omcbs = 1 - cos(betas);
+    p.sinbs2 = h_sq(sin(betas));
+    double dadbs = sin(betas) / ff / (1 - cos(betas)) +
+                   (k + 1) * (cos(betas) + 1) * tan(betas / 2) / h_sq(cos(betas / 2)) / 2 / g / k;
+    p.gamA = -ff * sin(betas) - h_sq(ff) * cos(betas) * dadbs;
+    p.tanbs = tan(betas);
+    p.twootan = 2. / tan(betas);
+    p.kp1 = k + 1;
+    return p;
+}
+
+inline SpoP make_spo(double R0, double tg)
+{
+    SpoP p;
+    p.R0 = R0;
+    p.sl = tan(tg);
+    p.sl2 = h_sq(p.sl);
+    p.R02 = h_sq(R0);
+    p.twoslR0 = 2 * p.sl * R0;
+    p.ctg = cos(tg);
+    p.stg = sin(tg);
+    return p;
+}
+
+inline ConicP make_conic(double R, double K, bool opd, double nr)
+{
+    ConicP p;
+    p.R = R; p.K = K;
+    p.Kp1 = K + 1;
+    p.twoR = 2 * R;
+    p.R2 = h_sq(R);
+    p.sgnR = -R / fabs(R);
+    p.nr = nr;
+    p.kis_m1 = (K == -1) ? 1 : 0;
+    p.opd = opd ? 1 : 0;
+    return p;
+}
+
+inline RadgratP make_radgrat(double wave, double dpermm, double order)
+{
+    RadgratP p;
+    p.neg_half_pi32 = -h_pi32() / 2;
+    p.dpermm = dpermm; p.order = order; p.wave = wave;
+    return p;
+}
+
+// Fold (coeff, rorder, aorder) into the (n,|m|) table of pxf_ray.cuh.  Returns the highest
+// radial order, or -1 for an invalid table (n>15, |m|>n, n-|m| odd).
+inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const int32_t *aorder,
+                     int arrsize, double rad, bool opd, double nr)
+{
+    memset(&z, 0, sizeof(z));
+    z.rad = rad; z.nr = nr; z.tol = h_tol10(); z.opd = opd ? 1 : 0;
+    int nmax = 0;
+    for (int i = 0; i < arrsize; i++) {
+        int n = rorder[i], mm = aorder[i], m = mm < 0 ? -mm : mm;
+        if (n < 0 || n > PXF_ZERN_MAXN || m > n || ((n - m) & 1)) return -1;
+        if (n > nmax) nmax = n;
+    }
+    // the reference sizes its tables from znum (specialFunctions.f95:154-161); radial orders
+    // beyond radnum-1 would index out of bounds there.  Mirror the table size.
+    int tznum = 1, radnum = 1;
+    while (tznum < arrsize) { tznum += radnum + 1; radnum += 1; }
+    if (nmax > radnum - 1) return -1;
+    z.nmax = nmax;
+    const double sqrthalf32 = (double)sqrtf(0.5f);
+    int e = 0;
+    for (int ni = 0; ni <= PXF_ZERN_MAXN; ni++) {
+        for (int j = 0; j <= ni / 2; j++) {
+            double n = ni, m = ni - 2 * j;
+            ZernEntry &t = z.e[e + j];
+            if (j >= 2) {
+                t.h3 = -4 * (m + 2) * (m + 1) / (n + m + 2) / (n - m);
+                t.h2 = t.h3 * (n + m + 4) * (n - m - 2) / 4. / (m + 3) + (m + 2);
+                t.h1 = .5 * (m + 4) * (m + 3) - (m + 4) * t.h2 + t.h3 * (n + m + 6) * (n - m - 4) / 8.;
+            }
+        }
+        e += ni / 2 + 1;
+    }
+    for (int i = 0; i < arrsize; i++) {
+        int n = rorder[i], mm = aorder[i], m = mm < 0 ? -mm : mm;
+        int base = 0;
+        for (int q = 0; q < n; q++) base += q / 2 + 1;
+        ZernEntry &t = z.e[base + (n - m) / 2];
+        double norm = sqrt(2 * ((double)n + 1));
+        if (mm < 0) t.as += coeff[i] * norm;
+        else if (mm > 0) t.ac += coeff[i] * norm;
+        else t.ac += coeff[i] * (norm * sqrthalf32);
+    }
+    return nmax;
+}
+
+}  // namespace pxf

@@ -1,0 +1,133 @@
+// Ray sources on the device (sources.py:20-53 pointsource, :56-88 circularbeam, :91-127 annulus,
+// :130-170 subannulus).  Either from caller-supplied uniforms (numpy's legacy MT19937 stream
+// uploaded by the Python layer: "identical ray seeds") or from a counter-based Philox4x32-10
+// generator for bundles too large to draw on the host.  Writes all ten rows once: 80 B/ray.
+#include "pxf_internal.h"
+#include "pxf_ray.cuh"
+
+namespace pxf {
+
+struct RowPtrs { double *p[10]; };
+
+struct u32x4 { unsigned a, b, c, d; };
+
+PXF_DEV u32x4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    u32x4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+// numpy's random_sample: ((a>>5)*2^26 + (b>>6)) / 2^53
+PXF_DEV double u53(unsigned a, unsigned b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+struct SourceP { int kind; double a, b, c, d; double pi; };
+
+PXF_DEV void make_ray(Ray &r, const SourceP &p, double u1, double u2)
+{
+    r.opd = 0.; r.x = 0.; r.y = 0.; r.z = 0.; r.l = 0.; r.m = 0.; r.n = 0.; r.ux = 0.; r.uy = 0.; r.uz = 0.;
+    double s, c;
+    if (p.kind == 0) {            // subannulus(rin=a, rout=b, dphi=c, zhat=d)
+        double rho = sqrt(p.a * p.a + u1 * (p.b * p.b - p.a * p.a));
+        double theta = u2 * p.c - p.c / 2.;
+        sincos(theta, &s, &c);
+        r.x = rho * c; r.y = rho * s; r.n = p.d;
+    } else if (p.kind == 1) {     // circularbeam(rad=a)
+        double rho = sqrt(u1) * p.a;
+        double theta = u2 * 2 * p.pi;          // rand*2*np.pi
+        sincos(theta, &s, &c);
+        r.x = rho * c; r.y = rho * s; r.n = 1.;
+    } else if (p.kind == 2) {     // pointsource(ang=a): b = sin(ang) folded on the host
+        double rho = sqrt(u1) * p.b;
+        double theta = u2 * 2 * p.pi;
+        sincos(theta, &s, &c);
+        r.l = rho * c; r.m = rho * s;
+        r.n = sqrt(1. - r.l * r.l - r.m * r.m);
+    } else {                      // annulus(rin=a, rout=b, zhat=d)
+        double rho = sqrt(p.a * p.a + u1 * (p.b * p.b - p.a * p.a));
+        double theta = u2 * 2 * p.pi;
+        sincos(theta, &s, &c);
+        r.x = rho * c; r.y = rho * s; r.n = p.d;
+    }
+}
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_source(const RowPtrs P, int64_t num, int64_t first, unsigned long long seed,
+         const double *__restrict__ u1, const double *__restrict__ u2, const SourceP p)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < num; i += nthr) {
+        double a, b;
+        if (PHILOX) {
+            unsigned long long g = (unsigned long long)(first + i);
+            u32x4 o = philox4x32_10((unsigned)g, (unsigned)(g >> 32), 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32));
+            a = u53(o.a, o.b);
+            b = u53(o.c, o.d);
+        } else {
+            a = u1[i]; b = u2[i];
+        }
+        Ray r;
+        make_ray(r, p, a, b);
+        if (P.p[0]) P.p[0][i] = r.opd;
+        P.p[1][i] = r.x; P.p[2][i] = r.y; P.p[3][i] = r.z;
+        P.p[4][i] = r.l; P.p[5][i] = r.m; P.p[6][i] = r.n;
+        P.p[7][i] = r.ux; P.p[8][i] = r.uy; P.p[9][i] = r.uz;
+    }
+}
+
+static int source_launch(int kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+                         const double *u1, const double *u2, bool philox, double a, double b, double c, double d,
+                         cudaStream_t s)
+{
+    if (num < 0 || !rays || kind < 0 || kind > 3) { set_error("pxf_source: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    RowPtrs P;
+    for (int k = 0; k < 10; k++) {
+        P.p[k] = rays[k];
+        if (k > 0 && !rays[k]) { set_error("pxf_source: null row"); return PXF_ERR_INVALID; }
+    }
+    if (!philox && (!u1 || !u2)) { set_error("pxf_source: null uniforms"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    SourceP p;
+    p.kind = kind; p.a = a; p.b = b; p.c = c; p.d = d;
+    p.pi = 3.141592653589793;   // np.pi
+    if (kind == 2) p.b = sin(a);
+    int grid = grid_for(num, PXF_BLOCK, 8);
+    if (philox) k_source<true><<<grid, PXF_BLOCK, 0, s>>>(P, num, first, seed, u1, u2, p);
+    else k_source<false><<<grid, PXF_BLOCK, 0, s>>>(P, num, first, seed, u1, u2, p);
+    count_launch();
+    return check_launch("k_source");
+}
+
+}  // namespace pxf
+
+using namespace pxf;
+
+extern "C" {
+
+int pxf_source(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+               double a, double b, double c, double d, pxf_stream_t stream)
+{
+    return source_launch(kind, rays, num, first, seed, nullptr, nullptr, true, a, b, c, d,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, const double *u1,
+                            const double *u2, double a, double b, double c, double d, pxf_stream_t stream)
+{
+    return source_launch(kind, rays, num, 0, 0, u1, u2, false, a, b, c, d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
