@@ -299,14 +299,24 @@ int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, c
                             const double *u2, double a, double b, double c, double d,
                             pxf_stream_t stream);
 
-/* ======================= host-buffer entry points ======================= */
-/* The call an f2py user makes: HOST arrays in, HOST arrays mutated in place.  The ten host rows
- * are streamed through the device in chunks on internal streams (H2D, fused program, D2H
- * overlap); rows_host[k] may be NULL for rows the program neither reads nor writes.  When
- * hpd_host != NULL the unweighted HPD of the final bundle is also returned (the bundle then has to
- * fit on the device).  write_back=0 skips the D2H copy of the rays (analysis-only callers). */
+/* ======================= host-buffer entry point ======================== */
+/* The call an f2py user makes (the reference's extension modules take HOST numpy arrays and
+ * mutate them in place, e.g. transformations.py:29, surfaces.py:224): HOST rows in, HOST rows
+ * mutated in place, a whole op list per call.  The bundle streams through the device in chunks
+ * on three internal streams (H2D of chunk c+1, fused program on chunk c, D2H of chunk c-1
+ * overlap).  Only rows the program reads are uploaded, only rows it may write are downloaded;
+ * rows_host[k] may be NULL for rows it touches neither way.  Pinned (page-locked) host rows
+ * get full PCIe rate; pageable rows work but are staged by the driver.
+ *   write_back       0 skips the D2H of the ray rows (analysis-only callers)
+ *   hpd_host         nullable; receives the unweighted HPD (analyses.py:88-97) of the final
+ *                    bundle -- of the surviving rays when the program has VIGNETTE ops
+ *   alive_host       nullable uint8[num]; receives the survivor flags of VIGNETTE ops
+ *   alive_count_host nullable; number of surviving rays (-1 if it was not computed because
+ *                    neither hpd_host nor alive_host was given)
+ * Synchronous: returns when every host row is final. */
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
-                           int32_t write_back, double *hpd_host, int64_t *alive_count_host);
+                           int32_t write_back, double *hpd_host, uint8_t *alive_host,
+                           int64_t *alive_count_host);
 
 #ifdef __cplusplus
 }

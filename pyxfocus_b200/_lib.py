@@ -1,0 +1,130 @@
+"""ctypes binding of ``libpxf.so`` (the C ABI declared in ``include/pxf.h``).
+
+This is the only place the shared library is opened.  There is no CPU fallback:
+if the library is missing, ``lib()`` raises; if no CUDA device is present the
+entry points return ``PXF_ERR_CUDA`` and ``check()`` raises ``PxfError``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpxf.so")
+
+_c = ctypes
+_dp = _c.c_void_p          # device / host double*  (passed as integer addresses)
+_vp = _c.c_void_p
+_d = _c.c_double
+_i64 = _c.c_int64
+_i32 = _c.c_int32
+_u64 = _c.c_uint64
+_sz = _c.c_size_t
+_st = _c.c_void_p          # pxf_stream_t
+
+
+class PxfError(RuntimeError):
+    """Raised when a libpxf entry point returns a non-zero status (the analogue of
+    ``<f2py module>.error``)."""
+
+
+class pxf_op(ctypes.Structure):
+    _fields_ = [("code", _i32), ("reserved", _i32), ("p", _d * 6)]
+
+
+# name -> (restype, [argtypes]).  Order follows include/pxf.h.
+_NINE = [_dp] * 9
+SIGNATURES = {
+    "pxf_version": (_c.c_int, []),
+    "pxf_last_error": (_c.c_char_p, []),
+    "pxf_launch_count": (_i64, []),
+    "pxf_newton_cap": (_c.c_int, []),
+    # transformationsf
+    "pxf_transform": (_c.c_int, _NINE + [_i64] + [_d] * 6 + [_vp, _st]),
+    "pxf_itransform": (_c.c_int, _NINE + [_i64] + [_d] * 6 + [_vp, _st]),
+    "pxf_reflect": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
+    "pxf_refract": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _vp, _st]),
+    "pxf_radgrat": (_c.c_int, [_dp] * 5 + [_d, _i64, _d, _d, _vp, _st]),
+    "pxf_radgratw": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _vp, _st]),
+    "pxf_grat": (_c.c_int, [_dp] * 5 + [_i64, _d, _dp, _dp, _vp, _st]),
+    # surfacesf
+    "pxf_flat": (_c.c_int, _NINE + [_i64, _vp, _st]),
+    "pxf_flatopd": (_c.c_int, _NINE + [_dp, _i64, _d, _vp, _st]),
+    "pxf_conic": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
+    "pxf_conicopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _d, _vp, _st]),
+    # woltsurf
+    "pxf_wolterprimary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
+    "pxf_wolterprimaryopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _d, _d, _vp, _st]),
+    "pxf_woltersecondary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
+    "pxf_woltersine": (_c.c_int, _NINE + [_i64, _d, _d, _d, _d, _vp, _st]),
+    "pxf_wsprimary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
+    "pxf_wssecondary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
+    "pxf_spocone": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
+    # zernsurf (coeff/rorder/aorder are HOST pointers)
+    "pxf_tracezern": (_c.c_int, _NINE + [_i64, _vp, _vp, _vp, _i32, _d, _vp, _st]),
+    "pxf_tracezernopd": (_c.c_int, [_dp] * 10 + [_i64, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),
+    # fused program
+    "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
+    # vignetting / compaction
+    "pxf_vignette_flags": (_c.c_int, [_dp] * 3 + [_i64, _vp, _st]),
+    "pxf_compact_scratch_bytes": (_sz, [_i64]),
+    "pxf_compact_count": (_c.c_int, [_vp, _i64, _vp, _vp, _st]),
+    "pxf_compact_scatter": (_c.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _st]),
+    "pxf_compact_indices": (_c.c_int, [_vp, _i64, _vp, _vp, _st]),
+    "pxf_gather_rows": (_c.c_int, [_vp, _vp, _i32, _vp, _i64, _vp, _st]),
+    # analyses
+    "pxf_sums_scratch_bytes": (_sz, []),
+    "pxf_sums": (_c.c_int, [_i32] + [_dp] * 6 + [_i64, _d, _d, _dp, _vp, _st]),
+    "pxf_rho": (_c.c_int, [_dp, _dp, _i64, _d, _d, _dp, _st]),
+    "pxf_select_state_bytes": (_sz, []),
+    "pxf_select_begin": (_c.c_int, [_vp, _i64, _i64, _st]),
+    "pxf_select_hist": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _i32, _i32, _vp, _st]),
+    "pxf_select_hist_ptr": (_vp, [_vp]),
+    "pxf_select_nan_ptr": (_vp, [_vp]),
+    "pxf_select_narrow": (_c.c_int, [_i32, _vp, _st]),
+    "pxf_select_finish": (_c.c_int, [_vp, _i64, _dp, _st]),
+    "pxf_select_schedule": (_c.c_int, [_i32, _vp, _vp]),
+    "pxf_centroid_from_sums": (_c.c_int, [_dp, _dp, _st]),
+    "pxf_hpd_workspace_bytes": (_sz, []),
+    "pxf_hpd_unweighted_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _st]),
+    "pxf_centroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _vp, _st]),
+    "pxf_rmscentroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_hpd": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_analyticimageplane": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
+    "pxf_sort_scratch_bytes": (_sz, [_i64]),
+    "pxf_argsort": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _st]),
+    "pxf_scan_scratch_bytes": (_sz, [_i64]),
+    "pxf_cumsum_gather": (_c.c_int, [_dp, _vp, _i64, _dp, _vp, _st]),
+    # sources
+    "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
+    "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
+    # host-buffer entry point
+    "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Open libpxf.so (once) and declare every entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "pyxfocus_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `make -C pyxfocus_b200/csrc`).  There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().pxf_last_error()
+        raise PxfError("libpxf error %d: %s" % (rc, msg.decode() if msg else ""))
+
+
+def launch_count():
+    return int(lib().pxf_launch_count())

@@ -1,0 +1,191 @@
+"""Mirror of the hot-path part of the reference's ``analyses.py`` on the device ray bundle:
+``centroid`` (analyses.py:16-22), ``rmsCentroid`` (:24-30), ``rmsX/rmsY`` (:46-58), ``rho``
+(:60-71), ``rhocdf`` (:73-86), ``hpd`` (:88-97), ``analyticImagePlane`` (:118-133), plus
+``findimageplane`` (named by the reference's examples, defined nowhere in it; see below).
+
+Everything is reductions / order statistics computed by libpxf kernels: block+warp
+reductions for the sums, an exact radix *select* on the IEEE bit patterns of the radii for
+the unweighted median, a hand-written radix sort + scan for the weighted branch.  Scalars are
+returned as Python floats like numpy scalars in the reference.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._call import stream_ptr
+from .program import flush
+
+
+def _w(weights, x):
+    if weights is None:
+        return None
+    w = torch.as_tensor(weights, dtype=torch.float64, device=x.device).contiguous()
+    if w.shape != x.shape:
+        raise ValueError("weights must have one entry per ray")
+    return w
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def centroid(rays, weights=None):
+    """Centroid of the rays in the xy plane (np.average semantics)."""
+    flush(rays)
+    x, y = rays[1:3]
+    w = _w(weights, x)
+    cx, cy = ctypes.c_double(), ctypes.c_double()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_centroid(x.data_ptr(), y.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(cx),
+                                           ctypes.byref(cy), stream_ptr(x.device)))
+    return cx.value, cy.value
+
+
+def rmsCentroid(rays, weights=None):
+    """RMS distance of the rays from their centroid in the xy plane."""
+    flush(rays)
+    x, y = rays[1:3]
+    w = _w(weights, x)
+    out = ctypes.c_double()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_rmscentroid(x.data_ptr(), y.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(out),
+                                              stream_ptr(x.device)))
+    return out.value
+
+
+def _rms1(v, weights):
+    # 1-D analogue of rmsCentroid: feed the same row as x and a zero-extent y
+    w = _w(weights, v)
+    zero = torch.zeros_like(v)
+    out = ctypes.c_double()
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().pxf_rmscentroid(v.data_ptr(), zero.data_ptr(), _ptr(w), v.shape[0],
+                                              ctypes.byref(out), stream_ptr(v.device)))
+    return out.value
+
+
+def rmsX(rays, weights=None):
+    """RMS from centroid in the X direction (analyses.py:46-51)."""
+    flush(rays)
+    return _rms1(rays[1], weights)
+
+
+def rmsY(rays, weights=None):
+    """RMS from centroid in the Y direction (analyses.py:53-58)."""
+    flush(rays)
+    return _rms1(rays[2], weights)
+
+
+def rho(rays, weights=None, cent=False):
+    """Distance of every ray from the centroid (cent=True) or the origin (analyses.py:60-71)."""
+    flush(rays)
+    x, y = rays[1:3]
+    if cent is True:
+        cx, cy = centroid(rays, weights=weights)
+    else:
+        cx, cy = 0., 0.
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_rho(x.data_ptr(), y.data_ptr(), x.shape[0], cx, cy, out.data_ptr(),
+                                      stream_ptr(x.device)))
+    return out
+
+
+def argsort(keys):
+    """(sorted keys, int64 permutation) by the library's stable LSD radix sort."""
+    dev = keys.device
+    num = keys.shape[0]
+    L = _lib.lib()
+    ks = torch.empty_like(keys)
+    idx = torch.empty(num, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        scratch = torch.empty(int(L.pxf_sort_scratch_bytes(num)), dtype=torch.uint8, device=dev)
+        _lib.check(L.pxf_argsort(keys.data_ptr(), num, ks.data_ptr(), idx.data_ptr(), scratch.data_ptr(),
+                                 stream_ptr(dev)))
+    return ks, idx
+
+
+def rhocdf(rays, weights=None, cent=True):
+    """Radial CDF of the ray distribution: (sorted radii, cumulative weight / max)
+    (analyses.py:73-86)."""
+    r = rho(rays, weights=weights, cent=cent)
+    dev = r.device
+    num = r.shape[0]
+    w = _w(weights, r)
+    L = _lib.lib()
+    rs, idx = argsort(r)
+    cdf = torch.empty_like(r)
+    with torch.cuda.device(dev):
+        scratch = torch.empty(int(L.pxf_scan_scratch_bytes(num)), dtype=torch.uint8, device=dev)
+        if w is None:
+            w = torch.ones_like(r)
+        _lib.check(L.pxf_cumsum_gather(w.data_ptr(), idx.data_ptr(), num, cdf.data_ptr(), scratch.data_ptr(),
+                                       stream_ptr(dev)))
+    cdf = cdf / cdf.max()
+    return rs, cdf
+
+
+def hpd(rays, weights=None, cent=True):
+    """Half-power diameter about the centroid (the reference ignores ``cent``,
+    analyses.py:90).  Unweighted: 2*median(r).  Weighted:
+    r[argmin|cdf-.75|] - r[argmin|cdf-.25|]."""
+    flush(rays)
+    x, y = rays[1:3]
+    w = _w(weights, x)
+    out = ctypes.c_double()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_hpd(x.data_ptr(), y.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(out),
+                                      stream_ptr(x.device)))
+    return out.value
+
+
+def analyticImagePlane(rays, weights=None):
+    """Axial shift to the best image plane, Ron Elsner's analytic method (analyses.py:118-133)."""
+    flush(rays)
+    x, y, z, l, m, n = rays[1:7]
+    w = _w(weights, x)
+    out = ctypes.c_double()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_analyticimageplane(x.data_ptr(), y.data_ptr(), l.data_ptr(), m.data_ptr(),
+                                                     n.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(out),
+                                                     stream_ptr(x.device)))
+    return out.value
+
+
+def imageplane_sums(rays, weights=None):
+    """The nine weighted sums behind ``analyticImagePlane`` / ``findimageplane`` as a device
+    tensor [S0, Sx, Sy, Sa, Sb, Sxa, Syb, Saa, Sbb] with a=l/n, b=m/n (one pass, 40 B/ray)."""
+    flush(rays)
+    x, y, z, l, m, n = rays[1:7]
+    w = _w(weights, x)
+    L = _lib.lib()
+    dev = x.device
+    out = torch.zeros(16, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        scratch = torch.empty(int(L.pxf_sums_scratch_bytes()), dtype=torch.uint8, device=dev)
+        _lib.check(L.pxf_sums(2, x.data_ptr(), y.data_ptr(), l.data_ptr(), m.data_ptr(), n.data_ptr(), _ptr(w),
+                              x.shape[0], 0., 0., out.data_ptr(), scratch.data_ptr(), stream_ptr(dev)))
+    return out[:9]
+
+
+def findimageplane(rays, zscan, num, weights=None, sums=None):
+    """Scan the axial offset over ``linspace(-zscan, zscan, num)`` and return the offset of
+    minimum RMS spot radius about the centroid.
+
+    PARITY UNPINNED: the reference *calls* ``findimageplane(zscan,num)`` from its examples
+    (examples/axro/WSverify.py:74-77,161-164) but ships no definition.  This
+    follows the legacy behaviour those call sites imply (move the plane by dz, trace to it,
+    take rmsCentroid, keep the best dz).  Propagating a ray by dz changes (x,y) by
+    (l/n, m/n)*dz, so RMS^2(dz) is an exact quadratic in dz whose coefficients are the nine
+    sums of ``analyticImagePlane``: one pass over the bundle instead of ``num`` passes."""
+    S = (sums if sums is not None else imageplane_sums(rays, weights)).cpu().numpy()
+    W = S[0]
+    mx, my, ma, mb = S[1] / W, S[2] / W, S[3] / W, S[4] / W
+    vxx = S[7] / W - ma * ma + S[8] / W - mb * mb            # Var(a)+Var(b)
+    cxa = S[5] / W - mx * ma + S[6] / W - my * mb            # Cov(x,a)+Cov(y,b)
+    dz = np.linspace(-zscan, zscan, int(num))
+    # RMS^2(dz) = RMS^2(0) + 2 dz Cov + dz^2 Var ; the constant does not move the argmin
+    merit = 2 * dz * cxa + dz ** 2 * vxx
+    return float(dz[np.argmin(merit)])

@@ -3,28 +3,9 @@
 // device code as the per-routine kernels (pxf_ray.cuh), so the result is bit-identical to
 // issuing the routines one by one.  Every ray runs the same program, so the opcode switch is
 // warp-uniform; only Newton trip counts and vignetting diverge.
-#include "pxf_internal.h"
-#include "pxf_params.h"
+#include "pxf_program.h"
 
 namespace pxf {
-
-#define FOP_PARAM_DOUBLES 28   // sizeof(WSP)/8 is the largest folded parameter block
-
-struct FusedOp {
-    int code;
-    int row;                 // VIGNETTE_BOX / ABS: bundle row index
-    double q[FOP_PARAM_DOUBLES];
-};
-struct FusedProgram {
-    int nops;
-    unsigned load_mask, store_mask;
-    int has_vignette;
-    FusedOp ops[PXF_MAX_OPS];
-};
-
-static_assert(sizeof(WSP) <= FOP_PARAM_DOUBLES * 8, "WSP does not fit a fused op slot");
-static_assert(sizeof(ConicP) <= FOP_PARAM_DOUBLES * 8, "ConicP does not fit");
-static_assert(sizeof(WolterSineP) <= FOP_PARAM_DOUBLES * 8, "WolterSineP does not fit");
 
 PXF_DEV double ray_row(const Ray &r, int row)
 {

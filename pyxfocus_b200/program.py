@@ -1,0 +1,204 @@
+"""Fused per-ray programs: a whole chain of f2py routines in ONE kernel launch.
+
+The reference runs a trace as a sequence of Fortran calls, each a full pass over the
+bundle in memory (~7 passes for a Wolter-I pair).  ``Program`` records the
+same routines -- same names and argument meaning as the f2py modules -- and
+``pxf_trace_program`` executes the list per ray in registers: rows are read from HBM once
+and written once.  The arithmetic is the same device code as the per-routine kernels, so the
+result is bit-identical to issuing the routines one by one.
+
+Two ways to use it:
+
+* explicitly::
+
+      prog = Program().transform(0, 0, 8400., 0, 0, 0).wolterprimary(220., 8400., 1.).reflect()
+      prog.run(rays)
+
+* transparently, with the reference's own call sequence::
+
+      with fused(rays):
+          tran.transform(rays, 0, 0, -8400., 0, 0, 0)
+          surf.wolterprimary(rays, 220., 8400.)
+          tran.reflect(rays)
+      # one kernel launch happens on exit (or as soon as something needs the rays)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._call import stream_ptr
+
+OP = dict(TRANSFORM=1, ITRANSFORM=2, REFLECT=3, REFRACT=4, RADGRAT=5, FLAT=6, FLATOPD=7, CONIC=8,
+          CONICOPD=9, WOLTERPRIMARY=10, WOLTERPRIMARYOPD=11, WOLTERSECONDARY=12, WOLTERSINE=13,
+          WSPRIMARY=14, WSSECONDARY=15, SPOCONE=16, VIGNETTE_MAG=17, VIGNETTE_BOX=18,
+          VIGNETTE_ABS=19, KICK=20)
+MAX_OPS = 24
+_VIGNETTES = (OP["VIGNETTE_MAG"], OP["VIGNETTE_BOX"], OP["VIGNETTE_ABS"])
+
+
+class Program:
+    """An ordered list of per-ray operations (arguments as the Fortran routine sees them)."""
+
+    def __init__(self):
+        self.ops = []
+
+    def __len__(self):
+        return len(self.ops)
+
+    def add(self, code, *p):
+        if len(p) > 6:
+            raise ValueError("an op carries at most 6 scalars")
+        self.ops.append((int(code), [float(v) for v in p]))
+        return self
+
+    # --- transformationsf ---
+    def transform(self, tx, ty, tz, rx, ry, rz):
+        return self.add(OP["TRANSFORM"], tx, ty, tz, rx, ry, rz)
+
+    def itransform(self, tx, ty, tz, rx, ry, rz):
+        return self.add(OP["ITRANSFORM"], tx, ty, tz, rx, ry, rz)
+
+    def reflect(self):
+        return self.add(OP["REFLECT"])
+
+    def refract(self, n1, n2):
+        return self.add(OP["REFRACT"], n1, n2)
+
+    def radgrat(self, wave, dpermm, order):
+        return self.add(OP["RADGRAT"], wave, dpermm, order)
+
+    # --- surfacesf ---
+    def flat(self):
+        return self.add(OP["FLAT"])
+
+    def flatopd(self, nr):
+        return self.add(OP["FLATOPD"], nr)
+
+    def conic(self, r, k):
+        return self.add(OP["CONIC"], r, k)
+
+    def conicopd(self, r, k, nr):
+        return self.add(OP["CONICOPD"], r, k, nr)
+
+    # --- woltsurf ---
+    def wolterprimary(self, r0, z0, psi):
+        return self.add(OP["WOLTERPRIMARY"], r0, z0, psi)
+
+    def wolterprimaryopd(self, r0, z0, psi, nr):
+        return self.add(OP["WOLTERPRIMARYOPD"], r0, z0, psi, nr)
+
+    def woltersecondary(self, r0, z0, psi):
+        return self.add(OP["WOLTERSECONDARY"], r0, z0, psi)
+
+    def woltersine(self, r0, z0, amp, freq):
+        return self.add(OP["WOLTERSINE"], r0, z0, amp, freq)
+
+    def wsprimary(self, alpha, z0, psi):
+        return self.add(OP["WSPRIMARY"], alpha, z0, psi)
+
+    def wssecondary(self, alpha, z0, psi):
+        return self.add(OP["WSSECONDARY"], alpha, z0, psi)
+
+    def spocone(self, r0, tg):
+        return self.add(OP["SPOCONE"], r0, tg)
+
+    # --- per-ray predicates (the ray stops at the op; use with ``alive``) ---
+    def vignette_mag(self):
+        """keep rays with l^2+m^2+n^2 > .1 (transformations.py:220-223)"""
+        return self.add(OP["VIGNETTE_MAG"])
+
+    def vignette_box(self, row, lo, hi):
+        """keep rays with lo < rays[row] < hi"""
+        return self.add(OP["VIGNETTE_BOX"], row, lo, hi)
+
+    def vignette_abs(self, row, hi):
+        """keep rays with |rays[row]| < hi"""
+        return self.add(OP["VIGNETTE_ABS"], row, hi)
+
+    def kick(self, dl, dm, sn):
+        """l += dl, m += dm, n = sn*sqrt(1-l^2-m^2) (field-angle kick, axialHeights.py:94-95)"""
+        return self.add(OP["KICK"], dl, dm, sn)
+
+    # --- execution ---
+    def has_vignette(self):
+        return any(c in _VIGNETTES for c, _ in self.ops)
+
+    def c_ops(self):
+        arr = (_lib.pxf_op * len(self.ops))()
+        for k, (code, p) in enumerate(self.ops):
+            arr[k].code = code
+            for j, v in enumerate(p):
+                arr[k].p[j] = v
+        return arr
+
+    def run(self, rays, alive=None):
+        """Execute on a bundle (list of ten CUDA fp64 rows).  Returns the ``alive`` uint8
+        tensor when the program contains a vignette predicate (allocated if not given)."""
+        if not self.ops:
+            return alive
+        if len(self.ops) > MAX_OPS:
+            # split into several launches; still one HBM round trip per <=24 elements
+            head, tail = Program(), Program()
+            head.ops, tail.ops = self.ops[:MAX_OPS], self.ops[MAX_OPS:]
+            if head.has_vignette() or tail.has_vignette():
+                raise ValueError("programs with vignette predicates are limited to %d ops" % MAX_OPS)
+            head.run(rays)
+            return tail.run(rays)
+        dev = rays[1].device
+        num = rays[1].shape[0]
+        for r in rays:
+            if r is not None and (not r.is_cuda or r.dtype != torch.float64 or not r.is_contiguous()
+                                  or r.shape[0] != num):
+                raise ValueError("ray rows must be contiguous 1-D float64 CUDA tensors of equal length")
+        if self.has_vignette() and alive is None:
+            alive = torch.empty(num, dtype=torch.uint8, device=dev)
+        ptrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in rays])
+        ops = self.c_ops()
+        with torch.cuda.device(dev):
+            rc = _lib.lib().pxf_trace_program(ptrs, num, ops, len(self.ops),
+                                              alive.data_ptr() if alive is not None else None,
+                                              stream_ptr(dev))
+        _lib.check(rc)
+        return alive
+
+
+# ------------------------------------------------------------------ transparent recording
+_active = {}     # id(rays list) -> (rays, Program)
+
+
+def recorder_for(rays):
+    """Program currently recording for this bundle, or None."""
+    ent = _active.get(id(rays))
+    return ent[1] if ent is not None and ent[0] is rays else None
+
+
+def flush(rays):
+    """Execute whatever is pending for this bundle (called by anything that reads the rays)."""
+    prog = recorder_for(rays)
+    if prog is not None and len(prog):
+        todo = Program()
+        todo.ops, prog.ops = prog.ops, []
+        todo.run(rays)
+
+
+class fused:
+    """Context manager: calls of the ``transformations``/``surfaces`` API on ``rays`` inside the
+    block are recorded and executed as one kernel on exit."""
+
+    def __init__(self, rays):
+        self.rays = rays
+
+    def __enter__(self):
+        if id(self.rays) in _active:
+            raise RuntimeError("bundle is already recording")
+        _active[id(self.rays)] = (self.rays, Program())
+        return self.rays
+
+    def __exit__(self, et, ev, tb):
+        try:
+            if et is None:
+                flush(self.rays)
+        finally:
+            _active.pop(id(self.rays), None)
+        return False

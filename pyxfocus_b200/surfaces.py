@@ -1,0 +1,191 @@
+"""Mirror of the hot-path part of the reference's ``surfaces.py`` on the device ray bundle:
+``flat`` (surfaces.py:14-29), ``zernsurf`` (:31-47), ``conic`` (:104-113),
+``wolterprimary`` (:219-227), ``wolterprimarynode`` (:229-236), ``woltersecondary``
+(:238-243), ``woltersine`` (:265-270), ``wsPrimary`` (:331-347), ``wsSecondary`` (:367-383),
+``spoCone/spoPrimary/spoSecondary`` (:403-441), ``focus/focusI`` (:502-519).
+
+Same names, argument order and results; ``ind=`` masks run as in-kernel predicates, and inside
+``with program.fused(rays):`` unmasked calls are recorded into one fused kernel.
+"""
+import numpy as np
+import torch
+
+from . import conicsolve as con
+from . import surfacesf as surf
+from . import transformations as tran
+from . import woltsurf as wolt
+from . import zernsurf as zern
+from .analyses import analyticImagePlane
+from .program import flush, recorder_for
+
+
+def flat(rays, ind=None, nr=None):
+    """Trace rays to the XY plane.  As in the reference, ``ind`` takes precedence over ``nr``
+    (the masked branch calls the non-OPD routine, surfaces.py:17-24)."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    if ind is not None:
+        flush(rays)
+        surf.flat(x, y, z, l, m, n, ux, uy, uz, mask=ind)
+        return
+    prog = recorder_for(rays)
+    if nr is not None:
+        if prog is not None:
+            prog.flatopd(nr)
+        else:
+            surf.flatopd(x, y, z, l, m, n, ux, uy, uz, opd, nr)
+    else:
+        if prog is not None:
+            prog.flat()
+        else:
+            surf.flat(x, y, z, l, m, n, ux, uy, uz)
+    return
+
+
+def zernsurf(rays, coeff, rad, rorder=None, aorder=None, nr=None):
+    """Zernike sag surface, theta = arctan2(y,x).  ``rorder``/``aorder`` must be given: the
+    reference's default comes from the un-vendored ``utilities.imaging.zernikemod.zmodes``
+    (surfaces.py:10,36-37), whose ordering is not pinned anywhere in the reference tree."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    if rorder is None or aorder is None:
+        raise NotImplementedError("pass rorder/aorder explicitly: the reference's default ordering lives in "
+                                  "the third-party module utilities.imaging.zernikemod (not vendored)")
+    flush(rays)
+    if nr is None:
+        zern.tracezern(x, y, z, l, m, n, ux, uy, uz, coeff, np.array(rorder), np.array(aorder), rad)
+    else:
+        zern.tracezernopd(opd, x, y, z, l, m, n, ux, uy, uz, coeff, np.array(rorder), np.array(aorder), rad, nr)
+    return
+
+
+def conic(rays, R, K, nr=None):
+    """Conic with radius of curvature R and conic constant K."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    prog = recorder_for(rays)
+    if nr is not None:
+        if prog is not None:
+            prog.conicopd(R, K, nr)
+        else:
+            surf.conicopd(opd, x, y, z, l, m, n, ux, uy, uz, R, K, nr)
+    else:
+        if prog is not None:
+            prog.conic(R, K)
+        else:
+            surf.conic(x, y, z, l, m, n, ux, uy, uz, R, K)
+    return
+
+
+def wolterprimary(rays, r0, z0, psi=1., nr=None):
+    """Wolter-I primary (paraboloid), no vignetting."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    prog = recorder_for(rays)
+    if nr is None:
+        if prog is not None:
+            prog.wolterprimary(r0, z0, psi)
+        else:
+            wolt.wolterprimary(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi)
+    else:
+        if prog is not None:
+            prog.wolterprimaryopd(r0, z0, psi, nr)
+        else:
+            wolt.wolterprimaryopd(opd, x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, nr)
+    return
+
+
+def wolterprimarynode(rays, r0, z0, psi=1.):
+    """Wolter node at the current origin, focus at (-r0,0,-z0)."""
+    tran.transform(rays, -r0, 0, -z0, 0, 0, 0)
+    wolterprimary(rays, r0, z0, psi)
+    tran.itransform(rays, -r0, 0, -z0, 0, 0, 0)
+    return
+
+
+def woltersecondary(rays, r0, z0, psi=1.):
+    """Wolter-I secondary (hyperboloid), no vignetting."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    prog = recorder_for(rays)
+    if prog is not None:
+        prog.woltersecondary(r0, z0, psi)
+    else:
+        wolt.woltersecondary(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi)
+    return
+
+
+def woltersine(rays, r0, z0, amp, freq):
+    """Wolter-I primary with an axial sinusoid."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    prog = recorder_for(rays)
+    if prog is not None:
+        prog.woltersine(r0, z0, amp, freq)
+    else:
+        wolt.woltersine(x, y, z, l, m, n, ux, uy, uz, r0, z0, amp, freq)
+    return
+
+
+def _ws(rays, which, r0, z0, psi, check):
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    a, p, d, e = con.woltparam(r0, z0)
+    if check is True:
+        # The reference's check=True path overwrites the scalar z0 with an array before the
+        # Fortran call (surfaces.py:340-342) and cannot run; here it does what its docstring says.
+        flush(rays)
+        x0, y0, zz0 = x.clone(), y.clone(), z.clone()
+    prog = recorder_for(rays)
+    if prog is not None and check is not True:
+        getattr(prog, which)(a, z0, psi)
+        return
+    getattr(wolt, which)(x, y, z, l, m, n, ux, uy, uz, a, z0, psi)
+    if check is True:
+        return torch.logical_and(x0 == x, torch.logical_and(y0 == y, zz0 == z))
+    return
+
+
+def wsPrimary(rays, r0, z0, psi, check=False):
+    """Wolter-Schwarzschild primary; alpha from ``conicsolve.woltparam``."""
+    return _ws(rays, "wsprimary", r0, z0, psi, check)
+
+
+def wsSecondary(rays, r0, z0, psi, check=False):
+    """Wolter-Schwarzschild secondary."""
+    return _ws(rays, "wssecondary", r0, z0, psi, check)
+
+
+def spoCone(rays, R0, tg, ind=None):
+    """SPO cone with intersection radius R0 and slope angle tg."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    prog = recorder_for(rays) if ind is None else None
+    if prog is not None:
+        prog.spocone(R0, tg)
+        return
+    flush(rays)
+    wolt.spocone(x, y, z, l, m, n, ux, uy, uz, R0, tg, mask=ind)
+    return
+
+
+def spoPrimary(rays, R0, F, d=.605, ind=None):
+    """SPO primary: tg = atan((R0+d/2)/F)/4."""
+    tg = .25 * np.arctan((R0 + d / 2) / F)
+    spoCone(rays, R0, tg, ind=ind)
+    return
+
+
+def spoSecondary(rays, R0, F, d=.605, ind=None):
+    """SPO secondary: tg = 3 atan((R0+d/2)/F)/4."""
+    tg = .75 * np.arctan((R0 + d / 2) / F)
+    spoCone(rays, R0, tg, ind=ind)
+    return
+
+
+def focus(rays, fn, weights=None, nr=None, coords=None):
+    """Two-pass best focus (surfaces.py:502-510)."""
+    dz1 = fn(rays, weights=weights)
+    tran.transform(rays, 0, 0, dz1, 0, 0, 0, coords=coords)
+    flat(rays, nr=nr)
+    dz2 = fn(rays, weights=weights)
+    tran.transform(rays, 0, 0, dz2, 0, 0, 0, coords=coords)
+    flat(rays, nr=nr)
+    return dz1 + dz2
+
+
+def focusI(rays, weights=None, nr=None, coords=None):
+    """Best focus from the analytic image plane (surfaces.py:518-519)."""
+    return focus(rays, analyticImagePlane, weights=weights, nr=nr, coords=coords)

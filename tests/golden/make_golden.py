@@ -1,0 +1,221 @@
+"""Generate the golden fixtures in this directory.
+
+Run in the BUILD container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's *unmodified* Python layer (sources / transformations / surfaces /
+analyses) through ``oracle.refload`` -- with the C oracle standing in for the four f2py
+Fortran modules, which cannot be compiled here (no Fortran compiler) -- runs the BASELINE
+configurations at small sizes and stores inputs and outputs as .npz.  The GPU parity tests
+upload the stored inputs, run the CUDA engine and compare with the stored outputs; the CPU
+tests re-run the oracle restatement (oracle/pyref.py, oracle/chains.py) against them.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import chains, refload  # noqa: E402
+
+
+def copy(rays):
+    return [np.array(r, dtype=np.float64, copy=True) for r in rays]
+
+
+def pack(prefix, rays):
+    return {prefix: np.stack([np.asarray(r, dtype=np.float64) for r in rays])}
+
+
+def main():
+    ref = refload.load()
+    src, tran, surf, anal = ref.sources, ref.transformations, ref.surfaces, ref.analyses
+    out = {}
+
+    # ---- config 1: Wolter-I pair, on axis (singlePassAlignment.py:246-269)
+    N = 4000
+    np.random.seed(0)
+    st = np.random.get_state()
+    u = np.random.rand(2 * N)
+    np.random.set_state(st)
+    rays = src.subannulus(220., 220.6, 2 * np.pi, N, zhat=-1.)
+    g = dict(u1=u[:N], u2=u[N:])
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -8400., 0, 0, 0)
+    surf.wolterprimary(rays, 220., 8400.)
+    g.update(pack("after_primary", rays))
+    tran.reflect(rays)
+    surf.woltersecondary(rays, 220., 8400.)
+    tran.reflect(rays)
+    surf.flat(rays)
+    g.update(pack("rays_out", rays))
+    g["hpd"] = anal.hpd(rays)
+    g["rms"] = anal.rmsCentroid(rays)
+    g["centroid"] = np.array(anal.centroid(rays))
+    w = np.linspace(.5, 1.5, N)
+    g["weights"] = w
+    g["hpd_w"] = anal.hpd(rays, weights=w)
+    g["rms_w"] = anal.rmsCentroid(rays, weights=w)
+    g["centroid_w"] = np.array(anal.centroid(rays, weights=w))
+    r, cdf = anal.rhocdf(rays, weights=w)
+    g["rhocdf_r"], g["rhocdf_cdf"] = r, cdf
+    np.savez_compressed(os.path.join(HERE, "wolter1.npz"), **g)
+
+    # ---- config 2: Wolter-Schwarzschild, 10 arcmin off axis (axialHeights.py:77-113)
+    N = 4000
+    a0, a1 = chains.ws_aperture()
+    theta = 10. / 60. * np.pi / 180.
+    np.random.seed(0)
+    rays = src.subannulus(a0, a1, 100. / 220., N)
+    g = dict(a0=a0, a1=a1, theta=theta)
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -1.e4, 0, 0, 0)
+    surf.wsPrimary(rays, 220., 1.e4, 1.)
+    rays[4] = rays[4] + np.sin(theta)
+    rays[6] = -np.sqrt(1. - rays[4] ** 2)
+    tran.reflect(rays)
+    surf.wsSecondary(rays, 220., 1.e4, 1.)
+    tran.reflect(rays)
+    g.update(pack("after_secondary", rays))
+    g["dz_analytic"] = anal.analyticImagePlane(rays)
+    g["focus"] = surf.focusI(rays)
+    g.update(pack("rays_out", rays))
+    g["hpd"] = anal.hpd(rays)
+    g["rms"] = anal.rmsCentroid(rays)
+    np.savez_compressed(os.path.join(HERE, "ws_offaxis.npz"), **g)
+
+    # ---- config 2b: far off axis (25 arcmin): rays hit the 26-iteration cap and are restored
+    theta = 25. / 60. * np.pi / 180.
+    np.random.seed(1)
+    rays = src.subannulus(a0, a1, 100. / 220., 2000)
+    g = dict(theta=theta)
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -1.e4, 0, 0, 0)
+    surf.wsPrimary(rays, 220., 1.e4, 1.)
+    rays[4] = rays[4] + np.sin(theta)
+    rays[6] = -np.sqrt(1. - rays[4] ** 2)
+    tran.reflect(rays)
+    before = copy(rays)
+    surf.wsSecondary(rays, 220., 1.e4, 1.)
+    g["restored"] = np.logical_and(before[1] == rays[1], np.logical_and(before[2] == rays[2], before[3] == rays[3]))
+    g.update(pack("rays_out", rays))
+    np.savez_compressed(os.path.join(HERE, "ws_cap.npz"), **g)
+
+    # ---- config 3: Zernike figure error (singlePassAlignment.py:22-56 style) + Wolter-I + vignette
+    N = 2000
+    ro, ao = chains.zernike_orders(7)
+    coeff = chains.zernike_coeff(36, 0)
+    np.random.seed(2)
+    rays = src.circularbeam(60., N)
+    g = dict(coeff=coeff, rorder=ro, aorder=ao, rad=62.5)
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -100., 0, 0, 0)
+    surf.zernsurf(rays, coeff, 62.5, rorder=ro, aorder=ao, nr=1.)
+    g.update(pack("after_zern", rays))
+    tran.reflect(rays)
+    tran.transform(rays, 0, 0, 50., 0, 0, 0)
+    surf.flat(rays, nr=1.)
+    g.update(pack("rays_out", rays))
+    # non-OPD variant on a fresh bundle
+    np.random.seed(3)
+    rays = src.circularbeam(60., N)
+    g.update(pack("rays_in2", rays))
+    tran.transform(rays, 1., -2., -100., 1e-3, -2e-3, .3)
+    surf.zernsurf(rays, coeff, 62.5, rorder=ro, aorder=ao)
+    g.update(pack("rays_out2", rays))
+    np.savez_compressed(os.path.join(HERE, "zernike.npz"), **g)
+
+    # ---- config 4: SPO cones + radial grating with masks + vignette (arcus/cat.py:203-288 style)
+    N = 4000
+    R0, F = 737., 12.e3
+    np.random.seed(4)
+    rays = src.subannulus(R0, R0 + .605, 30. / R0, N, zhat=-1.)
+    g = dict(R0=R0, F=F)
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, 0, 0, 0, .01)
+    surf.spoPrimary(rays, R0, F)
+    tran.reflect(rays)
+    surf.spoSecondary(rays, R0, F)
+    tran.reflect(rays)
+    g.update(pack("after_spo", rays))
+    # move to a grating 200 mm above the focus, hub further down +y
+    tran.transform(rays, 0, 0, -(F - 200.), 0, 0, 0)
+    tran.transform(rays, R0 * 200. / F * 0 + 0., 0, 0, 0, 0, 0)
+    surf.flat(rays)
+    tran.transform(rays, 0, 11832.911 - 0., 0, 0, 0, 0)      # origin to the hub
+    mask = rays[1] > np.median(rays[1])
+    g["mask"] = mask
+    tran.reflect(rays, ind=mask)
+    tran.radgrat(rays, 160. / 11832.911, -3, 2.4, ind=mask)
+    wave = np.random.uniform(3.6, 7.2, N)
+    g["wave"] = wave
+    tran.radgrat(rays, 160. / 11832.911, 1, wave, ind=~mask)
+    g.update(pack("after_grat", rays))
+    # evanescent diffraction -> NaN n for part of the bundle (transformationsf.f95:231-234)
+    evan = np.arange(N) % 7 == 0
+    g["evan"] = evan
+    tran.radgrat(rays, 160. / 11832.911, 150, 2.4, ind=evan)
+    # a small sphere most rays miss -> direction zeroed (surfacesf.f95:342-345)
+    g.update(pack("after_evan", rays))
+    g.update(pack("vignetted_evan", tran.vignette(rays)))      # NaN > .1 is False: removed
+    tran.transform(rays, np.mean(rays[1]), np.mean(rays[2]), 0, 0, 0, 0)
+    surf.conic(rays, 10., 0.)
+    g.update(pack("after_miss", rays))
+    v = tran.vignette(rays)
+    g.update(pack("vignetted", v))
+    keep = np.logical_and(rays[1] > 0., np.abs(rays[2]) < 10.)
+    g["keep"] = keep
+    g.update(pack("vignetted_mask", tran.vignette(rays, ind=keep)))
+    np.savez_compressed(os.path.join(HERE, "spo_grating.npz"), **g)
+
+    # ---- remaining routines: conic(+opd), refract, woltersine, wolterprimaryopd, itransform, grat, flat(ind)
+    N = 1500
+    np.random.seed(5)
+    rays = src.pointsource(.02, N)
+    g = {}
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -500., 0, 0, 0)
+    surf.conic(rays, 1000., -1.)
+    g.update(pack("after_conic", rays))
+    tran.refract(rays, 1., 1.5)
+    g.update(pack("after_refract", rays))
+    tran.transform(rays, 0, 0, 10., 0, 0, 0)
+    surf.conic(rays, -800., .3, nr=1.5)
+    g.update(pack("after_conicopd", rays))
+    tran.refract(rays, 1.5, 1.)
+    tran.itransform(rays, .3, -.2, 5., .01, .02, -.03)
+    g.update(pack("after_itransform", rays))
+    sel = np.arange(0, N, 3)
+    g["sel"] = sel
+    surf.flat(rays, ind=sel)
+    g.update(pack("after_flat_ind", rays))
+    order = np.random.randint(-2, 3, N).astype(np.float64)
+    wv = np.random.uniform(1., 2., N)
+    g["grat_order"], g["grat_wave"] = order, wv
+    order[::50] = 150.       # evanescent: l**2+m**2 > 1 -> direction zeroed (transformationsf.f95:297-301)
+    g["grat_order"] = order
+    tran.grat(rays, 160.e-6, order, wv * 1.e-6)
+    g.update(pack("after_grat", rays))
+    np.random.seed(6)
+    rays = src.subannulus(220., 220.4, .2, N, zhat=-1.)
+    g.update(pack("rays_in2", rays))
+    tran.transform(rays, 0, 0, -8400., 0, 0, 0)
+    surf.woltersine(rays, 220., 8400., 1.e-4, 1. / 20.)
+    g.update(pack("after_woltersine", rays))
+    np.random.seed(7)
+    rays = src.subannulus(220., 220.4, .2, N, zhat=-1.)
+    tran.transform(rays, 0, 0, -8400., 0, 0, 0)
+    surf.wolterprimary(rays, 220., 8400., psi=1.3, nr=1.)
+    g.update(pack("after_primaryopd", rays))
+    np.savez_compressed(os.path.join(HERE, "misc.npz"), **g)
+    print("golden fixtures written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
+
+
+if __name__ == "__main__":
+    main()
