@@ -179,6 +179,11 @@ typedef struct pxf_op {
  * otherwise.  Required when the program contains a VIGNETTE op. */
 int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
                       uint8_t *alive, pxf_stream_t stream);
+/* Out-of-place variant: rows are read from rays_in and every row the program reads or writes
+ * is stored to rays_out (rows it touches neither way are not copied).  rays_in is left
+ * untouched, e.g. to trace one source bundle through several configurations. */
+int pxf_trace_program_to(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                         const pxf_op *ops, int32_t nops, uint8_t *alive, pxf_stream_t stream);
 
 /* ======================= vignetting / compaction ======================== */
 /* flags[i] = (l^2+m^2+n^2 > .1), the default predicate of transformations.vignette
@@ -313,10 +318,13 @@ int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, c
  *   alive_host       nullable uint8[num]; receives the survivor flags of VIGNETTE ops
  *   alive_count_host nullable; number of surviving rays (-1 if it was not computed because
  *                    neither hpd_host nor alive_host was given)
+ *   x_dev_keep/y_dev_keep  nullable pair of caller-owned DEVICE rows (num doubles, 16-byte
+ *                    aligned): the final x,y stay resident there for follow-up analyses (a
+ *                    sharded bundle's global HPD)
  * Synchronous: returns when every host row is final. */
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
-                           int64_t *alive_count_host);
+                           int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pxf_tracezernopd": (_c.c_int, [_dp] * 10 + [_i64, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),
     # fused program
     "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
+    "pxf_trace_program_to": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _st]),
     # vignetting / compaction
     "pxf_vignette_flags": (_c.c_int, [_dp] * 3 + [_i64, _vp, _st]),
     "pxf_compact_scratch_bytes": (_sz, [_i64]),
@@ -97,7 +98,7 @@ SIGNATURES = {
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
     "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
     # host-buffer entry point
-    "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

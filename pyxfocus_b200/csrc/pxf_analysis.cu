@@ -500,10 +500,10 @@ int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, co
 int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy, double *rho_out,
             pxf_stream_t stream)
 {
+    if (num == 0) return PXF_OK;
     if (num < 0 || !x || !y || !rho_out) { set_error("pxf_rho: bad argument"); return PXF_ERR_INVALID; }
     int rc = need_device();
     if (rc) return rc;
-    if (num == 0) return PXF_OK;
     k_rho<<<grid_for(num, PXF_BLOCK * 2, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, y, num, cx, cy, nullptr, rho_out);
     count_launch();
@@ -685,6 +685,7 @@ size_t pxf_hpd_workspace_bytes(void)
 int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
             pxf_stream_t stream)
 {
+    if (num == 0 && hpd_host) { *hpd_host = __builtin_nan(""); return PXF_OK; }   // np.median([]) is nan
     if (num < 0 || !x || !y || !hpd_host) { set_error("pxf_hpd: bad argument"); return PXF_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc = need_device();
@@ -725,10 +726,10 @@ static inline RowTable *ctab(const void *scratch, int64_t ntiles)
 int pxf_vignette_flags(const double *l, const double *m, const double *n, int64_t num,
                        uint8_t *flags, pxf_stream_t stream)
 {
+    if (num == 0) return PXF_OK;
     if (num < 0 || !l || !m || !n || !flags) { set_error("pxf_vignette_flags: bad argument"); return PXF_ERR_INVALID; }
     int rc = need_device();
     if (rc) return rc;
-    if (num == 0) return PXF_OK;
     k_vignette_flags<<<grid_for(num, PXF_BLOCK * 2, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         l, m, n, num, flags);
     count_launch();
@@ -738,11 +739,11 @@ int pxf_vignette_flags(const double *l, const double *m, const double *n, int64_
 int pxf_compact_count(const uint8_t *flags, int64_t num, void *scratch, int64_t *count_host,
                       pxf_stream_t stream)
 {
+    if (num == 0 && count_host) { *count_host = 0; return PXF_OK; }
     if (num < 0 || !flags || !scratch || !count_host) { set_error("pxf_compact_count: bad argument"); return PXF_ERR_INVALID; }
     int rc = need_device();
     if (rc) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (num == 0) { *count_host = 0; return PXF_OK; }
     int64_t ntiles = (num + CTILE - 1) / CTILE;
     k_compact_count<<<(unsigned)ntiles, PXF_BLOCK, 0, s>>>(flags, num, ccnt(scratch, ntiles));
     k_compact_scan<<<1, 1024, 0, s>>>(ccnt(scratch, ntiles), ntiles, coff(scratch));
@@ -758,13 +759,13 @@ int pxf_compact_count(const uint8_t *flags, int64_t num, void *scratch, int64_t 
 int pxf_compact_scatter(const double *const *rows_in, double *const *rows_out, int32_t nrows,
                         const uint8_t *flags, int64_t num, const void *scratch, pxf_stream_t stream)
 {
+    if (num == 0) return PXF_OK;
     if (num < 0 || !rows_in || !rows_out || nrows < 1 || nrows > 16 || !flags || !scratch) {
         set_error("pxf_compact_scatter: bad argument");
         return PXF_ERR_INVALID;
     }
     int rc = need_device();
     if (rc) return rc;
-    if (num == 0) return PXF_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int64_t ntiles = (num + CTILE - 1) / CTILE;
     RowTable h;
@@ -779,10 +780,11 @@ int pxf_compact_scatter(const double *const *rows_in, double *const *rows_out, i
 int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, int64_t *idx_out,
                         pxf_stream_t stream)
 {
-    if (num < 0 || !flags || !scratch || !idx_out) { set_error("pxf_compact_indices: bad argument"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    if (num < 0 || !flags || !scratch) { set_error("pxf_compact_indices: bad argument"); return PXF_ERR_INVALID; }
     int rc = need_device();
     if (rc) return rc;
-    if (num == 0) return PXF_OK;
+    // idx_out may be NULL only if no ray survives (nothing is written then)
     int64_t ntiles = (num + CTILE - 1) / CTILE;
     k_compact_scatter<1><<<(unsigned)ntiles, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         nullptr, nullptr, 0, flags, num, coff(scratch), reinterpret_cast<long long *>(idx_out));

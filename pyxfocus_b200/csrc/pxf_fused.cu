@@ -103,9 +103,10 @@ PXF_DEV void fstore2(const Ray &a, const Ray &b, const RowPtrs &P, unsigned M, i
 
 template <bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_program(const RowPtrs P, const int64_t num, uint8_t *__restrict__ alive,
+k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
           const __grid_constant__ FusedProgram prog)
 {
+    // P: rows read, Q: rows written (Q == P for the in-place f2py semantics)
     const unsigned LM = prog.load_mask, SM = prog.store_mask;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
@@ -117,7 +118,7 @@ k_program(const RowPtrs P, const int64_t num, uint8_t *__restrict__ alive,
             fload2(a, b, P, LM, i);
             const bool ka = run_program(a, prog);
             const bool kb = run_program(b, prog);
-            fstore2(a, b, P, SM, i);
+            fstore2(a, b, Q, SM, i);
             if (alive) { alive[i] = ka ? 1 : 0; alive[i + 1] = kb ? 1 : 0; }
         }
         if ((num & 1) && tid == 0) {
@@ -125,7 +126,7 @@ k_program(const RowPtrs P, const int64_t num, uint8_t *__restrict__ alive,
             Ray a;
             fload1(a, P, LM, i);
             const bool ka = run_program(a, prog);
-            fstore1(a, P, SM, i);
+            fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
         }
     } else {
@@ -133,7 +134,7 @@ k_program(const RowPtrs P, const int64_t num, uint8_t *__restrict__ alive,
             Ray a;
             fload1(a, P, LM, i);
             const bool ka = run_program(a, prog);
-            fstore1(a, P, SM, i);
+            fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
         }
     }
@@ -238,20 +239,25 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
     return PXF_OK;
 }
 
-int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s)
+int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s,
+                   double *const rays_out[10])
 {
     if (num < 0 || !rays) { set_error("program: bad argument"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     if (fp.has_vignette && !alive) { set_error("program with a VIGNETTE op needs an alive array"); return PXF_ERR_INVALID; }
     if (num == 0) return PXF_OK;
-    RowPtrs P;
+    RowPtrs P, Q;
     bool aligned = true;
-    const unsigned used = fp.load_mask | fp.store_mask;
     for (int k = 0; k < 10; k++) {
         P.p[k] = rays[k];
-        if (used & (1u << k)) {
-            if (!rays[k]) { set_error("program: null row pointer (row %d)", k); return PXF_ERR_INVALID; }
-            if (reinterpret_cast<uintptr_t>(rays[k]) & 15) aligned = false;
+        Q.p[k] = rays_out ? rays_out[k] : rays[k];
+        if (fp.load_mask & (1u << k)) {
+            if (!P.p[k]) { set_error("program: null input row pointer (row %d)", k); return PXF_ERR_INVALID; }
+            if (reinterpret_cast<uintptr_t>(P.p[k]) & 15) aligned = false;
+        }
+        if (fp.store_mask & (1u << k)) {
+            if (!Q.p[k]) { set_error("program: null output row pointer (row %d)", k); return PXF_ERR_INVALID; }
+            if (reinterpret_cast<uintptr_t>(Q.p[k]) & 15) aligned = false;
         }
     }
     static int ctas[2] = {0, 0};
@@ -265,10 +271,10 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
     }
     if (aligned) {
         int grid = grid_for((num + 1) >> 1, PXF_BLOCK, ctas[v]);
-        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, num, alive, fp);
+        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, fp);
     } else {
         int grid = grid_for(num, PXF_BLOCK, ctas[v]);
-        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, num, alive, fp);
+        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, fp);
     }
     count_launch();
     return check_launch("k_program");
@@ -284,5 +290,18 @@ extern "C" int pxf_trace_program(double *const rays[10], int64_t num, const pxf_
     FusedProgram fp;
     int rc = build_program(fp, ops, nops);
     if (rc) return rc;
-    return launch_program(rays, num, fp, alive, reinterpret_cast<cudaStream_t>(stream));
+    return launch_program(rays, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                                    const pxf_op *ops, int32_t nops, uint8_t *alive, pxf_stream_t stream)
+{
+    if (!rays_out) { set_error("pxf_trace_program_to: null output table"); return PXF_ERR_INVALID; }
+    FusedProgram fp;
+    int rc = build_program(fp, ops, nops);
+    if (rc) return rc;
+    // out of place: rows that are read but never written must still appear in the output
+    // bundle, so every row the program touches is stored
+    fp.store_mask |= fp.load_mask;
+    return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out);
 }

@@ -54,7 +54,7 @@ size_t pxf_hpd_workspace_bytes(void);
 
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
-                           int64_t *alive_count_host)
+                           int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep)
 {
     if (!rows_host || num < 0) { set_error("pxf_host_trace_program: bad argument"); return PXF_ERR_INVALID; }
     FusedProgram fp;
@@ -85,10 +85,20 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     const int nslots = nchunks < HOST_SLOTS ? (int)nchunks : HOST_SLOTS;
     // x,y of the final bundle stay resident when the HPD is wanted (rows 1,2 then live in the
     // full-length arrays and the slots alias into them)
-    const bool xy_full = want_hpd;
+    const bool keep_xy = x_dev_keep && y_dev_keep;      // caller-owned device rows of length num
+    if (keep_xy && ((reinterpret_cast<uintptr_t>(x_dev_keep) | reinterpret_cast<uintptr_t>(y_dev_keep)) & 15)) {
+        set_error("pxf_host_trace_program: x_dev_keep/y_dev_keep must be 16-byte aligned");
+        return PXF_ERR_INVALID;
+    }
+    const bool xy_full = want_hpd || keep_xy;
+    double *fx = nullptr, *fy = nullptr;
     if (xy_full) {
-        PXF_CUDA(cudaMalloc(&R.full_x, (size_t)(nchunks * chunk) * 8));
-        PXF_CUDA(cudaMalloc(&R.full_y, (size_t)(nchunks * chunk) * 8));
+        if (keep_xy) { fx = x_dev_keep; fy = y_dev_keep; }
+        else {
+            PXF_CUDA(cudaMalloc(&R.full_x, (size_t)(nchunks * chunk) * 8));
+            PXF_CUDA(cudaMalloc(&R.full_y, (size_t)(nchunks * chunk) * 8));
+            fx = R.full_x; fy = R.full_y;
+        }
         if (want_alive) PXF_CUDA(cudaMalloc(&R.full_alive, (size_t)(nchunks * chunk)));
     }
     for (int k = 0; k < nslots; k++) {
@@ -112,7 +122,7 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
         const int64_t n = (lo + chunk <= num) ? chunk : (num - lo);
         double *rows[10];
         for (int r = 0; r < 10; r++) rows[r] = R.slot_rows[k][r];
-        if (xy_full) { rows[1] = R.full_x + lo; rows[2] = R.full_y + lo; }
+        if (xy_full) { rows[1] = fx + lo; rows[2] = fy + lo; }
         uint8_t *alive = want_alive ? (xy_full ? R.full_alive + lo : R.slot_alive[k]) : nullptr;
         // the slot is free once its previous D2H finished
         if (c >= nslots) PXF_CUDA(cudaStreamWaitEvent(R.s_in, R.out_done[k], 0));
@@ -136,7 +146,7 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     PXF_CUDA(cudaStreamSynchronize(R.s_run));
 
     if (want_hpd) {
-        const double *hx = R.full_x, *hy = R.full_y;
+        const double *hx = fx, *hy = fy;
         int64_t hn = num;
         double *cx = nullptr, *cy = nullptr;
         if (want_alive) {
@@ -151,7 +161,7 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
                     cudaFree(scr); if (cx) cudaFree(cx);
                     set_error("pxf_host_trace_program: out of device memory"); return PXF_ERR_NOMEM;
                 }
-                const double *in2[2] = {R.full_x, R.full_y};
+                const double *in2[2] = {fx, fy};
                 double *out2[2] = {cx, cy};
                 rc = pxf_compact_scatter(in2, out2, 2, R.full_alive, num, scr, reinterpret_cast<pxf_stream_t>(R.s_run));
                 cudaStreamSynchronize(R.s_run);

@@ -330,7 +330,7 @@ static int launch_op(RowPtrs P, int64_t num, const uint8_t *mask, const double *
 {
     if (num < 0) { set_error("num < 0"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
-    if (num == 0) return PXF_OK;
+    if (num == 0) return PXF_OK;   // empty bundle: nothing to do (pointers may be NULL)
     const unsigned used = Op::LOAD | Op::STORE;
     bool aligned = true;
     for (int k = 0; k < 10; k++) {

@@ -26,6 +26,7 @@ static_assert(sizeof(WolterSineP) <= FOP_PARAM_DOUBLES * 8, "WolterSineP does no
 
 // pxf_fused.cu
 int build_program(FusedProgram &fp, const pxf_op *ops, int nops);
-int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s);
+int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s,
+                   double *const rays_out[10] = nullptr);
 
 }  // namespace pxf

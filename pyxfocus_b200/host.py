@@ -13,12 +13,14 @@ from . import _lib
 from .program import Program
 
 
-def trace(rays, prog, write_back=True, hpd=False, alive=False):
+def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
     """Run ``prog`` (a ``Program``) on a host bundle.
 
     rays : list of ten 1-D contiguous float64 numpy arrays (or torch CPU tensors, e.g.
            pinned), mutated in place like the Fortran does.  Entries the program neither
            reads nor writes may be None.
+    keep_xy : optional pair of CUDA float64 tensors (length num) that receive the final x,y
+           and stay resident on the device (e.g. for ``dist.hpd`` over a sharded bundle).
     Returns a dict with ``hpd`` (if requested), ``alive`` (uint8 flags, if requested and the
     program vignettes) and ``alive_count``.
     """
@@ -56,7 +58,9 @@ def trace(rays, prog, write_back=True, hpd=False, alive=False):
     rc = _lib.lib().pxf_host_trace_program(tab, num, ops, len(prog), 1 if write_back else 0,
                                            ctypes.byref(h) if hpd else None,
                                            flags.ctypes.data if flags is not None else None,
-                                           ctypes.byref(cnt))
+                                           ctypes.byref(cnt),
+                                           keep_xy[0].data_ptr() if keep_xy is not None else None,
+                                           keep_xy[1].data_ptr() if keep_xy is not None else None)
     _lib.check(rc)
     out = {"alive_count": int(cnt.value)}
     if hpd:

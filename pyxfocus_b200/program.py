@@ -132,9 +132,11 @@ class Program:
                 arr[k].p[j] = v
         return arr
 
-    def run(self, rays, alive=None):
+    def run(self, rays, alive=None, out=None):
         """Execute on a bundle (list of ten CUDA fp64 rows).  Returns the ``alive`` uint8
-        tensor when the program contains a vignette predicate (allocated if not given)."""
+        tensor when the program contains a vignette predicate (allocated if not given).
+        ``out``: optional second bundle -- rows are read from ``rays`` and every row the program
+        touches is written to ``out``; ``rays`` is left untouched."""
         if not self.ops:
             return alive
         if len(self.ops) > MAX_OPS:
@@ -143,8 +145,8 @@ class Program:
             head.ops, tail.ops = self.ops[:MAX_OPS], self.ops[MAX_OPS:]
             if head.has_vignette() or tail.has_vignette():
                 raise ValueError("programs with vignette predicates are limited to %d ops" % MAX_OPS)
-            head.run(rays)
-            return tail.run(rays)
+            head.run(rays, out=out)
+            return tail.run(out if out is not None else rays)
         dev = rays[1].device
         num = rays[1].shape[0]
         for r in rays:
@@ -155,10 +157,13 @@ class Program:
             alive = torch.empty(num, dtype=torch.uint8, device=dev)
         ptrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in rays])
         ops = self.c_ops()
+        ap = alive.data_ptr() if alive is not None else None
         with torch.cuda.device(dev):
-            rc = _lib.lib().pxf_trace_program(ptrs, num, ops, len(self.ops),
-                                              alive.data_ptr() if alive is not None else None,
-                                              stream_ptr(dev))
+            if out is None:
+                rc = _lib.lib().pxf_trace_program(ptrs, num, ops, len(self.ops), ap, stream_ptr(dev))
+            else:
+                optrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in out])
+                rc = _lib.lib().pxf_trace_program_to(ptrs, optrs, num, ops, len(self.ops), ap, stream_ptr(dev))
         _lib.check(rc)
         return alive
 

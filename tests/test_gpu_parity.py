@@ -1,0 +1,732 @@
+"""GPU parity tests: every CUDA routine (through the C ABI, via the f2py-shaped modules)
+against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star / SURVEY.md 7 "FMA"):
+  * routines whose per-ray arithmetic is + - * / sqrt only are BIT-EXACT against the oracle
+    (libpxf is built -fmad=false, the oracle -ffp-contract=off; scalar-only libm calls are
+    made on the host by the same glibc);
+  * routines that call libm per ray (atan2/sin/cos/asin/acos/pow) agree to 1e-12: positions
+    relative to the system length scale, unit-vector components absolutely;
+  * surviving-ray index sets are bit-exact; HPD within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from util import (assert_bit_equal, assert_close, chains, copy, of, pyref, random_bundle, rows_of,
+                  run_steps_gpu, steps_to_program, to_dev, to_host)
+
+pytestmark = pytest.mark.gpu
+
+N = 50_001          # odd: exercises the double2 tail
+
+
+@pytest.fixture(scope="module")
+def pxf():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import pyxfocus_b200
+    return pyxfocus_b200
+
+
+def wolter_inputs(n=N, seed=0):
+    rays = chains.wolter1_source(n, seed=seed, dphi=1.0)
+    pyref.transform(rays, 0, 0, -8400., 0, 0, 0)
+    return rays
+
+
+def after_primary(n=N, seed=0):
+    rays = wolter_inputs(n, seed)
+    of.woltsurf.wolterprimary(*rays[1:], 220., 8400., 1.)
+    of.transformationsf.reflect(*rays[4:])
+    return rays
+
+
+# --------------------------------------------------------------------------- per routine
+ALGEBRAIC = [
+    ("transform", lambda: random_bundle(N, 1), [("transform", (1.5, -2.5, 100., .1, -.2, .3))]),
+    ("transform_translate_only", lambda: random_bundle(N, 2), [("transform", (0., 0., 8400., 0., 0., 0.))]),
+    ("itransform", lambda: random_bundle(N, 3), [("itransform", (1.5, -2.5, 100., .1, -.2, .3))]),
+    ("reflect", lambda: random_bundle(N, 4), [("reflect", ())]),
+    ("flat", lambda: random_bundle(N, 5), [("flat", ())]),
+    ("flatopd", lambda: random_bundle(N, 6), [("flatopd", (1.5,))]),
+    ("wolterprimary", wolter_inputs, [("wolterprimary", (220., 8400., 1.))]),
+    ("wolterprimary_psi", wolter_inputs, [("wolterprimary", (220., 8400., 1.7))]),
+    ("wolterprimaryopd", wolter_inputs, [("wolterprimaryopd", (220., 8400., 1., 1.3))]),
+    ("woltersecondary", after_primary, [("woltersecondary", (220., 8400., 1.))]),
+    ("conic_parabola", lambda: conic_inputs(7), [("conic", (1000., -1.))]),
+    ("conic_sphere_miss", lambda: conic_inputs(8, spread=900.), [("conic", (500., 0.))]),
+    ("conicopd", lambda: conic_inputs(9), [("conicopd", (-800., .3, 1.5))]),
+    ("spocone", lambda: spo_inputs(10), [("spocone", (737., .25 * np.arctan((737. + .3025) / 12.e3)))]),
+    ("spocone_miss", lambda: random_bundle(N, 11), [("spocone", (5., .3))]),
+]
+
+
+def conic_inputs(seed, spread=30.):
+    np.random.seed(seed)
+    rays = pyref.circularbeam(spread, N)
+    rng = np.random.default_rng(seed)
+    rays[4][:] = rng.normal(0, .01, N)
+    rays[5][:] = rng.normal(0, .01, N)
+    rays[6][:] = np.sqrt(1 - rays[4] ** 2 - rays[5] ** 2)
+    rays[6][::97] = 1.0          # exercises the K=-1, |n|==1 special case (surfacesf.f95:316-317)
+    rays[4][::97] = 0.
+    rays[5][::97] = 0.
+    rays[3][:] = -50.
+    return rays
+
+
+def spo_inputs(seed):
+    np.random.seed(seed)
+    rays = pyref.subannulus(737., 737.605, .04, N, zhat=-1.)
+    pyref.transform(rays, 0, 0, -300., 0, 0, .01)
+    return rays
+
+
+@pytest.mark.parametrize("name,make,steps", ALGEBRAIC, ids=[a[0] for a in ALGEBRAIC])
+def test_algebraic_routines_bit_exact(pxf, name, make, steps):
+    cpu = make()
+    dev = to_dev(cpu)
+    chains.run_steps_cpu(cpu, steps)
+    run_steps_gpu(dev, steps)
+    assert_bit_equal(to_host(dev), cpu, what=name)
+
+
+def test_grat_bit_exact(pxf):
+    cpu = random_bundle(N, 12)
+    rng = np.random.default_rng(12)
+    order = rng.integers(-2, 3, N).astype(np.float64)
+    order[::41] = 400.          # evanescent -> zeroed direction
+    wave = rng.uniform(1e-6, 2e-6, N)
+    dev = to_dev(cpu)
+    of.transformationsf.grat(cpu[1], cpu[2], cpu[4], cpu[5], cpu[6], 1.6e-4, order, wave)
+    pxf.transformations.grat(dev, 1.6e-4, order, wave)
+    assert_bit_equal(to_host(dev), cpu, what="grat")
+
+
+LIBM = [
+    ("refract", lambda: refract_inputs(13), [("refract", (1., 1.5))], 1.),
+    ("refract_out", lambda: refract_inputs(14), [("refract", (1.5, 1.))], 1.),
+    ("radgrat", lambda: grating_inputs(15), [("radgrat", (2.4, 160. / 11832.911, -3.))], 1.2e4),
+    ("woltersine", wolter_inputs, [("woltersine", (220., 8400., 1.e-4, .05))], 8.4e3),
+    ("wsprimary", lambda: ws_inputs(16), [("wsprimary", (pyref.woltparam(220., 1.e4)[0], 1.e4, 1.))], 1.e4),
+    ("ws_pair_offaxis", lambda: ws_inputs(17), chains.ws_steps(8. / 60. * np.pi / 180.)[1:], 1.e4),
+]
+
+
+def refract_inputs(seed):
+    rays = random_bundle(N, seed)
+    # normals within ~40 deg of the direction so that both refraction senses are real
+    rng = np.random.default_rng(seed)
+    for k in range(3):
+        rays[7 + k][:] = rays[4 + k] + .4 * rng.normal(0, 1, N)
+    nrm = np.sqrt(rays[7] ** 2 + rays[8] ** 2 + rays[9] ** 2)
+    for k in range(3):
+        rays[7 + k] /= nrm
+    rays[7][::53] *= -1
+    rays[8][::53] *= -1
+    rays[9][::53] *= -1      # flipped normals (dot<0 branch)
+    rays[7][::101] = rays[4][::101]
+    rays[8][::101] = rays[5][::101]
+    rays[9][::101] = rays[6][::101]    # dot == 1 (or its neighbour): skip branch
+    return rays
+
+
+def grating_inputs(seed):
+    rng = np.random.default_rng(seed)
+    rays = random_bundle(N, seed)
+    rays[1][:] = rng.uniform(-40, 40, N)
+    rays[2][:] = 11832.911 + rng.uniform(-40, 40, N)
+    rays[4][:] = rng.normal(0, .02, N)
+    rays[5][:] = rng.normal(0, .02, N)
+    rays[6][:] = -np.sqrt(1 - rays[4] ** 2 - rays[5] ** 2)
+    return rays
+
+
+def ws_inputs(seed):
+    rays = chains.ws_source(N, seed=seed)
+    pyref.transform(rays, 0, 0, -1.e4, 0, 0, 0)
+    return rays
+
+
+@pytest.mark.parametrize("name,make,steps,scale", LIBM, ids=[a[0] for a in LIBM])
+def test_libm_routines_close(pxf, name, make, steps, scale):
+    cpu = make()
+    dev = to_dev(cpu)
+    chains.run_steps_cpu(cpu, steps)
+    run_steps_gpu(dev, steps)
+    assert_close(to_host(dev), cpu, pos_scale=scale, tol=1e-12, what=name)
+
+
+def test_ws_far_off_axis_chaotic_fringe(pxf):
+    """Beyond the graze angle ~10% of the rays never converge on the secondary (restored in
+    place) and the boundary of that set is a Newton fractal: for the few rays on it a 1-ulp
+    libm difference (CUDA vs glibc -- or one glibc vs another) changes the *discrete* outcome
+    (which root / restored or not).  Everything off that fringe must still agree to 1e-12."""
+    cpu = ws_inputs(18)
+    steps = chains.ws_steps(24. / 60. * np.pi / 180.)[1:]
+    dev = to_dev(cpu)
+    chains.run_steps_cpu(cpu, steps)
+    run_steps_gpu(dev, steps)
+    got = to_host(dev)
+    bad = np.zeros(N, bool)
+    for k in range(1, 10):
+        scale = 1.e4 if k < 4 else 1.
+        d = np.abs(got[k] - cpu[k])
+        bad |= ~((d <= 1e-12 * scale) | (np.isnan(got[k]) & np.isnan(cpu[k])))
+    print("chaotic fringe: %d of %d rays differ" % (bad.sum(), N))
+    assert bad.mean() < 2e-3
+
+
+def test_ws_cap_restores_same_rays(pxf):
+    """Rays that exhaust the 26-iteration cap are restored in place (woltsurf.f95:562-580):
+    the set of restored rays must be identical."""
+    cpu = ws_inputs(19)
+    steps = chains.ws_steps(24. / 60. * np.pi / 180.)[1:4]
+    chains.run_steps_cpu(cpu, steps)
+    dev = to_dev(cpu)
+    before = copy(cpu)
+    a = pyref.woltparam(220., 1.e4)[0]
+    of.woltsurf.wssecondary(*cpu[1:], a, 1.e4, 1.)
+    pxf.woltsurf.wssecondary(*dev[1:], a, 1.e4, 1.)
+    got = to_host(dev)
+    rest_cpu = (before[1] == cpu[1]) & (before[2] == cpu[2]) & (before[3] == cpu[3])
+    rest_gpu = (before[1] == got[1]) & (before[2] == got[2]) & (before[3] == got[3])
+    assert rest_cpu.sum() > 100, "test needs rays that hit the cap"
+    assert np.array_equal(rest_cpu, rest_gpu)
+
+
+def test_radgratw_sign_from_y(pxf):
+    cpu = grating_inputs(20)
+    cpu[2][::3] *= -1          # radgratW takes the sign of n from y (transformationsf.f95:258)
+    wave = np.random.default_rng(20).uniform(3.6, 7.2, N)
+    dev = to_dev(cpu)
+    of.transformationsf.radgratw(cpu[1], cpu[2], cpu[4], cpu[5], cpu[6], wave, 160. / 11832.911, 1.)
+    pxf.transformations.radgrat(dev, 160. / 11832.911, 1., wave)
+    assert_close(to_host(dev), cpu, pos_scale=1.2e4, what="radgratw")
+
+
+@pytest.mark.parametrize("opd", [False, True])
+def test_tracezern(pxf, opd):
+    ro, ao = chains.zernike_orders(7)
+    coeff = chains.zernike_coeff(36, 0)
+    np.random.seed(21)
+    cpu = pyref.circularbeam(60., N)
+    pyref.transform(cpu, 1., -2., -100., 1e-3, -2e-3, .3)
+    dev = to_dev(cpu)
+    if opd:
+        of.zernsurf.tracezernopd(*cpu, coeff, ro, ao, 62.5, 1.)
+        pxf.surfaces.zernsurf(dev, coeff, 62.5, rorder=ro, aorder=ao, nr=1.)
+    else:
+        of.zernsurf.tracezern(*cpu[1:], coeff, ro, ao, 62.5)
+        pxf.surfaces.zernsurf(dev, coeff, 62.5, rorder=ro, aorder=ao)
+    assert_close(to_host(dev), cpu, pos_scale=100., tol=1e-12, what="tracezern")
+
+
+def test_tracezern_high_order(pxf):
+    ro, ao = chains.zernike_orders(11)
+    coeff = chains.zernike_coeff(ro.size, 3, sigma=2e-5)
+    np.random.seed(22)
+    cpu = pyref.circularbeam(55., 20_000)
+    pyref.transform(cpu, 0, 0, -10., 0, 0, 0)
+    dev = to_dev(cpu)
+    of.zernsurf.tracezern(*cpu[1:], coeff, ro, ao, 62.5)
+    pxf.surfaces.zernsurf(dev, coeff, 62.5, rorder=ro, aorder=ao)
+    assert_close(to_host(dev), cpu, pos_scale=100., tol=1e-12, what="tracezern n<=11")
+
+
+# --------------------------------------------------------------------------- masks
+def test_masked_execution_matches_gather_scatter(pxf):
+    """ind= as an in-kernel predicate == the reference's gather -> Fortran -> scatter."""
+    rng = np.random.default_rng(23)
+    mask = rng.random(N) < .4
+    idx = np.where(mask)
+    # transform
+    cpu = random_bundle(N, 23)
+    dev = to_dev(cpu)
+    pyref.masked(of.transformationsf.transform, cpu[1:], mask, -1., 2., -3., -.1, .2, -.3)
+    pxf.transformations.transform(dev, 1., -2., 3., .1, -.2, .3, ind=mask)
+    assert_bit_equal(to_host(dev), cpu, what="transform ind=bool")
+    # reflect with an np.where tuple
+    pyref.masked(of.transformationsf.reflect, cpu[4:], idx)
+    pxf.transformations.reflect(dev, ind=idx)
+    assert_bit_equal(to_host(dev), cpu, what="reflect ind=where")
+    # flat with an integer index array
+    sel = np.arange(0, N, 3)
+    pyref.masked(of.surfacesf.flat, cpu[1:], sel)
+    pxf.surfaces.flat(dev, ind=sel)
+    assert_bit_equal(to_host(dev), cpu, what="flat ind=int")
+    # spoCone masked
+    cpu = spo_inputs(24)
+    dev = to_dev(cpu)
+    tg = .25 * np.arctan((737. + .3025) / 12.e3)
+    pyref.masked(of.woltsurf.spocone, cpu[1:], mask, 737., tg)
+    pxf.surfaces.spoCone(dev, 737., tg, ind=mask)
+    assert_bit_equal(to_host(dev), cpu, what="spoCone ind")
+
+
+def test_unaligned_rows_take_scalar_path(pxf):
+    """Rows that are not 16-byte aligned (odd offsets into a larger tensor) must give the
+    same bits as the double2 path."""
+    import torch
+    cpu = wolter_inputs(10_001, 25)
+    big = torch.zeros(10, 10_004, dtype=torch.float64, device="cuda")
+    dev = [big[i, 1:10_002] for i in range(10)]          # 8-byte offset -> misaligned
+    for i in range(10):
+        dev[i].copy_(torch.from_numpy(cpu[i]))
+    assert dev[1].data_ptr() % 16 == 8
+    steps = chains.wolter1_steps()[1:]
+    chains.run_steps_cpu(cpu, steps)
+    dev_c = [d.contiguous() for d in dev]                # 1-D slices are already contiguous views
+    run_steps_gpu(dev_c, steps)
+    assert_bit_equal([d.cpu().numpy() for d in dev_c], cpu, what="unaligned")
+
+
+# --------------------------------------------------------------------------- fused program
+def test_fused_program_bit_identical_to_per_routine(pxf):
+    cpu = chains.wolter1_source(N, seed=26)
+    steps = chains.wolter1_steps()
+    a = to_dev(cpu)
+    b = to_dev(cpu)
+    run_steps_gpu(a, steps)
+    steps_to_program(steps).run(b)
+    chains.run_steps_cpu(cpu, steps)
+    ha, hb = to_host(a), to_host(b)
+    assert_bit_equal(hb, ha, what="fused vs per-routine")
+    assert_bit_equal(hb, cpu, what="fused vs oracle")
+
+
+def test_fused_context_records_reference_calls(pxf):
+    cpu = chains.wolter1_source(20_000, seed=27)
+    dev = to_dev(cpu)
+    before = pxf.launch_count()
+    with pxf.fused(dev):
+        pxf.transformations.transform(dev, 0, 0, -8400., 0, 0, 0)
+        pxf.surfaces.wolterprimary(dev, 220., 8400.)
+        pxf.transformations.reflect(dev)
+        pxf.surfaces.woltersecondary(dev, 220., 8400.)
+        pxf.transformations.reflect(dev)
+        pxf.surfaces.flat(dev)
+    assert pxf.launch_count() - before == 1, "the whole chain must be ONE kernel launch"
+    chains.run_steps_cpu(cpu, chains.wolter1_steps())
+    assert_bit_equal(to_host(dev), cpu, what="fused context")
+
+
+def test_fused_all_opcodes(pxf):
+    """Every opcode of the fused interpreter against its per-routine kernel (bit-identical:
+    same device code) on chains that keep the rays physical."""
+    a0 = pyref.woltparam(220., 1.e4)[0]
+    cases = {
+        "ws": (lambda: ws_inputs(28), chains.ws_steps(6. / 60. * np.pi / 180.)[1:] + [("flatopd", (1.1,))]),
+        "conic": (lambda: conic_inputs(29), [("conic", (1000., -1.)), ("refract", (1., 1.5)),
+                                            ("transform", (0., 0., -10., 0., 0., 0.)),
+                                            ("conicopd", (-800., .3, 1.5)), ("refract", (1.5, 1.)),
+                                            ("itransform", (.3, -.2, 5., .01, .02, -.03)), ("flat", ())]),
+        "spo": (lambda: spo_inputs(30), [("spocone", (737., .25 * np.arctan((737. + .3025) / 12.e3))), ("reflect", ()),
+                                         ("spocone", (737., .75 * np.arctan((737. + .3025) / 12.e3))), ("reflect", ()),
+                                         ("transform", (0., -11832.911, 11000., 0., 0., 0.)), ("flat", ()),
+                                         ("radgrat", (2.4, 160. / 11832.911, -3.))]),
+        "sine": (wolter_inputs, [("woltersine", (220., 8400., 1e-4, .05)), ("reflect", ()),
+                                 ("wolterprimaryopd", (220., 8400., 1., 1.))]),
+        "wsprim": (lambda: ws_inputs(31), [("wsprimary", (a0, 1.e4, 1.))]),
+    }
+    for name, (make, steps) in cases.items():
+        cpu = make()
+        a, b = to_dev(cpu), to_dev(cpu)
+        run_steps_gpu(a, steps)
+        steps_to_program(steps).run(b)
+        assert_bit_equal(to_host(b), to_host(a), what="fused[%s]" % name)
+
+
+def test_fused_vignette_predicates(pxf):
+    """In-program vignetting: rays stop at the predicate; alive flags == the masks the
+    reference scripts build (examples/axro/slf.py:145-147)."""
+    cpu = chains.wolter1_source(N, seed=32, dphi=1.2)
+    dev = to_dev(cpu)
+    prog = (pxf.Program().transform(0, 0, 8400., 0, 0, 0).wolterprimary(220., 8400., 1.).reflect()
+            .vignette_box(3, 8426., 8526.).vignette_abs(2, 50.)
+            .woltersecondary(220., 8400., 1.).reflect().vignette_mag().flat())
+    alive = prog.run(dev).cpu().numpy().astype(bool)
+    # oracle: same chain with numpy masks
+    chains.run_steps_cpu(cpu, chains.wolter1_steps()[:3])
+    keep = (cpu[3] > 8426.) & (cpu[3] < 8526.) & (np.abs(cpu[2]) < 50.)
+    assert 0 < keep.sum() < N
+    assert np.array_equal(alive, keep), "surviving-ray set differs"
+    surv = pyref.vignette(cpu, ind=keep)
+    chains.run_steps_cpu(surv, chains.wolter1_steps()[3:])
+    got = pxf.transformations.vignette(dev, ind=alive)
+    assert_bit_equal(to_host(got), surv, what="fused vignette survivors")
+
+
+# --------------------------------------------------------------------------- vignette / compaction
+def test_vignette_default_and_mask(pxf, golden):
+    g = golden("spo_grating")
+    for src_key, out_key, ind in (("after_evan", "vignetted_evan", None), ("after_miss", "vignetted", None),
+                                  ("after_miss", "vignetted_mask", g["keep"])):
+        dev = to_dev(rows_of(g[src_key]))
+        out = pxf.transformations.vignette(dev, ind=ind)
+        assert_bit_equal(to_host(out), rows_of(g[out_key]), what=out_key)
+
+
+def test_vignette_index_sets_and_order(pxf):
+    import torch
+    rng = np.random.default_rng(33)
+    for n in (1, 31, 32, 33, 2047, 2048, 2049, 300_001):
+        cpu = random_bundle(n, 33)
+        kill = rng.random(n) < .37
+        for k in (4, 5, 6):
+            cpu[k][kill] = 0.
+        cpu[6][::11] = np.nan
+        dev = to_dev(cpu)
+        want = pyref.vignette(cpu)
+        got = pxf.transformations.vignette(dev)
+        assert_bit_equal(to_host(got), want, what="vignette n=%d" % n)
+        flags = torch.from_numpy((cpu[4] ** 2 + cpu[5] ** 2 + cpu[6] ** 2 > .1).astype(np.uint8)).cuda()
+        idx = pxf.transformations.surviving_indices(flags).cpu().numpy()
+        assert np.array_equal(idx, np.where(cpu[4] ** 2 + cpu[5] ** 2 + cpu[6] ** 2 > .1)[0])
+    # integer index arrays (np.where output, repeats, negative) behave like numpy fancy indexing
+    cpu = random_bundle(1000, 34)
+    dev = to_dev(cpu)
+    sel = np.array([5, 5, 999, 0, -1, 17])
+    assert_bit_equal(to_host(pxf.transformations.vignette(dev, ind=sel)), pyref.vignette(cpu, ind=sel))
+    assert pxf.transformations.vignette(dev, ind=np.zeros(1000, bool))[1].shape[0] == 0
+
+
+# --------------------------------------------------------------------------- analyses
+def test_analyses_match_numpy(pxf, golden):
+    g = golden("wolter1")
+    rays = rows_of(g["rays_out"])
+    dev = to_dev(rays)
+    A = pxf.analyses
+    w = g["weights"]
+    cx, cy = A.centroid(dev)
+    assert abs(cx - g["centroid"][0]) <= 1e-12 * 220 and abs(cy - g["centroid"][1]) <= 1e-12 * 220
+    assert A.rmsCentroid(dev) == pytest.approx(float(g["rms"]), rel=1e-9)
+    assert A.hpd(dev) == pytest.approx(float(g["hpd"]), rel=1e-9)
+    assert A.hpd(dev, weights=w) == pytest.approx(float(g["hpd_w"]), rel=1e-9)
+    assert A.rmsCentroid(dev, weights=w) == pytest.approx(float(g["rms_w"]), rel=1e-9)
+    r, cdf = A.rhocdf(dev, weights=w)
+    assert np.allclose(r.cpu().numpy(), g["rhocdf_r"], rtol=1e-9, atol=0)
+    assert np.allclose(cdf.cpu().numpy(), g["rhocdf_cdf"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 1000, 1001, 65_536, 1_000_003])
+def test_hpd_exact_order_statistics(pxf, n):
+    """Unweighted hpd == 2*np.median(r): the select must return the exact middle order
+    statistics (even n: mean of the two)."""
+    rng = np.random.default_rng(n)
+    cpu = random_bundle(n, n)
+    cpu[1][:] = rng.normal(0, 1e-3, n) + 5.
+    cpu[2][:] = rng.standard_cauchy(n) * 1e-3 - 2.
+    if n > 100:
+        cpu[1][: n // 3] = cpu[1][0]          # many exact ties
+        cpu[2][: n // 3] = cpu[2][0]
+    dev = to_dev(cpu)
+    want = pyref.hpd(cpu)
+    got = pxf.analyses.hpd(dev)
+    assert got == pytest.approx(want, rel=1e-9)
+    # and bit-exact against the median of the radii the device itself computes
+    r = pxf.analyses.rho(dev, cent=True).cpu().numpy()
+    assert got == 2. * np.median(r)
+
+
+def test_hpd_nan_propagates(pxf):
+    cpu = random_bundle(1001, 35)
+    cpu[1][17] = np.nan
+    assert np.isnan(pxf.analyses.hpd(to_dev(cpu)))
+
+
+def test_weighted_hpd_and_sort(pxf):
+    import torch
+    n = 200_003
+    rng = np.random.default_rng(36)
+    cpu = random_bundle(n, 36)
+    w = rng.uniform(.1, 2., n)
+    dev = to_dev(cpu)
+    assert pxf.analyses.hpd(dev, weights=w) == pytest.approx(pyref.hpd(cpu, weights=w), rel=1e-9)
+    keys = torch.from_numpy(rng.normal(0, 1, n)).cuda()
+    keys[::1000] = float("inf")
+    keys[5::1000] = float("-inf")
+    keys[7::5000] = float("nan")
+    ks, idx = pxf.analyses.argsort(keys)
+    kc, kn = keys.cpu().numpy(), ks.cpu().numpy()
+    assert np.array_equal(kn, np.sort(kc), equal_nan=True)
+    assert np.array_equal(kc[idx.cpu().numpy()], kn, equal_nan=True)
+    # stability: equal keys keep their original order
+    ii = idx.cpu().numpy()
+    same = kn[1:] == kn[:-1]
+    assert (ii[1:][same] > ii[:-1][same]).all()
+
+
+def test_image_plane_and_focus(pxf, golden):
+    g = golden("ws_offaxis")
+    cpu = rows_of(g["after_secondary"])
+    dev = to_dev(cpu)
+    dz = pxf.analyses.analyticImagePlane(dev)
+    assert dz == pytest.approx(float(g["dz_analytic"]), rel=1e-9)
+    f = pxf.surfaces.focusI(dev)
+    assert f == pytest.approx(float(g["focus"]), rel=1e-9)
+    assert_close(to_host(dev), rows_of(g["rays_out"]), pos_scale=1.e4, tol=1e-11, what="focusI rays")
+    assert pxf.analyses.hpd(dev) == pytest.approx(float(g["hpd"]), rel=1e-9)
+    assert pxf.analyses.rmsCentroid(dev) == pytest.approx(float(g["rms"]), rel=1e-9)
+    # findimageplane (parity unpinned): brute-force scan with the oracle agrees on the grid point
+    cpu = rows_of(g["rays_out"])
+    dev = to_dev(cpu)
+    pyref.transform(cpu, 0, 0, 3.3, 0, 0, 0)
+    of.surfacesf.flat(*cpu[1:])
+    pxf.transformations.transform(dev, 0, 0, 3.3, 0, 0, 0)
+    pxf.surfaces.flat(dev)
+    best = pxf.analyses.findimageplane(dev, 20., 101)
+    scan = np.linspace(-20., 20., 101)
+    rms = []
+    for dzs in scan:
+        t = copy(cpu)
+        pyref.transform(t, 0, 0, dzs, 0, 0, 0)
+        of.surfacesf.flat(*t[1:])
+        rms.append(pyref.rmsCentroid(t))
+    assert best == pytest.approx(scan[int(np.argmin(rms))], abs=1e-9)
+    assert abs(best - (-3.3)) <= .4 + 1e-9
+
+
+# --------------------------------------------------------------------------- sources
+def test_sources_from_numpy_seeds(pxf):
+    for name, args in (("subannulus", (220., 220.6, 1.3, 10_001, -1.)), ("annulus", (200., 230., 10_001, 1.)),
+                       ("circularbeam", (12.5, 10_001)), ("pointsource", (.03, 10_001))):
+        np.random.seed(37)
+        want = getattr(pyref, name)(*args)
+        np.random.seed(37)
+        got = to_host(getattr(pxf.sources, name)(*args))
+        # device sqrt is exact, sin/cos agree with glibc to an ulp or two
+        assert_close(got, want, pos_scale=max(1., abs(args[0])), tol=2e-15, what=name)
+
+
+def test_sources_philox_sharding(pxf):
+    """Device RNG: shards generated with first= offsets concatenate to the single-GPU stream."""
+    whole = to_host(pxf.sources.subannulus(220., 220.6, 1., 10_000, zhat=-1., rng="philox", seed=5))
+    a = to_host(pxf.sources.subannulus(220., 220.6, 1., 4_000, zhat=-1., rng="philox", seed=5, first=0))
+    b = to_host(pxf.sources.subannulus(220., 220.6, 1., 6_000, zhat=-1., rng="philox", seed=5, first=4_000))
+    assert_bit_equal([np.concatenate([p, q]) for p, q in zip(a, b)], whole, what="philox shards")
+    r = np.hypot(whole[1], whole[2])
+    assert r.min() >= 220. - 1e-9 and r.max() <= 220.6 + 1e-9
+    u = (r ** 2 - 220. ** 2) / (220.6 ** 2 - 220. ** 2)
+    assert abs(u.mean() - .5) < .02 and abs(np.arctan2(whole[2], whole[1]).mean()) < .02
+    other = to_host(pxf.sources.subannulus(220., 220.6, 1., 10_000, zhat=-1., rng="philox", seed=6))
+    assert not np.array_equal(other[1], whole[1])
+
+
+# --------------------------------------------------------------------------- golden fixtures
+def test_golden_wolter1(pxf, golden):
+    g = golden("wolter1")
+    # sources from the stored uniforms
+    got = to_host(pxf.sources.subannulus(220., 220.6, 2 * np.pi, 4000, zhat=-1., uniforms=(g["u1"], g["u2"])))
+    assert_close(got, rows_of(g["rays_in"]), pos_scale=220., tol=2e-15, what="golden source")
+    dev = to_dev(rows_of(g["rays_in"]))
+    T, S = pxf.transformations, pxf.surfaces
+    T.transform(dev, 0, 0, -8400., 0, 0, 0)
+    S.wolterprimary(dev, 220., 8400.)
+    assert_bit_equal(to_host(dev), rows_of(g["after_primary"]), what="golden after_primary")
+    T.reflect(dev)
+    S.woltersecondary(dev, 220., 8400.)
+    T.reflect(dev)
+    S.flat(dev)
+    assert_bit_equal(to_host(dev), rows_of(g["rays_out"]), what="golden rays_out")
+    assert pxf.analyses.hpd(dev) == pytest.approx(float(g["hpd"]), rel=1e-9)
+
+
+def test_golden_ws(pxf, golden):
+    g = golden("ws_offaxis")
+    dev = to_dev(rows_of(g["rays_in"]))
+    T, S = pxf.transformations, pxf.surfaces
+    with pxf.fused(dev):
+        T.transform(dev, 0, 0, -1.e4, 0, 0, 0)
+        S.wsPrimary(dev, 220., 1.e4, 1.)
+    dev[4].add_(np.sin(float(g["theta"])))                 # rays[4] = rays[4] + sin(offaxis)
+    dev[6].copy_(-(1. - dev[4] ** 2).sqrt())               # rays[6] = -sqrt(1-rays[4]**2)
+    T.reflect(dev)
+    S.wsSecondary(dev, 220., 1.e4, 1.)
+    T.reflect(dev)
+    assert_close(to_host(dev), rows_of(g["after_secondary"]), pos_scale=1.e4, what="golden ws after_secondary")
+    g2 = golden("ws_cap")
+    dev = to_dev(rows_of(g2["rays_in"]))
+    T.transform(dev, 0, 0, -1.e4, 0, 0, 0)
+    S.wsPrimary(dev, 220., 1.e4, 1.)
+    pxf.Program().kick(np.sin(float(g2["theta"])), 0., -1.).run(dev)
+    T.reflect(dev)
+    fail = S.wsSecondary(dev, 220., 1.e4, 1., check=True).cpu().numpy()
+    assert np.array_equal(fail, g2["restored"]), "set of non-converged (restored) rays differs"
+    assert_close(to_host(dev), rows_of(g2["rays_out"]), pos_scale=1.e4, what="golden ws_cap")
+
+
+def test_golden_zernike(pxf, golden):
+    g = golden("zernike")
+    T, S = pxf.transformations, pxf.surfaces
+    dev = to_dev(rows_of(g["rays_in"]))
+    T.transform(dev, 0, 0, -100., 0, 0, 0)
+    S.zernsurf(dev, g["coeff"], float(g["rad"]), rorder=g["rorder"], aorder=g["aorder"], nr=1.)
+    assert_close(to_host(dev), rows_of(g["after_zern"]), pos_scale=100., what="golden after_zern")
+    T.reflect(dev)
+    T.transform(dev, 0, 0, 50., 0, 0, 0)
+    S.flat(dev, nr=1.)
+    assert_close(to_host(dev), rows_of(g["rays_out"]), pos_scale=150., what="golden zern rays_out")
+    dev = to_dev(rows_of(g["rays_in2"]))
+    T.transform(dev, 1., -2., -100., 1e-3, -2e-3, .3)
+    S.zernsurf(dev, g["coeff"], float(g["rad"]), rorder=g["rorder"], aorder=g["aorder"])
+    assert_close(to_host(dev), rows_of(g["rays_out2"]), pos_scale=100., what="golden zern rays_out2")
+
+
+def test_golden_spo_grating(pxf, golden):
+    g = golden("spo_grating")
+    T, S = pxf.transformations, pxf.surfaces
+    R0, F = float(g["R0"]), float(g["F"])
+    dev = to_dev(rows_of(g["rays_in"]))
+    T.transform(dev, 0, 0, 0, 0, 0, .01)
+    S.spoPrimary(dev, R0, F)
+    T.reflect(dev)
+    S.spoSecondary(dev, R0, F)
+    T.reflect(dev)
+    assert_bit_equal(to_host(dev), rows_of(g["after_spo"]), what="golden after_spo")
+    T.transform(dev, 0, 0, -(F - 200.), 0, 0, 0)
+    T.transform(dev, 0., 0, 0, 0, 0, 0)
+    S.flat(dev)
+    T.transform(dev, 0, 11832.911, 0, 0, 0, 0)
+    mask = g["mask"]
+    T.reflect(dev, ind=mask)
+    T.radgrat(dev, 160. / 11832.911, -3, 2.4, ind=mask)
+    T.radgrat(dev, 160. / 11832.911, 1, g["wave"], ind=~mask)
+    assert_close(to_host(dev), rows_of(g["after_grat"]), pos_scale=1.2e4, what="golden after_grat")
+    T.radgrat(dev, 160. / 11832.911, 150, 2.4, ind=g["evan"])
+    assert_close(to_host(dev), rows_of(g["after_evan"]), pos_scale=1.2e4, what="golden after_evan (NaN pattern)")
+
+
+def test_golden_misc(pxf, golden):
+    g = golden("misc")
+    T, S = pxf.transformations, pxf.surfaces
+    dev = to_dev(rows_of(g["rays_in"]))
+    T.transform(dev, 0, 0, -500., 0, 0, 0)
+    S.conic(dev, 1000., -1.)
+    assert_bit_equal(to_host(dev), rows_of(g["after_conic"]), what="golden after_conic")
+    T.refract(dev, 1., 1.5)
+    assert_close(to_host(dev), rows_of(g["after_refract"]), pos_scale=500., what="golden after_refract")
+    T.transform(dev, 0, 0, 10., 0, 0, 0)
+    S.conic(dev, -800., .3, nr=1.5)
+    assert_close(to_host(dev), rows_of(g["after_conicopd"]), pos_scale=500., what="golden after_conicopd")
+    T.refract(dev, 1.5, 1.)
+    T.itransform(dev, .3, -.2, 5., .01, .02, -.03)
+    assert_close(to_host(dev), rows_of(g["after_itransform"]), pos_scale=500., what="golden after_itransform")
+    S.flat(dev, ind=g["sel"])
+    assert_close(to_host(dev), rows_of(g["after_flat_ind"]), pos_scale=500., what="golden after_flat_ind")
+    T.grat(dev, 160.e-6, g["grat_order"], g["grat_wave"] * 1.e-6)
+    assert_close(to_host(dev), rows_of(g["after_grat"]), pos_scale=500., what="golden after_grat")
+    dev = to_dev(rows_of(g["rays_in2"]))
+    T.transform(dev, 0, 0, -8400., 0, 0, 0)
+    S.woltersine(dev, 220., 8400., 1.e-4, 1. / 20.)
+    assert_close(to_host(dev), rows_of(g["after_woltersine"]), pos_scale=8.4e3, what="golden after_woltersine")
+
+
+# --------------------------------------------------------------------------- edge cases / errors
+def test_empty_and_tiny_bundles(pxf):
+    import torch
+    for n in (0, 1, 2, 3):
+        cpu = wolter_inputs(max(n, 1), 38)
+        cpu = [r[:n].copy() for r in cpu]
+        dev = to_dev(cpu) if n else [torch.empty(0, dtype=torch.float64, device="cuda") for _ in range(10)]
+        steps = chains.wolter1_steps()[1:]
+        if n:
+            chains.run_steps_cpu(cpu, steps)
+        run_steps_gpu(dev, steps)
+        steps_to_program(steps).run(to_dev(cpu) if n else dev)
+        assert_bit_equal(to_host(dev), cpu, what="n=%d" % n)
+    empty = [torch.empty(0, dtype=torch.float64, device="cuda") for _ in range(10)]
+    assert pxf.transformations.vignette(empty)[1].shape[0] == 0
+    assert np.isnan(pxf.analyses.hpd(empty))
+
+
+def test_f2py_style_argument_errors(pxf):
+    import torch
+    good = to_dev(random_bundle(100, 39))
+    T = pxf.transformationsf
+    with pytest.raises(ValueError):
+        T.reflect(good[4].float(), *good[5:])                       # wrong dtype
+    with pytest.raises(ValueError):
+        T.reflect(good[4][::2], *good[5:])                          # non-contiguous
+    with pytest.raises(ValueError):
+        T.reflect(good[4][:50].contiguous(), *good[5:])             # length mismatch
+    with pytest.raises(ValueError):
+        T.reflect(good[4].cpu(), *good[5:])                         # CPU tensor
+    with pytest.raises(pxf.PxfError):
+        pxf.zernsurf.tracezern(*good[1:], np.zeros(3), [0, 1, 5], [0, 1, 1], 10.)   # n too high for 3 terms
+    with pytest.raises((pxf.PxfError, ValueError)):
+        pxf.Program().add(99).run(good)                             # unknown opcode
+    with pytest.raises(NotImplementedError):
+        pxf.surfaces.zernsurf(good, np.zeros(3), 10.)               # un-vendored default ordering
+    assert torch.cuda.is_available()
+
+
+def test_numpy_arrays_are_accepted_in_place(pxf):
+    """Literal drop-in: the f2py-shaped modules also take the reference's host numpy arrays and
+    mutate them in place (staged through the device)."""
+    cpu = wolter_inputs(5_001, 40)
+    ref = copy(cpu)
+    pxf.woltsurf.wolterprimary(*cpu[1:], 220., 8400., 1.)
+    pxf.transformationsf.reflect(*cpu[4:])
+    of.woltsurf.wolterprimary(*ref[1:], 220., 8400., 1.)
+    of.transformationsf.reflect(*ref[4:])
+    assert_bit_equal(cpu, ref, what="numpy in place")
+
+
+# --------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("n", [20_000_000])
+def test_full_size_properties(pxf, n):
+    """At a BASELINE-scale bundle the oracle is too slow; check size-independent properties:
+    rays land ON the prescription surfaces (conicsolve closed forms), the fused chain focuses
+    to the same HPD as the oracle's sample, transform/itransform and double reflection are
+    identities to rounding, compaction keeps exactly the flagged rays in order, the sort is
+    sorted and a permutation, and the select equals torch's own median."""
+    import torch
+    from pyxfocus_b200 import conicsolve as con
+    S, T, A = pxf.surfaces, pxf.transformations, pxf.analyses
+    rays = pxf.sources.subannulus(220., 220.6, 2 * np.pi, n, zhat=-1., rng="philox", seed=1)
+    with pxf.fused(rays):
+        T.transform(rays, 0, 0, -8400., 0, 0, 0)
+        S.wolterprimary(rays, 220., 8400.)
+    r = torch.sqrt(rays[1] ** 2 + rays[2] ** 2).cpu().numpy()
+    assert np.abs(r - con.primrad(rays[3].cpu().numpy(), 220., 8400.)).max() <= 1e-12 * 220.
+    with pxf.fused(rays):
+        T.reflect(rays)
+        S.woltersecondary(rays, 220., 8400.)
+    r = torch.sqrt(rays[1] ** 2 + rays[2] ** 2).cpu().numpy()
+    assert np.abs(r - con.secrad(rays[3].cpu().numpy(), 220., 8400.)).max() <= 1e-10 * 220.
+    nrm = (rays[7] ** 2 + rays[8] ** 2 + rays[9] ** 2).sqrt()
+    assert float((nrm - 1).abs().max()) <= 4e-16
+    keep = copy_dev(rays)
+    T.reflect(rays)
+    T.reflect(rays)                                  # same normal twice = identity to rounding
+    for k in (4, 5, 6):
+        assert float((rays[k] - keep[k]).abs().max()) <= 1e-15
+    T.transform(rays, 1., 2., 3., .1, .2, .3)
+    T.itransform(rays, 1., 2., 3., .1, .2, .3)
+    for k in range(1, 10):
+        assert float((rays[k] - keep[k]).abs().max()) <= 1e-12 * (8.5e3 if k < 4 else 1.)
+    rays = keep
+    with pxf.fused(rays):
+        T.reflect(rays)
+        S.flat(rays)
+    h = A.hpd(rays)
+    cpu = chains.wolter1_source(100_000, 0)
+    assert h == pytest.approx(chains.wolter1_cpu(cpu), rel=.05)      # same optics, different sample
+    rad = A.rho(rays, cent=True)
+    assert h == 2. * float(torch.median(rad)) or h == pytest.approx(2. * float(rad.median()), rel=1e-6)
+    srt = torch.sort(rad).values
+    k0, k1 = (n - 1) // 2, n // 2
+    assert h == float(srt[k0] + srt[k1])             # 2 * (a+b)/2, exact
+    ks, idx = A.argsort(rad)
+    assert torch.equal(ks, srt)
+    assert torch.equal(torch.sort(idx).values, torch.arange(n, device="cuda"))
+    flags = (rays[1] > 0) & (rays[2].abs() < 1e-5)
+    out = T.vignette(rays, ind=flags)
+    assert out[1].shape[0] == int(flags.sum())
+    assert torch.equal(out[1], rays[1][flags]) and torch.equal(out[9], rays[9][flags])
+
+
+def copy_dev(rays):
+    import pyxfocus_b200
+    return pyxfocus_b200.transformations.copy_rays(rays)

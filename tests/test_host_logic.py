@@ -1,0 +1,97 @@
+"""Host-side logic that needs no GPU: program recording, mask conversion, sharding, 4x4
+coordinate bookkeeping, argument validation."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_program_records_reference_calls_with_negated_transform_args():
+    import pyxfocus_b200 as pxf
+    from pyxfocus_b200.program import OP, recorder_for
+    rays = [torch.zeros(4, dtype=torch.float64) for _ in range(10)]     # never executed
+    with pytest.raises(Exception):
+        with pxf.fused(rays):
+            pxf.transformations.transform(rays, 1., 2., 3., .1, .2, .3)
+            pxf.surfaces.wolterprimary(rays, 220., 8400.)
+            pxf.transformations.reflect(rays)
+            pxf.surfaces.wsPrimary(rays, 220., 1.e4, 1.)
+            pxf.surfaces.flat(rays, nr=1.5)
+            prog = recorder_for(rays)
+            assert [c for c, _ in prog.ops] == [OP["TRANSFORM"], OP["WOLTERPRIMARY"], OP["REFLECT"],
+                                                OP["WSPRIMARY"], OP["FLATOPD"]]
+            assert prog.ops[0][1] == [-1., -2., -3., -.1, -.2, -.3]     # transformations.py:29
+            assert prog.ops[1][1] == [220., 8400., 1.]
+            assert prog.ops[3][1][0] == pytest.approx(.25 * np.arctan(220. / 1.e4))   # alpha from woltparam
+            raise KeyError("stop before the (GPU) flush")
+    assert recorder_for(rays) is None                                    # context cleaned up
+
+
+def test_program_limits():
+    import pyxfocus_b200 as pxf
+    p = pxf.Program()
+    with pytest.raises(ValueError):
+        p.add(1, *range(7))
+    p.vignette_box(3, 1., 2.)
+    assert p.has_vignette() and len(p) == 1
+    ops = p.c_ops()
+    assert ops[0].code == 18 and list(ops[0].p)[:3] == [3., 1., 2.]
+
+
+def test_mask_conversion():
+    from pyxfocus_b200._call import to_mask
+    cpu = torch.device("cpu")
+    m = np.array([True, False, True, False, False])
+    assert to_mask(m, 5, cpu).tolist() == [1, 0, 1, 0, 0]
+    assert to_mask(np.where(m), 5, cpu).tolist() == [1, 0, 1, 0, 0]          # np.where tuple
+    assert to_mask(np.array([4, 4, 0]), 5, cpu).tolist() == [1, 0, 0, 0, 1]  # index array with repeats
+    assert to_mask(torch.tensor([False, True, True, False, False]), 5, cpu).tolist() == [0, 1, 1, 0, 0]
+    assert to_mask(np.array([], dtype=np.int64), 5, cpu).tolist() == [0] * 5
+    with pytest.raises(IndexError):
+        to_mask(np.array([True, False]), 5, cpu)
+
+
+def test_shard_ranges_cover_the_bundle_in_rank_order():
+    from pyxfocus_b200.dist import shard_range
+    for num in (0, 1, 7, 1000, 10 ** 9 + 3):
+        for world in (1, 2, 4, 8):
+            edges = [shard_range(num, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == num
+            for (a, b), (c, d) in zip(edges, edges[1:]):
+                assert b == c and b >= a
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_coordinate_bookkeeping_roundtrip():
+    from pyxfocus_b200 import transformations as T
+    c = T.newCoords()
+    T._update_coords_fwd(c, 1., -2., 3., .1, .2, -.3)
+    assert np.allclose(c[1] @ c[3], np.identity(4), atol=1e-14)      # global->local then local->global
+    assert np.allclose(c[0] @ c[2], np.identity(4), atol=1e-14)
+    assert np.allclose(T.rotationM(.1, .2, .3) @ T.rotationM(.1, .2, .3, inverse=True), np.identity(4), atol=1e-15)
+    # a point at the new origin maps to zero
+    p = c[1] @ np.array([1., -2., 3., 1.])
+    assert np.allclose(p[:3], 0., atol=1e-14)
+
+
+def test_bundle_alloc_alignment_rule():
+    from pyxfocus_b200._call import bundle_alloc
+    for n in (0, 1, 2, 5, 1000, 1001):
+        rows = bundle_alloc(n, "cpu")
+        assert len(rows) == 10 and all(r.shape[0] == n and r.is_contiguous() for r in rows)
+        # consecutive rows are an even number of doubles apart -> every row keeps 16-byte alignment
+        if n:
+            assert ((rows[1].data_ptr() - rows[0].data_ptr()) // 8) % 2 == 0
+
+
+def test_host_trace_argument_validation():
+    import pyxfocus_b200 as pxf
+    rows = [np.zeros(4) for _ in range(10)]
+    with pytest.raises(ValueError):
+        pxf.host.trace(rows, pxf.Program())                              # empty program
+    rows[3] = np.zeros(5)
+    with pytest.raises(ValueError):
+        pxf.host.trace(rows, pxf.Program().reflect())                    # ragged rows
+    rows[3] = np.zeros(4, dtype=np.float32)
+    with pytest.raises(ValueError):
+        pxf.host.trace(rows, pxf.Program().reflect())                    # wrong dtype

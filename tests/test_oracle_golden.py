@@ -1,0 +1,105 @@
+"""The oracle restatement (oracle/pyref.py + oracle/chains.py over the C oracle) against
+(a) the committed golden vectors, which were produced by the reference's own unmodified
+Python layer (tests/golden/make_golden.py), and (b) the live reference Python when
+/root/reference is present (build container only)."""
+import numpy as np
+import pytest
+
+from oracle import chains, pyref, refload
+from oracle import f2py as of
+from util import assert_bit_equal, copy, rows_of
+
+
+def test_golden_wolter1_reproduced_by_restatement(golden):
+    g = golden("wolter1")
+    np.random.seed(0)
+    rays = pyref.subannulus(220., 220.6, 2 * np.pi, 4000, zhat=-1.)
+    assert_bit_equal(rays, rows_of(g["rays_in"]), what="subannulus")
+    assert np.array_equal(g["u1"], np.random.RandomState(0).rand(8000)[:4000])
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[:2])
+    assert_bit_equal(rays, rows_of(g["after_primary"]), what="after_primary")
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[2:])
+    assert_bit_equal(rays, rows_of(g["rays_out"]), what="rays_out")
+    w = g["weights"]
+    assert pyref.hpd(rays) == g["hpd"] and pyref.rmsCentroid(rays) == g["rms"]
+    assert pyref.hpd(rays, weights=w) == g["hpd_w"] and pyref.rmsCentroid(rays, weights=w) == g["rms_w"]
+    assert np.array_equal(np.array(pyref.centroid(rays, weights=w)), g["centroid_w"])
+    r, cdf = pyref.rhocdf(rays, weights=w)
+    assert np.array_equal(r, g["rhocdf_r"]) and np.array_equal(cdf, g["rhocdf_cdf"])
+
+
+def test_golden_ws_reproduced_by_restatement(golden):
+    g = golden("ws_offaxis")
+    a0, a1 = chains.ws_aperture()
+    assert a0 == g["a0"] and a1 == g["a1"]
+    assert a0 == 220.13737656836065 and a1 == 221.23348169132342       # SURVEY.md 3.2 probe
+    rays = chains.ws_source(4000, 0)
+    assert_bit_equal(rays, rows_of(g["rays_in"]), what="ws rays_in")
+    chains.run_steps_cpu(rays, chains.ws_steps(float(g["theta"])))
+    assert_bit_equal(rays, rows_of(g["after_secondary"]), what="ws after_secondary")
+    assert pyref.analyticImagePlane(rays) == g["dz_analytic"]
+    assert pyref.focusI(rays) == g["focus"]
+    assert_bit_equal(rays, rows_of(g["rays_out"]), what="ws rays_out")
+    assert pyref.hpd(rays) == g["hpd"] and pyref.rmsCentroid(rays) == g["rms"]
+
+
+def test_golden_vignette_reproduced_by_restatement(golden):
+    g = golden("spo_grating")
+    assert_bit_equal(pyref.vignette(rows_of(g["after_evan"])), rows_of(g["vignetted_evan"]))
+    assert_bit_equal(pyref.vignette(rows_of(g["after_miss"])), rows_of(g["vignetted"]))
+    assert_bit_equal(pyref.vignette(rows_of(g["after_miss"]), ind=g["keep"]), rows_of(g["vignetted_mask"]))
+    # masked gather/scatter idiom
+    rays = rows_of(g["after_grat"])
+    pyref.masked(of.transformationsf.radgrat, [rays[1], rays[2], rays[4], rays[5], rays[6]], g["evan"],
+                 2.4, 160. / 11832.911, 150)
+    assert_bit_equal(rays, rows_of(g["after_evan"]), what="masked radgrat")
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_restatement_matches_live_reference_python():
+    """Every numpy restatement in oracle/pyref.py against the reference's own function."""
+    ref = refload.load()
+    src, tran, anal, surf, con = ref.sources, ref.transformations, ref.analyses, ref.surfaces, ref.conicsolve
+    for name, args in (("subannulus", (220., 220.6, 1.3, 5001, -1.)), ("annulus", (200., 230., 5001, 1.)),
+                       ("circularbeam", (12.5, 5001)), ("pointsource", (.03, 5001))):
+        np.random.seed(11)
+        a = getattr(src, name)(*args)
+        np.random.seed(11)
+        b = getattr(pyref, name)(*args)
+        assert_bit_equal(b, a, what=name)
+    rays = chains.wolter1_source(5001, 12)
+    chains.run_steps_cpu(rays, chains.wolter1_steps())
+    rays[6][::13] = np.nan
+    rays[4][::17] = 0.; rays[5][::17] = 0.; rays[6][::17] = 0.
+    assert_bit_equal(pyref.vignette(copy(rays)), tran.vignette(copy(rays)), what="vignette")
+    good = pyref.vignette(copy(rays))
+    w = np.random.default_rng(12).uniform(.2, 3., good[1].size)
+    for fn in ("centroid", "rmsCentroid", "hpd", "analyticImagePlane"):
+        for ww in (None, w):
+            assert np.array_equal(np.array(getattr(pyref, fn)(good, weights=ww)),
+                                  np.array(getattr(anal, fn)(good, weights=ww))), fn
+    ra, ca = anal.rhocdf(good, weights=w)
+    rb, cb = pyref.rhocdf(good, weights=w)
+    assert np.array_equal(ra, rb) and np.array_equal(ca, cb)
+    assert pyref.woltparam(220., 8400.) == con.woltparam(220., 8400.)
+    a, b = copy(good), copy(good)
+    assert pyref.focusI(a) == surf.focusI(b)
+    assert_bit_equal(a, b, what="focusI")
+    # the mirrored host-side helpers of the product package
+    import importlib
+    import sys
+    import types
+    # import the pure-numpy product modules without touching CUDA: they only need _lib lazily
+    from pyxfocus_b200 import conicsolve as pcon
+    from pyxfocus_b200 import transformations as ptran
+    for f, a in (("primrad", (8450., 220., 8400.)), ("secrad", (8350., 220., 8400.)), ("woltparam", (220., 8400.)),
+                 ("primfocus", (220., 8400.)), ("wsRMS", (1., 1e-3, 6e-3, 200., 1e4)), ("wsFoc", (3., 1., 200., 1e4, 6e-3))):
+        assert np.array_equal(np.array(getattr(pcon, f)(*a)), np.array(getattr(con, f)(*a))), f
+    for inv in (False, True):
+        assert np.allclose(ptran.rotationM(.1, -.2, .3, inverse=inv), tran.rotationM(.1, -.2, .3, inverse=inv),
+                           rtol=0, atol=1e-16)
+    assert np.array_equal(ptran.translationM(1., 2., 3.), tran.translationM(1., 2., 3.))
+    c1, c2 = ptran.newCoords(), tran.newCoords()
+    ptran._update_coords_fwd(c1, 1., 2., 3., .1, .2, .3)
+    rotm, tranm = tran.rotationM(.1, .2, .3), tran.translationM(1., 2., 3.)
+    assert np.allclose(c1[1], np.dot(np.dot(rotm, tranm), c2[1]), atol=1e-15)

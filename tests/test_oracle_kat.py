@@ -1,0 +1,266 @@
+"""Known-answer checks that pin the CPU oracle itself.
+
+The reference ships no tests or golden vectors and its Fortran cannot be compiled here, so the
+oracle (a C restatement of the .f95 loops) is pinned by physics: closed forms from the
+reference's own conicsolve.py, algebraic identities, and the three independent Zernike
+implementations inside specialFunctions.f95.
+"""
+import numpy as np
+import pytest
+
+from oracle import chains, pyref
+from oracle import f2py as of
+
+T, S, W, Z, SP = of.transformationsf, of.surfacesf, of.woltsurf, of.zernsurf, of.specialfunctions
+
+
+def _vs(r0, z0, psi=1.):
+    alpha = .25 * np.arctan(r0 / z0)
+    thetah = 2 * (1 + 2 * psi) / (1 + psi) * alpha
+    thetap = 2 * psi / (1 + psi) * alpha
+    p = z0 * np.tan(4 * alpha) * np.tan(thetap)
+    d = z0 * np.tan(4 * alpha) * np.tan(4 * alpha - thetah)
+    e = np.cos(4 * alpha) * (1 + np.tan(4 * alpha) * np.tan(thetah))
+    return p, d, e
+
+
+def primrad(z, r0, z0, psi=1.):          # conicsolve.py:7-15
+    p, d, e = _vs(r0, z0, psi)
+    return np.sqrt(p ** 2 + 2 * p * z + (4 * e ** 2 * p * d) / (e ** 2 - 1))
+
+
+def secrad(z, r0, z0, psi=1.):           # conicsolve.py:29-37
+    p, d, e = _vs(r0, z0, psi)
+    return np.sqrt(e ** 2 * (d + z) ** 2 - z ** 2)
+
+
+def test_K1_on_axis_wolter_focus_and_real4_delta():
+    """Perfect on-axis Wolter-I focuses to a point; the spot size that remains is the REAL*4
+    rounding of flat's propagation distance (surfacesf.f95:4-29): 1.278e-5 mm at 1e5 rays,
+    seed 0.  A pure-double flat would give ~8e-11."""
+    rays = chains.wolter1_source(100_000, 0)
+    h = chains.wolter1_cpu(rays)
+    assert h == pytest.approx(1.278e-5, rel=2e-3)
+    # the same chain with a double-precision delta
+    rays = chains.wolter1_source(100_000, 0)
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[:-1])
+    delta = -rays[3] / rays[6]
+    rays[1] += delta * rays[4]
+    rays[2] += delta * rays[5]
+    assert pyref.hpd(rays) < 1e-9
+
+
+def test_K2_rays_land_on_prescription_radii():
+    rays = chains.wolter1_source(20_000, 1)
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[:2])
+    r = np.hypot(rays[1], rays[2])
+    assert np.abs(r - primrad(rays[3], 220., 8400.)).max() < 1e-12 * 220
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[2:4])
+    r = np.hypot(rays[1], rays[2])
+    assert np.abs(r - secrad(rays[3], 220., 8400.)).max() < 1e-10 * 220
+    for k in (7, 8, 9):
+        assert np.isfinite(rays[k]).all()
+    assert np.abs(rays[7] ** 2 + rays[8] ** 2 + rays[9] ** 2 - 1).max() < 1e-15
+
+
+def test_K3_primary_only_focus_distance():
+    """After the paraboloid alone the rays cross the axis at primfocus (conicsolve.py:62-64)."""
+    rays = chains.wolter1_source(5_000, 2)
+    chains.run_steps_cpu(rays, chains.wolter1_steps()[:3])
+    alpha, p, d, e = pyref.woltparam(220., 8400.)
+    zf = 8400. + 2 * e ** 2 * d / (e ** 2 - 1)       # distance of the primary focus from the node plane
+    # axial crossing: t with x + l t = 0
+    t = -rays[1] / rays[4]
+    zc = rays[3] + rays[6] * t
+    assert np.abs(zc - (8400. - zf)).max() < 1e-6
+
+
+def test_K4_ws_offaxis_rms_vs_chase_vanspeybroeck():
+    """W-S off-axis blur is of the size Chase & Van Speybroeck Eq. 13 predicts (conicsolve.py:250-254);
+    SURVEY.md 3.2 measured rms/Z0 = 3.01e-6 at 5' vs 2.08e-6 closed form."""
+    alpha = pyref.woltparam(220., 1.e4)[0]
+    out = {}
+    for arcmin in (0., 5., 10.):
+        th = arcmin / 60. * np.pi / 180.
+        rays = chains.ws_source(50_000, 0)
+        chains.run_steps_cpu(rays, chains.ws_steps(th))
+        f = pyref.focusI(rays)
+        out[arcmin] = (f, pyref.rmsCentroid(rays) / 1.e4, pyref.hpd(rays))
+    assert abs(out[0.][0]) < 1e-3 and out[0.][2] < 1e-4            # on axis: sharp focus at the origin
+    assert out[5.][0] == pytest.approx(3.11, abs=.05)               # SURVEY probe: dz = +3.1149 mm
+    assert out[5.][1] == pytest.approx(3.01e-6, rel=.05)
+    assert out[10.][1] == pytest.approx(1.85e-5, rel=.05)
+    eq13 = .135 * 2 * (np.tan(5. / 60 * np.pi / 180) ** 2 / np.tan(alpha)) * 200. / 1.e4
+    assert .5 < out[5.][1] / eq13 < 3.
+
+
+def test_K5_conic_against_closed_form():
+    """conic lands rays on z = r^2/(R(1+sqrt(1-(1+K)r^2/R^2))) and gives a unit normal."""
+    rng = np.random.default_rng(3)
+    for R, K in ((1000., -1.), (500., 0.), (-800., .3), (300., -2.5)):
+        n = 5000
+        np.random.seed(3)
+        rays = pyref.circularbeam(40., n)
+        rays[4][:] = rng.normal(0, .01, n)
+        rays[5][:] = rng.normal(0, .01, n)
+        rays[6][:] = np.sqrt(1 - rays[4] ** 2 - rays[5] ** 2)
+        rays[3][:] = -20.
+        S.conic(*rays[1:], R, K)
+        r2 = rays[1] ** 2 + rays[2] ** 2
+        sag = r2 / (R * (1 + np.sqrt(1 - (1 + K) * r2 / R ** 2)))
+        # K=-1 with near-axial rays: the reference's quadratic has denom = l^2+m^2 ~ 1e-4 and
+        # cancels catastrophically (surfacesf.f95:319-326); that loss is part of its answer
+        assert np.abs(rays[3] - sag).max() < (1e-5 if K == -1. else 1e-9)
+        assert np.abs(rays[7] ** 2 + rays[8] ** 2 + rays[9] ** 2 - 1).max() < 1e-14
+
+
+def test_K6_itransform_inverts_transform():
+    from util import random_bundle
+    rays = random_bundle(10_000, 4)
+    keep = [r.copy() for r in rays]
+    T.transform(*rays[1:], 1., -2., 3., .1, -.2, .3)
+    T.itransform(*rays[1:], 1., -2., 3., .1, -.2, .3)
+    for k in range(1, 10):
+        assert np.abs(rays[k] - keep[k]).max() < 1e-12 * (400. if k < 4 else 1.)
+
+
+def test_K7_reflect_twice_is_identity_and_norm_preserving():
+    from util import random_bundle
+    rays = random_bundle(10_000, 5)
+    keep = [r.copy() for r in rays]
+    T.reflect(*rays[4:])
+    assert np.abs(rays[4] ** 2 + rays[5] ** 2 + rays[6] ** 2 - 1).max() < 1e-14
+    T.reflect(*rays[4:])
+    for k in (4, 5, 6):
+        assert np.abs(rays[k] - keep[k]).max() < 1e-14
+
+
+def test_K8_radgrat_order_zero_and_grating_equation():
+    from util import random_bundle
+    rng = np.random.default_rng(6)
+    n = 5000
+    rays = random_bundle(n, 6)
+    rays[1][:] = rng.uniform(-40, 40, n)
+    rays[2][:] = 11832.911 + rng.uniform(-40, 40, n)
+    rays[4][:] = rng.normal(0, .02, n)
+    rays[5][:] = rng.normal(0, .02, n)
+    rays[6][:] = -np.sqrt(1 - rays[4] ** 2 - rays[5] ** 2)
+    keep = [r.copy() for r in rays]
+    T.radgrat(rays[1], rays[2], rays[4], rays[5], rays[6], 2.4, 160. / 11832.911, 0.)
+    assert np.array_equal(rays[4], keep[4]) and np.array_equal(rays[5], keep[5])
+    T.radgrat(rays[1], rays[2], rays[4], rays[5], rays[6], 2.4, 160. / 11832.911, -3.)
+    d = 160. / 11832.911 * np.hypot(rays[1], rays[2])
+    dl, dm = rays[4] - keep[4], rays[5] - keep[5]
+    assert np.allclose(np.hypot(dl, dm), 3 * 2.4 / d, rtol=1e-9)
+    # the change is perpendicular to the local groove direction (radial from the hub)
+    rad = np.stack([rays[1], rays[2]]) / np.hypot(rays[1], rays[2])
+    assert np.abs(dl * rad[0] + dm * rad[1]).max() < 1e-7          # pi is REAL*4 in the reference: 8.7e-8 rad of yaw error
+    assert (np.sign(rays[6]) == np.sign(keep[6])).all()
+    # radgratW takes the sign of n from y
+    rays2 = [r.copy() for r in keep]
+    rays2[2][::2] *= -1
+    T.radgratw(rays2[1], rays2[2], rays2[4], rays2[5], rays2[6], np.full(n, 2.4), 160. / 11832.911, 1.)
+    assert (np.sign(rays2[6]) == np.sign(rays2[2])).all()
+
+
+def test_K9_hpd_of_a_uniform_disc_two_statistics():
+    np.random.seed(7)
+    rays = pyref.circularbeam(3., 400_000)
+    assert pyref.hpd(rays) == pytest.approx(np.sqrt(2.) * 3., rel=5e-3)
+    w = np.ones(400_000)
+    assert pyref.hpd(rays, weights=w) == pytest.approx(3. * (np.sqrt(.75) - np.sqrt(.25)), rel=5e-3)
+
+
+def _noll_orders(nmax):
+    return chains.zernike_orders(nmax)
+
+
+def test_K10_zernset_three_implementations_agree():
+    """zernset's q-recursion (specialFunctions.f95:142-232) against the closed-form radial
+    polynomial (:17-38) and an independent numpy evaluation of Z and its derivatives."""
+    ro, ao = _noll_orders(7)
+    from math import factorial as f
+
+    def R(n, m, rho):
+        return sum((-1) ** k * f(n - k) / (f(k) * f((n + m) // 2 - k) * f((n - m) // 2 - k)) * rho ** (n - 2 * k)
+                   for k in range((n - m) // 2 + 1))
+
+    def dR(n, m, rho):
+        return sum((-1) ** k * f(n - k) / (f(k) * f((n + m) // 2 - k) * f((n - m) // 2 - k)) * (n - 2 * k)
+                   * rho ** (n - 2 * k - 1) for k in range((n - m) // 2 + 1) if n - 2 * k > 0)
+
+    for rho in (.05, .3, .77, 1.):
+        for theta in (.1, 2.5, -1.7):
+            po, dr, dt = SP.zernset(rho, theta, ro, ao)
+            for i, (n, mm) in enumerate(zip(ro, ao)):
+                m = abs(int(mm))
+                n = int(n)
+                norm = np.sqrt(2 * (n + 1))
+                assert SP.radialpoly(rho, n, m) == pytest.approx(R(n, m, rho), rel=1e-12, abs=1e-14)
+                if mm < 0:
+                    zz, zr, zt = norm * R(n, m, rho) * np.sin(m * theta), norm * dR(n, m, rho) * np.sin(m * theta), \
+                        norm * R(n, m, rho) * np.cos(m * theta) * m
+                elif mm > 0:
+                    zz, zr, zt = norm * R(n, m, rho) * np.cos(m * theta), norm * dR(n, m, rho) * np.cos(m * theta), \
+                        -norm * R(n, m, rho) * np.sin(m * theta) * m
+                else:
+                    s = float(np.float32(np.sqrt(np.float32(.5))))      # sqrt(0.5) is REAL*4 in the reference
+                    zz, zr, zt = norm * s * R(n, m, rho), norm * s * dR(n, m, rho), 0.
+                assert po[i] == pytest.approx(zz, rel=1e-10, abs=1e-11)
+                assert dr[i] == pytest.approx(zr, rel=1e-8, abs=1e-9)
+                assert dt[i] == pytest.approx(zt, rel=1e-10, abs=1e-11)
+    # rho = 0 special cases (:174-184)
+    po, dr, dt = SP.zernset(0., .3, ro, ao)
+    assert po[0] == pytest.approx(np.sqrt(2.) * float(np.float32(np.sqrt(np.float32(.5)))))
+    assert np.isfinite(po).all() and np.isfinite(dr).all()
+
+
+def test_K11_legendre():
+    from numpy.polynomial import legendre as L
+    xs = np.linspace(-1, 1, 41)
+    for n in range(0, 9):
+        c = np.zeros(n + 1)
+        c[n] = 1
+        for x in xs:
+            assert SP.legendre(x, n) == pytest.approx(L.legval(x, c), abs=1e-12)
+            assert SP.legendrep(x, n) == pytest.approx(L.legval(x, L.legder(c)) if n else 0., abs=1e-10)
+    assert SP.legendre(1.7, 3) == SP.legendre(1., 3)          # clamp: evaluated at sign(x)
+    assert SP.legendrep(1.7, 3) == 0.
+
+
+def test_quirks_real4_literals():
+    """REAL*4 literals the reference promotes to double (SURVEY.md 8a-Q 2,3)."""
+    assert float(np.float32(np.arccos(np.float32(-1.)))) == 3.1415927410125732
+    assert float(np.float32(1e-8)) == 9.99999993922529e-09
+    # flat's delta is single precision: positions move by float32(-z/n)
+    x = np.array([1.]); y = np.array([2.]); z = np.array([-8400.123456789])
+    l = np.array([.01]); m = np.array([.02]); n = np.array([np.sqrt(1 - 5e-4)])
+    ux, uy, uz = np.zeros(1), np.zeros(1), np.zeros(1)
+    S.flat(x, y, z, l, m, n, ux, uy, uz)
+    d32 = float(np.float32(8400.123456789 / n[0]))
+    assert x[0] == 1. + d32 * .01 and y[0] == 2. + d32 * .02 and z[0] == 0. and uz[0] == 1.
+
+
+def test_ws_iteration_cap_semantics():
+    """A ray that cannot converge is restored to its entry point and keeps its old normal
+    (woltsurf.f95:454-469,562-580)."""
+    alpha = pyref.woltparam(220., 1.e4)[0]
+    rays = chains.ws_source(3000, 8)
+    chains.run_steps_cpu(rays, chains.ws_steps(25. / 60. * np.pi / 180.)[:4])
+    before = [r.copy() for r in rays]
+    W.wssecondary(*rays[1:], alpha, 1.e4, 1.)
+    restored = (rays[1] == before[1]) & (rays[2] == before[2]) & (rays[3] == before[3])
+    assert 0 < restored.sum() < 3000
+    for k in (7, 8, 9):
+        assert np.array_equal(rays[k][restored], before[k][restored])      # normal untouched
+    assert not np.array_equal(rays[7][~restored], before[7][~restored])
+
+
+def test_f2py_style_errors():
+    a = np.zeros(10)
+    with pytest.raises(ValueError):
+        T.reflect(a.astype(np.float32), a, a, a, a, a)
+    with pytest.raises(ValueError):
+        T.reflect(np.zeros(20)[::2], a, a, a, a, a)
+    with pytest.raises(ValueError):
+        T.reflect(np.zeros(5), a, a, a, a, a)
