@@ -233,9 +233,10 @@ int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy,
  *                        keys that match the prefix of each still-unresolved chain; NaN
  *                        keys are counted separately.  cxy_dev = device double[2] centroid.
  *   pxf_select_narrow  : pick the bin holding each rank, extend the prefixes, clear hist
- *   pxf_select_finish  : out_dev[0] = 2*median (mean of the two order statistics; NaN if
- *                        any key is NaN or num_total == 0 -- numpy semantics),
- *                        out_dev[1], out_dev[2] = the two order statistics
+ *   pxf_select_finish  : out_dev (double[4]): [0] = 2*median (mean of the two order
+ *                        statistics; NaN if any key is NaN or num_total == 0 -- numpy
+ *                        semantics), [1], [2] = the two order statistics, [3] = 1 unless a
+ *                        bracketed select missed (see below)
  *   pxf_select_schedule: digit schedule (shift,bits) of pass `pass`; returns #passes (5). */
 size_t pxf_select_state_bytes(void);
 int pxf_select_begin(void *state, int64_t k0, int64_t k1, pxf_stream_t stream);
@@ -249,11 +250,37 @@ int pxf_select_finish(void *state, int64_t num_total, double *out_dev, pxf_strea
 int pxf_select_schedule(int32_t pass, int32_t *shift, int32_t *bits);
 /* cxy_dev[0] = sums[1]/sums[0], cxy_dev[1] = sums[2]/sums[0] (np.average) */
 int pxf_centroid_from_sums(const double *sums_dev, double *cxy_dev, pxf_stream_t stream);
-/* Unweighted HPD entirely on the device: centroid sums -> centroid -> 5 select passes.
- * out_dev: device double[3] as pxf_select_finish; workspace: pxf_hpd_workspace_bytes(). */
-size_t pxf_hpd_workspace_bytes(void);
+/* Bracketed select: the median of 1e8 radii without five full passes.  A strided sample of
+ * pxf_bracket_samples() radii gives, by an exact select of the sample order statistics
+ * pxf_bracket_sample_ranks(), a bracket [lo,hi] around the median; ONE pass
+ * (pxf_bracket_collect) counts the radii below lo and appends those inside the bracket to a
+ * candidate buffer (capacity pxf_bracket_capacity(num)); the exact select then runs on the
+ * candidates (pxf_select_begin_bracket -> pxf_select_hist_keys/narrow x5 -> pxf_select_finish).
+ * A miss (rank outside the bracket, buffer overflow) marks the state invalid -- out_dev[3]==0
+ * from pxf_select_finish -- and the caller falls back to the five-pass select: the result is
+ * exact either way.  counters: device uint64[4] = {#below, #inside, #NaN, #overflowed shards},
+ * zeroed by the caller; a sharded bundle all-reduces them. */
+int64_t pxf_bracket_min_num(void);
+int32_t pxf_bracket_samples(void);
+int64_t pxf_bracket_capacity(int64_t num);
+void pxf_bracket_sample_ranks(int32_t nsamp, int64_t *a, int64_t *b);
+int pxf_select_sample(const double *x, const double *y, int64_t num, const double *cxy_dev, int32_t nsamp,
+                      double *keys_out, pxf_stream_t stream);
+int pxf_bracket_collect(const double *x, const double *y, int64_t num, const double *cxy_dev,
+                        const double *lohi_dev, double *cand, int64_t cap, uint64_t *counters,
+                        pxf_stream_t stream);
+int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t *counters,
+                             int64_t cap_total, pxf_stream_t stream);
+int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_dev, int32_t shift,
+                         int32_t bits, void *state, pxf_stream_t stream);
+/* Unweighted HPD entirely on the device.  out_dev: double[4] = {2*median, lower middle, upper
+ * middle, valid}.  mode 0 = automatic (bracketed select for bundles >= pxf_bracket_min_num()),
+ * 1 = force the five-pass select.  With mode 0 the caller checks out_dev[3]: 0 means the
+ * bracket missed (probability ~1e-9) and the call must be repeated with mode 1.
+ * workspace: pxf_hpd_workspace_bytes(num). */
+size_t pxf_hpd_workspace_bytes(int64_t num);
 int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev,
-                           void *workspace, pxf_stream_t stream);
+                           void *workspace, int32_t mode, pxf_stream_t stream);
 /* rows_out[r][i] = rows_in[r][idx[i]] for nrows <= 16 rows (vignette with an index array,
  * transformations.py:225).  rows_in/rows_out are HOST arrays of device pointers;
  * table_scratch: >= 256 B device. */
@@ -325,6 +352,8 @@ int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, c
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
                            int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep);
+/* Frees the streams / device buffers the host entry point caches between calls. */
+void pxf_host_release(void);
 
 #ifdef __cplusplus
 }

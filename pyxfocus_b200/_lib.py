@@ -84,8 +84,16 @@ SIGNATURES = {
     "pxf_select_finish": (_c.c_int, [_vp, _i64, _dp, _st]),
     "pxf_select_schedule": (_c.c_int, [_i32, _vp, _vp]),
     "pxf_centroid_from_sums": (_c.c_int, [_dp, _dp, _st]),
-    "pxf_hpd_workspace_bytes": (_sz, []),
-    "pxf_hpd_unweighted_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _st]),
+    "pxf_bracket_min_num": (_i64, []),
+    "pxf_bracket_samples": (_i32, []),
+    "pxf_bracket_capacity": (_i64, [_i64]),
+    "pxf_bracket_sample_ranks": (None, [_i32, _vp, _vp]),
+    "pxf_select_sample": (_c.c_int, [_dp, _dp, _i64, _dp, _i32, _dp, _st]),
+    "pxf_bracket_collect": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_select_begin_bracket": (_c.c_int, [_vp, _i64, _i64, _vp, _i64, _st]),
+    "pxf_select_hist_keys": (_c.c_int, [_dp, _i64, _vp, _i32, _i32, _vp, _st]),
+    "pxf_hpd_workspace_bytes": (_sz, [_i64]),
+    "pxf_hpd_unweighted_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _i32, _st]),
     "pxf_centroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _vp, _st]),
     "pxf_rmscentroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_hpd": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
@@ -99,6 +107,7 @@ SIGNATURES = {
     "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
     # host-buffer entry point
     "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "pxf_host_release": (None, []),
 }
 
 _lib = None

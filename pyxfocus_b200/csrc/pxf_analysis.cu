@@ -156,7 +156,7 @@ struct SelectState {
     unsigned long long prefix[2];   // resolved high bits of each chain (right aligned)
     unsigned long long rank[2];     // 0-based rank still to resolve inside the prefix group
     int nprefix;                    // 1 while both order statistics share a prefix, else 2
-    int pad;
+    int valid;                      // 0 when a bracketed select missed its bracket (caller falls back)
 };
 
 PXF_DEV unsigned long long key_of(double r) { return (unsigned long long)__double_as_longlong(r); }
@@ -286,7 +286,7 @@ __global__ void k_select_init(SelectState *st, unsigned long long k0, unsigned l
                               unsigned long long *hist, int nh, unsigned long long *nan_count)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        st->prefix[0] = 0; st->prefix[1] = 0; st->rank[0] = k0; st->rank[1] = k1; st->nprefix = 1; st->pad = 0;
+        st->prefix[0] = 0; st->prefix[1] = 0; st->rank[0] = k0; st->rank[1] = k1; st->nprefix = 1; st->valid = 1;
         if (nan_count) *nan_count = 0;
     }
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nh; t += gridDim.x * blockDim.x) hist[t] = 0ull;
@@ -303,6 +303,118 @@ __global__ void k_select_result(const SelectState *st, const unsigned long long 
     out[0] = med * 2.;
     out[1] = a;
     out[2] = b;
+    out[3] = st->valid ? 1. : 0.;
+}
+
+// ------------------------------------------------------------------ bracketed select
+// np.median over 1e8 radii does not need five full passes: a strided sample of S radii gives
+// (by an exact select on the sample) a bracket [lo,hi] that holds the two middle order
+// statistics with overwhelming probability; ONE pass over the bundle then counts the radii
+// below lo and collects the few per cent inside the bracket, and the exact select finishes on
+// that small buffer.  If the bracket misses (or the candidate buffer overflows) the state is
+// flagged invalid and the caller reruns the full five-pass select -- the result is exact
+// either way.
+#define BRACKET_SAMPLES 65536
+#define BRACKET_MIN_NUM (int64_t(1) << 21)
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_select_sample(const double *__restrict__ x, const double *__restrict__ y, int64_t num,
+                const double *__restrict__ cxy, int nsamp, double *__restrict__ keys)
+{
+    const double cx = cxy[0], cy = cxy[1];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nsamp; j += gridDim.x * blockDim.x) {
+        const int64_t i = (int64_t)(((unsigned long long)j * (unsigned long long)num) / (unsigned long long)nsamp);
+        keys[j] = sqrt(sq(x[i] - cx) + sq(y[i] - cy));
+    }
+}
+
+// counters: [0] #(r < lo), [1] #(lo <= r <= hi) (may exceed cap), [2] #NaN, [3] #shards whose buffer overflowed
+template <bool VEC2>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_bracket_collect(const double *__restrict__ x, const double *__restrict__ y, int64_t num,
+                  const double *__restrict__ cxy, const double *__restrict__ lohi,
+                  double *__restrict__ cand, unsigned long long cap, unsigned long long *__restrict__ counters)
+{
+    const double cx = cxy[0], cy = cxy[1];
+    const double lo = lohi[1], hi = lohi[2];
+    const int lane = threadIdx.x & 31;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    unsigned int below = 0, nans = 0;
+    constexpr int PER = VEC2 ? 2 : 1;
+    const int64_t items = VEC2 ? (num >> 1) : num;
+    const int64_t nround = (items + nthr - 1) / nthr;      // whole warps iterate together (ballots)
+    for (int64_t it = 0; it < nround; it++) {
+        const int64_t q = tid + it * nthr;
+        double r[2] = {0., 0.};
+        bool in[2] = {false, false};
+        if (q < items) {
+            if (VEC2) {
+                const double2 xv = *reinterpret_cast<const double2 *>(x + 2 * q);
+                const double2 yv = *reinterpret_cast<const double2 *>(y + 2 * q);
+                r[0] = sqrt(sq(xv.x - cx) + sq(yv.x - cy));
+                r[1] = sqrt(sq(xv.y - cx) + sq(yv.y - cy));
+            } else {
+                r[0] = sqrt(sq(x[q] - cx) + sq(y[q] - cy));
+            }
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                if (r[k] != r[k]) nans++;
+                else if (r[k] < lo) below++;
+                else if (r[k] <= hi) in[k] = true;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const unsigned m = __ballot_sync(0xffffffffu, in[k]);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(&counters[1], (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (in[k]) {
+                    const unsigned long long dst = base + __popc(m & ((1u << lane) - 1));
+                    if (dst < cap) cand[dst] = r[k];
+                }
+            }
+        }
+    }
+    if (VEC2 && (num & 1) && tid == 0) {
+        const double rr = sqrt(sq(x[num - 1] - cx) + sq(y[num - 1] - cy));
+        if (rr != rr) nans++;
+        else if (rr < lo) below++;
+        else if (rr <= hi) {
+            const unsigned long long dst = atomicAdd(&counters[1], 1ull);
+            if (dst < cap) cand[dst] = rr;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        below += __shfl_down_sync(0xffffffffu, below, o);
+        nans += __shfl_down_sync(0xffffffffu, nans, o);
+    }
+    if (lane == 0) {
+        if (below) atomicAdd(&counters[0], (unsigned long long)below);
+        if (nans) atomicAdd(&counters[2], (unsigned long long)nans);
+    }
+}
+
+// ranks inside the candidate buffer = global ranks - #below; flags the state invalid when the
+// bracket does not contain both ranks or the buffer overflowed.  counters are the (possibly
+// all-reduced) totals.
+__global__ void k_select_begin_bracket(SelectState *st, unsigned long long k0, unsigned long long k1,
+                                       const unsigned long long *__restrict__ counters, unsigned long long cap_total,
+                                       unsigned long long *hist, int nh, unsigned long long *nan_count)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long below = counters[0], ncand = counters[1];
+        const bool ok = counters[3] == 0 && ncand <= cap_total && k0 >= below && k1 < below + ncand;
+        st->prefix[0] = 0; st->prefix[1] = 0;
+        st->rank[0] = ok ? k0 - below : 0; st->rank[1] = ok ? k1 - below : 0;
+        st->nprefix = 1; st->valid = ok ? 1 : 0;
+        if (nan_count) *nan_count = counters[2];
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nh; t += gridDim.x * blockDim.x) hist[t] = 0ull;
 }
 
 // ------------------------------------------------------------------ compaction
@@ -653,21 +765,117 @@ int pxf_analyticimageplane(const double *x, const double *y, const double *l, co
     return PXF_OK;
 }
 
-int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev /*[3]*/,
-                           void *workspace, pxf_stream_t stream)
+// ---- bracketed-select primitives (also used by the sharded path) ----------------------------
+int64_t pxf_bracket_min_num(void) { return BRACKET_MIN_NUM; }
+int32_t pxf_bracket_samples(void) { return BRACKET_SAMPLES; }
+/* candidate-buffer capacity (doubles) for a shard of num rays: 4 % of the shard */
+int64_t pxf_bracket_capacity(int64_t num) { int64_t c = num / 25; return c < 65536 ? 65536 : c; }
+/* sample ranks whose order statistics bracket the median: 0.5 +- 6 sigma of the sample quantile */
+void pxf_bracket_sample_ranks(int32_t nsamp, int64_t *a, int64_t *b)
 {
-    // workspace: pxf_hpd_workspace_bytes()
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    double sigma = 0.5 / sqrt((double)nsamp);
+    int64_t d = (int64_t)ceil(6. * sigma * nsamp) + 1;
+    *a = nsamp / 2 - d; *b = nsamp / 2 + d;
+    if (*a < 0) *a = 0;
+    if (*b > nsamp - 1) *b = nsamp - 1;
+}
+
+/* keys_out[j] = radius of ray floor(j*num/nsamp) about the device centroid, j < nsamp */
+int pxf_select_sample(const double *x, const double *y, int64_t num, const double *cxy_dev, int32_t nsamp,
+                      double *keys_out, pxf_stream_t stream)
+{
+    if (num <= 0 || nsamp <= 0 || !x || !y || !cxy_dev || !keys_out) { set_error("pxf_select_sample: bad argument"); return PXF_ERR_INVALID; }
     int rc = need_device();
     if (rc) return rc;
-    char *ws = static_cast<char *>(workspace);
-    double *sums = reinterpret_cast<double *>(ws + pxf_sums_scratch_bytes());
-    double *cxy = sums + 16;
-    void *state = ws + pxf_sums_scratch_bytes() + 32 * sizeof(double);
-    if ((rc = sums_launch(PXF_SUMS_CENTROID, x, y, nullptr, nullptr, nullptr, nullptr, num, 0., 0., nullptr, sums, ws, s)))
-        return rc;
-    k_centroid_from_sums<<<1, 1, 0, s>>>(sums, cxy);
+    k_select_sample<<<grid_for(nsamp, PXF_BLOCK, 4), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, y, num, cxy_dev, nsamp, keys_out);
     count_launch();
+    return check_launch("k_select_sample");
+}
+
+/* One pass: counters[0] += #(r<lo), counters[1] += #(lo<=r<=hi) with those radii appended to
+ * cand (capacity cap; overflow only counted), counters[2] += #NaN.  lohi_dev = the 4-double
+ * output of pxf_select_finish on the sample ([1]=lo, [2]=hi).  counters: device uint64[4],
+ * zeroed by the caller. */
+int pxf_bracket_collect(const double *x, const double *y, int64_t num, const double *cxy_dev,
+                        const double *lohi_dev, double *cand, int64_t cap, uint64_t *counters, pxf_stream_t stream)
+{
+    if (num < 0 || !cxy_dev || !lohi_dev || !cand || cap <= 0 || !counters) { set_error("pxf_bracket_collect: bad argument"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    if (!x || !y) { set_error("pxf_bracket_collect: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    unsigned long long *c = reinterpret_cast<unsigned long long *>(counters);
+    if (aligned)
+        k_bracket_collect<true><<<grid_for((num + 1) >> 1, PXF_BLOCK, 6), PXF_BLOCK, 0, s>>>(x, y, num, cxy_dev, lohi_dev, cand, (unsigned long long)cap, c);
+    else
+        k_bracket_collect<false><<<grid_for(num, PXF_BLOCK, 6), PXF_BLOCK, 0, s>>>(x, y, num, cxy_dev, lohi_dev, cand, (unsigned long long)cap, c);
+    count_launch();
+    return check_launch("k_bracket_collect");
+}
+
+/* Begin the select over the candidate buffers: ranks k0,k1 are GLOBAL ranks, counters the
+ * (all-reduced) totals, cap_total the summed capacities.  Marks the state invalid on a miss. */
+int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t *counters, int64_t cap_total,
+                             pxf_stream_t stream)
+{
+    if (!state || k0 < 0 || k1 < k0 || !counters) { set_error("pxf_select_begin_bracket: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_select_begin_bracket<<<16, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        st_of(state), (unsigned long long)k0, (unsigned long long)k1, reinterpret_cast<const unsigned long long *>(counters),
+        (unsigned long long)cap_total, hist_of(state), 2 * 8192, nan_of(state));
+    count_launch();
+    return check_launch("k_select_begin_bracket");
+}
+
+/* histogram pass over a key buffer whose length lives on the device (min(*count_dev, cap)) */
+int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_dev, int32_t shift, int32_t bits,
+                         void *state, pxf_stream_t stream)
+{
+    if (!state || !keys || cap <= 0 || bits < 1 || bits > 13 || shift < 0 || shift + bits > 64) {
+        set_error("pxf_select_hist_keys: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    int rc = need_device();
+    if (rc) return rc;
+    return select_pass(nullptr, nullptr, keys, cap, reinterpret_cast<const unsigned long long *>(count_dev), nullptr,
+                       shift, bits, st_of(state), hist_of(state), nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// workspace layout of the device-side HPD
+struct HpdWs {
+    char *sums_scr; double *sums, *cxy, *lohi, *samp; void *stA, *stB; unsigned long long *counters; double *cand;
+    int64_t cap;
+};
+static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t hpd_ws_carve(HpdWs &w, char *base, int64_t num)
+{
+    size_t off = 0;
+    w.sums_scr = base + off; off += a256(pxf_sums_scratch_bytes());
+    w.sums = (double *)(base + off); off += 256;
+    w.cxy = (double *)(base + off); off += 256;
+    w.lohi = (double *)(base + off); off += 256;
+    w.counters = (unsigned long long *)(base + off); off += 256;
+    w.stA = base + off; off += a256(pxf_select_state_bytes());
+    w.stB = base + off; off += a256(pxf_select_state_bytes());
+    w.samp = (double *)(base + off); off += a256((size_t)BRACKET_SAMPLES * 8);
+    w.cap = num >= BRACKET_MIN_NUM ? pxf_bracket_capacity(num) : 0;
+    w.cand = (double *)(base + off); off += a256((size_t)w.cap * 8);
+    return off;
+}
+size_t pxf_hpd_workspace_bytes(int64_t num)
+{
+    HpdWs w;
+    return hpd_ws_carve(w, nullptr, num < 0 ? 0 : num) + 256;
+}
+
+static int hpd_full(const double *x, const double *y, int64_t num, const double *cxy, void *state, double *out_dev,
+                    pxf_stream_t stream)
+{
+    int rc;
     int64_t k0 = num > 0 ? (num - 1) / 2 : 0, k1 = num > 0 ? num / 2 : 0;
     if ((rc = pxf_select_begin(state, k0, k1, stream))) return rc;
     for (int p = 0; p < 5 && num > 0; p++) {
@@ -677,9 +885,45 @@ int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double
     return pxf_select_finish(state, num, out_dev, stream);
 }
 
-size_t pxf_hpd_workspace_bytes(void)
+/* Unweighted HPD entirely on the device.  out_dev: double[4] = {2*median, lower middle, upper
+ * middle, valid}.  mode 0 = automatic (bracketed select for large bundles: one full pass
+ * instead of five), 1 = force the five-pass select.  With mode 0 the caller must check
+ * out_dev[3]: 0 means the bracket missed (probability ~1e-9) and the call has to be repeated
+ * with mode 1.  workspace: pxf_hpd_workspace_bytes(num). */
+int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev,
+                           void *workspace, int32_t mode, pxf_stream_t stream)
 {
-    return pxf_sums_scratch_bytes() + 32 * sizeof(double) + pxf_select_state_bytes();
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    if (num < 0 || !out_dev || !workspace || (num > 0 && (!x || !y))) { set_error("pxf_hpd_unweighted_dev: bad argument"); return PXF_ERR_INVALID; }
+    HpdWs w;
+    hpd_ws_carve(w, static_cast<char *>(workspace), num);
+    if ((rc = sums_launch(PXF_SUMS_CENTROID, x, y, nullptr, nullptr, nullptr, nullptr, num, 0., 0., nullptr, w.sums, w.sums_scr, s)))
+        return rc;
+    k_centroid_from_sums<<<1, 1, 0, s>>>(w.sums, w.cxy);
+    count_launch();
+    if (mode == 1 || num < BRACKET_MIN_NUM) return hpd_full(x, y, num, w.cxy, w.stA, out_dev, stream);
+    // 1. bracket from a strided sample (exact select of two sample order statistics)
+    int64_t ra, rb;
+    pxf_bracket_sample_ranks(BRACKET_SAMPLES, &ra, &rb);
+    if ((rc = pxf_select_sample(x, y, num, w.cxy, BRACKET_SAMPLES, w.samp, stream))) return rc;
+    if ((rc = pxf_select_begin(w.stA, ra, rb, stream))) return rc;
+    for (int p = 0; p < 5; p++) {
+        if ((rc = pxf_select_hist(nullptr, nullptr, w.samp, BRACKET_SAMPLES, nullptr, kShift[p], kBits[p], w.stA, stream))) return rc;
+        if ((rc = pxf_select_narrow(kBits[p], w.stA, stream))) return rc;
+    }
+    if ((rc = pxf_select_finish(w.stA, BRACKET_SAMPLES, w.lohi, stream))) return rc;
+    // 2. one pass: count below, collect the bracket
+    PXF_CUDA(cudaMemsetAsync(w.counters, 0, 32, s));
+    if ((rc = pxf_bracket_collect(x, y, num, w.cxy, w.lohi, w.cand, w.cap, reinterpret_cast<uint64_t *>(w.counters), stream))) return rc;
+    // 3. exact select among the candidates
+    if ((rc = pxf_select_begin_bracket(w.stB, (num - 1) / 2, num / 2, reinterpret_cast<uint64_t *>(w.counters), w.cap, stream))) return rc;
+    for (int p = 0; p < 5; p++) {
+        if ((rc = pxf_select_hist_keys(w.cand, w.cap, reinterpret_cast<uint64_t *>(w.counters + 1), kShift[p], kBits[p], w.stB, stream))) return rc;
+        if ((rc = pxf_select_narrow(kBits[p], w.stB, stream))) return rc;
+    }
+    return pxf_select_finish(w.stB, num, out_dev, stream);
 }
 
 int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
@@ -692,12 +936,16 @@ int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, doub
     if (rc) return rc;
     if (w) return pxf_hpd_weighted(x, y, w, num, hpd_host, stream);
     Scratch sc;
-    if ((rc = sc.alloc(pxf_hpd_workspace_bytes() + 64, s))) return rc;
-    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_hpd_workspace_bytes());
-    if ((rc = pxf_hpd_unweighted_dev(x, y, num, out, sc.p, stream))) return rc;
-    double h[3];
-    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PXF_CUDA(cudaStreamSynchronize(s));
+    const size_t wb = pxf_hpd_workspace_bytes(num);
+    if ((rc = sc.alloc(wb + 64, s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + wb);
+    double h[4];
+    for (int mode = 0; mode < 2; mode++) {
+        if ((rc = pxf_hpd_unweighted_dev(x, y, num, out, sc.p, mode, stream))) return rc;
+        PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+        PXF_CUDA(cudaStreamSynchronize(s));
+        if (h[3] != 0.) break;          // valid (always the case for mode 1)
+    }
     *hpd_host = h[0];
     return PXF_OK;
 }

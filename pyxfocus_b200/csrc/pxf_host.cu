@@ -5,42 +5,89 @@
 // max(H2D, D2H), not their sum, and device memory is bounded by the ring, not the bundle.
 // Only the rows the program reads are uploaded and only the rows it writes are downloaded
 // (the liveness masks of build_program).  When the caller also wants the HPD, final x,y stay
-// resident in full-length device rows and the radix-select HPD runs on them at the end.
+// resident in full-length device rows and the select-based HPD runs on them at the end.
+// Streams, events and device buffers are cached between calls (pxf_host_release frees them).
+#include <chrono>
+#include <mutex>
+#include <stdlib.h>
 #include "pxf_program.h"
 
 namespace pxf {
 
-#define HOST_SLOTS 3
-#define HOST_CHUNK (int64_t(1) << 22)   // rays per chunk: 32 MiB per row, ~2.5 ms of PCIe per row
+#define HOST_SLOTS 4
+#define HOST_CHUNK (int64_t(1) << 21)   // rays per chunk: 16 MiB per row
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PXF_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pxf_host_trace_program: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return PXF_ERR_NOMEM;
+        }
+        cap = bytes;
+        return PXF_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
 
 struct HostRing {
+    int device = -1;
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
     cudaEvent_t in_done[HOST_SLOTS] = {}, run_done[HOST_SLOTS] = {}, out_done[HOST_SLOTS] = {};
-    double *slot_rows[HOST_SLOTS][10] = {};
-    uint8_t *slot_alive[HOST_SLOTS] = {};
-    double *full_x = nullptr, *full_y = nullptr;
-    uint8_t *full_alive = nullptr;
-    void *misc = nullptr;
+    DevBuf slot_rows[HOST_SLOTS][10];
+    DevBuf slot_alive[HOST_SLOTS];
+    DevBuf full_x, full_y, full_alive, misc, cx, cy, scr;
 
-    ~HostRing()
+    int init()
+    {
+        int dev = 0;
+        PXF_CUDA(cudaGetDevice(&dev));
+        if (device == dev && s_in) return PXF_OK;
+        release();
+        device = dev;
+        PXF_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        PXF_CUDA(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+        PXF_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < HOST_SLOTS; k++) {
+            PXF_CUDA(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
+            PXF_CUDA(cudaEventCreateWithFlags(&run_done[k], cudaEventDisableTiming));
+            PXF_CUDA(cudaEventCreateWithFlags(&out_done[k], cudaEventDisableTiming));
+        }
+        return PXF_OK;
+    }
+    void release()
     {
         for (int k = 0; k < HOST_SLOTS; k++) {
-            for (int r = 0; r < 10; r++)
-                if (slot_rows[k][r]) cudaFree(slot_rows[k][r]);
-            if (slot_alive[k]) cudaFree(slot_alive[k]);
+            for (int r = 0; r < 10; r++) slot_rows[k][r].release();
+            slot_alive[k].release();
             if (in_done[k]) cudaEventDestroy(in_done[k]);
             if (run_done[k]) cudaEventDestroy(run_done[k]);
             if (out_done[k]) cudaEventDestroy(out_done[k]);
+            in_done[k] = run_done[k] = out_done[k] = nullptr;
         }
-        if (full_x) cudaFree(full_x);
-        if (full_y) cudaFree(full_y);
-        if (full_alive) cudaFree(full_alive);
-        if (misc) cudaFree(misc);
+        full_x.release(); full_y.release(); full_alive.release(); misc.release(); cx.release(); cy.release(); scr.release();
         if (s_in) cudaStreamDestroy(s_in);
         if (s_run) cudaStreamDestroy(s_run);
         if (s_out) cudaStreamDestroy(s_out);
+        s_in = s_run = s_out = nullptr;
+        device = -1;
     }
 };
+
+static HostRing g_ring;
+static std::mutex g_ring_mutex;
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 }  // namespace pxf
 
@@ -48,9 +95,11 @@ using namespace pxf;
 
 extern "C" {
 
-int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev, void *workspace,
-                           pxf_stream_t stream);
-size_t pxf_hpd_workspace_bytes(void);
+void pxf_host_release(void)
+{
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    g_ring.release();
+}
 
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
@@ -75,55 +124,54 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
         if (hpd_host) *hpd_host = __builtin_nan("");
         return PXF_OK;
     }
-
-    HostRing R;
-    PXF_CUDA(cudaStreamCreateWithFlags(&R.s_in, cudaStreamNonBlocking));
-    PXF_CUDA(cudaStreamCreateWithFlags(&R.s_run, cudaStreamNonBlocking));
-    PXF_CUDA(cudaStreamCreateWithFlags(&R.s_out, cudaStreamNonBlocking));
-    const int64_t chunk = num < HOST_CHUNK ? ((num + 1) & ~int64_t(1)) : HOST_CHUNK;
-    const int64_t nchunks = (num + chunk - 1) / chunk;
-    const int nslots = nchunks < HOST_SLOTS ? (int)nchunks : HOST_SLOTS;
-    // x,y of the final bundle stay resident when the HPD is wanted (rows 1,2 then live in the
-    // full-length arrays and the slots alias into them)
     const bool keep_xy = x_dev_keep && y_dev_keep;      // caller-owned device rows of length num
     if (keep_xy && ((reinterpret_cast<uintptr_t>(x_dev_keep) | reinterpret_cast<uintptr_t>(y_dev_keep)) & 15)) {
         set_error("pxf_host_trace_program: x_dev_keep/y_dev_keep must be 16-byte aligned");
         return PXF_ERR_INVALID;
     }
+    static int debug = -1;
+    if (debug < 0) { const char *e = getenv("PXF_HOST_DEBUG"); debug = (e && e[0] == '1') ? 1 : 0; }
+    const double t0 = now_ms();
+
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    HostRing &R = g_ring;
+    if ((rc = R.init())) return rc;
+    const int64_t chunk = num < HOST_CHUNK ? ((num + 1) & ~int64_t(1)) : HOST_CHUNK;
+    const int64_t nchunks = (num + chunk - 1) / chunk;
+    const int nslots = nchunks < HOST_SLOTS ? (int)nchunks : HOST_SLOTS;
+    // x,y of the final bundle stay resident when the HPD is wanted (rows 1,2 then live in
+    // full-length arrays and the slots alias into them)
     const bool xy_full = want_hpd || keep_xy;
     double *fx = nullptr, *fy = nullptr;
     if (xy_full) {
         if (keep_xy) { fx = x_dev_keep; fy = y_dev_keep; }
         else {
-            PXF_CUDA(cudaMalloc(&R.full_x, (size_t)(nchunks * chunk) * 8));
-            PXF_CUDA(cudaMalloc(&R.full_y, (size_t)(nchunks * chunk) * 8));
-            fx = R.full_x; fy = R.full_y;
+            if ((rc = R.full_x.ensure((size_t)(nchunks * chunk) * 8))) return rc;
+            if ((rc = R.full_y.ensure((size_t)(nchunks * chunk) * 8))) return rc;
+            fx = static_cast<double *>(R.full_x.p); fy = static_cast<double *>(R.full_y.p);
         }
-        if (want_alive) PXF_CUDA(cudaMalloc(&R.full_alive, (size_t)(nchunks * chunk)));
+        if (want_alive && (rc = R.full_alive.ensure((size_t)(nchunks * chunk)))) return rc;
     }
     for (int k = 0; k < nslots; k++) {
-        PXF_CUDA(cudaEventCreateWithFlags(&R.in_done[k], cudaEventDisableTiming));
-        PXF_CUDA(cudaEventCreateWithFlags(&R.run_done[k], cudaEventDisableTiming));
-        PXF_CUDA(cudaEventCreateWithFlags(&R.out_done[k], cudaEventDisableTiming));
         for (int r = 0; r < 10; r++) {
             if (!(USED & (1u << r))) continue;
             if (xy_full && (r == 1 || r == 2)) continue;
-            PXF_CUDA(cudaMalloc(&R.slot_rows[k][r], (size_t)chunk * 8));
+            if ((rc = R.slot_rows[k][r].ensure((size_t)chunk * 8))) return rc;
         }
-        if (want_alive && !xy_full) PXF_CUDA(cudaMalloc(&R.slot_alive[k], (size_t)chunk));
+        if (want_alive && !xy_full && (rc = R.slot_alive[k].ensure((size_t)chunk))) return rc;
     }
+    const double t1 = now_ms();
 
     int64_t alive_total = 0;
-    // per-chunk survivor counts are reduced on the host from the flags when the caller asks
-    // for them; the flags themselves are tiny next to the rows (1 B/ray)
     for (int64_t c = 0; c < nchunks; c++) {
         const int k = (int)(c % nslots);
         const int64_t lo = c * chunk;
         const int64_t n = (lo + chunk <= num) ? chunk : (num - lo);
         double *rows[10];
-        for (int r = 0; r < 10; r++) rows[r] = R.slot_rows[k][r];
+        for (int r = 0; r < 10; r++) rows[r] = static_cast<double *>(R.slot_rows[k][r].p);
         if (xy_full) { rows[1] = fx + lo; rows[2] = fy + lo; }
-        uint8_t *alive = want_alive ? (xy_full ? R.full_alive + lo : R.slot_alive[k]) : nullptr;
+        uint8_t *alive = want_alive ? (xy_full ? static_cast<uint8_t *>(R.full_alive.p) + lo
+                                               : static_cast<uint8_t *>(R.slot_alive[k].p)) : nullptr;
         // the slot is free once its previous D2H finished
         if (c >= nslots) PXF_CUDA(cudaStreamWaitEvent(R.s_in, R.out_done[k], 0));
         for (int r = 0; r < 10; r++)
@@ -131,7 +179,6 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
                 PXF_CUDA(cudaMemcpyAsync(rows[r], rows_host[r] + lo, (size_t)n * 8, cudaMemcpyHostToDevice, R.s_in));
         PXF_CUDA(cudaEventRecord(R.in_done[k], R.s_in));
         PXF_CUDA(cudaStreamWaitEvent(R.s_run, R.in_done[k], 0));
-        if (c >= nslots) PXF_CUDA(cudaStreamWaitEvent(R.s_run, R.out_done[k], 0));
         if ((rc = launch_program(rows, n, fp, alive, R.s_run))) return rc;
         PXF_CUDA(cudaEventRecord(R.run_done[k], R.s_run));
         PXF_CUDA(cudaStreamWaitEvent(R.s_out, R.run_done[k], 0));
@@ -143,53 +190,48 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
             PXF_CUDA(cudaMemcpyAsync(alive_host + lo, alive, (size_t)n, cudaMemcpyDeviceToHost, R.s_out));
         PXF_CUDA(cudaEventRecord(R.out_done[k], R.s_out));
     }
+    const double t2 = now_ms();
     PXF_CUDA(cudaStreamSynchronize(R.s_run));
+    const double t3 = now_ms();
 
     if (want_hpd) {
         const double *hx = fx, *hy = fy;
         int64_t hn = num;
-        double *cx = nullptr, *cy = nullptr;
+        pxf_stream_t ps = reinterpret_cast<pxf_stream_t>(R.s_run);
         if (want_alive) {
             // HPD over the surviving rays only: compact x,y by the alive flags first
-            size_t sb = pxf_compact_scratch_bytes(num);
-            void *scr = nullptr;
-            PXF_CUDA(cudaMalloc(&scr, sb));
+            if ((rc = R.scr.ensure(pxf_compact_scratch_bytes(num)))) return rc;
             int64_t cnt = 0;
-            rc = pxf_compact_count(R.full_alive, num, scr, &cnt, reinterpret_cast<pxf_stream_t>(R.s_run));
-            if (!rc && cnt > 0) {
-                if (cudaMalloc(&cx, (size_t)cnt * 8) != cudaSuccess || cudaMalloc(&cy, (size_t)cnt * 8) != cudaSuccess) {
-                    cudaFree(scr); if (cx) cudaFree(cx);
-                    set_error("pxf_host_trace_program: out of device memory"); return PXF_ERR_NOMEM;
-                }
+            const uint8_t *fa = static_cast<const uint8_t *>(R.full_alive.p);
+            if ((rc = pxf_compact_count(fa, num, R.scr.p, &cnt, ps))) return rc;
+            if (cnt > 0) {
+                if ((rc = R.cx.ensure((size_t)(cnt + 1) * 8)) || (rc = R.cy.ensure((size_t)(cnt + 1) * 8))) return rc;
                 const double *in2[2] = {fx, fy};
-                double *out2[2] = {cx, cy};
-                rc = pxf_compact_scatter(in2, out2, 2, R.full_alive, num, scr, reinterpret_cast<pxf_stream_t>(R.s_run));
-                cudaStreamSynchronize(R.s_run);
+                double *out2[2] = {static_cast<double *>(R.cx.p), static_cast<double *>(R.cy.p)};
+                if ((rc = pxf_compact_scatter(in2, out2, 2, fa, num, R.scr.p, ps))) return rc;
             }
-            cudaFree(scr);
-            if (rc) { if (cx) cudaFree(cx); if (cy) cudaFree(cy); return rc; }
-            hx = cx; hy = cy; hn = cnt;
+            hx = static_cast<const double *>(R.cx.p); hy = static_cast<const double *>(R.cy.p); hn = cnt;
             alive_total = cnt;
         }
         if (hn > 0) {
-            if (cudaMalloc(&R.misc, pxf_hpd_workspace_bytes() + 64) != cudaSuccess) {
-                if (cx) cudaFree(cx); if (cy) cudaFree(cy);
-                set_error("pxf_host_trace_program: out of device memory"); return PXF_ERR_NOMEM;
+            const size_t wb = pxf_hpd_workspace_bytes(hn);
+            if ((rc = R.misc.ensure(wb + 64))) return rc;
+            double *out = reinterpret_cast<double *>((char *)R.misc.p + wb);
+            double h[4] = {0, 0, 0, 0};
+            for (int mode = 0; mode < 2; mode++) {
+                if ((rc = pxf_hpd_unweighted_dev(hx, hy, hn, out, R.misc.p, mode, ps))) return rc;
+                PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, R.s_run));
+                PXF_CUDA(cudaStreamSynchronize(R.s_run));
+                if (h[3] != 0.) break;
             }
-            double *out = reinterpret_cast<double *>((char *)R.misc + pxf_hpd_workspace_bytes());
-            rc = pxf_hpd_unweighted_dev(hx, hy, hn, out, R.misc, reinterpret_cast<pxf_stream_t>(R.s_run));
-            double h[3] = {0, 0, 0};
-            if (!rc && cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, R.s_run) != cudaSuccess) rc = PXF_ERR_CUDA;
-            cudaStreamSynchronize(R.s_run);
             *hpd_host = h[0];
         } else {
             *hpd_host = __builtin_nan("");
         }
-        if (cx) cudaFree(cx);
-        if (cy) cudaFree(cy);
-        if (rc) return rc;
     }
+    const double t4 = now_ms();
     PXF_CUDA(cudaStreamSynchronize(R.s_out));
+    const double t5 = now_ms();
     if (alive_count_host) {
         if (!want_alive) *alive_count_host = num;
         else if (want_hpd) *alive_count_host = alive_total;
@@ -201,6 +243,10 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
             *alive_count_host = -1;   // flags were not requested anywhere
         }
     }
+    if (debug)
+        fprintf(stderr, "[pxf_host] num=%lld chunks=%lld: alloc %.1f ms, enqueue %.1f ms, wait-run %.1f ms, hpd %.1f ms, "
+                        "wait-d2h %.1f ms, total %.1f ms\n", (long long)num, (long long)nchunks, t1 - t0, t2 - t1,
+                t3 - t2, t4 - t3, t5 - t4, t5 - t0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("pxf_host_trace_program: %s", cudaGetErrorString(e)); return PXF_ERR_CUDA; }
     return PXF_OK;

@@ -89,20 +89,30 @@ def shard_range(num, rank, world):
 
 
 class CudaSelect:
-    """libpxf radix-select primitives on one shard (device-resident state)."""
+    """libpxf select primitives on one shard (device-resident state).  The gloo tests replace
+    this class by a numpy stand-in with the same interface to exercise the drivers below."""
 
     def __init__(self, x, y, cxy):
         self.x, self.y, self.cxy = x, y, cxy
         self.dev = x.device
         self.L = _lib.lib()
         self.s = stream_ptr(self.dev)
+        self.num = int(x.shape[0])
+        self.state = self._new_state()
+        self.hist, self.nan = self._views(self.state)
+        self.keys = None           # key buffer the histogram passes read (None: radii of x,y)
+        self.key_count = None
+
+    # -- state helpers
+    def _new_state(self):
         nbytes = int(self.L.pxf_select_state_bytes())
-        self.state = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=self.dev)   # 8-byte aligned
-        base = self.state.data_ptr()
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=self.dev)   # 8-byte aligned
+
+    def _views(self, state):
+        base = state.data_ptr()
         ho = (int(self.L.pxf_select_hist_ptr(base)) - base) // 8
         no = (int(self.L.pxf_select_nan_ptr(base)) - base) // 8
-        self.hist = self.state[ho:ho + 2 * 8192]
-        self.nan = self.state[no:no + 1]
+        return state[ho:ho + 2 * 8192], state[no:no + 1]
 
     def schedule(self):
         shift, bits = ctypes.c_int32(), ctypes.c_int32()
@@ -113,13 +123,18 @@ class CudaSelect:
             out.append((shift.value, bits.value))
         return out
 
+    # -- five-pass select over the shard's radii (or over a key buffer)
     def begin(self, k0, k1):
         _lib.check(self.L.pxf_select_begin(self.state.data_ptr(), k0, k1, self.s))
 
     def histogram(self, shift, bits):
         """Add this shard's digit histogram; returns the tensor to all-reduce."""
-        if self.x.shape[0] > 0:
-            _lib.check(self.L.pxf_select_hist(self.x.data_ptr(), self.y.data_ptr(), None, self.x.shape[0],
+        if self.keys is not None:
+            _lib.check(self.L.pxf_select_hist_keys(self.keys.data_ptr(), self.keys.shape[0],
+                                                   self.key_count.data_ptr() if self.key_count is not None else None,
+                                                   shift, bits, self.state.data_ptr(), self.s))
+        elif self.num > 0:
+            _lib.check(self.L.pxf_select_hist(self.x.data_ptr(), self.y.data_ptr(), None, self.num,
                                               self.cxy.data_ptr(), shift, bits, self.state.data_ptr(), self.s))
         return self.hist[:2 << bits]
 
@@ -129,27 +144,105 @@ class CudaSelect:
     def nan_count(self):
         return self.nan
 
-    def finish(self, total):
-        out = torch.empty(3, dtype=torch.float64, device=self.dev)
+    def finish(self, total, read=True):
+        """(2*median, lower, upper, valid); with read=False the 4 doubles stay on the device
+        in ``self.last`` and nothing is returned (no host sync)."""
+        out = torch.empty(4, dtype=torch.float64, device=self.dev)
         _lib.check(self.L.pxf_select_finish(self.state.data_ptr(), total, out.data_ptr(), self.s))
+        self.last = out
+        if not read:
+            return None
         h = out.cpu().numpy()
-        return float(h[0]), float(h[1]), float(h[2])
+        return float(h[0]), float(h[1]), float(h[2]), bool(h[3] != 0.)
+
+    # -- bracketed select
+    def bracket_params(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        ns = int(self.L.pxf_bracket_samples())
+        self.L.pxf_bracket_sample_ranks(ns, ctypes.byref(a), ctypes.byref(b))
+        return int(self.L.pxf_bracket_min_num()), ns, int(a.value), int(b.value)
+
+    def sample(self, nsamp):
+        """nsamp strided radii of this shard (device tensor)."""
+        keys = torch.empty(nsamp, dtype=torch.float64, device=self.dev)
+        _lib.check(self.L.pxf_select_sample(self.x.data_ptr(), self.y.data_ptr(), self.num, self.cxy.data_ptr(),
+                                            nsamp, keys.data_ptr(), self.s))
+        return keys
+
+    def use_keys(self, keys, count=None):
+        self.keys, self.key_count = keys, count
+
+    def collect(self, lohi):
+        """One pass over the shard: returns (candidate buffer, local counters[4] int64)."""
+        cap = int(self.L.pxf_bracket_capacity(self.num))
+        cand = torch.empty(cap, dtype=torch.float64, device=self.dev)
+        counters = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        _lib.check(self.L.pxf_bracket_collect(self.x.data_ptr(), self.y.data_ptr(), self.num, self.cxy.data_ptr(),
+                                              lohi.data_ptr(), cand.data_ptr(), cap, counters.data_ptr(), self.s))
+        counters[3] = (counters[1] > cap).to(torch.int64)      # this shard's buffer overflowed
+        return cand, counters, cap
+
+    def begin_bracket(self, k0, k1, counters, cap_total):
+        _lib.check(self.L.pxf_select_begin_bracket(self.state.data_ptr(), k0, k1, counters.data_ptr(), cap_total,
+                                                   self.s))
+
+
+def _five_passes(sel, group, reduce=True):
+    for shift, bits in sel.schedule():
+        h = sel.histogram(shift, bits)
+        if reduce:
+            all_reduce_sum(h, group)
+        sel.narrow(bits)
 
 
 def select_median_pair(sel, total, group=None):
-    """Drive a distributed exact select of the two middle order statistics of ``total``
-    keys spread over the ranks of ``group``.  ``sel`` provides the per-shard primitives
-    (``CudaSelect``; the gloo tests substitute a CPU stand-in to exercise this logic).
-    Returns (2*median, lower middle, upper middle), identical on every rank."""
+    """Distributed exact select of the two middle order statistics of ``total`` keys spread
+    over the ranks of ``group``: five passes, each all-reducing a 2x8192 histogram.
+    Returns (2*median, lower middle, upper middle, valid), identical on every rank."""
     k0 = (total - 1) // 2 if total > 0 else 0
     k1 = total // 2 if total > 0 else 0
+    sel.use_keys(None)
     sel.begin(k0, k1)
     if total > 0:
-        for shift, bits in sel.schedule():
-            h = sel.histogram(shift, bits)
-            all_reduce_sum(h, group)
-            sel.narrow(bits)
+        _five_passes(sel, group)
     all_reduce_sum(sel.nan_count(), group)
+    return sel.finish(total)
+
+
+def bracket_median_pair(sel, total, min_shard, group=None):
+    """The same statistic with ONE pass over the shards instead of five (see include/pxf.h,
+    "Bracketed select").  Every rank contributes an equal share of the sample; the sample is
+    all-gathered so that each rank derives the identical bracket; the per-shard counters and
+    the candidate histograms are all-reduced.  Returns None when the bundle is too small for
+    a bracket (caller uses ``select_median_pair``); a result with valid=False means the
+    bracket missed and the caller must fall back as well."""
+    world = _world(group)
+    min_num, nsamp, ra, rb = sel.bracket_params()
+    per = nsamp // world
+    if total < min_num or min_shard < max(4 * per, 1):
+        return None
+    mine = sel.sample(per)
+    if world > 1:
+        allk = torch.empty(per * world, dtype=mine.dtype, device=mine.device)
+        td.all_gather_into_tensor(allk, mine, group=group)
+    else:
+        allk = mine
+    n_s = per * world
+    scale = n_s / float(nsamp)
+    # bracket = two order statistics of the gathered sample (local select, no collective)
+    sel.use_keys(allk)
+    sel.begin(max(0, int(ra * scale)), min(n_s - 1, int(rb * scale) + 1))
+    _five_passes(sel, group, reduce=False)
+    sel.finish(n_s, read=False)
+    lohi = sel.last
+    cand, local, cap = sel.collect(lohi)
+    glob = local.clone()
+    caps = torch.tensor([cap], dtype=torch.int64, device=glob.device)
+    all_reduce_sum(glob, group)
+    all_reduce_sum(caps, group)
+    sel.use_keys(cand, local[1:2])
+    sel.begin_bracket((total - 1) // 2, total // 2, glob, int(caps.item()))
+    _five_passes(sel, group)
     return sel.finish(total)
 
 
@@ -159,10 +252,19 @@ def hpd(rays, group=None, return_stats=False):
     flush(rays)
     x, y = rays[1:3]
     dev = x.device
-    sums = all_reduce_sum(_sums(0, rays, None, 0., 0.), group)
+    sums = _sums(0, rays, None, 0., 0.)
+    sums[4] = float(x.shape[0])
+    big = sums.clone()
+    all_reduce_sum(sums[:4], group)
+    if _world(group) > 1:
+        td.all_reduce(big[4:5], op=td.ReduceOp.MIN, group=group)
     total = int(round(float(sums[3].item())))
+    min_shard = int(round(float(big[4].item())))
     with torch.cuda.device(dev):
         cxy = torch.empty(2, dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().pxf_centroid_from_sums(sums.data_ptr(), cxy.data_ptr(), stream_ptr(dev)))
-        res = select_median_pair(CudaSelect(x, y, cxy), total, group)
-    return res if return_stats else res[0]
+        sel = CudaSelect(x, y, cxy)
+        res = bracket_median_pair(sel, total, min_shard, group)
+        if res is None or not res[3]:
+            res = select_median_pair(sel, total, group)
+    return res[:3] if return_stats else res[0]

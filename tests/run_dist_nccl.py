@@ -1,0 +1,53 @@
+"""Executed under torchrun by tests/test_gpu_dist.py (one rank per GPU, NCCL): the sharded
+trace + analyses must reproduce the single-GPU result of the whole bundle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    td.init_process_group("nccl", device_id=dev)
+    import pyxfocus_b200 as pxf
+    from pyxfocus_b200 import dist
+
+    prog = (pxf.Program().transform(0., 0., 8400., 0., 0., 0.).wolterprimary(220., 8400., 1.).reflect()
+            .woltersecondary(220., 8400., 1.).reflect().flat())
+    ok = True
+    for total in (100_003, 6_000_001):            # five-pass path and bracketed path
+        lo, hi = dist.shard_range(total, rank, world)
+        shard = pxf.sources.subannulus(220., 220.6, 2 * np.pi, hi - lo, zhat=-1., rng="philox", seed=3, first=lo, device=dev)
+        prog.run(shard)
+        h = dist.hpd(shard)
+        rms = dist.rmsCentroid(shard)
+        cx, cy = dist.centroid(shard)
+        dz = dist.analyticImagePlane(shard)
+        # every rank recomputes the whole bundle alone and compares
+        whole = pxf.sources.subannulus(220., 220.6, 2 * np.pi, total, zhat=-1., rng="philox", seed=3, first=0, device=dev)
+        prog.run(whole)
+        assert torch.equal(whole[1][lo:hi], shard[1]) and torch.equal(whole[9][lo:hi], shard[9]), "shard != slice of whole"
+        h1 = pxf.analyses.hpd(whole)
+        r1 = pxf.analyses.rmsCentroid(whole)
+        c1 = pxf.analyses.centroid(whole)
+        d1 = pxf.analyses.analyticImagePlane(whole)
+        good = (abs(h - h1) <= 1e-9 * abs(h1) and abs(rms - r1) <= 1e-9 * r1 and abs(cx - c1[0]) <= 1e-15
+                and abs(cy - c1[1]) <= 1e-15 and abs(dz - d1) <= 1e-6 * max(1., abs(d1)))
+        print("rank %d total %d: hpd %.15e vs %.15e rms %.6e/%.6e dz %.6e/%.6e -> %s" % (rank, total, h, h1, rms, r1, dz, d1, good),
+              flush=True)
+        ok = ok and good
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    td.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

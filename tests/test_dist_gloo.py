@@ -19,28 +19,48 @@ SCHEDULE = [(51, 13), (38, 13), (25, 13), (12, 13), (0, 12)]
 
 
 class NumpySelect:
-    """CPU stand-in for dist.CudaSelect (same interface, same semantics)."""
+    """CPU stand-in for dist.CudaSelect (same interface, same semantics as the kernels)."""
 
-    def __init__(self, r):
-        self.keys = np.ascontiguousarray(r, dtype=np.float64).view(np.uint64)
-        self.isnan = np.isnan(r)
+    def __init__(self, x, y, cx, cy, min_num=2000, nsamp=4096):
+        self.r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+        self.num = self.r.shape[0]
         self.hist = torch.zeros(2 * 8192, dtype=torch.int64)
         self.nan = torch.zeros(1, dtype=torch.int64)
+        self.keys = None
+        self.key_count = None
+        self.valid = True
+        self.min_num, self.nsamp = min_num, nsamp
+        self.collect_calls = 0
 
     def schedule(self):
         return SCHEDULE
+
+    def _cur(self):
+        if self.keys is None:
+            return self.r
+        k = self.keys.numpy()
+        if self.key_count is not None:
+            k = k[:min(int(self.key_count.item()), k.shape[0])]
+        return k
+
+    def use_keys(self, keys, count=None):
+        self.keys, self.key_count = keys, count
 
     def begin(self, k0, k1):
         self.prefix = [0, 0]
         self.rank = [int(k0), int(k1)]
         self.nprefix = 1
+        self.valid = True
         self.hist.zero_()
         self.nan.zero_()
 
     def histogram(self, shift, bits):
         nb = 1 << bits
-        k = self.keys[~self.isnan]
-        self.nan += int(self.isnan.sum())
+        r = self._cur()
+        isnan = np.isnan(r)
+        k = np.ascontiguousarray(r[~isnan]).view(np.uint64)
+        if self.keys is None:
+            self.nan += int(isnan.sum())
         top = (k >> np.uint64(shift + bits)) if shift + bits < 64 else np.zeros_like(k)
         dig = ((k >> np.uint64(shift)) & np.uint64(nb - 1)).astype(np.int64)
         h = np.zeros(2 * nb, dtype=np.int64)
@@ -62,7 +82,7 @@ class NumpySelect:
             b = int(np.searchsorted(c, self.rank[j], side="right"))
             base = int(c[b - 1]) if b > 0 else 0
             p = self.prefix[j] if self.nprefix == 2 else self.prefix[0]
-            newp.append(((p << bits) | b) & (2 ** 64 - 1))
+            newp.append(((p << bits) | min(b, nb - 1)) & (2 ** 64 - 1))
             self.rank[j] -= base
         self.prefix = newp
         self.nprefix = 1 if newp[0] == newp[1] else 2
@@ -71,13 +91,49 @@ class NumpySelect:
     def nan_count(self):
         return self.nan
 
-    def finish(self, total):
+    def finish(self, total, read=True):
         a = np.array([self.prefix[0]], dtype=np.uint64).view(np.float64)[0]
         b = np.array([self.prefix[1]], dtype=np.uint64).view(np.float64)[0]
         med = (a + b) / 2.
         if total == 0 or int(self.nan.item()) > 0:
             med = float("nan")
-        return 2. * med, float(a), float(b)
+        self.last = torch.tensor([2. * med, a, b, 1. if self.valid else 0.], dtype=torch.float64)
+        if not read:
+            return None
+        return 2. * med, float(a), float(b), self.valid
+
+    # bracketed select
+    def bracket_params(self):
+        sigma = .5 / np.sqrt(self.nsamp)
+        d = int(np.ceil(6 * sigma * self.nsamp)) + 1
+        return self.min_num, self.nsamp, max(0, self.nsamp // 2 - d), min(self.nsamp - 1, self.nsamp // 2 + d)
+
+    def sample(self, nsamp):
+        idx = (np.arange(nsamp, dtype=np.int64) * self.num) // nsamp
+        return torch.from_numpy(self.r[idx].copy())
+
+    def collect(self, lohi):
+        self.collect_calls += 1
+        lo, hi = float(lohi[1]), float(lohi[2])
+        cap = max(64, self.num // 4)
+        r = self.r
+        inside = r[(r >= lo) & (r <= hi)]
+        cand = torch.zeros(cap, dtype=torch.float64)
+        cand[:min(cap, inside.shape[0])] = torch.from_numpy(inside[:cap].copy())
+        counters = torch.tensor([int((r < lo).sum()), inside.shape[0], int(np.isnan(r).sum()),
+                                 int(inside.shape[0] > cap)], dtype=torch.int64)
+        return cand, counters, cap
+
+    def begin_bracket(self, k0, k1, counters, cap_total):
+        below, ncand, nan, over = [int(v) for v in counters.tolist()]
+        ok = over == 0 and ncand <= cap_total and k0 >= below and k1 < below + ncand
+        self.prefix = [0, 0]
+        self.rank = [k0 - below, k1 - below] if ok else [0, 0]
+        self.nprefix = 1
+        self.valid = ok
+        self.hist.zero_()
+        self.nan.zero_()
+        self.nan += nan
 
 
 def _free_port():
@@ -96,8 +152,8 @@ def _worker(rank, world, port, n, seed, with_nan, q):
     rng = np.random.default_rng(seed)
     x = rng.normal(3., 1e-3, n)
     y = rng.standard_cauchy(n) * 1e-3 - 1.
-    x[: n // 4] = x[0]
-    y[: n // 4] = y[0]                                   # exact ties across shards
+    x[: n // 20] = x[0]
+    y[: n // 20] = y[0]                                  # exact ties across shards
     if with_nan:
         x[n // 2] = np.nan
     lo, hi = dist.shard_range(n, rank, world)
@@ -106,14 +162,19 @@ def _worker(rank, world, port, n, seed, with_nan, q):
     s = torch.tensor([float(hi - lo), xs.sum(), ys.sum()], dtype=torch.float64)
     dist.all_reduce_sum(s)
     cx, cy = float(s[1] / s[0]), float(s[2] / s[0])
-    r = np.sqrt((xs - cx) ** 2 + (ys - cy) ** 2)
-    res = dist.select_median_pair(NumpySelect(r), n)
-    q.put((rank, res, cx, cy))
+    sel = NumpySelect(xs, ys, cx, cy)
+    m = torch.tensor([float(hi - lo)], dtype=torch.float64)
+    td.all_reduce(m, op=td.ReduceOp.MIN)
+    res = dist.bracket_median_pair(sel, n, int(m.item()))
+    used_bracket = res is not None and res[3]
+    if not used_bracket:
+        res = dist.select_median_pair(sel, n)
+    q.put((rank, res[:3], cx, cy, bool(used_bracket), sel.collect_calls))
     td.barrier()
     td.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,with_nan", [(2, 100_001, False), (3, 4_100, False), (2, 1000, True)])
+@pytest.mark.parametrize("world,n,with_nan", [(2, 100_001, False), (3, 4_100, False), (2, 60_000, True)])
 def test_sharded_exact_median_over_gloo(world, n, with_nan):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -129,13 +190,15 @@ def test_sharded_exact_median_over_gloo(world, n, with_nan):
     rng = np.random.default_rng(123)
     x = rng.normal(3., 1e-3, n)
     y = rng.standard_cauchy(n) * 1e-3 - 1.
-    x[: n // 4] = x[0]
-    y[: n // 4] = y[0]
+    x[: n // 20] = x[0]
+    y[: n // 20] = y[0]
     if with_nan:
         x[n // 2] = np.nan
     res0 = out[0][1]
-    for rank, res, cx, cy in out:
+    for rank, res, cx, cy, used, calls in out:
         assert res == res0 or (np.isnan(res[0]) and np.isnan(res0[0])), "ranks disagree"
+        if n >= 50_000 and not with_nan:
+            assert used and calls == 1, "bracket path (one pass over the shard) not taken"
     cx, cy = out[0][2], out[0][3]
     r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
     if with_nan:

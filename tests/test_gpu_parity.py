@@ -409,7 +409,7 @@ def test_analyses_match_numpy(pxf, golden):
     assert np.allclose(cdf.cpu().numpy(), g["rhocdf_cdf"], rtol=1e-12, atol=0)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 1000, 1001, 65_536, 1_000_003])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 1000, 1001, 65_536, 1_000_003, 2_097_152, 3_000_001, 6_000_000])
 def test_hpd_exact_order_statistics(pxf, n):
     """Unweighted hpd == 2*np.median(r): the select must return the exact middle order
     statistics (even n: mean of the two)."""
@@ -429,10 +429,29 @@ def test_hpd_exact_order_statistics(pxf, n):
     assert got == 2. * np.median(r)
 
 
+def test_hpd_bracket_fallback_on_ties_at_the_median(pxf):
+    """60 % of the radii identical and sitting on the median: the bracketed select overflows its
+    candidate buffer, flags itself invalid and the five-pass select takes over -- still exact."""
+    n = 4_000_001
+    rng = np.random.default_rng(41)
+    cpu = random_bundle(n, 41)
+    cpu[1][:] = rng.normal(0, 1., n)
+    cpu[2][:] = rng.normal(0, 1., n)
+    th = rng.uniform(0, 2 * np.pi, int(.6 * n))
+    cpu[1][: th.size] = 1.17 * np.cos(th[0])
+    cpu[2][: th.size] = 1.17 * np.sin(th[0])
+    dev = to_dev(cpu)
+    got = pxf.analyses.hpd(dev)
+    r = pxf.analyses.rho(dev, cent=True).cpu().numpy()
+    assert got == 2. * np.median(r)
+    assert got == pytest.approx(pyref.hpd(cpu), rel=1e-9)
+
+
 def test_hpd_nan_propagates(pxf):
-    cpu = random_bundle(1001, 35)
-    cpu[1][17] = np.nan
-    assert np.isnan(pxf.analyses.hpd(to_dev(cpu)))
+    for n in (1001, 2_500_000):
+        cpu = random_bundle(n, 35)
+        cpu[1][17] = np.nan
+        assert np.isnan(pxf.analyses.hpd(to_dev(cpu)))
 
 
 def test_weighted_hpd_and_sort(pxf):
