@@ -219,9 +219,11 @@ def run_engine(args):
     prog = (pxf.Program().transform(0., 0., Z0, 0., 0., 0.).wolterprimary(R0, Z0, PSI).reflect()
             .woltersecondary(R0, Z0, PSI).reflect().flat())
 
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+
     def step():
-        prog.run(src, out=out)
-        return pdist.hpd(out) if world > 1 else pxf.analyses.hpd(out)
+        prog.run(src, out=out, sums=sums)          # trace kernel also emits the centroid sums
+        return pdist.hpd(out, sums=sums) if world > 1 else pxf.analyses.hpd(out, sums=sums)
 
     def barrier():
         if world > 1:
@@ -242,9 +244,9 @@ def run_engine(args):
     ev0.record()
     for k in range(args.steps):
         kev[k][0].record()
-        prog.run(src, out=out)
+        prog.run(src, out=out, sums=sums)
         kev[k][1].record()
-        hp = pdist.hpd(out) if world > 1 else pxf.analyses.hpd(out)
+        hp = pdist.hpd(out, sums=sums) if world > 1 else pxf.analyses.hpd(out, sums=sums)
     ev1.record()
     barrier()
     launches = pxf.launch_count() - launches0

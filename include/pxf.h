@@ -184,6 +184,13 @@ int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, in
  * untouched, e.g. to trace one source bundle through several configurations. */
 int pxf_trace_program_to(double *const rays_in[10], double *const rays_out[10], int64_t num,
                          const pxf_op *ops, int32_t nops, uint8_t *alive, pxf_stream_t stream);
+/* As above (rays_out == NULL: in place) and, from the same kernel, the centroid sums of the
+ * FINAL bundle over the surviving rays: sums_dev (device double[16]) = {count, sum x, sum y,
+ * count}, i.e. what analyses.centroid / hpd (analyses.py:16-22,88-97) need next -- no extra
+ * pass over x,y.  scratch: pxf_sums_scratch_bytes() device bytes. */
+int pxf_trace_program_sums(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                           const pxf_op *ops, int32_t nops, uint8_t *alive, double *sums_dev,
+                           void *scratch, pxf_stream_t stream);
 
 /* ======================= vignetting / compaction ======================== */
 /* flags[i] = (l^2+m^2+n^2 > .1), the default predicate of transformations.vignette
@@ -281,6 +288,13 @@ int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_
 size_t pxf_hpd_workspace_bytes(int64_t num);
 int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev,
                            void *workspace, int32_t mode, pxf_stream_t stream);
+/* Same with the centroid sums {count, sum x, sum y} already on the device (sums_dev, e.g. from
+ * pxf_trace_program_sums); NULL computes them with one pass over x,y. */
+int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const double *sums_dev,
+                          double *out_dev, void *workspace, int32_t mode, pxf_stream_t stream);
+/* host-result convenience of the above (synchronises; falls back to the five-pass select itself) */
+int pxf_hpd_with_sums(const double *x, const double *y, int64_t num, const double *sums_dev,
+                      double *hpd_host, pxf_stream_t stream);
 /* rows_out[r][i] = rows_in[r][idx[i]] for nrows <= 16 rows (vignette with an index array,
  * transformations.py:225).  rows_in/rows_out are HOST arrays of device pointers;
  * table_scratch: >= 256 B device. */

@@ -10,8 +10,8 @@ $SMALL > $O/${R}_bench_small.json 2> $O/${R}_bench_small.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $O/${R}_launches.csv $SMALL > $O/${R}_ncu_launches.log 2>&1
 $SMALL > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_program -s 3 -c 1 \
-    -o $O/${R}_k_program -f $SMALL > $O/${R}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_chain -s 3 -c 1 \
+    -o $O/${R}_k_chain -f $SMALL > $O/${R}_ncu_full.log 2>&1
 $SMALL > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_select_hist -s 15 -c 2 \
-    -o $O/${R}_k_select_hist -f $SMALL > $O/${R}_ncu_full_select.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_bracket_collect -s 3 -c 1 \
+    -o $O/${R}_k_bracket_collect -f $SMALL > $O/${R}_ncu_full_select.log 2>&1

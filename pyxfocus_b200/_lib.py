@@ -64,6 +64,7 @@ SIGNATURES = {
     # fused program
     "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_to": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _st]),
+    "pxf_trace_program_sums": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _dp, _vp, _st]),
     # vignetting / compaction
     "pxf_vignette_flags": (_c.c_int, [_dp] * 3 + [_i64, _vp, _st]),
     "pxf_compact_scratch_bytes": (_sz, [_i64]),
@@ -94,6 +95,8 @@ SIGNATURES = {
     "pxf_select_hist_keys": (_c.c_int, [_dp, _i64, _vp, _i32, _i32, _vp, _st]),
     "pxf_hpd_workspace_bytes": (_sz, [_i64]),
     "pxf_hpd_unweighted_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _i32, _st]),
+    "pxf_hpd_from_sums_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _vp, _i32, _st]),
+    "pxf_hpd_with_sums": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _st]),
     "pxf_centroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _vp, _st]),
     "pxf_rmscentroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_hpd": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),

@@ -127,17 +127,23 @@ def rhocdf(rays, weights=None, cent=True):
     return rs, cdf
 
 
-def hpd(rays, weights=None, cent=True):
+def hpd(rays, weights=None, cent=True, sums=None):
     """Half-power diameter about the centroid (the reference ignores ``cent``,
     analyses.py:90).  Unweighted: 2*median(r).  Weighted:
-    r[argmin|cdf-.75|] - r[argmin|cdf-.25|]."""
+    r[argmin|cdf-.75|] - r[argmin|cdf-.25|].
+    ``sums`` (unweighted only): the centroid sums ``Program.run(..., sums=...)`` produced for
+    this very bundle; saves the pass over x,y that computes them."""
     flush(rays)
     x, y = rays[1:3]
     w = _w(weights, x)
     out = ctypes.c_double()
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().pxf_hpd(x.data_ptr(), y.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(out),
-                                      stream_ptr(x.device)))
+        if sums is not None and w is None:
+            _lib.check(_lib.lib().pxf_hpd_with_sums(x.data_ptr(), y.data_ptr(), x.shape[0], sums.data_ptr(),
+                                                    ctypes.byref(out), stream_ptr(x.device)))
+        else:
+            _lib.check(_lib.lib().pxf_hpd(x.data_ptr(), y.data_ptr(), _ptr(w), x.shape[0], ctypes.byref(out),
+                                          stream_ptr(x.device)))
     return out.value
 
 

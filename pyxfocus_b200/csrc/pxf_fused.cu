@@ -73,8 +73,9 @@ PXF_DEV bool run_program(Ray &r, const FusedProgram &prog)
 template <bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK)
 k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
-          const __grid_constant__ FusedProgram prog)
+          double *__restrict__ partials, const __grid_constant__ FusedProgram prog)
 {
+    double cnt = 0., sx = 0., sy = 0.;
     // P: rows read, Q: rows written (Q == P for the in-place f2py semantics)
     const unsigned LM = prog.load_mask, SM = prog.store_mask;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,6 +90,8 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const bool kb = run_program(b, prog);
             fstore2(a, b, Q, SM, i);
             if (alive) { alive[i] = ka ? 1 : 0; alive[i + 1] = kb ? 1 : 0; }
+            if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
+            if (kb) { cnt += 1.; sx += b.x; sy += b.y; }
         }
         if ((num & 1) && tid == 0) {
             const int64_t i = num - 1;
@@ -97,6 +100,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const bool ka = run_program(a, prog);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
+            if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
         }
     } else {
         for (int64_t i = tid; i < num; i += nthr) {
@@ -105,8 +109,10 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const bool ka = run_program(a, prog);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
+            if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
         }
     }
+    if (partials) centroid_block_reduce(cnt, sx, sy, partials);
 }
 
 // rows read (use) / possibly written (st) / unconditionally overwritten (kill) by each op
@@ -209,7 +215,7 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
 }
 
 int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s,
-                   double *const rays_out[10])
+                   double *const rays_out[10], double *partials, int *grid_out)
 {
     if (num < 0 || !rays) { set_error("program: bad argument"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
@@ -231,7 +237,7 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
     }
     {
         // statically specialised kernel for the canonical chains, else the interpreter below
-        int rc = launch_chain(P, Q, num, fp, alive, aligned, s);
+        int rc = launch_chain(P, Q, num, fp, alive, aligned, s, partials, grid_out);
         if (rc != PXF_ERR_UNSUPPORTED) return rc;
     }
     static int ctas[2] = {0, 0};
@@ -245,10 +251,12 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
     }
     if (aligned) {
         int grid = grid_for((num + 1) >> 1, PXF_BLOCK, ctas[v]);
-        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, fp);
+        if (grid_out) *grid_out = grid;
+        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
     } else {
         int grid = grid_for(num, PXF_BLOCK, ctas[v]);
-        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, fp);
+        if (grid_out) *grid_out = grid;
+        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
     }
     count_launch();
     return check_launch("k_program");
@@ -264,7 +272,7 @@ extern "C" int pxf_trace_program(double *const rays[10], int64_t num, const pxf_
     FusedProgram fp;
     int rc = build_program(fp, ops, nops);
     if (rc) return rc;
-    return launch_program(rays, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), nullptr);
+    return launch_program(rays, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr);
 }
 
 extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const rays_out[10], int64_t num,
@@ -277,5 +285,31 @@ extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const ray
     // out of place: rows that are read but never written must still appear in the output
     // bundle, so every row the program touches is stored
     fp.store_mask |= fp.load_mask;
-    return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out);
+    return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out, nullptr, nullptr);
+}
+
+// pxf_analysis.cu
+namespace pxf { int sums_finalize(const double *partial, int nblocks, int ns, double *out_dev, cudaStream_t s); }
+
+extern "C" int pxf_trace_program_sums(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                                      const pxf_op *ops, int32_t nops, uint8_t *alive, double *sums_dev,
+                                      void *scratch, pxf_stream_t stream)
+{
+    if (!sums_dev || !scratch) { set_error("pxf_trace_program_sums: null sums/scratch"); return PXF_ERR_INVALID; }
+    FusedProgram fp;
+    int rc = build_program(fp, ops, nops);
+    if (rc) return rc;
+    if (rays_out) fp.store_mask |= fp.load_mask;
+    // the sums need the final x,y in registers: make sure they are loaded even if the program
+    // itself never reads them
+    fp.load_mask |= (R_X | R_Y) & ~fp.store_mask;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (num == 0) {
+        PXF_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), s));
+        return PXF_OK;
+    }
+    int grid = 0;
+    rc = launch_program(rays_in, num, fp, alive, s, rays_out, static_cast<double *>(scratch), &grid);
+    if (rc) return rc;
+    return sums_finalize(static_cast<const double *>(scratch), grid, 4, sums_dev, s);
 }

@@ -56,13 +56,45 @@ PXF_DEV void fstore2(const Ray &a, const Ray &b, const RowPtrs &P, unsigned M, i
     FST2(R_M, 5, m) FST2(R_N, 6, n) FST2(R_UX, 7, ux) FST2(R_UY, 8, uy) FST2(R_UZ, 9, uz)
 }
 
+// Per-CTA partial sums of (count, x, y) over the final state of the surviving rays -- the
+// centroid that analyses.hpd / rmsCentroid need next -- written by the trace kernel itself so
+// that no extra pass over x,y is needed.  Layout matches k_sums: partial[blockIdx*9 + {0,1,2,3}]
+// = {count, sum x, sum y, count}.
+#define PXF_NSUM 9
+PXF_DEV void centroid_block_reduce(double cnt, double sx, double sy, double *__restrict__ partial)
+{
+    __shared__ double sh[3][PXF_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[3] = {cnt, sx, sy};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+        if (lane == 0) sh[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double t = lane < PXF_BLOCK / 32 ? sh[k][lane] : 0.;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+                partial[(int64_t)blockIdx.x * PXF_NSUM + k] = t;
+                if (k == 0) partial[(int64_t)blockIdx.x * PXF_NSUM + 3] = t;
+            }
+        }
+    }
+}
+
 // pxf_fused.cu
 int build_program(FusedProgram &fp, const pxf_op *ops, int nops);
+// partials (nullable): device double[grid*9] receiving the per-CTA centroid sums; *grid_out = CTAs launched
 int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s,
-                   double *const rays_out[10] = nullptr);
+                   double *const rays_out[10] = nullptr, double *partials = nullptr, int *grid_out = nullptr);
 // pxf_chain.cu: statically specialised kernels for the reference's canonical chains.  Returns
 // PXF_OK after launching, PXF_ERR_UNSUPPORTED when no specialisation matches the op list.
 int launch_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const FusedProgram &fp, uint8_t *alive,
-                 bool aligned, cudaStream_t s);
+                 bool aligned, cudaStream_t s, double *partials, int *grid_out);
 
 }  // namespace pxf

@@ -246,13 +246,14 @@ def bracket_median_pair(sel, total, min_shard, group=None):
     return sel.finish(total)
 
 
-def hpd(rays, group=None, return_stats=False):
+def hpd(rays, group=None, return_stats=False, sums=None):
     """Unweighted HPD (2 x median radius about the global centroid) of a sharded bundle;
-    exact, identical on every rank."""
+    exact, identical on every rank.  ``sums``: this shard's centroid sums from
+    ``Program.run(..., sums=...)`` (saves the local pass that computes them)."""
     flush(rays)
     x, y = rays[1:3]
     dev = x.device
-    sums = _sums(0, rays, None, 0., 0.)
+    sums = _sums(0, rays, None, 0., 0.) if sums is None else sums.clone()
     sums[4] = float(x.shape[0])
     big = sums.clone()
     all_reduce_sum(sums[:4], group)

@@ -132,11 +132,14 @@ class Program:
                 arr[k].p[j] = v
         return arr
 
-    def run(self, rays, alive=None, out=None):
+    def run(self, rays, alive=None, out=None, sums=None):
         """Execute on a bundle (list of ten CUDA fp64 rows).  Returns the ``alive`` uint8
         tensor when the program contains a vignette predicate (allocated if not given).
         ``out``: optional second bundle -- rows are read from ``rays`` and every row the program
-        touches is written to ``out``; ``rays`` is left untouched."""
+        touches is written to ``out``; ``rays`` is left untouched.
+        ``sums``: optional CUDA float64 tensor (>= 16 entries) that receives, from the same
+        kernel, {count, sum x, sum y, count} of the final bundle over the surviving rays --
+        pass it on to ``analyses.hpd(..., sums=sums)`` to skip the centroid pass."""
         if not self.ops:
             return alive
         if len(self.ops) > MAX_OPS:
@@ -146,7 +149,7 @@ class Program:
             if head.has_vignette() or tail.has_vignette():
                 raise ValueError("programs with vignette predicates are limited to %d ops" % MAX_OPS)
             head.run(rays, out=out)
-            return tail.run(out if out is not None else rays)
+            return tail.run(out if out is not None else rays, sums=sums)
         dev = rays[1].device
         num = rays[1].shape[0]
         for r in rays:
@@ -158,12 +161,21 @@ class Program:
         ptrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in rays])
         ops = self.c_ops()
         ap = alive.data_ptr() if alive is not None else None
+        optrs = None
+        if out is not None:
+            optrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in out])
         with torch.cuda.device(dev):
-            if out is None:
-                rc = _lib.lib().pxf_trace_program(ptrs, num, ops, len(self.ops), ap, stream_ptr(dev))
+            L = _lib.lib()
+            if sums is not None:
+                if not sums.is_cuda or sums.dtype != torch.float64 or sums.numel() < 16 or not sums.is_contiguous():
+                    raise ValueError("sums must be a contiguous CUDA float64 tensor with >= 16 entries")
+                scratch = torch.empty(int(L.pxf_sums_scratch_bytes()), dtype=torch.uint8, device=dev)
+                rc = L.pxf_trace_program_sums(ptrs, optrs, num, ops, len(self.ops), ap, sums.data_ptr(),
+                                              scratch.data_ptr(), stream_ptr(dev))
+            elif out is None:
+                rc = L.pxf_trace_program(ptrs, num, ops, len(self.ops), ap, stream_ptr(dev))
             else:
-                optrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in out])
-                rc = _lib.lib().pxf_trace_program_to(ptrs, optrs, num, ops, len(self.ops), ap, stream_ptr(dev))
+                rc = L.pxf_trace_program_to(ptrs, optrs, num, ops, len(self.ops), ap, stream_ptr(dev))
         _lib.check(rc)
         return alive
 

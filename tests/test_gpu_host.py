@@ -109,3 +109,36 @@ def test_sharded_hpd_single_rank_matches_analyses(pxf):
         ax, ay = pxf.analyses.centroid(dev)
         assert (cx, cy) == (ax, ay)
         assert pxf.dist.analyticImagePlane(dev) == pytest.approx(pxf.analyses.analyticImagePlane(dev), rel=1e-12)
+
+
+def test_fused_centroid_sums(pxf):
+    """Program.run(..., sums=) returns the centroid sums of the final bundle from the trace
+    kernel itself (specialised chain and generic interpreter) and hpd(..., sums=) uses them."""
+    import torch
+    for n in (1, 50_001, 3_000_001):
+        cpu = chains.wolter1_source(n, seed=56)
+        for steps in (chains.wolter1_steps(), chains.wolter1_steps()[:4]):          # chain kernel / interpreter
+            dev = to_dev(cpu)
+            ref = to_dev(cpu)
+            sums = torch.zeros(16, dtype=torch.float64, device="cuda")
+            prog = steps_to_program(steps)
+            prog.run(dev, sums=sums)
+            prog.run(ref)
+            assert_bit_equal(to_host(dev), to_host(ref), what="sums variant changes no ray")
+            s = sums.cpu().numpy()
+            x, y = to_host(ref)[1], to_host(ref)[2]
+            assert s[0] == n and s[3] == n
+            assert s[1] == pytest.approx(x.sum(), rel=1e-11, abs=1e-9)
+            assert s[2] == pytest.approx(y.sum(), rel=1e-11, abs=1e-9)
+            h0 = pxf.analyses.hpd(ref)
+            assert pxf.analyses.hpd(dev, sums=sums) == pytest.approx(h0, rel=1e-9)
+    # with vignetting the sums cover the surviving rays only
+    cpu = chains.wolter1_source(200_001, seed=57, dphi=1.2)
+    dev = to_dev(cpu)
+    sums = torch.zeros(16, dtype=torch.float64, device="cuda")
+    prog = (pxf.Program().transform(0, 0, 8400., 0, 0, 0).wolterprimary(220., 8400., 1.).reflect()
+            .vignette_abs(2, 50.).woltersecondary(220., 8400., 1.).reflect().flat())
+    alive = prog.run(dev, sums=sums).bool()
+    s = sums.cpu().numpy()
+    assert s[0] == int(alive.sum())
+    assert s[1] == pytest.approx(float(dev[1][alive].sum()), rel=1e-11, abs=1e-9)
