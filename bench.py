@@ -223,7 +223,7 @@ def run_engine(args):
 
     def step():
         prog.run(src, out=out, sums=sums)          # trace kernel also emits the centroid sums
-        return pdist.hpd(out, sums=sums) if world > 1 else pxf.analyses.hpd(out, sums=sums)
+        return pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
 
     def barrier():
         if world > 1:
@@ -246,7 +246,7 @@ def run_engine(args):
         kev[k][0].record()
         prog.run(src, out=out, sums=sums)
         kev[k][1].record()
-        hp = pdist.hpd(out, sums=sums) if world > 1 else pxf.analyses.hpd(out, sums=sums)
+        hp = pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
     ev1.record()
     barrier()
     launches = pxf.launch_count() - launches0
@@ -277,9 +277,10 @@ def run_engine(args):
     achieved = TRACE_BYTES_PER_RAY * n / (trace_ms * 1e-3) / 1e9
     traffic = None
     try:
+        # dram__bytes_read+write of the fused kernel from the ncu --set full capture (taken at
+        # 2e7 rays/launch; the kernel streams, so bytes scale with the ray count)
         tj = json.load(open(os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")))
-        if int(tj.get("rays_per_launch", -1)) == n:
-            traffic = tj.get("dram_bytes_per_launch")
+        traffic = float(tj["dram_bytes_per_ray"]) * n
     except (OSError, ValueError):
         pass
     line = {

@@ -127,6 +127,25 @@ int pxf_spocone(double *x, double *y, double *z, double *l, double *m, double *n
                 double *ux, double *uy, double *uz, int64_t num, double R0, double tg,
                 const uint8_t *mask, pxf_stream_t stream);
 
+/* Legendre-Legendre deformed shells.  coeff/axial/az are HOST pointers (cnum terms, orders
+ * 0..15), like the Zernike tables below. */
+/* woltsurf.f95:219-288 */
+int pxf_wolterprimll(double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num, double r0, double z0,
+                     double zmax, double zmin, double dphi, const double *coeff, const int32_t *axial,
+                     const int32_t *az, int32_t cnum, const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:293-379 */
+int pxf_woltersecll(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                    double zmax, double zmin, double dphi, const double *coeff, const int32_t *axial,
+                    const int32_t *az, int32_t cnum, const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:643-718 */
+int pxf_ellipsoidwoltll(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                        double S, double zmax, double zmin, double dphi, const double *coeff,
+                        const int32_t *axial, const int32_t *az, int32_t cnum, const uint8_t *mask,
+                        pxf_stream_t stream);
+
 /* ======================= zernsurf ======================================= */
 /* zernsurf.f95:8-101.  coeff/rorder/aorder are HOST pointers (arrsize entries; the f2py
  * wrapper receives them as small numpy arrays, surfaces.py:39-43).  rorder[i] <= 15. */
@@ -265,8 +284,9 @@ int pxf_centroid_from_sums(const double *sums_dev, double *cxy_dev, pxf_stream_t
  * candidates (pxf_select_begin_bracket -> pxf_select_hist_keys/narrow x5 -> pxf_select_finish).
  * A miss (rank outside the bracket, buffer overflow) marks the state invalid -- out_dev[3]==0
  * from pxf_select_finish -- and the caller falls back to the five-pass select: the result is
- * exact either way.  counters: device uint64[4] = {#below, #inside, #NaN, #overflowed shards},
- * zeroed by the caller; a sharded bundle all-reduces them. */
+ * exact either way.  counters: device uint64[5] = {#below, #inside, #NaN, #overflowed shards,
+ * summed capacities}, zeroed by the caller; a sharded bundle all-reduces them;
+ * pxf_select_begin_bracket reads the capacity from counters[4] when cap_total < 0. */
 int64_t pxf_bracket_min_num(void);
 int32_t pxf_bracket_samples(void);
 int64_t pxf_bracket_capacity(int64_t num);

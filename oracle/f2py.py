@@ -63,6 +63,9 @@ def _declare(L):
     L.pxfo_wsprimary.argtypes = nine + [_i64, _d, _d, _d]
     L.pxfo_wssecondary.argtypes = nine + [_i64, _d, _d, _d]
     L.pxfo_spocone.argtypes = nine + [_i64, _d, _d]
+    L.pxfo_wolterprimll.argtypes = nine + [_i64, _d, _d, _d, _d, _d, _dp, _ip, _ip, _i32]
+    L.pxfo_woltersecll.argtypes = nine + [_i64, _d, _d, _d, _d, _d, _d, _dp, _ip, _ip, _i32]
+    L.pxfo_ellipsoidwoltll.argtypes = nine + [_i64, _d, _d, _d, _d, _d, _d, _d, _dp, _ip, _ip, _i32]
     L.pxfo_zernset.argtypes = [_d, _d, _ip, _ip, _i32, _dp, _dp, _dp]
     L.pxfo_tracezern.argtypes = nine + [_i64, _dp, _ip, _ip, _i32, _d]
     L.pxfo_tracezernopd.argtypes = [_dp] * 10 + [_i64, _dp, _ip, _ip, _i32, _d, _d]
@@ -223,7 +226,35 @@ def _spocone(x, y, z, l, m, n, ux, uy, uz, r0, tg):
     lib().pxfo_spocone(*p, num, r0, tg)
 
 
-woltsurf = SimpleNamespace(wolterprimary=_wolterprimary, wolterprimaryopd=_wolterprimaryopd,
+def _ll_tables(coeff, axial, az):
+    cb, cp = _in(coeff)
+    a, b = _orders(axial, az, cb.shape[0])
+    return cb, cp, a, b
+
+
+def _wolterprimll(x, y, z, l, m, n, ux, uy, uz, r0, z0, zmax, zmin, dphi, coeff, axial, az):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    cb, cp, a, b = _ll_tables(coeff, axial, az)
+    lib().pxfo_wolterprimll(*p, num, r0, z0, zmax, zmin, dphi, cp, a.ctypes.data_as(_ip), b.ctypes.data_as(_ip),
+                            cb.shape[0])
+
+
+def _woltersecll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, zmax, zmin, dphi, coeff, axial, az):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    cb, cp, a, b = _ll_tables(coeff, axial, az)
+    lib().pxfo_woltersecll(*p, num, r0, z0, psi, zmax, zmin, dphi, cp, a.ctypes.data_as(_ip),
+                           b.ctypes.data_as(_ip), cb.shape[0])
+
+
+def _ellipsoidwoltll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, s, zmax, zmin, dphi, coeff, axial, az):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    cb, cp, a, b = _ll_tables(coeff, axial, az)
+    lib().pxfo_ellipsoidwoltll(*p, num, r0, z0, psi, s, zmax, zmin, dphi, cp, a.ctypes.data_as(_ip),
+                               b.ctypes.data_as(_ip), cb.shape[0])
+
+
+woltsurf = SimpleNamespace(wolterprimll=_wolterprimll, woltersecll=_woltersecll, ellipsoidwoltll=_ellipsoidwoltll,
+                           wolterprimary=_wolterprimary, wolterprimaryopd=_wolterprimaryopd,
                            woltersecondary=_woltersecondary, woltersine=_woltersine,
                            wsprimary=_wsprimary, wssecondary=_wssecondary, spocone=_spocone)
 

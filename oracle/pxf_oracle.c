@@ -47,6 +47,9 @@ static inline double pow4(double a) { double t = a * a; return t * t; }
 /* REAL*4 acos(-1.) promoted to double: 3.1415927410125732 */
 static inline double pi32(void) { return (double)acosf(-1.0f); }
 
+double pxfo_legendre(double x, int n);
+double pxfo_legendrep(double x, int n);
+
 /* ------------------------------------------------------------------ */
 /* transformationsf.f95                                               */
 /* ------------------------------------------------------------------ */
@@ -741,6 +744,129 @@ double pxfo_legendrep(double x, int n)
     }
     if (fabs(x) > 1.) lp = 0.;
     return lp;
+}
+
+/* ------------------------------------------------------------------ */
+/* woltsurf.f95 -- Legendre-Legendre deformed shells */
+/* ------------------------------------------------------------------ */
+
+/* The Legendre additive block shared by wolterprimLL (:247-261), woltersecLL (:323-343) and
+ * ellipsoidWoltLL (:674-688); evaluation order as written there. */
+static void ll_terms(double x, double y, double z, double zmax, double zmin, double dphi,
+                     const double *coeff, const int32_t *axial, const int32_t *az, int cnum,
+                     double *add, double *addx, double *addy, double *addz)
+{
+    double ang = atan2(y, x);
+    double zarg = (z - ((zmax + zmin) / 2.)) / ((zmax - zmin) / 2.);
+    double targ = 2 * ang / dphi;
+    double a0 = 0., ax = 0., ay = 0., azz = 0.;
+    for (int a = 0; a < cnum; a++) {
+        a0 = a0 + coeff[a] * pxfo_legendre(zarg, axial[a]) * pxfo_legendre(targ, az[a]);
+        ax = ax - coeff[a] * pxfo_legendre(zarg, axial[a]) * pxfo_legendrep(targ, az[a]) * (2 / dphi) * (y / (sq(y) + sq(x)));
+        ay = ay + coeff[a] * pxfo_legendre(zarg, axial[a]) * pxfo_legendrep(targ, az[a]) * (2 / dphi) * (x / (sq(y) + sq(x)));
+        azz = azz + coeff[a] * pxfo_legendrep(zarg, axial[a]) * pxfo_legendre(targ, az[a]) * 2 / (zmax - zmin);
+    }
+    *add = a0; *addx = ax; *addy = ay; *addz = azz;
+}
+
+/* woltsurf.f95:219-288 (thetah = 3.*alpha, thetap = alpha; tol 1.e-10) */
+void pxfo_wolterprimll(double *x, double *y, double *z, double *l, double *m, double *n,
+                       double *ux, double *uy, double *uz, int64_t num, double r0, double z0,
+                       double zmax, double zmin, double dphi, const double *coeff,
+                       const int32_t *axial, const int32_t *az, int cnum)
+{
+    double alpha = .25 * atan(r0 / z0);
+    double thetah = 3. * alpha;
+    double thetap = alpha;
+    double p = z0 * tan(4 * alpha) * tan(thetap);
+    double d = z0 * tan(4 * alpha) * tan(4 * alpha - thetah);
+    double e = cos(4 * alpha) * (1 + tan(4 * alpha) * tan(thetah));
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp, add, addx, addy, addz, G;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+            ll_terms(x[i], y[i], z[i], zmax, zmin, dphi, coeff, axial, az, cnum, &add, &addx, &addy, &addz);
+            G = sqrt(sq(x[i]) + sq(y[i])) + add;
+            F = -(sq(G) - sq(p) - 2 * p * z[i] - 4 * sq(e) * p * d / (sq(e) - 1));
+            Fx = -2 * G * (x[i] / sqrt(sq(x[i]) + sq(y[i])) + addx);
+            Fy = -2 * G * (y[i] / sqrt(sq(x[i]) + sq(y[i])) + addy);
+            Fz = 2 * p - 2 * G * addz;
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+        ux[i] = Fx / Fp; uy[i] = Fy / Fp; uz[i] = Fz / Fp;
+    }
+}
+
+/* woltsurf.f95:293-379 (general psi; tol 1.e-7) */
+void pxfo_woltersecll(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                      double zmax, double zmin, double dphi, const double *coeff,
+                      const int32_t *axial, const int32_t *az, int cnum)
+{
+    double p, d, e;
+    vanspeybroeck(r0, z0, psi, &p, &d, &e);
+    (void)p;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp, add, addx, addy, addz, G;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM7 && it++ < PXF_NEWTON_CAP) {
+            ll_terms(x[i], y[i], z[i], zmax, zmin, dphi, coeff, axial, az, cnum, &add, &addx, &addy, &addz);
+            G = sqrt(sq(x[i]) + sq(y[i])) + add;
+            F = -(sq(G) - sq(e) * sq(d + z[i]) + sq(z[i]));
+            Fx = -2 * G * (x[i] / sqrt(sq(x[i]) + sq(y[i])) + addx);
+            Fy = -2 * G * (y[i] / sqrt(sq(x[i]) + sq(y[i])) + addy);
+            Fz = 2 * sq(e) * (d + z[i]) - 2 * z[i] - 2 * G * addz;
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+        ux[i] = Fx / Fp; uy[i] = Fy / Fp; uz[i] = Fz / Fp;
+    }
+}
+
+/* woltsurf.f95:643-718 (ellipsoid primary with L-L terms; tol 1.e-10) */
+void pxfo_ellipsoidwoltll(double *x, double *y, double *z, double *l, double *m, double *n,
+                          double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                          double S, double zmax, double zmin, double dphi, const double *coeff,
+                          const int32_t *axial, const int32_t *az, int cnum)
+{
+    double P = r0 / sin((psi * asin(r0 / z0) - asin(r0 / S)) / (1 + psi));
+    double ff = (S + P) / 2.;
+    double bq = -(sq(r0) + sq(ff - P) + sq(ff));
+    double cq = sq(ff) * sq(ff - P);
+    double aa = sqrt((-bq + sqrt(sq(bq) - 4 * cq)) / 2.);
+    double bb = sqrt(sq(aa) - sq(ff));
+    double zfoc = ff - P + z0;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp, add, addx, addy, addz, G;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+            ll_terms(x[i], y[i], z[i], zmax, zmin, dphi, coeff, axial, az, cnum, &add, &addx, &addy, &addz);
+            G = sqrt(sq(x[i]) + sq(y[i])) + add;
+            F = sq(z[i] - zfoc) / sq(aa) + sq(G) / sq(bb) - 1.;
+            Fx = 2 * G / sq(bb) * (x[i] / sqrt(sq(x[i]) + sq(y[i])) + addx);
+            Fy = 2 * G / sq(bb) * (y[i] / sqrt(sq(x[i]) + sq(y[i])) + addy);
+            Fz = 2 * (z[i] - zfoc) / sq(aa) + (2 * G / sq(bb)) * (addz);
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+        ux[i] = Fx / Fp; uy[i] = Fy / Fp; uz[i] = Fz / Fp;
+    }
 }
 
 /* ------------------------------------------------------------------ */

@@ -26,6 +26,20 @@ def bundle_alloc(num, device, nrows=10, zero=False):
     return [base[i, :num] for i in range(nrows)]
 
 
+def bundle_split(rays, sizes):
+    """Contiguous segments of a bundle as bundles of row VIEWS (no copies): a nested shell
+    assembly keeps all shells in one allocation and traces each shell's segment with its own
+    prescription (the reference loops over shells and concatenates, examples/axro/
+    axialHeights.py:247-305).  Segments that start on an even ray index keep the double2 path."""
+    out, lo = [], 0
+    for n in sizes:
+        out.append([r[lo:lo + n] for r in rays])
+        lo += int(n)
+    if lo != rays[1].shape[0]:
+        raise ValueError("segment sizes do not add up to the bundle length")
+    return out
+
+
 class Staged:
     """Resolve a group of f2py-style array arguments to device pointers."""
 

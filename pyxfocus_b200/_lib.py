@@ -58,6 +58,9 @@ SIGNATURES = {
     "pxf_wsprimary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
     "pxf_wssecondary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
     "pxf_spocone": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
+    "pxf_wolterprimll": (_c.c_int, _NINE + [_i64] + [_d] * 5 + [_vp, _vp, _vp, _i32, _vp, _st]),
+    "pxf_woltersecll": (_c.c_int, _NINE + [_i64] + [_d] * 6 + [_vp, _vp, _vp, _i32, _vp, _st]),
+    "pxf_ellipsoidwoltll": (_c.c_int, _NINE + [_i64] + [_d] * 7 + [_vp, _vp, _vp, _i32, _vp, _st]),
     # zernsurf (coeff/rorder/aorder are HOST pointers)
     "pxf_tracezern": (_c.c_int, _NINE + [_i64, _vp, _vp, _vp, _i32, _d, _vp, _st]),
     "pxf_tracezernopd": (_c.c_int, [_dp] * 10 + [_i64, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),

@@ -447,6 +447,7 @@ __global__ void k_select_begin_bracket(SelectState *st, unsigned long long k0, u
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const unsigned long long below = counters[0], ncand = counters[1];
+        if (cap_total == ~0ull) cap_total = counters[4];       // summed capacities travel with the counters
         const bool ok = counters[3] == 0 && ncand <= cap_total && k0 >= below && k1 < below + ncand;
         st->prefix[0] = 0; st->prefix[1] = 0;
         st->rank[0] = ok ? k0 - below : 0; st->rank[1] = ok ? k1 - below : 0;
@@ -856,7 +857,9 @@ int pxf_bracket_collect(const double *x, const double *y, int64_t num, const dou
 }
 
 /* Begin the select over the candidate buffers: ranks k0,k1 are GLOBAL ranks, counters the
- * (all-reduced) totals, cap_total the summed capacities.  Marks the state invalid on a miss. */
+ * (all-reduced) totals, cap_total the summed capacities (< 0: read it from counters[4], so a
+ * sharded caller can all-reduce it together with the counters and never sync the host).
+ * Marks the state invalid on a miss. */
 int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t *counters, int64_t cap_total,
                              pxf_stream_t stream)
 {
@@ -865,7 +868,7 @@ int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t
     if (rc) return rc;
     k_select_begin_bracket<<<16, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         st_of(state), (unsigned long long)k0, (unsigned long long)k1, reinterpret_cast<const unsigned long long *>(counters),
-        (unsigned long long)cap_total, hist_of(state), 2 * 8192, nan_of(state));
+        cap_total < 0 ? ~0ull : (unsigned long long)cap_total, hist_of(state), 2 * 8192, nan_of(state));
     count_launch();
     return check_launch("k_select_begin_bracket");
 }
@@ -968,7 +971,7 @@ int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const d
     }
     if ((rc = pxf_select_finish(w.stA, BRACKET_SAMPLES, w.lohi, stream))) return rc;
     // 2. one pass: count below, collect the bracket
-    PXF_CUDA(cudaMemsetAsync(w.counters, 0, 32, s));
+    PXF_CUDA(cudaMemsetAsync(w.counters, 0, 64, s));
     if ((rc = pxf_bracket_collect(x, y, num, w.cxy, w.lohi, w.cand, w.cap, reinterpret_cast<uint64_t *>(w.counters), stream))) return rc;
     // 3. exact select among the candidates
     if ((rc = pxf_select_begin_bracket(w.stB, (num - 1) / 2, num / 2, reinterpret_cast<uint64_t *>(w.counters), w.cap, stream))) return rc;

@@ -247,6 +247,15 @@ struct OpZern {
     }
 };
 
+template <int NMAX>
+struct OpLL {
+    using Params = LLP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = (NMAX + 1) * (NMAX + 1);
+    PXF_DEV static const double *table(const Params &p) { return p.C; }
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *smem, double, double) { op_ll<NMAX>(r, p, smem); }
+};
+
 // ------------------------------------------------------------------ the kernel
 template <class Op, bool MASKED, bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK)
@@ -367,6 +376,20 @@ static int launch_zern(RowPtrs P, int64_t num, const uint8_t *mask, const ZernP 
     if (z.nmax <= 7) return launch_op<OpZern<7, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
     if (z.nmax <= 11) return launch_op<OpZern<11, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
     return launch_op<OpZern<15, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+}
+
+static int launch_ll(RowPtrs P, int64_t num, const uint8_t *mask, int kind, double r0, double z0, double psi, double S,
+                     double zmax, double zmin, double dphi, const double *coeff, const int32_t *axial,
+                     const int32_t *az, int32_t cnum, pxf_stream_t stream)
+{
+    if (!coeff || !axial || !az || cnum <= 0) { set_error("bad Legendre table"); return PXF_ERR_INVALID; }
+    LLP q;
+    if (make_ll(q, kind, r0, z0, psi, S, zmax, zmin, dphi, coeff, axial, az, cnum) < 0) {
+        set_error("invalid Legendre orders (need 0 <= order <= %d)", PXF_LL_MAXN);
+        return PXF_ERR_INVALID;
+    }
+    if (q.stride == 8) return launch_op<OpLL<7>>(P, num, mask, nullptr, nullptr, q, stream);
+    return launch_op<OpLL<15>>(P, num, mask, nullptr, nullptr, q, stream);
 }
 
 }  // namespace pxf
@@ -532,6 +555,34 @@ int pxf_spocone(double *x, double *y, double *z, double *l, double *m, double *n
 {
     return launch_op<OpSpoCone>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
                                 make_spo(R0, tg), stream);
+}
+
+int pxf_wolterprimll(double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num, double r0, double z0,
+                     double zmax, double zmin, double dphi, const double *coeff, const int32_t *axial,
+                     const int32_t *az, int32_t cnum, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_ll(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, 0, r0, z0, 1., 0., zmax, zmin, dphi, coeff, axial,
+                     az, cnum, stream);
+}
+
+int pxf_woltersecll(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                    double zmax, double zmin, double dphi, const double *coeff, const int32_t *axial,
+                    const int32_t *az, int32_t cnum, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_ll(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, 1, r0, z0, psi, 0., zmax, zmin, dphi, coeff,
+                     axial, az, cnum, stream);
+}
+
+int pxf_ellipsoidwoltll(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
+                        double S, double zmax, double zmin, double dphi, const double *coeff,
+                        const int32_t *axial, const int32_t *az, int32_t cnum, const uint8_t *mask,
+                        pxf_stream_t stream)
+{
+    return launch_ll(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, 2, r0, z0, psi, S, zmax, zmin, dphi, coeff,
+                     axial, az, cnum, stream);
 }
 
 int pxf_tracezern(double *x, double *y, double *z, double *l, double *m, double *n,

@@ -155,6 +155,56 @@ inline RadgratP make_radgrat(double wave, double dpermm, double order)
     return p;
 }
 
+inline double h_tol7() { return (double)1.e-7f; }
+
+// Legendre-Legendre shells: fold the (coeff, axial, az) term list into the dense matrix of
+// pxf_ray.cuh.  kind 0/1/2 = wolterprimLL / woltersecLL / ellipsoidWoltLL; S only for kind 2.
+// Returns 0, or -1 for an invalid table (orders outside 0..15).
+inline int make_ll(LLP &q, int kind, double r0, double z0, double psi, double S, double zmax, double zmin,
+                   double dphi, const double *coeff, const int32_t *axial, const int32_t *az, int cnum)
+{
+    memset(&q, 0, sizeof(q));
+    q.kind = kind;
+    int nz = 0, nt = 0;
+    for (int a = 0; a < cnum; a++) {
+        if (axial[a] < 0 || axial[a] > PXF_LL_MAXN || az[a] < 0 || az[a] > PXF_LL_MAXN) return -1;
+        if (axial[a] > nz) nz = axial[a];
+        if (az[a] > nt) nt = az[a];
+    }
+    q.nz = nz; q.nt = nt;
+    q.stride = (nz <= 7 && nt <= 7) ? 8 : 16;
+    for (int a = 0; a < cnum; a++) q.C[axial[a] * q.stride + az[a]] += coeff[a];
+    q.zmid = (zmax + zmin) / 2.;
+    q.zhalf = (zmax - zmin) / 2.;
+    q.dphi = dphi;
+    q.twoodphi = 2 / dphi;
+    q.zrange = zmax - zmin;
+    if (kind == 0) {            // woltsurf.f95:235-241: thetah = 3.*alpha, thetap = alpha
+        double alpha = .25 * atan(r0 / z0);
+        double thetah = 3. * alpha, thetap = alpha;
+        double p = z0 * tan(4 * alpha) * tan(thetap);
+        double d = z0 * tan(4 * alpha) * tan(4 * alpha - thetah);
+        double e = cos(4 * alpha) * (1 + tan(4 * alpha) * tan(thetah));
+        q.g0 = h_sq(p); q.g1 = 2 * p; q.g2 = 4 * h_sq(e) * p * d / (h_sq(e) - 1);
+        q.tol = h_tol10();
+    } else if (kind == 1) {     // woltsurf.f95:307-312, tol 1.e-7 (:319)
+        double p, d, e;
+        vanspeybroeck(r0, z0, psi, p, d, e);
+        q.g0 = h_sq(e); q.g1 = 2 * h_sq(e); q.g2 = d;
+        q.tol = h_tol7();
+    } else {                    // woltsurf.f95:657-666
+        double P = r0 / sin((psi * asin(r0 / z0) - asin(r0 / S)) / (1 + psi));
+        double ff = (S + P) / 2.;
+        double bq = -(h_sq(r0) + h_sq(ff - P) + h_sq(ff));
+        double cq = h_sq(ff) * h_sq(ff - P);
+        double aa = sqrt((-bq + sqrt(h_sq(bq) - 4 * cq)) / 2.);
+        double bb = sqrt(h_sq(aa) - h_sq(ff));
+        q.g0 = ff - P + z0; q.g1 = h_sq(aa); q.g2 = h_sq(bb);
+        q.tol = h_tol10();
+    }
+    return 0;
+}
+
 // Fold (coeff, rorder, aorder) into the (n,|m|) table of pxf_ray.cuh.  Returns the highest
 // radial order, or -1 for an invalid table (n>15, |m|>n, n-|m| odd).
 inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const int32_t *aorder,

@@ -176,15 +176,16 @@ class CudaSelect:
         """One pass over the shard: returns (candidate buffer, local counters[4] int64)."""
         cap = int(self.L.pxf_bracket_capacity(self.num))
         cand = torch.empty(cap, dtype=torch.float64, device=self.dev)
-        counters = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        counters = torch.zeros(5, dtype=torch.int64, device=self.dev)
         _lib.check(self.L.pxf_bracket_collect(self.x.data_ptr(), self.y.data_ptr(), self.num, self.cxy.data_ptr(),
                                               lohi.data_ptr(), cand.data_ptr(), cap, counters.data_ptr(), self.s))
         counters[3] = (counters[1] > cap).to(torch.int64)      # this shard's buffer overflowed
-        return cand, counters, cap
+        counters[4] = cap                                       # capacities are summed by the all-reduce
+        return cand, counters
 
-    def begin_bracket(self, k0, k1, counters, cap_total):
-        _lib.check(self.L.pxf_select_begin_bracket(self.state.data_ptr(), k0, k1, counters.data_ptr(), cap_total,
-                                                   self.s))
+    def begin_bracket(self, k0, k1, counters):
+        """counters: the all-reduced [below, inside, nan, overflowed, capacity] totals."""
+        _lib.check(self.L.pxf_select_begin_bracket(self.state.data_ptr(), k0, k1, counters.data_ptr(), -1, self.s))
 
 
 def _five_passes(sel, group, reduce=True):
@@ -235,32 +236,33 @@ def bracket_median_pair(sel, total, min_shard, group=None):
     _five_passes(sel, group, reduce=False)
     sel.finish(n_s, read=False)
     lohi = sel.last
-    cand, local, cap = sel.collect(lohi)
+    cand, local = sel.collect(lohi)
     glob = local.clone()
-    caps = torch.tensor([cap], dtype=torch.int64, device=glob.device)
     all_reduce_sum(glob, group)
-    all_reduce_sum(caps, group)
     sel.use_keys(cand, local[1:2])
-    sel.begin_bracket((total - 1) // 2, total // 2, glob, int(caps.item()))
+    sel.begin_bracket((total - 1) // 2, total // 2, glob)
     _five_passes(sel, group)
     return sel.finish(total)
 
 
-def hpd(rays, group=None, return_stats=False, sums=None):
+def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None):
     """Unweighted HPD (2 x median radius about the global centroid) of a sharded bundle;
     exact, identical on every rank.  ``sums``: this shard's centroid sums from
-    ``Program.run(..., sums=...)`` (saves the local pass that computes them)."""
+    ``Program.run(..., sums=...)`` (saves the local pass that computes them).  ``total`` /
+    ``min_shard``: global ray count and smallest shard size when the caller knows them (e.g.
+    equal shards) -- then nothing is read back to the host before the final result, so the
+    whole analysis is enqueued behind the trace kernel without a sync."""
     flush(rays)
     x, y = rays[1:3]
     dev = x.device
     sums = _sums(0, rays, None, 0., 0.) if sums is None else sums.clone()
-    sums[4] = float(x.shape[0])
-    big = sums.clone()
     all_reduce_sum(sums[:4], group)
-    if _world(group) > 1:
-        td.all_reduce(big[4:5], op=td.ReduceOp.MIN, group=group)
-    total = int(round(float(sums[3].item())))
-    min_shard = int(round(float(big[4].item())))
+    if total is None or min_shard is None:
+        cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
+        if _world(group) > 1:
+            td.all_reduce(cnt, op=td.ReduceOp.MIN, group=group)
+        total = int(round(float(sums[3].item())))
+        min_shard = int(round(float(cnt.item())))
     with torch.cuda.device(dev):
         cxy = torch.empty(2, dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().pxf_centroid_from_sums(sums.data_ptr(), cxy.data_ptr(), stream_ptr(dev)))

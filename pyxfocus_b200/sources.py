@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._call import bundle_alloc, stream_ptr
+from ._call import bundle_alloc, bundle_split, stream_ptr  # noqa: F401
 
 _KIND = dict(subannulus=0, circularbeam=1, pointsource=2, annulus=3)
 

@@ -1,5 +1,8 @@
 """Replacement for the reference's f2py module ``woltsurf`` (``woltsurf.f95``,
 ``compiletrace.sh:4``).  See ``transformationsf`` for the conventions."""
+import numpy as np
+import torch
+
 from . import _lib
 from ._call import Staged, run
 
@@ -49,3 +52,41 @@ def wssecondary(x, y, z, l, m, n, ux, uy, uz, alpha, z0, psi, num=None, mask=Non
 def spocone(x, y, z, l, m, n, ux, uy, uz, r0, tg, num=None, mask=None):
     """woltsurf.f95:591-638"""
     _nine("pxf_spocone", (x, y, z, l, m, n, ux, uy, uz), (r0, tg), num, mask)
+
+
+def _ll(fn_name, arrs, scalars, coeff, axial, az, num, cnum, mask):
+    def host(a, dtype):
+        if isinstance(a, torch.Tensor):
+            a = a.detach().cpu().numpy()
+        return np.ascontiguousarray(np.asarray(a).ravel(), dtype=dtype)
+    c, ax, azz = host(coeff, np.float64), host(axial, np.int32), host(az, np.int32)
+    if cnum is not None and int(cnum) != c.shape[0]:
+        raise ValueError("shape(coeff,0)==cnum failed")
+    if ax.shape[0] != c.shape[0] or azz.shape[0] != c.shape[0]:
+        raise ValueError("shape(axial,0)==cnum failed")
+    st = Staged()
+    p = [st.inout(a) for a in arrs]
+    if num is not None and int(num) != st.num:
+        raise ValueError("shape(x,0)==num failed")
+    run(getattr(_lib.lib(), fn_name), st, *p, st.num, *scalars, c.ctypes.data, ax.ctypes.data, azz.ctypes.data,
+        c.shape[0], st.mask(mask), st.stream())
+
+
+def wolterprimll(x, y, z, l, m, n, ux, uy, uz, r0, z0, zmax, zmin, dphi, coeff, axial, az, num=None, cnum=None,
+                 mask=None):
+    """woltsurf.f95:219-288"""
+    _ll("pxf_wolterprimll", (x, y, z, l, m, n, ux, uy, uz), (r0, z0, zmax, zmin, dphi), coeff, axial, az, num, cnum, mask)
+
+
+def woltersecll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, zmax, zmin, dphi, coeff, axial, az, num=None, cnum=None,
+                mask=None):
+    """woltsurf.f95:293-379"""
+    _ll("pxf_woltersecll", (x, y, z, l, m, n, ux, uy, uz), (r0, z0, psi, zmax, zmin, dphi), coeff, axial, az, num, cnum,
+        mask)
+
+
+def ellipsoidwoltll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, s, zmax, zmin, dphi, coeff, axial, az, num=None,
+                    cnum=None, mask=None):
+    """woltsurf.f95:643-718"""
+    _ll("pxf_ellipsoidwoltll", (x, y, z, l, m, n, ux, uy, uz), (r0, z0, psi, s, zmax, zmin, dphi), coeff, axial, az, num,
+        cnum, mask)

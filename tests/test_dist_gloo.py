@@ -121,11 +121,11 @@ class NumpySelect:
         cand = torch.zeros(cap, dtype=torch.float64)
         cand[:min(cap, inside.shape[0])] = torch.from_numpy(inside[:cap].copy())
         counters = torch.tensor([int((r < lo).sum()), inside.shape[0], int(np.isnan(r).sum()),
-                                 int(inside.shape[0] > cap)], dtype=torch.int64)
-        return cand, counters, cap
+                                 int(inside.shape[0] > cap), cap], dtype=torch.int64)
+        return cand, counters
 
-    def begin_bracket(self, k0, k1, counters, cap_total):
-        below, ncand, nan, over = [int(v) for v in counters.tolist()]
+    def begin_bracket(self, k0, k1, counters):
+        below, ncand, nan, over, cap_total = [int(v) for v in counters.tolist()]
         ok = over == 0 and ncand <= cap_total and k0 >= below and k1 < below + ncand
         self.prefix = [0, 0]
         self.rank = [k0 - below, k1 - below] if ok else [0, 0]

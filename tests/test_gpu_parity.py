@@ -641,6 +641,49 @@ def test_golden_misc(pxf, golden):
     assert_close(to_host(dev), rows_of(g["after_woltersine"]), pos_scale=8.4e3, what="golden after_woltersine")
 
 
+# --------------------------------------------------------------------------- config 5: nested shells
+def test_nested_multishell_assembly_weighted_analyses(pxf):
+    """BASELINE config 5 in small: a nested Wolter-I assembly (one prescription per shell,
+    examples/axro/axialHeights.py:215-322 / SMARTX.py:163-259).  All shells live in ONE device
+    bundle; each shell's segment is traced by one fused launch with its own (r0,z0); a z-range
+    vignette and the area-weighted centroid / rms / hpd follow.  The oracle does what the
+    reference does: a Python loop over shells, then np.concatenate."""
+    rng = np.random.default_rng(42)
+    radii = np.linspace(200., 1500., 24)
+    per = 4000 + 2 * rng.integers(0, 500, radii.size)            # even segment sizes
+    cpu_shells, wts = [], []
+    for k, (r0, nk) in enumerate(zip(radii, per)):
+        z0 = np.sqrt(1.e4 ** 2 - r0 ** 2)
+        np.random.seed(100 + k)
+        rays = pyref.annulus(r0, r0 + .6, int(nk), zhat=-1.)
+        chains.run_steps_cpu(rays, chains.wolter1_steps(r0, z0, 1.))
+        cpu_shells.append(rays)
+        wts.append(np.full(int(nk), 2 * np.pi * r0 * .6 / nk))       # geometric area per ray
+    cpu = [np.concatenate([s[i] for s in cpu_shells]) for i in range(10)]
+    w = np.concatenate(wts)
+    # device: one allocation, per-shell views
+    total = int(per.sum())
+    from pyxfocus_b200._call import bundle_alloc, bundle_split
+    dev = bundle_alloc(total, "cuda", zero=True)
+    segs = bundle_split(dev, [int(v) for v in per])
+    for k, (r0, nk) in enumerate(zip(radii, per)):
+        z0 = np.sqrt(1.e4 ** 2 - r0 ** 2)
+        np.random.seed(100 + k)
+        src = pyref.annulus(r0, r0 + .6, int(nk), zhat=-1.)
+        for i in range(10):
+            segs[k][i].copy_(__import__("torch").from_numpy(src[i]))
+        steps_to_program(chains.wolter1_steps(r0, z0, 1.)).run(segs[k])
+    assert_bit_equal(to_host(dev), cpu, what="nested shells")
+    A = pxf.analyses
+    assert A.hpd(dev, weights=w) == pytest.approx(pyref.hpd(cpu, weights=w), rel=1e-9)
+    assert A.rmsCentroid(dev, weights=w) == pytest.approx(pyref.rmsCentroid(cpu, weights=w), rel=1e-9)
+    cx, cy = A.centroid(dev, weights=w)
+    rx, ry = pyref.centroid(cpu, weights=w)
+    assert abs(cx - rx) <= 1e-15 and abs(cy - ry) <= 1e-15
+    assert A.hpd(dev) == pytest.approx(pyref.hpd(cpu), rel=1e-9)
+    assert pxf.dist.hpd(dev) == A.hpd(dev)
+
+
 # --------------------------------------------------------------------------- edge cases / errors
 def test_empty_and_tiny_bundles(pxf):
     import torch
