@@ -1,9 +1,10 @@
 """Scalar mirror-prescription helpers mirrored from the reference's ``conicsolve.py``
 (host-side numpy; nothing here touches rays).  Only the functions the hot-path wrappers and
 the known-answer tests need: ``primrad`` (conicsolve.py:7-15), ``secrad`` (:29-37),
-``woltparam`` (:51-59), ``primfocus`` (:62-64), ``wsRMS`` (:250-254), ``wsFoc`` (:257-261).
+``woltparam`` (:51-59), ``primfocus`` (:62-64), ``wsRMS`` (:250-254), ``wsFoc`` (:257-261),
+``ellipsoidFunction`` (:263-281).
 """
-from numpy import arctan, cos, sqrt, tan
+from numpy import arcsin, arctan, cos, sin, sqrt, tan
 
 
 def _vs(r0, z0, psi):
@@ -53,3 +54,16 @@ def wsRMS(psi, theta, alpha, L1, z0):
 def wsFoc(r, psi, L1, z0, alpha):
     """Optimum focal-surface height at radius r (Chase & Van Speybroeck)."""
     return .0625 * (psi + 1) * (r ** 2 * L1 / z0 ** 2) / tan(alpha) ** 2
+
+
+def ellipsoidFunction(S, psi, R, F):
+    """(P, a, b, e, f) of the ellipsoid primary of an ellipsoid-hyperboloid telescope."""
+    P = R / sin((psi * arcsin(R / F) - arcsin(R / S)) / (1 + psi))
+    f = (S + P) / 2.
+    a = 1.
+    b = -(R ** 2 + (f - P) ** 2 + f ** 2)
+    c = f ** 2 * (f - P) ** 2
+    a = sqrt((-b + sqrt(b ** 2 - 4 * a * c)) / (2 * a))
+    b = sqrt(a ** 2 - f ** 2)
+    e = f / a
+    return P, a, b, e, f

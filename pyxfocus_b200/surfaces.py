@@ -2,7 +2,9 @@
 ``flat`` (surfaces.py:14-29), ``zernsurf`` (:31-47), ``conic`` (:104-113),
 ``wolterprimary`` (:219-227), ``wolterprimarynode`` (:229-236), ``woltersecondary``
 (:238-243), ``woltersine`` (:265-270), ``wsPrimary`` (:331-347), ``wsSecondary`` (:367-383),
-``spoCone/spoPrimary/spoSecondary`` (:403-441), ``focus/focusI`` (:502-519).
+``spoCone/spoPrimary/spoSecondary`` (:403-441), ``focus/focusI`` (:502-519); and the
+Legendre-Legendre shells ``primaryLL`` (:300-306), ``secondaryLL`` (:291-298),
+``ellipsoidPrimary/Secondary(LL)`` (:443-500).
 
 Same names, argument order and results; ``ind=`` masks run as in-kernel predicates, and inside
 ``with program.fused(rays):`` unmasked calls are recorded into one fused kernel.
@@ -172,6 +174,56 @@ def spoSecondary(rays, R0, F, d=.605, ind=None):
     """SPO secondary: tg = 3 atan((R0+d/2)/F)/4."""
     tg = .75 * np.arctan((R0 + d / 2) / F)
     spoCone(rays, R0, tg, ind=ind)
+    return
+
+
+def secondaryLL(rays, r0, z0, psi, zmax, zmin, dphi, coeff, axial, az):
+    """Wolter-I secondary with Legendre-Legendre figure terms, placed at the focus."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    wolt.woltersecll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, zmax, zmin, dphi, coeff, axial, az)
+    return
+
+
+def primaryLL(rays, r0, z0, zmax, zmin, dphi, coeff, axial, az):
+    """Wolter-I primary with Legendre-Legendre figure terms, placed at the focus."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    wolt.wolterprimll(x, y, z, l, m, n, ux, uy, uz, r0, z0, zmax, zmin, dphi, coeff, axial, az)
+    return
+
+
+def ellipsoidPrimary(rays, R0, F, S, psi):
+    """Primary of an ellipsoid-hyperboloid telescope (a conic placed at its vertex)."""
+    P, a, b, e, f = con.ellipsoidFunction(S, psi, R0, F)
+    R = b ** 2 / a
+    tran.transform(rays, 0, 0, F + f - P - a, 0, 0, 0)
+    conic(rays, R, -e ** 2)
+    tran.itransform(rays, 0, 0, F + f - P - a, 0, 0, 0)
+    return
+
+
+def ellipsoidSecondary(rays, R0, F, S, psi):
+    """Secondary of an ellipsoid-hyperboloid telescope (a Wolter secondary with an effective psi)."""
+    P, a, b, e, f = con.ellipsoidFunction(S, psi, R0, F)
+    psi_eff = np.arctan(R0 / P) / (np.arctan(R0 / F) - np.arctan(R0 / P))
+    woltersecondary(rays, R0, F, psi=psi_eff)
+    return
+
+
+def ellipsoidPrimaryLL(rays, R0, F, S, psi, zmax, zmin, dphi, coeff, axial, az):
+    """Ellipsoid primary with Legendre-Legendre figure terms."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    wolt.ellipsoidwoltll(x, y, z, l, m, n, ux, uy, uz, R0, F, psi, S, zmax, zmin, dphi, coeff, axial, az)
+    return
+
+
+def ellipsoidSecondaryLL(rays, R0, F, S, psi, zmax, zmin, dphi, coeff, axial, az):
+    """Hyperboloid secondary of an ellipsoid-hyperboloid telescope with L-L figure terms."""
+    P, a, b, e, f = con.ellipsoidFunction(S, psi, R0, F)
+    psi_eff = np.arctan(R0 / P) / (np.arctan(R0 / F) - np.arctan(R0 / P))
+    secondaryLL(rays, R0, F, psi_eff, zmax, zmin, dphi, coeff, axial, az)
     return
 
 

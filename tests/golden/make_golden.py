@@ -211,6 +211,57 @@ def main():
     surf.wolterprimary(rays, 220., 8400., psi=1.3, nr=1.)
     g.update(pack("after_primaryopd", rays))
     np.savez_compressed(os.path.join(HERE, "misc.npz"), **g)
+    # ---- Legendre-Legendre shells (examples/axro/singlePassAlignment.py:80,157,169 style)
+    N = 2000
+    rng = np.random.default_rng(8)
+    axial = np.array([0, 1, 2, 3, 1, 2, 4, 0, 5])
+    az = np.array([0, 0, 0, 1, 1, 2, 2, 3, 1])
+    coeff = rng.normal(0., 2.e-4, axial.size)
+    g = dict(coeff=coeff, axial=axial, az=az)
+    np.random.seed(8)
+    rays = src.subannulus(220., 220.6, .25, N, zhat=-1.)
+    g.update(pack("rays_in", rays))
+    tran.transform(rays, 0, 0, -8400., 0, 0, 0)
+    surf.primaryLL(rays, 220., 8400., 8500., 8400., .25, coeff, axial, az)
+    g.update(pack("after_primaryLL", rays))
+    tran.reflect(rays)
+    surf.secondaryLL(rays, 220., 8400., 1., 8400., 8300., .25, coeff * .5, axial, az)
+    g.update(pack("after_secondaryLL", rays))
+    tran.reflect(rays)
+    surf.flat(rays)
+    g.update(pack("rays_out", rays))
+    g["hpd"] = anal.hpd(rays)
+    # ellipsoid-hyperboloid with L-L terms, finite source distance S
+    np.random.seed(9)
+    rays = src.subannulus(220., 220.5, .25, N, zhat=-1.)
+    S = 2.5e5
+    # rays diverge from a point source at distance S above the node plane
+    tran.transform(rays, 0, 0, -8400. - 60., 0, 0, 0)
+    tran.pointTo(rays, 0., 0., 8400. + S, reverse=1.)
+    g.update(pack("rays_in2", rays))
+    surf.ellipsoidPrimaryLL(rays, 220., 8400., S, 1., 8500., 8400., .25, coeff, axial, az)
+    g.update(pack("after_ellipsoidLL", rays))
+    tran.reflect(rays)
+    surf.ellipsoidSecondaryLL(rays, 220., 8400., S, 1., 8400., 8300., .25, coeff * .5, axial, az)
+    tran.reflect(rays)
+    surf.flat(rays)
+    g.update(pack("rays_out2", rays))
+    g["S"] = S
+    # plain ellipsoid pair (conic + Wolter secondary with an effective psi)
+    np.random.seed(10)
+    rays = src.subannulus(220., 220.5, .25, N, zhat=-1.)
+    tran.transform(rays, 0, 0, -8400. - 60., 0, 0, 0)
+    tran.pointTo(rays, 0., 0., 8400. + S, reverse=1.)
+    g.update(pack("rays_in3", rays))
+    surf.ellipsoidPrimary(rays, 220., 8400., S, 1.)
+    tran.reflect(rays)
+    surf.ellipsoidSecondary(rays, 220., 8400., S, 1.)
+    tran.reflect(rays)
+    surf.flat(rays)
+    g.update(pack("rays_out3", rays))
+    g["hpd3"] = anal.hpd(rays)
+    np.savez_compressed(os.path.join(HERE, "legendre.npz"), **g)
+
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -684,6 +684,66 @@ def test_nested_multishell_assembly_weighted_analyses(pxf):
     assert pxf.dist.hpd(dev) == A.hpd(dev)
 
 
+# --------------------------------------------------------------------------- Legendre-Legendre shells
+def test_golden_legendre_shells(pxf, golden):
+    """wolterprimLL / woltersecLL / ellipsoidWoltLL and the ellipsoid pair,
+    against fixtures produced by the reference's own surfaces.primaryLL / secondaryLL /
+    ellipsoidPrimary(LL) / ellipsoidSecondary(LL)."""
+    g = golden("legendre")
+    T, S = pxf.transformations, pxf.surfaces
+    coeff, axial, az = g["coeff"], g["axial"], g["az"]
+    dev = to_dev(rows_of(g["rays_in"]))
+    T.transform(dev, 0, 0, -8400., 0, 0, 0)
+    S.primaryLL(dev, 220., 8400., 8500., 8400., .25, coeff, axial, az)
+    assert_close(to_host(dev), rows_of(g["after_primaryLL"]), pos_scale=8.5e3, what="primaryLL")
+    T.reflect(dev)
+    S.secondaryLL(dev, 220., 8400., 1., 8400., 8300., .25, coeff * .5, axial, az)
+    assert_close(to_host(dev), rows_of(g["after_secondaryLL"]), pos_scale=8.5e3, tol=1e-11, what="secondaryLL")
+    T.reflect(dev)
+    S.flat(dev)
+    assert_close(to_host(dev), rows_of(g["rays_out"]), pos_scale=8.5e3, tol=1e-11, what="LL rays_out")
+    assert pxf.analyses.hpd(dev) == pytest.approx(float(g["hpd"]), rel=1e-9)
+    Sd = float(g["S"])
+    dev = to_dev(rows_of(g["rays_in2"]))
+    S.ellipsoidPrimaryLL(dev, 220., 8400., Sd, 1., 8500., 8400., .25, coeff, axial, az)
+    assert_close(to_host(dev), rows_of(g["after_ellipsoidLL"]), pos_scale=8.5e3, what="ellipsoidPrimaryLL")
+    T.reflect(dev)
+    S.ellipsoidSecondaryLL(dev, 220., 8400., Sd, 1., 8400., 8300., .25, coeff * .5, axial, az)
+    T.reflect(dev)
+    S.flat(dev)
+    assert_close(to_host(dev), rows_of(g["rays_out2"]), pos_scale=8.5e3, tol=1e-11, what="ellipsoid LL rays_out")
+    dev = to_dev(rows_of(g["rays_in3"]))
+    S.ellipsoidPrimary(dev, 220., 8400., Sd, 1.)
+    T.reflect(dev)
+    S.ellipsoidSecondary(dev, 220., 8400., Sd, 1.)
+    T.reflect(dev)
+    S.flat(dev)
+    assert_bit_equal(to_host(dev), rows_of(g["rays_out3"]), rows=range(1, 10), what="ellipsoid pair (algebraic)")
+    assert pxf.analyses.hpd(dev) == pytest.approx(float(g["hpd3"]), rel=1e-9)
+
+
+def test_legendre_shells_vs_oracle_high_order_and_mask(pxf):
+    rng = np.random.default_rng(43)
+    # orders up to 11 exercise the 16x16 table; duplicates of one (axial,az) pair must add up
+    axial = np.array([0, 1, 9, 11, 3, 3, 2])
+    az = np.array([0, 2, 1, 4, 10, 10, 0])
+    coeff = rng.normal(0, 1e-4, axial.size)
+    cpu = wolter_inputs(20_001, 44)
+    mask = rng.random(20_001) < .5
+    dev = to_dev(cpu)
+    pyref.masked(of.woltsurf.wolterprimll, cpu[1:], mask, 220., 8400., 8500., 8400., 1., coeff, axial, az)
+    pxf.woltsurf.wolterprimll(*dev[1:], 220., 8400., 8500., 8400., 1., coeff, axial, az, mask=mask)
+    assert_close(to_host(dev), cpu, pos_scale=8.5e3, what="wolterprimll masked, order 11")
+    # rays outside the Legendre domain (|zarg|>1, |targ|>1): clamp semantics of legendre/legendrep
+    cpu = wolter_inputs(5_001, 45)
+    dev = to_dev(cpu)
+    of.woltsurf.wolterprimll(*cpu[1:], 220., 8400., 8460., 8440., .2, coeff[:3], axial[:3], az[:3])
+    pxf.woltsurf.wolterprimll(*dev[1:], 220., 8400., 8460., 8440., .2, coeff[:3], axial[:3], az[:3])
+    assert_close(to_host(dev), cpu, pos_scale=8.5e3, tol=1e-11, what="wolterprimll outside the domain")
+    with pytest.raises(pxf.PxfError):
+        pxf.woltsurf.wolterprimll(*dev[1:], 220., 8400., 8460., 8440., .2, [1.], [16], [0])
+
+
 # --------------------------------------------------------------------------- edge cases / errors
 def test_empty_and_tiny_bundles(pxf):
     import torch

@@ -264,3 +264,21 @@ def test_f2py_style_errors():
         T.reflect(np.zeros(20)[::2], a, a, a, a, a)
     with pytest.raises(ValueError):
         T.reflect(np.zeros(5), a, a, a, a, a)
+
+
+def test_legendre_shells_reduce_to_wolter_surfaces_without_terms():
+    """With every coefficient zero wolterprimLL / woltersecLL are the plain Wolter-I surfaces
+    (same root; psi=1 for the primary), and the ellipsoid pair images a point source at S."""
+    rays = chains.wolter1_source(3000, 9, dphi=.3)
+    pyref.transform(rays, 0, 0, -8400., 0, 0, 0)
+    a, b = [r.copy() for r in rays], [r.copy() for r in rays]
+    z3 = np.zeros(3)
+    W.wolterprimary(*a[1:], 220., 8400., 1.)
+    W.wolterprimll(*b[1:], 220., 8400., 8500., 8400., .3, z3, [0, 1, 2], [0, 1, 1])
+    for k in range(1, 10):
+        assert np.abs(a[k] - b[k]).max() < 1e-9
+    T.reflect(*a[4:]); T.reflect(*b[4:])
+    W.woltersecondary(*a[1:], 220., 8400., 1.3)
+    W.woltersecll(*b[1:], 220., 8400., 1.3, 8400., 8300., .3, z3, [0, 1, 2], [0, 1, 1])
+    for k in range(1, 10):
+        assert np.abs(a[k] - b[k]).max() < 1e-6            # woltersecLL stops at |delt| <= 1e-7 (woltsurf.f95:319)
