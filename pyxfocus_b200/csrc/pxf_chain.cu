@@ -17,28 +17,18 @@ namespace pxf {
 struct NoP { int unused; };
 
 // ---- op functors: P = folded parameter block (what build_program stores in FusedOp::q) ----
-// apply: one ray; apply2: two rays of the same thread (default: one after the other; the Newton
-// surfaces advance both rays through the same loop so their dependency chains interleave).
 #define PXF_CHAIN_OP(NAME, CODEV, PTYPE, CALL)                                        \
     struct NAME {                                                                     \
         using P = PTYPE;                                                              \
         static constexpr int CODE = CODEV;                                            \
         PXF_DEV static bool apply(Ray &r, const P &p) { CALL; return true; }          \
-        PXF_DEV static void apply2(Ray *rr, const P &p) { apply(rr[0], p); apply(rr[1], p); } \
-    };
-#define PXF_CHAIN_OP2(NAME, CODEV, PTYPE, CALL, CALL2)                                \
-    struct NAME {                                                                     \
-        using P = PTYPE;                                                              \
-        static constexpr int CODE = CODEV;                                            \
-        PXF_DEV static bool apply(Ray &r, const P &p) { CALL; return true; }          \
-        PXF_DEV static void apply2(Ray *rr, const P &p) { CALL2; }                    \
     };
 PXF_CHAIN_OP(CTransform, PXF_OP_TRANSFORM, TransformP, op_transform(r, p))
 PXF_CHAIN_OP(CITransform, PXF_OP_ITRANSFORM, TransformP, op_itransform(r, p))
 PXF_CHAIN_OP(CReflect, PXF_OP_REFLECT, NoP, (void)p; op_reflect(r))
 PXF_CHAIN_OP(CFlat, PXF_OP_FLAT, NoP, (void)p; op_flat(r, false, 0.))
-PXF_CHAIN_OP2(CWolterPrimary, PXF_OP_WOLTERPRIMARY, WolterP, op_wolterprimary(r, p), op_wolterprimary_w<2>(rr, p))
-PXF_CHAIN_OP2(CWolterSecondary, PXF_OP_WOLTERSECONDARY, WolterP, op_woltersecondary(r, p), op_woltersecondary_w<2>(rr, p))
+PXF_CHAIN_OP(CWolterPrimary, PXF_OP_WOLTERPRIMARY, WolterP, op_wolterprimary(r, p))
+PXF_CHAIN_OP(CWolterSecondary, PXF_OP_WOLTERSECONDARY, WolterP, op_woltersecondary(r, p))
 PXF_CHAIN_OP(CWsPrimary, PXF_OP_WSPRIMARY, WSP, op_wsprimary(r, p))
 PXF_CHAIN_OP(CWsSecondary, PXF_OP_WSSECONDARY, WSP, op_wssecondary(r, p))
 PXF_CHAIN_OP(CSpoCone, PXF_OP_SPOCONE, SpoP, op_spocone(r, p))
@@ -58,7 +48,6 @@ template <class... Ops> struct Chain;
 template <> struct Chain<> {
     static constexpr int N = 0;
     PXF_DEV static bool run(Ray &, const ChainP<> &) { return true; }
-    PXF_DEV static void run2(Ray *, const ChainP<> &) {}
     static void fill(ChainP<> &, const FusedOp *) {}
     static bool match(const FusedOp *, int n) { return n == 0; }
 };
@@ -68,11 +57,6 @@ template <class Op, class... Rest> struct Chain<Op, Rest...> {
     {
         if (!Op::apply(r, p.head)) return false;
         return Chain<Rest...>::run(r, p.tail);
-    }
-    PXF_DEV static void run2(Ray *rr, const ChainP<Op, Rest...> &p)      // chains carry no vignette ops
-    {
-        Op::apply2(rr, p.head);
-        Chain<Rest...>::run2(rr, p.tail);
     }
     static void fill(ChainP<Op, Rest...> &cp, const FusedOp *ops)
     {
@@ -89,7 +73,6 @@ template <class Op, class... Rest> struct Chain<Op, Rest...> {
 // ---- kernel -------------------------------------------------------------------------------
 // MODE 1: one ray per thread-iteration (8-byte accesses, also the path for unaligned rows)
 // MODE 2: two rays per thread-iteration (double2 accesses), traced one after the other
-// MODE 3: two rays per thread-iteration advanced together through the Newton loops
 // PF    : software prefetch -- the loads of the NEXT iteration are issued before the current
 //         rays are traced, so every warp keeps ~1.5-3 KB of loads in flight during its compute
 //         phase.  Without it the kernel is limited by bytes in flight: a warp is either waiting
@@ -149,12 +132,8 @@ k_chain(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict
             } else {
                 cload2<LMc>(cur[0], cur[1], P, LM, q << 1);
             }
-            if (MODE == 3) {
-                C::run2(cur, prm);
-            } else {
-                C::run(cur[0], prm);
-                C::run(cur[1], prm);
-            }
+            C::run(cur[0], prm);
+            C::run(cur[1], prm);
             const int64_t i = q << 1;
             cstore2<SMc>(cur[0], cur[1], Q, SM, i);
             if (alive) { alive[i] = 1; alive[i + 1] = 1; }
@@ -191,6 +170,160 @@ k_chain(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict
         }
     }
     if (partials) centroid_block_reduce(cnt, sx, sy, partials);
+}
+
+// ---- bulk-async (TMA) pipelined variant ------------------------------------------------------
+// The register-file variants above are limited by bytes in flight: a warp either waits for its
+// own loads or computes, and with ~70 % of its time in the fp64 Newton loops too few loads are
+// outstanding to keep HBM busy -- memory time and compute time ADD (2.6 ms + 1.6 ms measured)
+// instead of overlapping.  Here the loads are decoupled from the warps: one elected thread per CTA
+// streams 256-ray tiles of the live-in rows into an NST-deep shared-memory ring with 1-D bulk
+// copies (cp.async.bulk, completion on an mbarrier), NST-1 tiles ahead of the compute, so the
+// bytes in flight per SM are CTAs x (NST-1) x rows x 2 KB whatever the warps are doing.  Each
+// thread then traces ONE ray (lowest register pressure => more resident warps for the fp64 pipe)
+// and stores its rows directly (stores do not stall the issuing warp).
+PXF_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PXF_DEV void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+PXF_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+PXF_DEV void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+PXF_DEV void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+PXF_DEV void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class C, class CP, int NST, int MINB, unsigned LMc, unsigned SMc>
+__global__ void __launch_bounds__(PXF_BLOCK, MINB)
+k_chain_tma(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
+            double *__restrict__ partials, const unsigned LM, const unsigned SM, const __grid_constant__ CP prm)
+{
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    const unsigned lm = LMc ? LMc : LM;
+    const int nrow = __popc(lm);
+    const uint32_t stage_bytes = (uint32_t)nrow * PXF_BLOCK * 8u;
+    double *ring = reinterpret_cast<double *>(ring_raw);                        // [NST][nrow][PXF_BLOCK]
+    const uint32_t ring_s = smem_u32(ring_raw);
+    const uint32_t bar_s = ring_s + NST * stage_bytes;                          // full[NST], empty[NST]
+    const int lane = threadIdx.x & 31;
+    const int64_t ntile = num / PXF_BLOCK;                                      // full tiles only
+    const int64_t mine = ntile > blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) {
+            mbar_init(bar_s + 8u * s, 1);
+            mbar_init(bar_s + 8u * (NST + s), PXF_BLOCK / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t k) {
+        const int s = (int)(k % NST);
+        const int64_t base = ((int64_t)blockIdx.x + k * gridDim.x) * PXF_BLOCK;
+        const uint32_t full = bar_s + 8u * s;
+        mbar_expect_tx(full, stage_bytes);
+        uint32_t dst = ring_s + s * stage_bytes;
+#pragma unroll
+        for (int r = 0; r < 10; r++)
+            if ((lm >> r) & 1u) {
+                bulk_g2s(dst, P.p[r] + base, PXF_BLOCK * 8u, full);
+                dst += PXF_BLOCK * 8u;
+            }
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < NST && k < mine; k++) issue(k);
+
+    double cnt = 0., sx = 0., sy = 0.;
+    for (int64_t k = 0; k < mine; k++) {
+        const int s = (int)(k % NST);
+        // refill the stage every warp finished reading one tile ago
+        if (threadIdx.x == 0 && k >= 1 && k - 1 + NST < mine) {
+            mbar_wait(bar_s + 8u * (NST + (int)((k - 1) % NST)), (uint32_t)(((k - 1) / NST) & 1));
+            issue(k - 1 + NST);
+        }
+        __syncwarp();
+        mbar_wait(bar_s + 8u * s, (uint32_t)((k / NST) & 1));
+        const double *st = ring + (size_t)s * nrow * PXF_BLOCK + threadIdx.x;
+        Ray r;
+        {
+            double v[10];
+            int slot = 0;
+#pragma unroll
+            for (int q = 0; q < 10; q++) {
+                v[q] = 0.;
+                if ((lm >> q) & 1u) { v[q] = st[slot * PXF_BLOCK]; slot++; }
+            }
+            r.opd = v[0]; r.x = v[1]; r.y = v[2]; r.z = v[3]; r.l = v[4]; r.m = v[5]; r.n = v[6];
+            r.ux = v[7]; r.uy = v[8]; r.uz = v[9];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_s + 8u * (NST + s));
+        const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * PXF_BLOCK + threadIdx.x;
+        const bool ka = C::run(r, prm);
+        cstore1<SMc>(r, Q, SM, i);
+        if (alive) alive[i] = ka ? 1 : 0;
+        if (ka) { cnt += 1.; sx += r.x; sy += r.y; }
+    }
+    // ragged tail (< one tile): plain loads, by the CTA whose turn it would be
+    const int64_t rem = num - ntile * PXF_BLOCK;
+    if (rem > 0 && blockIdx.x == (unsigned)(ntile % gridDim.x) && threadIdx.x < rem) {
+        const int64_t i = ntile * PXF_BLOCK + threadIdx.x;
+        Ray r;
+        cload1<LMc>(r, P, LM, i);
+        const bool ka = C::run(r, prm);
+        cstore1<SMc>(r, Q, SM, i);
+        if (alive) alive[i] = ka ? 1 : 0;
+        if (ka) { cnt += 1.; sx += r.x; sy += r.y; }
+    }
+    if (partials) centroid_block_reduce(cnt, sx, sy, partials);
+}
+
+template <class C, class CP, int NST, int MINB, unsigned LMc, unsigned SMc>
+static int launch_tma(const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8_t *alive, unsigned LM, unsigned SM,
+                      const CP &cp, cudaStream_t s, double *partials, int *grid_out)
+{
+    static int ctas = 0;
+    auto kern = k_chain_tma<C, CP, NST, MINB, LMc, SMc>;
+    const unsigned lm = LMc ? LMc : LM;
+    int nrow = 0;
+    for (int r = 0; r < 10; r++) nrow += (lm >> r) & 1u;
+    const size_t smem = (size_t)NST * nrow * PXF_BLOCK * 8 + 2 * NST * 8;
+    if (ctas == 0 || LMc == 0) {
+        // (runtime masks: the ring size depends on the live rows, so re-query)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * NST * PXF_BLOCK * 8 + 2 * NST * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return PXF_ERR_UNSUPPORTED;
+        }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PXF_BLOCK, smem) != cudaSuccess || nb <= 0) {
+            cudaGetLastError();
+            return PXF_ERR_UNSUPPORTED;
+        }
+        ctas = nb;
+    }
+    const int grid = grid_for(num, PXF_BLOCK, ctas);
+    if (grid_out) *grid_out = grid;
+    kern<<<grid, PXF_BLOCK, smem, s>>>(P, Q, num, alive, partials, LM, SM, cp);
+    count_launch();
+    return check_launch("k_chain_tma");
 }
 
 template <class C, class CP, int MODE, bool PF, int MINB, unsigned LMc, unsigned SMc>
@@ -244,9 +377,20 @@ static int try_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const Fuse
 #define PXF_LV(MODE, PF, MINB)                                                                              \
     (stat ? launch_variant<C, CP, MODE, PF, MINB, LMc, SMc>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out) \
           : launch_variant<C, CP, MODE, false, MINB, 0u, 0u>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out))
+#define PXF_TV(NST, MINB)                                                                                  \
+    (stat ? launch_tma<C, CP, NST, MINB, LMc, SMc>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out)     \
+          : launch_tma<C, CP, NST, MINB, 0u, 0u>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out))
     if (!aligned) return PXF_LV(1, true, 3);
     if constexpr (TUNABLE) {
         switch (variant_override()) {
+            case 432: return PXF_TV(2, 3);
+            case 433: return PXF_TV(3, 3);
+            case 434: return PXF_TV(4, 3);
+            case 442: return PXF_TV(2, 4);
+            case 443: return PXF_TV(3, 4);
+            case 444: return PXF_TV(4, 4);
+            case 446: return PXF_TV(6, 4);
+            case 453: return PXF_TV(3, 5);
             case 130: return PXF_LV(1, false, 3);
             case 131: return PXF_LV(1, true, 3);
             case 141: return PXF_LV(1, true, 4);
@@ -254,14 +398,12 @@ static int try_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const Fuse
             case 221: return PXF_LV(2, true, 2);
             case 230: return PXF_LV(2, false, 3);
             case 231: return PXF_LV(2, true, 3);
-            case 320: return PXF_LV(3, false, 2);
-            case 321: return PXF_LV(3, true, 2);
-            case 331: return PXF_LV(3, true, 3);
             default: break;
         }
     }
     return PXF_LV(2, false, 3);      // tuned on B200 (profiles/r01_notes.md): two rays in sequence, 3 CTAs/SM, no prefetch
 #undef PXF_LV
+#undef PXF_TV
 }
 
 int launch_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const FusedProgram &fp, uint8_t *alive,

@@ -24,7 +24,8 @@ inline TransformP make_transform(double tx, double ty, double tz, double rx, dou
     p.cx = cos(rx); p.sx = sin(rx);
     p.cy = cos(ry); p.sy = sin(ry);
     p.cz = cos(rz); p.sz = sin(rz);
-    p.groups = 7; p.pad = 0;
+    p.groups = 7;
+    p.ident = ((p.cx == 1. && p.sx == 0.) ? 1 : 0) | ((p.cy == 1. && p.sy == 0.) ? 2 : 0) | ((p.cz == 1. && p.sz == 0.) ? 4 : 0);
     return p;
 }
 // transformationsf.f95:168-201: tmp = -rz; rotatevector(…,tmp,3) …

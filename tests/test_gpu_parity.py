@@ -12,7 +12,7 @@ Bar (BASELINE.json north_star / SURVEY.md 7 "FMA"):
 import numpy as np
 import pytest
 
-from util import (assert_bit_equal, assert_close, chains, copy, of, pyref, random_bundle, rows_of,
+from util import (ROWS, assert_bit_equal, assert_close, chains, copy, of, pyref, random_bundle, rows_of,
                   run_steps_gpu, steps_to_program, to_dev, to_host)
 
 pytestmark = pytest.mark.gpu
@@ -89,6 +89,85 @@ def test_algebraic_routines_bit_exact(pxf, name, make, steps):
     chains.run_steps_cpu(cpu, steps)
     run_steps_gpu(dev, steps)
     assert_bit_equal(to_host(dev), cpu, what=name)
+
+
+def assert_same_bits(got, want, what=""):
+    """Stricter than assert_bit_equal: the 64-bit patterns agree (sign of zero included); NaN
+    payloads are not compared, NaN positions are."""
+    for k in range(10):
+        a, b = np.asarray(got[k]), np.asarray(want[k])
+        na, nb = np.isnan(a), np.isnan(b)
+        assert np.array_equal(na, nb), "%s row %s: NaN pattern differs" % (what, ROWS[k])
+        ia, ib = a.view(np.uint64)[~na], b.view(np.uint64)[~nb]
+        bad = np.flatnonzero(ia != ib)
+        assert bad.size == 0, "%s row %s: %d bit patterns differ, first %r vs %r" % (
+            what, ROWS[k], bad.size, a[~na][bad[0]], b[~nb][bad[0]])
+
+
+def special_value_bundle(seed, huge=True):
+    """Finite rays salted with -0, +0, NaN, +-Inf, denormals and (optionally) huge values in every row."""
+    rays = random_bundle(N, seed)
+    rng = np.random.default_rng(seed + 1000)
+    specials = [-0., 0., np.nan, np.inf, -np.inf, 5e-324, -5e-324, 2.2e-308, -1e-310]
+    if huge:
+        specials += [1e300, -1e305, 2. ** 1017, -(2. ** 1016)]
+    specials = np.array(specials)
+    for r in rays:
+        idx = rng.choice(N, N // 8, replace=False)
+        r[idx] = rng.choice(specials, idx.size)
+    return rays
+
+
+# Identity rotations (angle +-0) skip their arithmetic only for finite, non-(-0) components; the
+# sign of every zero and the NaN poisoning of non-finite rays must still be the reference's.
+ZERO_ANGLE = [
+    ("translate", (0., 0., -8400., 0., 0., 0.)),
+    ("translate_negzero_angles", (1., -2., 3., -0., -0., -0.)),
+    ("rot_z_only", (0., 0., 0., 0., 0., .3)),
+    ("rot_x_only", (5., 0., 0., -.2, 0., -0.)),
+    ("rot_y_only", (0., 0., 0., -0., .7, 0.)),
+    ("general", (1., 2., 3., .1, -.2, .3)),
+]
+
+
+@pytest.mark.parametrize("name,args", ZERO_ANGLE, ids=[a[0] for a in ZERO_ANGLE])
+@pytest.mark.parametrize("routine", ["transform", "itransform"])
+def test_transform_special_values_same_bits(pxf, routine, name, args):
+    cpu = special_value_bundle(21)
+    dev = to_dev(cpu)
+    steps = [(routine, args)]
+    chains.run_steps_cpu(cpu, steps)
+    run_steps_gpu(dev, steps)
+    assert_same_bits(to_host(dev), cpu, what=routine + " " + name)
+    # and inside a fused program (liveness drops the dead triplets, same per-ray code)
+    cpu2 = special_value_bundle(22)
+    dev2 = to_dev(cpu2)
+    steps2 = [(routine, args), ("reflect", ()), (routine, args)]
+    chains.run_steps_cpu(cpu2, steps2)
+    steps_to_program(steps2).run(dev2)
+    assert_same_bits(to_host(dev2), cpu2, what="fused " + routine + " " + name)
+
+
+def test_division_helpers_same_bits_on_special_values(pxf):
+    """flat divides -z/n: zero dividends of either sign, zero/denormal/huge divisors, NaN and Inf
+    must come out with the operator's bits (the helpers only shortcut operands in a safe window)."""
+    cpu = special_value_bundle(23)
+    dev = to_dev(cpu)
+    steps = [("flat", ())]
+    chains.run_steps_cpu(cpu, steps)
+    run_steps_gpu(dev, steps)
+    assert_same_bits(to_host(dev), cpu, what="flat specials")
+    # Newton surfaces on garbage: every ray ends in the same state as the oracle's.  (No huge finite
+    # values here: the kernels evaluate Fx*l+Fy*m as -2*(x*l+y*m), which is the same double unless
+    # 2*x*l overflows while x*l does not -- beyond 8.9e307 the Inf/NaN patterns may differ.)
+    for name, a in (("wolterprimary", (220., 8400., 1.)), ("woltersecondary", (220., 8400., 1.))):
+        cpu = special_value_bundle(24, huge=False)
+        for k in (1, 2, 3):
+            cpu[k][::3] = random_bundle(N, 25)[k][::3]
+        dev = to_dev(cpu)
+        chains.run_steps_cpu(cpu, [(name, a)])
+        run_steps_gpu(dev, [(name, a)])
+        assert_same_bits(to_host(dev), cpu, what=name + " specials")
 
 
 def test_grat_bit_exact(pxf):
