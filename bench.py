@@ -40,8 +40,8 @@ PERCALL_BYTES_PER_RAY = 576
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--rays", type=float, default=1.25e8, help="rays per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -60,13 +60,20 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.lines = []          # (wall-clock time the line was read, line)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -75,7 +82,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -87,7 +94,17 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # nvidia-smi is started BEFORE the warm-up (its start-up holds driver locks for ~100 ms and
+        # must not land in the timed region); keep the samples read inside the timed region, or --
+        # when the region is shorter than the sampling period -- those taken under load since the
+        # warm-up began (the GPU runs the same step back to back from there on).
+        inside = [ln for t, ln in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        window = "timed region"
+        if not inside:
+            inside = [ln for t, ln in self.lines]
+            window = "warm-up + timed region"
+        self.window = window
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -104,7 +121,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+                "samples": len(sm), "power_w_max": max(power), "window": self.window}
 
 
 # ------------------------------------------------------------------------------- CPU arm
@@ -230,17 +247,19 @@ def run_engine(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)                 # let nvidia-smi finish its start-up before anything is timed
     for _ in range(max(args.warmup, 3)):
         hp = step()
     barrier()
     # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled alongside
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = pxf.launch_count()
     barrier()
+    clk.mark_begin()
     ev0.record()
     for k in range(args.steps):
         kev[k][0].record()
@@ -249,6 +268,7 @@ def run_engine(args):
         hp = pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
     ev1.record()
     barrier()
+    clk.mark_end()
     launches = pxf.launch_count() - launches0
     clocks = clk.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)

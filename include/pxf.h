@@ -301,9 +301,10 @@ int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t
 int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_dev, int32_t shift,
                          int32_t bits, void *state, pxf_stream_t stream);
 /* Unweighted HPD entirely on the device.  out_dev: double[4] = {2*median, lower middle, upper
- * middle, valid}.  mode 0 = automatic (bracketed select for bundles >= pxf_bracket_min_num()),
- * 1 = force the five-pass select.  With mode 0 the caller checks out_dev[3]: 0 means the
- * bracket missed (probability ~1e-9) and the call must be repeated with mode 1.
+ * middle, valid}.  mode 0 = automatic (bracketed select for bundles >= pxf_bracket_min_num(),
+ * small selects fused into single kernels), 1 = force the five-pass select, 2 = bracketed select
+ * through the pass-wise entry points above.  With mode 0/2 the caller checks out_dev[3]: 0 means
+ * the bracket missed (probability ~1e-9) and the call must be repeated with mode 1.
  * workspace: pxf_hpd_workspace_bytes(num). */
 size_t pxf_hpd_workspace_bytes(int64_t num);
 int pxf_hpd_unweighted_dev(const double *x, const double *y, int64_t num, double *out_dev,

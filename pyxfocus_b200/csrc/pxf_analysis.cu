@@ -457,6 +457,297 @@ __global__ void k_select_begin_bracket(SelectState *st, unsigned long long k0, u
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nh; t += gridDim.x * blockDim.x) hist[t] = 0ull;
 }
 
+// ------------------------------------------------------------------ single-GPU fast path
+// The pass-wise select above is built for the multi-GPU driver (a histogram all-reduce between
+// passes) and costs 11 launches of ~10 us for each of its two small selects.  On one GPU the
+// same result comes from four launches around the one big pass:
+//   k_select_sample_sums   centroid from the sums + strided sample of radii        (multi-CTA)
+//   k_bracket_small        ONE CTA: three 13-bit radix passes over the 64 Ki sample keys with
+//                          shared-memory histograms -> bracket [lo,hi] (the sample order statistics
+//                          ra, rb rounded outwards to 39-bit prefixes); zeroes the counters
+//   k_bracket_collect      the HBM pass (unchanged)
+//   k_cand_hist            candidates -> 4096 LINEAR bins over [lo,hi] (monotone, so bin order is
+//                          value order); the last CTA to finish scans the bins and picks the one or
+//                          two bins holding the middle ranks
+//   k_cand_finish          collects the few hundred keys of those bins; the last CTA sorts them in
+//                          shared memory and writes {2*median, lower, upper, valid}
+// Exact: every step either narrows by a monotone map or sorts; anything unexpected (bracket miss,
+// buffer overflow, ties piling into one bin) clears `valid` and the caller reruns the five-pass
+// select.
+#define FAST_NBINS 4096
+#define FAST_FINCAP 4096
+struct FastSel {
+    unsigned int ticket_hist, ticket_fin;
+    unsigned int bin_a, bin_b;
+    unsigned long long base_a;       // candidates in bins below bin_a
+    unsigned long long r0, r1;       // ranks of the two middle order statistics among the candidates
+    unsigned int nfin;
+    int valid;
+    int is_nan;
+    int pad;
+};
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_select_sample_sums(const double *__restrict__ x, const double *__restrict__ y, int64_t num,
+                     const double *__restrict__ sums, double *__restrict__ cxy, int nsamp, double *__restrict__ keys)
+{
+    // same arithmetic as k_centroid_from_sums; every thread computes it, thread 0 publishes it
+    const double cx = sums[1] / sums[0], cy = sums[2] / sums[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cxy[0] = cx; cxy[1] = cy; }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nsamp; j += gridDim.x * blockDim.x) {
+        const int64_t i = (int64_t)(((unsigned long long)j * (unsigned long long)num) / (unsigned long long)nsamp);
+        keys[j] = sqrt(sq(x[i] - cx) + sq(y[i] - cy));
+    }
+}
+
+// block-wide: find the bin holding 0-based rank `rank` in the nbins-entry shared histogram h
+// (nbins <= 8 * blockDim.x).  Returns through found[0] = bin, found[1] = count below the bin
+// (both untouched when rank >= total).  All threads must call.
+PXF_DEV void block_find_bin(const unsigned int *h, int nbins, unsigned long long rank, unsigned long long *wsum,
+                            unsigned long long *found)
+{
+    const int per = (nbins + blockDim.x - 1) / blockDim.x;
+    const int b0 = threadIdx.x * per;
+    unsigned long long local = 0;
+    for (int b = b0; b < b0 + per && b < nbins; b++) local += h[b];
+    unsigned long long incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0ull;
+        unsigned long long iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    const unsigned long long excl = wsum[warp] + incl - local;
+    if (rank >= excl && rank < excl + local) {
+        unsigned long long c = excl;
+        for (int b = b0; b < b0 + per && b < nbins; b++) {
+            const unsigned long long hb = h[b];
+            if (rank < c + hb) { found[0] = (unsigned long long)b; found[1] = c; break; }
+            c += hb;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long ra, unsigned long long rb,
+                double *__restrict__ lohi, unsigned long long *__restrict__ counters, FastSel *__restrict__ fs,
+                unsigned int *__restrict__ fhist)
+{
+    extern __shared__ unsigned int sh[];                // [2][8192]
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long found[2][2];
+    __shared__ unsigned long long prefix[2], rank[2];
+    __shared__ int np;
+    const int NB = 8192;
+    // housekeeping for the kernels that follow
+    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) fhist[t] = 0u;
+    if (threadIdx.x < 8) counters[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) {
+        fs->ticket_hist = 0; fs->ticket_fin = 0; fs->nfin = 0; fs->valid = 0; fs->is_nan = 0;
+        prefix[0] = prefix[1] = 0ull; rank[0] = ra; rank[1] = rb; np = 1;
+    }
+    __syncthreads();
+    const int shifts[3] = {51, 38, 25};
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = shifts[pass], hi = shift + 13;
+        const int npl = np;
+        const unsigned long long p0 = prefix[0], p1 = prefix[1];
+        for (int t = threadIdx.x; t < 2 * NB; t += blockDim.x) sh[t] = 0u;
+        if (threadIdx.x < 2) { found[threadIdx.x][0] = 0ull; found[threadIdx.x][1] = 0ull; }
+        __syncthreads();
+        // warp-aggregated (the first pass sees almost every key in the same one or two bins); loads
+        // issued eight at a time so the single CTA is not bound by one L2 latency per key
+        for (int j0 = 0; j0 < nsamp; j0 += 8 * blockDim.x) {
+            double rv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = j0 + u * blockDim.x + threadIdx.x;
+                rv[u] = j < nsamp ? keys[j] : __longlong_as_double(0x7ff8000000000000ll);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int bin = -1;
+                const double r = rv[u];
+                if (r == r) {
+                    const unsigned long long k = key_of(r);
+                    const unsigned long long top = hi >= 64 ? 0ull : (k >> hi);
+                    const int d = (int)((k >> shift) & (unsigned long long)(NB - 1));
+                    if (top == p0) bin = d;
+                    else if (npl == 2 && top == p1) bin = NB + d;
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (bin >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[bin], __popc(peers));
+            }
+        }
+        __syncthreads();
+        for (int j = 0; j < 2; j++)
+            block_find_bin(sh + ((npl == 2) ? j : 0) * NB, NB, rank[j], wsum, found[j]);
+        if (threadIdx.x == 0) {
+            const unsigned long long pa = prefix[0], pb = (npl == 2) ? prefix[1] : prefix[0];
+            prefix[0] = (pa << 13) | found[0][0];
+            prefix[1] = (pb << 13) | found[1][0];
+            rank[0] -= found[0][1];
+            rank[1] -= found[1][1];
+            np = (prefix[0] == prefix[1]) ? 1 : 2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // 39 resolved bits; round the bracket outwards over the 25 unresolved ones
+        lohi[1] = __longlong_as_double((long long)(prefix[0] << 25));
+        lohi[2] = __longlong_as_double((long long)((prefix[1] << 25) | ((1ull << 25) - 1ull)));
+    }
+}
+
+PXF_DEV int cand_bin(double r, double lo, double scale)
+{
+    const double t = (r - lo) * scale;          // monotone in r; NaN (hi == lo) -> bin 0
+    int b = t > 0. ? (t < (double)FAST_NBINS ? (int)t : FAST_NBINS - 1) : 0;
+    return b;
+}
+PXF_DEV double cand_scale(double lo, double hi)
+{
+    const double w = hi - lo;
+    return w > 0. ? (double)FAST_NBINS / w : 0.;
+}
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_cand_hist(const double *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ counters,
+            const double *__restrict__ lohi, unsigned long long k0, unsigned long long k1,
+            unsigned int *__restrict__ fhist, FastSel *__restrict__ fs)
+{
+    __shared__ unsigned int sh[FAST_NBINS];
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long found[2][2];
+    __shared__ bool last;
+    const unsigned long long below = counters[0], ncand = counters[1], nnan = counters[2];
+    const bool ok = nnan == 0 && counters[3] == 0 && ncand <= cap && k0 >= below && k1 < below + ncand;
+    if (!ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { fs->valid = nnan ? 1 : 0; fs->is_nan = nnan ? 1 : 0; }
+        return;
+    }
+    const double lo = lohi[1], scale = cand_scale(lo, lohi[2]);
+    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) sh[t] = 0u;
+    __syncthreads();
+    const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < ncand; i0 += 8 * nthr) {
+        double rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const unsigned long long i = i0 + u * nthr; rv[u] = i < ncand ? cand[i] : 0.; }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (i0 + u * nthr < ncand) atomicAdd(&sh[cand_bin(rv[u], lo, scale)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) {
+        const unsigned int v = sh[t];
+        if (v) atomicAdd(&fhist[t], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&fs->ticket_hist, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) sh[t] = __ldcg(&fhist[t]);
+    if (threadIdx.x < 2) { found[threadIdx.x][0] = 0ull; found[threadIdx.x][1] = 0ull; }
+    __syncthreads();
+    const unsigned long long r0 = k0 - below, r1 = k1 - below;
+    block_find_bin(sh, FAST_NBINS, r0, wsum, found[0]);
+    block_find_bin(sh, FAST_NBINS, r1, wsum, found[1]);
+    if (threadIdx.x == 0) {
+        fs->bin_a = (unsigned int)found[0][0];
+        fs->bin_b = (unsigned int)found[1][0];
+        fs->base_a = found[0][1];
+        fs->r0 = r0; fs->r1 = r1;
+        fs->valid = 1;
+    }
+}
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_cand_finish(const double *__restrict__ cand, const unsigned long long *__restrict__ counters,
+              const double *__restrict__ lohi, FastSel *__restrict__ fs, double *__restrict__ fin,
+              double *__restrict__ out)
+{
+    __shared__ double srt[FAST_FINCAP];
+    __shared__ bool last;
+    const int valid = fs->valid;
+    if (!valid || fs->is_nan) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+            out[0] = nanv; out[1] = nanv; out[2] = nanv; out[3] = valid ? 1. : 0.;
+        }
+        return;
+    }
+    const unsigned long long ncand = counters[1];
+    const double lo = lohi[1], scale = cand_scale(lo, lohi[2]);
+    const int ba = (int)fs->bin_a, bb = (int)fs->bin_b;
+    const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < ncand; i0 += 8 * nthr) {
+        double rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const unsigned long long i = i0 + u * nthr; rv[u] = i < ncand ? cand[i] : 0.; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int b = cand_bin(rv[u], lo, scale);
+            if (i0 + u * nthr < ncand && b >= ba && b <= bb) {
+                const unsigned int slot = atomicAdd(&fs->nfin, 1u);
+                if (slot < FAST_FINCAP) fin[slot] = rv[u];
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&fs->ticket_fin, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const unsigned int n = *reinterpret_cast<volatile unsigned int *>(&fs->nfin);
+    const unsigned long long i0 = fs->r0 - fs->base_a, i1 = fs->r1 - fs->base_a;
+    if (n > FAST_FINCAP || i1 >= n) {
+        if (threadIdx.x == 0) { out[0] = 0.; out[1] = 0.; out[2] = 0.; out[3] = 0.; }
+        return;
+    }
+    // bitonic sort of n keys padded with +Inf to a power of two
+    unsigned int m = 1;
+    while (m < n) m <<= 1;
+    for (unsigned int t = threadIdx.x; t < m; t += blockDim.x)
+        srt[t] = t < n ? __ldcg(&fin[t]) : __longlong_as_double(0x7ff0000000000000ll);
+    __syncthreads();
+    for (unsigned int k = 2; k <= m; k <<= 1) {
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int t = threadIdx.x; t < m; t += blockDim.x) {
+                const unsigned int u = t ^ j;
+                if (u > t) {
+                    const double a = srt[t], b = srt[u];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { srt[t] = b; srt[u] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double a = srt[i0], b = srt[i1];
+        out[0] = ((a + b) / 2.) * 2.;
+        out[1] = a; out[2] = b; out[3] = 1.;
+    }
+}
+
 // ------------------------------------------------------------------ compaction
 #define CTILE 2048   // rays per CTA tile: 8 warps x 8 chunks x 32 lanes
 
@@ -891,6 +1182,7 @@ int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_
 struct HpdWs {
     char *sums_scr; double *sums, *cxy, *lohi, *samp; void *stA, *stB; unsigned long long *counters; double *cand;
     int64_t cap;
+    FastSel *fs; unsigned int *fhist; double *fin;
 };
 static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t hpd_ws_carve(HpdWs &w, char *base, int64_t num)
@@ -904,6 +1196,9 @@ static size_t hpd_ws_carve(HpdWs &w, char *base, int64_t num)
     w.stA = base + off; off += a256(pxf_select_state_bytes());
     w.stB = base + off; off += a256(pxf_select_state_bytes());
     w.samp = (double *)(base + off); off += a256((size_t)BRACKET_SAMPLES * 8);
+    w.fs = (FastSel *)(base + off); off += a256(sizeof(FastSel));
+    w.fhist = (unsigned int *)(base + off); off += a256((size_t)FAST_NBINS * 4);
+    w.fin = (double *)(base + off); off += a256((size_t)FAST_FINCAP * 8);
     w.cap = num >= BRACKET_MIN_NUM ? pxf_bracket_capacity(num) : 0;
     w.cand = (double *)(base + off); off += a256((size_t)w.cap * 8);
     return off;
@@ -929,9 +1224,11 @@ static int hpd_full(const double *x, const double *y, int64_t num, const double 
 
 /* Unweighted HPD entirely on the device.  out_dev: double[4] = {2*median, lower middle, upper
  * middle, valid}.  mode 0 = automatic (bracketed select for large bundles: one full pass
- * instead of five), 1 = force the five-pass select.  With mode 0 the caller must check
- * out_dev[3]: 0 means the bracket missed (probability ~1e-9) and the call has to be repeated
- * with mode 1.  workspace: pxf_hpd_workspace_bytes(num). */
+ * instead of five, small selects fused into single kernels), 1 = force the five-pass select,
+ * 2 = the bracketed select built from the pass-wise entry points (what the multi-GPU driver
+ * runs with all-reduces in between).  With mode 0/2 the caller must check out_dev[3]: 0 means
+ * the bracket missed (probability ~1e-9) or ties overflowed a bin, and the call has to be
+ * repeated with mode 1.  workspace: pxf_hpd_workspace_bytes(num). */
 int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const double *sums_dev, double *out_dev,
                           void *workspace, int32_t mode, pxf_stream_t stream);
 
@@ -957,12 +1254,34 @@ int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const d
             return rc;
         sums_dev = w.sums;
     }
+    int64_t ra, rb;
+    pxf_bracket_sample_ranks(BRACKET_SAMPLES, &ra, &rb);
+    if (mode == 0 && num >= BRACKET_MIN_NUM) {
+        // single-GPU fast path (see k_bracket_small): 5 launches in all
+        static int smem_set = 0;
+        if (!smem_set) {
+            PXF_CUDA(cudaFuncSetAttribute(k_bracket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
+            smem_set = 1;
+        }
+        k_select_sample_sums<<<grid_for(BRACKET_SAMPLES, PXF_BLOCK, 4), PXF_BLOCK, 0, s>>>(
+            x, y, num, sums_dev, w.cxy, BRACKET_SAMPLES, w.samp);
+        k_bracket_small<<<1, 1024, 2 * 8192 * 4, s>>>(w.samp, BRACKET_SAMPLES, (unsigned long long)ra, (unsigned long long)rb,
+                                                       w.lohi, w.counters, w.fs, w.fhist);
+        count_launch(2);
+        if ((rc = check_launch("k_bracket_small"))) return rc;
+        if ((rc = pxf_bracket_collect(x, y, num, w.cxy, w.lohi, w.cand, w.cap, reinterpret_cast<uint64_t *>(w.counters), stream))) return rc;
+        const int g = grid_for(w.cap, PXF_BLOCK * 8, 2);     // few CTAs: each flushes a 4096-bin histogram
+        k_cand_hist<<<g, PXF_BLOCK, 0, s>>>(w.cand, (unsigned long long)w.cap, w.counters, w.lohi,
+                                            (unsigned long long)((num - 1) / 2), (unsigned long long)(num / 2), w.fhist, w.fs);
+        k_cand_finish<<<g, PXF_BLOCK, 0, s>>>(w.cand, w.counters, w.lohi, w.fs, w.fin, out_dev);
+        count_launch(2);
+        return check_launch("k_cand_finish");
+    }
     k_centroid_from_sums<<<1, 1, 0, s>>>(sums_dev, w.cxy);
     count_launch();
     if (mode == 1 || num < BRACKET_MIN_NUM) return hpd_full(x, y, num, w.cxy, w.stA, out_dev, stream);
+    // mode 2: the pass-wise bracketed select (what the multi-GPU driver runs, with all-reduces between passes)
     // 1. bracket from a strided sample (exact select of two sample order statistics)
-    int64_t ra, rb;
-    pxf_bracket_sample_ranks(BRACKET_SAMPLES, &ra, &rb);
     if ((rc = pxf_select_sample(x, y, num, w.cxy, BRACKET_SAMPLES, w.samp, stream))) return rc;
     if ((rc = pxf_select_begin(w.stA, ra, rb, stream))) return rc;
     for (int p = 0; p < 5; p++) {
