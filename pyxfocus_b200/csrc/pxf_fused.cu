@@ -184,7 +184,15 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
         unsigned use, st, kill;
         op_masks(o.code, f.row, use, st, kill);
         store |= st;
+        // forward constant tracking: whatever this op writes is no longer a known constant, except
+        // the plane's own outputs z = 0, u = (0,0,1) (surfacesf.f95:17-23)
+        fp.const_mask &= ~st;
+        if (o.code == PXF_OP_FLAT || o.code == PXF_OP_FLATOPD) {
+            fp.const_mask |= R_Z | R_NRM;
+            fp.const_val[3] = 0.; fp.const_val[7] = 0.; fp.const_val[8] = 0.; fp.const_val[9] = 1.;
+        }
     }
+    if (fp.has_vignette) fp.const_mask = 0;
     // Backward liveness: a row is read from HBM only if some op consumes its incoming value
     // before an op overwrites it unconditionally (e.g. the normals entering a transform that is
     // followed by a surface are dead: never loaded, never rotated).  Every row any op may write

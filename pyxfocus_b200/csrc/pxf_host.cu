@@ -6,10 +6,18 @@
 // Only the rows the program reads are uploaded and only the rows it writes are downloaded
 // (the liveness masks of build_program).  When the caller also wants the HPD, final x,y stay
 // resident in full-length device rows and the select-based HPD runs on them at the end.
+// Rows the program leaves at a known constant for every ray (z = 0 and the normal (0,0,1) after a
+// closing `flat`; FusedProgram::const_mask) are not downloaded at all: a few host threads fill
+// them in place while the DMA engines move the other rows -- for the Wolter-I chain that is 4 of
+// the 9 written rows, i.e. 40 instead of 72 B/ray over PCIe on the way back.  A constant row that
+// is also an INPUT row (z) is filled chunk by chunk, each only after its upload has completed.
 // Streams, events and device buffers are cached between calls (pxf_host_release frees them).
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <stdlib.h>
+#include <thread>
+#include <vector>
 #include "pxf_program.h"
 
 namespace pxf {
@@ -83,6 +91,14 @@ struct HostRing {
 
 static HostRing g_ring;
 static std::mutex g_ring_mutex;
+
+static void fill_const(double *dst, int64_t n, double v)
+{
+    if (v == 0.) memset(dst, 0, (size_t)n * 8);      // +0.0 is all-zero bits
+    else for (int64_t i = 0; i < n; i++) dst[i] = v;
+}
+
+static void CUDART_CB bump_counter(void *p) { static_cast<std::atomic<int64_t> *>(p)->fetch_add(1, std::memory_order_release); }
 
 static double now_ms()
 {
@@ -162,6 +178,40 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     }
     const double t1 = now_ms();
 
+    // constant output rows: filled on the host, never downloaded
+    const unsigned CM = write_back ? (SM & fp.const_mask) : 0u;
+    const unsigned CM_late = CM & LM;            // also inputs: chunk c may be overwritten only after its H2D
+    const unsigned CM_now = CM & ~LM;
+    std::atomic<int64_t> uploaded(0);
+    std::atomic<bool> abort_fill(false);
+    std::vector<std::thread> fillers;
+    if (CM) {
+        unsigned hc = std::thread::hardware_concurrency();
+        const int T = (int)(hc >= 16 ? 6 : hc >= 8 ? 4 : 2);
+        for (int t = 0; t < T; t++)
+            fillers.emplace_back([&, t, T]() {
+                for (int r = 0; r < 10; r++)
+                    if (CM_now & (1u << r)) {
+                        const int64_t a = num * t / T, b = num * (t + 1) / T;
+                        fill_const(rows_host[r] + a, b - a, fp.const_val[r]);
+                    }
+                if (!CM_late) return;
+                for (int64_t c = t; c < nchunks; c += T) {
+                    while (uploaded.load(std::memory_order_acquire) <= c) {
+                        if (abort_fill.load()) return;
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    }
+                    const int64_t lo = c * chunk, n = (lo + chunk <= num) ? chunk : (num - lo);
+                    for (int r = 0; r < 10; r++)
+                        if (CM_late & (1u << r)) fill_const(rows_host[r] + lo, n, fp.const_val[r]);
+                }
+            });
+    }
+    struct Joiner {       // error paths: stop the fillers and drain the callbacks that point at `uploaded`
+        std::vector<std::thread> &th; std::atomic<bool> &ab; cudaStream_t s; bool ok = false;
+        ~Joiner() { if (!ok) { ab.store(true); cudaStreamSynchronize(s); } for (auto &t : th) if (t.joinable()) t.join(); }
+    } joiner{fillers, abort_fill, R.s_in};
+
     int64_t alive_total = 0;
     for (int64_t c = 0; c < nchunks; c++) {
         const int k = (int)(c % nslots);
@@ -178,13 +228,14 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
             if (LM & (1u << r))
                 PXF_CUDA(cudaMemcpyAsync(rows[r], rows_host[r] + lo, (size_t)n * 8, cudaMemcpyHostToDevice, R.s_in));
         PXF_CUDA(cudaEventRecord(R.in_done[k], R.s_in));
+        if (CM_late) PXF_CUDA(cudaLaunchHostFunc(R.s_in, bump_counter, &uploaded));
         PXF_CUDA(cudaStreamWaitEvent(R.s_run, R.in_done[k], 0));
         if ((rc = launch_program(rows, n, fp, alive, R.s_run))) return rc;
         PXF_CUDA(cudaEventRecord(R.run_done[k], R.s_run));
         PXF_CUDA(cudaStreamWaitEvent(R.s_out, R.run_done[k], 0));
         if (write_back)
             for (int r = 0; r < 10; r++)
-                if (SM & (1u << r))
+                if ((SM & ~CM) & (1u << r))
                     PXF_CUDA(cudaMemcpyAsync(rows_host[r] + lo, rows[r], (size_t)n * 8, cudaMemcpyDeviceToHost, R.s_out));
         if (want_alive && alive_host)
             PXF_CUDA(cudaMemcpyAsync(alive_host + lo, alive, (size_t)n, cudaMemcpyDeviceToHost, R.s_out));
@@ -231,6 +282,9 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     }
     const double t4 = now_ms();
     PXF_CUDA(cudaStreamSynchronize(R.s_out));
+    PXF_CUDA(cudaStreamSynchronize(R.s_in));
+    joiner.ok = true;
+    for (auto &t : fillers) t.join();
     const double t5 = now_ms();
     if (alive_count_host) {
         if (!want_alive) *alive_count_host = num;

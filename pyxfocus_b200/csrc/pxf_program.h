@@ -17,6 +17,11 @@ struct FusedProgram {
     int nops;
     unsigned load_mask, store_mask;
     int has_vignette;
+    // rows whose final value is the same known constant for every ray (e.g. z = 0 and the normal
+    // (0,0,1) after a closing `flat`): the host-buffer entry point fills them on the host instead
+    // of downloading them.  Empty when the program can stop rays early (vignette predicates).
+    unsigned const_mask;
+    double const_val[10];
     FusedOp ops[PXF_MAX_OPS];
 };
 
