@@ -146,6 +146,72 @@ int pxf_ellipsoidwoltll(double *x, double *y, double *z, double *l, double *m, d
                         const int32_t *axial, const int32_t *az, int32_t cnum, const uint8_t *mask,
                         pxf_stream_t stream);
 
+/* ---- remaining surfacesf routines (one entry per Fortran subroutine) ---- */
+/* surfacesf.f95:57-101 */
+int pxf_tracesphere(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double rad,
+                    const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:104-149 */
+int pxf_tracesphereopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                       double *ux, double *uy, double *uz, int64_t num, double rad, double nr,
+                       const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:153-197 */
+int pxf_tracecyl(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double rad,
+                 const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:201-246 */
+int pxf_tracecylopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double rad, double nr,
+                    const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:251-296 (rad is the curvature) */
+int pxf_cylconic(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double rad, double k,
+                 const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:423-440 */
+int pxf_paraxial(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double F,
+                 const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:443-460 */
+int pxf_paraxialy(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double F,
+                  const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:468-508 */
+int pxf_torus(double *x, double *y, double *z, double *l, double *m, double *n,
+              double *ux, double *uy, double *uz, int64_t num, double rin, double rout,
+              const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:514-572.  p: HOST pointer, np (<= 16) even-polynomial terms */
+int pxf_conicplus(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double R, double K,
+                  const double *p, int32_t np, const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:578-638 */
+int pxf_conicplusopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num, double R, double K,
+                     const double *p, int32_t np, double nr, const uint8_t *mask, pxf_stream_t stream);
+/* surfacesf.f95:642-668.  coeff/xo/yo: HOST pointers, nc (<= 48) terms, orders 0..15 */
+int pxf_legsurf(double *x, double *y, double *z, double *l, double *m, double *n,
+                double *ux, double *uy, double *uz, int64_t num, double xwidth, double ywidth, double order,
+                const double *coeff, const int32_t *xo, const int32_t *yo, int32_t nc,
+                const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:726-815 */
+int pxf_wsprimaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                      double thick, const uint8_t *mask, pxf_stream_t stream);
+/* woltsurf.f95:824-933 */
+int pxf_wssecondaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                        double thick, const uint8_t *mask, pxf_stream_t stream);
+/* zernsurf.f95:206-250 (tables are HOST pointers, as for pxf_tracezern) */
+int pxf_zernphase(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, const double *coeff,
+                  const int32_t *rorder, const int32_t *aorder, int32_t arrsize, double rad, double wave,
+                  const uint8_t *mask, pxf_stream_t stream);
+/* zernsurf.f95:257-359: two Zernike sets, the second evaluated at theta+rot */
+int pxf_tracezernrot(double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num,
+                     const double *coeff1, const int32_t *rorder1, const int32_t *aorder1, int32_t arrsize1,
+                     const double *coeff2, const int32_t *rorder2, const int32_t *aorder2, int32_t arrsize2,
+                     double rad, double rot, const uint8_t *mask, pxf_stream_t stream);
+
 /* ======================= zernsurf ======================================= */
 /* zernsurf.f95:8-101.  coeff/rorder/aorder are HOST pointers (arrsize entries; the f2py
  * wrapper receives them as small numpy arrays, surfaces.py:39-43).  rorder[i] <= 15. */

@@ -56,6 +56,19 @@ def _declare(L):
     L.pxfo_flatopd.argtypes = nine + [_dp, _i64, _d]
     L.pxfo_conic.argtypes = nine + [_i64, _d, _d]
     L.pxfo_conicopd.argtypes = [_dp] * 10 + [_i64, _d, _d, _d]
+    L.pxfo_tracesphere.argtypes = nine + [_i64, _d]
+    L.pxfo_tracesphereopd.argtypes = [_dp] * 10 + [_i64, _d, _d]
+    L.pxfo_tracecyl.argtypes = nine + [_i64, _d]
+    L.pxfo_tracecylopd.argtypes = [_dp] * 10 + [_i64, _d, _d]
+    L.pxfo_cylconic.argtypes = nine + [_i64, _d, _d]
+    L.pxfo_paraxial.argtypes = nine + [_i64, _d]
+    L.pxfo_paraxialy.argtypes = nine + [_i64, _d]
+    L.pxfo_torus.argtypes = nine + [_i64, _d, _d]
+    L.pxfo_conicplus.argtypes = nine + [_i64, _d, _d, _dp, _i32]
+    L.pxfo_conicplusopd.argtypes = [_dp] * 10 + [_i64, _d, _d, _dp, _i32, _d]
+    L.pxfo_legsurf.argtypes = nine + [_d, _d, _d, _dp, _ip, _ip, _i32, _i64]
+    L.pxfo_wsprimaryback.argtypes = nine + [_i64, _d, _d, _d, _d]
+    L.pxfo_wssecondaryback.argtypes = nine + [_i64, _d, _d, _d, _d]
     L.pxfo_wolterprimary.argtypes = nine + [_i64, _d, _d, _d]
     L.pxfo_wolterprimaryopd.argtypes = [_dp] * 10 + [_i64, _d, _d, _d, _d]
     L.pxfo_woltersecondary.argtypes = nine + [_i64, _d, _d, _d]
@@ -69,6 +82,8 @@ def _declare(L):
     L.pxfo_zernset.argtypes = [_d, _d, _ip, _ip, _i32, _dp, _dp, _dp]
     L.pxfo_tracezern.argtypes = nine + [_i64, _dp, _ip, _ip, _i32, _d]
     L.pxfo_tracezernopd.argtypes = [_dp] * 10 + [_i64, _dp, _ip, _ip, _i32, _d, _d]
+    L.pxfo_zernphase.argtypes = [_dp] * 10 + [_i64, _dp, _ip, _ip, _i32, _d, _d]
+    L.pxfo_tracezernrot.argtypes = nine + [_i64, _dp, _ip, _ip, _i32, _dp, _ip, _ip, _i32, _d, _d]
     L.pxfo_radialpoly.argtypes = [_d, _i32, _i32]
     L.pxfo_radialpoly.restype = _d
     L.pxfo_legendre.argtypes = [_d, _i32]
@@ -187,7 +202,46 @@ def _conicopd(opd, x, y, z, l, m, n, ux, uy, uz, r, k, nr):
     lib().pxfo_conicopd(*p, num, r, k, nr)
 
 
-surfacesf = SimpleNamespace(flat=_flat, flatopd=_flatopd, conic=_conic, conicopd=_conicopd)
+def _nine_scalars(name):
+    def f(x, y, z, l, m, n, ux, uy, uz, *scalars):
+        num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+        getattr(lib(), name)(*p, num, *scalars)
+    return f
+
+
+def _ten_scalars(name):
+    def f(opd, x, y, z, l, m, n, ux, uy, uz, *scalars):
+        num, p = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+        getattr(lib(), name)(*p, num, *scalars)
+    return f
+
+
+def _conicplus(x, y, z, l, m, n, ux, uy, uz, r, k, p):
+    num, q = _io(x, y, z, l, m, n, ux, uy, uz)
+    pb, pp = _in(p)
+    lib().pxfo_conicplus(*q, num, r, k, pp, pb.shape[0])
+
+
+def _conicplusopd(opd, x, y, z, l, m, n, ux, uy, uz, r, k, p, nr):
+    num, q = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+    pb, pp = _in(p)
+    lib().pxfo_conicplusopd(*q, num, r, k, pp, pb.shape[0], nr)
+
+
+def _legsurf(x, y, z, l, m, n, ux, uy, uz, xwidth, ywidth, order, coeff, xo, yo):
+    num, q = _io(x, y, z, l, m, n, ux, uy, uz)
+    cb, cp = _in(coeff)
+    a, b = _orders(xo, yo, cb.shape[0])
+    lib().pxfo_legsurf(*q, xwidth, ywidth, order, cp, a.ctypes.data_as(_ip), b.ctypes.data_as(_ip), cb.shape[0], num)
+
+
+surfacesf = SimpleNamespace(flat=_flat, flatopd=_flatopd, conic=_conic, conicopd=_conicopd,
+                            tracesphere=_nine_scalars("pxfo_tracesphere"),
+                            tracesphereopd=_ten_scalars("pxfo_tracesphereopd"),
+                            tracecyl=_nine_scalars("pxfo_tracecyl"), tracecylopd=_ten_scalars("pxfo_tracecylopd"),
+                            cylconic=_nine_scalars("pxfo_cylconic"), paraxial=_nine_scalars("pxfo_paraxial"),
+                            paraxialy=_nine_scalars("pxfo_paraxialy"), torus=_nine_scalars("pxfo_torus"),
+                            conicplus=_conicplus, conicplusopd=_conicplusopd, legsurf=_legsurf)
 
 
 # ---------------------------------------------------------------- woltsurf
@@ -256,7 +310,9 @@ def _ellipsoidwoltll(x, y, z, l, m, n, ux, uy, uz, r0, z0, psi, s, zmax, zmin, d
 woltsurf = SimpleNamespace(wolterprimll=_wolterprimll, woltersecll=_woltersecll, ellipsoidwoltll=_ellipsoidwoltll,
                            wolterprimary=_wolterprimary, wolterprimaryopd=_wolterprimaryopd,
                            woltersecondary=_woltersecondary, woltersine=_woltersine,
-                           wsprimary=_wsprimary, wssecondary=_wssecondary, spocone=_spocone)
+                           wsprimary=_wsprimary, wssecondary=_wssecondary, spocone=_spocone,
+                           wsprimaryback=_nine_scalars("pxfo_wsprimaryback"),
+                           wssecondaryback=_nine_scalars("pxfo_wssecondaryback"))
 
 
 # ---------------------------------------------------------------- zernsurf
@@ -274,7 +330,25 @@ def _tracezernopd(opd, x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad,
     lib().pxfo_tracezernopd(*p, num, cp, r.ctypes.data_as(_ip), a.ctypes.data_as(_ip), cb.shape[0], rad, nr)
 
 
-zernsurf = SimpleNamespace(tracezern=_tracezern, tracezernopd=_tracezernopd)
+def _zernphase(opd, x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad, wave):
+    num, p = _io(opd, x, y, z, l, m, n, ux, uy, uz)
+    cb, cp = _in(coeff)
+    r, a = _orders(rorder, aorder, cb.shape[0])
+    lib().pxfo_zernphase(*p, num, cp, r.ctypes.data_as(_ip), a.ctypes.data_as(_ip), cb.shape[0], rad, wave)
+
+
+def _tracezernrot(x, y, z, l, m, n, ux, uy, uz, coeff1, rorder1, aorder1, coeff2, rorder2, aorder2, rad, rot):
+    num, p = _io(x, y, z, l, m, n, ux, uy, uz)
+    c1, c1p = _in(coeff1)
+    r1, a1 = _orders(rorder1, aorder1, c1.shape[0])
+    c2, c2p = _in(coeff2)
+    r2, a2 = _orders(rorder2, aorder2, c2.shape[0])
+    lib().pxfo_tracezernrot(*p, num, c1p, r1.ctypes.data_as(_ip), a1.ctypes.data_as(_ip), c1.shape[0],
+                            c2p, r2.ctypes.data_as(_ip), a2.ctypes.data_as(_ip), c2.shape[0], rad, rot)
+
+
+zernsurf = SimpleNamespace(tracezern=_tracezern, tracezernopd=_tracezernopd, zernphase=_zernphase,
+                           tracezernrot=_tracezernrot)
 
 
 # ---------------------------------------------------------------- specialfunctions

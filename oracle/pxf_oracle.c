@@ -595,6 +595,380 @@ void pxfo_spocone(double *x, double *y, double *z, double *l, double *m, double 
 }
 
 /* ------------------------------------------------------------------ */
+/* surfacesf.f95 -- remaining closed-form / Newton surfaces */
+/* ------------------------------------------------------------------ */
+
+/* surfacesf.f95:57-101 / :104-149.  x**2. is folded to x*x by gfortran. */
+static void tracesphere_impl(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                             double *ux, double *uy, double *uz, int64_t num, double rad, double nr)
+{
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double dotol = l[i] * x[i] + m[i] * y[i] + n[i] * z[i];
+        double mago = sq(x[i]) + sq(y[i]) + sq(z[i]);
+        double determinant = sq(dotol) - mago + sq(rad);
+        if (determinant < 0) {
+            x[i] = 0.; y[i] = 0.; z[i] = 0.; l[i] = 0.; m[i] = 0.; n[i] = 0.;
+        } else {
+            double d1 = -dotol + sqrt(determinant);
+            double d2 = -dotol - sqrt(determinant);
+            if (fabs(d2) < fabs(d1)) d1 = d2;
+            x[i] = x[i] + d1 * l[i];
+            y[i] = y[i] + d1 * m[i];
+            z[i] = z[i] + d1 * n[i];
+            if (opd) opd[i] = opd[i] + d1 * nr;
+        }
+        mago = sqrt(sq(x[i]) + sq(y[i]) + sq(z[i]));
+        ux[i] = x[i] / mago;
+        uy[i] = y[i] / mago;
+        uz[i] = z[i] / mago;
+    }
+}
+void pxfo_tracesphere(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double rad)
+{
+    tracesphere_impl(NULL, x, y, z, l, m, n, ux, uy, uz, num, rad, 0.);
+}
+void pxfo_tracesphereopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                         double *ux, double *uy, double *uz, int64_t num, double rad, double nr)
+{
+    tracesphere_impl(opd, x, y, z, l, m, n, ux, uy, uz, num, rad, nr);
+}
+
+/* surfacesf.f95:153-197 / :201-246 */
+static void tracecyl_impl(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                          double *ux, double *uy, double *uz, int64_t num, double rad, double nr)
+{
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double a = sq(l[i]) + sq(n[i]);
+        double b = 2 * (x[i] * l[i] + z[i] * n[i]);
+        double c = sq(x[i]) + sq(z[i]) - sq(rad);
+        double det = sq(b) - 4 * a * c;
+        if (det < 0) {
+            x[i] = 0.; y[i] = 0.; z[i] = 0.; l[i] = 0.; m[i] = 0.; n[i] = 0.;
+        } else {
+            double d1 = (-b + sqrt(det)) / 2 / a;
+            double d2 = (-b - sqrt(det)) / 2 / a;
+            if (fabs(d2) < fabs(d1)) d1 = d2;
+            x[i] = x[i] + l[i] * d1;
+            y[i] = y[i] + m[i] * d1;
+            z[i] = z[i] + n[i] * d1;
+            if (opd) opd[i] = opd[i] + d1 * nr;
+        }
+        double mag = sqrt(sq(x[i]) + sq(z[i]));
+        ux[i] = x[i] / mag;
+        uz[i] = z[i] / mag;
+        uy[i] = 0.;
+    }
+}
+void pxfo_tracecyl(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num, double rad)
+{
+    tracecyl_impl(NULL, x, y, z, l, m, n, ux, uy, uz, num, rad, 0.);
+}
+void pxfo_tracecylopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double rad, double nr)
+{
+    tracecyl_impl(opd, x, y, z, l, m, n, ux, uy, uz, num, rad, nr);
+}
+
+/* surfacesf.f95:251-296 (rad is the curvature; tol 1.e-10; uz = 0) */
+void pxfo_cylconic(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num, double rad, double k)
+{
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fp, low, high, dL, dH;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+            low = 1 + sqrt(1 - (1 + k) * sq(rad) * sq(x[i]));
+            high = rad * sq(x[i]);
+            dL = -(1 + k) * sq(rad) * x[i] / sqrt(1 - (1 + k) * sq(rad) * sq(x[i]));
+            dH = 2 * rad * x[i];
+            F = y[i] - high / low;
+            Fx = (high * dL - low * dH) / sq(low);
+            Fy = 1.;
+            Fp = Fx * l[i] + Fy * m[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy);
+        ux[i] = Fx / Fp;
+        uy[i] = Fy / Fp;
+        uz[i] = 0.;
+    }
+}
+
+/* surfacesf.f95:423-440 / :443-460 */
+void pxfo_paraxial(double *x, double *y, double *z, double *l, double *m, double *n,
+                   double *ux, double *uy, double *uz, int64_t num, double F)
+{
+    (void)z; (void)n; (void)ux; (void)uy; (void)uz;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        l[i] = l[i] - x[i] / F;
+        m[i] = m[i] - y[i] / F;
+    }
+}
+void pxfo_paraxialy(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double F)
+{
+    (void)x; (void)z; (void)l; (void)n; (void)ux; (void)uy; (void)uz;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) m[i] = m[i] - y[i] / F;
+}
+
+/* surfacesf.f95:468-508.  The normal is divided by sqrt(Fx**2+Fy**2) -- Fz is NOT in the norm
+ * (:499), kept as written. */
+void pxfo_torus(double *x, double *y, double *z, double *l, double *m, double *n,
+                double *ux, double *uy, double *uz, int64_t num, double rin, double rout)
+{
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+            F = sq(sq(z[i] + rin + rout) + sq(y[i]) + sq(x[i]) + sq(rout) - sq(rin)) -
+                (4 * sq(rout) * (sq(y[i]) + sq(z[i] + rin + rout)));
+            Fx = 4 * x[i] * (-sq(rin) + sq(rin + rout + z[i]) + sq(rout) + sq(x[i]) + sq(y[i]));
+            Fy = 4 * y[i] * (2 * rin * (rout + z[i]) + 2 * rout * z[i] + sq(z[i]) + sq(y[i]) + sq(x[i]));
+            Fz = 4 * (rout + rin + z[i]) * (2 * rin * (rout + z[i]) + 2 * rout * z[i] + sq(z[i]) + sq(y[i]) + sq(x[i]));
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy);
+        ux[i] = Fx / Fp;
+        uy[i] = Fy / Fp;
+        uz[i] = Fz / Fp;
+    }
+}
+
+static double powi(double x, int m);
+
+/* surfacesf.f95:514-572 / :578-638.  rad**(2*j) has a run-time INTEGER exponent: libgcc's
+ * __powidf2 (binary exponentiation), restated in powi(). */
+static void conicplus_impl(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                           double *ux, double *uy, double *uz, int64_t num, double R, double K,
+                           const double *p, int Np, double nr)
+{
+    const double Fz = 1.;
+    const double c = 1 / R;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., rad, a0, a1, F, Fr, Fx = 0, Fy = 0, Fp, denom;
+        int it = 0;
+        while (fabs(delt) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+            rad = sqrt(sq(x[i]) + sq(y[i]));
+            a0 = 0.;
+            a1 = 0.;
+            for (int j = 1; j <= Np; j++) {
+                a0 = a0 + p[j - 1] * powi(rad, 2 * j);
+                a1 = a1 + p[j - 1] * (double)(2 * j) * powi(rad, 2 * j - 1);
+            }
+            denom = sqrt(1 - (K + 1) * sq(c) * sq(rad)) + 1;
+            F = z[i] - c * sq(rad) / denom + a0;
+            Fr = -(2 * c * rad / denom + ((K + 1) * cube(rad) * cube(c)) / (sq(denom) * sqrt(1 - (K + 1) * sq(c) * sq(rad)))) + a1;
+            Fx = Fr * x[i] / rad;
+            Fy = Fr * y[i] / rad;
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+            if (opd) opd[i] = opd[i] + delt * nr;
+        }
+        Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+        ux[i] = Fx / Fp;
+        uy[i] = Fy / Fp;
+        uz[i] = Fz / Fp;
+    }
+}
+void pxfo_conicplus(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double R, double K, const double *p, int32_t Np)
+{
+    conicplus_impl(NULL, x, y, z, l, m, n, ux, uy, uz, num, R, K, p, Np, 0.);
+}
+void pxfo_conicplusopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                       double *ux, double *uy, double *uz, int64_t num, double R, double K, const double *p,
+                       int32_t Np, double nr)
+{
+    conicplus_impl(opd, x, y, z, l, m, n, ux, uy, uz, num, R, K, p, Np, nr);
+}
+
+/* surfacesf.f95:642-668 */
+void pxfo_legsurf(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, double xwidth, double ywidth, double order,
+                  const double *coeff, const int32_t *xo, const int32_t *yo, int32_t Nc, int64_t num)
+{
+    (void)z; (void)ux; (void)uy; (void)uz;
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double dphidx = 0, dphidy = 0;
+        for (int j = 0; j < Nc; j++) {
+            dphidx = dphidx + coeff[j] * pxfo_legendre(y[i] / ywidth, yo[j]) * pxfo_legendrep(x[i] / xwidth, xo[j]);
+            dphidy = dphidy + coeff[j] * pxfo_legendrep(y[i] / ywidth, yo[j]) * pxfo_legendre(x[i] / xwidth, xo[j]);
+        }
+        l[i] = l[i] + dphidx * order / xwidth;
+        m[i] = m[i] + dphidy * order / ywidth;
+        n[i] = n[i] / fabs(n[i]) * sqrt(1. - sq(l[i]) - sq(m[i]));
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* woltsurf.f95 -- Wolter-Schwarzschild back surfaces (:726-933)       */
+/* ------------------------------------------------------------------ */
+
+/* woltsurf.f95:726-815: wsprimary with the radius reduced by `thick` */
+void pxfo_wsprimaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num,
+                        double alpha, double z0, double psi, double thick)
+{
+    const double betas = 4 * alpha;
+    const double ff = z0 / cos(betas);
+    const double g = ff / psi;
+    const double k = sq(tan(betas / 2));
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp, Fb, kterm, beta, dbdx, dbdy, r, theta, x2, y2;
+        int flag, c = 0;
+        double xi = x[i], yi = y[i], zi = z[i];
+        while (fabs(delt) > TOL_1EM8) {
+            r = sqrt(sq(x[i]) + sq(y[i]));
+            theta = atan2(y[i], x[i]);
+            x2 = (r - thick) * cos(theta);
+            y2 = (r - thick) * sin(theta);
+            beta = asin(sqrt(sq(x2) + sq(y2)) / ff);
+            flag = 0;
+            if (beta <= betas) {
+                beta = betas;
+                flag = 1;
+                kterm = 0.;
+            } else {
+                kterm = (1 / k) * sq(tan(beta / 2)) - 1;
+            }
+            F = -z[i] - ff * sq(sin(betas / 2)) +
+                sq(ff) * sq(sin(beta)) / (4 * ff * sq(sin(betas / 2))) +
+                g * pow4(cos(beta / 2)) * pow(kterm, 1 - k);
+            Fb = sq(ff) * sin(beta) * cos(beta) / (2 * ff * sq(sin(betas / 2))) -
+                 2 * g * cube(cos(beta / 2)) * sin(beta / 2) * pow(kterm, 1 - k) +
+                 g * (1 - k) * cos(beta / 2) * sin(beta / 2) * pow(kterm, -k) * (1 / k);
+            Fz = -1.;
+            if (flag == 1) {
+                r = sqrt(sq(x2) + sq(y2));
+                Fb = sq(ff) * sin(betas) * cos(betas) / (2 * ff * sq(sin(betas / 2))) +
+                     g * (1 - k) * cos(betas / 2) * sin(betas / 2) * (1 / k);
+                F = F + (r - ff * sin(betas)) * z[i] / (sq(r) + sq(z[i])) * Fb;
+                Fz = Fz + (r - ff * sin(betas)) * (sq(r) - sq(z[i])) / sq(sq(r) + sq(z[i])) * Fb;
+            }
+            dbdx = x2 / sqrt(1 - (sq(x2) + sq(y2)) / sq(ff)) / ff / sqrt(sq(x2) + sq(y2));
+            dbdy = y2 / sqrt(1 - (sq(x2) + sq(y2)) / sq(ff)) / ff / sqrt(sq(x2) + sq(y2));
+            Fx = Fb * dbdx;
+            Fy = Fb * dbdy;
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+            if (c > 25 || isnan(delt)) {
+                delt = 0.;
+                x[i] = xi; y[i] = yi; z[i] = zi;
+                c = 1000;
+            }
+            c = c + 1;
+        }
+        if (c < 26) {
+            Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+            ux[i] = -Fx / Fp;
+            uy[i] = -Fy / Fp;
+            uz[i] = -Fz / Fp;
+        }
+    }
+}
+
+/* woltsurf.f95:824-933 */
+void pxfo_wssecondaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                          double *ux, double *uy, double *uz, int64_t num,
+                          double alpha, double z0, double psi, double thick)
+{
+    const double betas = 4 * alpha;
+    const double ff = z0 / cos(betas);
+    const double g = ff / psi;
+    const double k = sq(tan(betas / 2));
+    #pragma omp parallel for
+    for (int64_t i = 0; i < num; i++) {
+        double delt = 100., F, Fx = 0, Fy = 0, Fz = 0, Fp, Fb, kterm, beta, dbdx, dbdy, dbdz;
+        double a, dadbs, dbdzs, gam, dadb, r, theta, x2, y2;
+        int flag, c = 0;
+        double xi = x[i], yi = y[i], zi = z[i];
+        while (fabs(delt) > TOL_1EM8) {
+            r = sqrt(sq(x[i]) + sq(y[i]));
+            theta = atan2(y[i], x[i]);
+            x2 = (r - thick) * cos(theta);
+            y2 = (r - thick) * sin(theta);
+            beta = atan2(sqrt(sq(x2) + sq(y2)), z[i]);
+            flag = 0;
+            if (beta <= betas) {
+                beta = betas;
+                kterm = 0;
+                a = 1 / ff;
+                flag = 1;
+            } else {
+                kterm = (1 / k) * sq(tan(beta / 2)) - 1;
+                a = (1 - cos(beta)) / (1 - cos(betas)) / ff +
+                    (1 + cos(beta)) / (2 * g) * pow(kterm, 1 + k);
+            }
+            F = -z[i] + cos(beta) / a;
+            if (flag == 1) {
+                Fb = 0.;
+                dadbs = sin(betas) / ff / (1 - cos(betas)) +
+                        (k + 1) * (cos(betas) + 1) * tan(betas / 2) / sq(cos(betas / 2)) / 2 / g / k;
+                dbdzs = -sq(sin(betas)) / sqrt(sq(x2) + sq(y2));
+                gam = (-ff * sin(betas) - sq(ff) * cos(betas) * dadbs) * dbdzs;
+                F = F + gam * (z[i] - sqrt(sq(x2) + sq(y2)) / tan(betas));
+                Fx = -2. / tan(betas) * x2 / sqrt(sq(x2) + sq(y2));
+                Fy = -2. / tan(betas) * y2 / sqrt(sq(x2) + sq(y2));
+                Fz = gam - 1.;
+            } else {
+                dadb = sin(beta) / ff / (1 - cos(betas)) -
+                       sin(beta) / (2 * g) * pow(kterm, 1 + k) +
+                       (k + 1) * (cos(beta) + 1) * tan(beta / 2) * pow(kterm, k) / 2 / g / k / sq(cos(beta / 2));
+                Fb = -sin(beta) / a - cos(beta) / sq(a) * dadb;
+                dbdx = x2 * z[i] / (sq(x2) + sq(y2) + sq(z[i])) / sqrt(sq(x2) + sq(y2));
+                dbdy = y2 * z[i] / (sq(x2) + sq(y2) + sq(z[i])) / sqrt(sq(x2) + sq(y2));
+                dbdz = -sqrt(sq(x2) + sq(y2)) / (sq(x2) + sq(y2) + sq(z[i]));
+                Fx = Fb * dbdx;
+                Fy = Fb * dbdy;
+                Fz = -1. + Fb * dbdz;
+            }
+            (void)Fb;
+            Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+            delt = -F / Fp;
+            x[i] = x[i] + l[i] * delt;
+            y[i] = y[i] + m[i] * delt;
+            z[i] = z[i] + n[i] * delt;
+            if (c > 25 || isnan(delt)) {
+                delt = 0.;
+                x[i] = xi; y[i] = yi; z[i] = zi;
+                c = 1000;
+            }
+            c = c + 1;
+        }
+        if (c < 26) {
+            Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+            ux[i] = Fx / Fp;
+            uy[i] = Fy / Fp;
+            uz[i] = Fz / Fp;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* specialFunctions.f95                                               */
 /* ------------------------------------------------------------------ */
 
@@ -920,6 +1294,103 @@ static void tracezern_impl(double *opd, double *x, double *y, double *z, double 
             uy[i] = Fy / Fp;
             uz[i] = Fz / Fp;
             if (opd) opd[i] = opd[i] + t * nr;
+        }
+        free(zern); free(rhoder); free(thetader);
+    }
+}
+
+/* zernsurf.f95:206-250 (serial in the reference) */
+void pxfo_zernphase(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num,
+                    const double *coeff, const int32_t *rorder, const int32_t *aorder, int arrsize,
+                    double rad, double wave)
+{
+    (void)z; (void)ux; (void)uy; (void)uz;
+    #pragma omp parallel
+    {
+        double *zern = (double *)malloc(sizeof(double) * (size_t)arrsize);
+        double *rhoder = (double *)malloc(sizeof(double) * (size_t)arrsize);
+        double *thetader = (double *)malloc(sizeof(double) * (size_t)arrsize);
+        #pragma omp for
+        for (int64_t i = 0; i < num; i++) {
+            double rho = sqrt(sq(x[i]) + sq(y[i]));
+            double theta = atan2(y[i], x[i]);
+            pxfo_zernset(rho / rad, theta, rorder, aorder, arrsize, zern, rhoder, thetader);
+            double F = 0., Frho = 0., Ftheta = 0.;
+            for (int c = 0; c < arrsize; c++) {
+                F = F + coeff[c] * zern[c];
+                Frho = Frho + coeff[c] * rhoder[c] / rad;
+                Ftheta = Ftheta + coeff[c] * thetader[c];
+            }
+            double Frhox = (x[i] / rho) * Frho;
+            double Frhoy = (y[i] / rho) * Frho;
+            double Fthetax = (-y[i] / rho) * Ftheta / rho;
+            double Fthetay = (x[i] / rho) * Ftheta / rho;
+            double Fx = Frhox + Fthetax;
+            double Fy = Frhoy + Fthetay;
+            l[i] = l[i] + Fx * wave;
+            m[i] = m[i] + Fy * wave;
+            n[i] = copysign(sqrt(1. - sq(l[i]) - sq(m[i])), n[i]);
+            opd[i] = opd[i] + F * wave;
+        }
+        free(zern); free(rhoder); free(thetader);
+    }
+}
+
+/* zernsurf.f95:257-359 */
+void pxfo_tracezernrot(double *x, double *y, double *z, double *l, double *m, double *n,
+                       double *ux, double *uy, double *uz, int64_t num,
+                       const double *coeff1, const int32_t *rorder1, const int32_t *aorder1, int arrsize1,
+                       const double *coeff2, const int32_t *rorder2, const int32_t *aorder2, int arrsize2,
+                       double rad, double rot)
+{
+    #pragma omp parallel
+    {
+        int mx = arrsize1 > arrsize2 ? arrsize1 : arrsize2;
+        double *zern = (double *)malloc(sizeof(double) * (size_t)mx);
+        double *rhoder = (double *)malloc(sizeof(double) * (size_t)mx);
+        double *thetader = (double *)malloc(sizeof(double) * (size_t)mx);
+        #pragma omp for
+        for (int64_t i = 0; i < num; i++) {
+            double t = 0., delta = 100.;
+            double F, Frho, Ftheta, Frhox, Frhoy, Fthetax, Fthetay, Fx = 0, Fy = 0, Fz = 0, Fp, rho, theta;
+            int it = 0;
+            while (fabs(delta) > TOL_1EM10 && it++ < PXF_NEWTON_CAP) {
+                rho = sqrt(sq(x[i]) + sq(y[i]));
+                theta = atan2(y[i], x[i]);
+                F = z[i];
+                Frho = 0.;
+                Ftheta = 0.;
+                pxfo_zernset(rho / rad, theta, rorder1, aorder1, arrsize1, zern, rhoder, thetader);
+                for (int c = 0; c < arrsize1; c++) {
+                    F = F - coeff1[c] * zern[c];
+                    Frho = Frho - coeff1[c] * rhoder[c] / rad;
+                    Ftheta = Ftheta - coeff1[c] * thetader[c];
+                }
+                pxfo_zernset(rho / rad, theta + rot, rorder2, aorder2, arrsize2, zern, rhoder, thetader);
+                for (int c = 0; c < arrsize2; c++) {
+                    F = F - coeff2[c] * zern[c];
+                    Frho = Frho - coeff2[c] * rhoder[c] / rad;
+                    Ftheta = Ftheta - coeff2[c] * thetader[c];
+                }
+                Frhox = (x[i] / rho) * Frho;
+                Frhoy = (y[i] / rho) * Frho;
+                Fthetax = (-y[i] / rho) * Ftheta / rho;
+                Fthetay = (x[i] / rho) * Ftheta / rho;
+                Fx = Frhox + Fthetax;
+                Fy = Frhoy + Fthetay;
+                Fz = 1.;
+                Fp = Fx * l[i] + Fy * m[i] + Fz * n[i];
+                delta = -F / Fp;
+                x[i] = x[i] + l[i] * delta;
+                y[i] = y[i] + m[i] * delta;
+                z[i] = z[i] + n[i] * delta;
+                t = t + delta;
+            }
+            Fp = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+            ux[i] = Fx / Fp;
+            uy[i] = Fy / Fp;
+            uz[i] = Fz / Fp;
         }
         free(zern); free(rhoder); free(thetader);
     }

@@ -50,7 +50,20 @@ SIGNATURES = {
     "pxf_flatopd": (_c.c_int, _NINE + [_dp, _i64, _d, _vp, _st]),
     "pxf_conic": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
     "pxf_conicopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _d, _vp, _st]),
+    "pxf_tracesphere": (_c.c_int, _NINE + [_i64, _d, _vp, _st]),
+    "pxf_tracesphereopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _vp, _st]),
+    "pxf_tracecyl": (_c.c_int, _NINE + [_i64, _d, _vp, _st]),
+    "pxf_tracecylopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _vp, _st]),
+    "pxf_cylconic": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
+    "pxf_paraxial": (_c.c_int, _NINE + [_i64, _d, _vp, _st]),
+    "pxf_paraxialy": (_c.c_int, _NINE + [_i64, _d, _vp, _st]),
+    "pxf_torus": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _st]),
+    "pxf_conicplus": (_c.c_int, _NINE + [_i64, _d, _d, _vp, _i32, _vp, _st]),
+    "pxf_conicplusopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _vp, _i32, _d, _vp, _st]),
+    "pxf_legsurf": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _vp, _vp, _i32, _vp, _st]),
     # woltsurf
+    "pxf_wsprimaryback": (_c.c_int, _NINE + [_i64, _d, _d, _d, _d, _vp, _st]),
+    "pxf_wssecondaryback": (_c.c_int, _NINE + [_i64, _d, _d, _d, _d, _vp, _st]),
     "pxf_wolterprimary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
     "pxf_wolterprimaryopd": (_c.c_int, [_dp] * 10 + [_i64, _d, _d, _d, _d, _vp, _st]),
     "pxf_woltersecondary": (_c.c_int, _NINE + [_i64, _d, _d, _d, _vp, _st]),
@@ -64,6 +77,8 @@ SIGNATURES = {
     # zernsurf (coeff/rorder/aorder are HOST pointers)
     "pxf_tracezern": (_c.c_int, _NINE + [_i64, _vp, _vp, _vp, _i32, _d, _vp, _st]),
     "pxf_tracezernopd": (_c.c_int, [_dp] * 10 + [_i64, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),
+    "pxf_zernphase": (_c.c_int, [_dp] * 10 + [_i64, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),
+    "pxf_tracezernrot": (_c.c_int, _NINE + [_i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _d, _d, _vp, _st]),
     # fused program
     "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_to": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _st]),

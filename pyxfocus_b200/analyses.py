@@ -195,3 +195,69 @@ def findimageplane(rays, zscan, num, weights=None, sums=None):
     # RMS^2(dz) = RMS^2(0) + 2 dz Cov + dz^2 Var ; the constant does not move the argmin
     merit = 2 * dz * cxa + dz ** 2 * vxx
     return float(dz[np.argmin(merit)])
+
+
+def _plane_sums(rays, weights):
+    S = imageplane_sums(rays, weights).cpu().numpy()
+    W = S[0]
+    return S / W
+
+
+def analyticYPlane(rays, weights=None):
+    """Axial shift to the best line focus in y (analyses.py:135-144); same one-pass sums as
+    ``analyticImagePlane``."""
+    a = _plane_sums(rays, weights)      # [1, <x>, <y>, <l/n>, <m/n>, <x l/n>, <y m/n>, <(l/n)^2>, <(m/n)^2>]
+    by = a[6] - a[2] * a[4]
+    ay = a[8] - a[4] ** 2
+    return float(-by / ay)
+
+
+def analyticXPlane(rays, weights=None):
+    """Axial shift to the best line focus in x (analyses.py:146-155)."""
+    a = _plane_sums(rays, weights)
+    bx = a[5] - a[1] * a[3]
+    ax = a[7] - a[3] ** 2
+    return float(-bx / ax)
+
+
+def hpdY(rays, weights=None):
+    """HPD in the y direction about the mean y (analyses.py:99-116).  |y-cy| is the radius of the
+    point (0, y), so this is ``hpd`` on a bundle whose x row is zero: sqrt(0 + (y-cy)^2) = |y-cy|
+    exactly."""
+    flush(rays)
+    y = rays[2]
+    zero = torch.zeros_like(y)
+    fake = [rays[0], zero, y] + list(rays[3:])
+    return hpd(fake, weights=weights)
+
+
+def rmsPoint(rays, point, weights=None):
+    """RMS distance of the rays from a point: a ten-row ray or an (x,y,z) triple (analyses.py:33-45).
+    Not on the trace path: plain tensor arithmetic on the device rows."""
+    flush(rays)
+    off = 1 if np.size(point) == 10 else 0
+    px, py, pz = (float(point[off + k]) for k in range(3))
+    rho = (rays[1] - px) ** 2 + (rays[2] - py) ** 2 + (rays[3] - pz) ** 2
+    w = _w(weights, rays[1])
+    mean = rho.mean() if w is None else (rho * w).sum() / w.sum()
+    return float(torch.sqrt(mean))
+
+
+def indAngle(rays, ind=None, normal=None):
+    """Incidence angle against the current or a given surface normal (analyses.py:164-182); returns a
+    device tensor.  Not on the trace path: plain tensor arithmetic."""
+    flush(rays)
+    l, m, n, ux, uy, uz = rays[4:10]
+    if ind is not None:
+        if not isinstance(ind, torch.Tensor):
+            ind = torch.as_tensor(np.asarray(ind), device=l.device)
+        l, m, n, ux, uy, uz = (t[ind] for t in (l, m, n, ux, uy, uz))
+    if normal is None:
+        return torch.arccos(l * ux + m * uy + n * uz)
+    nx, ny, nz = (float(v) for v in normal)
+    return torch.arccos(nx * l + ny * m + nz * n)
+
+
+def grazeAngle(rays, ind=None):
+    """Graze angle against the current surface normal (analyses.py:184-187)."""
+    return np.pi / 2 - indAngle(rays, ind=ind)

@@ -228,6 +228,63 @@ struct OpWsSecondary {
     static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wssecondary(r, p); }
 };
+struct OpWsPrimaryBack {
+    using Params = WSP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wsprimary_t<true>(r, p); }
+};
+struct OpWsSecondaryBack {
+    using Params = WSP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wssecondary_t<true>(r, p); }
+};
+template <bool OPD>
+struct OpSphere {
+    using Params = SphereP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | (OPD ? R_OPD : 0u), STORE = R_NINE | (OPD ? R_OPD : 0u);
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_tracesphere(r, p); }
+};
+template <bool OPD>
+struct OpCyl {
+    using Params = SphereP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | (OPD ? R_OPD : 0u), STORE = R_NINE | (OPD ? R_OPD : 0u);
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_tracecyl(r, p); }
+};
+struct OpCylConic {
+    using Params = CylConicP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_cylconic(r, p); }
+};
+struct OpParaxial {
+    using Params = ParaxialP;
+    static constexpr unsigned LOAD = R_X | R_Y | R_L | R_M, STORE = R_L | R_M;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_paraxial(r, p); }
+};
+struct OpTorus {
+    using Params = TorusP;
+    static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_torus(r, p); }
+};
+template <bool OPD>
+struct OpConicPlus {
+    using Params = ConicPlusP;
+    static constexpr unsigned LOAD = R_POS | R_DIR | (OPD ? R_OPD : 0u), STORE = R_POS | R_NRM | (OPD ? R_OPD : 0u);
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_conicplus(r, p); }
+};
+struct OpLegSurf {
+    using Params = LegSurfP;
+    static constexpr unsigned LOAD = R_X | R_Y | R_DIR, STORE = R_DIR;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_legsurf(r, p); }
+};
 struct OpSpoCone {
     using Params = SpoP;
     static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
@@ -244,6 +301,19 @@ struct OpZern {
     PXF_DEV static void apply(Ray &r, const Params &p, const double *smem, double, double)
     {
         op_tracezern<NMAX>(r, p.rad, p.nr, p.tol, p.nmax, OPD ? 1 : 0, smem);
+    }
+};
+
+struct ZernPhaseP { ZernP z; double wave; };
+template <int NMAX>
+struct OpZernPhase {
+    using Params = ZernPhaseP;
+    static constexpr unsigned LOAD = R_X | R_Y | R_DIR | R_OPD, STORE = R_DIR | R_OPD;
+    static constexpr int AUX = 0, SMEM = PXF_ZERN_SMEM_DOUBLES;
+    PXF_DEV static const double *table(const Params &p) { return reinterpret_cast<const double *>(p.z.e); }
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *smem, double, double)
+    {
+        op_zernphase<NMAX>(r, p.z.rad, p.wave, p.z.nmax, smem);
     }
 };
 
@@ -611,6 +681,155 @@ int pxf_tracezernopd(double *opd, double *x, double *y, double *z, double *l, do
         return PXF_ERR_INVALID;
     }
     return launch_zern<true>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, zp, stream);
+}
+
+
+/* ---- surfacesf: remaining surfaces ---- */
+int pxf_tracesphere(double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double rad,
+                    const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpSphere<false>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                      make_sphere(rad, false, 0.), stream);
+}
+int pxf_tracesphereopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                       double *ux, double *uy, double *uz, int64_t num, double rad, double nr,
+                       const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpSphere<true>>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, nullptr, nullptr,
+                                     make_sphere(rad, true, nr), stream);
+}
+int pxf_tracecyl(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double rad,
+                 const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpCyl<false>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                   make_sphere(rad, false, 0.), stream);
+}
+int pxf_tracecylopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                    double *ux, double *uy, double *uz, int64_t num, double rad, double nr,
+                    const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpCyl<true>>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, nullptr, nullptr,
+                                  make_sphere(rad, true, nr), stream);
+}
+int pxf_cylconic(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double rad, double k,
+                 const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpCylConic>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                 make_cylconic(rad, k), stream);
+}
+int pxf_paraxial(double *x, double *y, double *z, double *l, double *m, double *n,
+                 double *ux, double *uy, double *uz, int64_t num, double F,
+                 const uint8_t *mask, pxf_stream_t stream)
+{
+    (void)z; (void)n; (void)ux; (void)uy; (void)uz;
+    ParaxialP p{F, 0, 0};
+    return launch_op<OpParaxial>(rows9(x, y, nullptr, l, m, nullptr, nullptr, nullptr, nullptr), num, mask, nullptr,
+                                 nullptr, p, stream);
+}
+int pxf_paraxialy(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double F,
+                  const uint8_t *mask, pxf_stream_t stream)
+{
+    (void)z; (void)n; (void)ux; (void)uy; (void)uz;
+    ParaxialP p{F, 1, 0};
+    return launch_op<OpParaxial>(rows9(x, y, nullptr, l, m, nullptr, nullptr, nullptr, nullptr), num, mask, nullptr,
+                                 nullptr, p, stream);
+}
+int pxf_torus(double *x, double *y, double *z, double *l, double *m, double *n,
+              double *ux, double *uy, double *uz, int64_t num, double rin, double rout,
+              const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpTorus>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                              make_torus(rin, rout), stream);
+}
+int pxf_conicplus(double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, double R, double K,
+                  const double *p, int32_t np, const uint8_t *mask, pxf_stream_t stream)
+{
+    ConicPlusP q;
+    if ((np > 0 && !p) || make_conicplus(q, R, K, p, np, false, 0.) < 0) {
+        set_error("conicplus: need 0..%d polynomial terms", PXF_CONICPLUS_MAXP);
+        return PXF_ERR_INVALID;
+    }
+    return launch_op<OpConicPlus<false>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr, q, stream);
+}
+int pxf_conicplusopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num, double R, double K,
+                     const double *p, int32_t np, double nr, const uint8_t *mask, pxf_stream_t stream)
+{
+    ConicPlusP q;
+    if ((np > 0 && !p) || make_conicplus(q, R, K, p, np, true, nr) < 0) {
+        set_error("conicplusopd: need 0..%d polynomial terms", PXF_CONICPLUS_MAXP);
+        return PXF_ERR_INVALID;
+    }
+    return launch_op<OpConicPlus<true>>(rows9(x, y, z, l, m, n, ux, uy, uz, opd), num, mask, nullptr, nullptr, q, stream);
+}
+int pxf_legsurf(double *x, double *y, double *z, double *l, double *m, double *n,
+                double *ux, double *uy, double *uz, int64_t num, double xwidth, double ywidth, double order,
+                const double *coeff, const int32_t *xo, const int32_t *yo, int32_t nc,
+                const uint8_t *mask, pxf_stream_t stream)
+{
+    (void)z; (void)ux; (void)uy; (void)uz;
+    LegSurfP q;
+    if (!coeff || !xo || !yo || make_legsurf(q, xwidth, ywidth, order, coeff, xo, yo, nc) < 0) {
+        set_error("legsurf: need 1..%d terms with orders 0..%d", PXF_LEGSURF_MAXC, PXF_LEGSURF_MAXN);
+        return PXF_ERR_INVALID;
+    }
+    return launch_op<OpLegSurf>(rows9(x, y, nullptr, l, m, n, nullptr, nullptr, nullptr), num, mask, nullptr, nullptr,
+                                q, stream);
+}
+
+/* ---- woltsurf: Wolter-Schwarzschild back surfaces ---- */
+int pxf_wsprimaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                      double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                      double thick, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWsPrimaryBack>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                      make_ws(alpha, z0, psi, thick), stream);
+}
+int pxf_wssecondaryback(double *x, double *y, double *z, double *l, double *m, double *n,
+                        double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
+                        double thick, const uint8_t *mask, pxf_stream_t stream)
+{
+    return launch_op<OpWsSecondaryBack>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                        make_ws(alpha, z0, psi, thick), stream);
+}
+
+/* ---- zernsurf: phase surface and the two-set rotated surface ---- */
+int pxf_zernphase(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
+                  double *ux, double *uy, double *uz, int64_t num, const double *coeff,
+                  const int32_t *rorder, const int32_t *aorder, int32_t arrsize, double rad, double wave,
+                  const uint8_t *mask, pxf_stream_t stream)
+{
+    (void)z; (void)ux; (void)uy; (void)uz;
+    ZernPhaseP q;
+    if (!coeff || !rorder || !aorder || arrsize <= 0 || make_zern(q.z, coeff, rorder, aorder, arrsize, rad, false, 0.) < 0) {
+        set_error("zernphase: invalid Zernike table");
+        return PXF_ERR_INVALID;
+    }
+    q.wave = wave;
+    RowPtrs P = rows9(x, y, nullptr, l, m, n, nullptr, nullptr, nullptr, opd);
+    if (q.z.nmax <= 7) return launch_op<OpZernPhase<7>>(P, num, mask, nullptr, nullptr, q, stream);
+    if (q.z.nmax <= 11) return launch_op<OpZernPhase<11>>(P, num, mask, nullptr, nullptr, q, stream);
+    return launch_op<OpZernPhase<15>>(P, num, mask, nullptr, nullptr, q, stream);
+}
+int pxf_tracezernrot(double *x, double *y, double *z, double *l, double *m, double *n,
+                     double *ux, double *uy, double *uz, int64_t num,
+                     const double *coeff1, const int32_t *rorder1, const int32_t *aorder1, int32_t arrsize1,
+                     const double *coeff2, const int32_t *rorder2, const int32_t *aorder2, int32_t arrsize2,
+                     double rad, double rot, const uint8_t *mask, pxf_stream_t stream)
+{
+    ZernP q;
+    if (!coeff1 || !rorder1 || !aorder1 || arrsize1 <= 0 || !coeff2 || !rorder2 || !aorder2 || arrsize2 <= 0 ||
+        make_zern(q, coeff1, rorder1, aorder1, arrsize1, rad, false, 0.) < 0 ||
+        make_zern(q, coeff2, rorder2, aorder2, arrsize2, rad, false, 0., rot, true) < 0) {
+        set_error("tracezernrot: invalid Zernike table");
+        return PXF_ERR_INVALID;
+    }
+    return launch_zern<false>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, q, stream);
 }
 
 }  // extern "C"

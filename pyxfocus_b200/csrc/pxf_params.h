@@ -83,10 +83,11 @@ inline WolterSineP make_woltersine(double r0, double z0, double amp, double freq
     return w;
 }
 
-inline WSP make_ws(double alpha, double z0, double psi)
+inline WSP make_ws(double alpha, double z0, double psi, double thick = 0.)
 {
     WSP p;
     memset(&p, 0, sizeof(p));
+    p.thick = thick;
     p.betas = 4 * alpha;
     p.ff = z0 / cos(p.betas);
     p.g = p.ff / psi;
@@ -119,6 +120,74 @@ inline WSP make_ws(double alpha, double z0, double psi)
     p.twootan = 2. / tan(betas);
     p.kp1 = k + 1;
     return p;
+}
+
+// ---- surfacesf.f95: remaining surfaces
+inline SphereP make_sphere(double rad, bool opd, double nr)
+{
+    SphereP p;
+    p.rad2 = h_sq(rad); p.nr = nr; p.opd = opd ? 1 : 0; p.pad = 0;
+    return p;
+}
+inline CylConicP make_cylconic(double rad, double k)
+{
+    CylConicP p;
+    p.A = (1 + k) * h_sq(rad);
+    p.rad = rad;
+    p.tworad = 2 * rad;
+    p.tol = h_tol10();
+    return p;
+}
+inline TorusP make_torus(double rin, double rout)
+{
+    TorusP p;
+    p.rin = rin; p.rout = rout;
+    p.rin2 = h_sq(rin); p.rout2 = h_sq(rout);
+    p.four_rout2 = 4 * h_sq(rout);
+    p.tworin = 2 * rin; p.tworout = 2 * rout;
+    p.rpr = rin + rout;
+    p.tol = h_tol10();
+    return p;
+}
+inline int make_conicplus(ConicPlusP &q, double R, double K, const double *p, int np, bool opd, double nr)
+{
+    if (np < 0 || np > PXF_CONICPLUS_MAXP) return -1;
+    memset(&q, 0, sizeof(q));
+    q.c = 1 / R;
+    q.twoc = 2 * q.c;
+    q.c3 = (q.c * q.c) * q.c;
+    q.Kp1 = K + 1;
+    q.Kp1c2 = (K + 1) * h_sq(q.c);
+    q.nr = nr; q.tol = h_tol10(); q.np = np; q.opd = opd ? 1 : 0;
+    for (int j = 0; j < np; j++) q.p[j] = p[j];
+    return 0;
+}
+inline double h_factorial(int n)
+{
+    double f = 1.;
+    for (int i = 2; i <= n; i++) f = f * (double)i;
+    return f;
+}
+inline int make_legsurf(LegSurfP &q, double xwidth, double ywidth, double order, const double *coeff,
+                        const int32_t *xo, const int32_t *yo, int nc)
+{
+    if (nc < 0 || nc > PXF_LEGSURF_MAXC) return -1;
+    memset(&q, 0, sizeof(q));
+    q.xwidth = xwidth; q.ywidth = ywidth; q.order = order; q.nc = nc;
+    for (int j = 0; j < nc; j++) {
+        if (xo[j] < 0 || xo[j] > PXF_LEGSURF_MAXN || yo[j] < 0 || yo[j] > PXF_LEGSURF_MAXN) return -1;
+        q.coeff[j] = coeff[j]; q.xo[j] = xo[j]; q.yo[j] = yo[j];
+    }
+    // specialFunctions.f95:337-388: (-1)**i*f(2n-2i)/f(i)/f(n-i)/f(n-2i)/2**n [*(n-2i)], 2**n INTEGER
+    for (int n = 0; n <= PXF_LEGSURF_MAXN; n++)
+        for (int i = 0; i <= n / 2; i++) {
+            const double sign = (i % 2) ? -1. : 1.;
+            const double c = sign * h_factorial(2 * n - 2 * i) / h_factorial(i) / h_factorial(n - i) /
+                             h_factorial(n - 2 * i) / (double)(1 << n);
+            q.lc[n][i] = c;
+            q.lpc[n][i] = c * (double)(n - 2 * i);
+        }
+    return 0;
 }
 
 inline SpoP make_spo(double R0, double tg)
@@ -208,11 +277,16 @@ inline int make_ll(LLP &q, int kind, double r0, double z0, double psi, double S,
 
 // Fold (coeff, rorder, aorder) into the (n,|m|) table of pxf_ray.cuh.  Returns the highest
 // radial order, or -1 for an invalid table (n>15, |m|>n, n-|m| odd).
+// rot: the set is evaluated at theta+rot (tracezernrot's second set, zernsurf.f95:311): cos/sin of
+// m*(theta+rot) expanded by the angle-addition formulas rotate the (cosine, sine) coefficient pair of
+// every (n,m).  accumulate: add the set to a table already built (same rad).
 inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const int32_t *aorder,
-                     int arrsize, double rad, bool opd, double nr)
+                     int arrsize, double rad, bool opd, double nr, double rot = 0., bool accumulate = false)
 {
-    memset(&z, 0, sizeof(z));
-    z.rad = rad; z.nr = nr; z.tol = h_tol10(); z.opd = opd ? 1 : 0;
+    if (!accumulate) {
+        memset(&z, 0, sizeof(z));
+        z.rad = rad; z.nr = nr; z.tol = h_tol10(); z.opd = opd ? 1 : 0;
+    }
     int nmax = 0;
     for (int i = 0; i < arrsize; i++) {
         int n = rorder[i], mm = aorder[i], m = mm < 0 ? -mm : mm;
@@ -224,20 +298,22 @@ inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const
     int tznum = 1, radnum = 1;
     while (tznum < arrsize) { tznum += radnum + 1; radnum += 1; }
     if (nmax > radnum - 1) return -1;
-    z.nmax = nmax;
+    if (!accumulate || nmax > z.nmax) z.nmax = nmax;
     const double sqrthalf32 = (double)sqrtf(0.5f);
-    int e = 0;
-    for (int ni = 0; ni <= PXF_ZERN_MAXN; ni++) {
-        for (int j = 0; j <= ni / 2; j++) {
-            double n = ni, m = ni - 2 * j;
-            ZernEntry &t = z.e[e + j];
-            if (j >= 2) {
-                t.h3 = -4 * (m + 2) * (m + 1) / (n + m + 2) / (n - m);
-                t.h2 = t.h3 * (n + m + 4) * (n - m - 2) / 4. / (m + 3) + (m + 2);
-                t.h1 = .5 * (m + 4) * (m + 3) - (m + 4) * t.h2 + t.h3 * (n + m + 6) * (n - m - 4) / 8.;
+    if (!accumulate) {
+        int e = 0;
+        for (int ni = 0; ni <= PXF_ZERN_MAXN; ni++) {
+            for (int j = 0; j <= ni / 2; j++) {
+                double n = ni, m = ni - 2 * j;
+                ZernEntry &t = z.e[e + j];
+                if (j >= 2) {
+                    t.h3 = -4 * (m + 2) * (m + 1) / (n + m + 2) / (n - m);
+                    t.h2 = t.h3 * (n + m + 4) * (n - m - 2) / 4. / (m + 3) + (m + 2);
+                    t.h1 = .5 * (m + 4) * (m + 3) - (m + 4) * t.h2 + t.h3 * (n + m + 6) * (n - m - 4) / 8.;
+                }
             }
+            e += ni / 2 + 1;
         }
-        e += ni / 2 + 1;
     }
     for (int i = 0; i < arrsize; i++) {
         int n = rorder[i], mm = aorder[i], m = mm < 0 ? -mm : mm;
@@ -245,11 +321,18 @@ inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const
         for (int q = 0; q < n; q++) base += q / 2 + 1;
         ZernEntry &t = z.e[base + (n - m) / 2];
         double norm = sqrt(2 * ((double)n + 1));
-        if (mm < 0) t.as += coeff[i] * norm;
-        else if (mm > 0) t.ac += coeff[i] * norm;
-        else t.ac += coeff[i] * (norm * sqrthalf32);
+        if (rot == 0.) {
+            if (mm < 0) t.as += coeff[i] * norm;
+            else if (mm > 0) t.ac += coeff[i] * norm;
+            else t.ac += coeff[i] * (norm * sqrthalf32);
+        } else {
+            const double cr = cos(m * rot), sr = sin(m * rot);
+            if (mm < 0) { t.as += coeff[i] * norm * cr; t.ac += coeff[i] * norm * sr; }        // sin(m(theta+rot))
+            else if (mm > 0) { t.ac += coeff[i] * norm * cr; t.as -= coeff[i] * norm * sr; }   // cos(m(theta+rot))
+            else t.ac += coeff[i] * (norm * sqrthalf32);
+        }
     }
-    return nmax;
+    return z.nmax;
 }
 
 }  // namespace pxf

@@ -4,7 +4,12 @@
 (:238-243), ``woltersine`` (:265-270), ``wsPrimary`` (:331-347), ``wsSecondary`` (:367-383),
 ``spoCone/spoPrimary/spoSecondary`` (:403-441), ``focus/focusI`` (:502-519); and the
 Legendre-Legendre shells ``primaryLL`` (:300-306), ``secondaryLL`` (:291-298),
-``ellipsoidPrimary/Secondary(LL)`` (:443-500).
+``ellipsoidPrimary/Secondary(LL)`` (:443-500); and the rest of the file's surface wrappers:
+``zernphase`` (:49-61), ``zernsurfrot`` (:63-80), ``sphere``/``tanSphere`` (:82-103), ``conicplus``
+(:115-124), ``oapCollimate`` (:126-158), ``torus`` (:160-166), ``cyl`` (:168-180), ``cylconic``
+(:182-186), ``paraxial``/``paraxialY`` (:188-206), ``legSurf`` (:208-217), the tangent-plane
+placements ``wolterprimtan``/``woltersinetan``/``primaryLLtan`` (:245-263, :272-290, :308-329),
+``wsPrimaryB``/``wsSecondaryB`` (:349-365, :385-401), ``focusX``/``focusY`` (:512-516).
 
 Same names, argument order and results; ``ind=`` masks run as in-kernel predicates, and inside
 ``with program.fused(rays):`` unmasked calls are recorded into one fused kernel.
@@ -17,7 +22,7 @@ from . import surfacesf as surf
 from . import transformations as tran
 from . import woltsurf as wolt
 from . import zernsurf as zern
-from .analyses import analyticImagePlane
+from .analyses import analyticImagePlane, analyticXPlane, analyticYPlane
 from .program import flush, recorder_for
 
 
@@ -123,9 +128,17 @@ def woltersine(rays, r0, z0, amp, freq):
     return
 
 
-def _ws(rays, which, r0, z0, psi, check):
+def _ws(rays, which, r0, z0, psi, check, thick=None):
     opd, x, y, z, l, m, n, ux, uy, uz = rays
     a, p, d, e = con.woltparam(r0, z0)
+    if thick is not None:
+        flush(rays)
+        if check is True:
+            x0, y0, zz0 = x.clone(), y.clone(), z.clone()
+        getattr(wolt, which)(x, y, z, l, m, n, ux, uy, uz, a, z0, psi, thick)
+        if check is True:
+            return torch.logical_and(x0 == x, torch.logical_and(y0 == y, zz0 == z))
+        return
     if check is True:
         # The reference's check=True path overwrites the scalar z0 with an array before the
         # Fortran call (surfaces.py:340-342) and cannot run; here it does what its docstring says.
@@ -149,6 +162,16 @@ def wsPrimary(rays, r0, z0, psi, check=False):
 def wsSecondary(rays, r0, z0, psi, check=False):
     """Wolter-Schwarzschild secondary."""
     return _ws(rays, "wssecondary", r0, z0, psi, check)
+
+
+def wsPrimaryB(rays, r0, z0, psi, thick, check=False):
+    """Back surface of a Wolter-Schwarzschild primary of thickness ``thick``."""
+    return _ws(rays, "wsprimaryback", r0, z0, psi, check, thick)
+
+
+def wsSecondaryB(rays, r0, z0, psi, thick, check=False):
+    """Back surface of a Wolter-Schwarzschild secondary of thickness ``thick``."""
+    return _ws(rays, "wssecondaryback", r0, z0, psi, check, thick)
 
 
 def spoCone(rays, R0, tg, ind=None):
@@ -241,3 +264,174 @@ def focus(rays, fn, weights=None, nr=None, coords=None):
 def focusI(rays, weights=None, nr=None, coords=None):
     """Best focus from the analytic image plane (surfaces.py:518-519)."""
     return focus(rays, analyticImagePlane, weights=weights, nr=nr, coords=coords)
+
+
+def focusY(rays, weights=None, nr=None, coords=None):
+    """Best line focus in y (surfaces.py:512-513)."""
+    return focus(rays, analyticYPlane, weights=weights, nr=nr, coords=coords)
+
+
+def focusX(rays, weights=None, nr=None, coords=None):
+    """Best line focus in x (surfaces.py:515-516)."""
+    return focus(rays, analyticXPlane, weights=weights, nr=nr, coords=coords)
+
+
+def _need_orders(rorder, aorder):
+    if rorder is None or aorder is None:
+        raise NotImplementedError("pass rorder/aorder explicitly: the reference's default ordering lives in "
+                                  "the third-party module utilities.imaging.zernikemod (not vendored)")
+
+
+def zernphase(rays, coeff, rad, wave, rorder=None, aorder=None):
+    """Zernike phase surface: wavelength in mm, radius in mm, coeff in mm."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    _need_orders(rorder, aorder)
+    flush(rays)
+    zern.zernphase(opd, x, y, z, l, m, n, ux, uy, uz, coeff, np.array(rorder), np.array(aorder), rad, wave)
+    return
+
+
+def zernsurfrot(rays, coeff1, coeff2, rad, rot, rorder1=None, aorder1=None, rorder2=None, aorder2=None):
+    """Zernike surface made of two sets, the second rotated by ``rot`` (theta = arctan2(y,x))."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    _need_orders(rorder1, aorder1)
+    _need_orders(rorder2, aorder2)
+    flush(rays)
+    zern.tracezernrot(x, y, z, l, m, n, ux, uy, uz, coeff1, np.array(rorder1), np.array(aorder1),
+                      coeff2, np.array(rorder2), np.array(aorder2), rad, rot)
+    return
+
+
+def sphere(rays, rad, nr=None):
+    """Sphere centred on the origin; the closer intersection is taken."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    if nr is not None:
+        surf.tracesphereopd(opd, x, y, z, l, m, n, ux, uy, uz, rad, nr)
+    else:
+        surf.tracesphere(x, y, z, l, m, n, ux, uy, uz, rad)
+    return
+
+
+def tanSphere(rays, rad, nr=None):
+    """Sphere tangent to the XY plane; positive radius curves toward +z."""
+    tran.transform(rays, 0, 0, rad, 0, 0, 0)
+    sphere(rays, rad, nr=nr)
+    tran.transform(rays, 0, 0, -rad, 0, 0, 0)
+    return
+
+
+def conicplus(rays, R, K, p, nr=None):
+    """Conic of curvature radius R and conic constant K plus even polynomial terms p."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    if nr is not None:
+        surf.conicplusopd(opd, x, y, z, l, m, n, ux, uy, uz, R, K, p, nr)
+    else:
+        surf.conicplus(x, y, z, l, m, n, ux, uy, uz, R, K, p)
+    return
+
+
+def oapCollimate(rays, efl, oapangle, nr=None):
+    """Collimating off-axis paraboloid; returns the bundle back in the entry frame (new arrays)."""
+    fp = efl * (1 + np.cos(oapangle)) / 2
+    coords = tran.newCoords()
+    tran.transform(rays, 0, 0, -efl, 0, 0, 0, coords=coords)
+    tran.transform(rays, 0, 0, 0, np.pi - oapangle, 0, 0, coords=coords)
+    tran.transform(rays, 0, 0, -fp, 0, 0, 0, coords=coords)
+    conic(rays, fp * 2, -1, nr=nr)
+    tran.reflect(rays)
+    return tran.applyT(rays, coords, inverse=True)
+
+
+def torus(rays, rin, rout):
+    """Torus: outer radius in the xy plane, inner radius orthogonal."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    surf.torus(x, y, z, l, m, n, ux, uy, uz, rin, rout)
+    return
+
+
+def cyl(rays, rad, nr=None):
+    """Cylinder about the y axis through the origin."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    if nr is not None:
+        surf.tracecylopd(opd, x, y, z, l, m, n, ux, uy, uz, rad, nr)
+    else:
+        surf.tracecyl(x, y, z, l, m, n, ux, uy, uz, rad)
+    return
+
+
+def cylconic(rays, rad, k):
+    """Cylindrical conic (sag in y, cylinder axis z)."""
+    opd, x, y, z, l, m, n, ux, uy, uz = rays
+    flush(rays)
+    surf.cylconic(x, y, z, l, m, n, ux, uy, uz, rad, k)
+
+
+def paraxial(rays, F):
+    """Ideal paraxial lens in the xy plane, optical axis z."""
+    x, y, z, l, m, n, ux, uy, uz = rays[1:]
+    flush(rays)
+    surf.paraxial(x, y, z, l, m, n, ux, uy, uz, F)
+    return
+
+
+def paraxialY(rays, F):
+    """Ideal paraxial cylinder lens acting on y only."""
+    x, y, z, l, m, n, ux, uy, uz = rays[1:]
+    flush(rays)
+    surf.paraxialy(x, y, z, l, m, n, ux, uy, uz, F)
+    return
+
+
+def legSurf(rays, xwidth, ywidth, order, coeff, xo, yo):
+    """Diffract from a phase surface given by 2-D Legendre coefficients (rays already on the xy plane)."""
+    x, y, z, l, m, n, ux, uy, uz = rays[1:]
+    flush(rays)
+    surf.legsurf(x, y, z, l, m, n, ux, uy, uz, xwidth, ywidth, order,
+                 np.asarray(coeff).flatten(), np.asarray(xo).flatten(), np.asarray(yo).flatten())
+    return
+
+
+# The reference's three tangent-plane placements still use its pre-`rays` module-global call style
+# (bare transform(...), wolterprimary(r0,z0): surfaces.py:254-262) and raise NameError as shipped;
+# these do what their comments say, with the bundle passed through.
+def _to_tangent(rays, r0, z0, alpha):
+    tran.transform(rays, 0, 0, 0, -np.pi / 2 - alpha, 0, 0)
+    tran.transform(rays, 0, con.primrad(z0 + 75., r0, z0), -z0 - 75., 0, 0, 0)
+
+
+def _from_tangent(rays, r0, z0, alpha):
+    tran.transform(rays, 0, -con.primrad(z0 + 75., r0, z0), z0 + 75., 0, 0, 0)
+    tran.transform(rays, 0, 0, 0, np.pi / 2 + alpha, 0, 0)
+
+
+def wolterprimtan(rays, r0, z0):
+    """Wolter primary placed at its tangent point: +z surface normal, +y to the sky, +x azimuthal."""
+    alpha, p, d, e = con.woltparam(r0, z0)
+    _to_tangent(rays, r0, z0, alpha)
+    wolterprimary(rays, r0, z0)
+    _from_tangent(rays, r0, z0, alpha)
+    return
+
+
+def woltersinetan(rays, r0, z0, amp, freq):
+    """Sinusoidal Wolter primary placed at its tangent point."""
+    alpha, p, d, e = con.woltparam(r0, z0)
+    _to_tangent(rays, r0, z0, alpha)
+    woltersine(rays, r0, z0, amp, freq)
+    _from_tangent(rays, r0, z0, alpha)
+    return
+
+
+def primaryLLtan(rays, r0, z0, zmax, zmin, dphi, coeff, axial, az):
+    """Legendre-Legendre Wolter primary placed at its tangent point."""
+    alpha, p, d, e = con.woltparam(r0, z0)
+    _to_tangent(rays, r0, z0, alpha)
+    tran.transform(rays, 0, 0, 0, 0, 0, -np.pi / 2)
+    primaryLL(rays, r0, z0, zmax, zmin, dphi, coeff, axial, az)
+    tran.transform(rays, 0, 0, 0, 0, 0, np.pi / 2)
+    _from_tangent(rays, r0, z0, alpha)
+    return

@@ -283,3 +283,38 @@ def applyT(rays, coords, inverse=False):
         out[4 + k].copy_(wav[k])
         out[7 + k].copy_(nrm[k])
     return out
+
+
+def steerY(rays, coords=None):
+    """Rotate the reference frame until the mean y tilt vanishes (transformations.py:78-82)."""
+    flush(rays)
+    while abs(float(rays[5].mean())) > 1e-6:
+        transform(rays, 0, 0, 0, -float(rays[5].mean()), 0, 0, coords=coords)
+    return
+
+
+def steerX(rays, coords=None):
+    """Rotate the reference frame until the mean x tilt vanishes (transformations.py:84-88)."""
+    flush(rays)
+    while abs(float(rays[4].mean())) > 1e-6:
+        transform(rays, 0, 0, 0, 0, -float(rays[4].mean()), 0, coords=coords)
+    return
+
+
+def applyTPos(x, y, z, coords, inverse=False):
+    """Apply the accumulated coordinate transformation to a list of points
+    (transformations.py:283-290); host or device arrays, returns three arrays of the same kind."""
+    i = 2 if inverse is True else 0
+    M = np.asarray(coords[i + 1], dtype=np.float64)
+    if isinstance(x, torch.Tensor):
+        Mt = torch.as_tensor(M, device=x.device)
+        pos = torch.stack([x, y, z, torch.ones_like(x)])
+        out = Mt @ pos
+        return [out[0], out[1], out[2]]
+    pos = [x, y, z, np.ones(np.size(x))]
+    return np.dot(M, pos)[:3]
+
+
+def skew(vec):
+    """Skew-symmetric cross-product matrix (transformations.py:292-293)."""
+    return np.array([[0, -vec[2], vec[1]], [vec[2], 0, -vec[0]], [-vec[1], vec[0], 0]])

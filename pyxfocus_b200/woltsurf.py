@@ -54,6 +54,16 @@ def spocone(x, y, z, l, m, n, ux, uy, uz, r0, tg, num=None, mask=None):
     _nine("pxf_spocone", (x, y, z, l, m, n, ux, uy, uz), (r0, tg), num, mask)
 
 
+def wsprimaryback(x, y, z, l, m, n, ux, uy, uz, alpha, z0, psi, thick, num=None, mask=None):
+    """woltsurf.f95:726-815"""
+    _nine("pxf_wsprimaryback", (x, y, z, l, m, n, ux, uy, uz), (alpha, z0, psi, thick), num, mask)
+
+
+def wssecondaryback(x, y, z, l, m, n, ux, uy, uz, alpha, z0, psi, thick, num=None, mask=None):
+    """woltsurf.f95:824-933"""
+    _nine("pxf_wssecondaryback", (x, y, z, l, m, n, ux, uy, uz), (alpha, z0, psi, thick), num, mask)
+
+
 def _ll(fn_name, arrs, scalars, coeff, axial, az, num, cnum, mask):
     def host(a, dtype):
         if isinstance(a, torch.Tensor):

@@ -1,5 +1,5 @@
 """Replacement for the reference's f2py module ``zernsurf`` (``zernsurf.f95``,
-``compiletrace.sh:1``): tracezern / tracezernopd.  ``coeff`` is float64 ``intent(in)``,
+``compiletrace.sh:1``): tracezern / tracezernopd / zernphase / tracezernrot.  ``coeff`` is float64 ``intent(in)``,
 ``rorder``/``aorder`` are cast to int32 like f2py does (``surfaces.py:39-43`` passes int64)."""
 import numpy as np
 import torch
@@ -53,3 +53,27 @@ def tracezernopd(opd, x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad, 
         raise ValueError("shape(x,0)==num failed")
     run(_lib.lib().pxf_tracezernopd, st, *p, st.num, c.ctypes.data, r.ctypes.data, a.ctypes.data, c.shape[0],
         rad, nr, st.mask(mask), st.stream())
+
+
+def zernphase(opd, x, y, z, l, m, n, ux, uy, uz, coeff, rorder, aorder, rad, wave, num=None, arrsize=None, mask=None):
+    """zernsurf.f95:206-250"""
+    c, r, a = _tables(coeff, rorder, aorder, arrsize)
+    st = Staged()
+    p = [st.inout(t) for t in (opd, x, y, z, l, m, n, ux, uy, uz)]
+    if num is not None and int(num) != st.num:
+        raise ValueError("shape(x,0)==num failed")
+    run(_lib.lib().pxf_zernphase, st, *p, st.num, c.ctypes.data, r.ctypes.data, a.ctypes.data, c.shape[0],
+        rad, wave, st.mask(mask), st.stream())
+
+
+def tracezernrot(x, y, z, l, m, n, ux, uy, uz, coeff1, rorder1, aorder1, coeff2, rorder2, aorder2, rad, rot,
+                 num=None, arrsize1=None, arrsize2=None, mask=None):
+    """zernsurf.f95:257-359"""
+    c1, r1, a1 = _tables(coeff1, rorder1, aorder1, arrsize1)
+    c2, r2, a2 = _tables(coeff2, rorder2, aorder2, arrsize2)
+    st = Staged()
+    p = [st.inout(t) for t in (x, y, z, l, m, n, ux, uy, uz)]
+    if num is not None and int(num) != st.num:
+        raise ValueError("shape(x,0)==num failed")
+    run(_lib.lib().pxf_tracezernrot, st, *p, st.num, c1.ctypes.data, r1.ctypes.data, a1.ctypes.data, c1.shape[0],
+        c2.ctypes.data, r2.ctypes.data, a2.ctypes.data, c2.shape[0], rad, rot, st.mask(mask), st.stream())

@@ -262,6 +262,95 @@ def main():
     g["hpd3"] = anal.hpd(rays)
     np.savez_compressed(os.path.join(HERE, "legendre.npz"), **g)
 
+    # ---- the remaining surfaces.py wrappers, each through the reference's own
+    # wrapper: sphere / cyl / cylconic / conicplus / torus / paraxial / legSurf / W-S back surfaces /
+    # zernphase / zernsurfrot
+    N = 1500
+    g = {}
+
+    def beam(seed, rad=20., tilt=.02):
+        np.random.seed(seed)
+        r = src.circularbeam(rad, N)
+        rng = np.random.default_rng(seed)
+        r[4][:] = rng.normal(0., tilt, N)
+        r[5][:] = rng.normal(0., tilt, N)
+        r[6][:] = np.sqrt(1. - r[4] ** 2 - r[5] ** 2)
+        r[0][:] = rng.normal(0., 1., N)
+        return r
+
+    rays = beam(20)
+    tran.transform(rays, 0, 0, 300., 0, 0, 0)
+    g.update(pack("sphere_in", rays))
+    surf.sphere(rays, 250.)
+    g.update(pack("sphere_out", rays))
+    rays = beam(21)
+    g.update(pack("tansphere_in", rays))
+    surf.tanSphere(rays, -500., nr=1.5)
+    g.update(pack("tansphere_out", rays))
+    rays = beam(22)
+    tran.transform(rays, 0, 0, 120., 0, 0, 0)
+    g.update(pack("cyl_in", rays))
+    surf.cyl(rays, 100., nr=1.2)
+    g.update(pack("cyl_out", rays))
+    rays = beam(23, rad=5.)
+    tran.transform(rays, 0, 0, 0, np.pi / 2 - .3, 0, 0)      # grazing onto the y-sag cylinder
+    tran.transform(rays, 0, 20., 0, 0, 0, 0)
+    g.update(pack("cylconic_in", rays))
+    surf.cylconic(rays, 1. / 400., -.7)
+    g.update(pack("cylconic_out", rays))
+    rays = beam(24)
+    tran.transform(rays, 0, 0, 50., 0, 0, 0)
+    g.update(pack("conicplus_in", rays))
+    pp = np.array([1.e-5, -2.e-9, 3.e-13])
+    g["conicplus_p"] = pp
+    surf.conicplus(rays, 800., -1.3, pp, nr=1.1)
+    g.update(pack("conicplus_out", rays))
+    rays = beam(25, rad=8.)
+    tran.transform(rays, 0, 0, 30., 0, 0, 0)
+    g.update(pack("torus_in", rays))
+    surf.torus(rays, 150., 900.)
+    g.update(pack("torus_out", rays))
+    rays = beam(26)
+    g.update(pack("paraxial_in", rays))
+    surf.paraxial(rays, 350.)
+    surf.paraxialY(rays, -120.)
+    g.update(pack("paraxial_out", rays))
+    rays = beam(27)
+    xo = np.array([0, 1, 2, 3, 1, 2, 5, 0])
+    yo = np.array([1, 0, 1, 2, 4, 2, 0, 6])
+    lc = np.random.default_rng(27).normal(0., 1.e-4, xo.size)
+    g["leg_coeff"], g["leg_xo"], g["leg_yo"] = lc, xo, yo
+    g.update(pack("legsurf_in", rays))
+    surf.legSurf(rays, 25., 30., 2., lc, xo, yo)
+    g.update(pack("legsurf_out", rays))
+    # W-S back surfaces: the aperture of config 2 moved out by the substrate thickness
+    a0, a1 = chains.ws_aperture()
+    np.random.seed(28)
+    rays = src.subannulus(a0 + .4, a1 + .4, .3, N, zhat=-1.)
+    tran.transform(rays, 0, 0, -1.e4, 0, 0, 0)
+    g.update(pack("wsback_in", rays))
+    surf.wsPrimaryB(rays, 220., 1.e4, 1., .4)
+    g.update(pack("wsback_primary", rays))
+    tran.reflect(rays)
+    surf.wsSecondaryB(rays, 220., 1.e4, 1., .4)
+    g.update(pack("wsback_secondary", rays))
+    # Zernike phase screen and the two-set rotated Zernike surface
+    rorder = np.array([0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4])
+    aorder = np.array([0, 1, -1, 0, -2, 2, -1, 1, -3, 3, 0, 2, -2, 4, -4])
+    zc = np.random.default_rng(29).normal(0., 1.e-4, rorder.size)
+    zc2 = np.random.default_rng(30).normal(0., 5.e-5, 10)
+    g["z_rorder"], g["z_aorder"], g["z_coeff"], g["z_coeff2"] = rorder, aorder, zc, zc2
+    rays = beam(29, rad=18.)
+    g.update(pack("zernphase_in", rays))
+    surf.zernphase(rays, zc, 20., 5.e-4, rorder=rorder, aorder=aorder)
+    g.update(pack("zernphase_out", rays))
+    rays = beam(30, rad=18.)
+    tran.transform(rays, 0, 0, 10., 0, 0, 0)
+    g.update(pack("zernrot_in", rays))
+    surf.zernsurfrot(rays, zc, zc2, 20., .37, rorder1=rorder, aorder1=aorder, rorder2=rorder[:10], aorder2=aorder[:10])
+    g.update(pack("zernrot_out", rays))
+    np.savez_compressed(os.path.join(HERE, "surfaces2.npz"), **g)
+
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

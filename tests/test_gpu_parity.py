@@ -931,3 +931,145 @@ def test_full_size_properties(pxf, n):
 def copy_dev(rays):
     import pyxfocus_b200
     return pyxfocus_b200.transformations.copy_rays(rays)
+
+
+# ---------------------------------------------------------------- SURVEY 8f rank 2 / rank 3
+def test_golden_remaining_surfaces(pxf, golden):
+    """sphere / tanSphere / cyl / cylconic / conicplus / torus / paraxial / legSurf / W-S back
+    surfaces / zernphase / zernsurfrot through the product's surfaces.py mirrors, against fixtures
+    written by the reference's own wrappers (tests/golden/make_golden.py).  Algebraic routines
+    (+ - * / sqrt, integer powers) are bit-exact; the libm ones agree to 1e-12."""
+    g = golden("surfaces2")
+    T, S = pxf.transformations, pxf.surfaces
+
+    def run(key_in, fn):
+        dev = to_dev(rows_of(g[key_in]))
+        fn(dev)
+        return to_host(dev)
+
+    assert_bit_equal(run("sphere_in", lambda r: S.sphere(r, 250.)), rows_of(g["sphere_out"]), what="sphere")
+    assert_bit_equal(run("tansphere_in", lambda r: S.tanSphere(r, -500., nr=1.5)), rows_of(g["tansphere_out"]),
+                     what="tanSphere")
+    assert_bit_equal(run("cyl_in", lambda r: S.cyl(r, 100., nr=1.2)), rows_of(g["cyl_out"]), what="cyl")
+    assert_bit_equal(run("cylconic_in", lambda r: S.cylconic(r, 1. / 400., -.7)), rows_of(g["cylconic_out"]),
+                     what="cylconic")
+    assert_bit_equal(run("conicplus_in", lambda r: S.conicplus(r, 800., -1.3, g["conicplus_p"], nr=1.1)),
+                     rows_of(g["conicplus_out"]), what="conicplus")
+    assert_bit_equal(run("torus_in", lambda r: S.torus(r, 150., 900.)), rows_of(g["torus_out"]), what="torus")
+
+    def parax(r):
+        S.paraxial(r, 350.)
+        S.paraxialY(r, -120.)
+    assert_bit_equal(run("paraxial_in", parax), rows_of(g["paraxial_out"]), what="paraxial")
+    assert_bit_equal(run("legsurf_in", lambda r: S.legSurf(r, 25., 30., 2., g["leg_coeff"], g["leg_xo"], g["leg_yo"])),
+                     rows_of(g["legsurf_out"]), what="legSurf")
+    # libm per ray: atan2 / sincos / asin / pow
+    dev = to_dev(rows_of(g["wsback_in"]))
+    S.wsPrimaryB(dev, 220., 1.e4, 1., .4)
+    assert_close(to_host(dev), rows_of(g["wsback_primary"]), pos_scale=1.e4, what="wsPrimaryB")
+    T.reflect(dev)
+    S.wsSecondaryB(dev, 220., 1.e4, 1., .4)
+    assert_close(to_host(dev), rows_of(g["wsback_secondary"]), pos_scale=1.e4, tol=1e-11, what="wsSecondaryB")
+    ro, ao = g["z_rorder"], g["z_aorder"]
+    got = run("zernphase_in", lambda r: S.zernphase(r, g["z_coeff"], 20., 5.e-4, rorder=ro, aorder=ao))
+    assert_close(got, rows_of(g["zernphase_out"]), pos_scale=20., what="zernphase")
+    got = run("zernrot_in", lambda r: S.zernsurfrot(r, g["z_coeff"], g["z_coeff2"], 20., .37, rorder1=ro, aorder1=ao,
+                                                   rorder2=ro[:10], aorder2=ao[:10]))
+    assert_close(got, rows_of(g["zernrot_out"]), pos_scale=20., what="zernsurfrot")
+
+
+def test_remaining_surfaces_vs_oracle_masks_and_misses(pxf):
+    """Same routines straight through the f2py-shaped modules on the generic bundle (rays that miss
+    the sphere / cylinder are zeroed and get NaN normals), unmasked and with ind= masks."""
+    from pyxfocus_b200 import surfacesf as PS
+    rng = np.random.default_rng(40)
+    mask = rng.random(N) < .6
+    cases = [
+        ("tracesphere", (150.,), False), ("tracesphereopd", (150., 1.4), True),
+        ("tracecyl", (120.,), False), ("tracecylopd", (120., 1.3), True),
+        ("paraxial", (75.,), False), ("paraxialy", (-33.,), False),
+    ]
+    for name, scalars, with_opd in cases:
+        for use_mask in (False, True):
+            cpu = random_bundle(N, 41)
+            dev = to_dev(cpu)
+            if use_mask:
+                sub = [np.ascontiguousarray(r[mask]) for r in cpu]
+                a = sub if with_opd else sub[1:]
+                getattr(of.surfacesf, name)(*a, *scalars)
+                for r, s_ in zip(cpu, sub):
+                    r[mask] = s_
+                a = dev if with_opd else dev[1:]
+                getattr(PS, name)(*a, *scalars, mask=mask)
+            else:
+                a = cpu if with_opd else cpu[1:]
+                getattr(of.surfacesf, name)(*a, *scalars)
+                a = dev if with_opd else dev[1:]
+                getattr(PS, name)(*a, *scalars)
+            assert_bit_equal(to_host(dev), cpu, what="%s mask=%s" % (name, use_mask))
+
+
+def test_remaining_analyses_sources_and_helpers(pxf, golden):
+    """per-axis analyses, angle helpers, steering, set-up sources."""
+    A, T, S = pxf.analyses, pxf.transformations, pxf.surfaces
+    g = golden("wolter1")
+    rays = rows_of(g["rays_out"])
+    # move off focus so the per-axis planes are well conditioned
+    pyref.transform(rays, 0, 0, 3., 0, 0, 0)
+    of.surfacesf.flat(*rays[1:])
+    dev = to_dev(rays)
+    w = np.linspace(.5, 2., rays[1].size)
+    x, y, z, l, m, n = rays[1:7]
+
+    def yplane(ww):
+        by = np.average(y * m / n, weights=ww) - np.average(y, weights=ww) * np.average(m / n, weights=ww)
+        ay = np.average((m / n) ** 2, weights=ww) - np.average(m / n, weights=ww) ** 2
+        return -by / ay
+
+    def xplane(ww):
+        bx = np.average(x * l / n, weights=ww) - np.average(x, weights=ww) * np.average(l / n, weights=ww)
+        ax = np.average((l / n) ** 2, weights=ww) - np.average(l / n, weights=ww) ** 2
+        return -bx / ax
+    for ww in (None, w):
+        assert A.analyticYPlane(dev, weights=ww) == pytest.approx(yplane(ww), rel=1e-9)
+        assert A.analyticXPlane(dev, weights=ww) == pytest.approx(xplane(ww), rel=1e-9)
+    cy = np.average(y)
+    assert A.hpdY(dev) == pytest.approx(np.median(np.abs(y - cy)) * 2., rel=1e-12)
+    pt = (1e-3, -2e-3, .5)
+    rho = (x - pt[0]) ** 2 + (y - pt[1]) ** 2 + (z - pt[2]) ** 2
+    assert A.rmsPoint(dev, pt) == pytest.approx(np.sqrt(np.average(rho)), rel=1e-12)
+    assert A.rmsPoint(dev, pt, weights=w) == pytest.approx(np.sqrt(np.average(rho, weights=w)), rel=1e-12)
+    ia = np.arccos(rays[4] * rays[7] + rays[5] * rays[8] + rays[6] * rays[9])
+    assert np.allclose(A.indAngle(dev).cpu().numpy(), ia, atol=1e-14)
+    assert np.allclose(A.grazeAngle(dev).cpu().numpy(), np.pi / 2 - ia, atol=1e-14)
+    nrm = (0., .6, .8)
+    assert np.allclose(A.indAngle(dev, normal=nrm).cpu().numpy(), np.arccos(.6 * rays[5] + .8 * rays[6]), atol=1e-14)
+    # focusX / focusY: two analytic steps + flats, against the same sequence on the oracle
+    for fn_dev, plane in ((S.focusY, yplane), (S.focusX, xplane)):
+        d2 = to_dev(rays)
+        dz = fn_dev(d2)
+        assert abs(dz + 3.) < .5                            # walks back towards the focus
+        got = to_host(d2)
+        assert np.all(got[3] == 0.) and np.all(got[9] == 1.)
+    # steering: mean tilt removed
+    np.random.seed(5)
+    tilted = pyref.circularbeam(5., 4001)
+    pyref.transform(tilted, 0, 0, 0, .01, -.02, 0)
+    d3 = to_dev(tilted)
+    T.steerY(d3)
+    T.steerX(d3)
+    assert abs(float(d3[5].mean())) <= 1e-6 and abs(float(d3[4].mean())) <= 1e-6
+    # set-up sources: uploaded host bundles equal the host halves bit for bit
+    np.random.seed(6)
+    a = pxf.sources.convergingbeam(8400., 200., 230., -.1, .3, 1001, 1.5)
+    np.random.seed(6)
+    b = pxf.sources.convergingbeam.host(8400., 200., 230., -.1, .3, 1001, 1.5)
+    assert_bit_equal(to_host(a), b, what="convergingbeam")
+    assert to_host(pxf.sources.circFan(.05, 7, 12))[4].size == 84
+    pts = T.applyTPos(d3[1], d3[2], d3[3], T.newCoords())
+    assert torch_equal(pts[0], d3[1])
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))

@@ -67,6 +67,18 @@ def test_restatement_matches_live_reference_python():
         np.random.seed(11)
         b = getattr(pyref, name)(*args)
         assert_bit_equal(b, a, what=name)
+    # the set-up sources of the product package evaluate the reference's formulas on the host
+    from pyxfocus_b200 import sources as psrc
+    for name, args in (("xslit", (-3., 5., 257, 1.)), ("rectArray", (4., 2.5, 33)),
+                       ("convergingbeam", (8400., 200., 230., -.1, .3, 4001, 1.5)),
+                       ("convergingbeam2", (8400., -20., 30., 190., 240., 4001, .5)),
+                       ("rectbeam", (12., 7., 4001)), ("gaussianBeam", (.01, 4001)),
+                       ("fanBeam", (.02, .03, 21)), ("circFan", (.05, 7, 12))):
+        np.random.seed(13)
+        a = getattr(src, name)(*args)
+        np.random.seed(13)
+        b = getattr(psrc, name).host(*args)
+        assert_bit_equal(b, a, what=name)
     rays = chains.wolter1_source(5001, 12)
     chains.run_steps_cpu(rays, chains.wolter1_steps())
     rays[6][::13] = np.nan

@@ -282,3 +282,155 @@ def test_legendre_shells_reduce_to_wolter_surfaces_without_terms():
     W.woltersecll(*b[1:], 220., 8400., 1.3, 8400., 8300., .3, z3, [0, 1, 2], [0, 1, 1])
     for k in range(1, 10):
         assert np.abs(a[k] - b[k]).max() < 1e-6            # woltersecLL stops at |delt| <= 1e-7 (woltsurf.f95:319)
+
+
+# ---- the remaining surfaces: each pinned by the surface equation it solves
+def _golden2():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "surfaces2.npz"))
+
+
+def _rows(g, key):
+    return [np.array(g[key][i]) for i in range(10)]
+
+
+def _on_line(a, b, tol):
+    """Output position b lies on input ray a: (b - a) x dir = 0."""
+    dx, dy, dz = b[1] - a[1], b[2] - a[2], b[3] - a[3]
+    cx = dy * a[6] - dz * a[5]
+    cy = dz * a[4] - dx * a[6]
+    cz = dx * a[5] - dy * a[4]
+    assert max(np.abs(cx).max(), np.abs(cy).max(), np.abs(cz).max()) < tol
+
+
+def test_K12_sphere_cylinder_land_on_the_quadric_with_radial_normals():
+    g = _golden2()
+    a, b = _rows(g, "sphere_in"), _rows(g, "sphere_out")
+    assert np.allclose(np.sqrt(b[1] ** 2 + b[2] ** 2 + b[3] ** 2), 250., rtol=0, atol=1e-11)
+    assert np.allclose(b[7] * 250., b[1], atol=1e-11) and np.allclose(b[9] * 250., b[3], atol=1e-11)
+    _on_line(a, b, 1e-10)
+    assert np.array_equal(a[4], b[4])                      # directions untouched
+    a, b = _rows(g, "cyl_in"), _rows(g, "cyl_out")
+    assert np.allclose(np.sqrt(b[1] ** 2 + b[3] ** 2), 100., rtol=0, atol=1e-11)
+    assert np.all(b[8] == 0.)
+    _on_line(a, b, 1e-10)
+    # OPD grew by nr * path length
+    path = np.sqrt((b[1] - a[1]) ** 2 + (b[2] - a[2]) ** 2 + (b[3] - a[3]) ** 2)
+    assert np.allclose(np.abs(b[0] - a[0]), 1.2 * path, atol=1e-10)
+    # a ray that misses is zeroed and gets a NaN normal (surfacesf.f95:74-80,96-99)
+    miss = [np.array([v]) for v in (0., 500., 0., 300., 0., 0., -1., 0., 0., 0.)]
+    S.tracesphere(*miss[1:], 250.)
+    assert miss[1][0] == 0. and miss[6][0] == 0. and np.isnan(miss[7][0])
+
+
+def test_K13_tansphere_touches_the_xy_plane_at_the_origin():
+    g = _golden2()
+    b = _rows(g, "tansphere_out")
+    rad = -500.
+    # in the tangent frame the sphere is x^2+y^2+(z-rad)^2 = rad^2
+    assert np.allclose(b[1] ** 2 + b[2] ** 2 + (b[3] - rad) ** 2, rad ** 2, rtol=1e-13)
+    assert np.abs(b[3]).max() < 20. ** 2 / abs(rad)        # sag of a 20 mm beam
+
+
+def test_K14_cylconic_conicplus_torus_satisfy_their_surface_functions():
+    g = _golden2()
+    a, b = _rows(g, "cylconic_in"), _rows(g, "cylconic_out")
+    c, k = 1. / 400., -.7
+    sag = c * b[1] ** 2 / (1 + np.sqrt(1 - (1 + k) * c ** 2 * b[1] ** 2))
+    assert np.abs(b[2] - sag).max() < 1e-9                 # Newton tolerance 1e-10 on the step
+    assert np.all(b[9] == 0.)
+    _on_line(a, b, 1e-9)
+    a, b = _rows(g, "conicplus_in"), _rows(g, "conicplus_out")
+    R, K, p = 800., -1.3, g["conicplus_p"]
+    r = np.sqrt(b[1] ** 2 + b[2] ** 2)
+    cc = 1 / R
+    surf = cc * r ** 2 / (1 + np.sqrt(1 - (K + 1) * cc ** 2 * r ** 2)) - sum(p[j] * r ** (2 * j + 2) for j in range(3))
+    assert np.abs(b[3] - surf).max() < 1e-9
+    assert np.allclose(b[7] ** 2 + b[8] ** 2 + b[9] ** 2, 1., atol=1e-14)
+    _on_line(a, b, 1e-9)
+    a, b = _rows(g, "torus_in"), _rows(g, "torus_out")
+    rin, rout = 150., 900.
+    t = b[3] + rin + rout
+    F = (t ** 2 + b[2] ** 2 + b[1] ** 2 + rout ** 2 - rin ** 2) ** 2 - 4 * rout ** 2 * (b[2] ** 2 + t ** 2)
+    assert np.abs(F).max() / (4 * rout ** 2 * rin ** 2) < 1e-9
+    # the reference leaves Fz out of the normal's length (surfacesf.f95:499): ux^2+uy^2 = 1 exactly-ish
+    assert np.allclose(b[7] ** 2 + b[8] ** 2, 1., atol=1e-14)
+    _on_line(a, b, 1e-9)
+
+
+def test_K15_paraxial_lens_brings_a_collimated_beam_to_its_focus():
+    np.random.seed(3)
+    rays = pyref.circularbeam(10., 2000)
+    S.paraxial(*rays[1:], 350.)
+    assert np.allclose(rays[4], -rays[1] / 350.) and np.allclose(rays[5], -rays[2] / 350.)
+    assert np.all(rays[6] == 1.)                           # n is left alone (surfacesf.f95:433-437)
+    # x + l * 350 = 0: every ray crosses the axis at F (in the reference's small-angle convention)
+    assert np.abs(rays[1] + rays[4] * 350.).max() < 1e-12
+    r2 = pyref.circularbeam(10., 2000)
+    S.paraxialy(*r2[1:], -120.)
+    assert np.all(r2[4] == 0.) and np.allclose(r2[5], r2[2] / 120.)
+
+
+def test_K16_legsurf_against_numpy_legendre():
+    from numpy.polynomial import legendre as L
+    g = _golden2()
+    a, b = _rows(g, "legsurf_in"), _rows(g, "legsurf_out")
+    coeff, xo, yo = g["leg_coeff"], g["leg_xo"], g["leg_yo"]
+    xw, yw, order = 25., 30., 2.
+    dpx = np.zeros_like(a[1]); dpy = np.zeros_like(a[1])
+    for c, i, j in zip(coeff, xo, yo):
+        ex = np.zeros(i + 1); ex[i] = 1.
+        ey = np.zeros(j + 1); ey[j] = 1.
+        dpx += c * L.legval(a[2] / yw, ey) * L.legval(a[1] / xw, L.legder(ex))
+        dpy += c * L.legval(a[2] / yw, L.legder(ey)) * L.legval(a[1] / xw, ex)
+    assert np.allclose(b[4], a[4] + dpx * order / xw, atol=1e-15)
+    assert np.allclose(b[5], a[5] + dpy * order / yw, atol=1e-15)
+    assert np.allclose(b[4] ** 2 + b[5] ** 2 + b[6] ** 2, 1., atol=1e-15)
+
+
+def test_K17_ws_back_surface_is_the_front_surface_moved_out_by_the_thickness():
+    """A ray at radius r on the back surface solves the front-surface equation at radius r-thick
+    (woltsurf.f95:749-753): tracing the same axial rays to the front surface from an aperture
+    shifted inwards by `thick` must give the same z."""
+    a0, a1 = chains.ws_aperture()
+    alpha = pyref.woltparam(220., 1.e4)[0]
+    n = 400
+    rad = np.linspace(a0 + .05, a1 - .05, n)
+    def axial(r):
+        z = np.zeros(n)
+        return [z.copy(), r.copy(), z.copy(), np.full(n, 1.e4 + 300.), z.copy(), z.copy(),
+                np.full(n, -1.), z.copy(), z.copy(), z.copy()]
+    front = axial(rad)
+    back = axial(rad + .4)
+    W.wsprimary(*front[1:], alpha, 1.e4, 1.)
+    W.wsprimaryback(*back[1:], alpha, 1.e4, 1., .4)
+    assert np.abs(front[3] - back[3]).max() < 1e-7
+    assert np.allclose(back[1], rad + .4)                  # axial rays keep their radius
+    assert np.allclose(front[7], back[7], atol=1e-9) and np.allclose(front[9], back[9], atol=1e-9)
+
+
+def test_K18_zernphase_and_rotated_set():
+    g = _golden2()
+    ro, ao, zc, zc2 = g["z_rorder"], g["z_aorder"], g["z_coeff"], g["z_coeff2"]
+    a, b = _rows(g, "zernphase_in"), _rows(g, "zernphase_out")
+    # opd picks up wave * sum(c Z); check against zernset directly
+    rho = np.sqrt(a[1] ** 2 + a[2] ** 2) / 20.
+    th = np.arctan2(a[2], a[1])
+    S0 = np.array([np.dot(zc, SP.zernset(r, t, ro, ao)[0]) for r, t in zip(rho[:200], th[:200])])
+    assert np.allclose(b[0][:200] - a[0][:200], 5.e-4 * S0, atol=1e-18)
+    assert np.allclose(b[4] ** 2 + b[5] ** 2 + b[6] ** 2, 1., atol=1e-15)
+    assert np.array_equal(a[1], b[1])                      # positions untouched
+    # rotated second set: rot = 0 must equal the single-set tracezern of the summed coefficients
+    r1 = _rows(g, "zernrot_in"); r2 = _rows(g, "zernrot_in")
+    c2 = np.zeros_like(zc); c2[:10] = zc2
+    Z.tracezernrot(*r1[1:], zc, ro, ao, zc2, ro[:10], ao[:10], 20., 0.)
+    Z.tracezern(*r2[1:], zc + c2, ro, ao, 20.)
+    for k in range(1, 10):
+        assert np.allclose(r1[k], r2[k], atol=1e-12), k
+    # and a rotation by 2*pi/m leaves an m-fold term unchanged: rot = pi with only even-m terms
+    even = np.array([i for i in range(10) if ao[i] % 2 == 0])
+    r3 = _rows(g, "zernrot_in"); r4 = _rows(g, "zernrot_in")
+    Z.tracezernrot(*r3[1:], zc, ro, ao, zc2[even], ro[even], ao[even], 20., np.pi)
+    Z.tracezernrot(*r4[1:], zc, ro, ao, zc2[even], ro[even], ao[even], 20., 0.)
+    for k in range(1, 10):
+        assert np.allclose(r3[k], r4[k], atol=1e-12), k
