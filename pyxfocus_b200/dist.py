@@ -10,6 +10,12 @@ Tracing needs no communication (rays are independent).  Only the reductions do
   Five passes resolve the full 64-bit pattern, i.e. the exact two middle order statistics
   of the GLOBAL bundle (np.median semantics).
 
+* weighted HPD (analyses.py:88-97 with weights): every rank sorts its own radii (the library's
+  radix sort) and prefix-sums its weights in that order; the global weighted quantile is then a
+  bisection over the 64-bit key space -- per step each rank looks up "my weight at or below this
+  key" in its sorted shard and the scalar is all-reduced -- i.e. a merge of the per-rank sorted
+  runs that never moves a ray (63 latency-bound all-reduces of one double per quantile).
+
 Collectives go through ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the
 CPU tests of the host logic).  With ``group=None`` and no initialised process group the
 functions degrade to the single-GPU result (world size 1).
@@ -245,13 +251,15 @@ def bracket_median_pair(sel, total, min_shard, group=None):
     return sel.finish(total)
 
 
-def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None):
-    """Unweighted HPD (2 x median radius about the global centroid) of a sharded bundle;
+def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None, weights=None):
+    """``weights`` given: the weighted statistic (``hpd_weighted``).  Otherwise: unweighted HPD (2 x median radius about the global centroid) of a sharded bundle;
     exact, identical on every rank.  ``sums``: this shard's centroid sums from
     ``Program.run(..., sums=...)`` (saves the local pass that computes them).  ``total`` /
     ``min_shard``: global ray count and smallest shard size when the caller knows them (e.g.
     equal shards) -- then nothing is read back to the host before the final result, so the
     whole analysis is enqueued behind the trace kernel without a sync."""
+    if weights is not None:
+        return hpd_weighted(rays, weights, group)
     flush(rays)
     x, y = rays[1:3]
     dev = x.device
@@ -271,3 +279,90 @@ def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=N
         if res is None or not res[3]:
             res = select_median_pair(sel, total, group)
     return res[:3] if return_stats else res[0]
+
+
+# ------------------------------------------------------------------ weighted HPD
+class CudaWeighted:
+    """Local half of the weighted quantile: radii about the global centroid, sorted, with the prefix
+    sums of the weights in sorted order (libpxf kernels: pxf_rho, pxf_argsort, pxf_cumsum_gather).
+    The gloo tests replace it with a CPU stand-in of the same interface."""
+
+    def __init__(self, rays, weights, cx, cy):
+        from . import analyses
+        x, y = rays[1:3]
+        dev = x.device
+        L = _lib.lib()
+        num = x.shape[0]
+        w = torch.as_tensor(weights, dtype=torch.float64, device=dev).contiguous()
+        r = torch.empty_like(x)
+        self.cum = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            if num > 0:
+                _lib.check(L.pxf_rho(x.data_ptr(), y.data_ptr(), num, cx, cy, r.data_ptr(), stream_ptr(dev)))
+                rs, idx = analyses.argsort(r)
+                scratch = torch.empty(int(L.pxf_scan_scratch_bytes(num)), dtype=torch.uint8, device=dev)
+                _lib.check(L.pxf_cumsum_gather(w.data_ptr(), idx.data_ptr(), num, self.cum.data_ptr(),
+                                               scratch.data_ptr(), stream_ptr(dev)))
+            else:
+                rs = r
+        self.keys = rs.view(torch.int64)          # radii are >= 0: the bit pattern orders like the value
+        self.device = dev
+
+
+def _weight_at_or_below(loc, key, strict=False):
+    """Sum of this shard's weights whose radius key is <= key (< key when strict); 0-d tensor."""
+    n = loc.keys.shape[0]
+    if n == 0:
+        return torch.zeros((), dtype=torch.float64, device=loc.device)
+    cnt = torch.searchsorted(loc.keys, key.reshape(1), right=not strict)[0]
+    val = loc.cum[torch.clamp(cnt - 1, min=0)]
+    return torch.where(cnt > 0, val, torch.zeros_like(val))
+
+
+def _largest_key_below(loc, key):
+    """Largest radius key of this shard that is < key, or -1."""
+    n = loc.keys.shape[0]
+    if n == 0:
+        return torch.full((), -1, dtype=torch.int64, device=loc.device)
+    cnt = torch.searchsorted(loc.keys, key.reshape(1), right=False)[0]
+    val = loc.keys[torch.clamp(cnt - 1, min=0)]
+    return torch.where(cnt > 0, val, torch.full_like(val, -1))
+
+
+def weighted_quantile_radius(loc, q, total_weight, group=None):
+    """Radius r[argmin |cdf - q|] of the GLOBAL sorted (radius, weight) sequence, cdf = cumulative
+    weight / total (first minimum, as numpy's argmin): the smallest key whose global cumulative
+    weight reaches q*W, or its predecessor when that one is at least as close.  Everything stays on
+    the device; identical on every rank."""
+    dev = loc.device
+    lo = torch.zeros((), dtype=torch.int64, device=dev)                         # invariant: answer in [lo, hi]
+    hi = torch.full((), 0x7ff0000000000000, dtype=torch.int64, device=dev)      # +Inf pattern
+    for _ in range(63):
+        mid = lo + (hi - lo) // 2
+        c = all_reduce_sum(_weight_at_or_below(loc, mid), group) / total_weight
+        ge = c >= q
+        hi = torch.where(ge, mid, hi)
+        lo = torch.where(ge, lo, mid + 1)
+    k_hi = hi
+    c_hi = all_reduce_sum(_weight_at_or_below(loc, k_hi), group) / total_weight
+    k_lo = _largest_key_below(loc, k_hi)
+    if _world(group) > 1:
+        td.all_reduce(k_lo, op=td.ReduceOp.MAX, group=group)
+    c_lo = all_reduce_sum(_weight_at_or_below(loc, k_hi, strict=True), group) / total_weight
+    take_lo = (k_lo >= 0) & (torch.abs(c_lo - q) <= torch.abs(c_hi - q))
+    key = torch.where(take_lo, k_lo, k_hi)
+    return key.view(torch.float64)
+
+
+def hpd_weighted(rays, weights, group=None, local_cls=CudaWeighted):
+    """Weighted HPD of a sharded bundle: r[argmin|cdf-.75|] - r[argmin|cdf-.25|] about the global
+    weighted centroid (analyses.py:88-97), identical on every rank."""
+    flush(rays)
+    cx, cy = centroid(rays, weights, group)
+    loc = local_cls(rays, weights, cx, cy)
+    n = loc.keys.shape[0]
+    wl = loc.cum[n - 1].clone() if n > 0 else torch.zeros((), dtype=torch.float64, device=loc.device)
+    W = all_reduce_sum(wl, group)
+    r75 = weighted_quantile_radius(loc, .75, W, group)
+    r25 = weighted_quantile_radius(loc, .25, W, group)
+    return float(r75 - r25)

@@ -207,3 +207,76 @@ def test_sharded_exact_median_over_gloo(world, n, with_nan):
         assert res0[0] == 2. * np.median(r)
         srt = np.sort(r)
         assert res0[1] == srt[(n - 1) // 2] and res0[2] == srt[n // 2]
+
+
+# ---------------------------------------------------------------- weighted HPD
+class NumpyWeighted:
+    """CPU stand-in for dist.CudaWeighted: sorted radius keys + prefix sums of the weights."""
+
+    def __init__(self, x, y, w, cx, cy):
+        r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+        idx = np.argsort(r, kind="stable")
+        self.keys = torch.from_numpy(np.ascontiguousarray(r[idx]).view(np.int64).copy())
+        self.cum = torch.from_numpy(np.cumsum(w[idx]))
+        self.device = torch.device("cpu")
+
+
+def _weighted_bundle(n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(3., 1e-3, n)
+    y = rng.standard_cauchy(n) * 1e-3 - 1.
+    w = rng.uniform(.2, 3., n)
+    x[: n // 50] = x[0]
+    y[: n // 50] = y[0]                                  # ties across shards
+    return x, y, w
+
+
+def _weighted_worker(rank, world, port, n, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from pyxfocus_b200 import dist
+    x, y, w = _weighted_bundle(n, seed)
+    lo, hi = dist.shard_range(n, rank, world)
+    if rank == world - 1 and world == 3:
+        lo = hi                                          # an EMPTY shard must not break the merge
+    xs, ys, ws = x[lo:hi], y[lo:hi], w[lo:hi]
+    s = torch.tensor([ws.sum(), (ws * xs).sum(), (ws * ys).sum()], dtype=torch.float64)
+    dist.all_reduce_sum(s)
+    cx, cy = float(s[1] / s[0]), float(s[2] / s[0])
+    loc = NumpyWeighted(xs, ys, ws, cx, cy)
+    wl = loc.cum[-1].clone() if loc.cum.shape[0] else torch.zeros((), dtype=torch.float64)
+    W = dist.all_reduce_sum(wl)
+    r75 = float(dist.weighted_quantile_radius(loc, .75, W))
+    r25 = float(dist.weighted_quantile_radius(loc, .25, W))
+    q.put((rank, r75, r25, cx, cy, lo, hi))
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 40_001), (3, 9_000)])
+def test_sharded_weighted_hpd_over_gloo(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_weighted_worker, args=(r, world, port, n, 321, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, w = _weighted_bundle(n, 321)
+    covered = np.zeros(n, dtype=bool)
+    for rank, r75, r25, cx, cy, lo, hi in out:
+        covered[lo:hi] = True
+        assert (r75, r25) == (out[0][1], out[0][2]), "ranks disagree"
+    x, y, w = x[covered], y[covered], w[covered]        # (world 3 drops the last shard on purpose)
+    cx, cy = out[0][3], out[0][4]
+    r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+    ind = np.argsort(r)
+    cdf = np.cumsum(w[ind])
+    cdf = cdf / cdf.max()
+    want75 = r[ind][np.argmin(np.abs(cdf - .75))]
+    want25 = r[ind][np.argmin(np.abs(cdf - .25))]
+    assert out[0][1] == want75 and out[0][2] == want25   # analyses.py:88-97, bit for bit
