@@ -383,11 +383,14 @@ def run_e2e(args, pxf, pdist, src, prog, n, world, dev, barrier):
         td.all_reduce(tt, op=td.ReduceOp.MAX)
         t = float(tt[0])
     return {"value": n * world * steps / t, "unit": "rays/s", "steps": steps,
-            "h2d_bytes_per_step": 48 * n * world, "d2h_bytes_per_step": 40 * n * world + 8,
-            "host_filled_bytes_per_step": 32 * n * world,
+            # x, y uploaded; z, l, m, n of the subannulus source are bitwise constant and are found so by
+            # the host-side chunk scan (filled on the device instead of uploaded)
+            "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": 40 * n * world + 8,
+            "host_scanned_bytes_per_step": 32 * n * world, "host_filled_bytes_per_step": 24 * n * world,
             "path": "pxf_host_trace_program: pinned host rows -> chunked H2D / fused kernel / D2H on 3 streams "
-                    "-> all nine rows mutated in place (x,y,l,m,n downloaded; z=0 and the normal (0,0,1) left "
-                    "by flat are filled by host threads instead of crossing PCIe) + HPD", "hpd": hp}
+                    "-> all nine rows mutated in place (constant input chunks are detected by a host scan and "
+                    "not uploaded; x,y,l,m,n downloaded; z=0 and the normal (0,0,1) left by flat are filled by "
+                    "host threads instead of crossing PCIe) + HPD", "hpd": hp}
 
 
 if __name__ == "__main__":

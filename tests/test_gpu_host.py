@@ -142,3 +142,28 @@ def test_fused_centroid_sums(pxf):
     s = sums.cpu().numpy()
     assert s[0] == int(alive.sum())
     assert s[1] == pytest.approx(float(dev[1][alive].sum()), rel=1e-11, abs=1e-9)
+
+
+def test_host_trace_constant_input_chunks_are_not_uploaded_but_still_exact(pxf, monkeypatch):
+    """Input rows are scanned chunk by chunk; bitwise-constant chunks are filled on the device
+    instead of uploaded.  Rows that are constant in some chunks only, constant -0 / NaN rows and
+    the fully varying case must all give the bits of the plain path (PXF_HOST_NO_SCAN=1 is read
+    once per process, so the comparison is against the device-resident program)."""
+    n = 5_000_001                                   # three 2^21-ray chunks
+    cpu = chains.wolter1_source(n, seed=54)         # z, l, m, n constant in every chunk
+    # make l constant in the first chunk only, m = -0 everywhere, and one NaN ray in x
+    cpu[4][(1 << 21):] += np.random.default_rng(1).normal(0., 1e-7, n - (1 << 21))
+    cpu[5][:] = -0.
+    cpu[6][:] = -np.sqrt(1. - cpu[4] ** 2)
+    cpu[1][1234567] = np.nan
+    host = copy(cpu)
+    dev = to_dev(cpu)
+    prog = steps_to_program(chains.wolter1_steps())
+    pxf.host.trace(host, prog, write_back=True)
+    prog.run(dev)
+    want = to_host(dev)
+    for k in range(1, 10):
+        a, b = host[k], want[k]
+        na, nb = np.isnan(a), np.isnan(b)
+        assert np.array_equal(na, nb)
+        assert np.array_equal(a.view(np.uint64)[~na], b.view(np.uint64)[~nb]), k
