@@ -366,6 +366,32 @@ int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t
                              int64_t cap_total, pxf_stream_t stream);
 int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_dev, int32_t shift,
                          int32_t bits, void *state, pxf_stream_t stream);
+/* Building blocks of the fused bracketed select for callers that put a collective between them
+ * (multi-GPU): sample -> all-gather -> pxf_small_select(npass 3) = bracket -> pxf_bracket_collect ->
+ * all-reduce counters -> pxf_cand_hist -> all-reduce the bins -> pxf_cand_scan -> pxf_cand_gather ->
+ * all-gather -> pxf_small_select(npass 5, fastsel) = the exact pair.
+ * pxf_small_select: ONE-CTA radix select of order statistics ra, rb of nseg x seg_cap keys, the first
+ * seg_counts[s] of each segment valid (NULL: all); npass 3 returns a bracket rounded outwards over the
+ * 25 unresolved bits, npass 5 the exact values; with `fastsel` the ranks and the valid/NaN verdict come
+ * from pxf_cand_scan.  out_dev = {a+b, a, b, valid}. */
+/* pack_out[4 + 2*nsamp] = {count, sum x, sum y, count | x, y of nsamp strided rays}: one rank's share of
+ * the single all-gather that replaces "all-reduce the centroid sums" + "all-gather the radius sample";
+ * pxf_sample_radii turns the gathered packs into the global sums, the centroid and the sample radii. */
+int pxf_sample_pack(const double *x, const double *y, int64_t num, const double *sums_dev, int32_t nsamp,
+                    double *pack_out, pxf_stream_t stream);
+int pxf_sample_radii(const double *gathered, int32_t world, int32_t nsamp, double *sums_out, double *cxy_out,
+                     double *keys_out, pxf_stream_t stream);
+size_t pxf_fastsel_bytes(void);
+int32_t pxf_fast_nbins(void);
+int32_t pxf_fast_fincap(void);
+int pxf_small_select(const double *keys, const int32_t *seg_counts, int32_t nseg, int32_t seg_cap, int64_t ra,
+                     int64_t rb, int32_t npass, const void *fastsel, double *out_dev, pxf_stream_t stream);
+int pxf_cand_hist(const double *cand, int64_t cap, const uint64_t *count_dev, const double *lohi_dev,
+                  uint32_t *fhist, pxf_stream_t stream);
+int pxf_cand_scan(const uint32_t *fhist, const uint64_t *counters, int64_t k0, int64_t k1, void *fastsel,
+                  pxf_stream_t stream);
+int pxf_cand_gather(const double *cand, int64_t cap, const uint64_t *count_dev, const double *lohi_dev,
+                    void *fastsel, double *fin, int32_t *fin_count, pxf_stream_t stream);
 /* Unweighted HPD entirely on the device.  out_dev: double[4] = {2*median, lower middle, upper
  * middle, valid}.  mode 0 = automatic (bracketed select for bundles >= pxf_bracket_min_num(),
  * small selects fused into single kernels), 1 = force the five-pass select, 2 = bracketed select

@@ -111,6 +111,15 @@ SIGNATURES = {
     "pxf_bracket_collect": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_select_begin_bracket": (_c.c_int, [_vp, _i64, _i64, _vp, _i64, _st]),
     "pxf_select_hist_keys": (_c.c_int, [_dp, _i64, _vp, _i32, _i32, _vp, _st]),
+    "pxf_sample_pack": (_c.c_int, [_dp, _dp, _i64, _dp, _i32, _dp, _st]),
+    "pxf_sample_radii": (_c.c_int, [_dp, _i32, _i32, _dp, _dp, _dp, _st]),
+    "pxf_fastsel_bytes": (_sz, []),
+    "pxf_fast_nbins": (_i32, []),
+    "pxf_fast_fincap": (_i32, []),
+    "pxf_small_select": (_c.c_int, [_dp, _vp, _i32, _i32, _i64, _i64, _i32, _vp, _dp, _st]),
+    "pxf_cand_hist": (_c.c_int, [_dp, _i64, _vp, _dp, _vp, _st]),
+    "pxf_cand_scan": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _st]),
+    "pxf_cand_gather": (_c.c_int, [_dp, _i64, _vp, _dp, _vp, _dp, _vp, _st]),
     "pxf_hpd_workspace_bytes": (_sz, [_i64]),
     "pxf_hpd_unweighted_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _vp, _i32, _st]),
     "pxf_hpd_from_sums_dev": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _vp, _i32, _st]),

@@ -542,28 +542,61 @@ PXF_DEV void block_find_bin(const unsigned int *h, int nbins, unsigned long long
     __syncthreads();
 }
 
+// ONE-CTA radix select of two order statistics of a small key set (<= ~1e6 keys, L2 resident):
+// npass = 3 resolves 39 bits and rounds the pair outwards over the other 25 (a bracket), npass = 5
+// resolves all 64 (the exact values).  The keys are nseg segments of seg_cap doubles of which the
+// first seg_counts[s] are valid (seg_counts == NULL: all of them) -- the layout an all-gather of
+// per-rank buffers produces.  ranks: (ra, rb), or taken from a FastSel (r0-base_a, r1-base_a) when
+// `fs` is given, in which case its valid / is_nan flags and any overflowed segment decide the
+// outcome first.  out = {a+b, a, b, valid}.  `hk_*` (nullable): buffers of the single-GPU pipeline
+// that this launch also resets.
 __global__ void __launch_bounds__(1024)
-k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long ra, unsigned long long rb,
-                double *__restrict__ lohi, unsigned long long *__restrict__ counters, FastSel *__restrict__ fs,
-                unsigned int *__restrict__ fhist)
+k_small_select(const double *__restrict__ keys, const int *__restrict__ seg_counts, int nseg, int seg_cap,
+               unsigned long long ra, unsigned long long rb, int npass, const FastSel *__restrict__ fs,
+               double *__restrict__ out, unsigned long long *__restrict__ hk_counters,
+               FastSel *__restrict__ hk_fs, unsigned int *__restrict__ hk_fhist)
 {
     extern __shared__ unsigned int sh[];                // [2][8192]
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long found[2][2];
     __shared__ unsigned long long prefix[2], rank[2];
-    __shared__ int np;
+    __shared__ int np, verdict;                         // verdict: 0 run, 1 invalid, 2 NaN
     const int NB = 8192;
-    // housekeeping for the kernels that follow
-    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) fhist[t] = 0u;
-    if (threadIdx.x < 8) counters[threadIdx.x] = 0ull;
+    if (hk_fhist) for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) hk_fhist[t] = 0u;
+    if (hk_counters && threadIdx.x < 8) hk_counters[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) {
-        fs->ticket_hist = 0; fs->ticket_fin = 0; fs->nfin = 0; fs->valid = 0; fs->is_nan = 0;
+        if (hk_fs) { hk_fs->ticket_hist = 0; hk_fs->ticket_fin = 0; hk_fs->nfin = 0; hk_fs->valid = 0; hk_fs->is_nan = 0; }
+        int v = 0;
+        if (fs) {
+            ra = fs->r0 - fs->base_a; rb = fs->r1 - fs->base_a;
+            if (fs->is_nan) v = 2;
+            else if (!fs->valid) v = 1;
+        }
+        unsigned long long have = 0;
+        for (int sgm = 0; sgm < nseg; sgm++) {
+            const int c = seg_counts ? seg_counts[sgm] : seg_cap;
+            if (c > seg_cap && v == 0) v = 1;            // a rank's buffer overflowed
+            have += (unsigned long long)(c < seg_cap ? c : seg_cap);
+        }
+        if (v == 0 && rb >= have) v = 1;
+        verdict = v;
         prefix[0] = prefix[1] = 0ull; rank[0] = ra; rank[1] = rb; np = 1;
     }
     __syncthreads();
-    const int shifts[3] = {51, 38, 25};
-    for (int pass = 0; pass < 3; pass++) {
-        const int shift = shifts[pass], hi = shift + 13;
+    if (verdict != 0) {
+        if (threadIdx.x == 0) {
+            const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+            const bool isn = verdict == 2;
+            out[0] = isn ? nanv : 0.; out[1] = isn ? nanv : 0.; out[2] = isn ? nanv : 0.; out[3] = isn ? 1. : 0.;
+        }
+        return;
+    }
+    const int total = nseg * seg_cap;
+    const int shifts[5] = {51, 38, 25, 12, 0};
+    const int nbits[5] = {13, 13, 13, 13, 12};
+    for (int pass = 0; pass < npass; pass++) {
+        const int shift = shifts[pass], bits = nbits[pass], hi = shift + bits;
+        const int nb = 1 << bits;
         const int npl = np;
         const unsigned long long p0 = prefix[0], p1 = prefix[1];
         for (int t = threadIdx.x; t < 2 * NB; t += blockDim.x) sh[t] = 0u;
@@ -571,12 +604,14 @@ k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long r
         __syncthreads();
         // warp-aggregated (the first pass sees almost every key in the same one or two bins); loads
         // issued eight at a time so the single CTA is not bound by one L2 latency per key
-        for (int j0 = 0; j0 < nsamp; j0 += 8 * blockDim.x) {
+        for (int j0 = 0; j0 < total; j0 += 8 * blockDim.x) {
             double rv[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int j = j0 + u * blockDim.x + threadIdx.x;
-                rv[u] = j < nsamp ? keys[j] : __longlong_as_double(0x7ff8000000000000ll);
+                bool ok = j < total;
+                if (ok && seg_counts) ok = (j % seg_cap) < seg_counts[j / seg_cap];
+                rv[u] = ok ? keys[j] : __longlong_as_double(0x7ff8000000000000ll);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
@@ -585,7 +620,7 @@ k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long r
                 if (r == r) {
                     const unsigned long long k = key_of(r);
                     const unsigned long long top = hi >= 64 ? 0ull : (k >> hi);
-                    const int d = (int)((k >> shift) & (unsigned long long)(NB - 1));
+                    const int d = (int)((k >> shift) & (unsigned long long)(nb - 1));
                     if (top == p0) bin = d;
                     else if (npl == 2 && top == p1) bin = NB + d;
                 }
@@ -595,11 +630,11 @@ k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long r
         }
         __syncthreads();
         for (int j = 0; j < 2; j++)
-            block_find_bin(sh + ((npl == 2) ? j : 0) * NB, NB, rank[j], wsum, found[j]);
+            block_find_bin(sh + ((npl == 2) ? j : 0) * NB, nb, rank[j], wsum, found[j]);
         if (threadIdx.x == 0) {
             const unsigned long long pa = prefix[0], pb = (npl == 2) ? prefix[1] : prefix[0];
-            prefix[0] = (pa << 13) | found[0][0];
-            prefix[1] = (pb << 13) | found[1][0];
+            prefix[0] = (pa << bits) | found[0][0];
+            prefix[1] = (pb << bits) | found[1][0];
             rank[0] -= found[0][1];
             rank[1] -= found[1][1];
             np = (prefix[0] == prefix[1]) ? 1 : 2;
@@ -607,9 +642,13 @@ k_bracket_small(const double *__restrict__ keys, int nsamp, unsigned long long r
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        // 39 resolved bits; round the bracket outwards over the 25 unresolved ones
-        lohi[1] = __longlong_as_double((long long)(prefix[0] << 25));
-        lohi[2] = __longlong_as_double((long long)((prefix[1] << 25) | ((1ull << 25) - 1ull)));
+        // unresolved low bits (25 after three passes, none after five): round the pair outwards
+        const int rem = npass >= 5 ? 0 : 64 - 13 * npass;
+        const unsigned long long ones = rem ? ((1ull << rem) - 1ull) : 0ull;
+        const double a = __longlong_as_double((long long)(rem ? (prefix[0] << rem) : prefix[0]));
+        const double b = __longlong_as_double((long long)(rem ? ((prefix[1] << rem) | ones) : prefix[1]));
+        out[0] = ((a + b) / 2.) * 2.;
+        out[1] = a; out[2] = b; out[3] = 1.;
     }
 }
 
@@ -625,21 +664,45 @@ PXF_DEV double cand_scale(double lo, double hi)
     return w > 0. ? (double)FAST_NBINS / w : 0.;
 }
 
+// validity of the bracket + the bin(s) holding the two middle ranks; h = the (global) histogram in
+// shared memory.  All threads of the CTA call.  cap_total == ~0: the summed capacities travel in
+// counters[4] (multi-GPU).
+PXF_DEV void cand_scan_block(const unsigned int *h, const unsigned long long *__restrict__ counters,
+                             unsigned long long cap_total, unsigned long long k0, unsigned long long k1,
+                             FastSel *__restrict__ fs, unsigned long long *wsum, unsigned long long (*found)[2])
+{
+    const unsigned long long below = counters[0], ncand = counters[1], nnan = counters[2];
+    if (cap_total == ~0ull) cap_total = counters[4];
+    const bool ok = nnan == 0 && counters[3] == 0 && ncand <= cap_total && k0 >= below && k1 < below + ncand;
+    if (threadIdx.x < 2) { found[threadIdx.x][0] = 0ull; found[threadIdx.x][1] = 0ull; }
+    __syncthreads();
+    const unsigned long long r0 = ok ? k0 - below : 0ull, r1 = ok ? k1 - below : 0ull;
+    block_find_bin(h, FAST_NBINS, r0, wsum, found[0]);
+    block_find_bin(h, FAST_NBINS, r1, wsum, found[1]);
+    if (threadIdx.x == 0) {
+        fs->bin_a = (unsigned int)found[0][0];
+        fs->bin_b = (unsigned int)found[1][0];
+        fs->base_a = found[0][1];
+        fs->r0 = r0; fs->r1 = r1;
+        fs->valid = (ok || nnan) ? 1 : 0;
+        fs->is_nan = nnan ? 1 : 0;
+        fs->nfin = 0; fs->ticket_fin = 0; fs->ticket_hist = 0;
+    }
+}
+
+// SCAN: single GPU -- the last CTA to finish also scans (counters are already global).
+template <bool SCAN>
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_cand_hist(const double *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ counters,
-            const double *__restrict__ lohi, unsigned long long k0, unsigned long long k1,
-            unsigned int *__restrict__ fhist, FastSel *__restrict__ fs)
+k_cand_hist(const double *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ ncand_ptr,
+            const unsigned long long *__restrict__ counters, const double *__restrict__ lohi,
+            unsigned long long k0, unsigned long long k1, unsigned int *__restrict__ fhist, FastSel *__restrict__ fs)
 {
     __shared__ unsigned int sh[FAST_NBINS];
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long found[2][2];
     __shared__ bool last;
-    const unsigned long long below = counters[0], ncand = counters[1], nnan = counters[2];
-    const bool ok = nnan == 0 && counters[3] == 0 && ncand <= cap && k0 >= below && k1 < below + ncand;
-    if (!ok) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { fs->valid = nnan ? 1 : 0; fs->is_nan = nnan ? 1 : 0; }
-        return;
-    }
+    unsigned long long ncand = *ncand_ptr;
+    if (ncand > cap) ncand = cap;                    // overflow is flagged through the counters
     const double lo = lohi[1], scale = cand_scale(lo, lohi[2]);
     for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) sh[t] = 0u;
     __syncthreads();
@@ -657,6 +720,7 @@ k_cand_hist(const double *__restrict__ cand, unsigned long long cap, const unsig
         const unsigned int v = sh[t];
         if (v) atomicAdd(&fhist[t], v);
     }
+    if (!SCAN) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(&fs->ticket_hist, 1u) == gridDim.x - 1;
@@ -664,36 +728,43 @@ k_cand_hist(const double *__restrict__ cand, unsigned long long cap, const unsig
     if (!last) return;
     __threadfence();
     for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) sh[t] = __ldcg(&fhist[t]);
-    if (threadIdx.x < 2) { found[threadIdx.x][0] = 0ull; found[threadIdx.x][1] = 0ull; }
     __syncthreads();
-    const unsigned long long r0 = k0 - below, r1 = k1 - below;
-    block_find_bin(sh, FAST_NBINS, r0, wsum, found[0]);
-    block_find_bin(sh, FAST_NBINS, r1, wsum, found[1]);
-    if (threadIdx.x == 0) {
-        fs->bin_a = (unsigned int)found[0][0];
-        fs->bin_b = (unsigned int)found[1][0];
-        fs->base_a = found[0][1];
-        fs->r0 = r0; fs->r1 = r1;
-        fs->valid = 1;
-    }
+    cand_scan_block(sh, counters, cap, k0, k1, fs, wsum, found);
+}
+
+// multi-GPU: the scan alone, on the all-reduced histogram and counters
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_cand_scan(const unsigned int *__restrict__ fhist, const unsigned long long *__restrict__ counters,
+            unsigned long long k0, unsigned long long k1, FastSel *__restrict__ fs)
+{
+    __shared__ unsigned int sh[FAST_NBINS];
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long found[2][2];
+    for (int t = threadIdx.x; t < FAST_NBINS; t += blockDim.x) sh[t] = fhist[t];
+    __syncthreads();
+    cand_scan_block(sh, counters, ~0ull, k0, k1, fs, wsum, found);
 }
 
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_cand_finish(const double *__restrict__ cand, const unsigned long long *__restrict__ counters,
+k_cand_finish(const double *__restrict__ cand, unsigned long long cap, const unsigned long long *__restrict__ ncand_ptr,
               const double *__restrict__ lohi, FastSel *__restrict__ fs, double *__restrict__ fin,
-              double *__restrict__ out)
+              double *__restrict__ out, int *__restrict__ fin_count)
 {
+    // fin_count != NULL (multi-GPU): gather this shard's keys of the chosen bins and report how many;
+    // the sort happens after the all-gather (k_small_select).  Otherwise the last CTA sorts in place.
     __shared__ double srt[FAST_FINCAP];
     __shared__ bool last;
     const int valid = fs->valid;
     if (!valid || fs->is_nan) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (fin_count) { *fin_count = 0; return; }
             const double nanv = __longlong_as_double(0x7ff8000000000000ll);
             out[0] = nanv; out[1] = nanv; out[2] = nanv; out[3] = valid ? 1. : 0.;
         }
         return;
     }
-    const unsigned long long ncand = counters[1];
+    unsigned long long ncand = *ncand_ptr;
+    if (ncand > cap) ncand = cap;
     const double lo = lohi[1], scale = cand_scale(lo, lohi[2]);
     const int ba = (int)fs->bin_a, bb = (int)fs->bin_b;
     const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
@@ -717,6 +788,10 @@ k_cand_finish(const double *__restrict__ cand, const unsigned long long *__restr
     if (!last) return;
     __threadfence();
     const unsigned int n = *reinterpret_cast<volatile unsigned int *>(&fs->nfin);
+    if (fin_count) {
+        if (threadIdx.x == 0) *fin_count = (int)(n < 0x7fffffffu ? n : 0x7fffffffu);    // > FAST_FINCAP = overflow
+        return;
+    }
     const unsigned long long i0 = fs->r0 - fs->base_a, i1 = fs->r1 - fs->base_a;
     if (n > FAST_FINCAP || i1 >= n) {
         if (threadIdx.x == 0) { out[0] = 0.; out[1] = 0.; out[2] = 0.; out[3] = 0.; }
@@ -1164,6 +1239,141 @@ int pxf_select_begin_bracket(void *state, int64_t k0, int64_t k1, const uint64_t
     return check_launch("k_select_begin_bracket");
 }
 
+// pack = [count, sum x, sum y, count | x of nsamp strided rays | y of the same rays]: what one rank
+// contributes to the all-gather that replaces "all-reduce the centroid sums" + "all-gather the sample"
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_sample_pack(const double *__restrict__ x, const double *__restrict__ y, int64_t num, const double *__restrict__ sums,
+              int nsamp, double *__restrict__ pack)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 4) pack[threadIdx.x] = sums[threadIdx.x];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nsamp; j += gridDim.x * blockDim.x) {
+        const int64_t i = num > 0 ? (int64_t)(((unsigned long long)j * (unsigned long long)num) / (unsigned long long)nsamp) : 0;
+        pack[4 + j] = num > 0 ? x[i] : __longlong_as_double(0x7ff8000000000000ll);
+        pack[4 + nsamp + j] = num > 0 ? y[i] : __longlong_as_double(0x7ff8000000000000ll);
+    }
+}
+// gathered = world packs.  Every thread adds the per-rank sums in rank order (identical on every rank
+// and every thread), thread 0 publishes the global sums and centroid, all compute the sample radii.
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_sample_radii(const double *__restrict__ gathered, int world, int nsamp, double *__restrict__ sums_out,
+               double *__restrict__ cxy, double *__restrict__ keys)
+{
+    const int stride = 4 + 2 * nsamp;
+    double s0 = 0., s1 = 0., s2 = 0.;
+    for (int r = 0; r < world; r++) {
+        s0 += gathered[(size_t)r * stride];
+        s1 += gathered[(size_t)r * stride + 1];
+        s2 += gathered[(size_t)r * stride + 2];
+    }
+    const double cx = s1 / s0, cy = s2 / s0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sums_out[0] = s0; sums_out[1] = s1; sums_out[2] = s2; sums_out[3] = s0;
+        cxy[0] = cx; cxy[1] = cy;
+    }
+    const int total = world * nsamp;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+        const int r = j / nsamp, q = j - r * nsamp;
+        const double xs = gathered[(size_t)r * stride + 4 + q], ys = gathered[(size_t)r * stride + 4 + nsamp + q];
+        keys[j] = sqrt(sq(xs - cx) + sq(ys - cy));
+    }
+}
+
+int pxf_sample_pack(const double *x, const double *y, int64_t num, const double *sums_dev, int32_t nsamp,
+                    double *pack_out, pxf_stream_t stream)
+{
+    if (num < 0 || nsamp <= 0 || (num > 0 && (!x || !y)) || !sums_dev || !pack_out) { set_error("pxf_sample_pack: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_sample_pack<<<grid_for(nsamp, PXF_BLOCK, 4), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, y, num, sums_dev, nsamp, pack_out);
+    count_launch();
+    return check_launch("k_sample_pack");
+}
+int pxf_sample_radii(const double *gathered, int32_t world, int32_t nsamp, double *sums_out, double *cxy_out,
+                     double *keys_out, pxf_stream_t stream)
+{
+    if (!gathered || world < 1 || nsamp <= 0 || !sums_out || !cxy_out || !keys_out) { set_error("pxf_sample_radii: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_sample_radii<<<grid_for((int64_t)world * nsamp, PXF_BLOCK, 4), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        gathered, world, nsamp, sums_out, cxy_out, keys_out);
+    count_launch();
+    return check_launch("k_sample_radii");
+}
+
+/* ---- building blocks of the fused bracketed select, for callers that put a collective between
+ * them (pyxfocus_b200/dist.py): sample -> all-gather -> pxf_small_select(3 passes) = bracket ->
+ * pxf_bracket_collect -> all-reduce counters -> pxf_cand_hist -> all-reduce 4096 bins ->
+ * pxf_cand_scan -> pxf_cand_gather -> all-gather -> pxf_small_select(5 passes) = exact pair. ---- */
+size_t pxf_fastsel_bytes(void) { return sizeof(FastSel); }
+int32_t pxf_fast_nbins(void) { return FAST_NBINS; }
+int32_t pxf_fast_fincap(void) { return FAST_FINCAP; }
+
+int pxf_small_select(const double *keys, const int32_t *seg_counts, int32_t nseg, int32_t seg_cap, int64_t ra, int64_t rb,
+                     int32_t npass, const void *fastsel, double *out_dev, pxf_stream_t stream)
+{
+    if (!keys || nseg < 1 || seg_cap < 1 || (int64_t)nseg * seg_cap > (int64_t(1) << 24) || (npass != 3 && npass != 5) ||
+        !out_dev || (!fastsel && (ra < 0 || rb < ra))) {
+        set_error("pxf_small_select: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    int rc = need_device();
+    if (rc) return rc;
+    static int smem_set = 0;
+    if (!smem_set) {
+        PXF_CUDA(cudaFuncSetAttribute(k_small_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
+        smem_set = 1;
+    }
+    k_small_select<<<1, 1024, 2 * 8192 * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
+        keys, seg_counts, nseg, seg_cap, (unsigned long long)ra, (unsigned long long)rb, npass,
+        static_cast<const FastSel *>(fastsel), out_dev, nullptr, nullptr, nullptr);
+    count_launch();
+    return check_launch("k_small_select");
+}
+
+/* fhist (pxf_fast_nbins() uint32, zeroed by the caller) += this shard's candidates in linear bins over [lo,hi] */
+int pxf_cand_hist(const double *cand, int64_t cap, const uint64_t *count_dev, const double *lohi_dev,
+                  uint32_t *fhist, pxf_stream_t stream)
+{
+    if (!cand || cap < 1 || !count_dev || !lohi_dev || !fhist) { set_error("pxf_cand_hist: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_cand_hist<false><<<grid_for(cap, PXF_BLOCK * 8, 2), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        cand, (unsigned long long)cap, reinterpret_cast<const unsigned long long *>(count_dev), nullptr, lohi_dev, 0ull, 0ull,
+        fhist, nullptr);
+    count_launch();
+    return check_launch("k_cand_hist");
+}
+
+/* counters: the all-reduced [below, inside, nan, overflowed, capacity]; fhist: the all-reduced bins */
+int pxf_cand_scan(const uint32_t *fhist, const uint64_t *counters, int64_t k0, int64_t k1, void *fastsel,
+                  pxf_stream_t stream)
+{
+    if (!fhist || !counters || !fastsel || k0 < 0 || k1 < k0) { set_error("pxf_cand_scan: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_cand_scan<<<1, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        fhist, reinterpret_cast<const unsigned long long *>(counters), (unsigned long long)k0, (unsigned long long)k1,
+        static_cast<FastSel *>(fastsel));
+    count_launch();
+    return check_launch("k_cand_scan");
+}
+
+/* fin (pxf_fast_fincap() doubles) <- this shard's candidates in the chosen bins; *fin_count = how many
+ * (more than the capacity = overflow, the final select then reports invalid) */
+int pxf_cand_gather(const double *cand, int64_t cap, const uint64_t *count_dev, const double *lohi_dev, void *fastsel,
+                    double *fin, int32_t *fin_count, pxf_stream_t stream)
+{
+    if (!cand || cap < 1 || !count_dev || !lohi_dev || !fastsel || !fin || !fin_count) { set_error("pxf_cand_gather: bad argument"); return PXF_ERR_INVALID; }
+    int rc = need_device();
+    if (rc) return rc;
+    k_cand_finish<<<grid_for(cap, PXF_BLOCK * 8, 2), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        cand, (unsigned long long)cap, reinterpret_cast<const unsigned long long *>(count_dev), lohi_dev,
+        static_cast<FastSel *>(fastsel), fin, nullptr, fin_count);
+    count_launch();
+    return check_launch("k_cand_gather");
+}
+
 /* histogram pass over a key buffer whose length lives on the device (min(*count_dev, cap)) */
 int pxf_select_hist_keys(const double *keys, int64_t cap, const uint64_t *count_dev, int32_t shift, int32_t bits,
                          void *state, pxf_stream_t stream)
@@ -1260,20 +1470,20 @@ int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const d
         // single-GPU fast path (see k_bracket_small): 5 launches in all
         static int smem_set = 0;
         if (!smem_set) {
-            PXF_CUDA(cudaFuncSetAttribute(k_bracket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
+            PXF_CUDA(cudaFuncSetAttribute(k_small_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
             smem_set = 1;
         }
         k_select_sample_sums<<<grid_for(BRACKET_SAMPLES, PXF_BLOCK, 4), PXF_BLOCK, 0, s>>>(
             x, y, num, sums_dev, w.cxy, BRACKET_SAMPLES, w.samp);
-        k_bracket_small<<<1, 1024, 2 * 8192 * 4, s>>>(w.samp, BRACKET_SAMPLES, (unsigned long long)ra, (unsigned long long)rb,
-                                                       w.lohi, w.counters, w.fs, w.fhist);
+        k_small_select<<<1, 1024, 2 * 8192 * 4, s>>>(w.samp, nullptr, 1, BRACKET_SAMPLES, (unsigned long long)ra,
+                                                      (unsigned long long)rb, 3, nullptr, w.lohi, w.counters, w.fs, w.fhist);
         count_launch(2);
-        if ((rc = check_launch("k_bracket_small"))) return rc;
+        if ((rc = check_launch("k_small_select"))) return rc;
         if ((rc = pxf_bracket_collect(x, y, num, w.cxy, w.lohi, w.cand, w.cap, reinterpret_cast<uint64_t *>(w.counters), stream))) return rc;
         const int g = grid_for(w.cap, PXF_BLOCK * 8, 2);     // few CTAs: each flushes a 4096-bin histogram
-        k_cand_hist<<<g, PXF_BLOCK, 0, s>>>(w.cand, (unsigned long long)w.cap, w.counters, w.lohi,
-                                            (unsigned long long)((num - 1) / 2), (unsigned long long)(num / 2), w.fhist, w.fs);
-        k_cand_finish<<<g, PXF_BLOCK, 0, s>>>(w.cand, w.counters, w.lohi, w.fs, w.fin, out_dev);
+        k_cand_hist<true><<<g, PXF_BLOCK, 0, s>>>(w.cand, (unsigned long long)w.cap, w.counters + 1, w.counters, w.lohi,
+                                                  (unsigned long long)((num - 1) / 2), (unsigned long long)(num / 2), w.fhist, w.fs);
+        k_cand_finish<<<g, PXF_BLOCK, 0, s>>>(w.cand, (unsigned long long)w.cap, w.counters + 1, w.lohi, w.fs, w.fin, out_dev, nullptr);
         count_launch(2);
         return check_launch("k_cand_finish");
     }

@@ -185,9 +185,44 @@ class CudaSelect:
         counters = torch.zeros(5, dtype=torch.int64, device=self.dev)
         _lib.check(self.L.pxf_bracket_collect(self.x.data_ptr(), self.y.data_ptr(), self.num, self.cxy.data_ptr(),
                                               lohi.data_ptr(), cand.data_ptr(), cap, counters.data_ptr(), self.s))
-        counters[3] = (counters[1] > cap).to(torch.int64)      # this shard's buffer overflowed
-        counters[4] = cap                                       # capacities are summed by the all-reduce
+        # (fill_ takes the scalar as a kernel argument; `counters[4] = cap` would stage it through a
+        # pageable host tensor, i.e. block the host until the stream -- the trace kernel -- has drained)
+        counters[3:4].copy_((counters[1:2] > cap).to(torch.int64))   # this shard's buffer overflowed
+        counters[4:5].fill_(cap)                                      # capacities are summed by the all-reduce
         return cand, counters
+
+    # -- fused small selects (single-CTA kernels; the collectives go between them)
+    def small_select(self, keys, seg_counts, nseg, seg_cap, ra, rb, npass, use_scan=False, read=False):
+        """Order statistics ra, rb of nseg x seg_cap keys -> device [a+b, a, b, valid]."""
+        out = torch.empty(4, dtype=torch.float64, device=self.dev)
+        _lib.check(self.L.pxf_small_select(keys.data_ptr(), seg_counts.data_ptr() if seg_counts is not None else None,
+                                           nseg, seg_cap, ra, rb, npass, self.fs.data_ptr() if use_scan else None,
+                                           out.data_ptr(), self.s))
+        self.last = out
+        if not read:
+            return out
+        h = out.cpu().numpy()
+        return float(h[0]), float(h[1]), float(h[2]), bool(h[3] != 0.)
+
+    def cand_hist(self, cand, count, lohi):
+        """This shard's candidates in linear bins over the bracket (int32 tensor to all-reduce)."""
+        fh = torch.zeros(int(self.L.pxf_fast_nbins()), dtype=torch.int32, device=self.dev)
+        _lib.check(self.L.pxf_cand_hist(cand.data_ptr(), cand.shape[0], count.data_ptr(), lohi.data_ptr(),
+                                        fh.data_ptr(), self.s))
+        return fh
+
+    def cand_scan(self, fhist, counters, k0, k1):
+        self.fs = torch.zeros((int(self.L.pxf_fastsel_bytes()) + 7) // 8, dtype=torch.int64, device=self.dev)
+        _lib.check(self.L.pxf_cand_scan(fhist.data_ptr(), counters.data_ptr(), k0, k1, self.fs.data_ptr(), self.s))
+
+    def cand_gather(self, cand, count, lohi):
+        """(fin buffer, its int32 count) of this shard: the candidates of the chosen bins."""
+        cap = int(self.L.pxf_fast_fincap())
+        fin = torch.empty(cap, dtype=torch.float64, device=self.dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        _lib.check(self.L.pxf_cand_gather(cand.data_ptr(), cand.shape[0], count.data_ptr(), lohi.data_ptr(),
+                                          self.fs.data_ptr(), fin.data_ptr(), cnt.data_ptr(), self.s))
+        return fin, cnt
 
     def begin_bracket(self, k0, k1, counters):
         """counters: the all-reduced [below, inside, nan, overflowed, capacity] totals."""
@@ -216,39 +251,57 @@ def select_median_pair(sel, total, group=None):
     return sel.finish(total)
 
 
-def bracket_median_pair(sel, total, min_shard, group=None):
+def bracket_median_pair(sel, total, min_shard, group=None, allk=None):
     """The same statistic with ONE pass over the shards instead of five (see include/pxf.h,
-    "Bracketed select").  Every rank contributes an equal share of the sample; the sample is
-    all-gathered so that each rank derives the identical bracket; the per-shard counters and
-    the candidate histograms are all-reduced.  Returns None when the bundle is too small for
-    a bracket (caller uses ``select_median_pair``); a result with valid=False means the
-    bracket missed and the caller must fall back as well."""
+    "Bracketed select") and four small collectives instead of ten 128 KiB all-reduces:
+
+      strided sample of every shard -> ALL-GATHER -> one-CTA select of two sample order statistics
+      = the identical bracket [lo,hi] on every rank -> one pass over the shard (count below, collect
+      inside) -> ALL-REDUCE the 5 counters -> candidates into 4096 linear bins over the bracket ->
+      ALL-REDUCE the bins -> scan (which bins hold the two middle ranks) -> each rank's few hundred
+      keys of those bins -> ALL-GATHER -> one-CTA exact select of the union.
+
+    Returns None when the bundle is too small for a bracket (caller uses ``select_median_pair``); a
+    result with valid=False means the bracket missed or a buffer overflowed (ties) and the caller
+    must fall back as well."""
     world = _world(group)
     min_num, nsamp, ra, rb = sel.bracket_params()
     per = nsamp // world
     if total < min_num or min_shard < max(4 * per, 1):
         return None
-    mine = sel.sample(per)
-    if world > 1:
-        allk = torch.empty(per * world, dtype=mine.dtype, device=mine.device)
-        td.all_gather_into_tensor(allk, mine, group=group)
-    else:
-        allk = mine
+    if allk is None:                 # (hpd() below gathers the sample together with the centroid sums)
+        mine = sel.sample(per)
+        if world > 1:
+            allk = torch.empty(per * world, dtype=mine.dtype, device=mine.device)
+            td.all_gather_into_tensor(allk, mine, group=group)
+        else:
+            allk = mine
     n_s = per * world
     scale = n_s / float(nsamp)
-    # bracket = two order statistics of the gathered sample (local select, no collective)
-    sel.use_keys(allk)
-    sel.begin(max(0, int(ra * scale)), min(n_s - 1, int(rb * scale) + 1))
-    _five_passes(sel, group, reduce=False)
-    sel.finish(n_s, read=False)
-    lohi = sel.last
+    lohi = sel.small_select(allk, None, 1, n_s, max(0, int(ra * scale)), min(n_s - 1, int(rb * scale) + 1), 3)
     cand, local = sel.collect(lohi)
-    glob = local.clone()
-    all_reduce_sum(glob, group)
-    sel.use_keys(cand, local[1:2])
-    sel.begin_bracket((total - 1) // 2, total // 2, glob)
-    _five_passes(sel, group)
-    return sel.finish(total)
+    fh = sel.cand_hist(cand, local[1:2], lohi)
+    if world > 1:
+        # counters and bins travel in ONE all-reduce, the per-rank key lists and their lengths in ONE
+        # all-gather: every collective here is latency bound
+        both = torch.cat([local, fh.to(torch.int64)])
+        all_reduce_sum(both, group)
+        glob, fh = both[:local.shape[0]].contiguous(), both[local.shape[0]:].to(torch.int32)
+    else:
+        glob = local
+    sel.cand_scan(fh, glob, (total - 1) // 2, total // 2)
+    fin, cnt = sel.cand_gather(cand, local[1:2], lohi)
+    cap = fin.shape[0]
+    if world > 1:
+        mine2 = torch.cat([fin, cnt.to(fin.dtype)])
+        gathered = torch.empty((cap + 1) * world, dtype=fin.dtype, device=fin.device)
+        td.all_gather_into_tensor(gathered, mine2, group=group)
+        gathered = gathered.view(world, cap + 1)
+        fin_all = gathered[:, :cap].contiguous()
+        cnt_all = gathered[:, cap].to(torch.int32).contiguous()
+    else:
+        fin_all, cnt_all = fin, cnt
+    return sel.small_select(fin_all, cnt_all, world, cap, 0, 0, 5, use_scan=True, read=True)
 
 
 def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None, weights=None):
@@ -263,19 +316,41 @@ def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=N
     flush(rays)
     x, y = rays[1:3]
     dev = x.device
+    L = _lib.lib()
+    world = _world(group)
     sums = _sums(0, rays, None, 0., 0.) if sums is None else sums.clone()
-    all_reduce_sum(sums[:4], group)
-    if total is None or min_shard is None:
-        cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
-        if _world(group) > 1:
-            td.all_reduce(cnt, op=td.ReduceOp.MIN, group=group)
-        total = int(round(float(sums[3].item())))
-        min_shard = int(round(float(cnt.item())))
     with torch.cuda.device(dev):
         cxy = torch.empty(2, dtype=torch.float64, device=dev)
-        _lib.check(_lib.lib().pxf_centroid_from_sums(sums.data_ptr(), cxy.data_ptr(), stream_ptr(dev)))
         sel = CudaSelect(x, y, cxy)
-        res = bracket_median_pair(sel, total, min_shard, group)
+        min_num, nsamp, _, _ = sel.bracket_params()
+        per = nsamp // world
+        res = None
+        if total is not None and min_shard is not None and total >= min_num and min_shard >= max(4 * per, 1):
+            # ONE all-gather carries every rank's centroid sums and its strided (x,y) sample; each rank
+            # then adds the sums in rank order (same bits everywhere) and takes the sample radii about
+            # the global centroid.
+            pack = torch.empty(4 + 2 * per, dtype=torch.float64, device=dev)
+            _lib.check(L.pxf_sample_pack(x.data_ptr(), y.data_ptr(), x.shape[0], sums.data_ptr(), per, pack.data_ptr(),
+                                         stream_ptr(dev)))
+            if world > 1:
+                gathered = torch.empty(pack.shape[0] * world, dtype=torch.float64, device=dev)
+                td.all_gather_into_tensor(gathered, pack, group=group)
+            else:
+                gathered = pack
+            allk = torch.empty(per * world, dtype=torch.float64, device=dev)
+            _lib.check(L.pxf_sample_radii(gathered.data_ptr(), world, per, sums.data_ptr(), cxy.data_ptr(),
+                                          allk.data_ptr(), stream_ptr(dev)))
+            res = bracket_median_pair(sel, total, min_shard, group, allk=allk)
+        else:
+            all_reduce_sum(sums[:4], group)
+            if total is None or min_shard is None:
+                cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
+                if world > 1:
+                    td.all_reduce(cnt, op=td.ReduceOp.MIN, group=group)
+                total = int(round(float(sums[3].item())))
+                min_shard = int(round(float(cnt.item())))
+            _lib.check(L.pxf_centroid_from_sums(sums.data_ptr(), cxy.data_ptr(), stream_ptr(dev)))
+            res = bracket_median_pair(sel, total, min_shard, group)
         if res is None or not res[3]:
             res = select_median_pair(sel, total, group)
     return res[:3] if return_stats else res[0]

@@ -27,6 +27,10 @@ def main():
         shard = pxf.sources.subannulus(220., 220.6, 2 * np.pi, hi - lo, zhat=-1., rng="philox", seed=3, first=lo, device=dev)
         prog.run(shard)
         h = dist.hpd(shard)
+        # caller-known sizes: nothing is read back before the result and the centroid sums travel in
+        # the sample all-gather (the path bench.py takes); must give the same bits
+        h2 = dist.hpd(shard, total=total, min_shard=total // world)
+        assert h2 == h, (h2, h)
         rms = dist.rmsCentroid(shard)
         cx, cy = dist.centroid(shard)
         dz = dist.analyticImagePlane(shard)

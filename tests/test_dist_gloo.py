@@ -124,6 +124,71 @@ class NumpySelect:
                                  int(inside.shape[0] > cap), cap], dtype=torch.int64)
         return cand, counters
 
+    # fused small selects: numpy versions of k_small_select / k_cand_hist / k_cand_scan / k_cand_finish
+    NBINS, FINCAP = 4096, 4096
+
+    def small_select(self, keys, seg_counts, nseg, seg_cap, ra, rb, npass, use_scan=False, read=False):
+        k = keys.numpy().reshape(nseg, seg_cap)
+        cnts = [seg_cap] * nseg if seg_counts is None else [int(c) for c in seg_counts.tolist()]
+        valid = True
+        if use_scan:
+            if self.fs["is_nan"]:
+                out = (float("nan"),) * 3 + (True,)
+                self.last = torch.tensor([out[0], out[1], out[2], 1.], dtype=torch.float64)
+                return out if read else self.last
+            valid = self.fs["valid"] and all(c <= seg_cap for c in cnts)
+            ra, rb = self.fs["r0"] - self.fs["base_a"], self.fs["r1"] - self.fs["base_a"]
+        v = np.concatenate([k[i, :min(cnts[i], seg_cap)] for i in range(nseg)]) if nseg else np.zeros(0)
+        v = np.sort(v[~np.isnan(v)])
+        if valid and rb >= v.size:
+            valid = False
+        if not valid:
+            a = b = 0.
+        else:
+            a, b = float(v[ra]), float(v[rb])
+            if npass == 3:                                  # bracket: round outwards over 25 bits
+                ua = np.array([a]).view(np.uint64)[0] >> np.uint64(25) << np.uint64(25)
+                ub = np.array([b]).view(np.uint64)[0] | np.uint64((1 << 25) - 1)
+                a = float(np.array([ua], dtype=np.uint64).view(np.float64)[0])
+                b = float(np.array([ub], dtype=np.uint64).view(np.float64)[0])
+        self.last = torch.tensor([(a + b) / 2. * 2., a, b, 1. if valid else 0.], dtype=torch.float64)
+        if not read:
+            return self.last
+        return (a + b) / 2. * 2., a, b, valid
+
+    @staticmethod
+    def _bins(r, lo, hi):
+        w = hi - lo
+        scale = NumpySelect.NBINS / w if w > 0 else 0.
+        t = (r - lo) * scale
+        return np.clip(np.where(t > 0, np.minimum(t, NumpySelect.NBINS - 1), 0), 0, NumpySelect.NBINS - 1).astype(np.int64)
+
+    def cand_hist(self, cand, count, lohi):
+        n = min(int(count.item()), cand.shape[0])
+        b = self._bins(cand.numpy()[:n], float(lohi[1]), float(lohi[2]))
+        return torch.from_numpy(np.bincount(b, minlength=self.NBINS).astype(np.int32))
+
+    def cand_scan(self, fhist, counters, k0, k1):
+        below, ncand, nan, over, cap_total = [int(v) for v in counters.tolist()]
+        ok = nan == 0 and over == 0 and ncand <= cap_total and k0 >= below and k1 < below + ncand
+        r0, r1 = (k0 - below, k1 - below) if ok else (0, 0)
+        c = np.cumsum(fhist.numpy().astype(np.int64))
+        ba = int(np.searchsorted(c, r0, side="right"))
+        bb = int(np.searchsorted(c, r1, side="right"))
+        self.fs = dict(valid=bool(ok or nan), is_nan=bool(nan), r0=r0, r1=r1, bin_a=ba, bin_b=bb,
+                       base_a=int(c[ba - 1]) if ba > 0 else 0)
+
+    def cand_gather(self, cand, count, lohi):
+        fin = torch.zeros(self.FINCAP, dtype=torch.float64)
+        if not self.fs["valid"] or self.fs["is_nan"]:
+            return fin, torch.zeros(1, dtype=torch.int32)
+        n = min(int(count.item()), cand.shape[0])
+        r = cand.numpy()[:n]
+        b = self._bins(r, float(lohi[1]), float(lohi[2]))
+        pick = r[(b >= self.fs["bin_a"]) & (b <= self.fs["bin_b"])]
+        fin[:min(pick.size, self.FINCAP)] = torch.from_numpy(pick[:self.FINCAP].copy())
+        return fin, torch.tensor([pick.size], dtype=torch.int32)
+
     def begin_bracket(self, k0, k1, counters):
         below, ncand, nan, over, cap_total = [int(v) for v in counters.tolist()]
         ok = over == 0 and ncand <= cap_total and k0 >= below and k1 < below + ncand
