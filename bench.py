@@ -32,6 +32,7 @@ R0, Z0, PSI = 220., 8400., 1.
 RIN, ROUT = 220., 220.6
 SURFACES_PER_RAY = 3                 # primary, secondary, focal plane
 # algorithmic HBM bytes per ray of the fused trace kernel: read x,y,z,l,m,n + write x,y,z,l,m,n,ux,uy,uz
+FP64_INSTR_PER_RAY = 283        # DADD+DMUL+DFMA+DSETP per ray, profiles/r01f_k_chain.txt (source page)
 TRACE_BYTES_PER_RAY = 6 * 8 + 9 * 8
 # per-routine API for comparison: 144+96+72+96+72+96
 PERCALL_BYTES_PER_RAY = 576
@@ -259,23 +260,51 @@ def run_engine(args):
         nw += 1
     barrier()
     # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled alongside
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ws = pxf.analyses.hpd_workspace(n, dev)
+
+    def timed_loop(deferred):
+        """K steps between two events.  deferred: every step's HPD is left on the device (float64[4] =
+        [HPD, lower, upper, valid]) and all K are read after the timed region -- nothing forces a host
+        round trip between steps (a stream of bundles analysed back to back).  Otherwise each step
+        reads its HPD back before the next trace is launched."""
+        res = torch.zeros(args.steps, 4, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        last = None
+        barrier()
+        clk.mark_begin()
+        e0.record()
+        for k in range(args.steps):
+            kev[k][0].record()
+            prog.run(src, out=out, sums=sums)
+            kev[k][1].record()
+            if deferred:
+                if world > 1:
+                    pdist.hpd(out, sums=sums, total=total, min_shard=n, out=res[k])
+                else:
+                    pxf.analyses.hpd_enqueue(out, res[k], ws, sums=sums)
+            else:
+                last = pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
+        e1.record()
+        barrier()
+        clk.mark_end()
+        if deferred:
+            h = res.cpu().numpy()
+            if not (h[:, 3] != 0.).all():
+                return None, None          # a bracket missed (~1e-9): the caller re-times with read-backs
+            last = float(h[-1, 0])
+        return e0.elapsed_time(e1), last
+
     launches0 = pxf.launch_count()
-    barrier()
-    clk.mark_begin()
-    ev0.record()
-    for k in range(args.steps):
-        kev[k][0].record()
-        prog.run(src, out=out, sums=sums)
-        kev[k][1].record()
-        hp = pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
-    ev1.record()
-    barrier()
-    clk.mark_end()
+    readback = "deferred: K results read after the timed region"
+    ms, hp_t = timed_loop(True)
+    if ms is None:
+        launches0 = pxf.launch_count()
+        readback = "per step"
+        ms, hp_t = timed_loop(False)
+    assert hp_t == hp or (hp_t != hp_t and hp != hp), "HPD changed between warm-up and timed steps"
     launches = pxf.launch_count() - launches0
     clocks = clk.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
     trace_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     if world > 1:
         t = torch.tensor([ms, trace_ms], dtype=torch.float64, device=dev)
@@ -315,16 +344,25 @@ def run_engine(args):
                                "subannulus -> transform -> wolterprimary -> reflect -> woltersecondary -> reflect -> flat -> hpd)",
                    "rays_per_gpu": n, "total_rays": total, "surfaces_per_ray": SURFACES_PER_RAY,
                    "interactions_per_s": value * SURFACES_PER_RAY, "r0": R0, "z0": Z0, "psi": PSI,
-                   "parallelism": "rays sharded %d-way, no trace-time communication; HPD = all-reduced "
-                                  "centroid sums + 5 all-reduced radix-select histograms" % world,
+                   "parallelism": "rays sharded %d-way, no trace-time communication; HPD = bracketed exact "
+                                  "select, 3 small collectives (sums+sample all-gather, counters+bins "
+                                  "all-reduce, key lists all-gather)" % world,
                    "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (48e-9 * n),
-                   "hpd": hp, "trace_kernel_ms": trace_ms},
+                   "hpd": hp, "trace_kernel_ms": trace_ms, "hpd_readback": readback},
         "roofline": {"bound": "hbm", "kernel": "k_program (fused trace)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                      "algorithmic_bytes_per_ray": TRACE_BYTES_PER_RAY, "traffic": traffic,
-                     "note": "the fused kernel is fp64-pipe bound, not HBM bound (Newton divides/sqrts, no FMA "
-                             "contraction for bit parity); see DESIGN.md and profiles/"},
+                     "note": "the fused kernel is COMPUTE bound (a compute-only replay of the chain takes the "
+                             "same 3.5 ms, profiles/r01_trace_compute.txt): serial fp64 Newton/division chains, "
+                             "no FMA contraction for bit parity; see DESIGN.md and profiles/r01_notes.md",
+                     # second denominator: fp64 warp instructions per ray from the ncu capture (static),
+                     # duration measured live; peak = 148 SMs x 64 lanes x sm_max clock, reached to 99 %
+                     # by profiles/micro/fp64_peak.cu
+                     "fp64": {"thread_instr_per_ray": FP64_INSTR_PER_RAY,
+                              "achieved_Tinstr_s": FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / 1e12,
+                              "peak_Tinstr_s": 148 * 64 * 1.965e9 / 1e12,
+                              "frac": FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / (148 * 64 * 1.965e9)}},
         "clocks": clocks,
         "gpu_launches": launches,
     }

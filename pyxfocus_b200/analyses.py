@@ -147,6 +147,25 @@ def hpd(rays, weights=None, cent=True, sums=None):
     return out.value
 
 
+def hpd_workspace(num, device):
+    """Scratch tensor for ``hpd_enqueue`` on bundles of up to ``num`` rays."""
+    return torch.empty(int(_lib.lib().pxf_hpd_workspace_bytes(int(num))) + 64, dtype=torch.uint8, device=device)
+
+
+def hpd_enqueue(rays, out, workspace, sums=None, mode=0):
+    """Unweighted ``hpd`` without the read-back: everything is enqueued on the current stream and the
+    result lands in ``out`` (device float64[4] = [HPD, lower middle radius, upper middle radius,
+    valid]).  For pipelines that analyse many bundles back to back and read the numbers at the end.
+    ``valid`` == 0 (bracket miss / ties piled in one bin: ~never) means: call again with mode=1."""
+    flush(rays)
+    x, y = rays[1:3]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_hpd_from_sums_dev(x.data_ptr(), y.data_ptr(), x.shape[0],
+                                                    sums.data_ptr() if sums is not None else None, out.data_ptr(),
+                                                    workspace.data_ptr(), mode, stream_ptr(x.device)))
+    return out
+
+
 def analyticImagePlane(rays, weights=None):
     """Axial shift to the best image plane, Ron Elsner's analytic method (analyses.py:118-133)."""
     flush(rays)

@@ -251,7 +251,7 @@ def select_median_pair(sel, total, group=None):
     return sel.finish(total)
 
 
-def bracket_median_pair(sel, total, min_shard, group=None, allk=None):
+def bracket_median_pair(sel, total, min_shard, group=None, allk=None, read=True):
     """The same statistic with ONE pass over the shards instead of five (see include/pxf.h,
     "Bracketed select") and four small collectives instead of ten 128 KiB all-reduces:
 
@@ -301,16 +301,19 @@ def bracket_median_pair(sel, total, min_shard, group=None, allk=None):
         cnt_all = gathered[:, cap].to(torch.int32).contiguous()
     else:
         fin_all, cnt_all = fin, cnt
-    return sel.small_select(fin_all, cnt_all, world, cap, 0, 0, 5, use_scan=True, read=True)
+    return sel.small_select(fin_all, cnt_all, world, cap, 0, 0, 5, use_scan=True, read=read)
 
 
-def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None, weights=None):
+def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=None, weights=None, out=None):
     """``weights`` given: the weighted statistic (``hpd_weighted``).  Otherwise: unweighted HPD (2 x median radius about the global centroid) of a sharded bundle;
     exact, identical on every rank.  ``sums``: this shard's centroid sums from
     ``Program.run(..., sums=...)`` (saves the local pass that computes them).  ``total`` /
     ``min_shard``: global ray count and smallest shard size when the caller knows them (e.g.
     equal shards) -- then nothing is read back to the host before the final result, so the
-    whole analysis is enqueued behind the trace kernel without a sync."""
+    whole analysis is enqueued behind the trace kernel without a sync.  ``out`` (device float64[4],
+    needs ``total``/``min_shard`` and a bundle large enough for the bracketed select): the result
+    [HPD, lower, upper, valid] is left there and NOTHING is read back -- for pipelines that analyse
+    bundle after bundle and read the numbers at the end; valid == 0 means "repeat without out"."""
     if weights is not None:
         return hpd_weighted(rays, weights, group)
     flush(rays)
@@ -340,8 +343,13 @@ def hpd(rays, group=None, return_stats=False, sums=None, total=None, min_shard=N
             allk = torch.empty(per * world, dtype=torch.float64, device=dev)
             _lib.check(L.pxf_sample_radii(gathered.data_ptr(), world, per, sums.data_ptr(), cxy.data_ptr(),
                                           allk.data_ptr(), stream_ptr(dev)))
-            res = bracket_median_pair(sel, total, min_shard, group, allk=allk)
+            res = bracket_median_pair(sel, total, min_shard, group, allk=allk, read=out is None)
+            if out is not None:
+                out.copy_(sel.last)
+                return out
         else:
+            if out is not None:
+                raise ValueError("dist.hpd(out=...) needs total/min_shard and a bundle large enough for the bracket")
             all_reduce_sum(sums[:4], group)
             if total is None or min_shard is None:
                 cnt = torch.tensor([float(x.shape[0])], dtype=torch.float64, device=dev)
