@@ -133,7 +133,7 @@ def to_mask(ind, num, device):
     if ind.dtype == torch.bool:
         if ind.shape[0] != num:
             raise IndexError("boolean index did not match ray count")
-        return ind.to(torch.uint8).contiguous()
+        return ind.contiguous().view(torch.uint8)       # a bool tensor already is one 0/1 byte per ray
     if ind.dtype == torch.uint8 and ind.shape[0] == num:
         return ind.contiguous()
     m = torch.zeros(num, dtype=torch.uint8, device=device)

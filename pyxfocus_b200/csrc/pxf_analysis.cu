@@ -39,32 +39,88 @@ PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m
     }
 }
 
-template <int MODE>
+// One pass, HBM bound: each thread keeps U independent accumulator sets (a single fp64 add chain per
+// quantity would be latency bound: 8 cycles per element) fed by U batched 16-byte loads per row, and
+// folds them in a fixed order at the end -- same bits on every run and for every grid of the same
+// size (the grid is a function of num only).
+template <int MODE, bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK)
 k_sums(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ l,
        const double *__restrict__ m, const double *__restrict__ n, const double *__restrict__ w,
        int64_t num, double a, double b, const double *__restrict__ ab_dev, double *__restrict__ partial)
 {
     constexpr int NS = MODE == PXF_SUMS_CENTROID ? 4 : (MODE == PXF_SUMS_RMS ? 2 : 9);
+    constexpr int U = MODE == PXF_SUMS_IMAGEPLANE ? 2 : 4;
     if (ab_dev) { a = ab_dev[0]; b = ab_dev[1]; }
-    double acc[NSUM];
+    double acc[U][NSUM];
 #pragma unroll
-    for (int k = 0; k < NSUM; k++) acc[k] = 0.;
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int k = 0; k < NSUM; k++) acc[u][k] = 0.;
     const bool has_w = w != nullptr;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tid; i < num; i += nthr) {
-        double xv = x[i], yv = y[i];
-        double lv = 0., mv = 0., nv = 1.;
-        if (MODE == PXF_SUMS_IMAGEPLANE) { lv = l[i]; mv = m[i]; nv = n[i]; }
-        double wv = has_w ? w[i] : 1.;
-        sums_accum<MODE>(acc, xv, yv, lv, mv, nv, wv, has_w, a, b);
+    if (VEC2) {
+        const int64_t npair = num >> 1;
+        for (int64_t q0 = tid; q0 < npair; q0 += U * nthr) {
+            double2 xv[U], yv[U], lv[U], mv[U], nv[U], wv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t q = q0 + u * nthr;
+                const bool in = q < npair;
+                const double2 z2 = make_double2(0., 0.), o2 = make_double2(1., 1.);
+                xv[u] = in ? *reinterpret_cast<const double2 *>(x + 2 * q) : z2;
+                yv[u] = in ? *reinterpret_cast<const double2 *>(y + 2 * q) : z2;
+                if (MODE == PXF_SUMS_IMAGEPLANE) {
+                    lv[u] = in ? *reinterpret_cast<const double2 *>(l + 2 * q) : z2;
+                    mv[u] = in ? *reinterpret_cast<const double2 *>(m + 2 * q) : z2;
+                    nv[u] = in ? *reinterpret_cast<const double2 *>(n + 2 * q) : o2;
+                } else { lv[u] = z2; mv[u] = z2; nv[u] = o2; }
+                wv[u] = (in && has_w) ? *reinterpret_cast<const double2 *>(w + 2 * q) : o2;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (q0 + u * nthr < npair) {
+                    sums_accum<MODE>(acc[u], xv[u].x, yv[u].x, lv[u].x, mv[u].x, nv[u].x, wv[u].x, has_w, a, b);
+                    sums_accum<MODE>(acc[u], xv[u].y, yv[u].y, lv[u].y, mv[u].y, nv[u].y, wv[u].y, has_w, a, b);
+                }
+        }
+        if ((num & 1) && tid == 0) {
+            const int64_t i = num - 1;
+            sums_accum<MODE>(acc[0], x[i], y[i], MODE == PXF_SUMS_IMAGEPLANE ? l[i] : 0., MODE == PXF_SUMS_IMAGEPLANE ? m[i] : 0.,
+                             MODE == PXF_SUMS_IMAGEPLANE ? n[i] : 1., has_w ? w[i] : 1., has_w, a, b);
+        }
+    } else {
+        for (int64_t i0 = tid; i0 < num; i0 += U * nthr) {
+            double xv[U], yv[U], lv[U], mv[U], nv[U], wv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t i = i0 + u * nthr;
+                const bool in = i < num;
+                xv[u] = in ? x[i] : 0.;
+                yv[u] = in ? y[i] : 0.;
+                lv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? l[i] : 0.;
+                mv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? m[i] : 0.;
+                nv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? n[i] : 1.;
+                wv[u] = (in && has_w) ? w[i] : 1.;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (i0 + u * nthr < num) sums_accum<MODE>(acc[u], xv[u], yv[u], lv[u], mv[u], nv[u], wv[u], has_w, a, b);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        double t = acc[0][k];
+#pragma unroll
+        for (int u = 1; u < U; u++) t += acc[u][k];
+        acc[0][k] = t;
     }
     __shared__ double sh[NSUM][PXF_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
-        double v = acc[k];
+        double v = acc[0][k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) sh[k][warp] = v;
@@ -110,23 +166,27 @@ static int sums_launch(int mode, const double *x, const double *y, const double 
     if (num < 0 || !x || !y || !out_dev || !scratch) { set_error("pxf_sums: bad argument"); return PXF_ERR_INVALID; }
     if (mode == PXF_SUMS_IMAGEPLANE && (!l || !m || !n)) { set_error("pxf_sums: l,m,n required"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
-    int grid = grid_for(num, PXF_BLOCK * 4, 8);
+    int grid = grid_for(num, PXF_BLOCK * 8, 4);
     if (grid > SUM_BLOCKS_MAX) grid = SUM_BLOCKS_MAX;
     double *partial = static_cast<double *>(scratch);
+    uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w);
+    if (mode == PXF_SUMS_IMAGEPLANE)
+        al |= reinterpret_cast<uintptr_t>(l) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(n);
+    const bool v2 = (al & 15) == 0;
     int ns;
-    if (mode == PXF_SUMS_CENTROID) {
-        ns = 4;
-        k_sums<PXF_SUMS_CENTROID><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
-    } else if (mode == PXF_SUMS_RMS) {
-        ns = 2;
-        k_sums<PXF_SUMS_RMS><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
-    } else if (mode == PXF_SUMS_IMAGEPLANE) {
-        ns = 9;
-        k_sums<PXF_SUMS_IMAGEPLANE><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);
-    } else {
+#define PXF_SUMS_GO(M)                                                                                         \
+    do {                                                                                                       \
+        if (v2) k_sums<M, true><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);        \
+        else k_sums<M, false><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);          \
+    } while (0)
+    if (mode == PXF_SUMS_CENTROID) { ns = 4; PXF_SUMS_GO(PXF_SUMS_CENTROID); }
+    else if (mode == PXF_SUMS_RMS) { ns = 2; PXF_SUMS_GO(PXF_SUMS_RMS); }
+    else if (mode == PXF_SUMS_IMAGEPLANE) { ns = 9; PXF_SUMS_GO(PXF_SUMS_IMAGEPLANE); }
+    else {
         set_error("pxf_sums: bad mode");
         return PXF_ERR_INVALID;
     }
+#undef PXF_SUMS_GO
     k_sums_final<<<1, PXF_BLOCK, 0, s>>>(partial, grid, ns, out_dev);
     count_launch(2);
     return check_launch("k_sums");
@@ -903,9 +963,12 @@ k_compact_scan(const unsigned int *__restrict__ tile_count, int64_t ntiles, long
 
 // Each warp owns 8 consecutive 32-ray chunks of the tile; ballot + popc give the rank inside a
 // chunk, a 64-entry shared scan gives the chunk base, the tile offset comes from k_compact_scan.
+// row pointers travel as a kernel argument (no pointer loads in the loop, no H2D staging copy)
+struct RowTable { const double *in[16]; double *out[16]; };
+
 template <int MODE>   // 0: scatter rows, 1: write indices
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_compact_scatter(const double *const *__restrict__ rows_in, double *const *__restrict__ rows_out, int nrows,
+k_compact_scatter(const __grid_constant__ RowTable T, int nrows,
                   const uint8_t *__restrict__ flags, int64_t num, const long long *__restrict__ offsets,
                   long long *__restrict__ idx_out)
 {
@@ -938,34 +1001,44 @@ k_compact_scatter(const double *const *__restrict__ rows_in, double *const *__re
     }
     __syncthreads();
     const long long tile_off = offsets[blockIdx.x];
+    long long dst[8];
+    bool keep[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const int chunk = warp * 8 + j;
-        const int64_t i = base + chunk * 32 + lane;
-        if ((ballots[j] >> lane) & 1u) {
-            const long long dst = tile_off + chunk_base[chunk] + __popc(ballots[j] & ((1u << lane) - 1));
-            if (MODE == 0) {
-                for (int r = 0; r < nrows; r++) rows_out[r][dst] = rows_in[r][i];
-            } else {
-                idx_out[dst] = i;
-            }
+        keep[j] = (ballots[j] >> lane) & 1u;
+        dst[j] = tile_off + chunk_base[chunk] + __popc(ballots[j] & ((1u << lane) - 1));
+    }
+    const int64_t i0 = base + warp * 256 + lane;
+    if (MODE == 0) {
+        // row-outer: the eight loads of a row are issued together, then the eight stores
+        for (int r = 0; r < nrows; r++) {
+            const double *__restrict__ src = T.in[r];
+            double *__restrict__ out = T.out[r];
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = keep[j] ? src[i0 + j * 32] : 0.;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (keep[j]) out[dst[j]] = v[j];
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (keep[j]) idx_out[dst[j]] = i0 + j * 32;
     }
 }
 
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_gather_rows(const double *const *__restrict__ rows_in, double *const *__restrict__ rows_out, int nrows,
-              const long long *__restrict__ idx, int64_t count)
+k_gather_rows(const __grid_constant__ RowTable T, int nrows, const long long *__restrict__ idx, int64_t count)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = tid; i < count; i += nthr) {
         const long long s = idx[i];
-        for (int r = 0; r < nrows; r++) rows_out[r][i] = rows_in[r][s];
+        for (int r = 0; r < nrows; r++) T.out[r][i] = T.in[r][s];
     }
 }
-
-struct RowTable { const double *in[16]; double *out[16]; };
 
 static int need_device()
 {
@@ -1612,10 +1685,9 @@ int pxf_compact_scatter(const double *const *rows_in, double *const *rows_out, i
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int64_t ntiles = (num + CTILE - 1) / CTILE;
     RowTable h;
+    memset(&h, 0, sizeof(h));
     for (int r = 0; r < nrows; r++) { h.in[r] = rows_in[r]; h.out[r] = rows_out[r]; }
-    RowTable *d = ctab(scratch, ntiles);
-    PXF_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    k_compact_scatter<0><<<(unsigned)ntiles, PXF_BLOCK, 0, s>>>(d->in, d->out, nrows, flags, num, coff(scratch), nullptr);
+    k_compact_scatter<0><<<(unsigned)ntiles, PXF_BLOCK, 0, s>>>(h, nrows, flags, num, coff(scratch), nullptr);
     count_launch();
     return check_launch("k_compact_scatter");
 }
@@ -1629,8 +1701,10 @@ int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, 
     if (rc) return rc;
     // idx_out may be NULL only if no ray survives (nothing is written then)
     int64_t ntiles = (num + CTILE - 1) / CTILE;
+    RowTable none;
+    memset(&none, 0, sizeof(none));
     k_compact_scatter<1><<<(unsigned)ntiles, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        nullptr, nullptr, 0, flags, num, coff(scratch), reinterpret_cast<long long *>(idx_out));
+        none, 0, flags, num, coff(scratch), reinterpret_cast<long long *>(idx_out));
     count_launch();
     return check_launch("k_compact_indices");
 }
@@ -1648,11 +1722,10 @@ int pxf_gather_rows(const double *const *rows_in, double *const *rows_out, int32
     if (count == 0) return PXF_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     RowTable h;
+    memset(&h, 0, sizeof(h));
     for (int r = 0; r < nrows; r++) { h.in[r] = rows_in[r]; h.out[r] = rows_out[r]; }
-    RowTable *d = static_cast<RowTable *>(table_scratch);
-    PXF_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    k_gather_rows<<<grid_for(count, PXF_BLOCK, 8), PXF_BLOCK, 0, s>>>(d->in, d->out, nrows,
-                                                                     reinterpret_cast<const long long *>(idx), count);
+    (void)table_scratch;
+    k_gather_rows<<<grid_for(count, PXF_BLOCK, 8), PXF_BLOCK, 0, s>>>(h, nrows, reinterpret_cast<const long long *>(idx), count);
     count_launch();
     return check_launch("k_gather_rows");
 }

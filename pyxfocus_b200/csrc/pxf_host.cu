@@ -228,6 +228,10 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     if (CM || scanning) {
         unsigned hc = std::thread::hardware_concurrency();
         int T = (int)(hc >= 4 ? (hc * 3) / 4 : 2);      // measured on the 16-vCPU B200 host: 8 -> 141 ms, 12 -> 135 ms
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU: the ranks share the host cores
+            const int lws = atoi(e);
+            if (lws > 1) T = T / lws > 2 ? T / lws : 2;
+        }
         if (const char *e = getenv("PXF_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) T = v; }
         for (int t = 0; t < T; t++)
             fillers.emplace_back([&, t, T]() {
