@@ -429,6 +429,40 @@ int pxf_analyticimageplane(const double *x, const double *y, const double *l, co
                            const double *n, const double *w, int64_t num, double *dz_host,
                            pxf_stream_t stream);
 
+/* Weighted HPD (analyses.py:88-97, weighted branch).  pxf_hpd_weighted = what pxf_hpd calls when
+ * w != NULL: the bracketed path for num >= pxf_wq_min_num(), the full sort otherwise or when the
+ * bracketed path reports valid == 0 (bracket miss, candidate overflow, NaN radius, NaN/negative
+ * weight).  pxf_hpd_weighted_sorted is the literal argsort -> cumsum -> argmin pipeline.
+ * The pxf_wq_* pieces are the steps of the bracketed path (also used by the sharded driver):
+ *   pxf_wq_sample    strided sample of (radius about cxy_dev, weight) pairs
+ *   pxf_wq_brackets  sorted sample + prefix weights -> closed brackets around the .25 / .75 crossings
+ *                    (state: pxf_wq_state_bytes(), layout double lohi[4], below[2], u64 count[2], nbad)
+ *   pxf_wq_collect   one pass: weight strictly below each bracket (deterministic tree) and the
+ *                    (radius, weight) pairs inside, appended to cand_r/w{0,1} (capacity cap each)
+ *   pxf_wq_argmin    argmin |(below + cum[i]) / total - q| inside a sorted window;
+ *                    out_dev[4] = {r, valid, cdf, index} */
+int pxf_hpd_weighted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+                     pxf_stream_t stream);
+int pxf_hpd_weighted_sorted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+                            pxf_stream_t stream);
+int pxf_hpd_weighted_bracket(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+                             int32_t *valid_host, pxf_stream_t stream);
+size_t pxf_wq_state_bytes(void);
+int64_t pxf_wq_min_num(void);
+int32_t pxf_wq_samples(int64_t num);
+int64_t pxf_wq_capacity(int64_t num);
+int pxf_wq_sample(const double *x, const double *y, const double *w, int64_t num, const double *cxy_dev,
+                  int32_t nsamp, double *rs_out, double *ws_out, pxf_stream_t stream);
+int pxf_wq_brackets(const double *rs_sorted, const double *cum, int32_t nsamp, void *state, pxf_stream_t stream);
+size_t pxf_wq_collect_scratch_bytes(void);
+int pxf_wq_collect(const double *x, const double *y, const double *w, int64_t num, const double *cxy_dev, void *state,
+                   double *cand_r0, double *cand_w0, double *cand_r1, double *cand_w1, int64_t cap, void *scratch,
+                   pxf_stream_t stream);
+double *pxf_wq_below_ptr(void *state, int32_t b);
+size_t pxf_wq_argmin_scratch_bytes(void);
+int pxf_wq_argmin(const double *rs_sorted, const double *cum, int64_t n, const double *below_dev, const double *total_dev,
+                  double q, double *out_dev, void *scratch, pxf_stream_t stream);
+
 /* Stable LSD radix sort of fp64 keys (ascending by IEEE total order of non-negative values;
  * negative keys and NaNs are ordered by their raw bit pattern after sign fix-up as in
  * np.sort) with the permutation (np.argsort equivalent, stable).  keys_out / idx_out device

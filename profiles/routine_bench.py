@@ -114,6 +114,9 @@ def main():
         timed_b2b(lambda: pxf.analyses.hpd(st3)))))
     rows.append(("analyticImagePlane", "analyses.py:118-133", 40, *(lambda ms: (ms, n / (ms * 1e-3), 40 * n / (ms * 1e-3) / 1e9, 40 * n / (ms * 1e-3) / 1e9 / peak))(
         timed_b2b(lambda: pxf.analyses.analyticImagePlane(st3)))))
+    wts = torch.linspace(.5, 2., n, dtype=torch.float64, device=dev)
+    rows.append(("hpd (weighted)", "analyses.py:88-97", 40, *(lambda ms: (ms, n / (ms * 1e-3), 40 * n / (ms * 1e-3) / 1e9, 40 * n / (ms * 1e-3) / 1e9 / peak))(
+        timed_b2b(lambda: pxf.analyses.hpd(st3, weights=wts), calls=5))))
     flags = (st3[1] > 0)
     f = float(flags.float().mean())
     b = 80 + 80 * f + 1

@@ -128,6 +128,20 @@ SIGNATURES = {
     "pxf_rmscentroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_hpd": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_analyticimageplane": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
+    "pxf_hpd_weighted": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_hpd_weighted_sorted": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_hpd_weighted_bracket": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _vp, _st]),
+    "pxf_wq_state_bytes": (_sz, []),
+    "pxf_wq_min_num": (_i64, []),
+    "pxf_wq_samples": (_i32, [_i64]),
+    "pxf_wq_capacity": (_i64, [_i64]),
+    "pxf_wq_sample": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _i32, _dp, _dp, _st]),
+    "pxf_wq_brackets": (_c.c_int, [_dp, _dp, _i32, _vp, _st]),
+    "pxf_wq_collect_scratch_bytes": (_sz, []),
+    "pxf_wq_collect": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _vp, _dp, _dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_wq_below_ptr": (_vp, [_vp, _i32]),
+    "pxf_wq_argmin_scratch_bytes": (_sz, []),
+    "pxf_wq_argmin": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _d, _dp, _vp, _st]),
     "pxf_sort_scratch_bytes": (_sz, [_i64]),
     "pxf_argsort": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _st]),
     "pxf_scan_scratch_bytes": (_sz, [_i64]),

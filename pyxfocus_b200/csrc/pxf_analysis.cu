@@ -1075,9 +1075,6 @@ using namespace pxf;
 
 extern "C" {
 
-int pxf_hpd_weighted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
-                     pxf_stream_t stream);   // pxf_sort.cu
-
 size_t pxf_sums_scratch_bytes(void) { return (size_t)SUM_BLOCKS_MAX * NSUM * sizeof(double); }
 
 int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, const double *m,

@@ -3,6 +3,7 @@
 // device code as the per-routine kernels (pxf_ray.cuh), so the result is bit-identical to
 // issuing the routines one by one.  Every ray runs the same program, so the opcode switch is
 // warp-uniform; only Newton trip counts and vignetting diverge.
+#include <stdlib.h>
 #include "pxf_program.h"
 
 namespace pxf {
@@ -33,9 +34,11 @@ PXF_DEV bool run_op(Ray &r, const FusedOp &op)
         case PXF_OP_FLATOPD: op_flat(r, true, op.q[0]); break;
         case PXF_OP_CONIC:
         case PXF_OP_CONICOPD: op_conic(r, *reinterpret_cast<const ConicP *>(op.q)); break;
+        // (parameter blocks of the Newton surfaces are copied to registers once: read through the
+        // op-indexed constant bank they would be re-fetched by an LDC on every use in every pass)
         case PXF_OP_WOLTERPRIMARY:
-        case PXF_OP_WOLTERPRIMARYOPD: op_wolterprimary(r, *reinterpret_cast<const WolterP *>(op.q)); break;
-        case PXF_OP_WOLTERSECONDARY: op_woltersecondary(r, *reinterpret_cast<const WolterP *>(op.q)); break;
+        case PXF_OP_WOLTERPRIMARYOPD: { const WolterP p = *reinterpret_cast<const WolterP *>(op.q); op_wolterprimary(r, p); break; }
+        case PXF_OP_WOLTERSECONDARY: { const WolterP p = *reinterpret_cast<const WolterP *>(op.q); op_woltersecondary(r, p); break; }
         case PXF_OP_WOLTERSINE: op_woltersine(r, *reinterpret_cast<const WolterSineP *>(op.q)); break;
         case PXF_OP_WSPRIMARY: op_wsprimary(r, *reinterpret_cast<const WSP *>(op.q)); break;
         case PXF_OP_WSSECONDARY: op_wssecondary(r, *reinterpret_cast<const WSP *>(op.q)); break;
@@ -70,8 +73,8 @@ PXF_DEV bool run_program(Ray &r, const FusedProgram &prog)
     return true;
 }
 
-template <bool VEC2>
-__global__ void __launch_bounds__(PXF_BLOCK)
+template <bool VEC2, int MINB = 1>
+__global__ void __launch_bounds__(PXF_BLOCK, MINB)
 k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
           double *__restrict__ partials, const __grid_constant__ FusedProgram prog)
 {
@@ -248,24 +251,21 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         int rc = launch_chain(P, Q, num, fp, alive, aligned, s, partials, grid_out);
         if (rc != PXF_ERR_UNSUPPORTED) return rc;
     }
-    static int ctas[2] = {0, 0};
-    const int v = aligned ? 1 : 0;
-    if (ctas[v] == 0) {
+    // PXF_PROGRAM_VARIANT (tuning): 0 = two rays per thread (double2 rows), 3/4 = one ray per thread with
+    // the register allocation capped for 3 / 4 resident CTAs per SM
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("PXF_PROGRAM_VARIANT"); variant = e ? atoi(e) : 3; }
+    auto go = [&](auto kern, int64_t items) {
         int nb = 0;
-        cudaError_t e = aligned ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program<true>, PXF_BLOCK, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program<false>, PXF_BLOCK, 0);
-        if (e != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
-        ctas[v] = nb;
-    }
-    if (aligned) {
-        int grid = grid_for((num + 1) >> 1, PXF_BLOCK, ctas[v]);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PXF_BLOCK, 0) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
+        const int grid = grid_for(items, PXF_BLOCK, nb);
         if (grid_out) *grid_out = grid;
-        k_program<true><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
-    } else {
-        int grid = grid_for(num, PXF_BLOCK, ctas[v]);
-        if (grid_out) *grid_out = grid;
-        k_program<false><<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
-    }
+        kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
+    };
+    if (aligned && variant == 0) go(k_program<true, 1>, (num + 1) >> 1);
+    else if (variant == 4) go(k_program<false, 4>, num);
+    else if (variant == 1) go(k_program<false, 1>, num);
+    else go(k_program<false, 3>, num);
     count_launch();
     return check_launch("k_program");
 }

@@ -4,6 +4,8 @@
 // of SM-count x resident-CTA blocks striding over ray pairs.
 #include <stdarg.h>
 #include <atomic>
+#include <stdlib.h>
+#include <type_traits>
 #include "pxf_internal.h"
 #include "pxf_params.h"
 
@@ -291,8 +293,13 @@ struct OpSpoCone {
     static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_spocone(r, p); }
 };
-template <int NMAX, bool OPD>
+// MINB: minimum resident CTAs per SM the register allocation is capped for; SCALAR: one ray per thread even
+// on aligned rows (the unrolled Zernike evaluation needs ~200 registers per ray: two rays per thread leave
+// 8 warps per SM to cover the fp64 latency)
+template <int NMAX, bool OPD, int MINB_ = 1, bool SCALAR_ = false>
 struct OpZern {
+    static constexpr int MINB = MINB_;
+    static constexpr bool SCALAR = SCALAR_;
     using Params = ZernP;
     static constexpr unsigned LOAD = R_POS | R_DIR | (OPD ? R_OPD : 0u);
     static constexpr unsigned STORE = R_POS | R_NRM | (OPD ? R_OPD : 0u);
@@ -327,8 +334,13 @@ struct OpLL {
 };
 
 // ------------------------------------------------------------------ the kernel
+template <class Op, class = void> struct OpMinB { static constexpr int v = 1; };
+template <class Op> struct OpMinB<Op, std::void_t<decltype(Op::MINB)>> { static constexpr int v = Op::MINB; };
+template <class Op, class = void> struct OpScalar { static constexpr bool v = false; };
+template <class Op> struct OpScalar<Op, std::void_t<decltype(Op::SCALAR)>> { static constexpr bool v = Op::SCALAR; };
+
 template <class Op, bool MASKED, bool VEC2>
-__global__ void __launch_bounds__(PXF_BLOCK)
+__global__ void __launch_bounds__(PXF_BLOCK, OpMinB<Op>::v)
 k_op(const RowPtrs P, const int64_t num, const uint8_t *__restrict__ mask,
      const double *__restrict__ aux0, const double *__restrict__ aux1,
      const __grid_constant__ typename Op::Params prm)
@@ -423,6 +435,10 @@ static int launch_op(RowPtrs P, int64_t num, const uint8_t *mask, const double *
     if (Op::AUX >= 1 && !aux0) { set_error("null per-ray argument"); return PXF_ERR_INVALID; }
     if (Op::AUX >= 2 && !aux1) { set_error("null per-ray argument"); return PXF_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if constexpr (OpScalar<Op>::v) {
+        if (mask) return launch3<Op, true, false>(P, num, mask, aux0, aux1, prm, s);
+        return launch3<Op, false, false>(P, num, mask, aux0, aux1, prm, s);
+    }
     if (mask) {
         if (aligned) return launch3<Op, true, true>(P, num, mask, aux0, aux1, prm, s);
         return launch3<Op, true, false>(P, num, mask, aux0, aux1, prm, s);
@@ -443,6 +459,8 @@ static RowPtrs rows9(double *x, double *y, double *z, double *l, double *m, doub
 template <bool OPD>
 static int launch_zern(RowPtrs P, int64_t num, const uint8_t *mask, const ZernP &z, pxf_stream_t stream)
 {
+    // (measured, profiles/r01h_notes.md: two rays per thread at ~240 registers = 8 warps/SM runs 3.69 ms per 5e7
+    // rays; one ray per thread capped for 1/2/3 CTAs per SM 4.12/3.99/4.03 ms -- the evaluation is issue bound)
     if (z.nmax <= 7) return launch_op<OpZern<7, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
     if (z.nmax <= 11) return launch_op<OpZern<11, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
     return launch_op<OpZern<15, OPD>>(P, num, mask, nullptr, nullptr, z, stream);

@@ -465,10 +465,10 @@ int pxf_cumsum_gather(const double *w, const int64_t *idx, int64_t num, double *
 }
 
 // analyses.hpd weighted branch (analyses.py:88-94): r,cdf = rhocdf(...); r[argmin|cdf-.75|]-r[argmin|cdf-.25|]
-int pxf_hpd_weighted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
+int pxf_hpd_weighted_sorted(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
                      pxf_stream_t stream)
 {
-    if (num <= 0 || !x || !y || !w || !hpd_host) { set_error("pxf_hpd_weighted: bad argument"); return PXF_ERR_INVALID; }
+    if (num <= 0 || !x || !y || !w || !hpd_host) { set_error("pxf_hpd_weighted_sorted: bad argument"); return PXF_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int rc;
     const size_t n = (size_t)num;
@@ -505,7 +505,7 @@ int pxf_hpd_weighted(const double *x, const double *y, const double *w, int64_t 
     k_cdf_argmin<<<grid, SORT_THREADS, 0, s>>>(cdf, num, small, .75, .25, am);
     k_hpdw_result<<<1, 32, 0, s>>>(am, grid, rs, small + 4);
     count_launch(4);
-    if ((rc = check_launch("pxf_hpd_weighted"))) return rc;
+    if ((rc = check_launch("pxf_hpd_weighted_sorted"))) return rc;
     double r[3];
     PXF_CUDA(cudaMemcpyAsync(r, small + 4, sizeof(r), cudaMemcpyDeviceToHost, s));
     PXF_CUDA(cudaStreamSynchronize(s));

@@ -555,6 +555,72 @@ def test_weighted_hpd_and_sort(pxf):
     assert (ii[1:][same] > ii[:-1][same]).all()
 
 
+def _hpd_weighted_c(pxf, dev, w, which):
+    """Call one of the weighted-HPD entry points directly; returns (hpd, valid)."""
+    import ctypes
+    import torch
+    from pyxfocus_b200 import _lib
+    x, y = dev[1:3]
+    wt = torch.as_tensor(w, dtype=torch.float64, device=x.device).contiguous()
+    out = ctypes.c_double(float("nan"))
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    if which == "bracket":
+        valid = ctypes.c_int32(-1)
+        _lib.check(L.pxf_hpd_weighted_bracket(x.data_ptr(), y.data_ptr(), wt.data_ptr(), x.shape[0], ctypes.byref(out),
+                                              ctypes.byref(valid), st))
+        return out.value, valid.value
+    _lib.check(L.pxf_hpd_weighted_sorted(x.data_ptr(), y.data_ptr(), wt.data_ptr(), x.shape[0], ctypes.byref(out), st))
+    return out.value, 1
+
+
+@pytest.mark.parametrize("n", [1 << 21, 3_000_001])
+def test_weighted_hpd_bracketed_path(pxf, n):
+    """Large bundles take the bracketed weighted-quantile path (pxf_wquant.cu): same number as numpy's
+    argsort -> cumsum -> argmin (analyses.py:73-97) and as the library's own full sort."""
+    rng = np.random.default_rng(136)
+    cpu = random_bundle(n, 136)
+    for w in (rng.uniform(.1, 2., n),                                   # mild weights
+              np.where(rng.random(n) < .01, 50., 1.) * rng.random(n),   # heavy tail, zeros possible
+              np.ones(n)):                                              # equal weights
+        dev = to_dev(cpu)
+        want = pyref.hpd(cpu, weights=w)
+        got, valid = _hpd_weighted_c(pxf, dev, w, "bracket")
+        assert valid == 1
+        assert got == pytest.approx(want, rel=1e-9)
+        full, _ = _hpd_weighted_c(pxf, dev, w, "sorted")
+        assert got == full                                              # same radii picked
+        assert pxf.analyses.hpd(dev, weights=w) == got
+
+
+def test_weighted_hpd_bracket_falls_back(pxf):
+    """Inputs the bracketed path refuses (negative weight, NaN radius) report valid == 0 and the public
+    call still returns what the full sort returns."""
+    n = 1 << 21
+    rng = np.random.default_rng(137)
+    cpu = random_bundle(n, 137)
+    w = rng.uniform(.1, 2., n)
+    w[12345] = -1.
+    dev = to_dev(cpu)
+    _, valid = _hpd_weighted_c(pxf, dev, w, "bracket")
+    assert valid == 0
+    full, _ = _hpd_weighted_c(pxf, dev, w, "sorted")
+    assert pxf.analyses.hpd(dev, weights=w) == full
+    assert full == pytest.approx(pyref.hpd(cpu, weights=w), rel=1e-9)
+    w[12345] = 1.
+    cpu[1][777] = np.nan
+    dev = to_dev(cpu)
+    _, valid = _hpd_weighted_c(pxf, dev, w, "bracket")
+    assert valid == 0
+    # a degenerate bundle (every radius equal): brackets collapse, capacity overflows -> fallback, same answer
+    cpu = random_bundle(n, 138)
+    cpu[1][:] = 3.
+    cpu[2][:] = 4.
+    dev = to_dev(cpu)
+    w = rng.uniform(.1, 2., n)
+    assert pxf.analyses.hpd(dev, weights=w) == pytest.approx(pyref.hpd(cpu, weights=w), abs=1e-12)
+
+
 def test_image_plane_and_focus(pxf, golden):
     g = golden("ws_offaxis")
     cpu = rows_of(g["after_secondary"])
