@@ -48,6 +48,14 @@ int pxf_version(void);
 const char *pxf_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t pxf_launch_count(void);
+/* Process-wide options.
+ *   PXF_OPT_WS_LIBM (default 0): 1 = evaluate the Wolter-Schwarzschild surfaces (wsprimary/wssecondary and the
+ *   back surfaces) with the reference's own libm call sequence (asin/atan2/sincos/tan/pow per Newton step)
+ *   instead of the algebraically identical transcendental-free form (half-angle identities, exp(k log x)).
+ *   Both agree with the reference to 1e-12 on every converging ray; the libm form additionally reproduces the
+ *   discrete outcome (restored or not) of the chaotic rays beyond the graze angle ray for ray. */
+enum pxf_option { PXF_OPT_WS_LIBM = 1 };
+int pxf_set_option(int32_t option, int32_t value);
 /* Iteration cap applied to the reference's uncapped Newton loops (oracle uses the same). */
 int pxf_newton_cap(void);
 
@@ -277,6 +285,21 @@ int pxf_trace_program_sums(double *const rays_in[10], double *const rays_out[10]
                            const pxf_op *ops, int32_t nops, uint8_t *alive, double *sums_dev,
                            void *scratch, pxf_stream_t stream);
 
+/* Segmented programs (nested mirror assemblies, BASELINE config 5; the reference loops over shells in Python,
+ * examples/axro/axialHeights.py:215-322): the bundle is the concatenation of nseg segments
+ * [seg_start[s], seg_start[s+1]) and segment s runs ops[s*nops .. s*nops+nops) -- the same opcode sequence
+ * for every segment, its own scalars.  ONE launch for the whole bundle.
+ *   pxf_segmented_table_fill folds the scalars into a host table (pxf_segmented_table_bytes bytes; seg_start
+ *   has nseg+1 entries, seg_start[0] == 0); the caller uploads it unchanged to device memory and passes both
+ *   copies to pxf_trace_program_segmented (the host copy is read for the row masks only).
+ *   rays_out == NULL: in place. */
+size_t pxf_segmented_table_bytes(int32_t nops, int32_t nseg);
+int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t nseg, const int64_t *seg_start,
+                             void *table_host);
+int pxf_trace_program_segmented(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                                const void *table_host, const void *table_dev, uint8_t *alive,
+                                pxf_stream_t stream);
+
 /* ======================= vignetting / compaction ======================== */
 /* flags[i] = (l^2+m^2+n^2 > .1), the default predicate of transformations.vignette
  * (transformations.py:220-223; NaN compares false). */
@@ -491,6 +514,11 @@ int pxf_source(int32_t kind, double *const rays[10], int64_t num, int64_t first,
 int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, const double *u1,
                             const double *u2, double a, double b, double c, double d,
                             pxf_stream_t stream);
+/* One launch for a nested assembly: segment s of the bundle is drawn from source `kind` (0 subannulus,
+ * 1 circularbeam, 3 annulus) with params_dev[4*s..4*s+3] = (a,b,c,d); seg_start_dev: device int64[nseg+1].
+ * Same Philox stream as per-segment pxf_source calls with first + seg_start[s]. */
+int pxf_source_segmented(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+                         int32_t nseg, const int64_t *seg_start_dev, const double *params_dev, pxf_stream_t stream);
 
 /* ======================= host-buffer entry point ======================== */
 /* The call an f2py user makes (the reference's extension modules take HOST numpy arrays and

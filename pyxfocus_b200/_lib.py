@@ -36,6 +36,7 @@ SIGNATURES = {
     "pxf_version": (_c.c_int, []),
     "pxf_last_error": (_c.c_char_p, []),
     "pxf_launch_count": (_i64, []),
+    "pxf_set_option": (_c.c_int, [_i32, _i32]),
     "pxf_newton_cap": (_c.c_int, []),
     # transformationsf
     "pxf_transform": (_c.c_int, _NINE + [_i64] + [_d] * 6 + [_vp, _st]),
@@ -148,6 +149,10 @@ SIGNATURES = {
     "pxf_cumsum_gather": (_c.c_int, [_dp, _vp, _i64, _dp, _vp, _st]),
     # sources
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
+    "pxf_source_segmented": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _i32, _vp, _dp, _st]),
+    "pxf_segmented_table_bytes": (_sz, [_i32, _i32]),
+    "pxf_segmented_table_fill": (_c.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "pxf_trace_program_segmented": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _st]),
     "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
     # host-buffer entry point
     "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -178,6 +183,14 @@ def check(rc):
     if rc != 0:
         msg = lib().pxf_last_error()
         raise PxfError("libpxf error %d: %s" % (rc, msg.decode() if msg else ""))
+
+
+OPT_WS_LIBM = 1
+
+
+def set_option(option, value):
+    """Process-wide library option (include/pxf.h, enum pxf_option)."""
+    check(lib().pxf_set_option(int(option), int(value)))
 
 
 def launch_count():

@@ -118,6 +118,62 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
     if (partials) centroid_block_reduce(cnt, sx, sy, partials);
 }
 
+// ---------------------------------------------------------------- segmented execution
+// Nested assemblies (BASELINE config 5; examples/axro/axialHeights.py:215-322, SMARTX.py:163-259): the bundle
+// is a concatenation of segments (one mirror shell each) and every segment runs the SAME opcode sequence with
+// its own folded scalars.  The reference loops over shells in Python; one launch per shell is launch bound at
+// 260 shells (measured 12 ms of launches for 1e7 rays).  Here one persistent grid walks the bundle in tiles of
+// SEG_TILE consecutive rays; a CTA stages the op table of the segment its tile lies in into shared memory
+// (re-staged only when the segment changes; a tile that straddles segments is processed piecewise).
+#define SEG_TILE (PXF_BLOCK * 8)
+struct SegHeader { unsigned load_mask, store_mask; int nops, nseg; };
+
+template <int MINB>
+__global__ void __launch_bounds__(PXF_BLOCK, MINB)
+k_program_seg(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
+              const long long *__restrict__ seg_start, const FusedOp *__restrict__ ops, const int nops, const int nseg,
+              const unsigned LM, const unsigned SM)
+{
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    FusedOp *sops = reinterpret_cast<FusedOp *>(seg_smem);
+    int staged = -1;
+    const int words = nops * (int)(sizeof(FusedOp) / 8);
+    for (int64_t t0 = (int64_t)blockIdx.x * SEG_TILE; t0 < num; t0 += (int64_t)gridDim.x * SEG_TILE) {
+        const int64_t t1 = t0 + SEG_TILE < num ? t0 + SEG_TILE : num;
+        int lo = 0, hi = nseg - 1;                     // last segment starting at or before t0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+        }
+        int seg = lo;
+        int64_t pos = t0;
+        while (pos < t1 && seg < nseg) {
+            int64_t send = seg_start[seg + 1];
+            if (send <= pos) { seg++; continue; }      // empty segment
+            if (send > t1) send = t1;
+            if (seg != staged) {                       // block-uniform
+                __syncthreads();
+                const double *src = reinterpret_cast<const double *>(ops + (int64_t)seg * nops);
+                double *dst = reinterpret_cast<double *>(sops);
+                for (int t = threadIdx.x; t < words; t += blockDim.x) dst[t] = src[t];
+                __syncthreads();
+                staged = seg;
+            }
+            for (int64_t i = pos + threadIdx.x; i < send; i += blockDim.x) {
+                Ray a;
+                fload1(a, P, LM, i);
+                bool keep = true;
+                for (int k = 0; k < nops; k++)
+                    if (!run_op(a, sops[k])) { keep = false; break; }
+                fstore1(a, Q, SM, i);
+                if (alive) alive[i] = keep ? 1 : 0;
+            }
+            pos = send;
+            seg++;
+        }
+    }
+}
+
 // rows read (use) / possibly written (st) / unconditionally overwritten (kill) by each op
 static void op_masks(int code, int row, unsigned &use, unsigned &st, unsigned &kill)
 {
@@ -251,10 +307,11 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         int rc = launch_chain(P, Q, num, fp, alive, aligned, s, partials, grid_out);
         if (rc != PXF_ERR_UNSUPPORTED) return rc;
     }
-    // PXF_PROGRAM_VARIANT (tuning): 0 = two rays per thread (double2 rows), 3/4 = one ray per thread with
-    // the register allocation capped for 3 / 4 resident CTAs per SM
+    // PXF_PROGRAM_VARIANT (tuning): 0 = two rays per thread (double2 rows), 1/3/4 = one ray per thread with
+    // the register allocation capped for 1 / 3 / 4 resident CTAs per SM.  Measured on config 3's 12-op tail at
+    // 5e7 rays (profiles/r01h_notes.md): 3.82 / 3.75 / 3.27 / 3.00 ms for 0 / 1 / 3 / 4.
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("PXF_PROGRAM_VARIANT"); variant = e ? atoi(e) : 3; }
+    if (variant < 0) { const char *e = getenv("PXF_PROGRAM_VARIANT"); variant = e ? atoi(e) : 4; }
     auto go = [&](auto kern, int64_t items) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PXF_BLOCK, 0) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
@@ -263,9 +320,9 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
     };
     if (aligned && variant == 0) go(k_program<true, 1>, (num + 1) >> 1);
-    else if (variant == 4) go(k_program<false, 4>, num);
+    else if (variant == 3) go(k_program<false, 3>, num);
     else if (variant == 1) go(k_program<false, 1>, num);
-    else go(k_program<false, 3>, num);
+    else go(k_program<false, 4>, num);
     count_launch();
     return check_launch("k_program");
 }
@@ -294,6 +351,90 @@ extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const ray
     // bundle, so every row the program touches is stored
     fp.store_mask |= fp.load_mask;
     return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out, nullptr, nullptr);
+}
+
+// ---- segmented programs -------------------------------------------------------------------------
+static size_t seg_align(size_t v) { return (v + 15) & ~(size_t)15; }
+static size_t seg_ops_offset(int nseg) { return seg_align(sizeof(SegHeader)) + seg_align((size_t)(nseg + 1) * 8); }
+
+extern "C" size_t pxf_segmented_table_bytes(int32_t nops, int32_t nseg)
+{
+    if (nops < 1 || nseg < 1) return 0;
+    return seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp);
+}
+
+extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t nseg, const int64_t *seg_start,
+                                        void *table_host)
+{
+    if (!ops || !seg_start || !table_host || nops < 1 || nops > PXF_MAX_OPS || nseg < 1) {
+        set_error("pxf_segmented_table_fill: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    if (seg_start[0] != 0) { set_error("segmented program: seg_start[0] must be 0"); return PXF_ERR_INVALID; }
+    for (int sgm = 0; sgm < nseg; sgm++)
+        if (seg_start[sgm + 1] < seg_start[sgm]) { set_error("segmented program: seg_start must be non-decreasing"); return PXF_ERR_INVALID; }
+    char *base = static_cast<char *>(table_host);
+    SegHeader *h = reinterpret_cast<SegHeader *>(base);
+    memset(h, 0, seg_align(sizeof(SegHeader)));
+    memcpy(base + seg_align(sizeof(SegHeader)), seg_start, (size_t)(nseg + 1) * 8);
+    FusedOp *dst = reinterpret_cast<FusedOp *>(base + seg_ops_offset(nseg));
+    h->nops = nops; h->nseg = nseg;
+    for (int sgm = 0; sgm < nseg; sgm++) {
+        FusedProgram fp;
+        int rc = build_program(fp, ops + (size_t)sgm * nops, nops);
+        if (rc) return rc;
+        if (sgm > 0)
+            for (int k = 0; k < nops; k++)
+                if (fp.ops[k].code != dst[k].code || fp.ops[k].row != dst[k].row) {   // dst[0..nops) = segment 0
+                    set_error("segmented program: every segment must run the same opcode sequence (segment %d, op %d)", sgm, k);
+                    return PXF_ERR_INVALID;
+                }
+        h->load_mask |= fp.load_mask;
+        h->store_mask |= fp.store_mask;
+        memcpy(dst + (size_t)sgm * nops, fp.ops, (size_t)nops * sizeof(FusedOp));
+    }
+    return PXF_OK;
+}
+
+extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                                           const void *table_host, const void *table_dev, uint8_t *alive,
+                                           pxf_stream_t stream)
+{
+    if (!rays_in || !table_host || !table_dev || num < 0) { set_error("pxf_trace_program_segmented: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    const SegHeader *h = static_cast<const SegHeader *>(table_host);
+    const int nops = h->nops, nseg = h->nseg;
+    const int64_t *hs = reinterpret_cast<const int64_t *>(static_cast<const char *>(table_host) + seg_align(sizeof(SegHeader)));
+    if (nops < 1 || nops > PXF_MAX_OPS || nseg < 1 || hs[nseg] != num) {
+        set_error("segmented program: table does not describe a bundle of %lld rays", (long long)num);
+        return PXF_ERR_INVALID;
+    }
+    if (num == 0) return PXF_OK;
+    unsigned LM = h->load_mask, SM = h->store_mask;
+    if (rays_out) SM |= LM;
+    RowPtrs P, Q;
+    for (int k = 0; k < 10; k++) {
+        P.p[k] = rays_in[k];
+        Q.p[k] = rays_out ? rays_out[k] : rays_in[k];
+        if ((LM & (1u << k)) && !P.p[k]) { set_error("segmented program: null input row pointer (row %d)", k); return PXF_ERR_INVALID; }
+        if ((SM & (1u << k)) && !Q.p[k]) { set_error("segmented program: null output row pointer (row %d)", k); return PXF_ERR_INVALID; }
+    }
+    const FusedOp *hops = reinterpret_cast<const FusedOp *>(static_cast<const char *>(table_host) + seg_ops_offset(nseg));
+    bool vig = false;
+    for (int k = 0; k < nops; k++)
+        if (hops[k].code == PXF_OP_VIGNETTE_MAG || hops[k].code == PXF_OP_VIGNETTE_BOX || hops[k].code == PXF_OP_VIGNETTE_ABS) vig = true;
+    if (vig && !alive) { set_error("program with a VIGNETTE op needs an alive array"); return PXF_ERR_INVALID; }
+    const char *db = static_cast<const char *>(table_dev);
+    const long long *dstart = reinterpret_cast<const long long *>(db + seg_align(sizeof(SegHeader)));
+    const FusedOp *dops = reinterpret_cast<const FusedOp *>(db + seg_ops_offset(nseg));
+    const size_t smem = (size_t)nops * sizeof(FusedOp);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program_seg<4>, PXF_BLOCK, smem) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
+    const int grid = grid_for(num, SEG_TILE, nb);
+    k_program_seg<4><<<grid, PXF_BLOCK, smem, s>>>(P, Q, num, alive, dstart, dops, nops, nseg, LM, SM);
+    count_launch();
+    return check_launch("k_program_seg");
 }
 
 // pxf_analysis.cu

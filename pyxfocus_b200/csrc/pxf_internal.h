@@ -13,6 +13,7 @@ namespace pxf {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+int opt_ws_libm();      // PXF_OPT_WS_LIBM
 
 // Persistent grid: SM count x resident CTAs, capped by the work available.
 int grid_for(int64_t work_items, int per_block, int ctas_per_sm);

@@ -24,6 +24,8 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int> g_ws_libm{0};
+int opt_ws_libm() { return g_ws_libm.load(std::memory_order_relaxed); }
 int sm_count()
 {
     if (g_sms == 0) {
@@ -48,6 +50,19 @@ int grid_for(int64_t work_items, int per_block, int ctas_per_sm)
 int Scratch::alloc(size_t bytes, cudaStream_t stream)
 {
     s = stream;
+    // The default pool gives its memory back to the driver at every synchronisation (release threshold 0), so
+    // each convenience call would re-map its scratch: measured 3-30 ms per analysis call at 1e7 rays.  Keep it.
+    static bool pooled[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pooled[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pooled[dev] = true;
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, stream);
     if (e != cudaSuccess) {
         p = nullptr;
@@ -490,6 +505,12 @@ extern "C" {
 int pxf_version(void) { return 100; }
 const char *pxf_last_error(void) { return g_err; }
 int64_t pxf_launch_count(void) { return g_launches.load(); }
+int pxf_set_option(int32_t option, int32_t value)
+{
+    if (option == PXF_OPT_WS_LIBM) { g_ws_libm.store(value ? 1 : 0); return PXF_OK; }
+    set_error("pxf_set_option: unknown option %d", option);
+    return PXF_ERR_INVALID;
+}
 int pxf_newton_cap(void) { return PXF_NEWTON_CAP; }
 
 int pxf_transform(double *x, double *y, double *z, double *l, double *m, double *n,

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <string.h>
 #include "pxf_ray.cuh"
+#include "pxf_internal.h"
 
 namespace pxf {
 
@@ -119,6 +120,14 @@ inline WSP make_ws(double alpha, double z0, double psi, double thick = 0.)
     p.tanbs = tan(betas);
     p.twootan = 2. / tan(betas);
     p.kp1 = k + 1;
+    p.fast = (!opt_ws_libm() && k > 0. && k < .25) ? 1. : 0.;
+    p.tanhbs = tan(betas / 2);
+    p.iff = 1 / ff;
+    p.idenF = 1 / p.denF;
+    p.idenFb = 1 / p.denFb;
+    p.c1 = 1 / (p.omcbs * ff);
+    p.c2 = 1 / p.twog;
+    p.c3 = p.kp1 / g / k;
     return p;
 }
 

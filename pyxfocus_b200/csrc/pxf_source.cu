@@ -87,6 +87,46 @@ k_source(const RowPtrs P, int64_t num, int64_t first, unsigned long long seed,
     }
 }
 
+// One launch for a nested assembly: segment s = rays [seg_start[s], seg_start[s+1]) drawn from the source
+// `kind` with its own parameters params[4*s .. 4*s+3] = (a,b,c,d).  Counter = first + global ray index, so the
+// stream is the same as per-segment launches with first = seg_start[s].
+#define SRC_TILE (PXF_BLOCK * 8)
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_source_seg(const RowPtrs P, int64_t num, int64_t first, unsigned long long seed, int kind,
+             const long long *__restrict__ seg_start, const double *__restrict__ params, int nseg, double pi)
+{
+    for (int64_t t0 = (int64_t)blockIdx.x * SRC_TILE; t0 < num; t0 += (int64_t)gridDim.x * SRC_TILE) {
+        const int64_t t1 = t0 + SRC_TILE < num ? t0 + SRC_TILE : num;
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+        }
+        int seg = lo;
+        int64_t pos = t0;
+        while (pos < t1 && seg < nseg) {
+            int64_t send = seg_start[seg + 1];
+            if (send <= pos) { seg++; continue; }
+            if (send > t1) send = t1;
+            SourceP p;
+            p.kind = kind; p.pi = pi;
+            p.a = params[4 * seg]; p.b = params[4 * seg + 1]; p.c = params[4 * seg + 2]; p.d = params[4 * seg + 3];
+            for (int64_t i = pos + threadIdx.x; i < send; i += blockDim.x) {
+                unsigned long long g = (unsigned long long)(first + i);
+                u32x4 o = philox4x32_10((unsigned)g, (unsigned)(g >> 32), 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32));
+                Ray r;
+                make_ray(r, p, u53(o.a, o.b), u53(o.c, o.d));
+                if (P.p[0]) P.p[0][i] = r.opd;
+                P.p[1][i] = r.x; P.p[2][i] = r.y; P.p[3][i] = r.z;
+                P.p[4][i] = r.l; P.p[5][i] = r.m; P.p[6][i] = r.n;
+                P.p[7][i] = r.ux; P.p[8][i] = r.uy; P.p[9][i] = r.uz;
+            }
+            pos = send;
+            seg++;
+        }
+    }
+}
+
 static int source_launch(int kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
                          const double *u1, const double *u2, bool philox, double a, double b, double c, double d,
                          cudaStream_t s)
@@ -122,6 +162,27 @@ int pxf_source(int32_t kind, double *const rays[10], int64_t num, int64_t first,
 {
     return source_launch(kind, rays, num, first, seed, nullptr, nullptr, true, a, b, c, d,
                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pxf_source_segmented(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+                         int32_t nseg, const int64_t *seg_start_dev, const double *params_dev, pxf_stream_t stream)
+{
+    if (num < 0 || !rays || kind < 0 || kind > 3 || kind == 2 || nseg < 1 || !seg_start_dev || !params_dev) {
+        set_error("pxf_source_segmented: bad argument (pointsource is not supported: its sin(ang) is folded per call)");
+        return PXF_ERR_INVALID;
+    }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    RowPtrs P;
+    for (int k = 0; k < 10; k++) {
+        P.p[k] = rays[k];
+        if (k > 0 && !rays[k]) { set_error("pxf_source_segmented: null row"); return PXF_ERR_INVALID; }
+    }
+    if (num == 0) return PXF_OK;
+    const int grid = grid_for(num, SRC_TILE, 8);
+    k_source_seg<<<grid, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        P, num, first, seed, kind, reinterpret_cast<const long long *>(seg_start_dev), params_dev, nseg, 3.141592653589793);
+    count_launch();
+    return check_launch("k_source_seg");
 }
 
 int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, const double *u1,

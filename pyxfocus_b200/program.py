@@ -180,6 +180,72 @@ class Program:
         return alive
 
 
+class SegmentedProgram:
+    """One launch for a bundle made of segments that run the same routines with different scalars -- a nested
+    mirror assembly, one shell per segment (the reference loops over shells in Python,
+    examples/axro/axialHeights.py:215-322, SMARTX.py:163-259)::
+
+        progs = [Program().transform(0, 0, z0[k], 0, 0, 0).wolterprimary(r0[k], z0[k], 1.).reflect() ... for k]
+        seg = SegmentedProgram(progs, sizes)      # sizes[k] = rays of shell k, concatenated in this order
+        seg.run(bundle)
+
+    The per-segment op tables are folded once on the host and uploaded once; ``run`` is a single kernel."""
+
+    def __init__(self, programs, sizes, device=None):
+        import numpy as np
+        if len(programs) != len(sizes) or not programs:
+            raise ValueError("one program per segment")
+        nops = len(programs[0])
+        if nops < 1 or nops > MAX_OPS:
+            raise ValueError("segmented programs carry 1..%d ops" % MAX_OPS)
+        for p in programs:
+            if [c for c, _ in p.ops] != [c for c, _ in programs[0].ops]:
+                raise ValueError("every segment must run the same routine sequence")
+        self.nseg, self.nops = len(programs), nops
+        self.has_vignette = programs[0].has_vignette()
+        start = np.zeros(self.nseg + 1, dtype=np.int64)
+        start[1:] = np.cumsum(np.asarray(sizes, dtype=np.int64))
+        self.seg_start = start
+        self.num = int(start[-1])
+        arr = (_lib.pxf_op * (self.nseg * nops))()
+        for sgm, prog in enumerate(programs):
+            for k, (code, p) in enumerate(prog.ops):
+                o = arr[sgm * nops + k]
+                o.code = code
+                for j, v in enumerate(p):
+                    o.p[j] = v
+        L = _lib.lib()
+        nbytes = int(L.pxf_segmented_table_bytes(nops, self.nseg))
+        self.table_host = torch.empty(nbytes, dtype=torch.uint8)
+        _lib.check(L.pxf_segmented_table_fill(arr, nops, self.nseg, start.ctypes.data, self.table_host.data_ptr()))
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.table_dev = self.table_host.to(dev)
+        self.seg_start_dev = torch.from_numpy(start).to(dev)
+
+    def run(self, rays, alive=None, out=None):
+        dev = rays[1].device
+        num = rays[1].shape[0]
+        if num != self.num:
+            raise ValueError("bundle has %d rays, the segments add up to %d" % (num, self.num))
+        if dev != self.table_dev.device:
+            raise ValueError("segment table lives on %s, rays on %s" % (self.table_dev.device, dev))
+        for r in rays:
+            if r is not None and (not r.is_cuda or r.dtype != torch.float64 or not r.is_contiguous()
+                                  or r.shape[0] != num):
+                raise ValueError("ray rows must be contiguous 1-D float64 CUDA tensors of equal length")
+        if self.has_vignette and alive is None:
+            alive = torch.empty(num, dtype=torch.uint8, device=dev)
+        ptrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in rays])
+        optrs = None
+        if out is not None:
+            optrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in out])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pxf_trace_program_segmented(
+                ptrs, optrs, num, self.table_host.data_ptr(), self.table_dev.data_ptr(),
+                alive.data_ptr() if alive is not None else None, stream_ptr(dev)))
+        return alive
+
+
 # ------------------------------------------------------------------ transparent recording
 _active = {}     # id(rays list) -> (rays, Program)
 

@@ -35,10 +35,18 @@ def _device(device):
     return torch.device(device)
 
 
-def _make(kind, num, a, b, c, d, rng, seed, first, device, uniforms=None):
+def _make(kind, num, a, b, c, d, rng, seed, first, device, uniforms=None, out=None):
     num = int(num)
-    dev = _device(device)
-    rays = bundle_alloc(num, dev)
+    if out is not None:
+        # generate into an existing bundle (e.g. one shell's segment of a nested assembly)
+        rays = out
+        dev = rays[1].device
+        for r in rays:
+            if not r.is_cuda or r.dtype != torch.float64 or not r.is_contiguous() or r.shape[0] != num:
+                raise ValueError("out must be ten contiguous float64 CUDA rows of length num")
+    else:
+        dev = _device(device)
+        rays = bundle_alloc(num, dev)
     ptrs = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
     L = _lib.lib()
     with torch.cuda.device(dev):
@@ -62,25 +70,57 @@ def _make(kind, num, a, b, c, d, rng, seed, first, device, uniforms=None):
     return rays
 
 
-def pointsource(ang, num, rng="numpy", seed=0, first=0, device=None, uniforms=None):
+def pointsource(ang, num, rng="numpy", seed=0, first=0, device=None, uniforms=None, out=None):
     """Point source with half-angle ``ang``; rays point in +z (sources.py:20-53)."""
-    return _make("pointsource", num, float(ang), 0., 0., 0., rng, seed, first, device, uniforms)
+    return _make("pointsource", num, float(ang), 0., 0., 0., rng, seed, first, device, uniforms, out)
 
 
-def circularbeam(rad, num, rng="numpy", seed=0, first=0, device=None, uniforms=None):
+def circularbeam(rad, num, rng="numpy", seed=0, first=0, device=None, uniforms=None, out=None):
     """Uniform circular beam of radius ``rad``, rays in +z (sources.py:56-88)."""
-    return _make("circularbeam", num, float(rad), 0., 0., 0., rng, seed, first, device, uniforms)
+    return _make("circularbeam", num, float(rad), 0., 0., 0., rng, seed, first, device, uniforms, out)
 
 
-def annulus(rin, rout, num, zhat=-1., rng="numpy", seed=0, first=0, device=None, uniforms=None):
+def annulus(rin, rout, num, zhat=-1., rng="numpy", seed=0, first=0, device=None, uniforms=None, out=None):
     """Annulus of rays (sources.py:91-127)."""
-    return _make("annulus", num, float(rin), float(rout), 0., float(zhat), rng, seed, first, device, uniforms)
+    return _make("annulus", num, float(rin), float(rout), 0., float(zhat), rng, seed, first, device, uniforms, out)
 
 
-def subannulus(rin, rout, dphi, num, zhat=1., rng="numpy", seed=0, first=0, device=None, uniforms=None):
+def subannulus(rin, rout, dphi, num, zhat=1., rng="numpy", seed=0, first=0, device=None, uniforms=None, out=None):
     """Sub-apertured annulus centred on theta=0 (+x) (sources.py:130-170)."""
     return _make("subannulus", num, float(rin), float(rout), float(dphi), float(zhat), rng, seed, first, device,
-                 uniforms)
+                 uniforms, out)
+
+
+def segments(kind, params, sizes, seed=0, first=0, device=None, out=None):
+    """A nested assembly's source in ONE launch: segment k holds ``sizes[k]`` rays of source ``kind``
+    ('subannulus' (rin, rout, dphi, zhat), 'annulus' (rin, rout, 0, zhat) or 'circularbeam' (rad, 0, 0, 0)) with
+    parameters ``params[k]``; device Philox stream, identical to per-segment calls with
+    ``first + sum(sizes[:k])``.  Returns the bundle (``bundle_split(bundle, sizes)`` gives per-segment views)."""
+    if kind not in ("subannulus", "annulus", "circularbeam"):
+        raise ValueError("segments: kind must be subannulus, annulus or circularbeam")
+    sizes = [int(v) for v in sizes]
+    total = sum(sizes)
+    par = np.zeros((len(sizes), 4), dtype=np.float64)
+    for k, p in enumerate(params):
+        par[k, :len(p)] = p
+    start = np.zeros(len(sizes) + 1, dtype=np.int64)
+    start[1:] = np.cumsum(sizes)
+    if out is not None:
+        rays, dev = out, out[1].device
+        if rays[1].shape[0] != total:
+            raise ValueError("out has %d rays, the segments add up to %d" % (rays[1].shape[0], total))
+    else:
+        dev = _device(device)
+        rays = bundle_alloc(total, dev)
+    ptrs = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
+    with torch.cuda.device(dev):
+        st = torch.from_numpy(start).to(dev)
+        pr = torch.from_numpy(par).to(dev)
+        _lib.check(_lib.lib().pxf_source_segmented(_KIND[kind], ptrs, total, int(first), int(seed) & (2 ** 64 - 1),
+                                                   len(sizes), st.data_ptr(), pr.data_ptr(), stream_ptr(dev)))
+        st.record_stream(torch.cuda.current_stream(dev))
+        pr.record_stream(torch.cuda.current_stream(dev))
+    return rays
 
 
 def from_numpy(rays, device=None):
