@@ -12,9 +12,11 @@ Tracing needs no communication (rays are independent).  Only the reductions do
 
 * weighted HPD (analyses.py:88-97 with weights): every rank sorts its own radii (the library's
   radix sort) and prefix-sums its weights in that order; the global weighted quantile is then a
-  bisection over the 64-bit key space -- per step each rank looks up "my weight at or below this
-  key" in its sorted shard and the scalar is all-reduced -- i.e. a merge of the per-rank sorted
-  runs that never moves a ray (63 latency-bound all-reduces of one double per quantile).
+  64-ary search over the 64-bit key space -- per step each rank looks up "my weight at or below this
+  key" for 63 pivots per quantile in its sorted shard and one [2, 63] all-reduce merges them -- i.e. a
+  merge of the per-rank sorted runs that never moves a ray (11 latency-bound all-reduces).  Large bundles
+  do not even sort the shard: a gathered sample brackets the two crossings, one pass collects the ~1 % of
+  (radius, weight) pairs inside, and only those windows are sorted and merged (``hpd_weighted_bracketed``).
 
 Collectives go through ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the
 CPU tests of the host logic).  With ``group=None`` and no initialised process group the
@@ -392,60 +394,211 @@ class CudaWeighted:
         self.device = dev
 
 
-def _weight_at_or_below(loc, key, strict=False):
-    """Sum of this shard's weights whose radius key is <= key (< key when strict); 0-d tensor."""
-    n = loc.keys.shape[0]
-    if n == 0:
-        return torch.zeros((), dtype=torch.float64, device=loc.device)
-    cnt = torch.searchsorted(loc.keys, key.reshape(1), right=not strict)[0]
-    val = loc.cum[torch.clamp(cnt - 1, min=0)]
+def _weight_at_or_below(keys, cum, key, strict=False):
+    """Weight of this shard's sorted (keys, cum) run at or below each entry of ``key`` (below when strict)."""
+    if keys.shape[0] == 0:
+        return torch.zeros(key.shape, dtype=torch.float64, device=key.device)
+    cnt = torch.searchsorted(keys, key.reshape(-1), right=not strict).reshape(key.shape)
+    val = cum[torch.clamp(cnt - 1, min=0)]
     return torch.where(cnt > 0, val, torch.zeros_like(val))
 
 
-def _largest_key_below(loc, key):
-    """Largest radius key of this shard that is < key, or -1."""
-    n = loc.keys.shape[0]
-    if n == 0:
-        return torch.full((), -1, dtype=torch.int64, device=loc.device)
-    cnt = torch.searchsorted(loc.keys, key.reshape(1), right=False)[0]
-    val = loc.keys[torch.clamp(cnt - 1, min=0)]
+def _largest_key_below(keys, key):
+    """Largest key of this shard's sorted run that is < key (0-d), or -1."""
+    if keys.shape[0] == 0:
+        return torch.full((), -1, dtype=torch.int64, device=key.device)
+    cnt = torch.searchsorted(keys, key.reshape(1), right=False)[0]
+    val = keys[torch.clamp(cnt - 1, min=0)]
     return torch.where(cnt > 0, val, torch.full_like(val, -1))
 
 
-def weighted_quantile_radius(loc, q, total_weight, group=None):
-    """Radius r[argmin |cdf - q|] of the GLOBAL sorted (radius, weight) sequence, cdf = cumulative
-    weight / total (first minimum, as numpy's argmin): the smallest key whose global cumulative
-    weight reaches q*W, or its predecessor when that one is at least as close.  Everything stays on
-    the device; identical on every rank."""
-    dev = loc.device
-    lo = torch.zeros((), dtype=torch.int64, device=dev)                         # invariant: answer in [lo, hi]
-    hi = torch.full((), 0x7ff0000000000000, dtype=torch.int64, device=dev)      # +Inf pattern
-    for _ in range(63):
-        mid = lo + (hi - lo) // 2
-        c = all_reduce_sum(_weight_at_or_below(loc, mid), group) / total_weight
-        ge = c >= q
-        hi = torch.where(ge, mid, hi)
-        lo = torch.where(ge, lo, mid + 1)
+_KARY = 63          # pivots per step: 11 steps of one [2, 63] all-reduce resolve the 63-bit key space
+_KARY_STEPS = 11
+
+
+def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None):
+    """For each quantile q = qs[i]: the radius r[argmin |cdf - q|] of the GLOBAL sorted (radius, weight) sequence
+    formed by every rank's sorted run ``runs[i] = (keys, cum)`` (cdf = (offsets[i] + cumulative weight) / total;
+    first minimum, as numpy's argmin): the smallest key whose global cumulative weight reaches q*W, or its
+    predecessor when that one is at least as close.  A (K+1)-ary search over the 64-bit key space: per step
+    every rank looks up "my weight at or below this key" for K pivots per quantile in its sorted run and ONE
+    [len(qs), K] all-reduce merges them -- the rays never move.  Everything stays on the device and is
+    identical on every rank.  Returns (radii [len(qs)] float64, valid [len(qs)] bool): valid is False when no key
+    of the runs reaches q, or when the predecessor would lie outside the runs although weight lies below them
+    (``offsets[i]`` > 0) -- the bracketed caller then falls back to the full sort."""
+    dev = runs[0][0].device
+    nq = len(qs)
+    q = torch.tensor(list(qs), dtype=torch.float64, device=dev)
+    off = torch.zeros(nq, dtype=torch.float64, device=dev) if offsets is None else offsets.to(torch.float64)
+    lo = torch.zeros(nq, dtype=torch.int64, device=dev)                              # invariant: answer in [lo, hi]
+    hi = torch.full((nq,), 0x7ff0000000000000, dtype=torch.int64, device=dev)        # +Inf pattern
+    jj = torch.arange(1, _KARY + 1, dtype=torch.int64, device=dev)                   # j+1
+
+    def cdf_at(keys2d, strict=False):
+        loc = torch.stack([_weight_at_or_below(runs[i][0], runs[i][1], keys2d[i], strict) for i in range(nq)])
+        return (all_reduce_sum(loc, group) + off.reshape(nq, 1)) / total_weight
+
+    for _ in range(_KARY_STEPS):
+        n = hi - lo + 1
+        step, rem = n // (_KARY + 1), n % (_KARY + 1)
+        piv = lo.reshape(nq, 1) + jj * step.reshape(nq, 1) + torch.minimum(jj.expand(nq, _KARY), rem.reshape(nq, 1)) - 1
+        piv = torch.minimum(piv, hi.reshape(nq, 1))
+        ge = cdf_at(piv) >= q.reshape(nq, 1)
+        anyge = ge.any(dim=1)
+        first = torch.argmax(ge.to(torch.int8), dim=1)                               # first pivot reaching q
+        pj = torch.gather(piv, 1, first.reshape(nq, 1)).reshape(nq)
+        pprev = torch.gather(piv, 1, torch.clamp(first - 1, min=0).reshape(nq, 1)).reshape(nq)
+        new_hi = torch.where(anyge, pj, hi)
+        new_lo = torch.where(anyge, torch.where(first > 0, pprev + 1, lo), piv[:, -1] + 1)
+        lo, hi = torch.minimum(new_lo, new_hi), new_hi
     k_hi = hi
-    c_hi = all_reduce_sum(_weight_at_or_below(loc, k_hi), group) / total_weight
-    k_lo = _largest_key_below(loc, k_hi)
+    c_hi = cdf_at(k_hi.reshape(nq, 1)).reshape(nq)
+    k_lo = torch.stack([_largest_key_below(runs[i][0], k_hi[i]) for i in range(nq)])
     if _world(group) > 1:
         td.all_reduce(k_lo, op=td.ReduceOp.MAX, group=group)
-    c_lo = all_reduce_sum(_weight_at_or_below(loc, k_hi, strict=True), group) / total_weight
+    c_lo = cdf_at(k_hi.reshape(nq, 1), strict=True).reshape(nq)
     take_lo = (k_lo >= 0) & (torch.abs(c_lo - q) <= torch.abs(c_hi - q))
     key = torch.where(take_lo, k_lo, k_hi)
-    return key.view(torch.float64)
+    valid = (c_hi >= q) & ((k_lo >= 0) | (off == 0.))
+    return key.view(torch.float64), valid
 
 
-def hpd_weighted(rays, weights, group=None, local_cls=CudaWeighted):
+def weighted_quantile_radius(loc, q, total_weight, group=None):
+    """One quantile of the full sorted runs (``loc.keys``, ``loc.cum``); see ``weighted_quantile_radii``."""
+    r, _ = weighted_quantile_radii([(loc.keys, loc.cum)], [q], total_weight, group)
+    return r[0]
+
+
+class CudaWeightedBracket:
+    """Local half of the bracketed weighted quantile (libpxf pxf_wq_* kernels, pxf_wquant.cu): strided
+    (radius, weight) sample, brackets from the gathered sample, one collect pass, sorted candidate windows.
+    The gloo tests replace it with a numpy stand-in of the same interface."""
+
+    def __init__(self, rays, weights, cx, cy):
+        x, y = rays[1:3]
+        self.x, self.y = x, y
+        self.device = x.device
+        self.num = x.shape[0]
+        self.w = torch.as_tensor(weights, dtype=torch.float64, device=x.device).contiguous()
+        self.cxy = torch.tensor([cx, cy], dtype=torch.float64, device=x.device)
+        self.L = _lib.lib()
+        self.state = torch.zeros(int(self.L.pxf_wq_state_bytes()) // 8, dtype=torch.float64, device=x.device)
+
+    def params(self, total):
+        return int(self.L.pxf_wq_min_num()), int(self.L.pxf_wq_samples(int(total)))
+
+    def sample(self, nsamp):
+        """[2, nsamp]: radii and weights of a strided sample, weights scaled by rays-per-sample so that samples
+        of differently sized shards combine into one unbiased weighted cdf; padded with (+Inf, 0)."""
+        out = torch.empty(2, nsamp, dtype=torch.float64, device=self.device)
+        out[0].fill_(float("inf"))
+        out[1].zero_()
+        take = min(nsamp, self.num)
+        if take > 0:
+            with torch.cuda.device(self.device):
+                _lib.check(self.L.pxf_wq_sample(self.x.data_ptr(), self.y.data_ptr(), self.w.data_ptr(), self.num,
+                                                self.cxy.data_ptr(), take, out[0].data_ptr(), out[1].data_ptr(),
+                                                stream_ptr(self.device)))
+            out[1, :take].mul_(self.num / take)
+        return out
+
+    def _sorted(self, r, w):
+        from . import analyses
+        n = r.shape[0]
+        rs, idx = analyses.argsort(r)
+        cum = torch.empty_like(r)
+        with torch.cuda.device(self.device):
+            scratch = torch.empty(int(self.L.pxf_scan_scratch_bytes(n)), dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.pxf_cumsum_gather(w.data_ptr(), idx.data_ptr(), n, cum.data_ptr(), scratch.data_ptr(),
+                                                stream_ptr(self.device)))
+        return rs, cum
+
+    def set_brackets(self, gathered):
+        """gathered: [world, 2, nsamp] samples of every rank (identical everywhere) -> brackets in the state."""
+        r = gathered[:, 0, :].reshape(-1).contiguous()
+        w = gathered[:, 1, :].reshape(-1).contiguous()
+        rs, cum = self._sorted(r, w)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.pxf_wq_brackets(rs.data_ptr(), cum.data_ptr(), rs.shape[0], self.state.data_ptr(),
+                                              stream_ptr(self.device)))
+
+    def collect(self, cap):
+        """One pass over the shard.  Returns float64[5]: weight below bracket 0 / 1, candidates in bracket
+        0 / 1 beyond the capacity (0 = fits), rays the bracketed path refuses (NaN radius, NaN/negative weight)."""
+        dev = self.device
+        self.cand = torch.empty(4, max(cap, 1), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            scratch = torch.empty(int(self.L.pxf_wq_collect_scratch_bytes()), dtype=torch.uint8, device=dev)
+            _lib.check(self.L.pxf_wq_collect(self.x.data_ptr(), self.y.data_ptr(), self.w.data_ptr(), self.num,
+                                             self.cxy.data_ptr(), self.state.data_ptr(), self.cand[0].data_ptr(),
+                                             self.cand[1].data_ptr(), self.cand[2].data_ptr(), self.cand[3].data_ptr(),
+                                             cap, scratch.data_ptr(), stream_ptr(dev)))
+        cnt = self.state[6:9].view(torch.int64)                   # count[0], count[1], nbad
+        self.counts = cnt[:2]
+        self.cap = cap
+        over = torch.clamp(cnt[:2] - cap, min=0).to(torch.float64)
+        return torch.cat([self.state[4:6], over, cnt[2:3].to(torch.float64)])
+
+    def windows(self):
+        """[(keys, cum)] x 2: this shard's candidates of each bracket, sorted, with prefix weights."""
+        n0, n1 = (int(v) for v in self.counts.cpu())
+        out = []
+        for b, n in ((0, n0), (1, n1)):
+            n = min(n, self.cap)
+            if n == 0:
+                out.append((torch.empty(0, dtype=torch.int64, device=self.device),
+                            torch.empty(0, dtype=torch.float64, device=self.device)))
+                continue
+            rs, cum = self._sorted(self.cand[2 * b, :n].contiguous(), self.cand[2 * b + 1, :n].contiguous())
+            out.append((rs.view(torch.int64), cum))
+        return out
+
+
+def hpd_weighted_bracketed(loc, total, total_weight, group=None):
+    """Bracketed weighted HPD of a sharded bundle (the multi-GPU form of pxf_hpd_weighted_bracket): returns
+    (hpd 0-d tensor, valid bool).  Collectives: one all-gather of the samples, one all-reduce of 5 doubles, then
+    the (K+1)-ary merge of the sorted candidate windows (11 all-reduces of [2, 63] doubles + 3 small ones)."""
+    world = _world(group)
+    dev = loc.device
+    _, nsamp = loc.params(total)
+    per = max(nsamp // world, 1024)
+    mine = loc.sample(per)
+    if world > 1:
+        flat = torch.empty(world * mine.numel(), dtype=torch.float64, device=dev)
+        td.all_gather_into_tensor(flat, mine.reshape(-1).contiguous(), group=group)
+        gathered = flat.reshape((world,) + tuple(mine.shape))
+    else:
+        gathered = mine.reshape((1,) + tuple(mine.shape))
+    loc.set_brackets(gathered)
+    cap = max(int(loc.num) // 8, 65536)
+    st = all_reduce_sum(loc.collect(cap), group)
+    below, bad = st[:2], st[2:]
+    runs = loc.windows()
+    r, valid = weighted_quantile_radii(runs, [.25, .75], total_weight, group, offsets=below)
+    ok = bool(valid.all().item()) and float(bad.sum().item()) == 0.
+    return r[1] - r[0], ok
+
+
+def hpd_weighted(rays, weights, group=None, local_cls=CudaWeighted, bracket_cls=CudaWeightedBracket):
     """Weighted HPD of a sharded bundle: r[argmin|cdf-.75|] - r[argmin|cdf-.25|] about the global
-    weighted centroid (analyses.py:88-97), identical on every rank."""
+    weighted centroid (analyses.py:88-97), identical on every rank.  Large bundles take the bracketed path
+    (no rank sorts more than the ~1 % of its rays next to the two crossings); small ones, or a bracket miss,
+    the full local sort."""
     flush(rays)
-    cx, cy = centroid(rays, weights, group)
+    dev = rays[1].device
+    s = all_reduce_sum(torch.cat([_sums(0, rays, weights, 0., 0.)[:3],
+                                  torch.tensor([float(rays[1].shape[0])], dtype=torch.float64, device=dev)]), group)
+    h = s.cpu().numpy()
+    cx, cy, total = float(h[1] / h[0]), float(h[2] / h[0]), int(round(h[3]))
+    if bracket_cls is not None:
+        br = bracket_cls(rays, weights, cx, cy)
+        if total >= br.params(total)[0]:
+            res, ok = hpd_weighted_bracketed(br, total, s[0], group)
+            if ok:
+                return float(res)
     loc = local_cls(rays, weights, cx, cy)
     n = loc.keys.shape[0]
     wl = loc.cum[n - 1].clone() if n > 0 else torch.zeros((), dtype=torch.float64, device=loc.device)
     W = all_reduce_sum(wl, group)
-    r75 = weighted_quantile_radius(loc, .75, W, group)
-    r25 = weighted_quantile_radius(loc, .25, W, group)
-    return float(r75 - r25)
+    r, _ = weighted_quantile_radii([(loc.keys, loc.cum)] * 2, [.25, .75], W, group)
+    return float(r[1] - r[0])

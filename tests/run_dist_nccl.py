@@ -44,13 +44,21 @@ def main():
         d1 = pxf.analyses.analyticImagePlane(whole)
         good = (abs(h - h1) <= 1e-9 * abs(h1) and abs(rms - r1) <= 1e-9 * r1 and abs(cx - c1[0]) <= 1e-15
                 and abs(cy - c1[1]) <= 1e-15 and abs(dz - d1) <= 1e-6 * max(1., abs(d1)))
-        if total < 1_000_000:
-            # weighted HPD: sorted shards merged by key-space bisection vs the single-GPU sort
-            ww = torch.linspace(.5, 2., total, dtype=torch.float64, device=dev)
-            hw = dist.hpd(shard, weights=ww[lo:hi])
-            hw1 = pxf.analyses.hpd(whole, weights=ww)
-            print("rank %d weighted hpd %.15e vs %.15e" % (rank, hw, hw1), flush=True)
-            good = good and abs(hw - hw1) <= 1e-9 * abs(hw1)
+        # weighted HPD: small = sorted shards merged by the 64-ary key-space search; large = gathered sample
+        # brackets + candidate windows (no rank sorts its shard) -- both vs the single-GPU result
+        ww = torch.linspace(.5, 2., total, dtype=torch.float64, device=dev)
+        hw = dist.hpd(shard, weights=ww[lo:hi])
+        hw1 = pxf.analyses.hpd(whole, weights=ww)
+        print("rank %d weighted hpd %.15e vs %.15e" % (rank, hw, hw1), flush=True)
+        good = good and abs(hw - hw1) <= 1e-9 * abs(hw1)
+        if total > 1_000_000:
+            from pyxfocus_b200 import dist as D
+            cxw, cyw = D.centroid(shard, ww[lo:hi])
+            br = D.CudaWeightedBracket(shard, ww[lo:hi], cxw, cyw)
+            W = D.all_reduce_sum(ww[lo:hi].sum())
+            res, okb = D.hpd_weighted_bracketed(br, total, W)
+            print("rank %d bracketed weighted hpd %.15e valid %s" % (rank, float(res), okb), flush=True)
+            good = good and okb and abs(float(res) - hw1) <= 1e-9 * abs(hw1)
         print("rank %d total %d: hpd %.15e vs %.15e rms %.6e/%.6e dz %.6e/%.6e -> %s" % (rank, total, h, h1, rms, r1, dz, d1, good),
               flush=True)
         ok = ok and good

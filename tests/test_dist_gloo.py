@@ -345,3 +345,152 @@ def test_sharded_weighted_hpd_over_gloo(world, n):
     want75 = r[ind][np.argmin(np.abs(cdf - .75))]
     want25 = r[ind][np.argmin(np.abs(cdf - .25))]
     assert out[0][1] == want75 and out[0][2] == want25   # analyses.py:88-97, bit for bit
+
+
+# ---------------------------------------------------------------- bracketed weighted HPD (pxf_wquant.cu logic)
+class NumpyWeightedBracket:
+    """CPU stand-in for dist.CudaWeightedBracket: same interface, numpy restatement of the pxf_wq_* kernels
+    (k_wq_sample, k_wq_brackets, k_wq_collect) so that the sharded driver runs over gloo."""
+    Z = 6.0
+
+    def __init__(self, x, y, w, cx, cy, nsamp_total):
+        self.r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+        self.w = w
+        self.num = x.shape[0]
+        self.device = torch.device("cpu")
+        self.nsamp_total = nsamp_total
+
+    def params(self, total):
+        return 0, self.nsamp_total
+
+    def sample(self, nsamp):
+        out = np.zeros((2, nsamp))
+        out[0] = np.inf
+        take = min(nsamp, self.num)
+        if take:
+            idx = (np.arange(take, dtype=np.uint64) * np.uint64(self.num)) // np.uint64(take)
+            out[0, :take] = self.r[idx.astype(np.int64)]
+            out[1, :take] = self.w[idx.astype(np.int64)] * (self.num / take)
+        return torch.from_numpy(out)
+
+    def set_brackets(self, gathered):
+        g = gathered.numpy()
+        r, w = g[:, 0, :].reshape(-1), g[:, 1, :].reshape(-1)
+        idx = np.argsort(r, kind="stable")
+        rs, cum = r[idx], np.cumsum(w[idx])
+        n, W = rs.shape[0], cum[-1]
+        wi = np.diff(cum, prepend=0.)
+        design = max(n * float((wi * wi).sum()) / (W * W), 1.)
+        self.lohi = []
+        for q in (.25, .75):
+            delta = self.Z * np.sqrt(q * (1 - q) * design / n) + 2. / n
+            lo, hi = 0., np.inf
+            if q - delta > 0:
+                p = int(np.searchsorted(cum, (q - delta) * W, side="left"))
+                lo = rs[p - 1] if p > 0 else 0.
+            if q + delta < 1:
+                p = int(np.searchsorted(cum, (q + delta) * W, side="left"))
+                hi = rs[p + 1] if p + 1 < n else np.inf
+            self.lohi.append((lo, hi))
+
+    def collect(self, cap):
+        out = np.zeros(5)
+        self.win = []
+        for b, (lo, hi) in enumerate(self.lohi):
+            out[b] = self.w[self.r < lo].sum()
+            inside = (self.r >= lo) & (self.r <= hi)
+            out[2 + b] = max(int(inside.sum()) - cap, 0)
+            self.win.append((self.r[inside], self.w[inside]))
+        out[4] = int(np.isnan(self.r).sum() + (~(self.w >= 0)).sum())
+        return torch.from_numpy(out)
+
+    def windows(self):
+        res = []
+        for r, w in self.win:
+            idx = np.argsort(r, kind="stable")
+            res.append((torch.from_numpy(np.ascontiguousarray(r[idx]).view(np.int64).copy()),
+                        torch.from_numpy(np.cumsum(w[idx]))))
+        return res
+
+
+def _bracket_worker(rank, world, port, n, seed, nsamp, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from pyxfocus_b200 import dist
+    x, y, w = _weighted_bundle(n, seed)
+    lo, hi = dist.shard_range(n, rank, world)
+    if rank == world - 1 and world == 3:
+        lo = hi                                          # an EMPTY shard
+    xs, ys, ws = x[lo:hi], y[lo:hi], w[lo:hi]
+    s = torch.tensor([ws.sum(), (ws * xs).sum(), (ws * ys).sum(), float(hi - lo)], dtype=torch.float64)
+    dist.all_reduce_sum(s)
+    cx, cy = float(s[1] / s[0]), float(s[2] / s[0])
+    loc = NumpyWeightedBracket(xs, ys, ws, cx, cy, nsamp)
+    res, ok = dist.hpd_weighted_bracketed(loc, int(s[3]), s[0])
+    q.put((rank, float(res), ok, cx, cy, lo, hi))
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,nsamp", [(2, 200_001, 16384), (3, 90_000, 8192)])
+def test_sharded_bracketed_weighted_hpd_over_gloo(world, n, nsamp):
+    """dist.hpd_weighted_bracketed: gathered sample -> brackets -> local collect -> 64-ary merge of the sorted
+    candidate windows, over gloo at world 2 and 3 (one empty shard): same radii as numpy's full
+    argsort -> cumsum -> argmin on the whole bundle."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bracket_worker, args=(r, world, port, n, 654, nsamp, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, w = _weighted_bundle(n, 654)
+    covered = np.zeros(n, dtype=bool)
+    for rank, res, ok, cx, cy, lo, hi in out:
+        covered[lo:hi] = True
+        assert ok, "bracket reported a miss"
+        assert res == out[0][1], "ranks disagree"
+    x, y, w = x[covered], y[covered], w[covered]
+    cx, cy = out[0][3], out[0][4]
+    r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+    ind = np.argsort(r)
+    cdf = np.cumsum(w[ind])
+    cdf = cdf / cdf.max()
+    want = r[ind][np.argmin(np.abs(cdf - .75))] - r[ind][np.argmin(np.abs(cdf - .25))]
+    assert out[0][1] == pytest.approx(want, rel=1e-12)
+
+
+def test_kary_merge_matches_bisection_semantics():
+    """weighted_quantile_radii on one rank == numpy argmin semantics for random runs, including the
+    predecessor-is-closer case, an offset, and validity flags."""
+    from pyxfocus_b200 import dist
+    rng = np.random.default_rng(77)
+    for trial in range(20):
+        n = int(rng.integers(1, 400))
+        r = np.sort(rng.random(n))
+        w = rng.random(n) + .01
+        cum = np.cumsum(w)
+        off = float(rng.random() * 2.) if trial % 2 else 0.
+        W = off + cum[-1] + (float(rng.random()) if trial % 3 == 0 else 0.)
+        qs = [.25, .75]
+        runs = [(torch.from_numpy(r.view(np.int64).copy()), torch.from_numpy(cum))] * 2
+        got, valid = dist.weighted_quantile_radii(runs, qs, torch.tensor(W), offsets=torch.tensor([off, off]))
+        cdf = (off + cum) / W
+        for i, qq in enumerate(qs):
+            reach = np.nonzero(cdf >= qq)[0]
+            if reach.size == 0:
+                assert not bool(valid[i])
+                continue
+            j = int(reach[0])
+            if j == 0:
+                assert bool(valid[i]) == (off == 0.)
+                want = r[0]
+            else:
+                assert bool(valid[i])
+                want = r[j - 1] if abs(cdf[j - 1] - qq) <= abs(cdf[j] - qq) else r[j]
+            if bool(valid[i]):
+                assert float(got[i]) == want
