@@ -476,7 +476,10 @@ int32_t pxf_wq_samples(int64_t num);
 int64_t pxf_wq_capacity(int64_t num);
 int pxf_wq_sample(const double *x, const double *y, const double *w, int64_t num, const double *cxy_dev,
                   int32_t nsamp, double *rs_out, double *ws_out, pxf_stream_t stream);
-int pxf_wq_brackets(const double *rs_sorted, const double *cum, int32_t nsamp, void *state, pxf_stream_t stream);
+/* keybits: the sample is ordered by the top `keybits` bits of the radius patterns (64 = fully sorted; the
+ * single-GPU driver sorts the sample on 32); the brackets are widened by the unordered low bits. */
+int pxf_wq_brackets(const double *rs_sorted, const double *cum, int32_t nsamp, int32_t keybits, void *state,
+                    pxf_stream_t stream);
 size_t pxf_wq_collect_scratch_bytes(void);
 int pxf_wq_collect(const double *x, const double *y, const double *w, int64_t num, const double *cxy_dev, void *state,
                    double *cand_r0, double *cand_w0, double *cand_r1, double *cand_w1, int64_t cap, void *scratch,
@@ -493,6 +496,11 @@ int pxf_wq_argmin(const double *rs_sorted, const double *cum, int64_t n, const d
 size_t pxf_sort_scratch_bytes(int64_t num);
 int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
                 void *scratch, pxf_stream_t stream);
+/* Same, sorting only on the bytes of the 64-bit key whose bit is set in `digits` (bit 0 = least significant
+ * byte); 0 = detect the constant bytes with one histogram read-back (what pxf_argsort does).  With a mask
+ * nothing is read back: for keys from a known narrow range, or when a partial order is enough. */
+int pxf_argsort_digits(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
+                       void *scratch, int32_t digits, pxf_stream_t stream);
 /* out[i] = inclusive prefix sum of (w ? w[idx[i]] : 1.0)  (np.cumsum(weights[ind]),
  * analyses.py:83-85).  scratch: pxf_scan_scratch_bytes(num). */
 size_t pxf_scan_scratch_bytes(int64_t num);

@@ -137,7 +137,7 @@ SIGNATURES = {
     "pxf_wq_samples": (_i32, [_i64]),
     "pxf_wq_capacity": (_i64, [_i64]),
     "pxf_wq_sample": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _i32, _dp, _dp, _st]),
-    "pxf_wq_brackets": (_c.c_int, [_dp, _dp, _i32, _vp, _st]),
+    "pxf_wq_brackets": (_c.c_int, [_dp, _dp, _i32, _i32, _vp, _st]),
     "pxf_wq_collect_scratch_bytes": (_sz, []),
     "pxf_wq_collect": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _vp, _dp, _dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_wq_below_ptr": (_vp, [_vp, _i32]),
@@ -145,6 +145,7 @@ SIGNATURES = {
     "pxf_wq_argmin": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _d, _dp, _vp, _st]),
     "pxf_sort_scratch_bytes": (_sz, [_i64]),
     "pxf_argsort": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _st]),
+    "pxf_argsort_digits": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _i32, _st]),
     "pxf_scan_scratch_bytes": (_sz, [_i64]),
     "pxf_cumsum_gather": (_c.c_int, [_dp, _vp, _i64, _dp, _vp, _st]),
     # sources

@@ -82,52 +82,63 @@ k_sort_hist(const u64 *__restrict__ keys, Chunking ck, int shift, u32 *__restric
     table[(size_t)threadIdx.x * ck.G + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of the digit-major table (256*G entries) by one CTA, 64-bit carries
+// Exclusive scan of the digit-major table [256][G]: CTA d scans row d (G <= 1024 entries, one per thread) and
+// writes the row total; the scatter kernel adds the exclusive scan of the 256 row totals itself.  (A single CTA
+// chaining through all 256*G entries took 91 us per pass -- four times the histogram and scatter together.)
 __global__ void __launch_bounds__(1024)
-k_sort_scan(const u32 *__restrict__ table, int n, u64 *__restrict__ offs)
+k_sort_scan_rows(const u32 *__restrict__ table, int G, u64 *__restrict__ offs, u64 *__restrict__ dtot)
 {
     __shared__ u64 wsum[32];
-    __shared__ u64 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < n; b0 += blockDim.x) {
-        int b = b0 + threadIdx.x;
-        u64 v = b < n ? (u64)table[b] : 0ull;
+    const size_t row = (size_t)blockIdx.x * G;
+    const u64 v = (int)threadIdx.x < G ? (u64)table[row + threadIdx.x] : 0ull;
+    u64 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = wsum[lane], iw = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, iw, o);
+            if (lane >= o) iw += t;
+        }
+        wsum[lane] = iw - w;
+    }
+    __syncthreads();
+    const u64 excl = wsum[warp] + incl - v;
+    if ((int)threadIdx.x < G) offs[row + threadIdx.x] = excl;
+    if (threadIdx.x == 1023) dtot[blockIdx.x] = excl + v;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
+               u32 *__restrict__ vout, Chunking ck, int shift, const u64 *__restrict__ offs /*[256][G]*/,
+               const u64 *__restrict__ dtot /*[256]*/)
+{
+    __shared__ u64 run[256];                     // running global offset per digit for this chunk
+    __shared__ u32 whist[SORT_WARPS][256];       // per-warp digit counts inside the tile
+    __shared__ u64 dwarp[SORT_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        // digit base = exclusive scan of the 256 row totals (SORT_THREADS == 256: one digit per thread)
+        const u64 v = dtot[threadIdx.x];
         u64 incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u64 t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) wsum[warp] = incl;
+        if (lane == 31) dwarp[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            u64 w = wsum[lane], iw = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u64 t = __shfl_up_sync(0xffffffffu, iw, o);
-                if (lane >= o) iw += t;
-            }
-            wsum[lane] = iw - w;
-        }
-        __syncthreads();
-        u64 excl = carry + wsum[warp] + incl - v;
-        if (b < n) offs[b] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
+        u64 base = 0;
+        for (int q = 0; q < warp; q++) base += dwarp[q];
+        run[threadIdx.x] = base + incl - v + offs[(size_t)threadIdx.x * ck.G + blockIdx.x];
     }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
-               u32 *__restrict__ vout, Chunking ck, int shift, const u64 *__restrict__ offs /*[256][G]*/)
-{
-    __shared__ u64 run[256];                     // running global offset per digit for this chunk
-    __shared__ u32 whist[SORT_WARPS][256];       // per-warp digit counts inside the tile
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    run[threadIdx.x] = offs[(size_t)threadIdx.x * ck.G + blockIdx.x];
     const int64_t lo = (int64_t)blockIdx.x * ck.per;
     const int64_t hi = lo + ck.per < ck.num ? lo + ck.per : ck.num;
     for (int64_t t0 = lo; t0 < hi; t0 += SORT_TILE) {
@@ -219,14 +230,20 @@ k_scan_chunk_sums(const double *__restrict__ w, const long long *__restrict__ id
     }
 }
 
-__global__ void k_scan_chunk_offsets(double *__restrict__ csum, int G)
+__global__ void __launch_bounds__(1024) k_scan_chunk_offsets(double *__restrict__ csum, int G)
 {
-    // serial exclusive scan of <= 1024 chunk sums (left-to-right like np.cumsum)
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // serial exclusive scan of <= 1024 chunk sums (left-to-right like np.cumsum), staged through shared
+    // memory so that the one scanning thread does not chain G global-memory round trips
+    __shared__ double sh[SORT_MAXG + 1];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) sh[g] = csum[g];
+    __syncthreads();
+    if (threadIdx.x == 0) {
         double run = 0.;
-        for (int g = 0; g < G; g++) { double t = csum[g]; csum[g] = run; run += t; }
-        csum[G] = run;
+        for (int g = 0; g < G; g++) { double t = sh[g]; sh[g] = run; run += t; }
+        sh[G] = run;
     }
+    __syncthreads();
+    for (int g = threadIdx.x; g <= G; g += blockDim.x) csum[g] = sh[g];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -399,13 +416,16 @@ size_t pxf_sort_scratch_bytes(int64_t num)
 {
     size_t n = (size_t)(num > 0 ? num : 1);
     return 2 * align256(n * 8) + 2 * align256(n * 4) + align256((size_t)256 * SORT_MAXG * 4) +
-           align256((size_t)256 * SORT_MAXG * 8) + align256(8 * 256 * 8) + 1024;
+           align256((size_t)256 * SORT_MAXG * 8) + align256(9 * 256 * 8) + 1024;
 }
 
-int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
-                void *scratch, pxf_stream_t stream)
+// digits: bit d set = sort on byte d of the 64-bit key (LSD order).  0 = automatic: one up-front histogram of all
+// eight bytes is read back (host sync) and bytes that are constant over the array are skipped.  A caller that
+// knows which bytes can differ (e.g. keys from a narrow bracket) passes the mask and nothing is read back.
+int pxf_argsort_digits(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
+                       void *scratch, int32_t digits, pxf_stream_t stream)
 {
-    if (num < 0 || !keys_in || !scratch || num > 0xffffffffll) { set_error("pxf_argsort: bad argument"); return PXF_ERR_INVALID; }
+    if (num < 0 || !keys_in || !scratch || num > 0xffffffffll || digits < 0 || digits > 255) { set_error("pxf_argsort: bad argument"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     if (num == 0) return PXF_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -417,24 +437,30 @@ int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *i
     u32 *vB = (u32 *)p; p += align256(n * 4);
     u32 *table = (u32 *)p; p += align256((size_t)256 * SORT_MAXG * 4);
     u64 *offs = (u64 *)p; p += align256((size_t)256 * SORT_MAXG * 8);
-    u64 *ghist = (u64 *)p;
+    u64 *ghist = (u64 *)p;                 // [8][256] digit histogram, then [256] row totals of the current pass
+    u64 *dtot = ghist + 8 * 256;
     Chunking ck = make_chunking(num);
     PXF_CUDA(cudaMemsetAsync(ghist, 0, 8 * 256 * 8, s));
     k_sort_prepare<<<ck.G, SORT_THREADS, 0, s>>>(keys_in, kA, vA, ck, ghist);
     count_launch();
-    u64 hg[8 * 256];
-    PXF_CUDA(cudaMemcpyAsync(hg, ghist, sizeof(hg), cudaMemcpyDeviceToHost, s));
-    PXF_CUDA(cudaStreamSynchronize(s));
+    if (digits == 0) {
+        u64 hg[8 * 256];
+        PXF_CUDA(cudaMemcpyAsync(hg, ghist, sizeof(hg), cudaMemcpyDeviceToHost, s));
+        PXF_CUDA(cudaStreamSynchronize(s));
+        for (int d = 0; d < 8; d++) {
+            bool trivial = false;
+            for (int b = 0; b < 256; b++)
+                if (hg[d * 256 + b] == (u64)num) { trivial = true; break; }
+            if (!trivial) digits |= 1 << d;
+        }
+    }
     u64 *ki = kA, *ko = kB;
     u32 *vi = vA, *vo = vB;
     for (int d = 0; d < 8; d++) {
-        bool trivial = false;
-        for (int b = 0; b < 256; b++)
-            if (hg[d * 256 + b] == (u64)num) { trivial = true; break; }
-        if (trivial) continue;
+        if (!(digits & (1 << d))) continue;
         k_sort_hist<<<ck.G, SORT_THREADS, 0, s>>>(ki, ck, 8 * d, table);
-        k_sort_scan<<<1, 1024, 0, s>>>(table, 256 * ck.G, offs);
-        k_sort_scatter<<<ck.G, SORT_THREADS, 0, s>>>(ki, vi, ko, vo, ck, 8 * d, offs);
+        k_sort_scan_rows<<<256, 1024, 0, s>>>(table, ck.G, offs, dtot);
+        k_sort_scatter<<<ck.G, SORT_THREADS, 0, s>>>(ki, vi, ko, vo, ck, 8 * d, offs, dtot);
         count_launch(3);
         u64 *tk = ki; ki = ko; ko = tk;
         u32 *tv = vi; vi = vo; vo = tv;
@@ -443,6 +469,12 @@ int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *i
         ki, vi, num, keys_out, reinterpret_cast<long long *>(idx_out));
     count_launch();
     return check_launch("pxf_argsort");
+}
+
+int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
+                void *scratch, pxf_stream_t stream)
+{
+    return pxf_argsort_digits(keys_in, num, keys_out, idx_out, scratch, 0, stream);
 }
 
 size_t pxf_scan_scratch_bytes(int64_t num) { (void)num; return (size_t)(SORT_MAXG + 8) * 8; }
@@ -458,7 +490,7 @@ int pxf_cumsum_gather(const double *w, const int64_t *idx, int64_t num, double *
     double *csum = static_cast<double *>(scratch);
     const long long *ix = reinterpret_cast<const long long *>(idx);
     k_scan_chunk_sums<<<ck.G, SORT_THREADS, 0, s>>>(w, ix, ck, csum);
-    k_scan_chunk_offsets<<<1, 32, 0, s>>>(csum, ck.G);
+    k_scan_chunk_offsets<<<1, 1024, 0, s>>>(csum, ck.G);
     k_scan_apply<<<ck.G, SORT_THREADS, 0, s>>>(w, ix, ck, csum, out);
     count_launch(3);
     return check_launch("pxf_cumsum_gather");

@@ -18,6 +18,7 @@
 // minimum is next to the crossing).  Anything else -- bracket miss, buffer overflow, a negative or NaN
 // weight, a NaN radius -- clears `valid` and the caller runs the full sort.  Radii are bit-identical
 // to k_rho's; the cdf differs from a sequential np.cumsum only by summation order.
+#include <string.h>
 #include "pxf_internal.h"
 #include "pxf_ray.cuh"
 
@@ -63,11 +64,16 @@ PXF_DEV int wq_lower_bound(const double *cum, int n, double target)
 
 // One CTA.  rs: sorted sample radii, cum: inclusive prefix sums of the sample weights in that order.
 __global__ void __launch_bounds__(PXF_BLOCK)
-k_wq_brackets(const double *__restrict__ rs, const double *__restrict__ cum, int n, double z, WqState *__restrict__ st)
+k_wq_brackets(const double *__restrict__ rs, const double *__restrict__ cum, int n, double z, long long lowmask,
+              WqState *__restrict__ st)
 {
     __shared__ double sh[PXF_BLOCK / 32];
+    // Kish design factor n*sum(w^2)/W^2 from <= 16384 evenly spaced weights (it only sets the bracket width)
+    const int stride = n > 16384 ? n / 16384 : 1;
+    const int m = (n + stride - 1) / stride;
     double s2 = 0.;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int i = j * stride;
         const double wi = cum[i] - (i ? cum[i - 1] : 0.);
         s2 += wi * wi;
     }
@@ -78,6 +84,7 @@ k_wq_brackets(const double *__restrict__ rs, const double *__restrict__ cum, int
     if (threadIdx.x == 0) {
         double t = 0.;
         for (int q = 0; q < PXF_BLOCK / 32; q++) t += sh[q];
+        t *= (double)n / (double)m;
         const double W = cum[n - 1];
         double design = (double)n * t / (W * W);           // >= 1; 1 for equal weights
         if (!(design >= 1.)) design = 1.;                  // also catches NaN
@@ -90,10 +97,14 @@ k_wq_brackets(const double *__restrict__ rs, const double *__restrict__ cum, int
             if (q - delta > 0.) {
                 const int p = wq_lower_bound(cum, n, (q - delta) * W);
                 lo = p > 0 ? rs[p - 1] : 0.;
+                // the sample is ordered by the top `keybits` bits of the radius pattern only: round down
+                lo = __longlong_as_double(__double_as_longlong(lo) & ~lowmask);
             }
             if (q + delta < 1.) {
                 const int p = wq_lower_bound(cum, n, (q + delta) * W);
                 hi = p + 1 < n ? rs[p + 1] : inf;
+                if (hi < inf) hi = __longlong_as_double(__double_as_longlong(hi) | lowmask);   // ... and up
+                if (!(hi <= inf)) hi = inf;
             }
             if (!(lo == lo)) lo = 0.;
             if (!(hi == hi)) hi = inf;
@@ -279,11 +290,19 @@ __global__ void k_wq_result(const WqArg *__restrict__ partial, int nblk, const d
                             const double *__restrict__ cum, int64_t n, const double *__restrict__ below_ptr,
                             const double *__restrict__ total_ptr, double q, double *__restrict__ out)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    double v = partial[0].v;
-    long long i = partial[0].i;
-    for (int b = 1; b < nblk; b++)
+    // one warp
+    const int lane = threadIdx.x & 31;
+    double v = __longlong_as_double(0x7ff0000000000000ll);
+    long long i = 0x7fffffffffffffffll;
+    for (int b = lane; b < nblk; b += 32)
         if (wq_better(partial[b].v, partial[b].i, v, i)) { v = partial[b].v; i = partial[b].i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, i, o);
+        if (wq_better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+    if (lane) return;
     const double P = *below_ptr, W = *total_ptr;
     const double cfirst = (P + cum[0]) / W, clast = (P + cum[n - 1]) / W;
     const bool ok = i >= 0 && i < n && v == v && cfirst < q && clast > q && W > 0.;
@@ -326,10 +345,12 @@ int pxf_wq_sample(const double *x, const double *y, const double *w, int64_t num
     return check_launch("k_wq_sample");
 }
 
-int pxf_wq_brackets(const double *rs_sorted, const double *cum, int32_t nsamp, void *state, pxf_stream_t stream)
+int pxf_wq_brackets(const double *rs_sorted, const double *cum, int32_t nsamp, int32_t keybits, void *state,
+                    pxf_stream_t stream)
 {
-    if (nsamp <= 0 || !rs_sorted || !cum || !state) { set_error("pxf_wq_brackets: bad argument"); return PXF_ERR_INVALID; }
-    k_wq_brackets<<<1, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rs_sorted, cum, nsamp, WQ_Z,
+    if (nsamp <= 0 || !rs_sorted || !cum || !state || keybits < 16 || keybits > 64) { set_error("pxf_wq_brackets: bad argument"); return PXF_ERR_INVALID; }
+    const long long lowmask = keybits >= 64 ? 0ll : (long long)((~0ull) >> keybits);
+    k_wq_brackets<<<1, PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rs_sorted, cum, nsamp, WQ_Z, lowmask,
                                                                                static_cast<WqState *>(state));
     count_launch();
     return check_launch("k_wq_brackets");
@@ -437,9 +458,10 @@ int pxf_hpd_weighted_bracket(const double *x, const double *y, const double *w, 
     if ((rc = pxf_centroid_from_sums(sums, small, stream))) return rc;
     // 2. sample -> brackets
     if ((rc = pxf_wq_sample(x, y, w, num, small, nsamp, srs, sws, stream))) return rc;
-    if ((rc = pxf_argsort(srs, nsamp, sorted, idx, sort_scr, stream))) return rc;
+    // the sample only has to be ordered well enough for a bracket: sort on the top 32 bits of the pattern
+    if ((rc = pxf_argsort_digits(srs, nsamp, sorted, idx, sort_scr, 0xF0, stream))) return rc;
     if ((rc = pxf_cumsum_gather(sws, idx, nsamp, cum, scan_scr, stream))) return rc;
-    if ((rc = pxf_wq_brackets(sorted, cum, nsamp, state, stream))) return rc;
+    if ((rc = pxf_wq_brackets(sorted, cum, nsamp, 32, state, stream))) return rc;
     // 3. one pass over the bundle
     if ((rc = pxf_wq_collect(x, y, w, num, small, state, cand[0], cand[1], cand[2], cand[3], cap, col_scr, stream))) return rc;
     WqState h;
@@ -450,7 +472,15 @@ int pxf_hpd_weighted_bracket(const double *x, const double *y, const double *w, 
     const double qs[2] = {.25, .75};
     for (int b = 0; b < 2; b++) {
         const int64_t n = (int64_t)h.count[b];
-        if ((rc = pxf_argsort(cand[2 * b], n, sorted, idx, sort_scr, stream))) return rc;
+        // every candidate pattern lies in [lo, hi]: bytes above the highest differing bit are constant
+        unsigned long long klo, khi;
+        memcpy(&klo, &h.lohi[2 * b], 8);
+        memcpy(&khi, &h.lohi[2 * b + 1], 8);
+        int digits = 0;
+        for (int d = 0; d < 8; d++)
+            if (((klo ^ khi) >> (8 * d)) != 0) digits |= 1 << d;
+        if (digits == 0) digits = 1;
+        if ((rc = pxf_argsort_digits(cand[2 * b], n, sorted, idx, sort_scr, digits, stream))) return rc;
         if ((rc = pxf_cumsum_gather(cand[2 * b + 1], idx, n, cum, scan_scr, stream))) return rc;
         if ((rc = pxf_wq_argmin(sorted, cum, n, pxf_wq_below_ptr(state, b), sums, qs[b], small + 8 + 4 * b, am_scr, stream))) return rc;
     }

@@ -519,7 +519,7 @@ class CudaWeightedBracket:
         w = gathered[:, 1, :].reshape(-1).contiguous()
         rs, cum = self._sorted(r, w)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.pxf_wq_brackets(rs.data_ptr(), cum.data_ptr(), rs.shape[0], self.state.data_ptr(),
+            _lib.check(self.L.pxf_wq_brackets(rs.data_ptr(), cum.data_ptr(), rs.shape[0], 64, self.state.data_ptr(),
                                               stream_ptr(self.device)))
 
     def collect(self, cap):
