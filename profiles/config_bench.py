@@ -104,7 +104,7 @@ def config3(n, dev):
         with stage("fused tail (12 ops)"):
             alive = prog.run(rays)
         with stage("vignette (compaction)"):
-            surv = T.vignette(rays, ind=alive)
+            surv = T.compact(rays, alive)      # alive: uint8 flags from the program's vignette predicates
         with stage("hpd + rms"):
             res = dict(kept=surv[1].shape[0] / n, hpd=A.hpd(surv), rms=A.rmsCentroid(surv))
         return res

@@ -434,4 +434,92 @@ int launch_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const FusedPro
     return rc;
 }
 
+// ---- segmented specialised chain (nested assemblies) --------------------------------------------
+// Same tiling as k_program_seg (pxf_fused.cu) with the op list known at compile time: the per-segment
+// parameter pack ChainP (not an op table) is staged in shared memory and the chain runs straight-line.
+#define CSEG_TILE (PXF_BLOCK * 8)
+template <class C, class CP, int MINB>
+__global__ void __launch_bounds__(PXF_BLOCK, MINB)
+k_chain_seg(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
+            const long long *__restrict__ seg_start, const CP *__restrict__ table, const int nseg,
+            const unsigned LM, const unsigned SM)
+{
+    __shared__ __align__(16) CP sp;
+    static_assert(sizeof(CP) % 8 == 0, "parameter pack must be a whole number of doubles");
+    int staged = -1;
+    for (int64_t t0 = (int64_t)blockIdx.x * CSEG_TILE; t0 < num; t0 += (int64_t)gridDim.x * CSEG_TILE) {
+        const int64_t t1 = t0 + CSEG_TILE < num ? t0 + CSEG_TILE : num;
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+        }
+        int seg = lo;
+        int64_t pos = t0;
+        while (pos < t1 && seg < nseg) {
+            int64_t send = seg_start[seg + 1];
+            if (send <= pos) { seg++; continue; }
+            if (send > t1) send = t1;
+            if (seg != staged) {
+                __syncthreads();
+                const double *src = reinterpret_cast<const double *>(table + seg);
+                double *dst = reinterpret_cast<double *>(&sp);
+                for (int t = threadIdx.x; t < (int)(sizeof(CP) / 8); t += blockDim.x) dst[t] = src[t];
+                __syncthreads();
+                staged = seg;
+            }
+            for (int64_t i = pos + threadIdx.x; i < send; i += blockDim.x) {
+                Ray a;
+                fload1(a, P, LM, i);
+                const bool keep = C::run(a, sp);
+                fstore1(a, Q, SM, i);
+                if (alive) alive[i] = keep ? 1 : 0;
+            }
+            pos = send;
+            seg++;
+        }
+    }
+}
+
+using SegWolter = Chain<CTransform, CWolterPrimary, CReflect, CWolterSecondary, CReflect, CFlat>;
+using SegWolterP = ChainP<CTransform, CWolterPrimary, CReflect, CWolterSecondary, CReflect, CFlat>;
+
+size_t seg_chain_bytes(int nseg) { return (size_t)nseg * sizeof(SegWolterP); }
+
+// ops: segment-major folded op table.  Returns the chain id (1 = Wolter-I pair to the focal plane) after filling
+// dst with one parameter pack per segment, or 0 when no specialisation matches.
+int seg_chain_fill(const FusedOp *ops, int nops, int nseg, void *dst)
+{
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char *e = getenv("PXF_NO_SPECIALIZE");
+        disabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (disabled || nops != SegWolter::N || !SegWolter::match(ops, nops)) return 0;
+    SegWolterP *out = static_cast<SegWolterP *>(dst);
+    for (int sgm = 0; sgm < nseg; sgm++) {
+        memset(&out[sgm], 0, sizeof(SegWolterP));
+        SegWolter::fill(out[sgm], ops + (size_t)sgm * nops);
+    }
+    return 1;
+}
+
+int seg_chain_launch(int chain_id, const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8_t *alive,
+                     const long long *seg_start_dev, const void *table_dev, int nseg, unsigned LM, unsigned SM,
+                     cudaStream_t s)
+{
+    if (chain_id != 1) return PXF_ERR_UNSUPPORTED;
+    auto kern = k_chain_seg<SegWolter, SegWolterP, 3>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PXF_BLOCK, 0) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 3; }
+        ctas = nb;
+    }
+    const int grid = grid_for(num, CSEG_TILE, ctas);
+    kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, seg_start_dev, static_cast<const SegWolterP *>(table_dev), nseg, LM, SM);
+    count_launch();
+    return check_launch("k_chain_seg");
+}
+
 }  // namespace pxf

@@ -126,7 +126,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
 // SEG_TILE consecutive rays; a CTA stages the op table of the segment its tile lies in into shared memory
 // (re-staged only when the segment changes; a tile that straddles segments is processed piecewise).
 #define SEG_TILE (PXF_BLOCK * 8)
-struct SegHeader { unsigned load_mask, store_mask; int nops, nseg; };
+struct SegHeader { unsigned load_mask, store_mask; int nops, nseg; int chain_id, pad[3]; };
 
 template <int MINB>
 __global__ void __launch_bounds__(PXF_BLOCK, MINB)
@@ -360,8 +360,9 @@ static size_t seg_ops_offset(int nseg) { return seg_align(sizeof(SegHeader)) + s
 extern "C" size_t pxf_segmented_table_bytes(int32_t nops, int32_t nseg)
 {
     if (nops < 1 || nseg < 1) return 0;
-    return seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp);
+    return seg_align(seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp)) + seg_chain_bytes(nseg);
 }
+static size_t seg_chain_offset(int nops, int nseg) { return seg_align(seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp)); }
 
 extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t nseg, const int64_t *seg_start,
                                         void *table_host)
@@ -393,6 +394,8 @@ extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t
         h->store_mask |= fp.store_mask;
         memcpy(dst + (size_t)sgm * nops, fp.ops, (size_t)nops * sizeof(FusedOp));
     }
+    // a statically specialised kernel for the canonical chains: one parameter pack per segment behind the op table
+    h->chain_id = seg_chain_fill(dst, nops, nseg, base + seg_chain_offset(nops, nseg));
     return PXF_OK;
 }
 
@@ -429,6 +432,10 @@ extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *co
     const FusedOp *dops = reinterpret_cast<const FusedOp *>(db + seg_ops_offset(nseg));
     const size_t smem = (size_t)nops * sizeof(FusedOp);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (h->chain_id != 0 && !vig) {
+        int rc = seg_chain_launch(h->chain_id, P, Q, num, alive, dstart, db + seg_chain_offset(nops, nseg), nseg, LM, SM, s);
+        if (rc != PXF_ERR_UNSUPPORTED) return rc;
+    }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_program_seg<4>, PXF_BLOCK, smem) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 2; }
     const int grid = grid_for(num, SEG_TILE, nb);

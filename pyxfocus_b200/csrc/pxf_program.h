@@ -102,4 +102,11 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
 int launch_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const FusedProgram &fp, uint8_t *alive,
                  bool aligned, cudaStream_t s, double *partials, int *grid_out);
 
+// segmented specialised chains (pxf_chain.cu)
+size_t seg_chain_bytes(int nseg);
+int seg_chain_fill(const FusedOp *ops, int nops, int nseg, void *dst);
+int seg_chain_launch(int chain_id, const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8_t *alive,
+                     const long long *seg_start_dev, const void *table_dev, int nseg, unsigned LM, unsigned SM,
+                     cudaStream_t s);
+
 }  // namespace pxf

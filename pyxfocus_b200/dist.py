@@ -416,7 +416,7 @@ _KARY = 63          # pivots per step: 11 steps of one [2, 63] all-reduce resolv
 _KARY_STEPS = 11
 
 
-def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None):
+def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None, key_ranges=None):
     """For each quantile q = qs[i]: the radius r[argmin |cdf - q|] of the GLOBAL sorted (radius, weight) sequence
     formed by every rank's sorted run ``runs[i] = (keys, cum)`` (cdf = (offsets[i] + cumulative weight) / total;
     first minimum, as numpy's argmin): the smallest key whose global cumulative weight reaches q*W, or its
@@ -432,13 +432,22 @@ def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None):
     off = torch.zeros(nq, dtype=torch.float64, device=dev) if offsets is None else offsets.to(torch.float64)
     lo = torch.zeros(nq, dtype=torch.int64, device=dev)                              # invariant: answer in [lo, hi]
     hi = torch.full((nq,), 0x7ff0000000000000, dtype=torch.int64, device=dev)        # +Inf pattern
+    steps = _KARY_STEPS
+    if key_ranges is not None:
+        # every key of run i lies in key_ranges[i] (identical on every rank): a narrower space, fewer steps
+        lo = torch.tensor([max(int(a), 0) for a, _ in key_ranges], dtype=torch.int64, device=dev)
+        hi = torch.tensor([min(int(b), 0x7ff0000000000000) for _, b in key_ranges], dtype=torch.int64, device=dev)
+        width = max(max(int(b) - int(a) + 1, 1) for a, b in key_ranges)
+        steps = 1
+        while (_KARY + 1) ** steps < width:
+            steps += 1
     jj = torch.arange(1, _KARY + 1, dtype=torch.int64, device=dev)                   # j+1
 
     def cdf_at(keys2d, strict=False):
         loc = torch.stack([_weight_at_or_below(runs[i][0], runs[i][1], keys2d[i], strict) for i in range(nq)])
         return (all_reduce_sum(loc, group) + off.reshape(nq, 1)) / total_weight
 
-    for _ in range(_KARY_STEPS):
+    for _ in range(steps):
         n = hi - lo + 1
         step, rem = n // (_KARY + 1), n % (_KARY + 1)
         piv = lo.reshape(nq, 1) + jj * step.reshape(nq, 1) + torch.minimum(jj.expand(nq, _KARY), rem.reshape(nq, 1)) - 1
@@ -502,12 +511,16 @@ class CudaWeightedBracket:
             out[1, :take].mul_(self.num / take)
         return out
 
-    def _sorted(self, r, w):
-        from . import analyses
+    def _sorted(self, r, w, digits):
+        """(keys sorted on the bytes in ``digits``, prefix sums of the weights in that order); no read-back."""
         n = r.shape[0]
-        rs, idx = analyses.argsort(r)
+        rs = torch.empty_like(r)
+        idx = torch.empty(n, dtype=torch.int64, device=self.device)
         cum = torch.empty_like(r)
         with torch.cuda.device(self.device):
+            sscr = torch.empty(int(self.L.pxf_sort_scratch_bytes(n)), dtype=torch.uint8, device=self.device)
+            _lib.check(self.L.pxf_argsort_digits(r.data_ptr(), n, rs.data_ptr(), idx.data_ptr(), sscr.data_ptr(), digits,
+                                                 stream_ptr(self.device)))
             scratch = torch.empty(int(self.L.pxf_scan_scratch_bytes(n)), dtype=torch.uint8, device=self.device)
             _lib.check(self.L.pxf_cumsum_gather(w.data_ptr(), idx.data_ptr(), n, cum.data_ptr(), scratch.data_ptr(),
                                                 stream_ptr(self.device)))
@@ -517,9 +530,10 @@ class CudaWeightedBracket:
         """gathered: [world, 2, nsamp] samples of every rank (identical everywhere) -> brackets in the state."""
         r = gathered[:, 0, :].reshape(-1).contiguous()
         w = gathered[:, 1, :].reshape(-1).contiguous()
-        rs, cum = self._sorted(r, w)
+        # a bracket only needs the sample ordered on the top 32 bits of the radius pattern (pxf_wquant.cu)
+        rs, cum = self._sorted(r, w, 0xF0)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.pxf_wq_brackets(rs.data_ptr(), cum.data_ptr(), rs.shape[0], 64, self.state.data_ptr(),
+            _lib.check(self.L.pxf_wq_brackets(rs.data_ptr(), cum.data_ptr(), rs.shape[0], 32, self.state.data_ptr(),
                                               stream_ptr(self.device)))
 
     def collect(self, cap):
@@ -541,15 +555,20 @@ class CudaWeightedBracket:
 
     def windows(self):
         """[(keys, cum)] x 2: this shard's candidates of each bracket, sorted, with prefix weights."""
-        n0, n1 = (int(v) for v in self.counts.cpu())
+        host = self.state[:9].cpu()                               # one read-back: brackets and counts
+        n0, n1 = (int(v) for v in host[6:8].view(torch.int64))
+        pat = host[:4].view(torch.int64)
+        self.key_range = [(int(pat[0]), int(pat[1])), (int(pat[2]), int(pat[3]))]
         out = []
         for b, n in ((0, n0), (1, n1)):
             n = min(n, self.cap)
+            diff = self.key_range[b][0] ^ self.key_range[b][1]
+            digits = sum(1 << d for d in range(8) if (diff >> (8 * d)) != 0) or 1
             if n == 0:
                 out.append((torch.empty(0, dtype=torch.int64, device=self.device),
                             torch.empty(0, dtype=torch.float64, device=self.device)))
                 continue
-            rs, cum = self._sorted(self.cand[2 * b, :n].contiguous(), self.cand[2 * b + 1, :n].contiguous())
+            rs, cum = self._sorted(self.cand[2 * b, :n].contiguous(), self.cand[2 * b + 1, :n].contiguous(), digits)
             out.append((rs.view(torch.int64), cum))
         return out
 
@@ -574,7 +593,8 @@ def hpd_weighted_bracketed(loc, total, total_weight, group=None):
     st = all_reduce_sum(loc.collect(cap), group)
     below, bad = st[:2], st[2:]
     runs = loc.windows()
-    r, valid = weighted_quantile_radii(runs, [.25, .75], total_weight, group, offsets=below)
+    r, valid = weighted_quantile_radii(runs, [.25, .75], total_weight, group, offsets=below,
+                                       key_ranges=getattr(loc, "key_range", None))
     ok = bool(valid.all().item()) and float(bad.sum().item()) == 0.
     return r[1] - r[0], ok
 
@@ -586,6 +606,9 @@ def hpd_weighted(rays, weights, group=None, local_cls=CudaWeighted, bracket_cls=
     the full local sort."""
     flush(rays)
     dev = rays[1].device
+    if _world(group) == 1 and local_cls is CudaWeighted and bracket_cls is CudaWeightedBracket:
+        from . import analyses
+        return analyses.hpd(rays, weights=weights)
     s = all_reduce_sum(torch.cat([_sums(0, rays, weights, 0., 0.)[:3],
                                   torch.tensor([float(rays[1].shape[0])], dtype=torch.float64, device=dev)]), group)
     h = s.cpu().numpy()

@@ -906,6 +906,20 @@ def test_segmented_program_and_source_match_per_shell_launches(pxf):
     alive1 = sp.run(one)
     assert np.array_equal(alive1.cpu().numpy(), alive_ref.cpu().numpy())
     assert_bit_equal(to_host(one), want, rows=range(1, 10), what="segmented program (in place)")
+    # the canonical Wolter-I chain takes the statically specialised segmented kernel (k_chain_seg): same bits
+    def chain(r0, z0):
+        return (pxf.Program().transform(0, 0, z0, 0, 0, 0).wolterprimary(r0, z0, 1.).reflect()
+                .woltersecondary(r0, z0, 1.).reflect().flat())
+    one = pxf.sources.segments("annulus", [(r, r + .6, 0., -1.) for r in radii], sizes, seed=5, first=100)
+    ref = to_dev(to_host(one))
+    rsegs = bundle_split(ref, sizes)
+    for k, nk in enumerate(sizes):
+        if nk:
+            chain(radii[k], z0s[k]).run(rsegs[k])
+    before = pxf.launch_count()
+    pxf.SegmentedProgram([chain(r, z) for r, z in zip(radii, z0s)], sizes).run(one)
+    assert pxf.launch_count() - before == 1
+    assert_bit_equal(to_host(one), to_host(ref), rows=range(1, 10), what="segmented Wolter-I chain")
     with pytest.raises(ValueError):
         pxf.SegmentedProgram([prog(200., 9000.), pxf.Program().flat()], [4, 4])
     with pytest.raises(ValueError):
