@@ -488,6 +488,25 @@ double *pxf_wq_below_ptr(void *state, int32_t b);
 size_t pxf_wq_argmin_scratch_bytes(void);
 int pxf_wq_argmin(const double *rs_sorted, const double *cum, int64_t n, const double *below_dev, const double *total_dev,
                   double q, double *out_dev, void *scratch, pxf_stream_t stream);
+/* Sharded merge of sorted runs (two quantiles at once): each rank holds per quantile a sorted run of radius
+ * patterns (int64) with prefix weights.  state (pxf_wq_merge_state_bytes): int64 lo[2], hi[2], klo[2];
+ * double res[2], valid[2].  Per step: probe (this rank's weight at or below each of K pivots of [lo,hi] ->
+ * out_dev[2*K]), the caller all-reduces out_dev (sum), narrow (shrinks [lo,hi] by K+1).  When lo == hi:
+ * final_probe (out_dev[4] = weight at or below / strictly below hi per quantile; klo = largest local key
+ * below hi), the caller all-reduces out_dev (sum) and klo (max), finish -> res[i] = r[argmin|cdf-q_i|],
+ * valid[i].  offsets_dev (nullable): weight below the runs; total_dev: total weight. */
+size_t pxf_wq_merge_state_bytes(void);
+int64_t *pxf_wq_merge_klo_ptr(void *state);
+double *pxf_wq_merge_result_ptr(void *state);
+int pxf_wq_merge_begin(void *state, int64_t lo0, int64_t hi0, int64_t lo1, int64_t hi1, pxf_stream_t stream);
+int pxf_wq_merge_probe(const int64_t *keys0, const double *cum0, int64_t n0, const int64_t *keys1, const double *cum1,
+                       int64_t n1, const void *state, int32_t K, double *out_dev, pxf_stream_t stream);
+int pxf_wq_merge_narrow(void *state, const double *sum_dev, const double *offsets_dev, const double *total_dev,
+                        double q0, double q1, int32_t K, pxf_stream_t stream);
+int pxf_wq_merge_final_probe(const int64_t *keys0, const double *cum0, int64_t n0, const int64_t *keys1,
+                             const double *cum1, int64_t n1, void *state, double *out_dev, pxf_stream_t stream);
+int pxf_wq_merge_finish(void *state, const double *sum_dev, const double *offsets_dev, const double *total_dev,
+                        double q0, double q1, pxf_stream_t stream);
 
 /* Stable LSD radix sort of fp64 keys (ascending by IEEE total order of non-negative values;
  * negative keys and NaNs are ordered by their raw bit pattern after sign fix-up as in

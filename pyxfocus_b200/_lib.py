@@ -143,6 +143,14 @@ SIGNATURES = {
     "pxf_wq_below_ptr": (_vp, [_vp, _i32]),
     "pxf_wq_argmin_scratch_bytes": (_sz, []),
     "pxf_wq_argmin": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _d, _dp, _vp, _st]),
+    "pxf_wq_merge_state_bytes": (_sz, []),
+    "pxf_wq_merge_klo_ptr": (_vp, [_vp]),
+    "pxf_wq_merge_result_ptr": (_vp, [_vp]),
+    "pxf_wq_merge_begin": (_c.c_int, [_vp, _i64, _i64, _i64, _i64, _st]),
+    "pxf_wq_merge_probe": (_c.c_int, [_vp, _dp, _i64, _vp, _dp, _i64, _vp, _i32, _dp, _st]),
+    "pxf_wq_merge_narrow": (_c.c_int, [_vp, _dp, _dp, _dp, _d, _d, _i32, _st]),
+    "pxf_wq_merge_final_probe": (_c.c_int, [_vp, _dp, _i64, _vp, _dp, _i64, _vp, _dp, _st]),
+    "pxf_wq_merge_finish": (_c.c_int, [_vp, _dp, _dp, _dp, _d, _d, _st]),
     "pxf_sort_scratch_bytes": (_sz, [_i64]),
     "pxf_argsort": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _st]),
     "pxf_argsort_digits": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _i32, _st]),

@@ -312,6 +312,116 @@ __global__ void k_wq_result(const WqArg *__restrict__ partial, int nblk, const d
     out[3] = (double)i;
 }
 
+// ---------------------------------------------------------------- sharded merge: (K+1)-ary key-space search
+// dist.weighted_quantile_radii on the device.  Each rank holds, per quantile i (NQ = 2), a sorted run of radius
+// patterns keys[i][0..n[i]) with the prefix sums of their weights.  The GLOBAL answer -- smallest key whose
+// global cumulative weight reaches q*W -- is found without moving a ray: per step K pivots split [lo,hi], every
+// rank reports its weight at or below each pivot (k_wq_merge_probe), ONE all-reduce of [2][K] doubles merges
+// them, and k_wq_merge_narrow shrinks [lo,hi] by a factor K+1 identically on every rank.
+#define WQ_MERGE_MAXK 255
+struct WqMerge {
+    long long lo[2], hi[2];      // invariant: answer in [lo, hi]
+    long long klo[2];            // final phase: largest local key below hi (or -1)
+    double res[2], valid[2];     // final result
+};
+
+PXF_DEV long long wq_pivot(long long lo, long long hi, int j, int K)
+{
+    // j-th of K pivots splitting [lo,hi] into K+1 nearly equal parts (the torch driver's formula)
+    const long long n = hi - lo + 1;
+    const long long step = n / (K + 1), rem = n % (K + 1);
+    long long p = lo + (long long)(j + 1) * step + ((long long)(j + 1) < rem ? (long long)(j + 1) : rem) - 1;
+    return p < hi ? p : hi;
+}
+// number of keys <= key (strict: < key)
+PXF_DEV long long wq_count(const long long *__restrict__ keys, long long n, long long key, bool strict)
+{
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const long long v = keys[mid];
+        if (strict ? v < key : v <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+struct WqRuns { const long long *keys[2]; const double *cum[2]; long long n[2]; };
+
+__global__ void k_wq_merge_begin(WqMerge *m, long long lo0, long long hi0, long long lo1, long long hi1)
+{
+    m->lo[0] = lo0; m->hi[0] = hi0; m->lo[1] = lo1; m->hi[1] = hi1;
+    m->klo[0] = m->klo[1] = -1;
+    m->res[0] = m->res[1] = 0.; m->valid[0] = m->valid[1] = 0.;
+}
+
+// thread t = i*K + j
+__global__ void k_wq_merge_probe(const WqRuns R, const WqMerge *__restrict__ m, int K, double *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * K) return;
+    const int i = t / K, j = t % K;
+    const long long key = wq_pivot(m->lo[i], m->hi[i], j, K);
+    const long long cnt = wq_count(R.keys[i], R.n[i], key, false);
+    out[t] = cnt > 0 ? R.cum[i][cnt - 1] : 0.;
+}
+
+// one warp per quantile
+__global__ void k_wq_merge_narrow(WqMerge *m, const double *__restrict__ sum, const double *__restrict__ offsets,
+                                  const double *__restrict__ total, double q0, double q1, int K)
+{
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (i >= 2) return;
+    const double q = i ? q1 : q0, W = *total, off = offsets ? offsets[i] : 0.;
+    const long long lo = m->lo[i], hi = m->hi[i];
+    int first = K;                                     // first pivot whose global cdf reaches q
+    for (int j = lane; j < K; j += 32)
+        if ((sum[i * K + j] + off) / W >= q) { first = j; break; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_down_sync(0xffffffffu, first, o);
+        first = other < first ? other : first;
+    }
+    if (lane == 0) {
+        long long nlo, nhi;
+        if (first < K) {
+            nhi = wq_pivot(lo, hi, first, K);
+            nlo = first > 0 ? wq_pivot(lo, hi, first - 1, K) + 1 : lo;
+        } else {
+            nhi = hi;
+            nlo = wq_pivot(lo, hi, K - 1, K) + 1;
+        }
+        if (nlo > nhi) nlo = nhi;
+        m->lo[i] = nlo; m->hi[i] = nhi;
+    }
+}
+
+// final phase, local part: out[i*2+0] = weight at or below hi, out[i*2+1] = weight strictly below hi,
+// m->klo[i] = largest local key below hi (or -1)
+__global__ void k_wq_merge_final_probe(const WqRuns R, WqMerge *m, double *__restrict__ out)
+{
+    const int i = threadIdx.x;
+    if (i >= 2) return;
+    const long long key = m->hi[i];
+    const long long le = wq_count(R.keys[i], R.n[i], key, false), lt = wq_count(R.keys[i], R.n[i], key, true);
+    out[2 * i] = le > 0 ? R.cum[i][le - 1] : 0.;
+    out[2 * i + 1] = lt > 0 ? R.cum[i][lt - 1] : 0.;
+    m->klo[i] = lt > 0 ? R.keys[i][lt - 1] : -1;
+}
+
+// after all-reduce(sum) of out and all-reduce(max) of klo
+__global__ void k_wq_merge_finish(WqMerge *m, const double *__restrict__ sum, const double *__restrict__ offsets,
+                                  const double *__restrict__ total, double q0, double q1)
+{
+    const int i = threadIdx.x;
+    if (i >= 2) return;
+    const double q = i ? q1 : q0, W = *total, off = offsets ? offsets[i] : 0.;
+    const double chi = (sum[2 * i] + off) / W, clo = (sum[2 * i + 1] + off) / W;
+    const long long klo = m->klo[i], khi = m->hi[i];
+    const bool take_lo = klo >= 0 && fabs(clo - q) <= fabs(chi - q);
+    m->res[i] = __longlong_as_double(take_lo ? klo : khi);
+    m->valid[i] = (chi >= q && (klo >= 0 || off == 0.)) ? 1. : 0.;
+}
+
 static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace pxf
@@ -417,6 +527,74 @@ int pxf_wq_argmin(const double *rs_sorted, const double *cum, int64_t n, const d
     return check_launch("k_wq_argmin");
 }
 size_t pxf_wq_argmin_scratch_bytes(void) { return 1024 * sizeof(WqArg); }
+
+/* ---- sharded merge of sorted runs (dist.weighted_quantile_radii on the device) ---- */
+size_t pxf_wq_merge_state_bytes(void) { return a256(sizeof(WqMerge)); }
+int64_t *pxf_wq_merge_klo_ptr(void *state) { return reinterpret_cast<int64_t *>(static_cast<WqMerge *>(state)->klo); }
+double *pxf_wq_merge_result_ptr(void *state) { return static_cast<WqMerge *>(state)->res; }
+
+static int wq_runs(WqRuns &R, const int64_t *keys0, const double *cum0, int64_t n0, const int64_t *keys1,
+                   const double *cum1, int64_t n1)
+{
+    if (n0 < 0 || n1 < 0 || (n0 > 0 && (!keys0 || !cum0)) || (n1 > 0 && (!keys1 || !cum1))) { set_error("pxf_wq_merge: bad run"); return PXF_ERR_INVALID; }
+    R.keys[0] = reinterpret_cast<const long long *>(keys0); R.cum[0] = cum0; R.n[0] = n0;
+    R.keys[1] = reinterpret_cast<const long long *>(keys1); R.cum[1] = cum1; R.n[1] = n1;
+    return PXF_OK;
+}
+
+int pxf_wq_merge_begin(void *state, int64_t lo0, int64_t hi0, int64_t lo1, int64_t hi1, pxf_stream_t stream)
+{
+    if (!state || lo0 < 0 || lo1 < 0 || hi0 < lo0 || hi1 < lo1) { set_error("pxf_wq_merge_begin: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    k_wq_merge_begin<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<WqMerge *>(state), lo0, hi0, lo1, hi1);
+    count_launch();
+    return check_launch("k_wq_merge_begin");
+}
+
+int pxf_wq_merge_probe(const int64_t *keys0, const double *cum0, int64_t n0, const int64_t *keys1, const double *cum1,
+                       int64_t n1, const void *state, int32_t K, double *out_dev, pxf_stream_t stream)
+{
+    WqRuns R;
+    int rc = wq_runs(R, keys0, cum0, n0, keys1, cum1, n1);
+    if (rc) return rc;
+    if (!state || !out_dev || K < 1 || K > WQ_MERGE_MAXK) { set_error("pxf_wq_merge_probe: bad argument"); return PXF_ERR_INVALID; }
+    k_wq_merge_probe<<<(2 * K + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        R, static_cast<const WqMerge *>(state), K, out_dev);
+    count_launch();
+    return check_launch("k_wq_merge_probe");
+}
+
+int pxf_wq_merge_narrow(void *state, const double *sum_dev, const double *offsets_dev, const double *total_dev,
+                        double q0, double q1, int32_t K, pxf_stream_t stream)
+{
+    if (!state || !sum_dev || !total_dev || K < 1 || K > WQ_MERGE_MAXK) { set_error("pxf_wq_merge_narrow: bad argument"); return PXF_ERR_INVALID; }
+    k_wq_merge_narrow<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<WqMerge *>(state), sum_dev, offsets_dev,
+                                                                            total_dev, q0, q1, K);
+    count_launch();
+    return check_launch("k_wq_merge_narrow");
+}
+
+int pxf_wq_merge_final_probe(const int64_t *keys0, const double *cum0, int64_t n0, const int64_t *keys1,
+                             const double *cum1, int64_t n1, void *state, double *out_dev, pxf_stream_t stream)
+{
+    WqRuns R;
+    int rc = wq_runs(R, keys0, cum0, n0, keys1, cum1, n1);
+    if (rc) return rc;
+    if (!state || !out_dev) { set_error("pxf_wq_merge_final_probe: bad argument"); return PXF_ERR_INVALID; }
+    k_wq_merge_final_probe<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(R, static_cast<WqMerge *>(state), out_dev);
+    count_launch();
+    return check_launch("k_wq_merge_final_probe");
+}
+
+int pxf_wq_merge_finish(void *state, const double *sum_dev, const double *offsets_dev, const double *total_dev,
+                        double q0, double q1, pxf_stream_t stream)
+{
+    if (!state || !sum_dev || !total_dev) { set_error("pxf_wq_merge_finish: bad argument"); return PXF_ERR_INVALID; }
+    k_wq_merge_finish<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<WqMerge *>(state), sum_dev, offsets_dev,
+                                                                            total_dev, q0, q1);
+    count_launch();
+    return check_launch("k_wq_merge_finish");
+}
 
 // Bracketed weighted HPD; *valid_host = 0 means "run the full sort".
 int pxf_hpd_weighted_bracket(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,

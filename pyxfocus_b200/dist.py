@@ -428,19 +428,17 @@ def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None, ke
     (``offsets[i]`` > 0) -- the bracketed caller then falls back to the full sort."""
     dev = runs[0][0].device
     nq = len(qs)
+    if dev.type == "cuda" and nq == 2:
+        return _weighted_quantile_radii_cuda(runs, qs, total_weight, group, offsets, key_ranges)
     q = torch.tensor(list(qs), dtype=torch.float64, device=dev)
     off = torch.zeros(nq, dtype=torch.float64, device=dev) if offsets is None else offsets.to(torch.float64)
     lo = torch.zeros(nq, dtype=torch.int64, device=dev)                              # invariant: answer in [lo, hi]
     hi = torch.full((nq,), 0x7ff0000000000000, dtype=torch.int64, device=dev)        # +Inf pattern
-    steps = _KARY_STEPS
     if key_ranges is not None:
         # every key of run i lies in key_ranges[i] (identical on every rank): a narrower space, fewer steps
         lo = torch.tensor([max(int(a), 0) for a, _ in key_ranges], dtype=torch.int64, device=dev)
         hi = torch.tensor([min(int(b), 0x7ff0000000000000) for _, b in key_ranges], dtype=torch.int64, device=dev)
-        width = max(max(int(b) - int(a) + 1, 1) for a, b in key_ranges)
-        steps = 1
-        while (_KARY + 1) ** steps < width:
-            steps += 1
+    steps = _merge_steps(key_ranges)[1] if key_ranges is not None and nq == 2 else _KARY_STEPS
     jj = torch.arange(1, _KARY + 1, dtype=torch.int64, device=dev)                   # j+1
 
     def cdf_at(keys2d, strict=False):
@@ -470,6 +468,53 @@ def weighted_quantile_radii(runs, qs, total_weight, group=None, offsets=None, ke
     key = torch.where(take_lo, k_lo, k_hi)
     valid = (c_hi >= q) & ((k_lo >= 0) | (off == 0.))
     return key.view(torch.float64), valid
+
+
+def _merge_steps(key_ranges):
+    if key_ranges is None:
+        return (0, 0x7ff0000000000000, 0, 0x7ff0000000000000), _KARY_STEPS
+    (a0, b0), (a1, b1) = key_ranges
+    a0, a1 = max(int(a0), 0), max(int(a1), 0)
+    b0, b1 = max(min(int(b0), 0x7ff0000000000000), a0), max(min(int(b1), 0x7ff0000000000000), a1)
+    width = max(b0 - a0 + 1, b1 - a1 + 1, 1)
+    steps = 1
+    while (_KARY + 1) ** steps < width:
+        steps += 1
+    return (a0, b0, a1, b1), steps
+
+
+def _weighted_quantile_radii_cuda(runs, qs, total_weight, group, offsets, key_ranges):
+    """``weighted_quantile_radii`` with libpxf kernels (pxf_wq_merge_*): two launches and one all-reduce per step
+    instead of ~25 small tensor ops.  Same pivots, same narrowing, same result."""
+    dev = runs[0][0].device
+    L = _lib.lib()
+    (k0, c0), (k1, c1) = runs
+    k0, c0, k1, c1 = k0.contiguous(), c0.contiguous(), k1.contiguous(), c1.contiguous()
+    n0, n1 = int(k0.shape[0]), int(k1.shape[0])
+    W = total_weight.reshape(1).to(torch.float64).contiguous()
+    off = None if offsets is None else offsets.to(torch.float64).contiguous()
+    (a0, b0, a1, b1), steps = _merge_steps(key_ranges)
+    world = _world(group)
+    with torch.cuda.device(dev):
+        st = torch.zeros(int(L.pxf_wq_merge_state_bytes()) // 8, dtype=torch.float64, device=dev)
+        probe = torch.empty(2 * _KARY, dtype=torch.float64, device=dev)
+        fin = torch.empty(4, dtype=torch.float64, device=dev)
+        s = stream_ptr(dev)
+        offp = off.data_ptr() if off is not None else None
+        _lib.check(L.pxf_wq_merge_begin(st.data_ptr(), a0, b0, a1, b1, s))
+        for _ in range(steps):
+            _lib.check(L.pxf_wq_merge_probe(k0.data_ptr(), c0.data_ptr(), n0, k1.data_ptr(), c1.data_ptr(), n1,
+                                            st.data_ptr(), _KARY, probe.data_ptr(), s))
+            all_reduce_sum(probe, group)
+            _lib.check(L.pxf_wq_merge_narrow(st.data_ptr(), probe.data_ptr(), offp, W.data_ptr(), float(qs[0]), float(qs[1]),
+                                             _KARY, s))
+        _lib.check(L.pxf_wq_merge_final_probe(k0.data_ptr(), c0.data_ptr(), n0, k1.data_ptr(), c1.data_ptr(), n1,
+                                              st.data_ptr(), fin.data_ptr(), s))
+        all_reduce_sum(fin, group)
+        if world > 1:
+            td.all_reduce(st[4:6].view(torch.int64), op=td.ReduceOp.MAX, group=group)      # klo[2]
+        _lib.check(L.pxf_wq_merge_finish(st.data_ptr(), fin.data_ptr(), offp, W.data_ptr(), float(qs[0]), float(qs[1]), s))
+    return st[6:8].clone(), st[8:10] != 0.
 
 
 def weighted_quantile_radius(loc, q, total_weight, group=None):

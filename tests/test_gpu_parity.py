@@ -656,6 +656,38 @@ def test_weighted_hpd_bracket_falls_back(pxf):
     assert pxf.analyses.hpd(dev, weights=w) == pytest.approx(pyref.hpd(cpu, weights=w), abs=1e-12)
 
 
+def test_sharded_merge_kernels_match_the_tensor_driver(pxf):
+    """pxf_wq_merge_* (the device form of dist.weighted_quantile_radii) == the tensor-op driver the gloo tests
+    exercise: random sorted runs, offsets, bracket key ranges, empty runs, a quantile no key reaches."""
+    import torch
+    from pyxfocus_b200 import dist
+    rng = np.random.default_rng(91)
+    for trial in range(24):
+        runs_cpu, ranges = [], []
+        for i in range(2):
+            n = 0 if trial == 5 and i == 0 else int(rng.integers(1, 3000))
+            r = np.sort(rng.random(n) * (10. ** rng.integers(-6, 3)))
+            if n > 10 and trial % 4 == 0:
+                r[n // 2: n // 2 + 5] = r[n // 2]                      # ties
+            w = rng.random(n) + .01
+            runs_cpu.append((torch.from_numpy(r.view(np.int64).copy()), torch.from_numpy(np.cumsum(w))))
+            lo = float(r[0]) * .99 if n else 0.
+            hi = float(r[-1]) * 1.01 if n else 1.
+            ranges.append((int(np.float64(lo).view(np.int64)), int(np.float64(hi).view(np.int64))))
+        off = torch.tensor([float(rng.random() * 3.), float(rng.random() * 3.)]) if trial % 2 else None
+        tot = sum(float(c[-1]) if c.shape[0] else 0. for _, c in runs_cpu) / 2. + (float(off.mean()) if off is not None else 0.)
+        W = torch.tensor(tot * (1.0 if trial % 3 else 5.0))           # x5: no key reaches .75
+        kr = ranges if trial % 3 == 1 else None
+        want, wv = dist.weighted_quantile_radii(runs_cpu, [.25, .75], W, offsets=off, key_ranges=kr)
+        runs_gpu = [(k.cuda(), c.cuda()) for k, c in runs_cpu]
+        got, gv = dist.weighted_quantile_radii(runs_gpu, [.25, .75], W.cuda(), offsets=None if off is None else off.cuda(),
+                                               key_ranges=kr)
+        assert np.array_equal(gv.cpu().numpy(), wv.numpy()), trial
+        for i in range(2):
+            if bool(wv[i]):
+                assert float(got[i]) == float(want[i]), (trial, i)
+
+
 def test_image_plane_and_focus(pxf, golden):
     g = golden("ws_offaxis")
     cpu = rows_of(g["after_secondary"])
