@@ -1120,6 +1120,36 @@ def test_full_size_properties(pxf, n):
     out = T.vignette(rays, ind=flags)
     assert out[1].shape[0] == int(flags.sum())
     assert torch.equal(out[1], rays[1][flags]) and torch.equal(out[9], rays[9][flags])
+    # weighted HPD: the bracketed path picks the same two radii as torch's full sort + cumsum + argmin
+    w = torch.linspace(.5, 2., n, dtype=torch.float64, device="cuda")
+    hw = A.hpd(rays, weights=w)
+    cxw, cyw = A.centroid(rays, weights=w)
+    rw = torch.sqrt((rays[1] - cxw) ** 2 + (rays[2] - cyw) ** 2)
+    order = torch.argsort(rw, stable=True)
+    cdf = torch.cumsum(w[order], 0)
+    cdf = cdf / cdf.max()
+    want = float(rw[order][torch.argmin((cdf - .75).abs())] - rw[order][torch.argmin((cdf - .25).abs())])
+    assert hw == pytest.approx(want, rel=1e-9)
+    del order, cdf, rw
+    # a nested assembly in one launch == the same shells one by one (first and last shell compared)
+    radii = np.linspace(200., 1500., 260)
+    sizes = [n // 260] * 260
+    sizes[-1] += n - sum(sizes)
+    z0s = [float(np.sqrt(1.e4 ** 2 - r ** 2)) for r in radii]
+
+    def chain(r0, z0):
+        return (pxf.Program().transform(0, 0, z0, 0, 0, 0).wolterprimary(r0, z0, 1.).reflect()
+                .woltersecondary(r0, z0, 1.).reflect().flat())
+    nest = pxf.sources.segments("annulus", [(r, r + .6, 0., -1.) for r in radii], sizes, seed=2)
+    pxf.SegmentedProgram([chain(r, z) for r, z in zip(radii, z0s)], sizes).run(nest)
+    for k, first in ((0, 0), (259, n - sizes[-1])):
+        one = pxf.sources.annulus(radii[k], radii[k] + .6, sizes[k], zhat=-1., rng="philox", seed=2, first=first)
+        chain(radii[k], z0s[k]).run(one)
+        for row in range(1, 10):
+            assert torch.equal(one[row], nest[row][first:first + sizes[k]]), (k, row)
+    assert float(nest[3].abs().max()) == 0.                   # every shell focused onto its focal plane z = 0
+    hp = A.hpd(nest)
+    assert 0. < hp < 1e-3
 
 
 def copy_dev(rays):
