@@ -183,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline():
@@ -370,7 +370,7 @@ def run_engine(args):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         td.destroy_process_group()
 
@@ -431,8 +431,19 @@ def run_e2e(args, pxf, pdist, src, prog, n, world, dev, barrier):
                     "host threads instead of crossing PCIe) + HPD", "hpd": hp}
 
 
+def emit(line):
+    """The one JSON line, on the real stdout."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    # rank 0 prints exactly ONE line on stdout: anything a library writes to fd 1 meanwhile (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) goes to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
