@@ -124,8 +124,10 @@ def main():
                  *(lambda ms: (ms, n / (ms * 1e-3), b * n / (ms * 1e-3) / 1e9, b * n / (ms * 1e-3) / 1e9 / peak))(
                      timed_b2b(lambda: pxf.transformations.vignette(st3, ind=flags), calls=10))))
     rad = pxf.analyses.rho(st3, cent=True)
-    rows.append(("argsort (stable LSD radix, 64-bit keys)", "analyses.py:76", 0,
-                 *(lambda ms: (ms, n / (ms * 1e-3), 0., 0.))(timed_b2b(lambda: pxf.analyses.argsort(rad), calls=5))))
+    # algorithmic traffic of an argsort: keys read once, sorted keys and the int64 permutation written once
+    rows.append(("argsort (stable LSD radix, 64-bit keys)", "analyses.py:76", 24,
+                 *(lambda ms: (ms, n / (ms * 1e-3), 24 * n / (ms * 1e-3) / 1e9, 24 * n / (ms * 1e-3) / 1e9 / peak))(
+                     timed_b2b(lambda: pxf.analyses.argsort(rad), calls=5))))
     print("rays per launch: %d; HBM peak (measured copy rate): %.1f GB/s" % (n, peak))
     print("%-40s %-30s %7s %9s %11s %9s %6s" % ("routine", "reference", "B/ray", "ms", "Grays/s", "GB/s", "frac"))
     for r in rows:

@@ -509,15 +509,19 @@ int seg_chain_launch(int chain_id, const RowPtrs &P, const RowPtrs &Q, int64_t n
                      cudaStream_t s)
 {
     if (chain_id != 1) return PXF_ERR_UNSUPPORTED;
-    auto kern = k_chain_seg<SegWolter, SegWolterP, 3>;
-    static int ctas = 0;
-    if (ctas == 0) {
+    // PXF_SEG_MINB (tuning): resident CTAs per SM the register allocation is capped for
+    static int minb = -1;
+    if (minb < 0) { const char *e = getenv("PXF_SEG_MINB"); minb = e ? atoi(e) : 4; }    // measured at 2e7 rays, 260 shells: 0.92 / 0.78 / 0.72 / 0.76 ms for 2 / 3 / 4 / 5
+    auto go = [&](auto kern) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PXF_BLOCK, 0) != cudaSuccess || nb <= 0) { cudaGetLastError(); nb = 3; }
-        ctas = nb;
-    }
-    const int grid = grid_for(num, CSEG_TILE, ctas);
-    kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, seg_start_dev, static_cast<const SegWolterP *>(table_dev), nseg, LM, SM);
+        const int grid = grid_for(num, CSEG_TILE, nb);
+        kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, seg_start_dev, static_cast<const SegWolterP *>(table_dev), nseg, LM, SM);
+    };
+    if (minb == 2) go(k_chain_seg<SegWolter, SegWolterP, 2>);
+    else if (minb == 3) go(k_chain_seg<SegWolter, SegWolterP, 3>);
+    else if (minb == 5) go(k_chain_seg<SegWolter, SegWolterP, 5>);
+    else go(k_chain_seg<SegWolter, SegWolterP, 4>);
     count_launch();
     return check_launch("k_chain_seg");
 }
