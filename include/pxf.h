@@ -526,6 +526,23 @@ size_t pxf_scan_scratch_bytes(int64_t num);
 int pxf_cumsum_gather(const double *w, const int64_t *idx, int64_t num, double *out,
                       void *scratch, pxf_stream_t stream);
 
+/* ======================= reconstruct ================= */
+/* reconstruct.f95:1-128  reconstruct(xang,yang,xdim,ydim,criteria,h,phase,phasec,maxiter): Southwell successive
+ * over-relaxation in the reference's lexicographic Gauss-Seidel order, run as a diagonal-parity pipeline
+ * (bit-identical, see pxf_reconstruct.cu).  Arrays: device, column-major [xdim][ydim], 100. = invalid lenslet;
+ * xang, yang, phase are updated in place like the Fortran intent(inout) arguments, phasec receives the result.
+ * *sweeps_host (nullable) = sweeps executed.  Synchronises the stream. */
+int pxf_reconstruct(double *xang, double *yang, int32_t xdim, int32_t ydim, double criteria, double h, double *phase,
+                    double *phasec, int32_t maxiter, int64_t *sweeps_host, pxf_stream_t stream);
+/* reconstruct.f95:136-187  southwellbin(x,y,l,m,num,binsize,xang,yang,phase,xdim,ydim): mean direction cosines of
+ * the rays in each lenslet -> slopes tan(asin(.)), 100. for empty lenslets.  Per-lenslet sums are taken in ray
+ * order (stable sort by cell, one thread per cell), i.e. the single-thread semantics of the reference loop.
+ * scratch: pxf_southwellbin_scratch_bytes(num, xdim, ydim). */
+size_t pxf_southwellbin_scratch_bytes(int64_t num, int32_t xdim, int32_t ydim);
+int pxf_southwellbin(const double *x, const double *y, const double *l, const double *m, int64_t num, double binsize,
+                     double *xang, double *yang, double *phase, int32_t xdim, int32_t ydim, void *scratch,
+                     pxf_stream_t stream);
+
 /* ======================= sources ======================================== */
 /* Device-side ray generation for bundles too large for host MT19937 (SURVEY 7 "RNG parity").
  * Counter-based Philox4x32-10, key=(seed lo,hi), counter=(global ray index, stream id);

@@ -92,6 +92,9 @@ def _declare(L):
     L.pxfo_legendrep.restype = _d
     L.pxfo_woltersecondary_steps.argtypes = [_d] * 9
     L.pxfo_woltersecondary_steps.restype = _i32
+    L.pxfo_reconstruct.argtypes = [_dp, _dp, _i32, _i32, _d, _d, _dp, _dp, _i32]
+    L.pxfo_reconstruct.restype = _i64
+    L.pxfo_southwellbin.argtypes = [_dp] * 4 + [_i64, _d, _dp, _dp, _dp, _i32, _i32]
 
 
 def _io(*arrs):
@@ -368,3 +371,47 @@ specialfunctions = SimpleNamespace(
     legendre=lambda x, n: lib().pxfo_legendre(float(x), int(n)),
     legendrep=lambda x, n: lib().pxfo_legendrep(float(x), int(n)),
 )
+
+
+# ---------------------------------------------------------------- reconstruct (reconstruct.f95)
+def _io2(*arrs):
+    """intent(inout) 2-D arrays: f2py wants Fortran-contiguous float64 of one shape."""
+    shape = None
+    out = []
+    for a in arrs:
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.ndim != 2 or not a.flags.f_contiguous:
+            raise ValueError("failed in converting argument to C/Fortran array: "
+                             "intent(inout) array must be a Fortran-contiguous 2-D float64 ndarray")
+        if shape is None:
+            shape = a.shape
+        elif a.shape != shape:
+            raise ValueError("shape mismatch against xdim,ydim")
+        out.append(a.ctypes.data_as(_dp))
+    return shape, out
+
+
+def _reconstruct(xang, yang, criteria, h, phase, maxiter):
+    """phasec = reconstruct(xang,yang,criteria,h,phase,maxiter) -- the f2py signature of reconstruct.f95:1
+    (xdim, ydim hidden; xang, yang, phase intent(inout), phasec intent(out)).  ``_reconstruct.sweeps`` holds the
+    number of sweeps of the last call (test aid)."""
+    (xdim, ydim), (px, py, pp) = _io2(xang, yang, phase)
+    phasec = np.zeros((xdim, ydim), order="F")
+    _reconstruct.sweeps = int(lib().pxfo_reconstruct(px, py, xdim, ydim, float(criteria), float(h), pp,
+                                                      phasec.ctypes.data_as(_dp), int(maxiter)))
+    return phasec
+
+
+def _southwellbin(x, y, l, m, binsize, xdim, ydim):
+    """xang,yang,phase = southwellbin(x,y,l,m,binsize,xdim,ydim) (reconstruct.f95:136)."""
+    xs, px = _in(x)
+    n = xs.shape[0]
+    ys, py = _in(y, n)
+    ls, pl = _in(l, n)
+    ms, pm = _in(m, n)
+    xang, yang, phase = (np.zeros((int(xdim), int(ydim)), order="F") for _ in range(3))
+    lib().pxfo_southwellbin(px, py, pl, pm, n, float(binsize), xang.ctypes.data_as(_dp), yang.ctypes.data_as(_dp),
+                            phase.ctypes.data_as(_dp), int(xdim), int(ydim))
+    return xang, yang, phase
+
+
+reconstruct = SimpleNamespace(reconstruct=_reconstruct, southwellbin=_southwellbin)

@@ -1431,3 +1431,95 @@ int pxfo_woltersecondary_steps(double x, double y, double z, double l, double m,
     }
     return it;
 }
+
+/* ======================================================================== reconstruct.f95
+ * Southwell wavefront reconstruction.  Arrays are Fortran column-major:
+ * A(xi,yi) = a[(xi-1) + (yi-1)*xdim], xi fastest. */
+#define RA(a, xi, yi) (a)[((xi) - 1) + (int64_t)((yi) - 1) * xdim]
+
+/* reconstruct.f95:1-128.  Successive over-relaxation in lexicographic Gauss-Seidel order (xi outer,
+ * yi inner); 100. marks an invalid lenslet.  Returns the number of sweeps executed (the Fortran
+ * returns nothing; used by the tests). */
+int64_t pxfo_reconstruct(double *xang, double *yang, int32_t xdim, int32_t ydim, double criteria, double h,
+                         double *phase, double *phasec, int32_t maxiter)
+{
+    const double pi = (double)3.1415926535897931f;        /* :13 default-real literal: REAL*4 */
+    const double w = 2 / (1 + sin(pi / (sqrt((double)xdim * (double)ydim) + 1)));   /* :14 */
+    const int64_t ncell = (int64_t)xdim * ydim;
+    int64_t sweeps = 0;
+    int counter = 0;
+    memcpy(phasec, phase, (size_t)ncell * sizeof(double));                         /* :17 */
+    for (;;) {
+        double rms = 0.;
+        int nannum = 0;
+        for (int xi = 2; xi <= xdim - 1; xi++) {
+            for (int yi = 2; yi <= ydim - 1; yi++) {
+                int compute = 1;
+                double yplus = 0, yneg = 0, xplus = 0, xneg = 0, pyplus, pyneg, pxplus, pxneg, bk = 0, psum = 0, goodpix = 4.;
+                if (RA(phasec, xi, yi) == 100.) compute = 0;                       /* :33-35 */
+                if (compute == 1) {
+                    yplus = RA(yang, xi, yi + 1); if (yplus == 100.) yplus = -RA(yang, xi, yi);   /* :39-42 */
+                    yneg = RA(yang, xi, yi - 1);  if (yneg == 100.) yneg = -RA(yang, xi, yi);
+                    xplus = RA(xang, xi + 1, yi); if (xplus == 100.) xplus = -RA(xang, xi, yi);
+                    xneg = RA(xang, xi - 1, yi);  if (xneg == 100.) xneg = -RA(xang, xi, yi);
+                    bk = .5 * (yplus - yneg + xplus - xneg) * h;                   /* :57 */
+                    pyplus = RA(phasec, xi, yi + 1); if (pyplus == 100.) { pyplus = 0.; goodpix = goodpix - 1; }
+                    pyneg = RA(phasec, xi, yi - 1);  if (pyneg == 100.) { pyneg = 0.; goodpix = goodpix - 1; }
+                    pxplus = RA(phasec, xi + 1, yi); if (pxplus == 100.) { pxplus = 0.; goodpix = goodpix - 1; }
+                    pxneg = RA(phasec, xi - 1, yi);  if (pxneg == 100.) { pxneg = 0.; goodpix = goodpix - 1; }
+                    psum = pyplus + pyneg + pxplus + pxneg;                        /* :85 */
+                    if (goodpix == 0.) {                                           /* :88-94 */
+                        RA(phasec, xi, yi) = 100.;
+                        RA(phase, xi, yi) = 100.;
+                        RA(xang, xi, yi) = 100.;
+                        RA(yang, xi, yi) = 100.;
+                        compute = 0;
+                    }
+                }
+                if (compute == 1) {
+                    RA(phasec, xi, yi) = RA(phasec, xi, yi) + w * ((psum + bk) / goodpix - RA(phasec, xi, yi));   /* :99 */
+                    nannum = nannum + 1;
+                    double dlt = RA(phasec, xi, yi) - RA(phase, xi, yi);
+                    rms = rms + dlt * dlt;                                         /* :103 */
+                }
+            }
+        }
+        sweeps++;
+        rms = sqrt(rms / nannum);                                                  /* :112 (0/0 = NaN when no cell) */
+        memcpy(phase, phasec, (size_t)ncell * sizeof(double));                     /* :114 */
+        if (rms < criteria) break;
+        counter = counter + 1;
+        if (counter > maxiter) break;
+    }
+    return sweeps;
+}
+
+/* reconstruct.f95:136-187.  xang, yang, phase are intent(out) and accumulated into without being
+ * cleared (:165-166): the routine relies on zero-filled arrays; restated with an explicit clear.  Rays
+ * whose bin falls outside the array corrupt memory in the reference; they are skipped here.  The
+ * reference's OpenMP loop races on the bins; single-thread semantics (ray order) are restated. */
+void pxfo_southwellbin(const double *x, const double *y, const double *l, const double *m, int64_t num,
+                       double binsize, double *xang, double *yang, double *phase, int32_t xdim, int32_t ydim)
+{
+    const int64_t ncell = (int64_t)xdim * ydim;
+    int *accum = (int *)calloc((size_t)ncell, sizeof(int));
+    memset(xang, 0, (size_t)ncell * sizeof(double));
+    memset(yang, 0, (size_t)ncell * sizeof(double));
+    memset(phase, 0, (size_t)ncell * sizeof(double));
+    for (int64_t i = 0; i < num; i++) {
+        int xb, yb;
+        if (xdim % 2 == 0) xb = (int)floor(x[i] / binsize) + xdim / 2 + 1 + 1;     /* :155-156 */
+        else xb = (int)floor((x[i] + binsize / 2) / binsize) + (xdim - 1) / 2 + 1;
+        if (ydim % 2 == 0) yb = (int)floor(y[i] / binsize) + ydim / 2 + 1 + 1;
+        else yb = (int)floor((y[i] + binsize / 2) / binsize) + (ydim - 1) / 2 + 1;
+        if (xb < 1 || xb > xdim || yb < 1 || yb > ydim) continue;
+        RA(xang, xb, yb) = RA(xang, xb, yb) + l[i];
+        RA(yang, xb, yb) = RA(yang, xb, yb) + m[i];
+        accum[(xb - 1) + (int64_t)(yb - 1) * xdim] += 1;
+    }
+    for (int64_t c = 0; c < ncell; c++) {
+        if (accum[c] == 0) { phase[c] = 100.; xang[c] = 100.; yang[c] = 100.; }
+        else { xang[c] = tan(asin(xang[c] / accum[c])); yang[c] = tan(asin(yang[c] / accum[c])); }   /* :180-181 */
+    }
+    free(accum);
+}

@@ -156,6 +156,10 @@ SIGNATURES = {
     "pxf_argsort_digits": (_c.c_int, [_dp, _i64, _dp, _vp, _vp, _i32, _st]),
     "pxf_scan_scratch_bytes": (_sz, [_i64]),
     "pxf_cumsum_gather": (_c.c_int, [_dp, _vp, _i64, _dp, _vp, _st]),
+    # reconstruct
+    "pxf_reconstruct": (_c.c_int, [_dp, _dp, _i32, _i32, _d, _d, _dp, _dp, _i32, _vp, _st]),
+    "pxf_southwellbin_scratch_bytes": (_sz, [_i64, _i32, _i32]),
+    "pxf_southwellbin": (_c.c_int, [_dp, _dp, _dp, _dp, _i64, _d, _dp, _dp, _dp, _i32, _i32, _vp, _st]),
     # sources
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
     "pxf_source_segmented": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _i32, _vp, _dp, _st]),

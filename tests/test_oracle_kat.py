@@ -434,3 +434,56 @@ def test_K18_zernphase_and_rotated_set():
     Z.tracezernrot(*r4[1:], zc, ro, ao, zc2[even], ro[even], ao[even], 20., 0.)
     for k in range(1, 10):
         assert np.allclose(r3[k], r4[k], atol=1e-12), k
+
+
+# ---------------------------------------------------------------- reconstruct.f95
+def _pad100(a):
+    t = np.zeros((a.shape[0] + 2, a.shape[1] + 2), order="F") + 100.
+    t[1:-1, 1:-1] = a
+    return t
+
+
+def test_K19_southwell_reconstruction_recovers_a_known_surface():
+    """reconstruct (reconstruct.f95:1-128) integrates the gradients of a Legendre surface inside a circular
+    aperture back to that surface (up to piston and the reference's sign convention, southwell.py:45-46)."""
+    n = 48
+    xg, yg = np.meshgrid(np.linspace(-1, 1, n), np.linspace(-1, 1, n))
+    img = np.polynomial.legendre.legval2d(xg, yg, [[0, 1, 0], [0, .5, 0], [1, 0, 0]])
+    gx, gy = np.gradient(img)
+    out = np.sqrt(xg ** 2 + yg ** 2) > 1
+    gx[out] = 100.
+    gy[out] = 100.
+    phase = np.zeros(gx.shape, order="F")
+    phase[out] = 100.
+    P, GX, GY = _pad100(phase), _pad100(gx), _pad100(gy)
+    pc = of.reconstruct.reconstruct(GX, GY, 1e-10, 1., P, 10000)
+    assert 50 < of.reconstruct.reconstruct.sweeps < 10000          # converged, not capped
+    assert np.array_equal(pc, P)                                   # phase is updated in place (:114)
+    res = -pc[1:-1, 1:-1]
+    assert (res[out] == -100.).all()
+    d = (res - img)[~out]
+    assert np.std(d) < 1e-7 * np.std(img[~out])
+
+
+def test_K20_southwellbin_mean_slopes_and_empty_lenslets():
+    """southwellbin (reconstruct.f95:136-187): every lenslet holds tan(asin(mean direction cosine)) of its rays,
+    empty lenslets are flagged 100., for even and odd array sizes (the two index formulas, :155-164)."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    x, y = rng.uniform(-9.9, 9.9, n), rng.uniform(-4.9, 4.9, n)
+    l, m = 1e-3 * x, -2e-3 * y
+    for xd, yd, bs in ((20, 10, 1.), (21, 11, 1.)):
+        xa, ya, ph = of.reconstruct.southwellbin(x, y, l, m, bs, xd, yd)
+        if xd % 2 == 0:
+            xb, yb = np.floor(x / bs).astype(int) + xd // 2 + 1, np.floor(y / bs).astype(int) + yd // 2 + 1
+        else:
+            xb, yb = np.floor((x + bs / 2) / bs).astype(int) + (xd - 1) // 2, np.floor((y + bs / 2) / bs).astype(int) + (yd - 1) // 2
+        for cx, cy in ((3, 4), (xd // 2, yd // 2), (xd - 3, 2)):
+            sel = (xb == cx) & (yb == cy)
+            if sel.any():
+                assert xa[cx, cy] == pytest.approx(np.tan(np.arcsin(l[sel].mean())), rel=1e-12)
+                assert ya[cx, cy] == pytest.approx(np.tan(np.arcsin(m[sel].mean())), rel=1e-12)
+                assert ph[cx, cy] == 0.
+        assert (xa[0, :] == 100.).all() or xd % 2 == 1             # even sizes never fill row 0 (:156: +1+1)
+        empty = ph == 100.
+        assert np.array_equal(empty, xa == 100.) and np.array_equal(empty, ya == 100.)
