@@ -71,12 +71,20 @@ k_sort_hist(const u64 *__restrict__ keys, Chunking ck, int shift, u32 *__restric
     const int64_t hi = lo + ck.per < ck.num ? lo + ck.per : ck.num;
     const int64_t span = hi > lo ? hi - lo : 0;
     const int64_t nround = (span + blockDim.x - 1) / blockDim.x;
-    for (int64_t r = 0; r < nround; r++) {
-        const int64_t i = lo + r * blockDim.x + threadIdx.x;
-        int d = -1;
-        if (i < hi) d = (int)((keys[i] >> shift) & 255);
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (d >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[d], __popc(peers));
+    // four rounds at a time: the loads are issued together (one key per thread per round was latency bound:
+    // 1.2 TB/s, profiles/r01h_sort_launches_summary.txt)
+    for (int64_t r = 0; r < nround; r += 4) {
+        int d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t i = lo + (r + u) * blockDim.x + threadIdx.x;
+            d[u] = (r + u < nround && i < hi) ? (int)((keys[i] >> shift) & 255) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            unsigned peers = __match_any_sync(0xffffffffu, d[u]);
+            if (d[u] >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[d[u]], __popc(peers));
+        }
     }
     __syncthreads();
     table[(size_t)threadIdx.x * ck.G + blockIdx.x] = sh[threadIdx.x];
