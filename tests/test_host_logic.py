@@ -95,3 +95,50 @@ def test_host_trace_argument_validation():
     rows[3] = np.zeros(4, dtype=np.float32)
     with pytest.raises(ValueError):
         pxf.host.trace(rows, pxf.Program().reflect())                    # wrong dtype
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (the driver parses it); everything else -- including what
+    libraries write to fd 1 -- goes to stderr.  The reference arm runs on the CPU, so it is checked here."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-rays", "2e5"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_segmented_program_host_side_validation():
+    """SegmentedProgram folds its tables on the host (no GPU needed up to the upload): shape checks and the
+    C-side fill (same routine sequence in every segment, seg_start monotone)."""
+    import ctypes
+    import pyxfocus_b200 as pxf
+    from pyxfocus_b200 import _lib
+    L = _lib.lib()
+    ops = (_lib.pxf_op * 4)()
+    for k, (code, p) in enumerate([(10, (220., 8400., 1.)), (3, ()), (10, (300., 8000., 1.)), (3, ())]):
+        ops[k].code = code
+        for j, v in enumerate(p):
+            ops[k].p[j] = v
+    start = np.array([0, 10, 25], dtype=np.int64)
+    nbytes = int(L.pxf_segmented_table_bytes(2, 2))
+    assert nbytes > 0
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    assert L.pxf_segmented_table_fill(ops, 2, 2, start.ctypes.data, buf.ctypes.data) == 0
+    hdr = buf[:16].view(np.int32)
+    assert hdr[2] == 2 and hdr[3] == 2                      # nops, nseg
+    ops[3].code = 6                                         # second segment runs a different routine
+    assert L.pxf_segmented_table_fill(ops, 2, 2, start.ctypes.data, buf.ctypes.data) != 0
+    assert b"same opcode sequence" in L.pxf_last_error()
+    ops[3].code = 3
+    bad = np.array([0, 30, 25], dtype=np.int64)
+    assert L.pxf_segmented_table_fill(ops, 2, 2, bad.ctypes.data, buf.ctypes.data) != 0
+    with pytest.raises(ValueError):
+        pxf.SegmentedProgram([pxf.Program().flat()], [3, 4])
