@@ -58,6 +58,29 @@ class stage:
         return False
 
 
+def config1(n, dev):
+    """BASELINE configs[0] at its own size (1e5 rays, examples/axro/singlePassAlignment.py:246-269): numpy-seeded
+    source (host MT19937 draws, uploaded), fused trace, hpd.  Launch-latency territory."""
+    n = 100_000
+
+    def step():
+        np.random.seed(0)
+        with stage("source (numpy draws + upload)"):
+            rays = sources.subannulus(220., 220.6, 2 * np.pi, n, zhat=-1., device=dev)
+        with stage("trace (fused, 6 ops)"):
+            with pxf.fused(rays):
+                T.transform(rays, 0, 0, -8400., 0, 0, 0)
+                S.wolterprimary(rays, 220., 8400.)
+                T.reflect(rays)
+                S.woltersecondary(rays, 220., 8400.)
+                T.reflect(rays)
+                S.flat(rays)
+        with stage("hpd"):
+            res = dict(hpd=A.hpd(rays))
+        return res
+    return step, 3, n
+
+
 def config2(n, dev):
     """W-S shell, one off-axis field point (5 arcmin), focusI + findimageplane x2 + hpd + rms
     (examples/axro/axialHeights.py:77-113, WSverify.py:159-167)."""
@@ -233,12 +256,12 @@ def main():
         return program_only(int(float(sys.argv[1])), dev, int(sys.argv[2]))
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    which = sys.argv[3].split(",") if len(sys.argv) > 3 else ["2", "3", "4", "5"]
+    which = sys.argv[3].split(",") if len(sys.argv) > 3 else ["1", "2", "3", "4", "5"]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     print("rays per pass: %d, reps %d" % (n, reps))
     print("%-8s %10s %10s %10s %12s %14s  %s" % ("config", "ms (best)", "ms (med)", "ms (wall)", "Grays/s", "Ginteract/s", "result"))
-    for name, make in (("2", config2), ("3", config3), ("4", config4), ("5", config5)):
+    for name, make in (("1", config1), ("2", config2), ("3", config3), ("4", config4), ("5", config5)):
         if name not in which:
             continue
         made = make(n, dev)

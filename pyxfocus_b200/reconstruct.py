@@ -46,10 +46,13 @@ def _up(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
 
 
-def reconstruct(xang, yang, criteria, h, phase, maxiter):
+def reconstruct(xang, yang, criteria, h, phase, maxiter, xdim=None, ydim=None):
     """Southwell reconstruction by successive over-relaxation; returns ``phasec``.  ``reconstruct.sweeps`` holds
-    the number of sweeps of the last call."""
-    xdim, ydim = _inout2(xang, yang, phase)
+    the number of sweeps of the last call.  ``xdim``, ``ydim``: f2py's optional trailing shape arguments."""
+    shape = _inout2(xang, yang, phase)
+    if (xdim is not None and int(xdim) != shape[0]) or (ydim is not None and int(ydim) != shape[1]):
+        raise ValueError("shape(xang,0)==xdim / shape(xang,1)==ydim failed")
+    xdim, ydim = shape
     dev = _device()
     dx, dy, dp = _up(xang, dev), _up(yang, dev), _up(phase, dev)
     dc = torch.empty_like(dp)
