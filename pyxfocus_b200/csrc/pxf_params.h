@@ -341,6 +341,30 @@ inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const
             else t.ac += coeff[i] * (norm * sqrthalf32);
         }
     }
+    // power-basis table for the nmax <= 7 kernel, rebuilt from the folded (n,|m|) entries:
+    //   R_n^m(rho) = sum_s (-1)**s (n-s)! / (s! ((n+m)/2-s)! ((n-m)/2-s)!) rho**(n-2s),  rho**(n-2s) = rho**m * u**((n-m)/2-s)
+    memset(z.pc, 0, sizeof(z.pc));
+    if (z.nmax <= 7) {
+        double fact[16];
+        fact[0] = 1.;
+        for (int i = 1; i < 16; i++) fact[i] = fact[i - 1] * i;
+        int e = 0;
+        for (int n = 0; n <= 7; n++) {
+            for (int j = 0; j <= n / 2; j++) {
+                const int m = n - 2 * j;
+                const ZernEntry &t = z.e[e + j];
+                if (t.ac != 0. || t.as != 0.)
+                    for (int sgn = 0; sgn <= (n - m) / 2; sgn++) {
+                        const double c = ((sgn & 1) ? -1. : 1.) * fact[n - sgn] /
+                                         (fact[sgn] * fact[(n + m) / 2 - sgn] * fact[(n - m) / 2 - sgn]);
+                        const int jj = (n - m) / 2 - sgn;
+                        z.pc[m][jj][0] += t.ac * c;
+                        z.pc[m][jj][1] += t.as * c;
+                    }
+            }
+            e += n / 2 + 1;
+        }
+    }
     return z.nmax;
 }
 
