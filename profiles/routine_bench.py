@@ -104,6 +104,13 @@ def main():
     zc = np.random.default_rng(0).normal(0., 1e-4, len(ro))
     zc[:3] = 0.
     add("tracezern (36 terms, n<=7)", "zernsurf.f95:8-101", 96, lambda: ZS.tracezern(*W[1:], zc, np.array(ro), np.array(ao), 230.), st3)
+    # Legendre-Legendre figure error on the Wolter primary (the reference's figure-error model, woltsurf.f95:219-288):
+    # all axial x azimuthal orders up to 5 (36 coefficients)
+    llc = np.random.default_rng(1).normal(0., 1e-5, 36)
+    lla = np.repeat(np.arange(6), 6).astype(np.int32)
+    llz = np.tile(np.arange(6), 6).astype(np.int32)
+    add("wolterprimll (36 LL terms, orders<=5)", "woltsurf.f95:219-288", 96,
+        lambda: WS.wolterprimll(*W[1:], 220., 8400., 8500., 8400., 2 * np.pi, llc, lla, llz), st1)
     # analyses / compaction
     x, y = st3[1], st3[2]
     rows.append(("centroid", "analyses.py:16-22", 16, *(lambda ms: (ms, n / (ms * 1e-3), 16 * n / (ms * 1e-3) / 1e9, 16 * n / (ms * 1e-3) / 1e9 / peak))(

@@ -258,6 +258,8 @@ inline int make_ll(LLP &q, int kind, double r0, double z0, double psi, double S,
     q.dphi = dphi;
     q.twoodphi = 2 / dphi;
     q.zrange = zmax - zmin;
+    q.izhalf = 1 / q.zhalf;
+    q.twoozrange = 2 / q.zrange;
     if (kind == 0) {            // woltsurf.f95:235-241: thetah = 3.*alpha, thetap = alpha
         double alpha = .25 * atan(r0 / z0);
         double thetah = 3. * alpha, thetap = alpha;
@@ -279,6 +281,7 @@ inline int make_ll(LLP &q, int kind, double r0, double z0, double psi, double S,
         double aa = sqrt((-bq + sqrt(h_sq(bq) - 4 * cq)) / 2.);
         double bb = sqrt(h_sq(aa) - h_sq(ff));
         q.g0 = ff - P + z0; q.g1 = h_sq(aa); q.g2 = h_sq(bb);
+        q.ig1 = 1 / q.g1; q.ig2 = 1 / q.g2;
         q.tol = h_tol10();
     }
     return 0;
