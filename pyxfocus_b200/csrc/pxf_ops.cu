@@ -339,8 +339,10 @@ struct OpZernPhase {
     }
 };
 
-template <int NMAX>
+template <int NMAX, int MINB_ = 1, bool SCALAR_ = false>
 struct OpLL {
+    static constexpr int MINB = MINB_;
+    static constexpr bool SCALAR = SCALAR_;
     using Params = LLP;
     static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
     static constexpr int AUX = 0, SMEM = (NMAX + 1) * (NMAX + 1);
@@ -491,7 +493,16 @@ static int launch_ll(RowPtrs P, int64_t num, const uint8_t *mask, int kind, doub
         set_error("invalid Legendre orders (need 0 <= order <= %d)", PXF_LL_MAXN);
         return PXF_ERR_INVALID;
     }
-    if (q.stride == 8) return launch_op<OpLL<7>>(P, num, mask, nullptr, nullptr, q, stream);
+    if (q.stride == 8) {
+        // PXF_LL_VARIANT (tuning): 0 = two rays per thread (~250 registers, 8 warps/SM), 1/2/3 = one ray per thread
+        // with the register allocation capped for 1/2/3 resident CTAs per SM
+        static int variant = -1;
+        if (variant < 0) { const char *e = getenv("PXF_LL_VARIANT"); variant = e ? atoi(e) : 2; }   // measured, 36 terms at 5e7 rays: 8.37 / 8.71 / 7.92 / 8.15 ms for 0 / 1 / 2 / 3
+        if (variant == 1) return launch_op<OpLL<7, 1, true>>(P, num, mask, nullptr, nullptr, q, stream);
+        if (variant == 0) return launch_op<OpLL<7>>(P, num, mask, nullptr, nullptr, q, stream);
+        if (variant == 3) return launch_op<OpLL<7, 3, true>>(P, num, mask, nullptr, nullptr, q, stream);
+        return launch_op<OpLL<7, 2, true>>(P, num, mask, nullptr, nullptr, q, stream);
+    }
     return launch_op<OpLL<15>>(P, num, mask, nullptr, nullptr, q, stream);
 }
 
