@@ -295,7 +295,7 @@ int pxf_reconstruct(double *xang, double *yang, int32_t xdim, int32_t ydim, doub
         };
         // one pipelined run over all the sweeps the reference could make; it stops itself two steps after the
         // first converged sweep has been recognised
-        const int ns_all = (int)(max_sweeps < 0x3fffffff ? max_sweeps : 0x3fffffff);
+        const int ns_all = (int)(max_sweeps < 0x1fffffff ? max_sweeps : 0x1fffffff);   // 2*ns_all time steps must fit an int
         if ((rc = run(ns_all, criteria, every))) return rc;
         ReconCtl hc;
         PXF_CUDA(cudaMemcpyAsync(&hc, ctl, sizeof(hc), cudaMemcpyDeviceToHost, s));
