@@ -309,7 +309,7 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
     }
     // PXF_PROGRAM_VARIANT (tuning): 0 = two rays per thread (double2 rows), 1/3/4 = one ray per thread with
     // the register allocation capped for 1 / 3 / 4 resident CTAs per SM.  Measured on config 3's 12-op tail at
-    // 5e7 rays (profiles/r01h_notes.md): 3.82 / 3.75 / 3.27 / 3.00 ms for 0 / 1 / 3 / 4.
+    // 5e7 rays (profiles/r01h_notes.md): 3.82 / 3.75 / 3.27 / 3.00 ms for 0 / 1 / 3 / 4 (5 and 6 CTAs/SM spill: 4.6 / 5.7 ms).
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("PXF_PROGRAM_VARIANT"); variant = e ? atoi(e) : 4; }
     auto go = [&](auto kern, int64_t items) {
