@@ -1297,3 +1297,44 @@ def test_remaining_analyses_sources_and_helpers(pxf, golden):
 def torch_equal(a, b):
     import torch
     return bool(torch.equal(a, b))
+
+
+def test_bench_scale_properties(pxf):
+    """The bench's own size (1.25e8 rays per GPU = BASELINE configs[4] sharded over 8): size-independent
+    properties of the fused trace, the exact select, the bracketed weighted quantiles and the compaction."""
+    import torch
+    from pyxfocus_b200._call import bundle_alloc
+    n = 125_000_000
+    A, T = pxf.analyses, pxf.transformations
+    src = pxf.sources.subannulus(220., 220.6, 2 * np.pi, n, zhat=-1., rng="philox", seed=0)
+    out = bundle_alloc(n, "cuda", zero=True)
+    sums = torch.zeros(16, dtype=torch.float64, device="cuda")
+    prog = (pxf.Program().transform(0., 0., 8400., 0., 0., 0.).wolterprimary(220., 8400., 1.).reflect()
+            .woltersecondary(220., 8400., 1.).reflect().flat())
+    prog.run(src, out=out, sums=sums)
+    # the source is untouched, every ray sits on the focal plane with the plane's normal
+    assert float(src[3].abs().max()) == 0. and float(src[6].max()) == -1.
+    assert float(out[3].abs().max()) == 0. and float(out[9].min()) == 1. and float(out[7].abs().max()) == 0.
+    # centroid sums emitted by the trace kernel == a separate pass (same fixed-shape tree is not required: 1e-15)
+    cx, cy = A.centroid(out)
+    assert float(sums[0]) == n
+    assert abs(float(sums[1]) / n - cx) <= 1e-15 and abs(float(sums[2]) / n - cy) <= 1e-15
+    # unweighted HPD == the two middle order statistics of a full sort
+    h = A.hpd(out, sums=sums)
+    rad = A.rho(out, cent=True)
+    srt = torch.sort(rad).values
+    assert h == float(srt[(n - 1) // 2] + srt[n // 2])
+    assert h == pytest.approx(1.28e-5, rel=.01)                       # the config-1 answer (REAL*4 delta in flat)
+    del srt
+    # weighted HPD: bracketed path == the library's full sort path, bit for bit
+    w = torch.linspace(.5, 2., n, dtype=torch.float64, device="cuda")
+    hb, valid = _hpd_weighted_c(pxf, out, w, "bracket")
+    hs, _ = _hpd_weighted_c(pxf, out, w, "sorted")
+    assert valid == 1 and hb == hs
+    del w, rad
+    # compaction keeps exactly the flagged rays, in order
+    flags = out[1] > 0
+    kept = T.vignette(out, ind=flags)
+    assert kept[1].shape[0] == int(flags.sum())
+    assert bool((kept[1] > 0).all())
+    assert torch.equal(kept[2][:1000], out[2][flags][:1000])
