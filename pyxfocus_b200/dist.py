@@ -670,3 +670,106 @@ def hpd_weighted(rays, weights, group=None, local_cls=CudaWeighted, bracket_cls=
     W = all_reduce_sum(wl, group)
     r, _ = weighted_quantile_radii([(loc.keys, loc.cum)] * 2, [.25, .75], W, group)
     return float(r[1] - r[0])
+
+
+# ------------------------------------------------------------------ sharded rhocdf: sample sort
+class CudaSortedRun:
+    """Local half of the sharded ``rhocdf``: this shard's radii about the global centroid, sorted, with their
+    weights in the same order (libpxf kernels: pxf_rho, pxf_argsort).  The gloo tests use a numpy stand-in."""
+
+    def __init__(self, rays, weights, cx, cy):
+        from . import analyses
+        x, y = rays[1:3]
+        dev = x.device
+        num = x.shape[0]
+        self.device = dev
+        w = None if weights is None else torch.as_tensor(weights, dtype=torch.float64, device=dev).contiguous()
+        if num == 0:
+            self.r = torch.empty(0, dtype=torch.float64, device=dev)
+            self.w = torch.empty(0, dtype=torch.float64, device=dev)
+            return
+        r = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pxf_rho(x.data_ptr(), y.data_ptr(), num, cx, cy, r.data_ptr(), stream_ptr(dev)))
+        self.r, idx = analyses.argsort(r)
+        self.w = torch.ones_like(r) if w is None else w[idx]
+
+    @staticmethod
+    def merge(r, w):
+        """Sort the concatenation of the received runs (stable: ties keep source-rank order)."""
+        from . import analyses
+        if r.shape[0] == 0:
+            return r, w
+        rs, idx = analyses.argsort(r.contiguous())
+        return rs, w[idx]
+
+    @staticmethod
+    def prefix(w):
+        """Inclusive prefix sums (pxf_cumsum_gather without a permutation)."""
+        out = torch.empty_like(w)
+        n = w.shape[0]
+        if n:
+            L = _lib.lib()
+            with torch.cuda.device(w.device):
+                scratch = torch.empty(int(L.pxf_scan_scratch_bytes(n)), dtype=torch.uint8, device=w.device)
+                _lib.check(L.pxf_cumsum_gather(w.contiguous().data_ptr(), None, n, out.data_ptr(), scratch.data_ptr(),
+                                               stream_ptr(w.device)))
+        return out
+
+
+_SPLIT_SAMPLES = 1024
+
+
+def rhocdf(rays, weights=None, cent=True, group=None, local_cls=CudaSortedRun):
+    """Sharded ``analyses.rhocdf`` (analyses.py:73-86): the GLOBAL sorted radii and cumulative weights, distributed --
+    rank g returns the g-th contiguous slice ``(r, cdf, first)`` of the global sorted order (``first`` = global index
+    of its first element); concatenating the slices in rank order gives what the single-GPU call returns.
+
+    A sample sort, the one place on this path with a real exchange step: every rank sorts its shard, the ranks
+    all-gather evenly spaced local quantiles and agree on world-1 splitters, each rank cuts its sorted run at the
+    splitters and ONE all-to-all moves every (radius, weight) pair to the rank that owns its value range; the
+    received runs are merged by a stable sort, prefix-summed, and offset by the all-gathered bucket totals.  The
+    cdf is normalised by the total weight (= the reference's cdf.max() for non-negative weights)."""
+    flush(rays)
+    world = _world(group)
+    rank = td.get_rank(group) if world > 1 else 0
+    cx, cy = centroid(rays, weights, group) if cent is True else (0., 0.)
+    run = local_cls(rays, weights, cx, cy)
+    dev = run.device
+    n = run.r.shape[0]
+    if world == 1:
+        cum = local_cls.prefix(run.w)
+        return run.r, (cum / cum[-1] if n else cum), 0
+    # splitters from evenly spaced local quantiles (+Inf padding for an empty shard)
+    if n > 0:
+        pos = ((torch.arange(_SPLIT_SAMPLES, device=dev, dtype=torch.float64) + .5) * (n / _SPLIT_SAMPLES)).long().clamp(max=n - 1)
+        mine = run.r[pos]
+    else:
+        mine = torch.full((_SPLIT_SAMPLES,), float("inf"), dtype=torch.float64, device=dev)
+    allq = torch.empty(world * _SPLIT_SAMPLES, dtype=torch.float64, device=dev)
+    td.all_gather_into_tensor(allq, mine.contiguous(), group=group)
+    allq = torch.sort(allq).values
+    split = allq[torch.arange(1, world, device=dev) * _SPLIT_SAMPLES]           # world-1 splitters, same on every rank
+    # bucket k = (split[k-1], split[k]]: cut the sorted run, exchange counts, then the pairs
+    cuts = torch.searchsorted(run.r, split, right=True)
+    bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cuts, torch.full((1,), n, dtype=torch.int64, device=dev)])
+    send_counts = bounds[1:] - bounds[:-1]
+    recv_counts = torch.empty_like(send_counts)
+    td.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    got_r = torch.empty(sum(rc), dtype=torch.float64, device=dev)
+    got_w = torch.empty(sum(rc), dtype=torch.float64, device=dev)
+    td.all_to_all_single(got_r, run.r.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
+    td.all_to_all_single(got_w, run.w.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
+    r, w = local_cls.merge(got_r, got_w)
+    cum = local_cls.prefix(w)
+    # offsets: weight and element count of the buckets before mine
+    tot = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+    mine2 = torch.stack([cum[-1] if r.shape[0] else torch.zeros((), dtype=torch.float64, device=dev),
+                         torch.tensor(float(r.shape[0]), dtype=torch.float64, device=dev)])
+    td.all_gather_into_tensor(tot, mine2.contiguous(), group=group)
+    tot = tot.reshape(world, 2)
+    woff = tot[:rank, 0].sum()
+    first = int(tot[:rank, 1].sum().item())
+    total = tot[:, 0].sum()
+    return r, (woff + cum) / total, first

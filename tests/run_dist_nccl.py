@@ -59,6 +59,16 @@ def main():
             res, okb = D.hpd_weighted_bracketed(br, total, W)
             print("rank %d bracketed weighted hpd %.15e valid %s" % (rank, float(res), okb), flush=True)
             good = good and okb and abs(float(res) - hw1) <= 1e-9 * abs(hw1)
+        # sharded rhocdf (sample sort, one all-to-all): this rank's slice of the global sorted radii / cdf
+        rs, cs, first = dist.rhocdf(shard, weights=ww[lo:hi])
+        r1s, c1s = pxf.analyses.rhocdf(whole, weights=ww)
+        m = rs.shape[0]
+        okr = torch.equal(rs, r1s[first:first + m]) and float((cs - c1s[first:first + m]).abs().max()) <= 1e-12
+        cnt = torch.tensor([float(m)], dtype=torch.float64, device=dev)
+        td.all_reduce(cnt)
+        okr = okr and int(cnt.item()) == total
+        print("rank %d rhocdf slice [%d, %d) of %d -> %s" % (rank, first, first + m, total, okr), flush=True)
+        good = good and okr
         print("rank %d total %d: hpd %.15e vs %.15e rms %.6e/%.6e dz %.6e/%.6e -> %s" % (rank, total, h, h1, rms, r1, dz, d1, good),
               flush=True)
         ok = ok and good

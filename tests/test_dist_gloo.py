@@ -494,3 +494,76 @@ def test_kary_merge_matches_bisection_semantics():
                 want = r[j - 1] if abs(cdf[j - 1] - qq) <= abs(cdf[j] - qq) else r[j]
             if bool(valid[i]):
                 assert float(got[i]) == want
+
+
+# ---------------------------------------------------------------- sharded rhocdf: sample sort + all-to-all
+class NumpySortedRun:
+    """CPU stand-in for dist.CudaSortedRun."""
+
+    def __init__(self, rays, weights, cx, cy):
+        x, y = rays[1].numpy(), rays[2].numpy()
+        r = np.sqrt((x - cx) ** 2 + (y - cy) ** 2)
+        idx = np.argsort(r, kind="stable")
+        self.r = torch.from_numpy(np.ascontiguousarray(r[idx]))
+        w = np.ones_like(r) if weights is None else np.asarray(weights, dtype=np.float64)
+        self.w = torch.from_numpy(np.ascontiguousarray(w[idx]))
+        self.device = torch.device("cpu")
+
+    @staticmethod
+    def merge(r, w):
+        idx = np.argsort(r.numpy(), kind="stable")
+        return torch.from_numpy(r.numpy()[idx].copy()), torch.from_numpy(w.numpy()[idx].copy())
+
+    @staticmethod
+    def prefix(w):
+        return torch.from_numpy(np.cumsum(w.numpy()))
+
+
+def _rhocdf_worker(rank, world, port, n, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from pyxfocus_b200 import dist
+    x, y, w = _weighted_bundle(n, seed)
+    lo, hi = dist.shard_range(n, rank, world)
+    if rank == 1 and world == 3:
+        hi = lo                                          # an EMPTY shard in the middle
+    rays = [None, torch.from_numpy(x[lo:hi].copy()), torch.from_numpy(y[lo:hi].copy())] + [None] * 7
+    # cent=False: radii about the origin (the centroid path needs the CUDA sums kernel)
+    r, cdf, first = dist.rhocdf(rays, weights=w[lo:hi], cent=False, local_cls=NumpySortedRun)
+    q.put((rank, r.numpy(), cdf.numpy(), first, lo, hi))
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 30_001), (3, 12_000)])
+def test_sharded_rhocdf_sample_sort_over_gloo(world, n):
+    """dist.rhocdf: local sort -> agreed splitters -> one all-to-all of (radius, weight) pairs -> merge -> prefix sums
+    with all-gathered offsets.  The slices, concatenated in rank order, are numpy's argsort -> cumsum -> /max of the
+    whole bundle (analyses.py:73-86); ties across shards and an empty shard included."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rhocdf_worker, args=(r, world, port, n, 99, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, w = _weighted_bundle(n, 99)
+    covered = np.zeros(n, dtype=bool)
+    for _, _, _, _, lo, hi in out:
+        covered[lo:hi] = True
+    x, y, w = x[covered], y[covered], w[covered]
+    r = np.sqrt(x ** 2 + y ** 2)
+    ind = np.argsort(r, kind="stable")
+    cdf = np.cumsum(w[ind])
+    cdf = cdf / cdf.max()
+    got_r = np.concatenate([t[1] for t in out])
+    got_c = np.concatenate([t[2] for t in out])
+    assert np.array_equal(got_r, r[ind])
+    assert np.abs(got_c - cdf).max() <= 1e-13
+    firsts = [t[3] for t in out]
+    assert firsts == list(np.cumsum([0] + [t[1].shape[0] for t in out[:-1]]))
+    assert sum(t[1].shape[0] for t in out) == int(covered.sum())
