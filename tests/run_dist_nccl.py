@@ -63,7 +63,9 @@ def main():
         rs, cs, first = dist.rhocdf(shard, weights=ww[lo:hi])
         r1s, c1s = pxf.analyses.rhocdf(whole, weights=ww)
         m = rs.shape[0]
-        okr = torch.equal(rs, r1s[first:first + m]) and float((cs - c1s[first:first + m]).abs().max()) <= 1e-12
+        # (the all-reduced centroid may differ from the single-GPU one in the last bit, and with it a few radii)
+        okr = (torch.allclose(rs, r1s[first:first + m], rtol=1e-12, atol=0.)
+               and float((cs - c1s[first:first + m]).abs().max()) <= 1e-12)
         cnt = torch.tensor([float(m)], dtype=torch.float64, device=dev)
         td.all_reduce(cnt)
         okr = okr and int(cnt.item()) == total
