@@ -18,6 +18,9 @@ Tracing needs no communication (rays are independent).  Only the reductions do
   do not even sort the shard: a gathered sample brackets the two crossings, one pass collects the ~1 % of
   (radius, weight) pairs inside, and only those windows are sorted and merged (``hpd_weighted_bracketed``).
 
+* full sorted CDF (``rhocdf``): a sample sort -- local sort, splitters agreed on from all-gathered local
+  quantiles, one all-to-all of (radius, weight) pairs, stable merge, prefix sums with all-gathered offsets.
+
 Collectives go through ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the
 CPU tests of the host logic).  With ``group=None`` and no initialised process group the
 functions degrade to the single-GPU result (world size 1).
