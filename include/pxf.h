@@ -257,6 +257,9 @@ enum {
     PXF_OP_VIGNETTE_MAG = 17,  /* kill ray unless l^2+m^2+n^2 > .1 (transformations.py:220-223) */
     PXF_OP_VIGNETTE_BOX = 18,  /* p: row(1..9),lo,hi ; kill ray unless lo < row < hi             */
     PXF_OP_VIGNETTE_ABS = 19,  /* p: row(1..9),hi    ; kill ray unless |row| < hi                */
+    PXF_OP_ZERNSURF = 21,      /* p: table (a DEVICE copy of what pxf_zern_table_fill wrote, its address bit-cast
+                                  into the double), opd flag (0: tracezern, 1: tracezernOPD), nmax as returned by
+                                  the fill.  Radial orders <= 7 only; at most one Zernike table per program.     */
     PXF_OP_KICK = 20           /* p: dl,dm,sn ; l+=dl, m+=dm, n=sn*sqrt(1-l^2-m^2) (field angle,
                                   examples/axro/axialHeights.py:94-95 with dm=0 uses l only)   */
 };
@@ -270,6 +273,12 @@ typedef struct pxf_op {
  * no OPD op is in the program).  alive (nullable): device uint8[num], set to 0 for rays killed
  * by a VIGNETTE op (they stop executing at that op; their state at that point is stored), 1
  * otherwise.  Required when the program contains a VIGNETTE op. */
+/* Table for a PXF_OP_ZERNSURF op: folds (coeff, rorder, aorder, rad, nr) exactly as pxf_tracezern[opd] does into
+ * pxf_zern_table_bytes() bytes of HOST memory; the caller uploads them unchanged.  Returns the highest radial order
+ * (>= 0) or -1 for an invalid term list. */
+size_t pxf_zern_table_bytes(void);
+int32_t pxf_zern_table_fill(const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                            double rad, int32_t opd, double nr, void *table_host);
 int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
                       uint8_t *alive, pxf_stream_t stream);
 /* Out-of-place variant: rows are read from rays_in and every row the program reads or writes

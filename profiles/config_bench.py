@@ -116,15 +116,14 @@ def config3(n, dev):
     def step():
         with stage("source"):
             rays = sources.subannulus(220., 220.6, 100. / 220., n, zhat=-1., rng="philox", seed=0, device=dev)
-        with stage("transform + zernsurf"):
-            T.transform(rays, 220.3, 0, -100., 0, 0, 0)
-            S.zernsurf(rays, coeff, 62.5, rorder=ro, aorder=ao, nr=1.)
-        prog = (pxf.Program().reflect().transform(0, 0, 0, -np.pi, 0, 0).flatopd(1.)
-                .transform(220.3, 0, 8600., 0, 0, 0)
-                .wolterprimary(220., 8400., 1.).reflect()
-                .vignette_box(3, 8426., 8526.).vignette_abs(2, 50.)
-                .woltersecondary(220., 8400., 1.).reflect().vignette_mag().flat())
-        with stage("fused tail (12 ops)"):
+        # one fused launch: transform -> zernsurf (table in shared memory) -> the Wolter-I pair with its vignettes
+        with stage("fused trace (14 ops incl. the Zernike surface)"):
+            prog = (pxf.Program().transform(-220.3, 0, 100., 0, 0, 0).zernsurf(coeff, ro, ao, 62.5, 1.)
+                    .reflect().transform(0, 0, 0, -np.pi, 0, 0).flatopd(1.)
+                    .transform(220.3, 0, 8600., 0, 0, 0)
+                    .wolterprimary(220., 8400., 1.).reflect()
+                    .vignette_box(3, 8426., 8526.).vignette_abs(2, 50.)
+                    .woltersecondary(220., 8400., 1.).reflect().vignette_mag().flat())
             alive = prog.run(rays)
         with stage("vignette (compaction)"):
             surv = T.compact(rays, alive)      # alive: uint8 flags from the program's vignette predicates

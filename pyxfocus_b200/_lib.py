@@ -163,6 +163,8 @@ SIGNATURES = {
     # sources
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
     "pxf_source_segmented": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _i32, _vp, _dp, _st]),
+    "pxf_zern_table_bytes": (_sz, []),
+    "pxf_zern_table_fill": (_i32, [_vp, _vp, _vp, _i32, _d, _i32, _d, _vp]),
     "pxf_segmented_table_bytes": (_sz, [_i32, _i32]),
     "pxf_segmented_table_fill": (_c.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "pxf_trace_program_segmented": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _st]),

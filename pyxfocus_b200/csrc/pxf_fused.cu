@@ -18,7 +18,10 @@ PXF_DEV double ray_row(const Ray &r, int row)
 }
 
 // returns false when the ray is vignetted at this op
-PXF_DEV bool run_op(Ray &r, const FusedOp &op)
+// ZERN: whether this instantiation carries the Zernike evaluation at all -- it needs ~3x the registers of every
+// other op, so programs without a PXF_OP_ZERNSURF op run a kernel compiled without it
+template <bool ZERN = false>
+PXF_DEV bool run_op(Ray &r, const FusedOp &op, const ZernP *zt = nullptr)
 {
     switch (op.code) {
         case PXF_OP_TRANSFORM: op_transform(r, *reinterpret_cast<const TransformP *>(op.q)); break;
@@ -55,6 +58,12 @@ PXF_DEV bool run_op(Ray &r, const FusedOp &op)
             double v = ray_row(r, op.row);
             return fabs(v) < op.q[0];
         }
+        case PXF_OP_ZERNSURF:
+            // zt: the table in shared memory (k_program); same device code as the per-routine kernel (nmax <= 7)
+            if constexpr (ZERN) {
+                if (zt) op_tracezern<7>(r, zt->rad, zt->nr, zt->tol, zt->nmax, op.q[1] != 0., reinterpret_cast<const double *>(zt->e));
+            }
+            break;
         case PXF_OP_KICK: {
             r.l = r.l + op.q[0];
             r.m = r.m + op.q[1];
@@ -66,19 +75,30 @@ PXF_DEV bool run_op(Ray &r, const FusedOp &op)
     return true;
 }
 
-PXF_DEV bool run_program(Ray &r, const FusedProgram &prog)
+template <bool ZERN = false>
+PXF_DEV bool run_program(Ray &r, const FusedProgram &prog, const ZernP *zt = nullptr)
 {
     for (int k = 0; k < prog.nops; k++)
-        if (!run_op(r, prog.ops[k])) return false;
+        if (!run_op<ZERN>(r, prog.ops[k], zt)) return false;
     return true;
 }
 
-template <bool VEC2, int MINB = 1>
+template <bool VEC2, int MINB = 1, bool ZERN = false>
 __global__ void __launch_bounds__(PXF_BLOCK, MINB)
 k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
           double *__restrict__ partials, const __grid_constant__ FusedProgram prog)
 {
     double cnt = 0., sx = 0., sy = 0.;
+    // the Zernike table of a PXF_OP_ZERNSURF op, staged once per CTA
+    __shared__ __align__(16) unsigned char zraw[ZERN ? sizeof(ZernP) : 16];
+    const ZernP *zt = nullptr;
+    if (ZERN && prog.zern) {
+        const double *src = reinterpret_cast<const double *>(prog.zern);
+        double *dst = reinterpret_cast<double *>(zraw);
+        for (int t = threadIdx.x; t < (int)(sizeof(ZernP) / 8); t += blockDim.x) dst[t] = src[t];
+        __syncthreads();
+        zt = reinterpret_cast<const ZernP *>(zraw);
+    }
     // P: rows read, Q: rows written (Q == P for the in-place f2py semantics)
     const unsigned LM = prog.load_mask, SM = prog.store_mask;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,8 +109,8 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const int64_t i = q << 1;
             Ray a, b;
             fload2(a, b, P, LM, i);
-            const bool ka = run_program(a, prog);
-            const bool kb = run_program(b, prog);
+            const bool ka = run_program<ZERN>(a, prog, zt);
+            const bool kb = run_program<ZERN>(b, prog, zt);
             fstore2(a, b, Q, SM, i);
             if (alive) { alive[i] = ka ? 1 : 0; alive[i + 1] = kb ? 1 : 0; }
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -100,7 +120,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const int64_t i = num - 1;
             Ray a;
             fload1(a, P, LM, i);
-            const bool ka = run_program(a, prog);
+            const bool ka = run_program<ZERN>(a, prog, zt);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -109,7 +129,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
         for (int64_t i = tid; i < num; i += nthr) {
             Ray a;
             fload1(a, P, LM, i);
-            const bool ka = run_program(a, prog);
+            const bool ka = run_program<ZERN>(a, prog, zt);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -194,6 +214,7 @@ static void op_masks(int code, int row, unsigned &use, unsigned &st, unsigned &k
         case PXF_OP_VIGNETTE_MAG: use = R_DIR; st = 0; kill = 0; break;
         case PXF_OP_VIGNETTE_BOX: case PXF_OP_VIGNETTE_ABS: use = 1u << row; st = 0; kill = 0; break;
         case PXF_OP_KICK: use = R_L | R_M; st = R_DIR; kill = R_N; break;
+        case PXF_OP_ZERNSURF: use = R_POS | R_DIR | (row ? R_OPD : 0u); st = R_POS | R_NRM | (row ? R_OPD : 0u); kill = R_POS | R_NRM; break;
         default: use = 0; st = 0; kill = 0; break;
     }
 }
@@ -236,6 +257,16 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
                 f.q[0] = p[1];
                 break;
             case PXF_OP_KICK: f.q[0] = p[0]; f.q[1] = p[1]; f.q[2] = p[2]; break;
+            case PXF_OP_ZERNSURF: {
+                const ZernP *tab;
+                memcpy(&tab, &p[0], sizeof(tab));
+                if (!tab || fp.zern) { set_error("program: PXF_OP_ZERNSURF needs a device table, and only one per program"); return PXF_ERR_INVALID; }
+                if (!(p[2] >= 0. && p[2] <= 7.)) { set_error("program: PXF_OP_ZERNSURF supports radial orders <= 7 (use pxf_tracezern)"); return PXF_ERR_UNSUPPORTED; }
+                fp.zern = tab;
+                f.q[0] = 0.; f.q[1] = p[1] != 0. ? 1. : 0.;
+                f.row = p[1] != 0. ? 1 : 0;            // opd flag: decides whether row 0 is touched
+                break;
+            }
             default: set_error("program: unknown opcode %d", o.code); return PXF_ERR_INVALID;
         }
         if (o.code == PXF_OP_VIGNETTE_MAG || o.code == PXF_OP_VIGNETTE_BOX || o.code == PXF_OP_VIGNETTE_ABS)
@@ -319,7 +350,17 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         if (grid_out) *grid_out = grid;
         kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
     };
-    if (aligned && variant == 0) go(k_program<true, 1>, (num + 1) >> 1);
+    if (fp.zern) {
+        // one ray per thread; PXF_ZERNPROG_MINB (tuning): register cap for 1 / 2 / 3 resident CTAs per SM.  Measured on
+        // config 3's 14-op program at 5e7 rays: 9.40 / 6.28 / 6.01 ms (4: 6.28 ms); the same work as three launches
+        // (transform, tracezern, 12-op tail) takes 7.0 ms
+        static int zm = -1;
+        if (zm < 0) { const char *e = getenv("PXF_ZERNPROG_MINB"); zm = e ? atoi(e) : 3; }
+        if (zm == 1) go(k_program<false, 1, true>, num);
+        else if (zm == 2) go(k_program<false, 2, true>, num);
+        else go(k_program<false, 3, true>, num);
+    }
+    else if (aligned && variant == 0) go(k_program<true, 1>, (num + 1) >> 1);
     else if (variant == 3) go(k_program<false, 3>, num);
     else if (variant == 1) go(k_program<false, 1>, num);
     else go(k_program<false, 4>, num);
@@ -353,6 +394,19 @@ extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const ray
     return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out, nullptr, nullptr);
 }
 
+extern "C" size_t pxf_zern_table_bytes(void) { return sizeof(ZernP); }
+
+extern "C" int32_t pxf_zern_table_fill(const double *coeff, const int32_t *rorder, const int32_t *aorder, int32_t arrsize,
+                                       double rad, int32_t opd, double nr, void *table_host)
+{
+    if (!coeff || !rorder || !aorder || arrsize <= 0 || !table_host) { set_error("pxf_zern_table_fill: bad argument"); return -1; }
+    ZernP z;
+    const int n = make_zern(z, coeff, rorder, aorder, arrsize, rad, opd != 0, nr);
+    if (n < 0) { set_error("pxf_zern_table_fill: invalid Zernike table"); return -1; }
+    memcpy(table_host, &z, sizeof(z));
+    return n;
+}
+
 // ---- segmented programs -------------------------------------------------------------------------
 static size_t seg_align(size_t v) { return (v + 15) & ~(size_t)15; }
 static size_t seg_ops_offset(int nseg) { return seg_align(sizeof(SegHeader)) + seg_align((size_t)(nseg + 1) * 8); }
@@ -384,6 +438,7 @@ extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t
         FusedProgram fp;
         int rc = build_program(fp, ops + (size_t)sgm * nops, nops);
         if (rc) return rc;
+        if (fp.zern) { set_error("segmented program: PXF_OP_ZERNSURF is not supported"); return PXF_ERR_UNSUPPORTED; }
         if (sgm > 0)
             for (int k = 0; k < nops; k++)
                 if (fp.ops[k].code != dst[k].code || fp.ops[k].row != dst[k].row) {   // dst[0..nops) = segment 0

@@ -22,6 +22,7 @@ struct FusedProgram {
     // of downloading them.  Empty when the program can stop rays early (vignette predicates).
     unsigned const_mask;
     double const_val[10];
+    const ZernP *zern;       // device table of the program's PXF_OP_ZERNSURF op (NULL: none); staged in shared memory
     FusedOp ops[PXF_MAX_OPS];
 };
 

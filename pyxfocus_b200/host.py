@@ -8,6 +8,7 @@ PCIe transfers overlapped with the kernel (``pxf_host_trace_program``, include/p
 import ctypes
 
 import numpy as np
+import torch
 
 from . import _lib
 from .program import Program
@@ -51,7 +52,7 @@ def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
     if num is None:
         raise ValueError("no rows given")
     tab = (ctypes.c_void_p * 10)(*ptrs)
-    ops = prog.c_ops()
+    ops = prog.c_ops(torch.device("cuda", torch.cuda.current_device()) if prog._tables else None)
     h = ctypes.c_double(float("nan"))
     cnt = ctypes.c_int64(-1)
     flags = np.empty(num, dtype=np.uint8) if (alive and prog.has_vignette()) else None

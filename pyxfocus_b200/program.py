@@ -32,7 +32,7 @@ from ._call import stream_ptr
 OP = dict(TRANSFORM=1, ITRANSFORM=2, REFLECT=3, REFRACT=4, RADGRAT=5, FLAT=6, FLATOPD=7, CONIC=8,
           CONICOPD=9, WOLTERPRIMARY=10, WOLTERPRIMARYOPD=11, WOLTERSECONDARY=12, WOLTERSINE=13,
           WSPRIMARY=14, WSSECONDARY=15, SPOCONE=16, VIGNETTE_MAG=17, VIGNETTE_BOX=18,
-          VIGNETTE_ABS=19, KICK=20)
+          VIGNETTE_ABS=19, KICK=20, ZERNSURF=21)
 MAX_OPS = 24
 _VIGNETTES = (OP["VIGNETTE_MAG"], OP["VIGNETTE_BOX"], OP["VIGNETTE_ABS"])
 
@@ -42,6 +42,8 @@ class Program:
 
     def __init__(self):
         self.ops = []
+        self._tables = {}        # op index -> host table (uint8 tensor) of a ZERNSURF op
+        self._dev_tables = {}    # (op index, device) -> its device copy
 
     def __len__(self):
         return len(self.ops)
@@ -103,6 +105,30 @@ class Program:
     def spocone(self, r0, tg):
         return self.add(OP["SPOCONE"], r0, tg)
 
+    # --- zernsurf ---
+    def zernsurf(self, coeff, rorder, aorder, rad, nr=None):
+        """tracezern / tracezernOPD (zernsurf.f95:8-203) inside the program; radial orders <= 7, one Zernike surface
+        per program.  The term list is folded on the host exactly as for the stand-alone routine; the table is
+        uploaded once per device and staged in shared memory by the kernel."""
+        import numpy as np
+        c = np.ascontiguousarray(coeff, dtype=np.float64)
+        r = np.ascontiguousarray(rorder, dtype=np.int32)
+        a = np.ascontiguousarray(aorder, dtype=np.int32)
+        if not (c.shape == r.shape == a.shape) or c.ndim != 1 or c.shape[0] == 0:
+            raise ValueError("coeff, rorder, aorder must be 1-D arrays of one length")
+        if any(code == OP["ZERNSURF"] for code, _ in self.ops):
+            raise ValueError("a program carries at most one Zernike surface")
+        L = _lib.lib()
+        tab = torch.empty(int(L.pxf_zern_table_bytes()), dtype=torch.uint8)
+        nmax = int(L.pxf_zern_table_fill(c.ctypes.data, r.ctypes.data, a.ctypes.data, c.shape[0], float(rad),
+                                         0 if nr is None else 1, 0. if nr is None else float(nr), tab.data_ptr()))
+        if nmax < 0:
+            raise ValueError("invalid Zernike term list")
+        if nmax > 7:
+            raise NotImplementedError("fused Zernike surfaces support radial orders <= 7")
+        self._tables[len(self.ops)] = tab
+        return self.add(OP["ZERNSURF"], 0., 0. if nr is None else 1., float(nmax))
+
     # --- per-ray predicates (the ray stops at the op; use with ``alive``) ---
     def vignette_mag(self):
         """keep rays with l^2+m^2+n^2 > .1 (transformations.py:220-223)"""
@@ -124,12 +150,21 @@ class Program:
     def has_vignette(self):
         return any(c in _VIGNETTES for c, _ in self.ops)
 
-    def c_ops(self):
+    def c_ops(self, device=None):
+        import struct
         arr = (_lib.pxf_op * len(self.ops))()
         for k, (code, p) in enumerate(self.ops):
             arr[k].code = code
             for j, v in enumerate(p):
                 arr[k].p[j] = v
+            if k in self._tables:
+                if device is None:
+                    raise ValueError("a program with a Zernike surface needs a device")
+                key = (k, str(device))
+                if key not in self._dev_tables:
+                    self._dev_tables[key] = self._tables[k].to(device)
+                # the table's device address travels bit-cast in p[0] (include/pxf.h, PXF_OP_ZERNSURF)
+                arr[k].p[0] = struct.unpack("d", struct.pack("Q", self._dev_tables[key].data_ptr()))[0]
         return arr
 
     def run(self, rays, alive=None, out=None, sums=None):
@@ -146,6 +181,8 @@ class Program:
             # split into several launches; still one HBM round trip per <=24 elements
             head, tail = Program(), Program()
             head.ops, tail.ops = self.ops[:MAX_OPS], self.ops[MAX_OPS:]
+            head._tables = {k: v for k, v in self._tables.items() if k < MAX_OPS}
+            tail._tables = {k - MAX_OPS: v for k, v in self._tables.items() if k >= MAX_OPS}
             if head.has_vignette() or tail.has_vignette():
                 raise ValueError("programs with vignette predicates are limited to %d ops" % MAX_OPS)
             head.run(rays, out=out)
@@ -159,7 +196,7 @@ class Program:
         if self.has_vignette() and alive is None:
             alive = torch.empty(num, dtype=torch.uint8, device=dev)
         ptrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in rays])
-        ops = self.c_ops()
+        ops = self.c_ops(dev)
         ap = alive.data_ptr() if alive is not None else None
         optrs = None
         if out is not None:
@@ -262,6 +299,7 @@ def flush(rays):
     if prog is not None and len(prog):
         todo = Program()
         todo.ops, prog.ops = prog.ops, []
+        todo._tables, prog._tables = prog._tables, {}
         todo.run(rays)
 
 

@@ -56,6 +56,10 @@ def zernsurf(rays, coeff, rad, rorder=None, aorder=None, nr=None):
     if rorder is None or aorder is None:
         raise NotImplementedError("pass rorder/aorder explicitly: the reference's default ordering lives in "
                                   "the third-party module utilities.imaging.zernikemod (not vendored)")
+    prog = recorder_for(rays)
+    if prog is not None and np.max(np.asarray(rorder)) <= 7 and not any(c == 21 for c, _ in prog.ops):
+        prog.zernsurf(coeff, rorder, aorder, rad, nr)       # radial orders <= 7: stays in the fused program
+        return
     flush(rays)
     if nr is None:
         zern.tracezern(x, y, z, l, m, n, ux, uy, uz, coeff, np.array(rorder), np.array(aorder), rad)

@@ -319,6 +319,49 @@ def test_radgratw_sign_from_y(pxf):
     assert_close(to_host(dev), cpu, pos_scale=1.2e4, what="radgratw")
 
 
+@pytest.mark.parametrize("nr", [None, 1.5])
+def test_fused_zernsurf_bit_identical_to_per_routine(pxf, nr):
+    """PXF_OP_ZERNSURF inside a fused program (table staged in shared memory) == transform, zernsurf, reflect,
+    flat issued one by one: same device code, same bits; also through `with fused(...)` recording."""
+    ro, ao = chains.zernike_orders(7)
+    coeff = chains.zernike_coeff(36, 3)
+    cpu = random_bundle(N, 77)
+    cpu[1] *= .4
+    cpu[2] *= .4                                       # inside the unit disc of rad = 62.5 mostly
+    T, S = pxf.transformations, pxf.surfaces
+    a = to_dev(cpu)
+    T.transform(a, 1., -2., -100., 1e-3, -2e-3, .3)
+    S.zernsurf(a, coeff, 62.5, rorder=ro, aorder=ao, nr=nr)
+    T.reflect(a)
+    S.flat(a, nr=nr)
+    b = to_dev(cpu)
+    before = pxf.launch_count()
+    with pxf.fused(b):
+        T.transform(b, 1., -2., -100., 1e-3, -2e-3, .3)
+        S.zernsurf(b, coeff, 62.5, rorder=ro, aorder=ao, nr=nr)
+        T.reflect(b)
+        S.flat(b, nr=nr)
+    assert pxf.launch_count() - before == 1
+    assert_bit_equal(to_host(b), to_host(a), what="fused zernsurf")
+    c = to_dev(cpu)
+    prog = (pxf.Program().transform(-1., 2., 100., -1e-3, 2e-3, -.3).zernsurf(coeff, ro, ao, 62.5, nr).reflect())
+    prog = prog.flat() if nr is None else prog.flatopd(nr)
+    prog.run(c)
+    assert_bit_equal(to_host(c), to_host(a), what="Program.zernsurf")
+    with pytest.raises(ValueError):
+        pxf.Program().zernsurf(coeff, ro, ao, 62.5).zernsurf(coeff, ro, ao, 62.5)
+    # radial order 8: not fusable -> the recorder flushes and runs the stand-alone routine, same result as unfused
+    ro9, ao9 = chains.zernike_orders(8)
+    c9 = chains.zernike_coeff(len(ro9), 4)
+    d, e = to_dev(cpu), to_dev(cpu)
+    T.transform(d, 0, 0, -100., 0, 0, 0)
+    S.zernsurf(d, c9, 62.5, rorder=ro9, aorder=ao9)
+    with pxf.fused(e):
+        T.transform(e, 0, 0, -100., 0, 0, 0)
+        S.zernsurf(e, c9, 62.5, rorder=ro9, aorder=ao9)
+    assert_bit_equal(to_host(e), to_host(d), what="zernsurf order 8 under fused()")
+
+
 @pytest.mark.parametrize("opd", [False, True])
 def test_tracezern(pxf, opd):
     ro, ao = chains.zernike_orders(7)
