@@ -35,7 +35,6 @@ def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
             ptrs.append(None)
             continue
         if hasattr(r, "data_ptr"):          # torch CPU tensor (possibly pinned)
-            import torch
             if r.is_cuda or r.dtype != torch.float64 or r.dim() != 1 or not r.is_contiguous():
                 raise ValueError("host rows must be contiguous 1-D float64 CPU arrays")
             n, p = r.shape[0], r.data_ptr()

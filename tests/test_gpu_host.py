@@ -167,3 +167,21 @@ def test_host_trace_constant_input_chunks_are_not_uploaded_but_still_exact(pxf, 
         na, nb = np.isnan(a), np.isnan(b)
         assert np.array_equal(na, nb)
         assert np.array_equal(a.view(np.uint64)[~na], b.view(np.uint64)[~nb]), k
+
+
+def test_host_trace_program_with_a_zernike_surface(pxf):
+    """A program holding PXF_OP_ZERNSURF through the host-array entry point (its table is a device copy the
+    Python layer uploads once): same bits as the device-resident program, opd row included."""
+    from util import random_bundle
+    n = 2_300_001                                            # two chunks
+    ro, ao = chains.zernike_orders(7)
+    coeff = chains.zernike_coeff(36, 5)
+    cpu = random_bundle(n, 78)
+    cpu[1] *= .4
+    cpu[2] *= .4
+    prog = (pxf.Program().transform(-1., 2., 100., 0, 0, .2).zernsurf(coeff, ro, ao, 62.5, 1.).reflect().flatopd(1.))
+    dev = to_dev(cpu)
+    prog.run(dev)
+    host = copy(cpu)
+    pxf.host.trace(host, prog, write_back=True)
+    assert_bit_equal(host, to_host(dev), what="host vs device, Zernike program")
