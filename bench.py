@@ -145,8 +145,31 @@ def cpu_step_factory(n):
     return fresh, step
 
 
-def omp_threads():
-    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def use_all_host_cores():
+    """The CPU arm runs on EVERY host core this process may use, whatever the launcher exported: torchrun sets
+    OMP_NUM_THREADS=1 for its workers, which would time the reference on one core.  Must run before liboracle
+    (libgomp) is loaded -- libgomp reads the variable once, at load time.  Returns the thread count the oracle's
+    OpenMP runtime then reports (omp_get_max_threads), i.e. the count actually used."""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    from oracle import f2py as of
+    lib = of.lib()
+    try:
+        import ctypes
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(n)
+        got = int(gomp.omp_get_max_threads())
+    except OSError:
+        got = n
+    return got
 
 
 def run_reference(args):
@@ -156,8 +179,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import f2py as of
-    of.lib()
+    cores = use_all_host_cores()
     n = int(args.ref_rays)
     fresh, step = cpu_step_factory(n)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -171,7 +193,6 @@ def run_reference(args):
         hp = step(rays)
         t += time.perf_counter() - t0
     val = n * args.steps / t
-    cores = omp_threads()
     sample = "%d steps x %.3g rays (same chain + hpd), C oracle port with OpenMP" % (args.steps, n)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
@@ -188,8 +209,7 @@ def run_reference(args):
 
 def cpu_baseline():
     """Bounded sample (~10-20 s) of the same step on the host cores."""
-    from oracle import f2py as of
-    of.lib()
+    cores = use_all_host_cores()
     n = 4_000_000
     fresh, step = cpu_step_factory(n)
     step(fresh())                                   # warm-up (page faults, thread pool)
@@ -203,12 +223,41 @@ def cpu_baseline():
     for r in ins:
         step(r)
     t = time.perf_counter() - t0
-    return {"value": n * reps / t, "unit": "rays/s", "cores": omp_threads(), "kind": "port",
+    return {"value": n * reps / t, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": "%d x %.1e rays, six oracle-routine passes + numpy hpd, OpenMP on all host cores "
                       "(C restatement of the f2py Fortran; the Fortran itself cannot be built here)" % (reps, n)}
 
 
 # ------------------------------------------------------------------------------- engine arm
+def sharded_parity_check(pxf, pdist, prog, rank, world, dev, total=6_000_001):
+    """N > 1, before anything is timed: trace a 6e6-ray bundle sharded over the ranks AND whole on every rank; the
+    shard must be the slice of the whole bundle bit for bit and the all-reduced HPD / rms must equal the single-GPU
+    ones (what tests/run_dist_nccl.py asserts, made visible in the bench line)."""
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    lo, hi = pdist.shard_range(total, rank, world)
+    shard = pxf.sources.subannulus(RIN, ROUT, 2 * np.pi, hi - lo, zhat=-1., rng="philox", seed=3, first=lo, device=dev)
+    prog.run(shard)
+    h = pdist.hpd(shard)
+    r = pdist.rmsCentroid(shard)
+    whole = pxf.sources.subannulus(RIN, ROUT, 2 * np.pi, total, zhat=-1., rng="philox", seed=3, first=0, device=dev)
+    prog.run(whole)
+    rows_equal = all(bool(torch.equal(whole[k][lo:hi], shard[k])) for k in range(1, 10))
+    h1 = pxf.analyses.hpd(whole)
+    r1 = pxf.analyses.rmsCentroid(whole)
+    flags = torch.tensor([1 if rows_equal else 0, 1 if abs(h - h1) <= 1e-9 * abs(h1) else 0, 1 if abs(r - r1) <= 1e-9 * r1 else 0],
+                         dtype=torch.int32, device=dev)
+    td.all_reduce(flags, op=td.ReduceOp.MIN)
+    f = flags.cpu().tolist()
+    del shard, whole
+    torch.cuda.empty_cache()
+    return {"rays": total, "rows_equal": bool(f[0]), "hpd_equal": bool(f[1]), "rms_equal": bool(f[2]),
+            "tolerance": "rows: same bits as the slice of the single-GPU bundle; hpd, rms: 1e-9 relative "
+                         "(the all-reduced centroid may differ from the one-GPU tree sum in the last bit)",
+            "hpd_sharded": h, "hpd_single_gpu": h1, "hpd_rel_diff": abs(h - h1) / abs(h1) if h1 else 0.}
+
+
 def run_engine(args):
     import numpy as np
     import torch
@@ -218,6 +267,12 @@ def run_engine(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    # nvidia-smi starts FIRST (before the process group, the library load and the source generation): its start-up
+    # holds driver locks for ~100 ms, which must be over long before the timed region on every rank's GPU
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    t_sampler = time.time()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -230,51 +285,71 @@ def run_engine(args):
     n = int(args.rays)
     total = n * world
     first = rank * n
-    # ---- resident inputs: source bundle generated on the device (counter-based, seed 0,
-    # global ray index => identical stream for any sharding)
-    src = pxf.sources.subannulus(RIN, ROUT, 2 * np.pi, n, zhat=-1., rng="philox", seed=0, first=first, device=dev)
-    out = bundle_alloc(n, dev, zero=True)
     prog = (pxf.Program().transform(0., 0., Z0, 0., 0., 0.).wolterprimary(R0, Z0, PSI).reflect()
             .woltersecondary(R0, Z0, PSI).reflect().flat())
-
-    sums = torch.zeros(16, dtype=torch.float64, device=dev)
-
-    def step():
-        prog.run(src, out=out, sums=sums)          # trace kernel also emits the centroid sums
-        return pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
 
     def barrier():
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()
 
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
-    # warm-up: at least W steps, and keep stepping (GPU busy, clocks up) until nvidia-smi has had
-    # ~0.4 s to finish its start-up, so that none of it lands in the timed region
-    t_w = time.time()
-    nw = 0
-    while nw < max(args.warmup, 3) or (world == 1 and time.time() - t_w < 0.4):
-        hp = step()
-        nw += 1
-    barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled alongside
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- N > 1: the sharded path must reproduce the single-GPU result of the whole bundle before it is timed
+    parity = sharded_parity_check(pxf, pdist, prog, rank, world, dev) if world > 1 else None
+
+    # ---- resident inputs: source bundle generated on the device (counter-based, seed 0,
+    # global ray index => identical stream for any sharding)
+    src = pxf.sources.subannulus(RIN, ROUT, 2 * np.pi, n, zhat=-1., rng="philox", seed=0, first=first, device=dev)
+    out = bundle_alloc(n, dev, zero=True)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
     ws = pxf.analyses.hpd_workspace(n, dev)
 
+    def step(res_row):
+        """One step: the fused trace (which also emits the centroid sums) + the HPD, result left on the device in
+        res_row = [HPD, lower, upper, valid] -- nothing forces a host round trip between steps."""
+        prog.run(src, out=out, sums=sums)
+        if world > 1:
+            pdist.hpd(out, sums=sums, total=total, min_shard=n, out=res_row)
+        else:
+            pxf.analyses.hpd_enqueue(out, res_row, ws, sums=sums)
+
+    def step_readback():
+        prog.run(src, out=out, sums=sums)
+        return pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
+
+    # ---- warm-up: the read-back path once (reference HPD value), then the path that is timed, at least W steps
+    # and -- on every rank alike -- until the sampler has been up for a second and has delivered samples
+    hp = step_readback()
+    wres = torch.zeros(4, dtype=torch.float64, device=dev)
+    nw = 0
+    go = torch.ones(1, dtype=torch.int32, device=dev)
+    while True:
+        step(wres)
+        nw += 1
+        if nw < max(args.warmup, 3):
+            continue
+        more = (time.time() - t_sampler < 1.0 or (clk.proc is not None and len(clk.lines) < 2)) and nw < 400
+        if world > 1:
+            go[0] = 1 if (rank == 0 and more) else 0
+            td.all_reduce(go, op=td.ReduceOp.MAX)        # rank 0 decides for everybody
+            more = bool(int(go.item()))
+        if not more:
+            break
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, clocks sampled alongside
+    K = args.steps
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]       # step boundaries
+
     def timed_loop(deferred):
-        """K steps between two events.  deferred: every step's HPD is left on the device (float64[4] =
-        [HPD, lower, upper, valid]) and all K are read after the timed region -- nothing forces a host
-        round trip between steps (a stream of bundles analysed back to back).  Otherwise each step
-        reads its HPD back before the next trace is launched."""
-        res = torch.zeros(args.steps, 4, dtype=torch.float64, device=dev)
+        res = torch.zeros(K, 4, dtype=torch.float64, device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         last = None
         barrier()
         clk.mark_begin()
         e0.record()
-        for k in range(args.steps):
+        for k in range(K):
+            bev[k].record()
             kev[k][0].record()
             prog.run(src, out=out, sums=sums)
             kev[k][1].record()
@@ -285,6 +360,7 @@ def run_engine(args):
                     pxf.analyses.hpd_enqueue(out, res[k], ws, sums=sums)
             else:
                 last = pdist.hpd(out, sums=sums, total=total, min_shard=n) if world > 1 else pxf.analyses.hpd(out, sums=sums)
+        bev[K].record()
         e1.record()
         barrier()
         clk.mark_end()
@@ -305,11 +381,25 @@ def run_engine(args):
     assert hp_t == hp or (hp_t != hp_t and hp != hp), "HPD changed between warm-up and timed steps"
     launches = pxf.launch_count() - launches0
     clocks = clk.stop() if rank == 0 else None
-    trace_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    trace_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    per_step = sorted(bev[k].elapsed_time(bev[k + 1]) for k in range(K))
+    step_med, step_max = per_step[K // 2], per_step[-1]
+    # per-step latency WITH a host read-back of every result (what a caller that needs each HPD before going on sees)
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(min(K, 10)):
+        barrier()
+        t0 = time.perf_counter()
+        step_readback()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
     if world > 1:
-        t = torch.tensor([ms, trace_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, trace_ms, step_med, step_max, lat[len(lat) // 2]], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms, trace_ms = float(t[0]), float(t[1])
+        ms, trace_ms, step_med, step_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        lat_med = float(t[4])
+    else:
+        lat_med = lat[len(lat) // 2]
     value = total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-array C ABI entry (pinned host rows -> device -> host)
@@ -328,17 +418,21 @@ def run_engine(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = TRACE_BYTES_PER_RAY * n / (trace_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        # dram__bytes_read+write of the fused kernel from the ncu --set full capture (taken at
-        # 2e7 rays/launch; the kernel streams, so bytes scale with the ray count)
+        # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel, one launch, from the committed
+        # ncu --set full capture named in the file (per-ray figure x rays per launch: the kernel streams)
         tj = json.load(open(os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")))
         traffic = float(tj["dram_bytes_per_ray"]) * n
-    except (OSError, ValueError):
+        traffic_src = "static: %s (%s rays/launch, kernel %s)" % (tj.get("capture"), tj.get("rays_per_launch_measured"), tj.get("kernel"))
+    except (OSError, ValueError, KeyError):
         pass
+    kname = pxf.last_trace_kernel() if hasattr(pxf, "last_trace_kernel") else "k_chain (fused trace)"
+    fp64_frac = FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / (148 * 64 * 1.965e9)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "warmup": nw, "ms_per_step": ms / args.steps, "ms_per_step_median": step_med, "ms_per_step_max": step_max,
+        "ms_per_step_with_readback": lat_med, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "wolter1_trace_hpd (BASELINE configs[0] chain at configs[4] scale: "
                                "subannulus -> transform -> wolterprimary -> reflect -> woltersecondary -> reflect -> flat -> hpd)",
@@ -348,24 +442,29 @@ def run_engine(args):
                                   "select, 3 small collectives (sums+sample all-gather, counters+bins "
                                   "all-reduce, key lists all-gather)" % world,
                    "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (48e-9 * n),
-                   "hpd": hp, "trace_kernel_ms": trace_ms, "hpd_readback": readback},
-        "roofline": {"bound": "hbm", "kernel": "k_program (fused trace)", "achieved": achieved, "peak": peak,
+                   "hpd": hp, "trace_kernel_ms": trace_ms, "hpd_readback": readback,
+                   "latency_note": "ms_per_step: K steps enqueued back to back, results read after the region; "
+                                   "ms_per_step_with_readback: median wall time of a step that reads its HPD back "
+                                   "before the next one starts (what the CPU arm does every step)"},
+        "roofline": {"bound": "fp64-issue", "kernel": kname, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                     "algorithmic_bytes_per_ray": TRACE_BYTES_PER_RAY, "traffic": traffic,
-                     "note": "the fused kernel is COMPUTE bound (a compute-only replay of the chain takes the "
-                             "same 3.5 ms, profiles/r01_trace_compute.txt): serial fp64 Newton/division chains, "
-                             "no FMA contraction for bit parity; see DESIGN.md and profiles/r01_notes.md",
+                     "algorithmic_bytes_per_ray": TRACE_BYTES_PER_RAY, "traffic": traffic, "traffic_source": traffic_src,
+                     "note": "achieved/peak/frac are the HBM figures the contract asks for (algorithmic bytes / kernel "
+                             "time vs the measured copy rate); the kernel itself is bound by fp64 instruction issue "
+                             "along serial Newton/division chains (no FMA contraction, for bit parity with the "
+                             "reference): a compute-only replay takes the same time (profiles/r01_trace_compute.txt)",
                      # second denominator: fp64 warp instructions per ray from the ncu capture (static),
                      # duration measured live; peak = 148 SMs x 64 lanes x sm_max clock, reached to 99 %
                      # by profiles/micro/fp64_peak.cu
                      "fp64": {"thread_instr_per_ray": FP64_INSTR_PER_RAY,
                               "achieved_Tinstr_s": FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / 1e12,
-                              "peak_Tinstr_s": 148 * 64 * 1.965e9 / 1e12,
-                              "frac": FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / (148 * 64 * 1.965e9)}},
+                              "peak_Tinstr_s": 148 * 64 * 1.965e9 / 1e12, "frac": fp64_frac}},
         "clocks": clocks,
         "gpu_launches": launches,
     }
+    if parity is not None:
+        line["parity_check"] = parity
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -256,12 +256,21 @@ enum {
     PXF_OP_SPOCONE = 16,       /* p: R0,tg                             */
     PXF_OP_VIGNETTE_MAG = 17,  /* kill ray unless l^2+m^2+n^2 > .1 (transformations.py:220-223) */
     PXF_OP_VIGNETTE_BOX = 18,  /* p: row(1..9),lo,hi ; kill ray unless lo < row < hi             */
-    PXF_OP_VIGNETTE_ABS = 19,  /* p: row(1..9),hi    ; kill ray unless |row| < hi                */
+    PXF_OP_VIGNETTE_ABS = 19,  /* p: row(1..9),hi[,c] ; kill ray unless |row - c| < hi (c defaults to 0)   */
     PXF_OP_ZERNSURF = 21,      /* p: table (a DEVICE copy of what pxf_zern_table_fill wrote, its address bit-cast
                                   into the double), opd flag (0: tracezern, 1: tracezernOPD), nmax as returned by
                                   the fill.  Radial orders <= 7 only; at most one Zernike table per program.     */
-    PXF_OP_KICK = 20           /* p: dl,dm,sn ; l+=dl, m+=dm, n=sn*sqrt(1-l^2-m^2) (field angle,
+    PXF_OP_KICK = 20,          /* p: dl,dm,sn ; l+=dl, m+=dm, n=sn*sqrt(1-l^2-m^2) (field angle,
                                   examples/axro/axialHeights.py:94-95 with dm=0 uses l only)   */
+    PXF_OP_KICKN = 22,         /* p: dl,dm ; l+=dl, m+=dm, n=-sqrt(n^2-dl^2-dm^2): the pointing offsets of
+                                  examples/arcus/cat.py:246-249                                 */
+    PXF_OP_VIGNETTE_RHOGT = 23, /* p: rho0 ; kill ray unless sqrt(x^2+y^2) > rho0 (the back-of-previous-shell test,
+                                  examples/axro/axialHeights.py:285-286)                        */
+    PXF_OP_GRATFAN = 24,       /* p: ang,hubdist,l,dpermm,order,wave ; the fanned radial-grating array of
+                                  examples/arcus/sector.py:636-700 as ONE per-ray loop (see pxf_trace_program_aux).
+                                  wave = NaN: per-ray wavelengths from aux.wave (radgratW), else scalar (radgrat). */
+    PXF_OP_ROTX_REMAINING = 25 /* p: ang,total ; apply transform(0,0,0,ang,0,0) (total - aux.count[i]) times: the
+                                  whole-bundle rotations a ray still receives after it met its grating */
 };
 typedef struct pxf_op {
     int32_t code;
@@ -281,6 +290,27 @@ int32_t pxf_zern_table_fill(const double *coeff, const int32_t *rorder, const in
                             double rad, int32_t opd, double nr, void *table_host);
 int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
                       uint8_t *alive, pxf_stream_t stream);
+/* Per-ray side arrays of the ops that need them (all device pointers, each nullable unless an op uses it):
+ *   wave       double[num]  per-ray wavelength of a PXF_OP_GRATFAN with p.wave = NaN
+ *   count      int32[num]   PXF_OP_GRATFAN writes the number of fan rotations the ray received before it met a
+ *                           grating (-1: it never did within `cap` gratings); PXF_OP_ROTX_REMAINING reads it
+ *   count_max  int32[1]     PXF_OP_GRATFAN raises it (atomic max) to the largest count of the launch; the caller
+ *                           zeroes it beforehand.  cap + 1 when some ray never met a grating.
+ *   cap        most gratings a ray may pass (<= 0: 4096); the reference's loop would not terminate instead.
+ * PXF_OP_GRATFAN, per ray (sector.py:681-707; each step is the masked whole-bundle call of the reference):
+ *   repeat { if |asin(n)| > .001: flat ; rho = -sqrt(x^2+y^2)*sign(y) ; if hubdist < rho < l+hubdist: stop ;
+ *            transform(0,0,0,ang,0,0) } ; reflect ; radgrat[W](dpermm, order, wave).
+ * rays_out == NULL: in place. */
+typedef struct pxf_program_aux {
+    const double *wave;
+    int32_t *count;
+    int32_t *count_max;
+    int32_t cap;
+    int32_t reserved;
+} pxf_program_aux;
+int pxf_trace_program_aux(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                          const pxf_op *ops, int32_t nops, uint8_t *alive, const pxf_program_aux *aux,
+                          double *sums_dev, void *scratch, pxf_stream_t stream);
 /* Out-of-place variant: rows are read from rays_in and every row the program reads or writes
  * is stored to rays_out (rows it touches neither way are not copied).  rays_in is left
  * untouched, e.g. to trace one source bundle through several configurations. */

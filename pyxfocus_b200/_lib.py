@@ -30,6 +30,11 @@ class pxf_op(ctypes.Structure):
     _fields_ = [("code", _i32), ("reserved", _i32), ("p", _d * 6)]
 
 
+class pxf_program_aux(ctypes.Structure):
+    _fields_ = [("wave", _c.c_void_p), ("count", _c.c_void_p), ("count_max", _c.c_void_p), ("cap", _i32),
+                ("reserved", _i32)]
+
+
 # name -> (restype, [argtypes]).  Order follows include/pxf.h.
 _NINE = [_dp] * 9
 SIGNATURES = {
@@ -84,6 +89,7 @@ SIGNATURES = {
     "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_to": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_sums": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _dp, _vp, _st]),
+    "pxf_trace_program_aux": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _dp, _vp, _st]),
     # vignetting / compaction
     "pxf_vignette_flags": (_c.c_int, [_dp] * 3 + [_i64, _vp, _st]),
     "pxf_compact_scratch_bytes": (_sz, [_i64]),

@@ -1052,11 +1052,10 @@ static int select_pass(const double *x, const double *y, const double *keys, int
                        const unsigned long long *count_dev, const double *cxy, int shift, int bits,
                        SelectState *st, unsigned long long *hist, unsigned long long *nan_count, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(k_select_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes(13));
         cudaFuncSetAttribute(k_select_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes(13));
-        attr_set = true;
     }
     int grid = grid_for(num, PXF_BLOCK * 8, 3);
     if (keys)
@@ -1389,11 +1388,9 @@ int pxf_small_select(const double *keys, const int32_t *seg_counts, int32_t nseg
     }
     int rc = need_device();
     if (rc) return rc;
-    static int smem_set = 0;
-    if (!smem_set) {
+    static bool smem_set[64] = {};
+    if (first_on_device(smem_set))
         PXF_CUDA(cudaFuncSetAttribute(k_small_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
-        smem_set = 1;
-    }
     k_small_select<<<1, 1024, 2 * 8192 * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
         keys, seg_counts, nseg, seg_cap, (unsigned long long)ra, (unsigned long long)rb, npass,
         static_cast<const FastSel *>(fastsel), out_dev, nullptr, nullptr, nullptr);
@@ -1538,11 +1535,9 @@ int pxf_hpd_from_sums_dev(const double *x, const double *y, int64_t num, const d
     pxf_bracket_sample_ranks(BRACKET_SAMPLES, &ra, &rb);
     if (mode == 0 && num >= BRACKET_MIN_NUM) {
         // single-GPU fast path (see k_bracket_small): 5 launches in all
-        static int smem_set = 0;
-        if (!smem_set) {
+        static bool smem_set[64] = {};
+        if (first_on_device(smem_set))
             PXF_CUDA(cudaFuncSetAttribute(k_small_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
-            smem_set = 1;
-        }
         k_select_sample_sums<<<grid_for(BRACKET_SAMPLES, PXF_BLOCK, 4), PXF_BLOCK, 0, s>>>(
             x, y, num, sums_dev, w.cxy, BRACKET_SAMPLES, w.samp);
         k_small_select<<<1, 1024, 2 * 8192 * 4, s>>>(w.samp, nullptr, 1, BRACKET_SAMPLES, (unsigned long long)ra,

@@ -306,8 +306,9 @@ static int launch_tma(const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8_t *
     int nrow = 0;
     for (int r = 0; r < 10; r++) nrow += (lm >> r) & 1u;
     const size_t smem = (size_t)NST * nrow * PXF_BLOCK * 8 + 2 * NST * 8;
-    if (ctas == 0 || LMc == 0) {
-        // (runtime masks: the ring size depends on the live rows, so re-query)
+    static bool seen[64] = {};
+    if (first_on_device(seen) || ctas == 0 || LMc == 0) {
+        // (runtime masks: the ring size depends on the live rows, so re-query; the attribute is per device)
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * NST * PXF_BLOCK * 8 + 2 * NST * 8) != cudaSuccess) {
             cudaGetLastError();
             return PXF_ERR_UNSUPPORTED;

@@ -20,10 +20,41 @@ PXF_DEV double ray_row(const Ray &r, int row)
 // returns false when the ray is vignetted at this op
 // ZERN: whether this instantiation carries the Zernike evaluation at all -- it needs ~3x the registers of every
 // other op, so programs without a PXF_OP_ZERNSURF op run a kernel compiled without it
-template <bool ZERN = false>
-PXF_DEV bool run_op(Ray &r, const FusedOp &op, const ZernP *zt = nullptr)
+// one atomic per warp: the largest grating count seen by the lanes that are here together
+PXF_DEV void count_max_update(int *dst, int k)
+{
+    const unsigned act = __activemask();
+    const int m = __reduce_max_sync(act, k);
+    if ((threadIdx.x & 31) == (__ffs(act) - 1)) atomicMax(dst, m);
+}
+
+// i: the ray's index in the bundle (side arrays); aux_*: FusedProgram::aux_* (null unless the program uses them)
+// AUX: whether this instantiation carries the side-array ops (the grating fan: asin + a data-dependent loop) -- like
+// ZERN they get their own kernel so that every other program keeps its register budget
+template <bool ZERN = false, bool AUX = false>
+PXF_DEV bool run_op(Ray &r, const FusedOp &op, const ZernP *zt = nullptr, int64_t i = 0,
+                    const double *aux_wave = nullptr, int *aux_count = nullptr, int *aux_count_max = nullptr)
 {
     switch (op.code) {
+        case PXF_OP_KICKN: op_kickn(r, *reinterpret_cast<const KickNP *>(op.q)); break;
+        case PXF_OP_VIGNETTE_RHOGT: {
+            double rho = sqrt(sq(r.x) + sq(r.y));
+            return rho > op.q[0];
+        }
+        case PXF_OP_GRATFAN:
+            if constexpr (AUX) {
+                const GratFanP &p = *reinterpret_cast<const GratFanP *>(op.q);
+                const int k = op_gratfan(r, p, p.wave_array ? aux_wave[i] : p.g.wave);
+                if (aux_count) aux_count[i] = k;
+                if (aux_count_max) count_max_update(aux_count_max, k < 0 ? p.cap + 1 : k);
+            }
+            break;
+        case PXF_OP_ROTX_REMAINING:
+            if constexpr (AUX) {
+                const int k = aux_count[i];
+                if (k >= 0) op_rotx_repeat(r, *reinterpret_cast<const TransformP *>(op.q), op.row - k);
+            }
+            break;
         case PXF_OP_TRANSFORM: op_transform(r, *reinterpret_cast<const TransformP *>(op.q)); break;
         case PXF_OP_ITRANSFORM: op_itransform(r, *reinterpret_cast<const TransformP *>(op.q)); break;
         case PXF_OP_REFLECT: op_reflect(r); break;
@@ -56,6 +87,7 @@ PXF_DEV bool run_op(Ray &r, const FusedOp &op, const ZernP *zt = nullptr)
         }
         case PXF_OP_VIGNETTE_ABS: {
             double v = ray_row(r, op.row);
+            if (op.q[2] != 0.) v = v - op.q[1];        // |row - centre| < hi (the centre is optional: v - 0 is v, but skip it)
             return fabs(v) < op.q[0];
         }
         case PXF_OP_ZERNSURF:
@@ -75,15 +107,15 @@ PXF_DEV bool run_op(Ray &r, const FusedOp &op, const ZernP *zt = nullptr)
     return true;
 }
 
-template <bool ZERN = false>
-PXF_DEV bool run_program(Ray &r, const FusedProgram &prog, const ZernP *zt = nullptr)
+template <bool ZERN = false, bool AUX = false>
+PXF_DEV bool run_program(Ray &r, const FusedProgram &prog, const ZernP *zt = nullptr, int64_t i = 0)
 {
     for (int k = 0; k < prog.nops; k++)
-        if (!run_op<ZERN>(r, prog.ops[k], zt)) return false;
+        if (!run_op<ZERN, AUX>(r, prog.ops[k], zt, i, prog.aux_wave, prog.aux_count, prog.aux_count_max)) return false;
     return true;
 }
 
-template <bool VEC2, int MINB = 1, bool ZERN = false>
+template <bool VEC2, int MINB = 1, bool ZERN = false, bool AUX = false>
 __global__ void __launch_bounds__(PXF_BLOCK, MINB)
 k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restrict__ alive,
           double *__restrict__ partials, const __grid_constant__ FusedProgram prog)
@@ -109,8 +141,8 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const int64_t i = q << 1;
             Ray a, b;
             fload2(a, b, P, LM, i);
-            const bool ka = run_program<ZERN>(a, prog, zt);
-            const bool kb = run_program<ZERN>(b, prog, zt);
+            const bool ka = run_program<ZERN, AUX>(a, prog, zt, i);
+            const bool kb = run_program<ZERN, AUX>(b, prog, zt, i + 1);
             fstore2(a, b, Q, SM, i);
             if (alive) { alive[i] = ka ? 1 : 0; alive[i + 1] = kb ? 1 : 0; }
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -120,7 +152,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
             const int64_t i = num - 1;
             Ray a;
             fload1(a, P, LM, i);
-            const bool ka = run_program<ZERN>(a, prog, zt);
+            const bool ka = run_program<ZERN, AUX>(a, prog, zt, i);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -129,7 +161,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
         for (int64_t i = tid; i < num; i += nthr) {
             Ray a;
             fload1(a, P, LM, i);
-            const bool ka = run_program<ZERN>(a, prog, zt);
+            const bool ka = run_program<ZERN, AUX>(a, prog, zt, i);
             fstore1(a, Q, SM, i);
             if (alive) alive[i] = ka ? 1 : 0;
             if (ka) { cnt += 1.; sx += a.x; sy += a.y; }
@@ -214,16 +246,20 @@ static void op_masks(int code, int row, unsigned &use, unsigned &st, unsigned &k
         case PXF_OP_VIGNETTE_MAG: use = R_DIR; st = 0; kill = 0; break;
         case PXF_OP_VIGNETTE_BOX: case PXF_OP_VIGNETTE_ABS: use = 1u << row; st = 0; kill = 0; break;
         case PXF_OP_KICK: use = R_L | R_M; st = R_DIR; kill = R_N; break;
+        case PXF_OP_KICKN: use = R_DIR; st = R_DIR; kill = 0; break;
+        case PXF_OP_VIGNETTE_RHOGT: use = R_X | R_Y; st = 0; kill = 0; break;
+        case PXF_OP_GRATFAN: case PXF_OP_ROTX_REMAINING: use = R_NINE; st = R_NINE; kill = 0; break;
         case PXF_OP_ZERNSURF: use = R_POS | R_DIR | (row ? R_OPD : 0u); st = R_POS | R_NRM | (row ? R_OPD : 0u); kill = R_POS | R_NRM; break;
         default: use = 0; st = 0; kill = 0; break;
     }
 }
 
-int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
+int build_program(FusedProgram &fp, const pxf_op *ops, int nops, const pxf_program_aux *aux)
 {
     if (!ops || nops < 1 || nops > PXF_MAX_OPS) { set_error("program: need 1..%d ops", PXF_MAX_OPS); return PXF_ERR_INVALID; }
     memset(&fp, 0, sizeof(fp));
     fp.nops = nops;
+    if (aux) { fp.aux_wave = aux->wave; fp.aux_count = aux->count; fp.aux_count_max = aux->count_max; }
     unsigned store = 0;
     for (int k = 0; k < nops; k++) {
         const pxf_op &o = ops[k];
@@ -254,9 +290,35 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
             case PXF_OP_VIGNETTE_ABS:
                 f.row = (int)p[0];
                 if (f.row < 0 || f.row > 9) { set_error("program: bad row in VIGNETTE_ABS"); return PXF_ERR_INVALID; }
-                f.q[0] = p[1];
+                f.q[0] = p[1]; f.q[1] = p[2]; f.q[2] = (p[2] != 0.) ? 1. : 0.;
                 break;
             case PXF_OP_KICK: f.q[0] = p[0]; f.q[1] = p[1]; f.q[2] = p[2]; break;
+            case PXF_OP_KICKN: { KickNP t; t.dl = p[0]; t.dm = p[1]; t.dl2 = p[0] * p[0]; t.dm2 = p[1] * p[1]; memcpy(f.q, &t, sizeof(t)); break; }
+            case PXF_OP_VIGNETTE_RHOGT: f.q[0] = p[0]; break;
+            case PXF_OP_GRATFAN: {
+                // p: ang, hubdist, l, dpermm, order, wave (NaN: per-ray wavelengths).  The script's
+                // tran.transform(rays,0,0,0,ang,0,0) reaches the Fortran negated (transformations.py:29).
+                GratFanP t;
+                memset(&t, 0, sizeof(t));
+                t.rot = make_transform(0., 0., 0., -p[0], 0., 0.);
+                t.wave_array = (p[5] != p[5]) ? 1 : 0;
+                t.g = make_radgrat(t.wave_array ? 0. : p[5], p[3], p[4]);
+                t.hub = p[1]; t.hub_l = p[2] + p[1]; t.thresh = .001;
+                t.cap = (aux && aux->cap > 0) ? aux->cap : 4096;
+                if (t.wave_array && !(aux && aux->wave)) { set_error("program: PXF_OP_GRATFAN with wave = NaN needs aux.wave"); return PXF_ERR_INVALID; }
+                memcpy(f.q, &t, sizeof(t));
+                fp.uses_aux = 1;
+                break;
+            }
+            case PXF_OP_ROTX_REMAINING: {
+                if (!(aux && aux->count)) { set_error("program: PXF_OP_ROTX_REMAINING needs aux.count"); return PXF_ERR_INVALID; }
+                if (!(p[1] >= 0. && p[1] <= 1.e6)) { set_error("program: PXF_OP_ROTX_REMAINING: bad total"); return PXF_ERR_INVALID; }
+                TransformP t = make_transform(0., 0., 0., -p[0], 0., 0.);
+                memcpy(f.q, &t, sizeof(t));
+                f.row = (int)p[1];                     // total rotations of the loop
+                fp.uses_aux = 1;
+                break;
+            }
             case PXF_OP_ZERNSURF: {
                 const ZernP *tab;
                 memcpy(&tab, &p[0], sizeof(tab));
@@ -269,7 +331,8 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
             }
             default: set_error("program: unknown opcode %d", o.code); return PXF_ERR_INVALID;
         }
-        if (o.code == PXF_OP_VIGNETTE_MAG || o.code == PXF_OP_VIGNETTE_BOX || o.code == PXF_OP_VIGNETTE_ABS)
+        if (o.code == PXF_OP_VIGNETTE_MAG || o.code == PXF_OP_VIGNETTE_BOX || o.code == PXF_OP_VIGNETTE_ABS ||
+            o.code == PXF_OP_VIGNETTE_RHOGT)
             fp.has_vignette = 1;
         unsigned use, st, kill;
         op_masks(o.code, f.row, use, st, kill);
@@ -309,6 +372,10 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops)
     }
     fp.load_mask = live;
     fp.store_mask = store;
+    // A ray stopped by a vignette predicate is stored in the state it had AT the predicate (the contract for dead
+    // rays: whatever the ops before the predicate made of them, nothing after).  Rows a later op would have
+    // overwritten are dead for the survivors but not for the stopped rays, so they must be loaded as well.
+    if (fp.has_vignette) fp.load_mask |= store;
     return PXF_OK;
 }
 
@@ -350,7 +417,11 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         if (grid_out) *grid_out = grid;
         kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, fp);
     };
-    if (fp.zern) {
+    if (fp.uses_aux) {
+        if (fp.zern) { set_error("program: a Zernike surface and a grating fan in one program are not supported"); return PXF_ERR_UNSUPPORTED; }
+        go(k_program<false, 3, false, true>, num);
+    }
+    else if (fp.zern) {
         // one ray per thread; PXF_ZERNPROG_MINB (tuning): register cap for 1 / 2 / 3 resident CTAs per SM.  Measured on
         // config 3's 14-op program at 5e7 rays: 9.40 / 6.28 / 6.01 ms (4: 6.28 ms); the same work as three launches
         // (transform, tracezern, 12-op tail) takes 7.0 ms
@@ -371,6 +442,8 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
 }  // namespace pxf
 
 using namespace pxf;
+// pxf_analysis.cu
+namespace pxf { int sums_finalize(const double *partial, int nblocks, int ns, double *out_dev, cudaStream_t s); }
 
 extern "C" int pxf_trace_program(double *const rays[10], int64_t num, const pxf_op *ops, int32_t nops,
                                  uint8_t *alive, pxf_stream_t stream)
@@ -392,6 +465,28 @@ extern "C" int pxf_trace_program_to(double *const rays_in[10], double *const ray
     // bundle, so every row the program touches is stored
     fp.store_mask |= fp.load_mask;
     return launch_program(rays_in, num, fp, alive, reinterpret_cast<cudaStream_t>(stream), rays_out, nullptr, nullptr);
+}
+
+extern "C" int pxf_trace_program_aux(double *const rays_in[10], double *const rays_out[10], int64_t num,
+                                     const pxf_op *ops, int32_t nops, uint8_t *alive, const pxf_program_aux *aux,
+                                     double *sums_dev, void *scratch, pxf_stream_t stream)
+{
+    FusedProgram fp;
+    int rc = build_program(fp, ops, nops, aux);
+    if (rc) return rc;
+    if (rays_out) fp.store_mask |= fp.load_mask;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!sums_dev) return launch_program(rays_in, num, fp, alive, s, rays_out, nullptr, nullptr);
+    if (!scratch) { set_error("pxf_trace_program_aux: sums need scratch"); return PXF_ERR_INVALID; }
+    fp.load_mask |= (R_X | R_Y) & ~fp.store_mask;
+    if (num == 0) {
+        PXF_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), s));
+        return PXF_OK;
+    }
+    int grid = 0;
+    rc = launch_program(rays_in, num, fp, alive, s, rays_out, static_cast<double *>(scratch), &grid);
+    if (rc) return rc;
+    return sums_finalize(static_cast<const double *>(scratch), grid, 4, sums_dev, s);
 }
 
 extern "C" size_t pxf_zern_table_bytes(void) { return sizeof(ZernP); }
@@ -438,7 +533,7 @@ extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t
         FusedProgram fp;
         int rc = build_program(fp, ops + (size_t)sgm * nops, nops);
         if (rc) return rc;
-        if (fp.zern) { set_error("segmented program: PXF_OP_ZERNSURF is not supported"); return PXF_ERR_UNSUPPORTED; }
+        if (fp.zern || fp.uses_aux) { set_error("segmented program: PXF_OP_ZERNSURF / PXF_OP_GRATFAN are not supported"); return PXF_ERR_UNSUPPORTED; }
         if (sgm > 0)
             for (int k = 0; k < nops; k++)
                 if (fp.ops[k].code != dst[k].code || fp.ops[k].row != dst[k].row) {   // dst[0..nops) = segment 0
@@ -480,7 +575,8 @@ extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *co
     const FusedOp *hops = reinterpret_cast<const FusedOp *>(static_cast<const char *>(table_host) + seg_ops_offset(nseg));
     bool vig = false;
     for (int k = 0; k < nops; k++)
-        if (hops[k].code == PXF_OP_VIGNETTE_MAG || hops[k].code == PXF_OP_VIGNETTE_BOX || hops[k].code == PXF_OP_VIGNETTE_ABS) vig = true;
+        if (hops[k].code == PXF_OP_VIGNETTE_MAG || hops[k].code == PXF_OP_VIGNETTE_BOX || hops[k].code == PXF_OP_VIGNETTE_ABS ||
+            hops[k].code == PXF_OP_VIGNETTE_RHOGT) vig = true;
     if (vig && !alive) { set_error("program with a VIGNETTE op needs an alive array"); return PXF_ERR_INVALID; }
     const char *db = static_cast<const char *>(table_dev);
     const long long *dstart = reinterpret_cast<const long long *>(db + seg_align(sizeof(SegHeader)));
@@ -498,9 +594,6 @@ extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *co
     count_launch();
     return check_launch("k_program_seg");
 }
-
-// pxf_analysis.cu
-namespace pxf { int sums_finalize(const double *partial, int nblocks, int ns, double *out_dev, cudaStream_t s); }
 
 extern "C" int pxf_trace_program_sums(double *const rays_in[10], double *const rays_out[10], int64_t num,
                                       const pxf_op *ops, int32_t nops, uint8_t *alive, double *sums_dev,

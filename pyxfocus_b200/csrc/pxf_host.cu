@@ -270,9 +270,11 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
             });
     }
     struct Joiner {       // error paths: stop the fillers and drain the callbacks that point at `uploaded`
-        std::vector<std::thread> &th; std::atomic<bool> &ab; cudaStream_t s; bool ok = false;
-        ~Joiner() { if (!ok) { ab.store(true); cudaStreamSynchronize(s); } for (auto &t : th) if (t.joinable()) t.join(); }
-    } joiner{fillers, abort_fill, R.s_in};
+        std::vector<std::thread> &th; std::atomic<bool> &ab; cudaStream_t s, s2, s3; bool ok = false;
+        // on failure nothing may still be writing into the caller's host rows after we return: drain all three streams
+        ~Joiner() { if (!ok) { ab.store(true); cudaStreamSynchronize(s); cudaStreamSynchronize(s2); cudaStreamSynchronize(s3); }
+                    for (auto &t : th) if (t.joinable()) t.join(); }
+    } joiner{fillers, abort_fill, R.s_in, R.s_run, R.s_out};
 
     int64_t alive_total = 0;
     size_t h2d_skipped = 0;

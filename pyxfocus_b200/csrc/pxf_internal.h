@@ -15,6 +15,18 @@ void count_launch(int n = 1);
 int sm_count();
 int opt_ws_libm();      // PXF_OPT_WS_LIBM
 
+// Per-device one-time guard: function attributes (cudaFuncSetAttribute) belong to a device's primary context, so
+// a process that works on cuda:0 and then on cuda:1 has to set them again there.  `seen` is a zero-initialised
+// static array at the call site; true exactly once per device.
+inline bool first_on_device(bool (&seen)[64])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return true; }
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 // Persistent grid: SM count x resident CTAs, capped by the work available.
 int grid_for(int64_t work_items, int per_block, int ctas_per_sm);
 

@@ -23,10 +23,16 @@ struct FusedProgram {
     unsigned const_mask;
     double const_val[10];
     const ZernP *zern;       // device table of the program's PXF_OP_ZERNSURF op (NULL: none); staged in shared memory
+    // per-ray side arrays (pxf_program_aux): wavelengths / grating counts of PXF_OP_GRATFAN, PXF_OP_ROTX_REMAINING
+    const double *aux_wave;
+    int *aux_count;
+    int *aux_count_max;
+    int uses_aux;            // some op reads or writes a side array (needs the ray index)
     FusedOp ops[PXF_MAX_OPS];
 };
 
 static_assert(sizeof(WSP) <= FOP_PARAM_DOUBLES * 8, "WSP does not fit a fused op slot");
+static_assert(sizeof(GratFanP) <= FOP_PARAM_DOUBLES * 8, "GratFanP does not fit a fused op slot");
 static_assert(sizeof(ConicP) <= FOP_PARAM_DOUBLES * 8, "ConicP does not fit");
 static_assert(sizeof(WolterSineP) <= FOP_PARAM_DOUBLES * 8, "WolterSineP does not fit");
 
@@ -94,7 +100,7 @@ PXF_DEV void centroid_block_reduce(double cnt, double sx, double sy, double *__r
 }
 
 // pxf_fused.cu
-int build_program(FusedProgram &fp, const pxf_op *ops, int nops);
+int build_program(FusedProgram &fp, const pxf_op *ops, int nops, const pxf_program_aux *aux = nullptr);
 // partials (nullable): device double[grid*9] receiving the per-CTA centroid sums; *grid_out = CTAs launched
 int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, uint8_t *alive, cudaStream_t s,
                    double *const rays_out[10] = nullptr, double *partials = nullptr, int *grid_out = nullptr);

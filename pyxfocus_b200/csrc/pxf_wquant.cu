@@ -480,11 +480,10 @@ int pxf_wq_collect(const double *x, const double *y, const double *w, int64_t nu
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     WqState *st = static_cast<WqState *>(state);
     double *partial = static_cast<double *>(scratch);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_on_device(attr)) {
         PXF_CUDA(cudaFuncSetAttribute(k_wq_collect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqStage)));
         PXF_CUDA(cudaFuncSetAttribute(k_wq_collect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqStage)));
-        attr = true;
     }
     int grid = 1;
     if (num > 0) {

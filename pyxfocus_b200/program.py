@@ -32,9 +32,10 @@ from ._call import stream_ptr
 OP = dict(TRANSFORM=1, ITRANSFORM=2, REFLECT=3, REFRACT=4, RADGRAT=5, FLAT=6, FLATOPD=7, CONIC=8,
           CONICOPD=9, WOLTERPRIMARY=10, WOLTERPRIMARYOPD=11, WOLTERSECONDARY=12, WOLTERSINE=13,
           WSPRIMARY=14, WSSECONDARY=15, SPOCONE=16, VIGNETTE_MAG=17, VIGNETTE_BOX=18,
-          VIGNETTE_ABS=19, KICK=20, ZERNSURF=21)
+          VIGNETTE_ABS=19, KICK=20, ZERNSURF=21, KICKN=22, VIGNETTE_RHOGT=23, GRATFAN=24, ROTX_REMAINING=25)
 MAX_OPS = 24
-_VIGNETTES = (OP["VIGNETTE_MAG"], OP["VIGNETTE_BOX"], OP["VIGNETTE_ABS"])
+_VIGNETTES = (OP["VIGNETTE_MAG"], OP["VIGNETTE_BOX"], OP["VIGNETTE_ABS"], OP["VIGNETTE_RHOGT"])
+_AUX_OPS = (OP["GRATFAN"], OP["ROTX_REMAINING"])
 
 
 class Program:
@@ -138,9 +139,35 @@ class Program:
         """keep rays with lo < rays[row] < hi"""
         return self.add(OP["VIGNETTE_BOX"], row, lo, hi)
 
-    def vignette_abs(self, row, hi):
-        """keep rays with |rays[row]| < hi"""
-        return self.add(OP["VIGNETTE_ABS"], row, hi)
+    def vignette_abs(self, row, hi, centre=0.):
+        """keep rays with |rays[row] - centre| < hi"""
+        return self.add(OP["VIGNETTE_ABS"], row, hi, centre)
+
+    def vignette_rhogt(self, rho0):
+        """keep rays with sqrt(x^2+y^2) > rho0 (examples/axro/axialHeights.py:285-286)"""
+        return self.add(OP["VIGNETTE_RHOGT"], rho0)
+
+    def kickn(self, dl, dm):
+        """l += dl, m += dm, n = -sqrt(n^2-dl^2-dm^2) (pointing offsets, examples/arcus/cat.py:246-249)"""
+        return self.add(OP["KICKN"], dl, dm)
+
+    def gratfan(self, ang, hubdist, l, dpermm, order, wave):
+        """The fanned radial-grating array of examples/arcus/sector.py:681-707 as one per-ray loop: each ray is
+        rotated about the hub axis by ``ang`` per grating (traced to the grating plane when steep enough) until it
+        lands between ``hubdist`` and ``l + hubdist`` from the hub, then reflected and diffracted.  ``wave``: a
+        float [nm] (radgrat) or a per-ray CUDA tensor (radgratW).  ``run`` needs ``aux=FanAux(...)``: the per-ray
+        grating index and its maximum come back there."""
+        if isinstance(wave, torch.Tensor):
+            self._wave = wave
+            w = float("nan")
+        else:
+            w = float(wave)
+        return self.add(OP["GRATFAN"], ang, hubdist, l, dpermm, order, w)
+
+    def rotx_remaining(self, ang, total):
+        """transform(0,0,0,ang,0,0) applied (total - count[i]) times: the whole-bundle fan rotations a ray still
+        receives after it met its grating (sector.py:693), with ``count`` from a previous ``gratfan``."""
+        return self.add(OP["ROTX_REMAINING"], ang, total)
 
     def kick(self, dl, dm, sn):
         """l += dl, m += dm, n = sn*sqrt(1-l^2-m^2) (field-angle kick, axialHeights.py:94-95)"""
@@ -167,7 +194,7 @@ class Program:
                 arr[k].p[0] = struct.unpack("d", struct.pack("Q", self._dev_tables[key].data_ptr()))[0]
         return arr
 
-    def run(self, rays, alive=None, out=None, sums=None):
+    def run(self, rays, alive=None, out=None, sums=None, aux=None):
         """Execute on a bundle (list of ten CUDA fp64 rows).  Returns the ``alive`` uint8
         tensor when the program contains a vignette predicate (allocated if not given).
         ``out``: optional second bundle -- rows are read from ``rays`` and every row the program
@@ -185,8 +212,14 @@ class Program:
             tail._tables = {k - MAX_OPS: v for k, v in self._tables.items() if k >= MAX_OPS}
             if head.has_vignette() or tail.has_vignette():
                 raise ValueError("programs with vignette predicates are limited to %d ops" % MAX_OPS)
-            head.run(rays, out=out)
-            return tail.run(out if out is not None else rays, sums=sums)
+            if out is not None:
+                # the head stores only the rows it touches: give `out` every row first, then run both parts in place
+                for k in range(10):
+                    if rays[k] is not None and out[k] is not None:
+                        out[k].copy_(rays[k])
+                rays = out
+            head.run(rays)
+            return tail.run(rays, sums=sums)
         dev = rays[1].device
         num = rays[1].shape[0]
         for r in rays:
@@ -201,9 +234,25 @@ class Program:
         optrs = None
         if out is not None:
             optrs = (ctypes.c_void_p * 10)(*[(r.data_ptr() if r is not None else None) for r in out])
+        uses_aux = any(c in _AUX_OPS for c, _ in self.ops)
+        if uses_aux and aux is None:
+            raise ValueError("programs with gratfan / rotx_remaining need aux=FanAux(...)")
         with torch.cuda.device(dev):
             L = _lib.lib()
-            if sums is not None:
+            if uses_aux:
+                if sums is not None and (not sums.is_cuda or sums.dtype != torch.float64 or sums.numel() < 16):
+                    raise ValueError("sums must be a contiguous CUDA float64 tensor with >= 16 entries")
+                scratch = (torch.empty(int(L.pxf_sums_scratch_bytes()), dtype=torch.uint8, device=dev)
+                           if sums is not None else None)
+                wave = getattr(self, "_wave", None)
+                if wave is not None and (not wave.is_cuda or wave.dtype != torch.float64 or not wave.is_contiguous()
+                                         or wave.shape[0] != num):
+                    raise ValueError("wave must be a contiguous CUDA float64 tensor with one entry per ray")
+                ca = aux.c_struct(num, dev, wave)
+                rc = L.pxf_trace_program_aux(ptrs, optrs, num, ops, len(self.ops), ap, ctypes.byref(ca),
+                                             sums.data_ptr() if sums is not None else None,
+                                             scratch.data_ptr() if scratch is not None else None, stream_ptr(dev))
+            elif sums is not None:
                 if not sums.is_cuda or sums.dtype != torch.float64 or sums.numel() < 16 or not sums.is_contiguous():
                     raise ValueError("sums must be a contiguous CUDA float64 tensor with >= 16 entries")
                 scratch = torch.empty(int(L.pxf_sums_scratch_bytes()), dtype=torch.uint8, device=dev)
@@ -215,6 +264,33 @@ class Program:
                 rc = L.pxf_trace_program_to(ptrs, optrs, num, ops, len(self.ops), ap, stream_ptr(dev))
         _lib.check(rc)
         return alive
+
+
+class FanAux:
+    """Side arrays of a grating-fan program (include/pxf.h, pxf_program_aux): ``count`` int32[num] = gratings passed
+    per ray (-1: none met), ``count_max`` int32[1] = the largest (cap + 1 if some ray met none)."""
+
+    def __init__(self, num, device, cap=4096):
+        self.count = torch.empty(int(num), dtype=torch.int32, device=device)
+        self.count_max = torch.zeros(1, dtype=torch.int32, device=device)
+        self.cap = int(cap)
+
+    def c_struct(self, num, dev, wave):
+        if self.count.shape[0] != num or self.count.device != dev:
+            raise ValueError("FanAux was made for another bundle")
+        a = _lib.pxf_program_aux()
+        a.wave = wave.data_ptr() if wave is not None else None
+        a.count = self.count.data_ptr()
+        a.count_max = self.count_max.data_ptr()
+        a.cap = self.cap
+        return a
+
+    def gratings(self):
+        """Largest grating index of the launch (one 4-byte read-back); raises if some ray met no grating."""
+        k = int(self.count_max.item())
+        if k > self.cap:
+            raise RuntimeError("gratfan: rays left after %d gratings (they never meet the array)" % self.cap)
+        return k
 
 
 class SegmentedProgram:
@@ -293,6 +369,16 @@ def recorder_for(rays):
     return ent[1] if ent is not None and ent[0] is rays else None
 
 
+_alive = {}      # id(rays list) -> (rays, uint8 flags) left by the vignette predicates of the last recording
+
+
+def last_alive(rays):
+    """uint8 flag row written by the vignette predicates recorded for this bundle (1 = the ray passed every
+    predicate), or None when the recording had none.  ``transformations.compact(rays, flags)`` removes the rest."""
+    ent = _alive.get(id(rays))
+    return ent[1] if ent is not None and ent[0] is rays else None
+
+
 def flush(rays):
     """Execute whatever is pending for this bundle (called by anything that reads the rays)."""
     prog = recorder_for(rays)
@@ -300,7 +386,11 @@ def flush(rays):
         todo = Program()
         todo.ops, prog.ops = prog.ops, []
         todo._tables, prog._tables = prog._tables, {}
-        todo.run(rays)
+        alive = todo.run(rays)
+        if alive is not None:
+            prev = last_alive(rays)
+            # (a ray stopped in an earlier launch of the same recording stays stopped)
+            _alive[id(rays)] = (rays, alive if prev is None else torch.minimum(prev, alive))
 
 
 class fused:
@@ -314,6 +404,7 @@ class fused:
         if id(self.rays) in _active:
             raise RuntimeError("bundle is already recording")
         _active[id(self.rays)] = (self.rays, Program())
+        _alive.pop(id(self.rays), None)
         return self.rays
 
     def __exit__(self, et, ev, tb):

@@ -255,13 +255,26 @@ def ellipsoidSecondaryLL(rays, R0, F, S, psi, zmax, zmin, dphi, coeff, axial, az
 
 
 def focus(rays, fn, weights=None, nr=None, coords=None):
-    """Two-pass best focus (surfaces.py:502-510)."""
+    """Two-pass best focus (surfaces.py:502-510).  Each "move the plane, trace to it" pair runs as one fused
+    kernel (same bits as the two calls)."""
+    from .program import fused, recorder_for
+    own = recorder_for(rays) is None
     dz1 = fn(rays, weights=weights)
-    tran.transform(rays, 0, 0, dz1, 0, 0, 0, coords=coords)
-    flat(rays, nr=nr)
+    if own:
+        with fused(rays):
+            tran.transform(rays, 0, 0, dz1, 0, 0, 0, coords=coords)
+            flat(rays, nr=nr)
+    else:
+        tran.transform(rays, 0, 0, dz1, 0, 0, 0, coords=coords)
+        flat(rays, nr=nr)
     dz2 = fn(rays, weights=weights)
-    tran.transform(rays, 0, 0, dz2, 0, 0, 0, coords=coords)
-    flat(rays, nr=nr)
+    if own:
+        with fused(rays):
+            tran.transform(rays, 0, 0, dz2, 0, 0, 0, coords=coords)
+            flat(rays, nr=nr)
+    else:
+        tran.transform(rays, 0, 0, dz2, 0, 0, 0, coords=coords)
+        flat(rays, nr=nr)
     return dz1 + dz2
 
 

@@ -181,20 +181,29 @@ def vignette(rays, ind=None):
         return compact(rays, flags)
 
 
-def compact(rays, flags):
-    """Order-preserving stream compaction of all ten rows by a uint8 flag row."""
+def compact(rays, flags, extra=None):
+    """Order-preserving stream compaction of all ten rows by a uint8 flag row.  ``extra``: further per-ray float64
+    rows (e.g. the weights that the reference scripts index with the same mask, ``weights = weights[ind]``)
+    compacted in the same pass; returns ``(bundle, [extra rows])`` then."""
     dev = rays[1].device
     num = rays[1].shape[0]
     L = _lib.lib()
     s = stream_ptr(dev)
+    extra = [] if extra is None else list(extra)
+    for e in extra:
+        if not e.is_cuda or e.dtype != torch.float64 or not e.is_contiguous() or e.shape[0] != num:
+            raise ValueError("extra rows must be contiguous float64 CUDA tensors with one entry per ray")
     with torch.cuda.device(dev):
         scratch = torch.empty(int(L.pxf_compact_scratch_bytes(num)), dtype=torch.uint8, device=dev)
         count = ctypes.c_int64(0)
         _lib.check(L.pxf_compact_count(flags.data_ptr(), num, scratch.data_ptr(), ctypes.byref(count), s))
-        out = bundle_alloc(count.value, dev)
-        pin = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
-        pout = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in out])
-        _lib.check(L.pxf_compact_scatter(pin, pout, 10, flags.data_ptr(), num, scratch.data_ptr(), s))
+        out = bundle_alloc(count.value, dev, nrows=10 + len(extra))
+        nr = 10 + len(extra)
+        pin = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in list(rays) + extra])
+        pout = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in out])
+        _lib.check(L.pxf_compact_scatter(pin, pout, nr, flags.data_ptr(), num, scratch.data_ptr(), s))
+    if extra:
+        return out[:10], out[10:]
     return out
 
 
@@ -290,6 +299,7 @@ def steerY(rays, coords=None):
     flush(rays)
     while abs(float(rays[5].mean())) > 1e-6:
         transform(rays, 0, 0, 0, -float(rays[5].mean()), 0, 0, coords=coords)
+        flush(rays)          # inside `with fused(rays)` the transform is only recorded: run it before re-reading the mean
     return
 
 
@@ -298,6 +308,7 @@ def steerX(rays, coords=None):
     flush(rays)
     while abs(float(rays[4].mean())) > 1e-6:
         transform(rays, 0, 0, 0, 0, -float(rays[4].mean()), 0, coords=coords)
+        flush(rays)
     return
 
 

@@ -1,0 +1,196 @@
+"""Whole-chain parity of BASELINE configs 1-5 on the GPU, three ways per configuration:
+
+    oracle      pyxfocus_b200/examples.py scripts on oracle.refapi (CPU restatement of the reference)
+    script      the SAME script text on the product's drop-in modules (per-routine kernels, torch masks)
+    fast        the GPU-arranged form (fused programs, segmented launches, in-kernel predicates, grating-fan loop)
+
+Bars: surviving-ray index sets / counts / grating indices identical; rows bit-exact where every routine on the
+chain is algebraic (configs 1, 5 and everything before the first libm routine), else 1e-12 (positions relative to
+the system length scale); HPD / rms / centroids 1e-9 relative.  ``fast`` must equal ``script`` bit for bit (same
+device code).  Also against the goldens produced by the reference's own Python layer (tests/golden/configs.npz).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from oracle import refapi  # noqa: E402
+from util import assert_bit_equal, assert_close  # noqa: E402
+from make_golden_configs import SIZES  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def pxf():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import pyxfocus_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def ex(pxf):
+    return pxf.examples
+
+
+@pytest.fixture(scope="module")
+def cpu(ex):
+    return ex.make_api(refapi.load(), ex.NumpyXP, "refapi")
+
+
+@pytest.fixture(scope="module")
+def gpu(ex):
+    return ex.product_api()
+
+
+def host(rays):
+    return [r.detach().cpu().numpy() for r in rays]
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def test_config1_all_three_ways(ex, cpu, gpu):
+    n = 100_000                                        # BASELINE configs[0] at its own size
+    o = ex.config1(cpu, n)
+    s = ex.config1(gpu, n)
+    f = ex.config1_fast(n)
+    assert_bit_equal(host(s["rays"]), o["rays"], rows=range(1, 10), what="config 1 script vs oracle")
+    assert_bit_equal(host(f["rays"]), o["rays"], rows=range(1, 10), what="config 1 fast vs oracle")
+    for r in (s, f):
+        assert rel(r["hpd"], o["hpd"]) <= 1e-9 and rel(r["rms"], o["rms"]) <= 1e-9
+    assert o["hpd"] == pytest.approx(1.278e-5, rel=2e-2)       # SURVEY.md 8d probe (REAL*4 delta signature)
+
+
+@pytest.mark.parametrize("arcmin", [0., 5., 10., 20., 30.])
+def test_config2_field_points(ex, cpu, gpu, arcmin):
+    n = 40_000
+    ap = ex.ws_aperture(cpu)
+    apg = ex.ws_aperture(gpu)                           # single-ray traces on the GPU
+    assert rel(apg[0], ap[0]) <= 1e-12 and rel(apg[1], ap[1]) <= 1e-12
+    th = arcmin / 60. * np.pi / 180.
+    o = ex.config2_point(cpu, n, th, ap)
+    s = ex.config2_point(gpu, n, th, ap)
+    f = ex.config2_point_fast(n, th, ap)
+    assert_bit_equal(host(f["rays"]), host(s["rays"]), what="config 2 fast vs script")
+    # rays the secondary's iteration cap restored in place are the "index set" of this configuration
+    bad = ~np.isfinite(o["rays"][1]) | (np.abs(o["rays"][1]) > 1e3)
+    got = host(s["rays"])
+    assert_close(got, o["rays"], pos_scale=1.e4, tol=1e-11, what="config 2 @ %g'" % arcmin)
+    for k in ("f", "hpd", "rms"):
+        assert rel(s[k], o[k]) <= 1e-9, (k, s[k], o[k])
+        assert rel(f[k], o[k]) <= 1e-9, (k, f[k], o[k])
+    assert s["d2"] == o["d2"] and s["d3"] == o["d3"] and f["d2"] == o["d2"] and f["d3"] == o["d3"]
+    if arcmin >= 20.:
+        assert bad.sum() > 0                            # beyond the graze angle: restored rays pollute the spot
+
+
+def test_config2_matches_reference_golden(ex, gpu, golden):
+    g = golden("configs")
+    ap = tuple(g["c2_aperture"])
+    for a in SIZES["c2_arcmin"]:
+        r = ex.config2_point_fast(SIZES["c2_n"], a / 60. * np.pi / 180., ap)
+        tag = "c2_%02d_" % int(a)
+        want = g[tag + "scalars"]
+        xy = np.stack([r["rays"][1].cpu().numpy(), r["rays"][2].cpu().numpy()])
+        assert np.abs(xy - g[tag + "xy"]).max() <= 1e-11 * 1e4, tag
+        assert rel(r["f"], want[0]) <= 1e-9 and r["d2"] == want[1] and r["d3"] == want[2], tag
+        assert rel(r["hpd"], want[3]) <= 1e-9 and rel(r["rms"], want[4]) <= 1e-9, tag
+
+
+def test_config3_whole_chain_with_index_set(ex, cpu, gpu, golden):
+    n = 200_000
+    o = ex.config3(cpu, n)
+    s = ex.config3(gpu, n)
+    f = ex.config3_fast(n)
+    for r, what in ((s, "script"), (f, "fast")):
+        assert np.array_equal(r["idx"].cpu().numpy(), o["idx"]), "config 3 %s: surviving-ray index set differs" % what
+        assert_close(host(r["rays"]), o["rays"], pos_scale=8.6e3, tol=1e-12, what="config 3 " + what)
+        assert rel(r["hpd"], o["hpd"]) <= 1e-9 and rel(r["rms"], o["rms"]) <= 1e-9
+    assert 0 < len(o["idx"]) < n
+    g = golden("configs")
+    r = ex.config3_fast(SIZES["c3_n"])
+    assert np.array_equal(r["idx"].cpu().numpy(), g["c3_idx"])
+    assert_close(host(r["rays"]), list(g["c3_rows"]), pos_scale=8.6e3, tol=1e-12, what="config 3 vs reference golden")
+    assert rel(r["hpd"], g["c3_scalars"][0]) <= 1e-9
+
+
+C4 = [(-1, 4.8), (-2, 2.4), (-3, 2.4), (-4, 1.2), (-5, .96), (-6, .8), (-7, .7), (-8, .6), (-1, "uniform")]
+
+
+@pytest.mark.parametrize("order,wave", C4, ids=["o%d_%s" % (-o, w) for o, w in C4])
+def test_config4_arcus_chain(ex, cpu, gpu, order, wave):
+    N, M = 150, 72                                      # 10 800 rays through 72 shells and ~26 gratings
+    kw = dict(order=order, wave=wave, offX=1e-4 if order == -2 else 0., offY=-5e-5 if order == -2 else 0.)
+    o = ex.config4(cpu, N, M, **kw)
+    f = ex.config4_fast(N, M, **kw)
+    ways = [(f, "fast")]
+    if order in (-3, -1):
+        s = ex.config4(gpu, N, M, **kw)                 # the script itself on the drop-in modules (masked launches)
+        ways.append((s, "script"))
+        assert_bit_equal(host(f["rays"]), host(s["rays"]), rows=range(1, 10), what="config 4 fast vs script")
+    for r, what in ways:
+        assert r["gratings"] == o["gratings"] and r["kept"] == o["kept"], what
+        assert_close(host(r["rays"]), o["rays"], pos_scale=1.2e4, tol=1e-12, rows=range(1, 10), what="config 4 " + what)
+        assert_close(host(r["surv"]), o["surv"], pos_scale=1.2e4, tol=1e-12, rows=range(1, 10), what="config 4 survivors " + what)
+        for k in ("dz", "cx", "cy"):
+            assert abs(r[k] - o[k]) <= 1e-9 * 1.2e4, (what, k, r[k], o[k])
+        assert rel(r["rmsY"], o["rmsY"]) <= 1e-6 and rel(r["hpdY"], o["hpdY"]) <= 1e-6, (what, r["rmsY"], o["rmsY"])
+    assert o["gratings"] >= 20
+
+
+def test_config4_matches_reference_golden(ex, golden):
+    g = golden("configs")
+    for order, wave in ((-1, 4.8), (-3, 2.4), (-8, .6)):
+        r = ex.config4_fast(SIZES["c4_n"], SIZES["c4_M"], order=order, wave=wave)
+        tag = "c4_o%d_s_" % (-order)
+        want = g[tag + "scalars"]
+        assert r["kept"] == want[0] and r["gratings"] == want[2]
+        assert_close(host(r["rays"])[1:], list(g[tag + "rows"]), pos_scale=1.2e4, tol=1e-12, rows=range(9), what=tag)
+        assert abs(r["dz"] - want[1]) <= 1e-9 * 1.2e4 and abs(r["cy"] - want[4]) <= 1e-9 * 1.2e4
+
+
+@pytest.mark.parametrize("offaxis", [0., 1. / 60. * np.pi / 180.])
+def test_config5_nested_assembly(ex, cpu, gpu, offaxis):
+    N, S = 700, 260                                     # 182 000 rays, 260 shells
+    o = ex.config5(cpu, N, S, offaxis=offaxis)
+    f = ex.config5_fast(N, S, offaxis=offaxis)
+    assert f["kept"] == o["kept"] and 0 < o["kept"] < N * S
+    assert_bit_equal(host(f["rays"]), o["rays"], rows=range(1, 10), what="config 5 fast vs oracle")
+    assert np.array_equal(f["weights"].cpu().numpy(), o["weights"])
+    for k in ("hpd", "rms", "area"):
+        assert rel(f[k], o[k]) <= 1e-9, (k, f[k], o[k])
+    assert abs(f["cx"] - o["cx"]) <= 1e-12 and abs(f["cy"] - o["cy"]) <= 1e-12
+    # the script itself, shell by shell on the drop-in modules, on a smaller assembly
+    o2 = ex.config5(cpu, 200, 40, offaxis=offaxis)
+    s2 = ex.config5(gpu, 200, 40, offaxis=offaxis)
+    assert s2["kept"] == o2["kept"]
+    assert_bit_equal(host(s2["rays"]), o2["rays"], rows=range(1, 10), what="config 5 script vs oracle")
+    assert rel(s2["hpd"], o2["hpd"]) <= 1e-9
+
+
+def test_config5_matches_reference_golden(ex, golden):
+    g = golden("configs")
+    r = ex.config5_fast(SIZES["c5_n"], SIZES["c5_shells"], offaxis=1. / 60. * np.pi / 180.)
+    want = g["c5_scalars"]
+    assert r["kept"] == want[0]
+    assert_bit_equal(host(r["rays"])[1:], list(g["c5_rows"]), rows=range(9), what="config 5 vs reference golden")
+    assert np.array_equal(r["weights"].cpu().numpy(), g["c5_weights"])
+    assert rel(r["hpd"], want[1]) <= 1e-9 and rel(r["rms"], want[2]) <= 1e-9
+
+
+def test_philox_sources_give_the_same_statistics(ex):
+    """Device-drawn sources (the throughput mode of bench.py's `configs`): same chains, different uniforms --
+    results agree with the numpy-seeded ones to sampling error."""
+    a = ex.config1_fast(200_000, rng="numpy")
+    b = ex.config1_fast(200_000, rng="philox")
+    assert rel(a["hpd"], b["hpd"]) <= .05
+    a = ex.config5_fast(300, 100)
+    b = ex.config5_fast(300, 100, rng="philox")
+    assert rel(a["area"], b["area"]) <= .02 and rel(a["hpd"], b["hpd"]) <= .25
