@@ -54,7 +54,7 @@ int64_t pxf_launch_count(void);
  *   instead of the algebraically identical transcendental-free form (half-angle identities, exp(k log x)).
  *   Both agree with the reference to 1e-12 on every converging ray; the libm form additionally reproduces the
  *   discrete outcome (restored or not) of the chaotic rays beyond the graze angle ray for ray. */
-enum pxf_option { PXF_OPT_WS_LIBM = 1 };
+enum pxf_option { PXF_OPT_WS_LIBM = 1, PXF_OPT_WS_RETRACE = 2, PXF_OPT_WS_GRAZE_PPM = 3 };
 int pxf_set_option(int32_t option, int32_t value);
 /* Iteration cap applied to the reference's uncapped Newton loops (oracle uses the same). */
 int pxf_newton_cap(void);
@@ -365,11 +365,18 @@ int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, 
  *   PXF_SUMS_IMAGEPLANE : [0]=sum w, [1]=sum w x, [2]=sum w y, [3]=sum w l/n, [4]=sum w m/n,
  *                         [5]=sum w x l/n, [6]=sum w y m/n, [7]=sum w (l/n)^2, [8]=sum w (m/n)^2
  * Deterministic (fixed-shape tree, no atomics).  scratch: pxf_sums_scratch_bytes() bytes. */
-enum { PXF_SUMS_CENTROID = 0, PXF_SUMS_RMS = 1, PXF_SUMS_IMAGEPLANE = 2 };
+enum { PXF_SUMS_CENTROID = 0, PXF_SUMS_RMS = 1, PXF_SUMS_IMAGEPLANE = 2, PXF_SUMS_IMAGEPLANE_Z = 3 };
 size_t pxf_sums_scratch_bytes(void);
 int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, const double *m,
              const double *n, const double *w, int64_t num, double a, double b,
              double *out_dev, void *scratch, pxf_stream_t stream);
+
+/* The PXF_SUMS_IMAGEPLANE sums taken at the rays' crossing of z = 0, (x - z l/n, y - z m/n): what a literal plane
+ * scan (move the plane by dz, trace to it, rmsCentroid -- the legacy findimageplane the reference's examples call,
+ * examples/axro/WSverify.py:161-164) needs when the rays are not on z = 0 (e.g. after transform(0,0,dz) without a
+ * flat).  analyticImagePlane itself ignores z (analyses.py:122-131) and uses pxf_sums. */
+int pxf_sums_z(const double *x, const double *y, const double *z, const double *l, const double *m,
+               const double *n, const double *w, int64_t num, double *out_dev, void *scratch, pxf_stream_t stream);
 
 /* rho[i] = sqrt((x-cx)^2+(y-cy)^2)  (analyses.py:60-71) */
 int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy, double *rho_out,

@@ -34,13 +34,48 @@ def build(force=False):
     return _SO
 
 
+_SO_CR = os.path.join(_HERE, "_build", "liboracle_cr.so")
+_libs = {}
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
         _lib = ctypes.CDLL(_SO)
         _declare(_lib)
+        _libs["system"] = _lib
     return _lib
+
+
+class libm:
+    """``with libm("cr"):`` -- run the oracle with every libm call correctly rounded (liboracle_cr.so: binary128
+    libquadmath, one rounding; see the header of pxf_oracle.c) instead of this image's glibc.  The reference's libm is
+    unpinned; for the chaotic Wolter-Schwarzschild rays the last bit of sin/atan2/pow decides discrete outcomes, and the
+    correctly rounded value is the one every libm approximates."""
+
+    def __init__(self, kind):
+        if kind not in ("cr", "system"):
+            raise ValueError(kind)
+        self.kind = kind
+
+    def __enter__(self):
+        global _lib
+        lib()
+        if self.kind not in _libs:
+            if not os.path.exists(_SO_CR) or os.path.getmtime(_SO_CR) < os.path.getmtime(_SRC):
+                subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+            L = ctypes.CDLL(_SO_CR)
+            _declare(L)
+            _libs[self.kind] = L
+        self.prev = _lib
+        _lib = _libs[self.kind]
+        return self
+
+    def __exit__(self, *a):
+        global _lib
+        _lib = self.prev
+        return False
 
 
 def _declare(L):

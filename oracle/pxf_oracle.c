@@ -33,6 +33,33 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* -DPXF_ORACLE_CR_LIBM (liboracle_cr.so): every libm call goes through binary128 (libquadmath) and is rounded
+ * to double ONCE -- correctly rounded results (up to the astronomically rare 113-bit ties).  The reference's own
+ * libm is unpinned (whatever glibc gfortran linked): glibc's double routines are within 1 ulp but
+ * not always the nearest double, and WHICH double they return differs between glibc versions.  For the chaotic
+ * Wolter-Schwarzschild rays beyond the graze angle that last bit decides discrete outcomes; the correctly rounded
+ * value is the one answer every conforming libm is an approximation of, so this variant is the canonical form the
+ * GPU's long-trip re-trace (which evaluates the same functions correctly rounded) is held to bit for bit. */
+#ifdef PXF_ORACLE_CR_LIBM
+#include <quadmath.h>
+static inline double cr_sin(double x) { return (double)sinq((__float128)x); }
+static inline double cr_cos(double x) { return (double)cosq((__float128)x); }
+static inline double cr_tan(double x) { return (double)tanq((__float128)x); }
+static inline double cr_asin(double x) { return (double)asinq((__float128)x); }
+static inline double cr_acos(double x) { return (double)acosq((__float128)x); }
+static inline double cr_atan(double x) { return (double)atanq((__float128)x); }
+static inline double cr_atan2(double y, double x) { return (double)atan2q((__float128)y, (__float128)x); }
+static inline double cr_pow(double x, double y) { return (double)powq((__float128)x, (__float128)y); }
+#define sin cr_sin
+#define cos cr_cos
+#define tan cr_tan
+#define asin cr_asin
+#define acos cr_acos
+#define atan cr_atan
+#define atan2 cr_atan2
+#define pow cr_pow
+#endif
+
 #define PXF_NEWTON_CAP 1000
 
 /* REAL*4 literals promoted to REAL*8 */

@@ -100,6 +100,7 @@ SIGNATURES = {
     # analyses
     "pxf_sums_scratch_bytes": (_sz, []),
     "pxf_sums": (_c.c_int, [_i32] + [_dp] * 6 + [_i64, _d, _d, _dp, _vp, _st]),
+    "pxf_sums_z": (_c.c_int, [_dp] * 7 + [_i64, _dp, _vp, _st]),
     "pxf_rho": (_c.c_int, [_dp, _dp, _i64, _d, _d, _dp, _st]),
     "pxf_select_state_bytes": (_sz, []),
     "pxf_select_begin": (_c.c_int, [_vp, _i64, _i64, _st]),
@@ -207,6 +208,8 @@ def check(rc):
 
 
 OPT_WS_LIBM = 1
+OPT_WS_RETRACE = 2
+OPT_WS_GRAZE_PPM = 3
 
 
 def set_option(option, value):

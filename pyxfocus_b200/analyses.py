@@ -179,9 +179,11 @@ def analyticImagePlane(rays, weights=None):
     return out.value
 
 
-def imageplane_sums(rays, weights=None):
+def imageplane_sums(rays, weights=None, at_z0=False):
     """The nine weighted sums behind ``analyticImagePlane`` / ``findimageplane`` as a device
-    tensor [S0, Sx, Sy, Sa, Sb, Sxa, Syb, Saa, Sbb] with a=l/n, b=m/n (one pass, 40 B/ray)."""
+    tensor [S0, Sx, Sy, Sa, Sb, Sxa, Syb, Saa, Sbb] with a=l/n, b=m/n (one pass, 40 B/ray).
+    ``at_z0``: take x, y where each ray crosses z = 0, (x - z a, y - z b) (48 B/ray) -- what a plane scan needs
+    when the rays are not on the plane; ``analyticImagePlane`` itself ignores z (analyses.py:122-131)."""
     flush(rays)
     x, y, z, l, m, n = rays[1:7]
     w = _w(weights, x)
@@ -190,12 +192,16 @@ def imageplane_sums(rays, weights=None):
     out = torch.zeros(16, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         scratch = torch.empty(int(L.pxf_sums_scratch_bytes()), dtype=torch.uint8, device=dev)
-        _lib.check(L.pxf_sums(2, x.data_ptr(), y.data_ptr(), l.data_ptr(), m.data_ptr(), n.data_ptr(), _ptr(w),
-                              x.shape[0], 0., 0., out.data_ptr(), scratch.data_ptr(), stream_ptr(dev)))
+        if at_z0:
+            _lib.check(L.pxf_sums_z(x.data_ptr(), y.data_ptr(), z.data_ptr(), l.data_ptr(), m.data_ptr(), n.data_ptr(),
+                                    _ptr(w), x.shape[0], out.data_ptr(), scratch.data_ptr(), stream_ptr(dev)))
+        else:
+            _lib.check(L.pxf_sums(2, x.data_ptr(), y.data_ptr(), l.data_ptr(), m.data_ptr(), n.data_ptr(), _ptr(w),
+                                  x.shape[0], 0., 0., out.data_ptr(), scratch.data_ptr(), stream_ptr(dev)))
     return out[:9]
 
 
-def findimageplane(rays, zscan, num, weights=None, sums=None):
+def findimageplane(rays, zscan, num, weights=None, sums=None, moved=0.):
     """Scan the axial offset over ``linspace(-zscan, zscan, num)`` and return the offset of
     minimum RMS spot radius about the centroid.
 
@@ -204,8 +210,15 @@ def findimageplane(rays, zscan, num, weights=None, sums=None):
     follows the legacy behaviour those call sites imply (move the plane by dz, trace to it,
     take rmsCentroid, keep the best dz).  Propagating a ray by dz changes (x,y) by
     (l/n, m/n)*dz, so RMS^2(dz) is an exact quadratic in dz whose coefficients are the nine
-    sums of ``analyticImagePlane``: one pass over the bundle instead of ``num`` passes."""
-    S = (sums if sums is not None else imageplane_sums(rays, weights)).cpu().numpy()
+    sums of ``analyticImagePlane`` (taken where the rays cross z = 0, so rays that are off the plane -- e.g.
+    after ``transform(rays,0,0,dz,...)`` without a ``flat`` -- scan as the literal loop would): one pass over the
+    bundle instead of ``num`` passes.  ``sums`` / ``moved``: sums from an earlier ``imageplane_sums(rays,
+    at_z0=True)`` and the z offset the frame has been moved by since (``transform(rays,0,0,moved,...)``): a second,
+    finer scan then costs no pass at all."""
+    S = (sums if sums is not None else imageplane_sums(rays, weights, at_z0=True)).cpu().numpy().copy()
+    if moved != 0.:
+        # the new z = 0 plane lies `moved` further along: x0' = x0 + moved a, y0' = y0 + moved b
+        S[1] += moved * S[3]; S[2] += moved * S[4]; S[5] += moved * S[7]; S[6] += moved * S[8]
     W = S[0]
     mx, my, ma, mb = S[1] / W, S[2] / W, S[3] / W, S[4] / W
     vxx = S[7] / W - ma * ma + S[8] / W - mb * mb            # Var(a)+Var(b)

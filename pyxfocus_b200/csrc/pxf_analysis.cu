@@ -13,7 +13,7 @@ namespace pxf {
 // ------------------------------------------------------------------ sums
 template <int MODE>
 PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m, double n, double w,
-                        bool has_w, double a, double b)
+                        bool has_w, double a, double b, double z = 0.)
 {
     if (MODE == PXF_SUMS_CENTROID) {
         acc[0] += w;
@@ -26,6 +26,12 @@ PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m
         acc[1] += has_w ? rho * w : rho;
     } else {
         double ln = l / n, mn = m / n;
+        if (MODE == PXF_SUMS_IMAGEPLANE_Z) {
+            // where the ray crosses z = 0: the literal plane scan (move the plane by dz, trace to it) propagates a
+            // ray by (dz - z)/n, so in terms of (x0, y0) its footprint at offset dz is (x0 + dz l/n, y0 + dz m/n)
+            x = x - ln * z;
+            y = y - mn * z;
+        }
         double t1 = x * l / n, t2 = y * m / n, t3 = sq(ln), t4 = sq(mn);
         acc[0] += w;
         acc[1] += has_w ? x * w : x;
@@ -47,10 +53,13 @@ template <int MODE, bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK)
 k_sums(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ l,
        const double *__restrict__ m, const double *__restrict__ n, const double *__restrict__ w,
-       int64_t num, double a, double b, const double *__restrict__ ab_dev, double *__restrict__ partial)
+       int64_t num, double a, double b, const double *__restrict__ ab_dev, double *__restrict__ partial,
+       const double *__restrict__ z = nullptr)
 {
     constexpr int NS = MODE == PXF_SUMS_CENTROID ? 4 : (MODE == PXF_SUMS_RMS ? 2 : 9);
-    constexpr int U = MODE == PXF_SUMS_IMAGEPLANE ? 2 : 4;
+    constexpr bool IP = MODE == PXF_SUMS_IMAGEPLANE || MODE == PXF_SUMS_IMAGEPLANE_Z;
+    constexpr bool ZZ = MODE == PXF_SUMS_IMAGEPLANE_Z;
+    constexpr int U = IP ? 2 : 4;
     if (ab_dev) { a = ab_dev[0]; b = ab_dev[1]; }
     double acc[U][NSUM];
 #pragma unroll
@@ -63,7 +72,7 @@ k_sums(const double *__restrict__ x, const double *__restrict__ y, const double 
     if (VEC2) {
         const int64_t npair = num >> 1;
         for (int64_t q0 = tid; q0 < npair; q0 += U * nthr) {
-            double2 xv[U], yv[U], lv[U], mv[U], nv[U], wv[U];
+            double2 xv[U], yv[U], lv[U], mv[U], nv[U], wv[U], zv[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int64_t q = q0 + u * nthr;
@@ -71,42 +80,44 @@ k_sums(const double *__restrict__ x, const double *__restrict__ y, const double 
                 const double2 z2 = make_double2(0., 0.), o2 = make_double2(1., 1.);
                 xv[u] = in ? *reinterpret_cast<const double2 *>(x + 2 * q) : z2;
                 yv[u] = in ? *reinterpret_cast<const double2 *>(y + 2 * q) : z2;
-                if (MODE == PXF_SUMS_IMAGEPLANE) {
+                if (IP) {
                     lv[u] = in ? *reinterpret_cast<const double2 *>(l + 2 * q) : z2;
                     mv[u] = in ? *reinterpret_cast<const double2 *>(m + 2 * q) : z2;
                     nv[u] = in ? *reinterpret_cast<const double2 *>(n + 2 * q) : o2;
                 } else { lv[u] = z2; mv[u] = z2; nv[u] = o2; }
+                zv[u] = (ZZ && in) ? *reinterpret_cast<const double2 *>(z + 2 * q) : z2;
                 wv[u] = (in && has_w) ? *reinterpret_cast<const double2 *>(w + 2 * q) : o2;
             }
 #pragma unroll
             for (int u = 0; u < U; u++)
                 if (q0 + u * nthr < npair) {
-                    sums_accum<MODE>(acc[u], xv[u].x, yv[u].x, lv[u].x, mv[u].x, nv[u].x, wv[u].x, has_w, a, b);
-                    sums_accum<MODE>(acc[u], xv[u].y, yv[u].y, lv[u].y, mv[u].y, nv[u].y, wv[u].y, has_w, a, b);
+                    sums_accum<MODE>(acc[u], xv[u].x, yv[u].x, lv[u].x, mv[u].x, nv[u].x, wv[u].x, has_w, a, b, zv[u].x);
+                    sums_accum<MODE>(acc[u], xv[u].y, yv[u].y, lv[u].y, mv[u].y, nv[u].y, wv[u].y, has_w, a, b, zv[u].y);
                 }
         }
         if ((num & 1) && tid == 0) {
             const int64_t i = num - 1;
-            sums_accum<MODE>(acc[0], x[i], y[i], MODE == PXF_SUMS_IMAGEPLANE ? l[i] : 0., MODE == PXF_SUMS_IMAGEPLANE ? m[i] : 0.,
-                             MODE == PXF_SUMS_IMAGEPLANE ? n[i] : 1., has_w ? w[i] : 1., has_w, a, b);
+            sums_accum<MODE>(acc[0], x[i], y[i], IP ? l[i] : 0., IP ? m[i] : 0.,
+                             IP ? n[i] : 1., has_w ? w[i] : 1., has_w, a, b, ZZ ? z[i] : 0.);
         }
     } else {
         for (int64_t i0 = tid; i0 < num; i0 += U * nthr) {
-            double xv[U], yv[U], lv[U], mv[U], nv[U], wv[U];
+            double xv[U], yv[U], lv[U], mv[U], nv[U], wv[U], zv[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int64_t i = i0 + u * nthr;
                 const bool in = i < num;
                 xv[u] = in ? x[i] : 0.;
                 yv[u] = in ? y[i] : 0.;
-                lv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? l[i] : 0.;
-                mv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? m[i] : 0.;
-                nv[u] = (in && MODE == PXF_SUMS_IMAGEPLANE) ? n[i] : 1.;
+                lv[u] = (in && IP) ? l[i] : 0.;
+                mv[u] = (in && IP) ? m[i] : 0.;
+                nv[u] = (in && IP) ? n[i] : 1.;
+                zv[u] = (in && ZZ) ? z[i] : 0.;
                 wv[u] = (in && has_w) ? w[i] : 1.;
             }
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (i0 + u * nthr < num) sums_accum<MODE>(acc[u], xv[u], yv[u], lv[u], mv[u], nv[u], wv[u], has_w, a, b);
+                if (i0 + u * nthr < num) sums_accum<MODE>(acc[u], xv[u], yv[u], lv[u], mv[u], nv[u], wv[u], has_w, a, b, zv[u]);
         }
     }
 #pragma unroll
@@ -161,27 +172,31 @@ k_sums_final(const double *__restrict__ partial, int nblocks, int ns, double *__
 
 static int sums_launch(int mode, const double *x, const double *y, const double *l, const double *m,
                        const double *n, const double *w, int64_t num, double a, double b,
-                       const double *ab_dev, double *out_dev, void *scratch, cudaStream_t s)
+                       const double *ab_dev, double *out_dev, void *scratch, cudaStream_t s, const double *z = nullptr)
 {
     if (num < 0 || !x || !y || !out_dev || !scratch) { set_error("pxf_sums: bad argument"); return PXF_ERR_INVALID; }
-    if (mode == PXF_SUMS_IMAGEPLANE && (!l || !m || !n)) { set_error("pxf_sums: l,m,n required"); return PXF_ERR_INVALID; }
+    const bool ip = mode == PXF_SUMS_IMAGEPLANE || mode == PXF_SUMS_IMAGEPLANE_Z;
+    if (ip && (!l || !m || !n)) { set_error("pxf_sums: l,m,n required"); return PXF_ERR_INVALID; }
+    if (mode == PXF_SUMS_IMAGEPLANE_Z && !z) { set_error("pxf_sums: z required"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     int grid = grid_for(num, PXF_BLOCK * 8, 4);
     if (grid > SUM_BLOCKS_MAX) grid = SUM_BLOCKS_MAX;
     double *partial = static_cast<double *>(scratch);
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w);
-    if (mode == PXF_SUMS_IMAGEPLANE)
-        al |= reinterpret_cast<uintptr_t>(l) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(n);
+    if (ip)
+        al |= reinterpret_cast<uintptr_t>(l) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(n) |
+              reinterpret_cast<uintptr_t>(z);
     const bool v2 = (al & 15) == 0;
     int ns;
 #define PXF_SUMS_GO(M)                                                                                         \
     do {                                                                                                       \
-        if (v2) k_sums<M, true><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);        \
-        else k_sums<M, false><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial);          \
+        if (v2) k_sums<M, true><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z);     \
+        else k_sums<M, false><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z);       \
     } while (0)
     if (mode == PXF_SUMS_CENTROID) { ns = 4; PXF_SUMS_GO(PXF_SUMS_CENTROID); }
     else if (mode == PXF_SUMS_RMS) { ns = 2; PXF_SUMS_GO(PXF_SUMS_RMS); }
     else if (mode == PXF_SUMS_IMAGEPLANE) { ns = 9; PXF_SUMS_GO(PXF_SUMS_IMAGEPLANE); }
+    else if (mode == PXF_SUMS_IMAGEPLANE_Z) { ns = 9; PXF_SUMS_GO(PXF_SUMS_IMAGEPLANE_Z); }
     else {
         set_error("pxf_sums: bad mode");
         return PXF_ERR_INVALID;
@@ -1082,6 +1097,13 @@ int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, co
 {
     return sums_launch(mode, x, y, l, m, n, w, num, a, b, nullptr, out_dev, scratch,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pxf_sums_z(const double *x, const double *y, const double *z, const double *l, const double *m,
+               const double *n, const double *w, int64_t num, double *out_dev, void *scratch, pxf_stream_t stream)
+{
+    return sums_launch(PXF_SUMS_IMAGEPLANE_Z, x, y, l, m, n, w, num, 0., 0., nullptr, out_dev, scratch,
+                       reinterpret_cast<cudaStream_t>(stream), z);
 }
 
 int pxf_rho(const double *x, const double *y, int64_t num, double cx, double cy, double *rho_out,

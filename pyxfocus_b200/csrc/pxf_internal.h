@@ -14,6 +14,8 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
 int opt_ws_libm();      // PXF_OPT_WS_LIBM
+int opt_ws_retrace();   // PXF_OPT_WS_RETRACE
+int opt_ws_graze_ppm(); // PXF_OPT_WS_GRAZE_PPM
 
 // Per-device one-time guard: function attributes (cudaFuncSetAttribute) belong to a device's primary context, so
 // a process that works on cuda:0 and then on cuda:1 has to set them again there.  `seen` is a zero-initialised

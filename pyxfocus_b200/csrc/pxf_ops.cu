@@ -25,7 +25,11 @@ void set_error(const char *fmt, ...)
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_ws_libm{0};
+static std::atomic<int> g_ws_retrace{PXF_WS_RETRACE_DEFAULT};
 int opt_ws_libm() { return g_ws_libm.load(std::memory_order_relaxed); }
+int opt_ws_retrace() { return g_ws_retrace.load(std::memory_order_relaxed); }
+static std::atomic<int> g_ws_graze_ppm{PXF_WS_GRAZE_PPM_DEFAULT};
+int opt_ws_graze_ppm() { return g_ws_graze_ppm.load(std::memory_order_relaxed); }
 int sm_count()
 {
     if (g_sms == 0) {
@@ -519,6 +523,8 @@ int64_t pxf_launch_count(void) { return g_launches.load(); }
 int pxf_set_option(int32_t option, int32_t value)
 {
     if (option == PXF_OPT_WS_LIBM) { g_ws_libm.store(value ? 1 : 0); return PXF_OK; }
+    if (option == PXF_OPT_WS_GRAZE_PPM) { g_ws_graze_ppm.store(value >= 0 ? value : PXF_WS_GRAZE_PPM_DEFAULT); return PXF_OK; }
+    if (option == PXF_OPT_WS_RETRACE) { g_ws_retrace.store(value > 0 ? value : PXF_WS_RETRACE_DEFAULT); return PXF_OK; }
     set_error("pxf_set_option: unknown option %d", option);
     return PXF_ERR_INVALID;
 }

@@ -121,6 +121,8 @@ inline WSP make_ws(double alpha, double z0, double psi, double thick = 0.)
     p.twootan = 2. / tan(betas);
     p.kp1 = k + 1;
     p.fast = (!opt_ws_libm() && k > 0. && k < .25) ? 1. : 0.;
+    p.retrace = (double)opt_ws_retrace();
+    p.graze_min = 1.e-6 * (double)opt_ws_graze_ppm();
     p.tanhbs = tan(betas / 2);
     p.iff = 1 / ff;
     p.idenF = 1 / p.denF;

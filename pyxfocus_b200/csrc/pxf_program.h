@@ -6,7 +6,7 @@
 
 namespace pxf {
 
-#define FOP_PARAM_DOUBLES 36   // sizeof(WSP)/8 is the largest folded parameter block
+#define FOP_PARAM_DOUBLES 38   // sizeof(WSP)/8 is the largest folded parameter block
 
 struct FusedOp {
     int code;

@@ -162,9 +162,11 @@ def ws_aperture(api, R0=WS["R0"], Z0=WS["Z0"], psi=WS["psi"], L=WS["L"], pmin=WS
 
 
 def config2_point(api, n, offaxis, aperture, rng_seed=0, R0=WS["R0"], Z0=WS["Z0"], psi=WS["psi"], az=WS["az"]):
-    """One field point of the W-S sweep: ``traceZeta`` (examples/axro/axialHeights.py:77-113) followed by the
-    best-focus refinement of the legacy sweep (examples/axro/WSverify.py:159-167): focusI, findimageplane(20,100),
-    findimageplane(1,100), flat, then hpd and rmsCentroid."""
+    """One field point of the W-S sweep: the chain of ``traceZeta`` (examples/axro/axialHeights.py:77-113) to the
+    nominal focal plane, the two-stage plane scan of the legacy sweep (examples/axro/WSverify.py:150-167:
+    flat, findimageplane(20,100), findimageplane(1,100), flat) with its hpd / rms, then traceZeta's own
+    refinement (focusI) and merit functions.  The scans come first on purpose: scanned from the best focus itself
+    the two grid points next to zero tie and the literal scan picks one from rounding noise."""
     src, tran, surf, anal = api.sources, api.tran, api.surf, api.anal
     a0, a1 = aperture
     seed(rng_seed)
@@ -176,13 +178,16 @@ def config2_point(api, n, offaxis, aperture, rng_seed=0, R0=WS["R0"], Z0=WS["Z0"
     tran.reflect(rays)
     surf.wsSecondary(rays, R0, Z0, psi)
     tran.reflect(rays)
-    f = surf.focusI(rays)
+    surf.flat(rays)
     d2 = findimageplane(api, rays, 20., 100)
     tran.transform(rays, 0, 0, d2, 0, 0, 0)
     d3 = findimageplane(api, rays, 1., 100)
     tran.transform(rays, 0, 0, d3, 0, 0, 0)
     surf.flat(rays)
-    return dict(rays=rays, f=f, d2=d2, d3=d3, hpd=anal.hpd(rays), rms=anal.rmsCentroid(rays))
+    hpd_scan, rms_scan = anal.hpd(rays), anal.rmsCentroid(rays)
+    f = surf.focusI(rays)
+    return dict(rays=rays, f=f, d2=d2, d3=d3, hpd_scan=hpd_scan, rms_scan=rms_scan, hpd=anal.hpd(rays),
+                rms=anal.rmsCentroid(rays))
 
 
 def config2(api, n=10_000_000, arcmin=None, aperture=None, rng_seed=0):
@@ -426,11 +431,12 @@ def _source_kw(rng, rng_seed, device, first=0):
     return dict(rng="philox", seed=rng_seed, first=first, device=device)
 
 
-def config1_fast(n=100_000, rng="numpy", rng_seed=0, device=None):
+def config1_fast(n=100_000, rng="numpy", rng_seed=0, device=None, sources=None):
     pxf = _pxf()
+    src = sources or pxf.sources
     tran, surf, anal = pxf.transformations, pxf.surfaces, pxf.analyses
     seed(rng_seed)
-    rays = pxf.sources.subannulus(220., 220.6, 2 * np.pi, n, zhat=-1., **_source_kw(rng, rng_seed, device))
+    rays = src.subannulus(220., 220.6, 2 * np.pi, n, zhat=-1., **_source_kw(rng, rng_seed, device))
     with pxf.fused(rays):
         tran.transform(rays, 0, 0, -8400., 0, 0, 0)
         surf.wolterprimary(rays, 220., 8400.)
@@ -442,12 +448,13 @@ def config1_fast(n=100_000, rng="numpy", rng_seed=0, device=None):
 
 
 def config2_point_fast(n, offaxis, aperture, rng="numpy", rng_seed=0, device=None,
-                       R0=WS["R0"], Z0=WS["Z0"], psi=WS["psi"], az=WS["az"]):
+                       R0=WS["R0"], Z0=WS["Z0"], psi=WS["psi"], az=WS["az"], sources=None):
     pxf = _pxf()
+    src = sources or pxf.sources
     tran, surf, anal = pxf.transformations, pxf.surfaces, pxf.analyses
     a0, a1 = aperture
     seed(rng_seed)
-    rays = pxf.sources.subannulus(a0, a1, az / R0, n, **_source_kw(rng, rng_seed, device))
+    rays = src.subannulus(a0, a1, az / R0, n, **_source_kw(rng, rng_seed, device))
     with pxf.fused(rays):
         tran.transform(rays, 0, 0, -Z0, 0, 0, 0)
         surf.wsPrimary(rays, R0, Z0, psi)
@@ -455,16 +462,19 @@ def config2_point_fast(n, offaxis, aperture, rng="numpy", rng_seed=0, device=Non
         tran.reflect(rays)
         surf.wsSecondary(rays, R0, Z0, psi)
         tran.reflect(rays)
-    f = surf.focusI(rays)
-    # a z translation leaves x, y, l/n, m/n alone: both scans read the same nine sums (one pass over the bundle)
-    s9 = anal.imageplane_sums(rays)
+        surf.flat(rays)
+    # both scans from ONE pass over the bundle: moving the frame by d2 only shifts the sums
+    s9 = anal.imageplane_sums(rays, at_z0=True)
     d2 = anal.findimageplane(rays, 20., 100, sums=s9)
-    d3 = anal.findimageplane(rays, 1., 100, sums=s9)
+    d3 = anal.findimageplane(rays, 1., 100, sums=s9, moved=d2)
     with pxf.fused(rays):
         tran.transform(rays, 0, 0, d2, 0, 0, 0)
         tran.transform(rays, 0, 0, d3, 0, 0, 0)
         surf.flat(rays)
-    return dict(rays=rays, f=f, d2=d2, d3=d3, hpd=anal.hpd(rays), rms=anal.rmsCentroid(rays))
+    hpd_scan, rms_scan = anal.hpd(rays), anal.rmsCentroid(rays)
+    f = surf.focusI(rays)
+    return dict(rays=rays, f=f, d2=d2, d3=d3, hpd_scan=hpd_scan, rms_scan=rms_scan, hpd=anal.hpd(rays),
+                rms=anal.rmsCentroid(rays))
 
 
 def config2_fast(n=10_000_000, arcmin=None, aperture=None, rng="numpy", rng_seed=0, device=None):
@@ -473,13 +483,14 @@ def config2_fast(n=10_000_000, arcmin=None, aperture=None, rng="numpy", rng_seed
     return [config2_point_fast(n, a / 60. * np.pi / 180., aperture, rng, rng_seed, device) for a in arcmin]
 
 
-def config3_fast(n=100_000_000, rng="numpy", rng_seed=0, device=None, want_idx=True):
+def config3_fast(n=100_000_000, rng="numpy", rng_seed=0, device=None, want_idx=True, sources=None):
     pxf = _pxf()
+    src = sources or pxf.sources
     tran, surf, anal = pxf.transformations, pxf.surfaces, pxf.analyses
     ro, ao = zernike_orders(7)
     coeff = zernike_coeff(len(ro), rng_seed)
     seed(rng_seed)
-    rays = pxf.sources.subannulus(220., 220.6, 100. / 220., n, zhat=-1., **_source_kw(rng, rng_seed, device))
+    rays = src.subannulus(220., 220.6, 100. / 220., n, zhat=-1., **_source_kw(rng, rng_seed, device))
     with pxf.fused(rays):
         prog = pxf.program.recorder_for(rays)
         tran.transform(rays, 220.3, 0, -100., 0, 0, 0)
@@ -503,8 +514,10 @@ def config3_fast(n=100_000_000, rng="numpy", rng_seed=0, device=None, want_idx=T
     return out
 
 
-def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_seed=0, device=None, offX=0., offY=0.):
+def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_seed=0, device=None, offX=0., offY=0.,
+                 sources=None):
     pxf = _pxf()
+    src = sources or pxf.sources
     import torch
     from pyxfocus_b200._call import bundle_alloc, bundle_split
     tran, surf, anal = pxf.transformations, pxf.surfaces, pxf.analyses
@@ -516,7 +529,7 @@ def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_se
     rays = bundle_alloc(N * M, dev, zero=True)
     if rng == "numpy":
         for i, seg in enumerate(bundle_split(rays, per)):
-            pxf.sources.subannulus(g.R[i], g.R[i] + .605, g.spanv[i], N, zhat=-1., out=seg)
+            src.subannulus(g.R[i], g.R[i] + .605, g.spanv[i], N, zhat=-1., out=seg)
     else:
         pxf.sources.segments("subannulus", [(g.R[i], g.R[i] + .605, g.spanv[i], -1.) for i in range(M)], per,
                              seed=rng_seed, out=rays)
@@ -551,8 +564,10 @@ def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_se
                 rmsY=anal.rmsY(surv, weights=w), hpdY=anal.hpdY(surv, weights=w))
 
 
-def config5_fast(n_per_shell=1000, nshell=260, offaxis=0., rng="numpy", rng_seed=0, device=None, first=0):
+def config5_fast(n_per_shell=1000, nshell=260, offaxis=0., rng="numpy", rng_seed=0, device=None, first=0,
+                 sources=None):
     pxf = _pxf()
+    src = sources or pxf.sources
     import torch
     from pyxfocus_b200._call import bundle_alloc, bundle_split
     tran, anal, conic = pxf.transformations, pxf.analyses, pxf.conicsolve
@@ -578,7 +593,7 @@ def config5_fast(n_per_shell=1000, nshell=260, offaxis=0., rng="numpy", rng_seed
     rays = bundle_alloc(N * len(per), dev, zero=True)
     if rng == "numpy":
         for k, sgm in enumerate(bundle_split(rays, per)):
-            pxf.sources.annulus(aper[k][0], aper[k][1], N, out=sgm)
+            src.annulus(aper[k][0], aper[k][1], N, out=sgm)
     else:
         pxf.sources.segments("annulus", aper, per, seed=rng_seed, first=first, out=rays)
     weights = torch.repeat_interleave(torch.as_tensor(np.array(wts), device=dev), N)

@@ -36,7 +36,7 @@ def main():
         r = ex.config2_point(api, SIZES["c2_n"], a / 60. * np.pi / 180., ap)
         tag = "c2_%02d_" % int(a)
         g[tag + "xy"] = stack(r["rays"], (1, 2))
-        g[tag + "scalars"] = np.array([r["f"], r["d2"], r["d3"], r["hpd"], r["rms"]])
+        g[tag + "scalars"] = np.array([r["f"], r["d2"], r["d3"], r["hpd"], r["rms"], r["hpd_scan"], r["rms_scan"]])
     r = ex.config3(api, SIZES["c3_n"])
     g["c3_rows"] = stack(r["rays"], range(10))
     g["c3_idx"] = np.asarray(r["idx"], dtype=np.int64)

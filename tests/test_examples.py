@@ -40,7 +40,7 @@ def test_config2_matches_golden(api, gold):
         r = ex.config2_point(api, SIZES["c2_n"], a / 60. * np.pi / 180., ap)
         tag = "c2_%02d_" % int(a)
         assert same(stack(r["rays"], (1, 2)), gold[tag + "xy"]), tag
-        assert same(np.array([r["f"], r["d2"], r["d3"], r["hpd"], r["rms"]]), gold[tag + "scalars"]), tag
+        assert same(np.array([r["f"], r["d2"], r["d3"], r["hpd"], r["rms"], r["hpd_scan"], r["rms_scan"]]), gold[tag + "scalars"]), tag
 
 
 def test_config3_matches_golden(api, gold):

@@ -101,3 +101,39 @@ def to_dev(rays, device="cuda"):
 def to_host(rays):
     from pyxfocus_b200 import sources
     return sources.to_numpy(rays)
+
+
+class UploadedSources:
+    """``sources`` stand-in for bit-level chain tests: the ORACLE's numpy source formulas (oracle/pyref.py, i.e. the
+    reference's: numpy cos/sin), uploaded.  The product's own numpy-seeded sources evaluate cos/sin on the device
+    and agree to 1e-12 (test_sources_from_numpy_seeds); with identical input rays every algebraic chain must then
+    agree bit for bit."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+
+    def _up(self, rays, out):
+        import torch
+        if out is None:
+            return to_dev(rays, self.device)
+        for k in range(10):
+            out[k].copy_(torch.from_numpy(np.ascontiguousarray(rays[k])))
+        return out
+
+    def subannulus(self, rin, rout, dphi, num, zhat=1., device=None, out=None, **kw):
+        return self._up(pyref.subannulus(rin, rout, dphi, int(num), zhat=zhat), out)
+
+    def annulus(self, rin, rout, num, zhat=-1., device=None, out=None, **kw):
+        return self._up(pyref.annulus(rin, rout, int(num), zhat=zhat), out)
+
+    def pointsource(self, ang, num, device=None, out=None, **kw):
+        return self._up(pyref.pointsource(ang, int(num)), out)
+
+
+def exact_product_api(ex, device=None):
+    """The product's modules with the sources swapped for ``UploadedSources``."""
+    from types import SimpleNamespace
+    import pyxfocus_b200 as pxf
+    mods = SimpleNamespace(sources=UploadedSources(), transformations=pxf.transformations, surfaces=pxf.surfaces,
+                           analyses=pxf.analyses, conicsolve=pxf.conicsolve)
+    return ex.make_api(mods, ex.TorchXP(device), "pyxfocus_b200 (oracle sources)")
