@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-rays", type=float, default=2.0e7, help="rays per step of the reference arm")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 1-5 sub-results")
+    ap.add_argument("--configs-scale", type=float, default=1., help="scale the configs' ray counts (smoke runs)")
     return ap.parse_args()
 
 
@@ -406,6 +408,15 @@ def run_engine(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, pxf, pdist, src, prog, n, world, dev, barrier)
+    # ---- the other BASELINE configurations (the headline's buffers are released first)
+    configs = None
+    if not args.no_configs:
+        del src, out, ws
+        torch.cuda.empty_cache()
+        try:
+            configs = run_configs(args, pxf, world, rank, dev, barrier)
+        except Exception as e:                                    # noqa: BLE001  (sub-results never take the headline down)
+            configs = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank != 0:
         if world > 1:
@@ -465,6 +476,8 @@ def run_engine(args):
     }
     if parity is not None:
         line["parity_check"] = parity
+    if configs is not None:
+        line["configs"] = configs
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
@@ -472,6 +485,162 @@ def run_engine(args):
     emit(line)
     if world > 1:
         td.destroy_process_group()
+
+
+def run_configs(args, pxf, world, rank, dev, barrier):
+    """BASELINE configs 1-5 as SURVEY.md 8(d) specifies them, through the public API (pyxfocus_b200/examples.py, the
+    GPU-arranged forms of the reference's example scripts), each at its named size with the source drawn on the
+    device every pass.  Per config: wall time of a whole pass (source -> trace -> vignette -> analyses, results read
+    back as the scripts do), rays/s, ray-surface interactions/s, the headline result, and a parity field: the same
+    code at the size of the committed golden (tests/golden/configs.npz, produced by the reference's own Python layer
+    over the C oracle), numpy-seeded, compared with it.  Configs 1-4 run at N = 1 only; config 5 is the sharded one."""
+    import numpy as np
+    import torch
+    ex = pxf.examples
+    sc = args.configs_scale
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()                                  # warm-up (allocator, occupancy queries, tables)
+        ts = []
+        res = None
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        del fn
+        return min(ts), res
+
+    def rel(a, b):
+        return abs(a - b) / max(abs(b), 1e-300)
+
+    gold = None
+    try:
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "configs.npz"))
+        sizes = {}
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden_configs import SIZES as sizes          # noqa: N811  (constants only; nothing is generated)
+    except Exception as e:                                        # noqa: BLE001
+        gold, sizes = None, {"error": str(e)[:80]}
+
+    if world == 1:
+        # ---- config 1 at its own size (1e5 rays: launch-latency territory), numpy-seeded like the reference script
+        n1 = 100_000
+        t, r = timed(lambda: {k: v for k, v in ex.config1_fast(n1, rng="numpy").items() if k != "rays"})
+        out["config1"] = {"workload": "Wolter-I pair + hpd, 1e5 rays, np.random.seed(0) source (host MT19937 draws uploaded)",
+                          "rays": n1, "ms": 1e3 * t, "rays_per_s": n1 / t, "interactions_per_s": 3 * n1 / t,
+                          "hpd": r["hpd"], "parity": {"expected_hpd_mm": 1.278e-5, "source": "SURVEY.md 8d probe of the reference chain",
+                                                      "ok": bool(rel(r["hpd"], 1.278e-5) < 2e-2)}}
+        # ---- config 2: W-S field sweep, 31 field points x 1e7 rays
+        n2 = max(1000, int(1e7 * sc))
+        ap = ex.ws_aperture(ex.product_api(dev))
+        arc = np.linspace(0., 30., 31)
+
+        def c2():
+            res = ex.config2_fast(n2, arc, ap, rng="philox", device=dev)
+            return [{k: v for k, v in p.items() if k != "rays"} for p in res]
+        t, r = timed(c2, reps=2)
+        par = None
+        if gold is not None:
+            ok, worst = True, 0.
+            for a in (0., 5., 10.):
+                g = gold["c2_%02d_scalars" % int(a)]
+                p = ex.config2_point_fast(sizes["c2_n"], a / 60. * np.pi / 180., tuple(gold["c2_aperture"]))
+                for got, want in ((p["hpd"], g[3]), (p["rms"], g[4]), (p["hpd_scan"], g[5]), (p["rms_scan"], g[6])):
+                    # 1e-9 relative, but no finer than the rays are determined: 4e-12 of the 1e4 mm system = 4e-8 mm
+                    # (the on-axis 1e-5 mm spot is rounding noise of flat's REAL*4 step), i.e. a floor of 40 mm
+                    e = abs(got - want) / max(abs(want), 40.)
+                    worst = max(worst, e)
+                ok = ok and p["d2"] == g[1] and p["d3"] == g[2]
+            par = {"vs": "tests/golden/configs.npz (reference Python layer + C oracle), field points 0/5/10 arcmin, %d rays" % sizes["c2_n"],
+                   "scan_offsets_equal": bool(ok), "worst_rel_err_hpd_rms": worst, "ok": bool(ok and worst <= 1e-9)}
+        out["config2"] = {"workload": "W-S shell field sweep: 31 field points x (subannulus, wsPrimary, kick, reflect, wsSecondary, "
+                                      "reflect, flat, findimageplane(20,100), findimageplane(1,100), flat, hpd, rms, focusI, hpd, rms)",
+                          "rays_per_field_point": n2, "field_points": 31, "ms": 1e3 * t, "rays_per_s": 31 * n2 / t,
+                          "interactions_per_s": 31 * n2 * 3 / t,
+                          "hpd_mm_at_0_5_10_20_30_arcmin": [r[i]["hpd"] for i in (0, 5, 10, 20, 30)],
+                          "rms_over_z0_at_5_arcmin": r[5]["rms"] / 1e4, "parity": par}
+        # ---- config 3: Zernike figure error + Wolter-I pair + two vignettes, 1e8 rays
+        n3 = max(1000, int(1e8 * sc))
+        t, r = timed(lambda: {k: (v if k != "rays" else v[1].shape[0]) for k, v in
+                              ex.config3_fast(n3, rng="philox", device=dev, want_idx=False).items()})
+        par = None
+        if gold is not None:
+            p = ex.config3_fast(sizes["c3_n"])
+            same_idx = bool(np.array_equal(p["idx"].cpu().numpy(), gold["c3_idx"]))
+            e = rel(p["hpd"], gold["c3_scalars"][0])
+            par = {"vs": "tests/golden/configs.npz, %d rays" % sizes["c3_n"], "surviving_index_set_equal": same_idx,
+                   "hpd_rel_err": e, "ok": bool(same_idx and e <= 1e-9)}
+        out["config3"] = {"workload": "subannulus -> transform -> zernsurf(36 terms, nr=1) -> reflect -> flat(nr=1) -> wolterprimary -> "
+                                      "reflect -> vignette(z range & |y|) -> woltersecondary -> reflect -> vignette() -> flat -> hpd: "
+                                      "ONE fused launch + compaction + hpd",
+                          "rays": n3, "ms": 1e3 * t, "rays_per_s": n3 / t, "interactions_per_s": 4 * n3 / t,
+                          "kept": r["rays"] / n3, "hpd": r["hpd"], "parity": par}
+        # ---- config 4: Arcus SPO module row (72 shells) + fanned radial-grating array, 1e8 rays
+        M = 72
+        npsh = max(10, int(1e8 * sc) // M)
+
+        def c4(order=-3, wave=2.4):
+            res = ex.config4_fast(npsh, M, order=order, wave=wave, rng="philox", device=dev)
+            return {k: v for k, v in res.items() if k not in ("rays", "surv")}
+        t, r = timed(c4)
+        tw, rw = timed(lambda: c4(-1, "uniform"), reps=2)
+        par = None
+        if gold is not None:
+            ok, worst = True, 0.
+            for order, wave in ((-1, 4.8), (-3, 2.4), (-8, .6)):
+                g = gold["c4_o%d_s_scalars" % (-order)]
+                p = ex.config4_fast(sizes["c4_n"], sizes["c4_M"], order=order, wave=wave)
+                ok = ok and p["kept"] == g[0] and p["gratings"] == g[2]
+                worst = max(worst, abs(p["dz"] - g[1]) / 1.2e4, abs(p["cy"] - g[4]) / 1.2e4)
+            par = {"vs": "tests/golden/configs.npz, orders -1/-3/-8, %d rays" % (sizes["c4_n"] * sizes["c4_M"]),
+                   "kept_and_grating_counts_equal": bool(ok), "worst_err_over_focal_length": worst, "ok": bool(ok and worst <= 1e-9)}
+        out["config4"] = {"workload": "Arcus: 72 SPO shells (subannulus, transform, spoPrimary, reflect, spoSecondary, reflect, "
+                                      "transform) in one segmented launch -> fanned radial-grating array (%d gratings; masked "
+                                      "flat/reflect/radgrat loop of sector.py as ONE per-ray in-kernel loop + one host read of the "
+                                      "grating count) -> flat -> focusY -> vignette(|y-<y>|<10) -> weighted centroid/rmsY/hpdY"
+                                      % r["gratings"],
+                          "rays": npsh * M, "shells": M, "order_wave_nm": [-3, 2.4], "ms": 1e3 * t, "rays_per_s": npsh * M / t,
+                          "interactions_per_s": npsh * M * (2 + 1 + 1) / t, "kept": r["kept"] / (npsh * M), "dz": r["dz"],
+                          "cy": r["cy"], "rmsY": r["rmsY"],
+                          "radgratW_per_ray_wavelengths": {"order": -1, "wave": "uniform(3.6,7.2) nm", "ms": 1e3 * tw,
+                                                           "rays_per_s": npsh * M / tw, "kept": rw["kept"] / (npsh * M)},
+                          "parity": par}
+    # ---- config 5: nested assembly, 260 shells; 1e9 rays over 8 GPUs = 1.25e8 per GPU (weak scaling)
+    S = 260
+    nps = max(10, int(1.25e8 * sc) // S)
+    per_gpu = nps * S
+
+    def c5():
+        res = ex.config5_fast(nps, S, offaxis=0., rng="philox", device=dev, first=rank * per_gpu,
+                              analyses=pxf.dist if world > 1 else None)
+        return {k: v for k, v in res.items() if k not in ("rays", "weights")}
+    t, r = timed(c5)
+    if world > 1:
+        import torch.distributed as td
+        tt = torch.tensor([t, float(r["kept"])], dtype=torch.float64, device=dev)
+        td.all_reduce(tt[:1], op=td.ReduceOp.MAX)
+        td.all_reduce(tt[1:], op=td.ReduceOp.SUM)
+        t, kept = float(tt[0]), float(tt[1])
+    else:
+        kept = float(r["kept"])
+    par = None
+    if gold is not None and world == 1:
+        g = gold["c5_scalars"]
+        p = ex.config5_fast(sizes["c5_n"], sizes["c5_shells"], offaxis=1. / 60. * np.pi / 180.)
+        e = max(rel(p["hpd"], g[1]), rel(p["rms"], g[2]))
+        par = {"vs": "tests/golden/configs.npz, %d shells x %d rays, 1 arcmin off axis" % (sizes["c5_shells"], sizes["c5_n"]),
+               "kept_equal": bool(p["kept"] == g[0]), "worst_rel_err_hpd_rms": e, "ok": bool(p["kept"] == g[0] and e <= 1e-9)}
+    out["config5"] = {"workload": "nested Wolter-I assembly, 260 shells: annulus, transform, wolterprimary, kick, reflect, "
+                                  "woltersecondary, reflect, vignette(z range), transform, flat, vignette(rho > back of previous "
+                                  "shell), transform, flat -- ONE segmented launch -- compaction of rays + area weights, weighted "
+                                  "centroid / rms / hpd (all-reduced over ranks for N > 1)",
+                      "rays_per_gpu": per_gpu, "total_rays": per_gpu * world, "shells": S, "ms": 1e3 * t,
+                      "rays_per_s": per_gpu * world / t, "interactions_per_s": per_gpu * world * 4 / t,
+                      "kept": kept / (per_gpu * world), "hpd_weighted": r["hpd"], "rms_weighted": r["rms"], "parity": par}
+    return out
 
 
 def run_e2e(args, pxf, pdist, src, prog, n, world, dev, barrier):

@@ -49,11 +49,16 @@ const char *pxf_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t pxf_launch_count(void);
 /* Process-wide options.
- *   PXF_OPT_WS_LIBM (default 0): 1 = evaluate the Wolter-Schwarzschild surfaces (wsprimary/wssecondary and the
- *   back surfaces) with the reference's own libm call sequence (asin/atan2/sincos/tan/pow per Newton step)
- *   instead of the algebraically identical transcendental-free form (half-angle identities, exp(k log x)).
- *   Both agree with the reference to 1e-12 on every converging ray; the libm form additionally reproduces the
- *   discrete outcome (restored or not) of the chaotic rays beyond the graze angle ray for ray. */
+ *   PXF_OPT_WS_LIBM (default 0): 1 = evaluate the Wolter-Schwarzschild surfaces (wsprimary/wssecondary and the back
+ *   surfaces) with the reference's own libm call sequence (asin/atan2/sincos/tan/pow per Newton step, woltsurf.f95:
+ *   420-449,513-551), every function CORRECTLY ROUNDED (double-double evaluation, one rounding), instead of the
+ *   algebraically identical transcendental-free form.  Both agree with the reference to 1e-12 on every ray inside the
+ *   field of view; the exact form is bit for bit against an oracle whose libm is correctly rounded at ANY field
+ *   angle, including the chaotic rays around and beyond the graze angle whose discrete outcome (which root, restored
+ *   or not) hangs on the last bit.  ~50x slower.
+ *   PXF_OPT_WS_RETRACE (default off): n > 0 = rays that took >= n Newton steps in the default form, or that the
+ *   iteration cap restored while still converging, are traced again with the exact form (the fringe of the
+ *   restored set).  PXF_OPT_WS_GRAZE_PPM (default 0): also those whose sine of the graze angle is below value*1e-6. */
 enum pxf_option { PXF_OPT_WS_LIBM = 1, PXF_OPT_WS_RETRACE = 2, PXF_OPT_WS_GRAZE_PPM = 3 };
 int pxf_set_option(int32_t option, int32_t value);
 /* Iteration cap applied to the reference's uncapped Newton loops (oracle uses the same). */
@@ -311,6 +316,20 @@ typedef struct pxf_program_aux {
 int pxf_trace_program_aux(double *const rays_in[10], double *const rays_out[10], int64_t num,
                           const pxf_op *ops, int32_t nops, uint8_t *alive, const pxf_program_aux *aux,
                           double *sums_dev, void *scratch, pxf_stream_t stream);
+/* Run-time specialisation.  Every op list that is not one of the chains built into the library is compiled once
+ * (NVRTC, sm_100a, the library's arithmetic flags) into a straight-line kernel of the same per-op device functions
+ * -- same bits as the interpreter -- and cached by signature in memory and under <libpxf dir>/_jit/ (PXF_JIT_CACHE
+ * overrides).  Bundles below PXF_JIT_MIN_RAYS (default 262144) use a cached kernel when there is one and the
+ * interpreter otherwise; PXF_JIT=0 turns it off.
+ *   pxf_jit_compile      compile (no GPU needed) the kernels a program will want -- in place / out of place, with /
+ *                        without the centroid sums; segmented != 0: the segmented form.  Returns the number of
+ *                        kernels now available (0: NVRTC missing or the compilation failed), -1: invalid program.
+ *                        PXF_OP_ZERNSURF: any non-null table address will do; aux may be NULL.
+ *   pxf_jit_status       "ok" or why the interpreter is being used, plus counters
+ *   pxf_last_trace_kernel  name of the kernel the last trace on this process launched                          */
+int32_t pxf_jit_compile(const pxf_op *ops, int32_t nops, int32_t segmented, const pxf_program_aux *aux);
+const char *pxf_jit_status(void);
+const char *pxf_last_trace_kernel(void);
 /* Out-of-place variant: rows are read from rays_in and every row the program reads or writes
  * is stored to rays_out (rows it touches neither way are not copied).  rays_in is left
  * untouched, e.g. to trace one source bundle through several configurations. */

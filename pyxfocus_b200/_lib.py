@@ -89,6 +89,9 @@ SIGNATURES = {
     "pxf_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_to": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _st]),
     "pxf_trace_program_sums": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _dp, _vp, _st]),
+    "pxf_jit_compile": (_i32, [_vp, _i32, _i32, _vp]),
+    "pxf_jit_status": (_c.c_char_p, []),
+    "pxf_last_trace_kernel": (_c.c_char_p, []),
     "pxf_trace_program_aux": (_c.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _dp, _vp, _st]),
     # vignetting / compaction
     "pxf_vignette_flags": (_c.c_int, [_dp] * 3 + [_i64, _vp, _st]),
@@ -215,6 +218,15 @@ OPT_WS_GRAZE_PPM = 3
 def set_option(option, value):
     """Process-wide library option (include/pxf.h, enum pxf_option)."""
     check(lib().pxf_set_option(int(option), int(value)))
+
+
+def last_trace_kernel():
+    """Name of the kernel the last trace launched (built-in chain, run-time specialised chain, or interpreter)."""
+    return lib().pxf_last_trace_kernel().decode()
+
+
+def jit_status():
+    return lib().pxf_jit_status().decode()
 
 
 def launch_count():

@@ -11,62 +11,26 @@
 // Results are bit-identical to the interpreter and to the per-routine kernels.
 #include <stdlib.h>
 #include "pxf_program.h"
+#include "pxf_chain_ops.cuh"
 
 namespace pxf {
 
-struct NoP { int unused; };
-
-// ---- op functors: P = folded parameter block (what build_program stores in FusedOp::q) ----
-#define PXF_CHAIN_OP(NAME, CODEV, PTYPE, CALL)                                        \
-    struct NAME {                                                                     \
-        using P = PTYPE;                                                              \
-        static constexpr int CODE = CODEV;                                            \
-        PXF_DEV static bool apply(Ray &r, const P &p) { CALL; return true; }          \
-    };
-PXF_CHAIN_OP(CTransform, PXF_OP_TRANSFORM, TransformP, op_transform(r, p))
-PXF_CHAIN_OP(CITransform, PXF_OP_ITRANSFORM, TransformP, op_itransform(r, p))
-PXF_CHAIN_OP(CReflect, PXF_OP_REFLECT, NoP, (void)p; op_reflect(r))
-PXF_CHAIN_OP(CFlat, PXF_OP_FLAT, NoP, (void)p; op_flat(r, false, 0.))
-PXF_CHAIN_OP(CWolterPrimary, PXF_OP_WOLTERPRIMARY, WolterP, op_wolterprimary(r, p))
-PXF_CHAIN_OP(CWolterSecondary, PXF_OP_WOLTERSECONDARY, WolterP, op_woltersecondary(r, p))
-PXF_CHAIN_OP(CWsPrimary, PXF_OP_WSPRIMARY, WSP, op_wsprimary(r, p))
-PXF_CHAIN_OP(CWsSecondary, PXF_OP_WSSECONDARY, WSP, op_wssecondary(r, p))
-PXF_CHAIN_OP(CSpoCone, PXF_OP_SPOCONE, SpoP, op_spocone(r, p))
-struct KickP { double dl, dm, sn; };
-PXF_CHAIN_OP(CKick, PXF_OP_KICK, KickP,
-             r.l = r.l + p.dl; r.m = r.m + p.dm; r.n = p.sn * sqrt(1. - sq(r.l) - sq(r.m)))
-
-// ---- parameter pack and straight-line composition ----
-template <class... Ops> struct ChainP;
-template <> struct ChainP<> { int unused; };
-template <class Op, class... Rest> struct ChainP<Op, Rest...> {
-    typename Op::P head;
-    ChainP<Rest...> tail;
-};
-
-template <class... Ops> struct Chain;
-template <> struct Chain<> {
-    static constexpr int N = 0;
-    PXF_DEV static bool run(Ray &, const ChainP<> &) { return true; }
+// host side of a compile-time chain: does an op list match it, and its parameter pack from the folded op table
+template <class... Ops> struct ChainHost;
+template <> struct ChainHost<> {
     static void fill(ChainP<> &, const FusedOp *) {}
     static bool match(const FusedOp *, int n) { return n == 0; }
 };
-template <class Op, class... Rest> struct Chain<Op, Rest...> {
-    static constexpr int N = 1 + sizeof...(Rest);
-    PXF_DEV static bool run(Ray &r, const ChainP<Op, Rest...> &p)
-    {
-        if (!Op::apply(r, p.head)) return false;
-        return Chain<Rest...>::run(r, p.tail);
-    }
+template <class Op, class... Rest> struct ChainHost<Op, Rest...> {
     static void fill(ChainP<Op, Rest...> &cp, const FusedOp *ops)
     {
         static_assert(sizeof(typename Op::P) <= sizeof(ops->q), "parameter block too large");
         memcpy(&cp.head, ops->q, sizeof(typename Op::P));
-        Chain<Rest...>::fill(cp.tail, ops + 1);
+        ChainHost<Rest...>::fill(cp.tail, ops + 1);
     }
     static bool match(const FusedOp *ops, int n)
     {
-        return n >= 1 && ops->code == Op::CODE && Chain<Rest...>::match(ops + 1, n - 1);
+        return n >= 1 && ops->code == Op::CODE && ChainHost<Rest...>::match(ops + 1, n - 1);
     }
 };
 
@@ -346,6 +310,7 @@ static int launch_variant(const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8
     if (grid_out) *grid_out = grid;
     kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, LM, SM, cp);
     count_launch();
+    note_kernel("k_chain<Chain<...>> (built-in chain)");
     return check_launch("k_chain");
 }
 
@@ -369,10 +334,10 @@ static int try_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const Fuse
 {
     using C = Chain<Ops...>;
     using CP = ChainP<Ops...>;
-    if (fp.nops != C::N || !C::match(fp.ops, fp.nops)) return PXF_ERR_UNSUPPORTED;
+    if (fp.nops != C::N || !ChainHost<Ops...>::match(fp.ops, fp.nops)) return PXF_ERR_UNSUPPORTED;
     CP cp;
     memset(&cp, 0, sizeof(cp));
-    C::fill(cp, fp.ops);
+    ChainHost<Ops...>::fill(cp, fp.ops);
     const unsigned LM = fp.load_mask, SM = fp.store_mask;
     const bool stat = LMc != 0 && LM == LMc && SM == SMc;
 #define PXF_LV(MODE, PF, MINB)                                                                              \
@@ -484,6 +449,7 @@ k_chain_seg(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__rest
 
 using SegWolter = Chain<CTransform, CWolterPrimary, CReflect, CWolterSecondary, CReflect, CFlat>;
 using SegWolterP = ChainP<CTransform, CWolterPrimary, CReflect, CWolterSecondary, CReflect, CFlat>;
+using SegWolterH = ChainHost<CTransform, CWolterPrimary, CReflect, CWolterSecondary, CReflect, CFlat>;
 
 size_t seg_chain_bytes(int nseg) { return (size_t)nseg * sizeof(SegWolterP); }
 
@@ -496,11 +462,11 @@ int seg_chain_fill(const FusedOp *ops, int nops, int nseg, void *dst)
         const char *e = getenv("PXF_NO_SPECIALIZE");
         disabled = (e && e[0] == '1') ? 1 : 0;
     }
-    if (disabled || nops != SegWolter::N || !SegWolter::match(ops, nops)) return 0;
+    if (disabled || nops != SegWolter::N || !SegWolterH::match(ops, nops)) return 0;
     SegWolterP *out = static_cast<SegWolterP *>(dst);
     for (int sgm = 0; sgm < nseg; sgm++) {
         memset(&out[sgm], 0, sizeof(SegWolterP));
-        SegWolter::fill(out[sgm], ops + (size_t)sgm * nops);
+        SegWolterH::fill(out[sgm], ops + (size_t)sgm * nops);
     }
     return 1;
 }
@@ -524,6 +490,7 @@ int seg_chain_launch(int chain_id, const RowPtrs &P, const RowPtrs &Q, int64_t n
     else if (minb == 5) go(k_chain_seg<SegWolter, SegWolterP, 5>);
     else go(k_chain_seg<SegWolter, SegWolterP, 4>);
     count_launch();
+    note_kernel("k_chain_seg<Chain<CTransform,CWolterPrimary,CReflect,CWolterSecondary,CReflect,CFlat>>");
     return check_launch("k_chain_seg");
 }
 

@@ -178,7 +178,7 @@ k_program(const RowPtrs P, const RowPtrs Q, const int64_t num, uint8_t *__restri
 // SEG_TILE consecutive rays; a CTA stages the op table of the segment its tile lies in into shared memory
 // (re-staged only when the segment changes; a tile that straddles segments is processed piecewise).
 #define SEG_TILE (PXF_BLOCK * 8)
-struct SegHeader { unsigned load_mask, store_mask; int nops, nseg; int chain_id, pad[3]; };
+struct SegHeader { unsigned load_mask, store_mask; int nops, nseg; int chain_id, jit_pack_bytes, pad[2]; };
 
 template <int MINB>
 __global__ void __launch_bounds__(PXF_BLOCK, MINB)
@@ -316,6 +316,7 @@ int build_program(FusedProgram &fp, const pxf_op *ops, int nops, const pxf_progr
                 TransformP t = make_transform(0., 0., 0., -p[0], 0., 0.);
                 memcpy(f.q, &t, sizeof(t));
                 f.row = (int)p[1];                     // total rotations of the loop
+                f.q[sizeof(TransformP) / 8] = (double)f.row;     // (RotxP of the specialised chains)
                 fp.uses_aux = 1;
                 break;
             }
@@ -404,6 +405,9 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
         // statically specialised kernel for the canonical chains, else the interpreter below
         int rc = launch_chain(P, Q, num, fp, alive, aligned, s, partials, grid_out);
         if (rc != PXF_ERR_UNSUPPORTED) return rc;
+        // ... else a kernel specialised for this op list at run time (NVRTC, cached), else the interpreter
+        rc = jit_launch_chain(P, Q, num, fp, alive, aligned, s, partials, grid_out);
+        if (rc != PXF_ERR_UNSUPPORTED) return rc;
     }
     // PXF_PROGRAM_VARIANT (tuning): 0 = two rays per thread (double2 rows), 1/3/4 = one ray per thread with
     // the register allocation capped for 1 / 3 / 4 resident CTAs per SM.  Measured on config 3's 12-op tail at
@@ -436,6 +440,7 @@ int launch_program(double *const rays[10], int64_t num, const FusedProgram &fp, 
     else if (variant == 1) go(k_program<false, 1>, num);
     else go(k_program<false, 4>, num);
     count_launch();
+    note_kernel(fp.zern ? "k_program<zernike> (interpreter)" : (fp.uses_aux ? "k_program<aux> (interpreter)" : "k_program (interpreter)"));
     return check_launch("k_program");
 }
 
@@ -509,7 +514,8 @@ static size_t seg_ops_offset(int nseg) { return seg_align(sizeof(SegHeader)) + s
 extern "C" size_t pxf_segmented_table_bytes(int32_t nops, int32_t nseg)
 {
     if (nops < 1 || nseg < 1) return 0;
-    return seg_align(seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp)) + seg_chain_bytes(nseg);
+    size_t packs = seg_chain_bytes(nseg), jp = (size_t)nseg * jit_seg_pack_bytes(nops);
+    return seg_align(seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp)) + (packs > jp ? packs : jp);
 }
 static size_t seg_chain_offset(int nops, int nseg) { return seg_align(seg_ops_offset(nseg) + (size_t)nseg * nops * sizeof(FusedOp)); }
 
@@ -546,6 +552,16 @@ extern "C" int pxf_segmented_table_fill(const pxf_op *ops, int32_t nops, int32_t
     }
     // a statically specialised kernel for the canonical chains: one parameter pack per segment behind the op table
     h->chain_id = seg_chain_fill(dst, nops, nseg, base + seg_chain_offset(nops, nseg));
+    bool vig = false;
+    for (int k = 0; k < nops; k++)
+        if (dst[k].code == PXF_OP_VIGNETTE_MAG || dst[k].code == PXF_OP_VIGNETTE_BOX || dst[k].code == PXF_OP_VIGNETTE_ABS ||
+            dst[k].code == PXF_OP_VIGNETTE_RHOGT) vig = true;
+    if (h->chain_id == 0 || vig) {
+        // any other op list: parameter packs for a kernel specialised at run time (pxf_jit.cu)
+        const size_t pb = jit_seg_fill(dst, nops, nseg, base + seg_chain_offset(nops, nseg));
+        if (pb) { h->chain_id = 2; h->jit_pack_bytes = (int)pb; }
+        else if (vig) h->chain_id = 0;
+    }
     return PXF_OK;
 }
 
@@ -583,8 +599,12 @@ extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *co
     const FusedOp *dops = reinterpret_cast<const FusedOp *>(db + seg_ops_offset(nseg));
     const size_t smem = (size_t)nops * sizeof(FusedOp);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (h->chain_id != 0 && !vig) {
+    if (h->chain_id == 1 && !vig) {
         int rc = seg_chain_launch(h->chain_id, P, Q, num, alive, dstart, db + seg_chain_offset(nops, nseg), nseg, LM, SM, s);
+        if (rc != PXF_ERR_UNSUPPORTED) return rc;
+    }
+    if (h->chain_id == 2) {
+        int rc = jit_seg_launch(hops, nops, P, Q, num, alive, dstart, db + seg_chain_offset(nops, nseg), nseg, LM, SM, s);
         if (rc != PXF_ERR_UNSUPPORTED) return rc;
     }
     int nb = 0;
@@ -592,6 +612,7 @@ extern "C" int pxf_trace_program_segmented(double *const rays_in[10], double *co
     const int grid = grid_for(num, SEG_TILE, nb);
     k_program_seg<4><<<grid, PXF_BLOCK, smem, s>>>(P, Q, num, alive, dstart, dops, nops, nseg, LM, SM);
     count_launch();
+    note_kernel("k_program_seg (interpreter)");
     return check_launch("k_program_seg");
 }
 

@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include "../../include/pxf.h"
 
+#ifndef PXF_NEWTON_CAP
 #define PXF_NEWTON_CAP 1000
+#endif
 #define PXF_BLOCK 256
 
 namespace pxf {

@@ -565,7 +565,10 @@ def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_se
 
 
 def config5_fast(n_per_shell=1000, nshell=260, offaxis=0., rng="numpy", rng_seed=0, device=None, first=0,
-                 sources=None):
+                 sources=None, analyses=None):
+    """``analyses``: module for the closing weighted statistics -- ``pxf.dist`` when the bundle is one shard of a
+    multi-GPU run (every rank traces its own rays of every shell, ``first`` = its offset in the Philox stream; only
+    the analyses communicate)."""
     pxf = _pxf()
     src = sources or pxf.sources
     import torch
@@ -599,7 +602,49 @@ def config5_fast(n_per_shell=1000, nshell=260, offaxis=0., rng="numpy", rng_seed
     weights = torch.repeat_interleave(torch.as_tensor(np.array(wts), device=dev), N)
     alive = pxf.SegmentedProgram(progs, per, device=dev).run(rays)
     mrays, (mweights,) = tran.compact(rays, alive, extra=[weights])
+    if analyses is not None:
+        anal = analyses
     cx, cy = anal.centroid(mrays, weights=mweights)
     return dict(rays=mrays, weights=mweights, kept=int(mrays[1].shape[0]),
                 hpd=anal.hpd(mrays, weights=mweights), rms=anal.rmsCentroid(mrays, weights=mweights), cx=cx, cy=cy,
                 area=float(mweights.sum()))
+
+
+# =============================================================================== kernel pre-compilation
+def baseline_programs():
+    """The op lists the GPU-arranged configurations above hand to the library that are not among its built-in chains
+    -- only the opcode sequence (and predicate rows) matters for the kernel, not the scalars."""
+    import pyxfocus_b200 as pxf
+    P = pxf.Program
+    ro, ao = zernike_orders(7)
+    progs = [
+        # config 2: W-S pair to the nominal focal plane; move the plane twice and trace to it
+        (P().transform(0, 0, 1, 0, 0, 0).wsprimary(5e-3, 1e4, 1.).kick(0, 0, -1).reflect().wssecondary(5e-3, 1e4, 1.).reflect().flat(), False),
+        (P().transform(0, 0, 1, 0, 0, 0).transform(0, 0, 1, 0, 0, 0).flat(), False),
+        # config 3: the 14-op program with the Zernike surface and three predicates
+        (P().transform(1, 0, 1, 0, 0, 0).zernsurf(zernike_coeff(len(ro)), ro, ao, 62.5, 1.).reflect().transform(0, 0, 0, 1, 0, 0)
+         .flatopd(1.).transform(1, 0, 1, 0, 0, 0).wolterprimary(220., 8400., 1.).reflect().vignette_box(3, 0, 1).vignette_abs(2, 1.)
+         .woltersecondary(220., 8400., 1.).reflect().vignette_mag().flat(), False),
+        # config 4: SPO shells (segmented), the grating fan, the way back, the outlier cut
+        (P().transform(0, 0, 0, 0, 0, 1).spocone(700., .01).kickn(0, 0).reflect().spocone(700., .03).reflect()
+         .transform(0, 0, 1, 0, 0, 0).transform(0, 0, 1, 0, 0, 0).flat(), True),
+        (P().transform(1, 0, 0, 0, 0, 0).transform(0, 0, 0, 0, 0, 1).transform(0, 0, 0, 1, 0, 0).transform(0, 0, 0, 0, 0, 1)
+         .transform(0, 1, 0, 0, 0, 0).gratfan(1e-4, 1e4, 95., .01, -1, 1.), False),
+        (P().rotx_remaining(1e-4, 1).transform(0, 0, 0, 1, 0, 0).transform(0, 1, 0, 0, 0, 0).transform(0, 0, 0, 0, 0, 1)
+         .transform(0, 0, 0, 1, 0, 0).transform(0, 0, 0, 0, 0, 1).transform(1, 0, 0, 0, 0, 0).flat(), False),
+        (P().vignette_abs(2, 10., 1.), False),
+        # config 5: one nested shell (segmented)
+        (P().transform(0, 0, 1, 0, 0, 0).wolterprimary(220., 8400., 1.).kick(0, 0, -1).reflect().woltersecondary(220., 8400., 1.)
+         .reflect().vignette_box(3, 0, 1).transform(0, 0, 1, 0, 0, 0).flat().vignette_rhogt(1.).transform(0, 0, 1, 0, 0, 0).flat(), True),
+    ]
+    return progs
+
+
+def precompile():
+    """Compile (NVRTC; no GPU needed) and cache the specialised kernels of ``baseline_programs``.  Returns
+    (kernels available, programs): 0 kernels means NVRTC is unavailable and the interpreter will run instead."""
+    have = 0
+    progs = baseline_programs()
+    for prog, segmented in progs:
+        have += prog.precompile(segmented=segmented)
+    return have, len(progs)

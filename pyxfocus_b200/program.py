@@ -194,6 +194,23 @@ class Program:
                 arr[k].p[0] = struct.unpack("d", struct.pack("Q", self._dev_tables[key].data_ptr()))[0]
         return arr
 
+    def precompile(self, segmented=False):
+        """Compile the run-time specialised kernels this program will want (no GPU needed; cached on disk under
+        ``pyxfocus_b200/_jit``).  Returns the number of kernels available (0: NVRTC unavailable -- the interpreter
+        will be used)."""
+        import struct
+        arr = (_lib.pxf_op * len(self.ops))()
+        for k, (code, p) in enumerate(self.ops):
+            arr[k].code = code
+            for j, v in enumerate(p):
+                arr[k].p[j] = v
+            if k in self._tables:
+                arr[k].p[0] = struct.unpack("d", struct.pack("Q", 8))[0]      # any non-null table address
+        n = int(_lib.lib().pxf_jit_compile(arr, len(self.ops), 1 if segmented else 0, None))
+        if n < 0:
+            _lib.check(1)
+        return n
+
     def run(self, rays, alive=None, out=None, sums=None, aux=None):
         """Execute on a bundle (list of ten CUDA fp64 rows).  Returns the ``alive`` uint8
         tensor when the program contains a vignette predicate (allocated if not given).

@@ -276,13 +276,12 @@ def test_ws_exact_mode_is_bit_for_bit_at_any_field_angle(pxf, arcmin):
         pxf.set_option(pxf.OPT_WS_LIBM, 0)
 
 
-@pytest.mark.parametrize("arcmin,allowed", [(0., 0.), (6., 0.), (10., 0.), (24., 0.), (30., 0.), (20., .03), (17., .2)])
+@pytest.mark.parametrize("arcmin,allowed", [(0., 0.), (6., 0.), (10., 0.), (24., 2e-4), (30., 2e-4), (20., .03), (17., .2)])
 def test_ws_far_off_axis_chaotic_fringe(pxf, arcmin, allowed):
-    """DEFAULT options: transcendental-free evaluation, with every long-trip ray (>= 12 Newton steps: the fringe of
-    the restored set) traced again with the exact form.  Inside the field of view and well beyond the graze angle
-    every ray -- converged or restored -- agrees with the (glibc) oracle to 1e-12: 0 rays differ.  In the chaotic band
-    around the graze angle (~12'-21' for this shell) the rays that differ are bounded and reported; exact mode
-    (previous test) is what reproduces those."""
+    """DEFAULT options (transcendental-free evaluation).  Inside the field of view every ray agrees with the (glibc)
+    oracle to 1e-12: 0 of 50001 differ.  In the chaotic band around the graze angle (~12'-21' for this shell) and on
+    the fringe of the restored set beyond it the rays that differ are bounded and reported; exact mode (previous
+    test) reproduces those bit for bit, fringe mode (next test) the restored sets beyond the band."""
     bad, _ = _ws_chain_diff(pxf, arcmin)
     print("default mode at %g': %d of %d rays off by > 1e-12" % (arcmin, bad.sum(), N))
     assert bad.mean() <= allowed
@@ -291,28 +290,34 @@ def test_ws_far_off_axis_chaotic_fringe(pxf, arcmin, allowed):
 @pytest.mark.parametrize("arcmin", [20., 24., 30.])
 def test_ws_cap_restores_same_rays(pxf, arcmin):
     """Rays that exhaust the 26-iteration cap are restored in place (woltsurf.f95:562-580): the set of restored
-    rays -- this routine's "surviving-ray index set" -- must be identical ray for ray, with default options and with
-    the literal libm evaluation forced for every ray (PXF_OPT_WS_LIBM)."""
+    rays is this routine's "surviving-ray index set".  Exact mode: identical ray for ray at every angle.  Fringe mode
+    (PXF_OPT_WS_RETRACE = 12): identical beyond the chaotic band (24', 30').  Default: differs on the fringe only
+    (< 1 % of the restored rays at 20', ~1e-4 at 24')."""
     a = pyref.woltparam(220., 1.e4)[0]
-    for libm in (1, 0):
+    for mode in ("exact", "fringe", "default"):
         cpu = ws_inputs(19)
         steps = chains.ws_steps(arcmin / 60. * np.pi / 180.)[1:4]
         chains.run_steps_cpu(cpu, steps)
         dev = to_dev(cpu)
         before = copy(cpu)
         of.woltsurf.wssecondary(*cpu[1:], a, 1.e4, 1.)
-        pxf.set_option(pxf.OPT_WS_LIBM, libm)
+        pxf.set_option(pxf.OPT_WS_LIBM, 1 if mode == "exact" else 0)
+        pxf.set_option(pxf.OPT_WS_RETRACE, 12 if mode == "fringe" else 0)
         try:
             pxf.woltsurf.wssecondary(*dev[1:], a, 1.e4, 1.)
         finally:
             pxf.set_option(pxf.OPT_WS_LIBM, 0)
+            pxf.set_option(pxf.OPT_WS_RETRACE, 0)
         got = to_host(dev)
         rest_cpu = (before[1] == cpu[1]) & (before[2] == cpu[2]) & (before[3] == cpu[3])
         rest_gpu = (before[1] == got[1]) & (before[2] == got[2]) & (before[3] == got[3])
         assert rest_cpu.sum() > 100, "test needs rays that hit the cap"
         ndiff = int((rest_cpu != rest_gpu).sum())
-        print("%g' libm=%d restored rays: %d (oracle) / %d (GPU), %d differ" % (arcmin, libm, rest_cpu.sum(), rest_gpu.sum(), ndiff))
-        assert ndiff == 0, "%d of %d restored rays differ (libm=%d)" % (ndiff, rest_cpu.sum(), libm)
+        print("%g' %s mode: restored rays %d (oracle) / %d (GPU), %d differ" % (arcmin, mode, rest_cpu.sum(), rest_gpu.sum(), ndiff))
+        if mode == "exact" or (mode == "fringe" and arcmin >= 24.):
+            assert ndiff == 0, "%d of %d restored rays differ (%s mode)" % (ndiff, rest_cpu.sum(), mode)
+        else:
+            assert ndiff <= 1e-2 * rest_cpu.sum(), "%d of %d restored rays differ (%s mode)" % (ndiff, rest_cpu.sum(), mode)
 
 
 @pytest.mark.parametrize("libm", [0, 1])
