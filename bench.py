@@ -382,6 +382,7 @@ def run_engine(args):
         ms, hp_t = timed_loop(False)
     assert hp_t == hp or (hp_t != hp_t and hp != hp), "HPD changed between warm-up and timed steps"
     launches = pxf.launch_count() - launches0
+    kname = pxf.last_trace_kernel()             # the kernel the timed steps launched
     clocks = clk.stop() if rank == 0 else None
     trace_ms = sum(a.elapsed_time(b) for a, b in kev) / K
     per_step = sorted(bev[k].elapsed_time(bev[k + 1]) for k in range(K))
@@ -438,7 +439,6 @@ def run_engine(args):
         traffic_src = "static: %s (%s rays/launch, kernel %s)" % (tj.get("capture"), tj.get("rays_per_launch_measured"), tj.get("kernel"))
     except (OSError, ValueError, KeyError):
         pass
-    kname = pxf.last_trace_kernel() if hasattr(pxf, "last_trace_kernel") else "k_chain (fused trace)"
     fp64_frac = FP64_INSTR_PER_RAY * n / (trace_ms * 1e-3) / (148 * 64 * 1.965e9)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,

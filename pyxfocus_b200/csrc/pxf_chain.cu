@@ -310,7 +310,7 @@ static int launch_variant(const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8
     if (grid_out) *grid_out = grid;
     kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, LM, SM, cp);
     count_launch();
-    note_kernel("k_chain<Chain<...>> (built-in chain)");
+    note_kernel(MODE >= 2 ? "k_chain<built-in chain, 2 rays/thread, double2 rows>" : "k_chain<built-in chain, 1 ray/thread>");
     return check_launch("k_chain");
 }
 

@@ -535,8 +535,12 @@ def config4_fast(n_per_shell=1000, M=72, order=-3, wave=2.4, rng="numpy", rng_se
                              seed=rng_seed, out=rays)
     weights = torch.cat([torch.full((N,), a / N, dtype=torch.float64, device=dev) for a in g.area])
     if isinstance(wave, str):
-        wave = torch.as_tensor(np.random.uniform(3.6, 7.2, size=N * M), device=dev) if rng == "numpy" else \
-            torch.empty(N * M, dtype=torch.float64, device=dev).uniform_(3.6, 7.2)
+        if rng == "numpy":
+            wave = torch.as_tensor(np.random.uniform(3.6, 7.2, size=N * M), device=dev)
+        else:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(rng_seed))
+            wave = 3.6 + 3.6 * torch.rand(N * M, dtype=torch.float64, device=dev, generator=gen)
     # one launch for the M shells: SPO pair, to the focus frame, to the plane of the outermost grating
     # (Program.* take the scalars as the Fortran routine sees them: transform arguments negated, transformations.py:29)
     shells = [pxf.Program().transform(0, 0, 0, 0, 0, -g.ang)
