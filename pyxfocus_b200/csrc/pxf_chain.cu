@@ -10,6 +10,7 @@
 // (pxf_ray.cuh) into one straight-line kernel whose parameters are direct constant-bank operands.
 // Results are bit-identical to the interpreter and to the per-routine kernels.
 #include <stdlib.h>
+#include <string>
 #include "pxf_program.h"
 #include "pxf_chain_ops.cuh"
 
@@ -310,7 +311,6 @@ static int launch_variant(const RowPtrs &P, const RowPtrs &Q, int64_t num, uint8
     if (grid_out) *grid_out = grid;
     kern<<<grid, PXF_BLOCK, 0, s>>>(P, Q, num, alive, partials, LM, SM, cp);
     count_launch();
-    note_kernel(MODE >= 2 ? "k_chain<built-in chain, 2 rays/thread, double2 rows>" : "k_chain<built-in chain, 1 ray/thread>");
     return check_launch("k_chain");
 }
 
@@ -346,6 +346,12 @@ static int try_chain(const RowPtrs &P, const RowPtrs &Q, int64_t num, const Fuse
 #define PXF_TV(NST, MINB)                                                                                  \
     (stat ? launch_tma<C, CP, NST, MINB, LMc, SMc>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out)     \
           : launch_tma<C, CP, NST, MINB, 0u, 0u>(P, Q, num, alive, LM, SM, cp, s, partials, grid_out))
+    {
+        std::string nm = "k_chain<Chain<";
+        const char *names[] = {Ops::NAME...};
+        for (size_t k = 0; k < sizeof...(Ops); k++) { if (k) nm += ", "; nm += names[k]; }
+        note_kernel((nm + ">> (built into libpxf)").c_str());
+    }
     if (!aligned) return PXF_LV(1, true, 3);
     if constexpr (TUNABLE) {
         switch (variant_override()) {

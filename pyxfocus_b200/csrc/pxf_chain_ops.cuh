@@ -44,10 +44,11 @@ PXF_DEV void chain_count_max(int *dst, int k)
 }
 
 // ---- op functors (CODE = the PXF_OP_* value, include/pxf.h) ----
-#define PXF_CHAIN_OP(NAME, CODEV, PTYPE, CALL)                                                        \
-    struct NAME {                                                                                     \
+#define PXF_CHAIN_OP(FUNCTOR, CODEV, PTYPE, CALL)                                                     \
+    struct FUNCTOR {                                                                                  \
         using P = PTYPE;                                                                              \
         static constexpr int CODE = CODEV;                                                            \
+        static constexpr const char *NAME = #FUNCTOR;                                                 \
         PXF_DEV static bool apply(Ray &r, const P &p, const ChainCtx &ctx) { (void)p; (void)ctx; CALL; return true; } \
     };
 PXF_CHAIN_OP(CTransform, 1, TransformP, op_transform(r, p))
