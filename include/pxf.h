@@ -650,6 +650,13 @@ int pxf_source_segmented(int32_t kind, double *const rays[10], int64_t num, int6
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
                            int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep);
+/* The same with a caller hint: const_rows_mask bit r set = the caller vouches that every entry of input row r
+ * equals its first (z, l, m, n of every PyXFocus source, sources.py:20-170) -- the row is then filled on the device
+ * without being scanned or uploaded.  Rows not vouched for are still scanned chunk by chunk. */
+int pxf_host_trace_program_hint(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
+                                int32_t write_back, double *hpd_host, uint8_t *alive_host,
+                                int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep,
+                                uint32_t const_rows_mask);
 /* Frees the streams / device buffers the host entry point caches between calls. */
 void pxf_host_release(void);
 

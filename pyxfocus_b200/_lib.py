@@ -181,6 +181,7 @@ SIGNATURES = {
     "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
     # host-buffer entry point
     "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "pxf_host_trace_program_hint": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _c.c_uint32]),
     "pxf_host_release": (None, []),
 }
 

@@ -100,8 +100,12 @@ struct HostRing {
 static HostRing g_ring;
 static std::mutex g_ring_mutex;
 
+static int chunk_is_constant(const double *p, int64_t n);
 static void fill_const(double *dst, int64_t n, double v)
 {
+    // a row that already holds the constant (the previous call left it there: a pipeline that traces bundle after
+    // bundle into the same arrays) is only read -- half the memory traffic of writing it, and no dirty lines
+    if (n > 0 && memcmp(dst, &v, 8) == 0 && chunk_is_constant(dst, n)) return;
     if (v == 0.) memset(dst, 0, (size_t)n * 8);      // +0.0 is all-zero bits
     else for (int64_t i = 0; i < n; i++) dst[i] = v;
 }
@@ -150,6 +154,15 @@ void pxf_host_release(void)
 int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
                            int32_t write_back, double *hpd_host, uint8_t *alive_host,
                            int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep)
+{
+    return pxf_host_trace_program_hint(rows_host, num, ops, nops, write_back, hpd_host, alive_host, alive_count_host,
+                                       x_dev_keep, y_dev_keep, 0u);
+}
+
+int pxf_host_trace_program_hint(double *const rows_host[10], int64_t num, const pxf_op *ops, int32_t nops,
+                                int32_t write_back, double *hpd_host, uint8_t *alive_host,
+                                int64_t *alive_count_host, double *x_dev_keep, double *y_dev_keep,
+                                uint32_t const_rows_mask)
 {
     if (!rows_host || num < 0) { set_error("pxf_host_trace_program: bad argument"); return PXF_ERR_INVALID; }
     FusedProgram fp;
@@ -225,13 +238,23 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
     const int64_t nverd = scanning ? (int64_t)n_in * nchunks : 0;
     std::unique_ptr<std::atomic<int>[]> verdict(new std::atomic<int>[nverd > 0 ? nverd : 1]);
     for (int64_t i = 0; i < nverd; i++) verdict[i].store(-1, std::memory_order_relaxed);
+    // rows the caller vouches for (every entry equals the first, e.g. z, l, m, n of a PyXFocus source): no scan
+    int64_t nscan = 0;
+    if (scanning)
+        for (int ri = 0; ri < n_in; ri++) {
+            if (const_rows_mask & (1u << in_rows[ri]))
+                for (int64_t c = 0; c < nchunks; c++) verdict[(int64_t)ri * nchunks + c].store(1, std::memory_order_relaxed);
+            else nscan++;
+        }
     if (CM || scanning) {
         unsigned hc = std::thread::hardware_concurrency();
         int T = (int)(hc >= 4 ? (hc * 3) / 4 : 2);      // measured on the 16-vCPU B200 host: 8 -> 141 ms, 12 -> 135 ms
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU: the ranks share the host cores
             const int lws = atoi(e);
-            if (lws > 1) T = T / lws > 2 ? T / lws : 2;
+            // every core, split evenly (the copies themselves are DMA): 32 cores / 8 ranks = 4 threads, not 3
+            if (lws > 1) T = (int)hc / lws > 2 ? (int)hc / lws : 2;
         }
+        if (T > 16) T = 16;
         if (const char *e = getenv("PXF_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) T = v; }
         for (int t = 0; t < T; t++)
             fillers.emplace_back([&, t, T]() {
@@ -240,9 +263,11 @@ int pxf_host_trace_program(double *const rows_host[10], int64_t num, const pxf_o
                     if (abort_fill.load()) return;
                     const int64_t c = job / n_in;
                     const int ri = (int)(job % n_in);
+                    std::atomic<int> &vd = verdict[(int64_t)ri * nchunks + c];
+                    if (vd.load(std::memory_order_relaxed) >= 0) continue;          // vouched for by the caller
                     const int64_t lo = c * chunk, n = (lo + chunk <= num) ? chunk : (num - lo);
                     const int v = chunk_is_constant(rows_host[in_rows[ri]] + lo, n);
-                    verdict[(int64_t)ri * nchunks + c].store(v, std::memory_order_release);
+                    vd.store(v, std::memory_order_release);
                 }
                 for (int r = 0; r < 10; r++)
                     if (CM_now & (1u << r)) {

@@ -13,8 +13,11 @@ import torch
 from . import _lib
 from .program import Program
 
+# z, l, m, n of subannulus / annulus / circularbeam (sources.py:56-170): one value for the whole bundle
+SOURCE_CONST_ROWS = (3, 4, 5, 6)
 
-def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
+
+def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None, const_rows=()):
     """Run ``prog`` (a ``Program``) on a host bundle.
 
     rays : list of ten 1-D contiguous float64 numpy arrays (or torch CPU tensors, e.g.
@@ -22,6 +25,9 @@ def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
            reads nor writes may be None.
     keep_xy : optional pair of CUDA float64 tensors (length num) that receive the final x,y
            and stay resident on the device (e.g. for ``dist.hpd`` over a sharded bundle).
+    const_rows : indices of input rows the caller knows to be constant over the bundle (z, l, m, n of every
+           ``sources.*`` bundle: ``host.SOURCE_CONST_ROWS``); they are filled on the device instead of being
+           scanned and uploaded.
     Returns a dict with ``hpd`` (if requested), ``alive`` (uint8 flags, if requested and the
     program vignettes) and ``alive_count``.
     """
@@ -55,12 +61,15 @@ def trace(rays, prog, write_back=True, hpd=False, alive=False, keep_xy=None):
     h = ctypes.c_double(float("nan"))
     cnt = ctypes.c_int64(-1)
     flags = np.empty(num, dtype=np.uint8) if (alive and prog.has_vignette()) else None
-    rc = _lib.lib().pxf_host_trace_program(tab, num, ops, len(prog), 1 if write_back else 0,
-                                           ctypes.byref(h) if hpd else None,
-                                           flags.ctypes.data if flags is not None else None,
-                                           ctypes.byref(cnt),
-                                           keep_xy[0].data_ptr() if keep_xy is not None else None,
-                                           keep_xy[1].data_ptr() if keep_xy is not None else None)
+    mask = 0
+    for r in const_rows:
+        mask |= 1 << int(r)
+    rc = _lib.lib().pxf_host_trace_program_hint(tab, num, ops, len(prog), 1 if write_back else 0,
+                                                ctypes.byref(h) if hpd else None,
+                                                flags.ctypes.data if flags is not None else None,
+                                                ctypes.byref(cnt),
+                                                keep_xy[0].data_ptr() if keep_xy is not None else None,
+                                                keep_xy[1].data_ptr() if keep_xy is not None else None, mask)
     _lib.check(rc)
     out = {"alive_count": int(cnt.value)}
     if hpd:

@@ -80,6 +80,7 @@ def test_recorded_wrapper_calls_run_on_the_device():
         sig = PIN["signatures"][c["module"]][c["routine"]]
         rays = pxf.sources.subannulus(220., 221., .1, n, zhat=-1., rng="philox", seed=1, device="cuda")
         pxf.transformations.transform(rays, 0, 0, -8400., 0, 0, 0)
+        pxf.surfaces.wolterprimary(rays, 220., 8400.)            # gives the bundle surface normals (reflect / refract)
         rows = dict(zip(["opd", "x", "y", "z", "l", "m", "n", "ux", "uy", "uz"], rays))
         args = []
         ntab = 3
