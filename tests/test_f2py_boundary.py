@@ -63,7 +63,7 @@ def test_wrapper_calls_bind_to_the_replacement_signatures():
         for kind, arg in zip(c["kinds"], sig["python_order"]):
             rank = sig["args"][arg]["rank"]
             if c["routine"] in ("grat",) and arg in ("order", "wave"):
-                continue        # transformations.grat passes scalars where the Fortran declares arrays (f2py broadcasts size-1)
+                continue        # transformations.grat passes its order/wave through: arrays in the Fortran, so callers must pass rows
             assert (kind in ("array", "int_array", "sequence")) == (rank > 0), (c["routine"], arg, kind, rank)
 
 
@@ -98,6 +98,15 @@ def test_recorded_wrapper_calls_run_on_the_device():
                              "d": 160., "dpermm": .01, "order": 1., "wave": 2.4e-6, "thick": .4, "f": 100.,
                              "rin": 100., "rout": 50., "amp": 1e-4, "freq": .1}.get(arg, .01))
         before = [r.clone() for r in rays]
+        # a recorded SCALAR where the Fortran declares an intent(inout) array (transformations.grat's order, wave): f2py
+        # refuses a Python float there unless num == 1, and so does the replacement; the call a user can make passes rows
+        lifted = [k for k, (kind, arg) in enumerate(zip(c["kinds"], sig["python_order"]))
+                  if kind == "scalar" and sig["args"][arg]["rank"] > 0]
+        if lifted:
+            with pytest.raises(ValueError):
+                getattr(m, c["routine"])(*args)
+            for k in lifted:
+                args[k] = torch.full((n,), float(args[k]), dtype=torch.float64, device="cuda")
         out = getattr(m, c["routine"])(*args)
         assert out is None, c["routine"]
         torch.cuda.synchronize()
