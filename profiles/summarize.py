@@ -67,5 +67,44 @@ def kernel(path):
                 print("  %-88s %18s %s" % (k, d[k][0], d[k][1]))
 
 
+def sass(path, rays=None):
+    """Dynamic instruction mix from the source page (ncu -i X --page source --csv [| gzip]): warp instructions
+    executed per opcode, their share, and -- given the rays per launch -- thread instructions per ray."""
+    import gzip
+    op = gzip.open if path.endswith('.gz') else open
+    rows = list(csv.reader(op(path, 'rt')))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
+    hdr = rows[hi]
+    si, ei, ti, wi = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed'), hdr.index('# Samples')
+    agg = collections.OrderedDict()
+    tot = tt = ts = 0
+    for r in rows[hi + 1:]:
+        if len(r) <= ti:
+            continue
+        toks = r[si].split()
+        if not toks:
+            continue
+        o = toks[1] if toks[0].startswith('@') and len(toks) > 1 else toks[0]
+        o = o.rstrip(';')
+        base = o.split('.')[0]
+        key = o if base in ('MUFU', 'IMAD', 'LDG', 'STG', 'LDS', 'STS', 'LDL', 'STL') else base
+        key = 'IMAD.MOV' if key.startswith('IMAD.MOV') else ('IMAD' if key.startswith('IMAD') else key)
+        e, t, smp = int(r[ei] or 0), int(r[ti] or 0), int(r[wi] or 0)
+        a = agg.setdefault(key, [0, 0, 0])
+        a[0] += e; a[1] += t; a[2] += smp
+        tot += e; tt += t; ts += smp
+    print(rows[0][1][:150] if rows and len(rows[0]) > 1 else '')
+    print("warp instructions executed: %d; thread instructions: %d%s; stall samples: %d" %
+          (tot, tt, ("; per ray: %.1f" % (tt / rays)) if rays else "", ts))
+    print("%-14s %14s %7s %10s %8s" % ("opcode", "warp instr", "share", "per ray" if rays else "", "samples"))
+    for k, (e, t, smp) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        if e == 0 and smp == 0:
+            continue
+        print("%-14s %14d %7.3f %10s %8.3f" % (k, e, e / max(tot, 1), ("%.2f" % (t / rays)) if rays else "", smp / max(ts, 1)))
+
+
 if __name__ == '__main__':
+    if sys.argv[1] == 'sass':
+        sass(sys.argv[2], float(sys.argv[3]) if len(sys.argv) > 3 else None)
+        sys.exit(0)
     {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2])

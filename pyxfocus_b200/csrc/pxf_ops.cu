@@ -237,18 +237,36 @@ struct OpWolterSine {
     static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_woltersine(r, p); }
 };
-struct OpWsPrimary {
+// MINB / SCALAR as for OpZern: the W-S Newton loops are latency bound at two rays per thread and 140 registers
+// (8 warps per SM, fp64 pipe 30 %: profiles/r02d_k_op_wsprimary.txt)
+template <int MINB_ = 1, bool SCALAR_ = false>
+struct OpWsPrimaryT {
+    static constexpr int MINB = MINB_;
+    static constexpr bool SCALAR = SCALAR_;
     using Params = WSP;
     static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
     static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wsprimary(r, p); }
 };
-struct OpWsSecondary {
+template <int MINB_ = 1, bool SCALAR_ = false>
+struct OpWsSecondaryT {
+    static constexpr int MINB = MINB_;
+    static constexpr bool SCALAR = SCALAR_;
     using Params = WSP;
     static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
     static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_wssecondary(r, p); }
 };
+typedef OpWsPrimaryT<> OpWsPrimary;
+typedef OpWsSecondaryT<> OpWsSecondary;
+static int ws_variant()
+{
+    // PXF_WS_VARIANT (tuning): 0 = two rays per thread, uncapped; 1 = two rays, capped for 2 CTAs/SM; 2/3/4 = one ray
+    // per thread capped for 3/4/2 CTAs/SM
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("PXF_WS_VARIANT"); variant = e ? atoi(e) : 2; }   // measured at 5e7 rays, primary / secondary: 2.60/5.70, 1.68/3.59, 1.51/3.21, 1.76/3.21, 1.76/3.58 ms for 0..4
+    return variant;
+}
 struct OpWsPrimaryBack {
     using Params = WSP;
     static constexpr unsigned LOAD = R_NINE, STORE = R_POS | R_NRM;
@@ -343,15 +361,16 @@ struct OpZernPhase {
     }
 };
 
-template <int NMAX, int MINB_ = 1, bool SCALAR_ = false>
+template <int N, int MINB_ = 2, bool SCALAR_ = false>
 struct OpLL {
     static constexpr int MINB = MINB_;
     static constexpr bool SCALAR = SCALAR_;
     using Params = LLP;
     static constexpr unsigned LOAD = R_POS | R_DIR, STORE = R_POS | R_NRM;
-    static constexpr int AUX = 0, SMEM = (NMAX + 1) * (NMAX + 1);
+    static constexpr int AUX = 0, SMEM = 0;
     PXF_DEV static const double *table(const Params &p) { return p.C; }
-    PXF_DEV static void apply(Ray &r, const Params &p, const double *smem, double, double) { op_ll<NMAX>(r, p, smem); }
+    // the coefficient matrix is read straight from the kernel parameter (constant bank, static offsets)
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double) { op_ll<N>(r, p, p.C); }
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -482,7 +501,18 @@ static int launch_zern(RowPtrs P, int64_t num, const uint8_t *mask, const ZernP 
 {
     // (measured, profiles/r01h_notes.md: two rays per thread at ~240 registers = 8 warps/SM runs 3.69 ms per 5e7
     // rays; one ray per thread capped for 1/2/3 CTAs per SM 4.12/3.99/4.03 ms -- the evaluation is issue bound)
-    if (z.nmax <= 7) return launch_op<OpZern<7, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+    if (z.nmax <= 7) {
+        // PXF_ZERN_VARIANT (tuning; the Cartesian Horner form needs far fewer live values than the polar one):
+        // 0 = two rays per thread, uncapped registers; 1 = two rays, capped for 2 CTAs/SM; 2/3/4 = one ray per thread
+        // capped for 3/4/2 CTAs/SM
+        static int variant = -1;
+        if (variant < 0) { const char *e = getenv("PXF_ZERN_VARIANT"); variant = e ? atoi(e) : 3; }   // measured, 36 terms at 5e7 rays: 1.81 / 1.35 / 1.46 / 1.35 / 1.50 ms for 0..4 (profiles/r02_notes.md)
+        if (variant == 1) return launch_op<OpZern<7, OPD, 2, false>>(P, num, mask, nullptr, nullptr, z, stream);
+        if (variant == 2) return launch_op<OpZern<7, OPD, 3, true>>(P, num, mask, nullptr, nullptr, z, stream);
+        if (variant == 3) return launch_op<OpZern<7, OPD, 4, true>>(P, num, mask, nullptr, nullptr, z, stream);
+        if (variant == 4) return launch_op<OpZern<7, OPD, 2, true>>(P, num, mask, nullptr, nullptr, z, stream);
+        return launch_op<OpZern<7, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
+    }
     if (z.nmax <= 11) return launch_op<OpZern<11, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
     return launch_op<OpZern<15, OPD>>(P, num, mask, nullptr, nullptr, z, stream);
 }
@@ -497,17 +527,23 @@ static int launch_ll(RowPtrs P, int64_t num, const uint8_t *mask, int kind, doub
         set_error("invalid Legendre orders (need 0 <= order <= %d)", PXF_LL_MAXN);
         return PXF_ERR_INVALID;
     }
-    if (q.stride == 8) {
-        // PXF_LL_VARIANT (tuning): 0 = two rays per thread (~250 registers, 8 warps/SM), 1/2/3 = one ray per thread
-        // with the register allocation capped for 1/2/3 resident CTAs per SM
+    // one instantiation per padded order (the Horner scheme is fully unrolled, coefficients read with static offsets)
+    switch (q.stride - 1) {
+    case 3: return launch_op<OpLL<3>>(P, num, mask, nullptr, nullptr, q, stream);
+    case 5: {
+        // PXF_LL_VARIANT (tuning): 0 = two rays per thread capped for 2 CTAs/SM; 1/2 = one ray per thread capped for
+        // 3/4 CTAs/SM; 3 = two rays per thread, uncapped
         static int variant = -1;
-        if (variant < 0) { const char *e = getenv("PXF_LL_VARIANT"); variant = e ? atoi(e) : 2; }   // measured, 36 terms at 5e7 rays: 8.37 / 8.71 / 7.92 / 8.15 ms for 0 / 1 / 2 / 3
-        if (variant == 1) return launch_op<OpLL<7, 1, true>>(P, num, mask, nullptr, nullptr, q, stream);
-        if (variant == 0) return launch_op<OpLL<7>>(P, num, mask, nullptr, nullptr, q, stream);
-        if (variant == 3) return launch_op<OpLL<7, 3, true>>(P, num, mask, nullptr, nullptr, q, stream);
-        return launch_op<OpLL<7, 2, true>>(P, num, mask, nullptr, nullptr, q, stream);
+        if (variant < 0) { const char *e = getenv("PXF_LL_VARIANT"); variant = e ? atoi(e) : 2; }   // measured, 36 terms at 5e7 rays: 2.68 / 2.58 / 2.55 / 3.74 ms for 0..3
+        if (variant == 1) return launch_op<OpLL<5, 3, true>>(P, num, mask, nullptr, nullptr, q, stream);
+        if (variant == 2) return launch_op<OpLL<5, 4, true>>(P, num, mask, nullptr, nullptr, q, stream);
+        if (variant == 3) return launch_op<OpLL<5, 1, false>>(P, num, mask, nullptr, nullptr, q, stream);
+        return launch_op<OpLL<5>>(P, num, mask, nullptr, nullptr, q, stream);
     }
-    return launch_op<OpLL<15>>(P, num, mask, nullptr, nullptr, q, stream);
+    case 7: return launch_op<OpLL<7>>(P, num, mask, nullptr, nullptr, q, stream);
+    case 11: return launch_op<OpLL<11>>(P, num, mask, nullptr, nullptr, q, stream);
+    default: return launch_op<OpLL<15>>(P, num, mask, nullptr, nullptr, q, stream);
+    }
 }
 
 }  // namespace pxf
@@ -663,6 +699,14 @@ int pxf_wsprimary(double *x, double *y, double *z, double *l, double *m, double 
                   double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
                   const uint8_t *mask, pxf_stream_t stream)
 {
+    if (ws_variant() == 1) return launch_op<OpWsPrimaryT<2, false>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 2) return launch_op<OpWsPrimaryT<3, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 3) return launch_op<OpWsPrimaryT<4, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 4) return launch_op<OpWsPrimaryT<2, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                  make_ws(alpha, z0, psi), stream);
     return launch_op<OpWsPrimary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
                                   make_ws(alpha, z0, psi), stream);
 }
@@ -671,6 +715,14 @@ int pxf_wssecondary(double *x, double *y, double *z, double *l, double *m, doubl
                     double *ux, double *uy, double *uz, int64_t num, double alpha, double z0, double psi,
                     const uint8_t *mask, pxf_stream_t stream)
 {
+    if (ws_variant() == 1) return launch_op<OpWsSecondaryT<2, false>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                    make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 2) return launch_op<OpWsSecondaryT<3, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                    make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 3) return launch_op<OpWsSecondaryT<4, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                    make_ws(alpha, z0, psi), stream);
+    if (ws_variant() == 4) return launch_op<OpWsSecondaryT<2, true>>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
+                                    make_ws(alpha, z0, psi), stream);
     return launch_op<OpWsSecondary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
                                     make_ws(alpha, z0, psi), stream);
 }

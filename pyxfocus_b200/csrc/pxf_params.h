@@ -253,8 +253,28 @@ inline int make_ll(LLP &q, int kind, double r0, double z0, double psi, double S,
         if (az[a] > nt) nt = az[a];
     }
     q.nz = nz; q.nt = nt;
-    q.stride = (nz <= 7 && nt <= 7) ? 8 : 16;
-    for (int a = 0; a < cnum; a++) q.C[axial[a] * q.stride + az[a]] += coeff[a];
+    const int top = nz > nt ? nz : nt;
+    const int N = top <= 3 ? 3 : top <= 5 ? 5 : top <= 7 ? 7 : top <= 11 ? 11 : 15;
+    q.stride = N + 1;
+    // power-basis coefficients of P_0..P_15 from (n+1) P_{n+1} = (2n+1) x P_n - n P_{n-1} (dyadic rationals with
+    // numerators < 2**53: exact), then  M[a][b] = sum_t coeff_t * L[axial_t][a] * L[az_t][b]  accumulated in long double
+    static long double L[PXF_LL_MAXN + 1][PXF_LL_MAXN + 1];
+    static bool have_L = false;
+    if (!have_L) {
+        memset(L, 0, sizeof(L));
+        L[0][0] = 1.L; L[1][1] = 1.L;
+        for (int n = 1; n < PXF_LL_MAXN; n++)
+            for (int k = 0; k <= n + 1; k++)
+                L[n + 1][k] = ((2 * n + 1) * (k ? L[n][k - 1] : 0.L) - n * L[n - 1][k]) / (n + 1);
+        have_L = true;
+    }
+    long double M[PXF_LL_MAXN + 1][PXF_LL_MAXN + 1];
+    memset(M, 0, sizeof(M));
+    for (int t = 0; t < cnum; t++)
+        for (int a = 0; a <= axial[t]; a++)
+            for (int b = 0; b <= az[t]; b++) M[a][b] += (long double)coeff[t] * L[axial[t]][a] * L[az[t]][b];
+    for (int a = 0; a <= N; a++)
+        for (int b = 0; b <= N; b++) q.C[a * q.stride + b] = (double)M[a][b];
     q.zmid = (zmax + zmin) / 2.;
     q.zhalf = (zmax - zmin) / 2.;
     q.dphi = dphi;
@@ -369,6 +389,31 @@ inline int make_zern(ZernP &z, const double *coeff, const int32_t *rorder, const
             }
             e += n / 2 + 1;
         }
+    }
+    // ... and the same polynomial in Cartesian form (ZernP::xy), expanded in long double
+    memset(z.xy, 0, sizeof(z.xy));
+    if (z.nmax <= 7) {
+        long double K[8][8];
+        memset(K, 0, sizeof(K));
+        long double binom[8][8];
+        memset(binom, 0, sizeof(binom));
+        for (int n = 0; n < 8; n++) {
+            binom[n][0] = 1.L;
+            for (int k = 1; k <= n; k++) binom[n][k] = binom[n - 1][k - 1] + (k <= n - 1 ? binom[n - 1][k] : 0.L);
+        }
+        for (int m = 0; m < PXF_ZERN_PM; m++)
+            for (int j = 0; j < PXF_ZERN_PJ; j++)
+                for (int cs = 0; cs < 2; cs++) {
+                    const long double c = z.pc[m][j][cs];
+                    if (c == 0.L || m + 2 * j > 7) continue;
+                    // Re / Im of (X+iY)**m: terms X**(m-k) Y**k with k even / odd, sign (-1)**(k div 2)
+                    for (int k = cs; k <= m; k += 2) {
+                        const long double w = c * binom[m][k] * (((k / 2) & 1) ? -1.L : 1.L);
+                        for (int i = 0; i <= j; i++) K[m - k + 2 * i][k + 2 * (j - i)] += w * binom[j][i];
+                    }
+                }
+        for (int a = 0; a < 8; a++)
+            for (int b = 0; a + b <= 7; b++) z.xy[PXF_ZERN_XYOFF(a) + b] = (double)K[a][b];
     }
     return z.nmax;
 }
