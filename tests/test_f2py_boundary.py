@@ -89,9 +89,9 @@ def test_recorded_wrapper_calls_run_on_the_device():
                 args.append(rows[arg])
             elif kind == "array":
                 per_ray = sig["args"][arg]["rank"] > 0 and arg in ("wave",)
-                args.append(torch.full((n,), 2.4e-6, dtype=torch.float64, device="cuda") if per_ray else np.zeros(ntab))
+                args.append(torch.full((n,), 2.4e-6, dtype=torch.float64, device="cuda") if per_ray else np.full(ntab, 1e-4))
             elif kind == "int_array":
-                args.append(np.array([0, 1, 1][:ntab]) if arg.startswith(("rorder", "axial")) else np.array([0, 1, -1][:ntab]))
+                args.append(np.array([0, 1, -1][:ntab]) if arg.startswith("aorder") else np.array([0, 1, 1][:ntab]))   # Zernike azimuthal orders may be negative (sine terms); Legendre orders not
             else:
                 args.append({"r0": 220., "z0": 8400., "psi": 1., "rad": 100., "r": 1000., "k": -1., "n1": 1., "n2": 1.5,
                              "alpha": .0065, "tg": .0065, "zmax": 8500., "zmin": 8400., "dphi": .1, "nr": 1.,
