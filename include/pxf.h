@@ -81,6 +81,18 @@ int pxf_reflect(double *l, double *m, double *n, double *ux, double *uy, double 
 /* transformationsf.f95:82-130 */
 int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double *uz, int64_t num,
                 double n1, double n2, const uint8_t *mask, pxf_stream_t stream);
+/* transformations.pointTo (transformations.py:91-100): l,m,n = reverse*(r - p0)/|r - p0|. */
+int pxf_pointto(const double *x, const double *y, const double *z, double *l, double *m, double *n, int64_t num,
+                double x0, double y0, double z0, double reverse, const uint8_t *mask, pxf_stream_t stream);
+/* transformations.applyT (transformations.py:257-280), in place: positions through the first three rows of the 4x4
+ * point matrix, direction cosines and normals through those of the 4x4 rotation matrix (HOST row-major double[>=12],
+ * i.e. coords[i+1] and coords[i]). */
+int pxf_applyt(double *x, double *y, double *z, double *l, double *m, double *n, double *ux, double *uy, double *uz,
+               int64_t num, const double *point_matrix, const double *rotation_matrix, pxf_stream_t stream);
+/* analyses.indAngle (analyses.py:164-182): ang[i] = arccos(l ux + m uy + n uz), or arccos(normal . (l,m,n)) when
+ * `normal` (HOST double[3]) is given (ux,uy,uz may then be NULL).  Rays with mask[i]==0 leave ang[i] untouched. */
+int pxf_indangle(const double *l, const double *m, const double *n, const double *ux, const double *uy, const double *uz,
+                 double *ang, int64_t num, const double *normal, const uint8_t *mask, pxf_stream_t stream);
 /* transformationsf.f95:205-238 (scalar wavelength; sign of n kept) */
 int pxf_radgrat(const double *x, const double *y, double *l, double *m, double *n, double wave,
                 int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream);
@@ -384,7 +396,8 @@ int pxf_compact_indices(const uint8_t *flags, int64_t num, const void *scratch, 
  *   PXF_SUMS_IMAGEPLANE : [0]=sum w, [1]=sum w x, [2]=sum w y, [3]=sum w l/n, [4]=sum w m/n,
  *                         [5]=sum w x l/n, [6]=sum w y m/n, [7]=sum w (l/n)^2, [8]=sum w (m/n)^2
  * Deterministic (fixed-shape tree, no atomics).  scratch: pxf_sums_scratch_bytes() bytes. */
-enum { PXF_SUMS_CENTROID = 0, PXF_SUMS_RMS = 1, PXF_SUMS_IMAGEPLANE = 2, PXF_SUMS_IMAGEPLANE_Z = 3 };
+enum { PXF_SUMS_CENTROID = 0, PXF_SUMS_RMS = 1, PXF_SUMS_IMAGEPLANE = 2, PXF_SUMS_IMAGEPLANE_Z = 3,
+       PXF_SUMS_POINT = 4 /* internal to pxf_rmspoint: sum w, sum w |r - p|^2 */ };
 size_t pxf_sums_scratch_bytes(void);
 int pxf_sums(int32_t mode, const double *x, const double *y, const double *l, const double *m,
              const double *n, const double *w, int64_t num, double a, double b,
@@ -513,6 +526,9 @@ int pxf_rmscentroid(const double *x, const double *y, const double *w, int64_t n
                     double *rms_host, pxf_stream_t stream);
 int pxf_hpd(const double *x, const double *y, const double *w, int64_t num, double *hpd_host,
             pxf_stream_t stream);
+/* analyses.rmsPoint (analyses.py:33-45): sqrt(average((x-px)^2+(y-py)^2+(z-pz)^2, weights)); w may be NULL. */
+int pxf_rmspoint(const double *x, const double *y, const double *z, const double *w, int64_t num,
+                 double px, double py, double pz, double *rms_host, pxf_stream_t stream);
 int pxf_analyticimageplane(const double *x, const double *y, const double *l, const double *m,
                            const double *n, const double *w, int64_t num, double *dz_host,
                            pxf_stream_t stream);
@@ -628,6 +644,32 @@ int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, c
  * Same Philox stream as per-segment pxf_source calls with first + seg_start[s]. */
 int pxf_source_segmented(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
                          int32_t nseg, const int64_t *seg_start_dev, const double *params_dev, pxf_stream_t stream);
+
+/* The reference's set-up sources (sources.py:173-471), generated on the device.
+ * Grid sources are functions of the global ray index first+i alone (numpy.linspace / meshgrid arithmetic restated:
+ * i*step + start, last point pinned to stop; meshgrid flattened row-major):
+ *   PXF_SRC_XSLIT     (sources.py:173-207)  a=xin b=xout c=zhat, n1 = num
+ *   PXF_SRC_RECTARRAY (sources.py:210-247)  a=xsize b=ysize,     n1 = num (n1*n1 rays)
+ *   PXF_SRC_FANBEAM   (sources.py:418-442)  a=xang b=yang,       n1 = num (n1*n1 rays)
+ *   PXF_SRC_CIRCFAN   (sources.py:444-471)  a=halfang,           n1 = rings, n2 = arms (n1*n2 rays)
+ * `num` rays starting at global index `first` are written (a shard of the source). */
+enum { PXF_SRC_XSLIT = 4, PXF_SRC_RECTARRAY = 5, PXF_SRC_CONVERGING = 6, PXF_SRC_CONVERGING2 = 7, PXF_SRC_RECTBEAM = 8,
+       PXF_SRC_GAUSSIAN = 9, PXF_SRC_FANBEAM = 10, PXF_SRC_CIRCFAN = 11 };
+int pxf_source_grid(int32_t kind, double *const rays[10], int64_t num, int64_t first, int64_t n1, int64_t n2,
+                    double a, double b, double c, pxf_stream_t stream);
+/* Beam sources: two or three random draws per ray.
+ *   PXF_SRC_CONVERGING  (sources.py:250-296) par = (zset, rin, rout, tmin, tmax, lscat); draws: radius, angle, scatter
+ *   PXF_SRC_CONVERGING2 (sources.py:299-345) par = (zset, xmin, xmax, ymin, ymax, lscat); draws: x, y, scatter
+ *   PXF_SRC_RECTBEAM    (sources.py:348-379) par = (xhalfwidth, yhalfwidth);             draws: x, y
+ *   PXF_SRC_GAUSSIAN    (sources.py:381-416) par = (ang);                                draws: two standard normals
+ * pxf_source_beam draws on the device (Philox4x32-10 keyed like pxf_source; block 1 of a ray's counter feeds the
+ * third draw, the normals are a Box-Muller pair); pxf_source_beam_from_draws applies the same formulas to
+ * caller-supplied device arrays (numpy's stream in the reference's order of draws; d3 may be NULL for two-draw
+ * kinds).  par is a HOST array. */
+int pxf_source_beam(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+                    const double *par, pxf_stream_t stream);
+int pxf_source_beam_from_draws(int32_t kind, double *const rays[10], int64_t num, const double *d1, const double *d2,
+                               const double *d3, const double *par, pxf_stream_t stream);
 
 /* ======================= host-buffer entry point ======================== */
 /* The call an f2py user makes (the reference's extension modules take HOST numpy arrays and

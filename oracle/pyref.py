@@ -59,6 +59,98 @@ def pointsource(ang, num):
     return [_zeros(num), _zeros(num), _zeros(num), _zeros(num), l, m, n, _zeros(num), _zeros(num), _zeros(num)]
 
 
+# ---------------------------------------------------------------- sources.py, the set-up sources (:173-471)
+# numpy restatements (same expressions, same order of draws from numpy's global stream); the product generates
+# these on the device (pxf_source_grid / pxf_source_beam) and the GPU tests compare against these.
+def _bundle(opd, x, y, z, l, m, n, ux, uy, uz):
+    return [np.array(a, dtype=np.float64) for a in (opd, x, y, z, l, m, n, ux, uy, uz)]
+
+
+def xslit(xin, xout, num, zhat=-1.):
+    """Slit of rays linearly spaced in x (sources.py:173-207)."""
+    x = np.linspace(xin, xout, num)
+    zero = np.repeat(0., num)
+    return _bundle(zero, x, zero, zero, zero, zero, np.repeat(zhat, num), zero, zero, zero)
+
+
+def rectArray(xsize, ysize, num):
+    """num x num rectangular grid of rays in +z (sources.py:210-247)."""
+    x, y = np.meshgrid(np.linspace(-xsize, xsize, num), np.linspace(-ysize, ysize, num))
+    zero = np.repeat(0., num ** 2)
+    return _bundle(zero, x.flatten(), y.flatten(), zero, zero, zero, np.repeat(1., num ** 2), zero, zero, zero)
+
+
+def _converging(x, y, rho, theta, zset, num, lscat):
+    z = np.repeat(zset, num)
+    lscat = lscat * np.tan((np.random.rand(num) - .5) * np.pi)
+    lscat = lscat / 60 ** 2 * np.pi / 180.
+    n = -np.cos(np.arctan(rho / zset) + lscat)
+    l = -np.sqrt(1 - n ** 2) * np.cos(theta)
+    m = -np.sqrt(1 - n ** 2) * np.sin(theta)
+    zero = np.repeat(0., num)
+    return _bundle(zero, x, y, z, l, m, n, zero, zero, zero)
+
+
+def convergingbeam(zset, rin, rout, tmin, tmax, num, lscat):
+    """Converging sub-apertured annulus beam placed at its nominal focus (sources.py:250-296)."""
+    rho = np.sqrt(rin ** 2 + np.random.rand(num) * (rout ** 2 - rin ** 2))
+    theta = tmin + np.random.rand(num) * (tmax - tmin)
+    x = rho * np.cos(theta)
+    y = rho * np.sin(theta)
+    return _converging(x, y, rho, theta, zset, num, lscat)
+
+
+def convergingbeam2(zset, xmin, xmax, ymin, ymax, num, lscat):
+    """Converging rectangular beam placed at its nominal focus (sources.py:299-345)."""
+    x = xmin + np.random.rand(num) * (xmax - xmin)
+    y = ymin + np.random.rand(num) * (ymax - ymin)
+    rho = np.sqrt(x ** 2 + y ** 2)
+    theta = np.arctan2(y, x)
+    return _converging(x, y, rho, theta, zset, num, lscat)
+
+
+def rectbeam(xhalfwidth, yhalfwidth, num):
+    """Uniform rectangular beam in +z (sources.py:348-379)."""
+    x = (np.random.rand(num) - .5) * 2 * xhalfwidth
+    y = (np.random.rand(num) - .5) * 2 * yhalfwidth
+    zero = np.repeat(0., num)
+    return _bundle(zero, x, y, zero, zero, zero, np.repeat(1., num), zero, zero, zero)
+
+
+def gaussianBeam(ang, num):
+    """Point source with a Gaussian angular profile (sources.py:381-416)."""
+    l = np.random.randn(num) * np.sin(ang) / np.sqrt(2)
+    m = np.random.randn(num) * np.sin(ang) / np.sqrt(2)
+    n = np.sqrt(1. - l ** 2 - m ** 2)
+    zero = np.repeat(0., num)
+    return _bundle(zero, zero, zero, zero, l, m, n, zero, zero, zero)
+
+
+def _fan(xa, ya):
+    num = np.size(xa)
+    l = np.sin(xa)
+    m = np.sin(ya)
+    n = np.sqrt(1. - l ** 2 - m ** 2)
+    zero = np.repeat(0., num)
+    return _bundle(zero, zero, zero, zero, l, m, n, zero, zero, zero)
+
+
+def fanBeam(xang, yang, num):
+    """Rectangular fan of rays from a point (sources.py:418-442)."""
+    xa, ya = np.meshgrid(np.linspace(-xang, xang, num), np.linspace(-yang, yang, num))
+    return _fan(xa.flatten(), ya.flatten())
+
+
+def circFan(halfang, rings, arms):
+    """Circular fan of rays from a point: ``rings`` radii x ``arms`` azimuths (sources.py:444-471)."""
+    rad = np.linspace(0, halfang, rings)
+    az = np.linspace(0, 2 * np.pi, arms + 1)[0:-1]
+    rr, aa = np.meshgrid(rad, az)
+    xx = np.sin(rr) * np.cos(aa)
+    yy = np.sin(rr) * np.sin(aa)
+    return _fan(xx.flatten(), yy.flatten())
+
+
 # ---------------------------------------------------------------- transformations.py
 def vignette(rays, ind=None):
     """transformations.py:214-225"""

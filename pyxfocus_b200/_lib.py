@@ -48,6 +48,9 @@ SIGNATURES = {
     "pxf_itransform": (_c.c_int, _NINE + [_i64] + [_d] * 6 + [_vp, _st]),
     "pxf_reflect": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
     "pxf_refract": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _vp, _st]),
+    "pxf_pointto": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _d, _d, _vp, _st]),
+    "pxf_applyt": (_c.c_int, _NINE + [_i64, _vp, _vp, _st]),
+    "pxf_indangle": (_c.c_int, [_dp] * 7 + [_i64, _vp, _vp, _st]),
     "pxf_radgrat": (_c.c_int, [_dp] * 5 + [_d, _i64, _d, _d, _vp, _st]),
     "pxf_radgratw": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _vp, _st]),
     "pxf_grat": (_c.c_int, [_dp] * 5 + [_i64, _d, _dp, _dp, _vp, _st]),
@@ -138,6 +141,7 @@ SIGNATURES = {
     "pxf_centroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _vp, _st]),
     "pxf_rmscentroid": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_hpd": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
+    "pxf_rmspoint": (_c.c_int, [_dp, _dp, _dp, _dp, _i64, _d, _d, _d, _vp, _st]),
     "pxf_analyticimageplane": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
     "pxf_hpd_weighted": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
     "pxf_hpd_weighted_sorted": (_c.c_int, [_dp, _dp, _dp, _i64, _vp, _st]),
@@ -179,6 +183,9 @@ SIGNATURES = {
     "pxf_segmented_table_fill": (_c.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "pxf_trace_program_segmented": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _st]),
     "pxf_source_from_uniform": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _d, _d, _d, _d, _st]),
+    "pxf_source_grid": (_c.c_int, [_i32, _vp, _i64, _i64, _i64, _i64, _d, _d, _d, _st]),
+    "pxf_source_beam": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _vp, _st]),
+    "pxf_source_beam_from_draws": (_c.c_int, [_i32, _vp, _i64, _dp, _dp, _dp, _vp, _st]),
     # host-buffer entry point
     "pxf_host_trace_program": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pxf_host_trace_program_hint": (_c.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _c.c_uint32]),

@@ -264,30 +264,37 @@ def hpdY(rays, weights=None):
 
 
 def rmsPoint(rays, point, weights=None):
-    """RMS distance of the rays from a point: a ten-row ray or an (x,y,z) triple (analyses.py:33-45).
-    Not on the trace path: plain tensor arithmetic on the device rows."""
+    """RMS distance of the rays from a point: a ten-row ray or an (x,y,z) triple (analyses.py:33-45)."""
     flush(rays)
     off = 1 if np.size(point) == 10 else 0
     px, py, pz = (float(point[off + k]) for k in range(3))
-    rho = (rays[1] - px) ** 2 + (rays[2] - py) ** 2 + (rays[3] - pz) ** 2
-    w = _w(weights, rays[1])
-    mean = rho.mean() if w is None else (rho * w).sum() / w.sum()
-    return float(torch.sqrt(mean))
+    x, y, z = rays[1:4]
+    w = _w(weights, x)
+    out = ctypes.c_double()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_rmspoint(x.data_ptr(), y.data_ptr(), z.data_ptr(), _ptr(w), x.shape[0], px, py, pz,
+                                           ctypes.byref(out), stream_ptr(x.device)))
+    return out.value
 
 
 def indAngle(rays, ind=None, normal=None):
     """Incidence angle against the current or a given surface normal (analyses.py:164-182); returns a
-    device tensor.  Not on the trace path: plain tensor arithmetic."""
+    device tensor (one pxf_indangle launch; ``ind`` -- bool mask or index array -- selects rays like numpy
+    indexing does in the reference, through the library's compaction / gather kernels)."""
     flush(rays)
     l, m, n, ux, uy, uz = rays[4:10]
-    if ind is not None:
-        if not isinstance(ind, torch.Tensor):
-            ind = torch.as_tensor(np.asarray(ind), device=l.device)
-        l, m, n, ux, uy, uz = (t[ind] for t in (l, m, n, ux, uy, uz))
-    if normal is None:
-        return torch.arccos(l * ux + m * uy + n * uz)
-    nx, ny, nz = (float(v) for v in normal)
-    return torch.arccos(nx * l + ny * m + nz * n)
+    dev = l.device
+    num = l.shape[0]
+    ang = torch.empty_like(l)
+    nrm = None if normal is None else (ctypes.c_double * 3)(*[float(v) for v in normal])
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.pxf_indangle(l.data_ptr(), m.data_ptr(), n.data_ptr(), ux.data_ptr(), uy.data_ptr(), uz.data_ptr(),
+                                  ang.data_ptr(), num, nrm, None, stream_ptr(dev)))
+    if ind is None:
+        return ang
+    from .transformations import take
+    return take([ang], ind)[0]
 
 
 def grazeAngle(rays, ind=None):

@@ -13,7 +13,7 @@ namespace pxf {
 // ------------------------------------------------------------------ sums
 template <int MODE>
 PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m, double n, double w,
-                        bool has_w, double a, double b, double z = 0.)
+                        bool has_w, double a, double b, double z = 0., double c = 0.)
 {
     if (MODE == PXF_SUMS_CENTROID) {
         acc[0] += w;
@@ -22,6 +22,11 @@ PXF_DEV void sums_accum(double acc[NSUM], double x, double y, double l, double m
         acc[3] += 1.;
     } else if (MODE == PXF_SUMS_RMS) {
         double rho = sq(x - a) + sq(y - b);
+        acc[0] += w;
+        acc[1] += has_w ? rho * w : rho;
+    } else if (MODE == PXF_SUMS_POINT) {
+        // analyses.py:33-45: (x-px)**2 + (y-py)**2 + (z-pz)**2
+        double rho = sq(x - a) + sq(y - b) + sq(z - c);
         acc[0] += w;
         acc[1] += has_w ? rho * w : rho;
     } else {
@@ -54,11 +59,11 @@ __global__ void __launch_bounds__(PXF_BLOCK)
 k_sums(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ l,
        const double *__restrict__ m, const double *__restrict__ n, const double *__restrict__ w,
        int64_t num, double a, double b, const double *__restrict__ ab_dev, double *__restrict__ partial,
-       const double *__restrict__ z = nullptr)
+       const double *__restrict__ z = nullptr, double c = 0.)
 {
-    constexpr int NS = MODE == PXF_SUMS_CENTROID ? 4 : (MODE == PXF_SUMS_RMS ? 2 : 9);
+    constexpr int NS = MODE == PXF_SUMS_CENTROID ? 4 : ((MODE == PXF_SUMS_RMS || MODE == PXF_SUMS_POINT) ? 2 : 9);
     constexpr bool IP = MODE == PXF_SUMS_IMAGEPLANE || MODE == PXF_SUMS_IMAGEPLANE_Z;
-    constexpr bool ZZ = MODE == PXF_SUMS_IMAGEPLANE_Z;
+    constexpr bool ZZ = MODE == PXF_SUMS_IMAGEPLANE_Z || MODE == PXF_SUMS_POINT;
     constexpr int U = IP ? 2 : 4;
     if (ab_dev) { a = ab_dev[0]; b = ab_dev[1]; }
     double acc[U][NSUM];
@@ -91,14 +96,14 @@ k_sums(const double *__restrict__ x, const double *__restrict__ y, const double 
 #pragma unroll
             for (int u = 0; u < U; u++)
                 if (q0 + u * nthr < npair) {
-                    sums_accum<MODE>(acc[u], xv[u].x, yv[u].x, lv[u].x, mv[u].x, nv[u].x, wv[u].x, has_w, a, b, zv[u].x);
-                    sums_accum<MODE>(acc[u], xv[u].y, yv[u].y, lv[u].y, mv[u].y, nv[u].y, wv[u].y, has_w, a, b, zv[u].y);
+                    sums_accum<MODE>(acc[u], xv[u].x, yv[u].x, lv[u].x, mv[u].x, nv[u].x, wv[u].x, has_w, a, b, zv[u].x, c);
+                    sums_accum<MODE>(acc[u], xv[u].y, yv[u].y, lv[u].y, mv[u].y, nv[u].y, wv[u].y, has_w, a, b, zv[u].y, c);
                 }
         }
         if ((num & 1) && tid == 0) {
             const int64_t i = num - 1;
             sums_accum<MODE>(acc[0], x[i], y[i], IP ? l[i] : 0., IP ? m[i] : 0.,
-                             IP ? n[i] : 1., has_w ? w[i] : 1., has_w, a, b, ZZ ? z[i] : 0.);
+                             IP ? n[i] : 1., has_w ? w[i] : 1., has_w, a, b, ZZ ? z[i] : 0., c);
         }
     } else {
         for (int64_t i0 = tid; i0 < num; i0 += U * nthr) {
@@ -117,7 +122,7 @@ k_sums(const double *__restrict__ x, const double *__restrict__ y, const double 
             }
 #pragma unroll
             for (int u = 0; u < U; u++)
-                if (i0 + u * nthr < num) sums_accum<MODE>(acc[u], xv[u], yv[u], lv[u], mv[u], nv[u], wv[u], has_w, a, b, zv[u]);
+                if (i0 + u * nthr < num) sums_accum<MODE>(acc[u], xv[u], yv[u], lv[u], mv[u], nv[u], wv[u], has_w, a, b, zv[u], c);
         }
     }
 #pragma unroll
@@ -172,17 +177,19 @@ k_sums_final(const double *__restrict__ partial, int nblocks, int ns, double *__
 
 static int sums_launch(int mode, const double *x, const double *y, const double *l, const double *m,
                        const double *n, const double *w, int64_t num, double a, double b,
-                       const double *ab_dev, double *out_dev, void *scratch, cudaStream_t s, const double *z = nullptr)
+                       const double *ab_dev, double *out_dev, void *scratch, cudaStream_t s, const double *z = nullptr,
+                       double c = 0.)
 {
     if (num < 0 || !x || !y || !out_dev || !scratch) { set_error("pxf_sums: bad argument"); return PXF_ERR_INVALID; }
     const bool ip = mode == PXF_SUMS_IMAGEPLANE || mode == PXF_SUMS_IMAGEPLANE_Z;
     if (ip && (!l || !m || !n)) { set_error("pxf_sums: l,m,n required"); return PXF_ERR_INVALID; }
-    if (mode == PXF_SUMS_IMAGEPLANE_Z && !z) { set_error("pxf_sums: z required"); return PXF_ERR_INVALID; }
+    if ((mode == PXF_SUMS_IMAGEPLANE_Z || mode == PXF_SUMS_POINT) && !z) { set_error("pxf_sums: z required"); return PXF_ERR_INVALID; }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     int grid = grid_for(num, PXF_BLOCK * 8, 4);
     if (grid > SUM_BLOCKS_MAX) grid = SUM_BLOCKS_MAX;
     double *partial = static_cast<double *>(scratch);
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w);
+    if (mode == PXF_SUMS_POINT) al |= reinterpret_cast<uintptr_t>(z);
     if (ip)
         al |= reinterpret_cast<uintptr_t>(l) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(n) |
               reinterpret_cast<uintptr_t>(z);
@@ -190,13 +197,14 @@ static int sums_launch(int mode, const double *x, const double *y, const double 
     int ns;
 #define PXF_SUMS_GO(M)                                                                                         \
     do {                                                                                                       \
-        if (v2) k_sums<M, true><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z);     \
-        else k_sums<M, false><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z);       \
+        if (v2) k_sums<M, true><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z, c);  \
+        else k_sums<M, false><<<grid, PXF_BLOCK, 0, s>>>(x, y, l, m, n, w, num, a, b, ab_dev, partial, z, c);    \
     } while (0)
     if (mode == PXF_SUMS_CENTROID) { ns = 4; PXF_SUMS_GO(PXF_SUMS_CENTROID); }
     else if (mode == PXF_SUMS_RMS) { ns = 2; PXF_SUMS_GO(PXF_SUMS_RMS); }
     else if (mode == PXF_SUMS_IMAGEPLANE) { ns = 9; PXF_SUMS_GO(PXF_SUMS_IMAGEPLANE); }
     else if (mode == PXF_SUMS_IMAGEPLANE_Z) { ns = 9; PXF_SUMS_GO(PXF_SUMS_IMAGEPLANE_Z); }
+    else if (mode == PXF_SUMS_POINT) { ns = 2; PXF_SUMS_GO(PXF_SUMS_POINT); }
     else {
         set_error("pxf_sums: bad mode");
         return PXF_ERR_INVALID;
@@ -1229,6 +1237,25 @@ int pxf_rmscentroid(const double *x, const double *y, const double *w, int64_t n
     k_centroid_from_sums<<<1, 1, 0, s>>>(out, cxy);
     count_launch();
     if ((rc = sums_launch(PXF_SUMS_RMS, x, y, nullptr, nullptr, nullptr, w, num, 0., 0., cxy, out, sc.p, s)))
+        return rc;
+    double h[2];
+    PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    *rms_host = sqrt(h[1] / h[0]);
+    return PXF_OK;
+}
+
+int pxf_rmspoint(const double *x, const double *y, const double *z, const double *w, int64_t num,
+                 double px, double py, double pz, double *rms_host, pxf_stream_t stream)
+{
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = need_device();
+    if (rc) return rc;
+    if (!rms_host) { set_error("pxf_rmspoint: null result"); return PXF_ERR_INVALID; }
+    Scratch sc;
+    if ((rc = sc.alloc(pxf_sums_scratch_bytes() + 16 * sizeof(double), s))) return rc;
+    double *out = reinterpret_cast<double *>((char *)sc.p + pxf_sums_scratch_bytes());
+    if ((rc = sums_launch(PXF_SUMS_POINT, x, y, nullptr, nullptr, nullptr, w, num, px, py, nullptr, out, sc.p, s, z, pz)))
         return rc;
     double h[2];
     PXF_CUDA(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s));

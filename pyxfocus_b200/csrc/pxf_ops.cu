@@ -188,6 +188,64 @@ struct OpGrat {
         op_grat(r, p.d, order, wave);
     }
 };
+// transformations.pointTo (transformations.py:91-100): direction cosines toward (reverse=-1) or away from a point
+struct PointToP { double x0, y0, z0, reverse; };
+struct OpPointTo {
+    using Params = PointToP;
+    static constexpr unsigned LOAD = R_POS, STORE = R_DIR;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        const double dx = r.x - p.x0, dy = r.y - p.y0, dz = r.z - p.z0;
+        const double R = sqrt(dx * dx + dy * dy + dz * dz);
+        r.l = p.reverse * dx / R;
+        r.m = p.reverse * dy / R;
+        r.n = p.reverse * dz / R;
+    }
+};
+// transformations.applyT (transformations.py:257-280): positions through the 4x4 point matrix, direction cosines and
+// normals through the 4x4 rotation matrix (the homogeneous coordinate is 1 for all three, as in the reference)
+struct ApplyTP { double P[12], R[12]; };
+struct OpApplyT {
+    using Params = ApplyTP;
+    static constexpr unsigned LOAD = R_NINE, STORE = R_NINE;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void mul(const double *M, double &a, double &b, double &c)
+    {
+        const double u = M[0] * a + M[1] * b + M[2] * c + M[3];
+        const double v = M[4] * a + M[5] * b + M[6] * c + M[7];
+        const double w = M[8] * a + M[9] * b + M[10] * c + M[11];
+        a = u; b = v; c = w;
+    }
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        mul(p.P, r.x, r.y, r.z);
+        mul(p.R, r.l, r.m, r.n);
+        mul(p.R, r.ux, r.uy, r.uz);
+    }
+};
+// analyses.indAngle (analyses.py:164-182): arccos(l*ux + m*uy + n*uz), or arccos(normal . (l,m,n)) for a fixed
+// normal; the angle is written to the row passed in the opd slot
+struct IndAngleP { double nx, ny, nz; int fixed; };
+struct OpIndAngle {
+    using Params = IndAngleP;
+    static constexpr unsigned LOAD = R_DIR | R_NRM, STORE = R_OPD;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        const double d = p.fixed ? p.nx * r.l + p.ny * r.m + p.nz * r.n : r.l * r.ux + r.m * r.uy + r.n * r.uz;
+        r.opd = acos(d);
+    }
+};
+struct OpIndAngleFixed {
+    using Params = IndAngleP;
+    static constexpr unsigned LOAD = R_DIR, STORE = R_OPD;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        r.opd = acos(p.nx * r.l + p.ny * r.m + p.nz * r.n);
+    }
+};
 struct FlatP { double nr; };
 struct OpFlat {
     using Params = FlatP;
@@ -599,6 +657,39 @@ int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double 
     p.ratio = n1 / n2;
     return launch_op<OpRefract>(rows9(nullptr, nullptr, nullptr, l, m, n, ux, uy, uz), num, mask, nullptr,
                                 nullptr, p, stream);
+}
+
+int pxf_pointto(const double *x, const double *y, const double *z, double *l, double *m, double *n, int64_t num,
+                double x0, double y0, double z0, double reverse, const uint8_t *mask, pxf_stream_t stream)
+{
+    PointToP p{x0, y0, z0, reverse};
+    return launch_op<OpPointTo>(rows9(const_cast<double *>(x), const_cast<double *>(y), const_cast<double *>(z), l, m, n,
+                                      nullptr, nullptr, nullptr), num, mask, nullptr, nullptr, p, stream);
+}
+
+int pxf_applyt(double *x, double *y, double *z, double *l, double *m, double *n, double *ux, double *uy, double *uz,
+               int64_t num, const double *point_matrix, const double *rotation_matrix, pxf_stream_t stream)
+{
+    if (!point_matrix || !rotation_matrix) { set_error("pxf_applyt: null matrix"); return PXF_ERR_INVALID; }
+    ApplyTP p;
+    for (int k = 0; k < 12; k++) { p.P[k] = point_matrix[k]; p.R[k] = rotation_matrix[k]; }
+    return launch_op<OpApplyT>(rows9(x, y, z, l, m, n, ux, uy, uz), num, nullptr, nullptr, nullptr, p, stream);
+}
+
+int pxf_indangle(const double *l, const double *m, const double *n, const double *ux, const double *uy, const double *uz,
+                 double *ang, int64_t num, const double *normal, const uint8_t *mask, pxf_stream_t stream)
+{
+    IndAngleP p{0., 0., 0., normal ? 1 : 0};
+    if (normal) {
+        p.nx = normal[0]; p.ny = normal[1]; p.nz = normal[2];
+        return launch_op<OpIndAngleFixed>(rows9(nullptr, nullptr, nullptr, const_cast<double *>(l), const_cast<double *>(m),
+                                                const_cast<double *>(n), nullptr, nullptr, nullptr, ang),
+                                          num, mask, nullptr, nullptr, p, stream);
+    }
+    return launch_op<OpIndAngle>(rows9(nullptr, nullptr, nullptr, const_cast<double *>(l), const_cast<double *>(m),
+                                       const_cast<double *>(n), const_cast<double *>(ux), const_cast<double *>(uy),
+                                       const_cast<double *>(uz), ang),
+                                 num, mask, nullptr, nullptr, p, stream);
 }
 
 int pxf_radgrat(const double *x, const double *y, double *l, double *m, double *n, double wave,

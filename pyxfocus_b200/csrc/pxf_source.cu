@@ -127,6 +127,188 @@ k_source_seg(const RowPtrs P, int64_t num, int64_t first, unsigned long long see
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The set-up sources (sources.py:173-471).  Grid sources (xslit, rectArray, fanBeam, circFan) are functions of
+// the ray index alone; beam sources (convergingbeam, convergingbeam2, rectbeam, gaussianBeam) take two or three
+// draws per ray, either uploaded (numpy's stream, in the reference's order of draws) or from Philox blocks
+// (counter word 2 = block number).  Every expression keeps the reference's order of operations (no contraction:
+// the library is built with -fmad=false).
+struct Lin { double start, stop, step, delta, div; long long n; int step_zero; };
+
+// numpy.linspace(start, stop, n)[i]: i*step + start with step = (stop-start)/(n-1), the last point pinned to stop;
+// when the step underflows to zero numpy divides first ((i/div)*delta + start); n == 1 gives start.
+PXF_DEV double lin_at(const Lin &q, long long i)
+{
+    if (q.n > 1 && i == q.n - 1) return q.stop;
+    const double t = (double)i;
+    if (q.n <= 1) return t * q.delta + q.start;
+    if (q.step_zero) return (t / q.div) * q.delta + q.start;
+    return t * q.step + q.start;
+}
+
+struct GridP { int kind; Lin u, v; long long nu; double zhat; };
+
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_source_grid(const RowPtrs P, int64_t num, int64_t first, const GridP p)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < num; i += nthr) {
+        const long long g = first + i;
+        double x = 0., y = 0., l = 0., m = 0., n;
+        if (p.kind == PXF_SRC_XSLIT) {                 // sources.py:173-207
+            x = lin_at(p.u, g);
+            n = p.zhat;
+        } else {
+            // np.meshgrid(u, v) flattened row-major: column index runs fastest
+            const long long c = g % p.nu, r = g / p.nu;
+            const double a = lin_at(p.u, c), b = lin_at(p.v, r);
+            if (p.kind == PXF_SRC_RECTARRAY) {         // sources.py:210-247
+                x = a; y = b; n = 1.;
+            } else {
+                double xa = a, ya = b;
+                if (p.kind == PXF_SRC_CIRCFAN) {       // sources.py:444-471: a = ring radius, b = arm azimuth
+                    double sb, cb;
+                    sincos(b, &sb, &cb);
+                    const double sa = sin(a);
+                    xa = sa * cb; ya = sa * sb;
+                }
+                l = sin(xa); m = sin(ya);              // sources.py:418-442 (fanBeam) and the tail of circFan
+                n = sqrt(1. - l * l - m * m);
+            }
+        }
+        if (P.p[0]) P.p[0][i] = 0.;
+        P.p[1][i] = x; P.p[2][i] = y; P.p[3][i] = 0.;
+        P.p[4][i] = l; P.p[5][i] = m; P.p[6][i] = n;
+        P.p[7][i] = 0.; P.p[8][i] = 0.; P.p[9][i] = 0.;
+    }
+}
+
+// a..f: the source's scalars, partly folded on the host (see beam_params)
+struct BeamP { int kind; double a, b, c, d, e, f, g; double pi; };
+
+PXF_DEV void make_beam_ray(Ray &r, const BeamP &p, double d1, double d2, double d3)
+{
+    r.opd = 0.; r.x = 0.; r.y = 0.; r.z = 0.; r.l = 0.; r.m = 0.; r.n = 0.; r.ux = 0.; r.uy = 0.; r.uz = 0.;
+    if (p.kind == PXF_SRC_RECTBEAM) {                  // sources.py:348-379: (rand-.5)*2*halfwidth
+        r.x = (d1 - .5) * 2 * p.a;
+        r.y = (d2 - .5) * 2 * p.b;
+        r.n = 1.;
+        return;
+    }
+    if (p.kind == PXF_SRC_GAUSSIAN) {                  // sources.py:381-416: randn*sin(ang)/sqrt(2)
+        r.l = d1 * p.a / p.b;
+        r.m = d2 * p.a / p.b;
+        r.n = sqrt(1. - r.l * r.l - r.m * r.m);
+        return;
+    }
+    double rho, theta, s, c;
+    if (p.kind == PXF_SRC_CONVERGING) {                // sources.py:250-296: a=zset b=rin^2 c=rout^2-rin^2 d=tmin e=tmax-tmin
+        rho = sqrt(p.b + d1 * p.c);
+        theta = p.d + d2 * p.e;
+        sincos(theta, &s, &c);
+        r.x = rho * c; r.y = rho * s;
+    } else {                                           // sources.py:299-345: b=xmin c=xmax-xmin d=ymin e=ymax-ymin
+        r.x = p.b + d1 * p.c;
+        r.y = p.d + d2 * p.e;
+        rho = sqrt(r.x * r.x + r.y * r.y);
+        theta = atan2(r.y, r.x);
+        sincos(theta, &s, &c);
+    }
+    r.z = p.a;
+    double ls = p.f * tan((d3 - .5) * p.pi);           // f = lscat
+    ls = ls / p.g * p.pi / 180.;                       // g = 60**2
+    r.n = -cos(atan(rho / p.a) + ls);
+    const double t = sqrt(1. - r.n * r.n);
+    r.l = -t * c;
+    r.m = -t * s;
+}
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(PXF_BLOCK)
+k_source_beam(const RowPtrs P, int64_t num, int64_t first, unsigned long long seed,
+              const double *__restrict__ d1, const double *__restrict__ d2, const double *__restrict__ d3,
+              const BeamP p)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const bool three = p.kind == PXF_SRC_CONVERGING || p.kind == PXF_SRC_CONVERGING2;
+    for (int64_t i = tid; i < num; i += nthr) {
+        double a, b, c = 0.;
+        if (PHILOX) {
+            const unsigned long long g = (unsigned long long)(first + i);
+            u32x4 o = philox4x32_10((unsigned)g, (unsigned)(g >> 32), 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32));
+            a = u53(o.a, o.b);
+            b = u53(o.c, o.d);
+            if (three) {
+                o = philox4x32_10((unsigned)g, (unsigned)(g >> 32), 1u, 0u, (unsigned)seed, (unsigned)(seed >> 32));
+                c = u53(o.a, o.b);
+            }
+            if (p.kind == PXF_SRC_GAUSSIAN) {
+                // Box-Muller on (1-a, b): a is in [0,1), so the logarithm's argument is in (0,1]
+                const double rad = sqrt(-2. * log(1. - a));
+                double sn, cs;
+                sincospi(2. * b, &sn, &cs);
+                a = rad * cs; b = rad * sn;
+            }
+        } else {
+            a = d1[i]; b = d2[i];
+            if (three) c = d3[i];
+        }
+        Ray r;
+        make_beam_ray(r, p, a, b, c);
+        if (P.p[0]) P.p[0][i] = r.opd;
+        P.p[1][i] = r.x; P.p[2][i] = r.y; P.p[3][i] = r.z;
+        P.p[4][i] = r.l; P.p[5][i] = r.m; P.p[6][i] = r.n;
+        P.p[7][i] = r.ux; P.p[8][i] = r.uy; P.p[9][i] = r.uz;
+    }
+}
+
+static Lin make_lin(double start, double stop, long long n)
+{
+    // numpy/_core/function_base.py linspace: div = n-1; delta = stop-start; step = delta/div
+    Lin q;
+    q.start = start; q.stop = stop; q.n = n;
+    q.div = (double)(n - 1);
+    q.delta = stop - start;
+    q.step = n > 1 ? q.delta / q.div : 0.;
+    q.step_zero = n > 1 && q.step == 0.;
+    return q;
+}
+
+static int rows_ok(RowPtrs &P, double *const rays[10], const char *who)
+{
+    if (!rays) { set_error("%s: null bundle", who); return PXF_ERR_INVALID; }
+    for (int k = 0; k < 10; k++) {
+        P.p[k] = rays[k];
+        if (k > 0 && !rays[k]) { set_error("%s: null row", who); return PXF_ERR_INVALID; }
+    }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    return PXF_OK;
+}
+
+static int beam_params(BeamP &p, int kind, const double *par)
+{
+    if (!par) return -1;
+    p.kind = kind; p.pi = 3.141592653589793;
+    p.a = p.b = p.c = p.d = p.e = p.f = 0.; p.g = 3600.;       // 60**2
+    switch (kind) {
+    case PXF_SRC_CONVERGING:    // (zset, rin, rout, tmin, tmax, lscat)
+        p.a = par[0]; p.b = par[1] * par[1]; p.c = par[2] * par[2] - p.b; p.d = par[3]; p.e = par[4] - par[3]; p.f = par[5];
+        return 0;
+    case PXF_SRC_CONVERGING2:   // (zset, xmin, xmax, ymin, ymax, lscat)
+        p.a = par[0]; p.b = par[1]; p.c = par[2] - par[1]; p.d = par[3]; p.e = par[4] - par[3]; p.f = par[5];
+        return 0;
+    case PXF_SRC_RECTBEAM:      // (xhalfwidth, yhalfwidth)
+        p.a = par[0]; p.b = par[1];
+        return 0;
+    case PXF_SRC_GAUSSIAN:      // (ang): np.sin(ang), np.sqrt(2)
+        p.a = sin(par[0]); p.b = sqrt(2.);
+        return 0;
+    }
+    return -1;
+}
+
 static int source_launch(int kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
                          const double *u1, const double *u2, bool philox, double a, double b, double c, double d,
                          cudaStream_t s)
@@ -189,6 +371,71 @@ int pxf_source_from_uniform(int32_t kind, double *const rays[10], int64_t num, c
                             const double *u2, double a, double b, double c, double d, pxf_stream_t stream)
 {
     return source_launch(kind, rays, num, 0, 0, u1, u2, false, a, b, c, d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pxf_source_grid(int32_t kind, double *const rays[10], int64_t num, int64_t first, int64_t n1, int64_t n2,
+                    double a, double b, double c, pxf_stream_t stream)
+{
+    RowPtrs P;
+    int rc = rows_ok(P, rays, "pxf_source_grid");
+    if (rc != PXF_OK) return rc;
+    GridP p;
+    p.kind = kind; p.zhat = c; p.nu = n1 > 0 ? n1 : 1;
+    int64_t total;
+    switch (kind) {
+    case PXF_SRC_XSLIT:     p.u = make_lin(a, b, n1); p.v = p.u; total = n1; break;
+    case PXF_SRC_RECTARRAY:
+    case PXF_SRC_FANBEAM:   p.u = make_lin(-a, a, n1); p.v = make_lin(-b, b, n1); total = n1 * n1; break;
+    case PXF_SRC_CIRCFAN: {
+        // rad = linspace(0, halfang, rings); az = linspace(0, 2*np.pi, arms+1)[:-1] (the pinned endpoint is dropped)
+        p.u = make_lin(0., a, n1);
+        p.v = make_lin(0., 2 * 3.141592653589793, n2 + 1);   // arm r < arms never is the pinned last point
+        total = n1 * n2;
+        break;
+    }
+    default: set_error("pxf_source_grid: bad kind %d", kind); return PXF_ERR_INVALID;
+    }
+    if (n1 < 0 || n2 < 0 || num < 0 || first < 0 || first + num > total) {
+        set_error("pxf_source_grid: rays [%lld, %lld) are not inside the %lld-ray source", (long long)first,
+                  (long long)(first + num), (long long)total);
+        return PXF_ERR_INVALID;
+    }
+    if (num == 0) return PXF_OK;
+    k_source_grid<<<grid_for(num, PXF_BLOCK, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, num, first, p);
+    count_launch();
+    return check_launch("k_source_grid");
+}
+
+int pxf_source_beam(int32_t kind, double *const rays[10], int64_t num, int64_t first, uint64_t seed,
+                    const double *par, pxf_stream_t stream)
+{
+    RowPtrs P;
+    int rc = rows_ok(P, rays, "pxf_source_beam");
+    if (rc != PXF_OK) return rc;
+    BeamP p;
+    if (num < 0 || beam_params(p, kind, par) < 0) { set_error("pxf_source_beam: bad argument"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    k_source_beam<true><<<grid_for(num, PXF_BLOCK, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        P, num, first, seed, nullptr, nullptr, nullptr, p);
+    count_launch();
+    return check_launch("k_source_beam");
+}
+
+int pxf_source_beam_from_draws(int32_t kind, double *const rays[10], int64_t num, const double *d1, const double *d2,
+                               const double *d3, const double *par, pxf_stream_t stream)
+{
+    RowPtrs P;
+    int rc = rows_ok(P, rays, "pxf_source_beam_from_draws");
+    if (rc != PXF_OK) return rc;
+    BeamP p;
+    if (num < 0 || beam_params(p, kind, par) < 0) { set_error("pxf_source_beam_from_draws: bad argument"); return PXF_ERR_INVALID; }
+    const bool three = kind == PXF_SRC_CONVERGING || kind == PXF_SRC_CONVERGING2;
+    if (num > 0 && (!d1 || !d2 || (three && !d3))) { set_error("pxf_source_beam_from_draws: null draws"); return PXF_ERR_INVALID; }
+    if (num == 0) return PXF_OK;
+    k_source_beam<false><<<grid_for(num, PXF_BLOCK, 8), PXF_BLOCK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        P, num, 0, 0, d1, d2, d3, p);
+    count_launch();
+    return check_launch("k_source_beam");
 }
 
 }  // extern "C"

@@ -12,9 +12,9 @@ CUDA kernel.  ``rng='philox'`` draws on the device (counter-based Philox4x32-10 
 
 The remaining sources of the reference (``xslit``, ``rectArray``, ``convergingbeam``,
 ``convergingbeam2``, ``rectbeam``, ``gaussianBeam``, ``fanBeam``, ``circFan``; sources.py:173-471)
-are set-up helpers, not part of the trace path: they evaluate the reference's numpy formulas on the
-host -- same expressions, same order of draws from numpy's global stream -- and upload the bundle
-once (``from_numpy``).
+are device kernels too (``pxf_source_grid`` / ``pxf_source_beam``): the grid sources restate
+``numpy.linspace`` / ``meshgrid`` index arithmetic, the beam sources take their draws either from
+numpy's global stream (uploaded, in the reference's order of draws) or from Philox.
 """
 import ctypes
 
@@ -140,111 +140,102 @@ def to_numpy(rays):
     return [r.detach().cpu().numpy() for r in rays]
 
 
-# ---- remaining reference sources: host numpy formulas, one upload -------------------------------
-def _uploaded(fn):
-    """``fn`` builds the reference-style bundle (ten numpy arrays) on the host; the public function
-    uploads it.  ``<source>.host(...)`` is the host half alone (what the CPU tests compare with the
-    reference)."""
-    def wrapper(*args, device=None, **kwargs):
-        return from_numpy(fn(*args, **kwargs), device=device)
-    wrapper.host = fn
-    wrapper.__name__ = fn.__name__
-    wrapper.__doc__ = fn.__doc__
-    return wrapper
+# ---- the reference's set-up sources (sources.py:173-471), generated on the device --------------------
+_XSLIT, _RECTARRAY, _CONVERGING, _CONVERGING2, _RECTBEAM, _GAUSSIAN, _FANBEAM, _CIRCFAN = 4, 5, 6, 7, 8, 9, 10, 11
 
 
-def _bundle(opd, x, y, z, l, m, n, ux, uy, uz):
-    return [np.array(a, dtype=np.float64) for a in (opd, x, y, z, l, m, n, ux, uy, uz)]
+def _grid(kind, total, n1, n2, a, b, c, first, num, device, out):
+    total = int(total)
+    first = int(first)
+    num = total - first if num is None else int(num)
+    if out is not None:
+        rays, dev = out, out[1].device
+        if rays[1].shape[0] != num:
+            raise ValueError("out has %d rays, the source (shard) has %d" % (rays[1].shape[0], num))
+    else:
+        dev = _device(device)
+        rays = bundle_alloc(num, dev)
+    ptrs = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pxf_source_grid(kind, ptrs, num, first, int(n1), int(n2), float(a), float(b), float(c),
+                                              stream_ptr(dev)))
+    return rays
 
 
-@_uploaded
-def xslit(xin, xout, num, zhat=-1.):
-    """Slit of rays linearly spaced in x (sources.py:173-207)."""
-    x = np.linspace(xin, xout, num)
-    zero = np.repeat(0., num)
-    return _bundle(zero, x, zero, zero, zero, zero, np.repeat(zhat, num), zero, zero, zero)
+def _beam(kind, num, par, ndraw, rng, seed, first, device, draws, out, normal=False):
+    num = int(num)
+    if out is not None:
+        rays, dev = out, out[1].device
+        if rays[1].shape[0] != num:
+            raise ValueError("out has %d rays, asked for %d" % (rays[1].shape[0], num))
+    else:
+        dev = _device(device)
+        rays = bundle_alloc(num, dev)
+    ptrs = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
+    cpar = (ctypes.c_double * 6)(*([float(v) for v in par] + [0.] * (6 - len(par))))
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        if rng == "philox":
+            rc = L.pxf_source_beam(kind, ptrs, num, int(first), int(seed) & (2 ** 64 - 1), cpar, stream_ptr(dev))
+        elif rng == "numpy":
+            if draws is None:
+                # numpy's global legacy stream, one vector per draw in the reference's order
+                draws = [(np.random.randn if normal else np.random.rand)(num) for _ in range(ndraw)]
+            if len(draws) != ndraw:
+                raise ValueError("this source takes %d draw vectors" % ndraw)
+            t = [torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64)).to(dev) for d in draws]
+            for d in t:
+                if d.shape[0] != num:
+                    raise ValueError("draw vectors must have num elements")
+            rc = L.pxf_source_beam_from_draws(kind, ptrs, num, t[0].data_ptr(), t[1].data_ptr(),
+                                              t[2].data_ptr() if ndraw > 2 else None, cpar, stream_ptr(dev))
+            torch.cuda.current_stream(dev).synchronize()   # the uploaded draws are freed on return
+        else:
+            raise ValueError("rng must be 'numpy' or 'philox'")
+    _lib.check(rc)
+    return rays
 
 
-@_uploaded
-def rectArray(xsize, ysize, num):
+def xslit(xin, xout, num, zhat=-1., first=0, count=None, device=None, out=None):
+    """Slit of rays linearly spaced in x (sources.py:173-207).  ``first``/``count`` generate a shard."""
+    return _grid(_XSLIT, num, num, 0, xin, xout, zhat, first, count, device, out)
+
+
+def rectArray(xsize, ysize, num, first=0, count=None, device=None, out=None):
     """num x num rectangular grid of rays in +z (sources.py:210-247)."""
-    x, y = np.meshgrid(np.linspace(-xsize, xsize, num), np.linspace(-ysize, ysize, num))
-    zero = np.repeat(0., num ** 2)
-    return _bundle(zero, x.flatten(), y.flatten(), zero, zero, zero, np.repeat(1., num ** 2), zero, zero, zero)
+    return _grid(_RECTARRAY, int(num) ** 2, num, 0, xsize, ysize, 0., first, count, device, out)
 
 
-def _converging(x, y, rho, theta, zset, num, lscat):
-    z = np.repeat(zset, num)
-    lscat = lscat * np.tan((np.random.rand(num) - .5) * np.pi)
-    lscat = lscat / 60 ** 2 * np.pi / 180.
-    n = -np.cos(np.arctan(rho / zset) + lscat)
-    l = -np.sqrt(1 - n ** 2) * np.cos(theta)
-    m = -np.sqrt(1 - n ** 2) * np.sin(theta)
-    zero = np.repeat(0., num)
-    return _bundle(zero, x, y, z, l, m, n, zero, zero, zero)
+def convergingbeam(zset, rin, rout, tmin, tmax, num, lscat, rng="numpy", seed=0, first=0, device=None, draws=None,
+                   out=None):
+    """Converging sub-apertured annulus beam placed at its nominal focus (sources.py:250-296).  With
+    ``rng='numpy'`` the three uniform vectors (radius, angle, scatter) come from numpy's global stream in the
+    reference's order -- or from ``draws`` -- and the geometry is evaluated on the device."""
+    return _beam(_CONVERGING, num, (zset, rin, rout, tmin, tmax, lscat), 3, rng, seed, first, device, draws, out)
 
 
-@_uploaded
-def convergingbeam(zset, rin, rout, tmin, tmax, num, lscat):
-    """Converging sub-apertured annulus beam placed at its nominal focus (sources.py:250-296)."""
-    rho = np.sqrt(rin ** 2 + np.random.rand(num) * (rout ** 2 - rin ** 2))
-    theta = tmin + np.random.rand(num) * (tmax - tmin)
-    x = rho * np.cos(theta)
-    y = rho * np.sin(theta)
-    return _converging(x, y, rho, theta, zset, num, lscat)
+def convergingbeam2(zset, xmin, xmax, ymin, ymax, num, lscat, rng="numpy", seed=0, first=0, device=None,
+                    draws=None, out=None):
+    """Converging rectangular beam placed at its nominal focus (sources.py:299-345); draws: x, y, scatter."""
+    return _beam(_CONVERGING2, num, (zset, xmin, xmax, ymin, ymax, lscat), 3, rng, seed, first, device, draws, out)
 
 
-@_uploaded
-def convergingbeam2(zset, xmin, xmax, ymin, ymax, num, lscat):
-    """Converging rectangular beam placed at its nominal focus (sources.py:299-345)."""
-    x = xmin + np.random.rand(num) * (xmax - xmin)
-    y = ymin + np.random.rand(num) * (ymax - ymin)
-    rho = np.sqrt(x ** 2 + y ** 2)
-    theta = np.arctan2(y, x)
-    return _converging(x, y, rho, theta, zset, num, lscat)
+def rectbeam(xhalfwidth, yhalfwidth, num, rng="numpy", seed=0, first=0, device=None, draws=None, out=None):
+    """Uniform rectangular beam in +z (sources.py:348-379); draws: x, y."""
+    return _beam(_RECTBEAM, num, (xhalfwidth, yhalfwidth), 2, rng, seed, first, device, draws, out)
 
 
-@_uploaded
-def rectbeam(xhalfwidth, yhalfwidth, num):
-    """Uniform rectangular beam in +z (sources.py:348-379)."""
-    x = (np.random.rand(num) - .5) * 2 * xhalfwidth
-    y = (np.random.rand(num) - .5) * 2 * yhalfwidth
-    zero = np.repeat(0., num)
-    return _bundle(zero, x, y, zero, zero, zero, np.repeat(1., num), zero, zero, zero)
+def gaussianBeam(ang, num, rng="numpy", seed=0, first=0, device=None, draws=None, out=None):
+    """Point source with a Gaussian angular profile (sources.py:381-416); draws: two standard-normal vectors
+    (``np.random.randn`` on the host, a Box-Muller pair per ray with ``rng='philox'``)."""
+    return _beam(_GAUSSIAN, num, (ang,), 2, rng, seed, first, device, draws, out, normal=True)
 
 
-@_uploaded
-def gaussianBeam(ang, num):
-    """Point source with a Gaussian angular profile (sources.py:381-416)."""
-    l = np.random.randn(num) * np.sin(ang) / np.sqrt(2)
-    m = np.random.randn(num) * np.sin(ang) / np.sqrt(2)
-    n = np.sqrt(1. - l ** 2 - m ** 2)
-    zero = np.repeat(0., num)
-    return _bundle(zero, zero, zero, zero, l, m, n, zero, zero, zero)
-
-
-def _fan(xa, ya):
-    num = np.size(xa)
-    l = np.sin(xa)
-    m = np.sin(ya)
-    n = np.sqrt(1. - l ** 2 - m ** 2)
-    zero = np.repeat(0., num)
-    return _bundle(zero, zero, zero, zero, l, m, n, zero, zero, zero)
-
-
-@_uploaded
-def fanBeam(xang, yang, num):
+def fanBeam(xang, yang, num, first=0, count=None, device=None, out=None):
     """Rectangular fan of rays from a point (sources.py:418-442)."""
-    xa, ya = np.meshgrid(np.linspace(-xang, xang, num), np.linspace(-yang, yang, num))
-    return _fan(xa.flatten(), ya.flatten())
+    return _grid(_FANBEAM, int(num) ** 2, num, 0, xang, yang, 0., first, count, device, out)
 
 
-@_uploaded
-def circFan(halfang, rings, arms):
+def circFan(halfang, rings, arms, first=0, count=None, device=None, out=None):
     """Circular fan of rays from a point: ``rings`` radii x ``arms`` azimuths (sources.py:444-471)."""
-    rad = np.linspace(0, halfang, rings)
-    az = np.linspace(0, 2 * np.pi, arms + 1)[0:-1]
-    rr, aa = np.meshgrid(rad, az)
-    xx = np.sin(rr) * np.cos(aa)
-    yy = np.sin(rr) * np.sin(aa)
-    return _fan(xx.flatten(), yy.flatten())
+    return _grid(_CIRCFAN, int(rings) * int(arms), rings, arms, halfang, 0., 0., first, count, device, out)

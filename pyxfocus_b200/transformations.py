@@ -79,12 +79,13 @@ def itransform(rays, dx, dy, dz, rx, ry, rz, coords=None, ind=None):
 
 
 def pointTo(rays, x0, y0, z0, reverse=-1.):
-    """Point all direction cosines toward (x0,y0,z0) (transformations.py:91-100)."""
+    """Point all direction cosines toward (x0,y0,z0) (transformations.py:91-100); one pxf_pointto launch."""
     flush(rays)
-    R = torch.sqrt((rays[1] - x0) ** 2 + (rays[2] - y0) ** 2 + (rays[3] - z0) ** 2)
-    rays[4].copy_(reverse * (rays[1] - x0) / R)
-    rays[5].copy_(reverse * (rays[2] - y0) / R)
-    rays[6].copy_(reverse * (rays[3] - z0) / R)
+    x, y, z, l, m, n = rays[1:7]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_pointto(x.data_ptr(), y.data_ptr(), z.data_ptr(), l.data_ptr(), m.data_ptr(),
+                                          n.data_ptr(), x.shape[0], float(x0), float(y0), float(z0), float(reverse),
+                                          None, stream_ptr(x.device)))
     return
 
 
@@ -147,37 +148,57 @@ def grat(rays, d, order, wave, ind=None):
     return
 
 
+def take(rows, ind):
+    """``[r[ind] for r in rows]`` for equally long float64 device rows: a bool mask is an order-preserving
+    compaction, an index array (or ``np.where`` tuple) a gather that may repeat / reorder like numpy fancy
+    indexing.  One library pass over all rows."""
+    rows = list(rows)
+    dev = rows[0].device
+    num = rows[0].shape[0]
+    nr = len(rows)
+    L = _lib.lib()
+    s = stream_ptr(dev)
+    if _is_mask(ind, num):
+        with torch.cuda.device(dev):
+            flags = to_mask(ind, num, dev)
+            scratch = torch.empty(int(L.pxf_compact_scratch_bytes(num)), dtype=torch.uint8, device=dev)
+            count = ctypes.c_int64(0)
+            _lib.check(L.pxf_compact_count(flags.data_ptr(), num, scratch.data_ptr(), ctypes.byref(count), s))
+            out = bundle_alloc(count.value, dev, nrows=nr)
+            pin = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in rows])
+            pout = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in out])
+            _lib.check(L.pxf_compact_scatter(pin, pout, nr, flags.data_ptr(), num, scratch.data_ptr(), s))
+        return out
+    idx = ind[0] if isinstance(ind, tuple) else ind
+    if not isinstance(idx, torch.Tensor):
+        idx = np.ascontiguousarray(idx)          # (a reversed / strided numpy view cannot be wrapped directly)
+    idx = torch.as_tensor(idx, device=dev).long().contiguous()
+    if idx.numel() and (int(idx.min()) < -num or int(idx.max()) >= num):
+        raise IndexError("index out of bounds for %d rays" % num)
+    idx = torch.where(idx < 0, idx + num, idx)
+    count = idx.shape[0]
+    out = bundle_alloc(count, dev, nrows=nr)
+    pin = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in rows])
+    pout = (ctypes.c_void_p * nr)(*[r.data_ptr() for r in out])
+    tab = torch.empty(256, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pxf_gather_rows(pin, pout, nr, idx.data_ptr(), count, tab.data_ptr(), s))
+    return out
+
+
 def vignette(rays, ind=None):
     """Remove vignetted rays (transformations.py:214-225).  ``ind`` selects the rays to KEEP
     (bool mask / index array / ``np.where`` tuple); default keeps ``l^2+m^2+n^2 > .1``.
     Returns a new bundle; order is preserved."""
     flush(rays)
+    if ind is not None:
+        return take(rays, ind)
     dev = rays[1].device
     num = rays[1].shape[0]
-    L = _lib.lib()
-    s = stream_ptr(dev)
-    if ind is not None and not _is_mask(ind, num):
-        # integer index array: a gather (may repeat / reorder, like numpy fancy indexing)
-        idx = ind[0] if isinstance(ind, tuple) else ind
-        idx = torch.as_tensor(idx, device=dev).long().contiguous()
-        if idx.numel() and (int(idx.min()) < -num or int(idx.max()) >= num):
-            raise IndexError("index out of bounds for %d rays" % num)
-        idx = torch.where(idx < 0, idx + num, idx)
-        count = idx.shape[0]
-        out = bundle_alloc(count, dev)
-        pin = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in rays])
-        pout = (ctypes.c_void_p * 10)(*[r.data_ptr() for r in out])
-        tab = torch.empty(256, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(L.pxf_gather_rows(pin, pout, 10, idx.data_ptr(), count, tab.data_ptr(), s))
-        return out
     with torch.cuda.device(dev):
-        if ind is None:
-            flags = torch.empty(num, dtype=torch.uint8, device=dev)
-            _lib.check(L.pxf_vignette_flags(rays[4].data_ptr(), rays[5].data_ptr(), rays[6].data_ptr(), num,
-                                            flags.data_ptr(), s))
-        else:
-            flags = to_mask(ind, num, dev)
+        flags = torch.empty(num, dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().pxf_vignette_flags(rays[4].data_ptr(), rays[5].data_ptr(), rays[6].data_ptr(), num,
+                                                 flags.data_ptr(), stream_ptr(dev)))
         return compact(rays, flags)
 
 
@@ -271,26 +292,21 @@ def translationM(tx, ty, tz):
 
 def applyT(rays, coords, inverse=False):
     """Apply a transformation matrix to the bundle; rotations only for the direction cosines
-    and normals (transformations.py:257-280).  Returns a new bundle."""
+    and normals (transformations.py:257-280).  Returns a new bundle (one copy + one pxf_applyt launch)."""
     flush(rays)
     i = 2 if inverse is True else 0
     dev = rays[1].device
-    P = torch.as_tensor(np.asarray(coords[i + 1], dtype=np.float64), device=dev)
-    R = torch.as_tensor(np.asarray(coords[i], dtype=np.float64), device=dev)
+    P = np.ascontiguousarray(coords[i + 1], dtype=np.float64)
+    R = np.ascontiguousarray(coords[i], dtype=np.float64)
+    if P.shape != (4, 4) or R.shape != (4, 4):
+        raise ValueError("coords must hold 4x4 matrices")
     num = rays[1].shape[0]
     out = bundle_alloc(num, dev)
-    out[0].copy_(rays[0])
-    on = torch.ones(num, dtype=torch.float64, device=dev)
-    pos = torch.stack([rays[1], rays[2], rays[3], on])
-    wav = torch.stack([rays[4], rays[5], rays[6], on])
-    nrm = torch.stack([rays[7], rays[8], rays[9], on])
-    pos = P @ pos
-    wav = R @ wav
-    nrm = R @ nrm
-    for k in range(3):
-        out[1 + k].copy_(pos[k])
-        out[4 + k].copy_(wav[k])
-        out[7 + k].copy_(nrm[k])
+    for k in range(10):
+        out[k].copy_(rays[k])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pxf_applyt(*[r.data_ptr() for r in out[1:]], num, P.ctypes.data, R.ctypes.data,
+                                         stream_ptr(dev)))
     return out
 
 

@@ -1360,12 +1360,6 @@ def test_remaining_analyses_sources_and_helpers(pxf, golden):
     T.steerY(d3)
     T.steerX(d3)
     assert abs(float(d3[5].mean())) <= 1e-6 and abs(float(d3[4].mean())) <= 1e-6
-    # set-up sources: uploaded host bundles equal the host halves bit for bit
-    np.random.seed(6)
-    a = pxf.sources.convergingbeam(8400., 200., 230., -.1, .3, 1001, 1.5)
-    np.random.seed(6)
-    b = pxf.sources.convergingbeam.host(8400., 200., 230., -.1, .3, 1001, 1.5)
-    assert_bit_equal(to_host(a), b, what="convergingbeam")
     assert to_host(pxf.sources.circFan(.05, 7, 12))[4].size == 84
     pts = T.applyTPos(d3[1], d3[2], d3[3], T.newCoords())
     assert torch_equal(pts[0], d3[1])
@@ -1415,3 +1409,146 @@ def test_bench_scale_properties(pxf):
     assert kept[1].shape[0] == int(flags.sum())
     assert bool((kept[1] > 0).all())
     assert torch.equal(kept[2][:1000], out[2][flags][:1000])
+
+
+# --------------------------------------------------------------------------- set-up sources, helpers
+def test_grid_sources_on_device(pxf):
+    """xslit / rectArray / fanBeam / circFan (sources.py:173-247,418-471) generated by k_source_grid against the numpy
+    restatement: the linspace/meshgrid positions bit for bit, sin/cos-derived cosines to an ulp or two; shards
+    (first/count) concatenate to the whole source."""
+    S = pxf.sources
+    for name, args in (("xslit", (-3., 5., 257, 1.)), ("xslit", (2., 2., 5)), ("xslit", (1., 4., 1)),
+                       ("rectArray", (4., 2.5, 33)), ("rectArray", (1., 1., 1)),
+                       ("fanBeam", (.02, .03, 21)), ("circFan", (.05, 7, 12)), ("circFan", (.3, 1, 5)),
+                       ("circFan", (.1, 64, 101))):
+        want = getattr(pyref, name)(*args)
+        got = to_host(getattr(S, name)(*args))
+        assert got[1].shape == want[1].shape, name
+        assert_bit_equal(got, want, rows=(0, 1, 2, 3, 7, 8, 9), what=name + " opd/x/y/z/normals")
+        if name in ("xslit", "rectArray"):
+            assert_bit_equal(got, want, what=name)
+        else:
+            for k in (4, 5, 6):
+                assert np.max(np.abs(got[k] - want[k])) <= 4e-16, (name, k)
+        total = want[1].size
+        if total > 3:
+            cut = total // 3 + 1
+            a = to_host(getattr(S, name)(*args, first=0, count=cut))
+            b = to_host(getattr(S, name)(*args, first=cut))
+            assert_bit_equal([np.concatenate([p, q]) for p, q in zip(a, b)], got, what=name + " shards")
+    with pytest.raises(pxf.PxfError):
+        S.xslit(0., 1., 10, first=8, count=5)
+
+
+def test_beam_sources_on_device(pxf):
+    """convergingbeam / convergingbeam2 / rectbeam / gaussianBeam (sources.py:250-416): numpy's draws uploaded in the
+    reference's order, geometry by k_source_beam.  rectbeam is pure multiply/subtract: bit for bit.  The converging
+    beams form sqrt(1-n^2) with n within a few 1e-4 of -1, which amplifies the one-ulp differences between the
+    device's and numpy's cos/atan/tan by 1/(1-n^2): l, m agree to 1e-12, positions to an ulp."""
+    S = pxf.sources
+    for name, args, tol in (("rectbeam", (12., 7., 4001), 0.),
+                            ("gaussianBeam", (.01, 4001), 4e-16),
+                            ("convergingbeam", (8400., 200., 230., -.1, .3, 4001, 1.5), 1e-12),
+                            ("convergingbeam2", (8400., -20., 30., 190., 240., 4001, .5), 1e-12)):
+        np.random.seed(13)
+        want = getattr(pyref, name)(*args)
+        np.random.seed(13)
+        got = to_host(getattr(S, name)(*args))
+        if tol == 0.:
+            assert_bit_equal(got, want, what=name)
+            continue
+        for k in range(10):
+            scale = max(1., float(np.max(np.abs(want[k]))))
+            t = 4e-16 * scale if k < 4 else tol
+            assert np.max(np.abs(got[k] - want[k])) <= t, (name, k, np.max(np.abs(got[k] - want[k])))
+    # explicit draws == the global stream
+    np.random.seed(13)
+    d = [np.random.rand(4001) for _ in range(3)]
+    a = to_host(S.convergingbeam(8400., 200., 230., -.1, .3, 4001, 1.5, draws=d))
+    np.random.seed(13)
+    b = to_host(S.convergingbeam(8400., 200., 230., -.1, .3, 4001, 1.5))
+    assert_bit_equal(a, b, what="draws")
+
+
+def test_beam_sources_philox(pxf):
+    """Device draws: shards concatenate to the single-GPU stream, and the distributions are the reference's."""
+    S = pxf.sources
+    N = 200_000
+    for name, args in (("rectbeam", (12., 7.)), ("gaussianBeam", (.01,)),
+                       ("convergingbeam", (8400., 200., 230., -.1, .3)), ("convergingbeam2", (8400., -20., 30., 190., 240.))):
+        tail = (1.5,) if name.startswith("converging") else ()
+        whole = to_host(getattr(S, name)(*args, N, *tail, rng="philox", seed=9))
+        a = to_host(getattr(S, name)(*args, 70_001, *tail, rng="philox", seed=9, first=0))
+        b = to_host(getattr(S, name)(*args, N - 70_001, *tail, rng="philox", seed=9, first=70_001))
+        assert_bit_equal([np.concatenate([p, q]) for p, q in zip(a, b)], whole, what=name + " philox shards")
+        other = to_host(getattr(S, name)(*args, N, *tail, rng="philox", seed=10))
+        assert not np.array_equal(other[1] + other[4], whole[1] + whole[4])
+        opd, x, y, z, l, m, n, ux, uy, uz = whole
+        assert np.all(np.abs(l ** 2 + m ** 2 + n ** 2 - 1.) < 1e-12)
+        if name == "rectbeam":
+            assert x.min() >= -12. and x.max() <= 12. and abs(x.mean()) < .1 and abs(x.std() - 24. / np.sqrt(12.)) < .05
+            assert y.min() >= -7. and y.max() <= 7. and abs(np.corrcoef(x, y)[0, 1]) < .01
+        elif name == "gaussianBeam":
+            sig = np.sin(.01) / np.sqrt(2.)
+            assert abs(l.std() / sig - 1.) < .01 and abs(m.std() / sig - 1.) < .01 and abs(l.mean()) < 1e-4
+            assert abs(np.corrcoef(l, m)[0, 1]) < .01
+            assert abs(np.mean(np.abs(l) < sig) - .6827) < .005            # a normal, not just the right variance
+        elif name == "convergingbeam":
+            r = np.hypot(x, y)
+            assert r.min() >= 200. - 1e-9 and r.max() <= 230. + 1e-9 and np.all(z == 8400.)
+            u = (r ** 2 - 200. ** 2) / (230. ** 2 - 200. ** 2)
+            th = np.arctan2(y, x)
+            assert abs(u.mean() - .5) < .005 and th.min() >= -.1 - 1e-12 and th.max() <= .3 + 1e-12
+            # the rays converge to the origin: footprint at z = 0 is set by the Lorentzian scatter (median |.| = lscat)
+            x0 = x - l / n * z
+            assert np.median(np.abs(np.hypot(x0, y - m / n * z))) < .2
+        else:
+            assert x.min() >= -20. and x.max() <= 30. and y.min() >= 190. and y.max() <= 240.
+
+
+def test_pointto_applyt_indangle_kernels(pxf):
+    """transformations.pointTo (:91-100) bit for bit; applyT (:257-280) against numpy's matrix product;
+    analyses.indAngle (:164-182) with mask / index selections."""
+    A, T = pxf.analyses, pxf.transformations
+    np.random.seed(21)
+    rays = pyref.subannulus(200., 230., .4, 5003, -1.)
+    pyref.transform(rays, 1., -2., 30., .01, -.02, .3)
+    rays[7][:] = np.sin(.1) * np.cos(np.linspace(0, 6, 5003))
+    rays[8][:] = np.sin(.1) * np.sin(np.linspace(0, 6, 5003))
+    rays[9][:] = np.cos(.1)
+    for rev in (-1., 1.):
+        want = copy(rays)
+        R = np.sqrt((want[1] - 3.) ** 2 + (want[2] + 4.) ** 2 + (want[3] - 8000.) ** 2)
+        want[4] = rev * (want[1] - 3.) / R
+        want[5] = rev * (want[2] + 4.) / R
+        want[6] = rev * (want[3] - 8000.) / R
+        dev = to_dev(rays)
+        T.pointTo(dev, 3., -4., 8000., reverse=rev)
+        assert_bit_equal(to_host(dev), want, what="pointTo")
+    coords = T.newCoords()
+    T._update_coords_fwd(coords, 1., 2., 3., .1, .2, .3)
+    T._update_coords_fwd(coords, -5., 0., 100., -.3, .05, 1.)
+    for inv in (False, True):
+        i = 2 if inv else 0
+        on = np.ones(5003)
+        pos = np.dot(coords[i + 1], [rays[1], rays[2], rays[3], on])[:3]
+        wav = np.dot(coords[i], [rays[4], rays[5], rays[6], on])[:3]
+        nrm = np.dot(coords[i], [rays[7], rays[8], rays[9], on])[:3]
+        dev = to_dev(rays)
+        got = to_host(T.applyT(dev, coords, inverse=inv))
+        assert_bit_equal(to_host(dev), rays, what="applyT leaves its input alone")
+        assert np.array_equal(got[0], rays[0])
+        for k in range(3):
+            assert np.max(np.abs(got[1 + k] - pos[k])) <= 1e-12 * max(1., np.max(np.abs(pos[k])))
+            assert np.max(np.abs(got[4 + k] - wav[k])) <= 1e-15 * 4
+            assert np.max(np.abs(got[7 + k] - nrm[k])) <= 1e-15 * 4
+    dev = to_dev(rays)
+    ia = np.arccos(rays[4] * rays[7] + rays[5] * rays[8] + rays[6] * rays[9])
+    mask = rays[1] > 215.
+    idx = np.where(mask)[0][::-3]
+    assert np.allclose(A.indAngle(dev, ind=mask).cpu().numpy(), ia[mask], rtol=0, atol=1e-14)
+    assert np.allclose(A.indAngle(dev, ind=idx).cpu().numpy(), ia[idx], rtol=0, atol=1e-14)
+    assert np.allclose(A.indAngle(dev, ind=np.where(mask)).cpu().numpy(), ia[mask], rtol=0, atol=1e-14)
+    got = A.indAngle(dev, ind=mask, normal=(0., .6, .8)).cpu().numpy()
+    assert np.allclose(got, np.arccos(.6 * rays[5][mask] + .8 * rays[6][mask]), rtol=0, atol=1e-14)
+    assert A.indAngle(dev, ind=np.zeros(5003, dtype=bool)).shape[0] == 0

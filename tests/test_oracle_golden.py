@@ -67,8 +67,7 @@ def test_restatement_matches_live_reference_python():
         np.random.seed(11)
         b = getattr(pyref, name)(*args)
         assert_bit_equal(b, a, what=name)
-    # the set-up sources of the product package evaluate the reference's formulas on the host
-    from pyxfocus_b200 import sources as psrc
+    # the set-up sources (the product generates them on the device; tests/test_gpu_parity.py compares with these)
     for name, args in (("xslit", (-3., 5., 257, 1.)), ("rectArray", (4., 2.5, 33)),
                        ("convergingbeam", (8400., 200., 230., -.1, .3, 4001, 1.5)),
                        ("convergingbeam2", (8400., -20., 30., 190., 240., 4001, .5)),
@@ -77,7 +76,7 @@ def test_restatement_matches_live_reference_python():
         np.random.seed(13)
         a = getattr(src, name)(*args)
         np.random.seed(13)
-        b = getattr(psrc, name).host(*args)
+        b = getattr(pyref, name)(*args)
         assert_bit_equal(b, a, what=name)
     rays = chains.wolter1_source(5001, 12)
     chains.run_steps_cpu(rays, chains.wolter1_steps())
