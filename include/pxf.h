@@ -589,16 +589,18 @@ int pxf_wq_merge_final_probe(const int64_t *keys0, const double *cum0, int64_t n
 int pxf_wq_merge_finish(void *state, const double *sum_dev, const double *offsets_dev, const double *total_dev,
                         double q0, double q1, pxf_stream_t stream);
 
-/* Stable LSD radix sort of fp64 keys (ascending by IEEE total order of non-negative values;
- * negative keys and NaNs are ordered by their raw bit pattern after sign fix-up as in
- * np.sort) with the permutation (np.argsort equivalent, stable).  keys_out / idx_out device
- * arrays of length num.  scratch: pxf_sort_scratch_bytes(num). */
+/* Stable LSD radix sort of fp64 keys with the permutation: np.argsort(keys, kind='stable') and np.sort (analyses.py:76).
+ * Order: -inf < ... < -0 == +0 < ... < +inf < NaN; keys that compare equal (ties, -0/+0, all NaNs) keep their input
+ * order, and the sorted keys carry the original bit patterns.  One-sweep passes (one kernel per non-constant key
+ * byte, decoupled look-back); nothing is read back, the call is asynchronous on `stream`.  keys_out / idx_out:
+ * device arrays of length num (either may be NULL); keys_out must not alias keys_in.
+ * scratch: pxf_sort_scratch_bytes(num). */
 size_t pxf_sort_scratch_bytes(int64_t num);
 int pxf_argsort(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
                 void *scratch, pxf_stream_t stream);
 /* Same, sorting only on the bytes of the 64-bit key whose bit is set in `digits` (bit 0 = least significant
- * byte); 0 = detect the constant bytes with one histogram read-back (what pxf_argsort does).  With a mask
- * nothing is read back: for keys from a known narrow range, or when a partial order is enough. */
+ * byte); 0 = skip the bytes that are constant over the array (decided on the device; what pxf_argsort does).
+ * A mask is for keys from a known narrow range, or when a partial order is enough. */
 int pxf_argsort_digits(const double *keys_in, int64_t num, double *keys_out, int64_t *idx_out,
                        void *scratch, int32_t digits, pxf_stream_t stream);
 /* out[i] = inclusive prefix sum of (w ? w[idx[i]] : 1.0)  (np.cumsum(weights[ind]),

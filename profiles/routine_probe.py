@@ -30,7 +30,7 @@ def main():
     cp(state, src)
     TF.transform(*state[1:], 0., 0., 8400., 0., 0., 0.)            # above the primary
     alpha = pxf.conicsolve.woltparam(220., 8400.)[0]
-    if name in ("refract", "woltersecll"):
+    if name in ("refract", "woltersecll", "woltersecondary"):
         WS.wolterprimary(*state[1:], 220., 8400., 1.)
         TF.reflect(*state[4:])
     if name == "wssecondary":
@@ -58,6 +58,7 @@ def main():
         "radgrat": lambda: TF.radgrat(W[1], W[2], W[4], W[5], W[6], 2.4e-6, 160. / 11832.911, -1.),
         "tracezern": lambda: ZS.tracezern(*W[1:], zc, np.array(ro), np.array(ao), 230.),
         "wolterprimll": lambda: WS.wolterprimll(*W[1:], 220., 8400., 8500., 8400., 2 * np.pi, llc, lla, llz),
+        "woltersecondary": lambda: WS.woltersecondary(*W[1:], 220., 8400., 1.),
         "woltersecll": lambda: WS.woltersecll(*W[1:], 220., 8400., 1., 8400., 8300., 2 * np.pi, llc, lla, llz),
     }
     fn = fns[name]

@@ -437,6 +437,21 @@ template <class Op> struct OpMinB<Op, std::void_t<decltype(Op::MINB)>> { static 
 template <class Op, class = void> struct OpScalar { static constexpr bool v = false; };
 template <class Op> struct OpScalar<Op, std::void_t<decltype(Op::SCALAR)>> { static constexpr bool v = Op::SCALAR; };
 
+// The same routine with another launch shape: registers capped for MINB_ CTAs per SM, one ray per thread if SCALAR_
+template <class Op, int MINB_, bool SCALAR_>
+struct Shaped : Op {
+    static constexpr int MINB = MINB_;
+    static constexpr bool SCALAR = SCALAR_;
+};
+// PXF_OP_VARIANT (tuning, compute-bound per-routine kernels): 0 = two rays per thread, registers uncapped;
+// 1/2/3 = one ray per thread capped for 3/4/5 CTAs per SM; 4 = two rays per thread capped for 2 CTAs per SM
+static int op_variant(int dflt)
+{
+    static int v = -2;
+    if (v == -2) { const char *e = getenv("PXF_OP_VARIANT"); v = e ? atoi(e) : -1; }
+    return v >= 0 ? v : dflt;
+}
+
 template <class Op, bool MASKED, bool VEC2>
 __global__ void __launch_bounds__(PXF_BLOCK, OpMinB<Op>::v)
 k_op(const RowPtrs P, const int64_t num, const uint8_t *__restrict__ mask,
@@ -543,6 +558,19 @@ static int launch_op(RowPtrs P, int64_t num, const uint8_t *mask, const double *
     }
     if (aligned) return launch3<Op, false, true>(P, num, mask, aux0, aux1, prm, s);
     return launch3<Op, false, false>(P, num, mask, aux0, aux1, prm, s);
+}
+
+template <class Op>
+static int launch_shaped(int dflt, RowPtrs P, int64_t num, const uint8_t *mask, const typename Op::Params &prm,
+                         pxf_stream_t stream)
+{
+    switch (op_variant(dflt)) {
+    case 1: return launch_op<Shaped<Op, 3, true>>(P, num, mask, nullptr, nullptr, prm, stream);
+    case 2: return launch_op<Shaped<Op, 4, true>>(P, num, mask, nullptr, nullptr, prm, stream);
+    case 3: return launch_op<Shaped<Op, 5, true>>(P, num, mask, nullptr, nullptr, prm, stream);
+    case 4: return launch_op<Shaped<Op, 2, false>>(P, num, mask, nullptr, nullptr, prm, stream);
+    default: return launch_op<Op>(P, num, mask, nullptr, nullptr, prm, stream);
+    }
 }
 
 static RowPtrs rows9(double *x, double *y, double *z, double *l, double *m, double *n,
@@ -655,8 +683,8 @@ int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double 
 {
     RefractP p;
     p.ratio = n1 / n2;
-    return launch_op<OpRefract>(rows9(nullptr, nullptr, nullptr, l, m, n, ux, uy, uz), num, mask, nullptr,
-                                nullptr, p, stream);
+    // (measured, 5e7 rays, variants 0..4: 1.408 / 1.283 / 1.229 / 1.300 / 1.408 ms, profiles/r02l_op_variants.txt)
+    return launch_shaped<OpRefract>(2, rows9(nullptr, nullptr, nullptr, l, m, n, ux, uy, uz), num, mask, p, stream);
 }
 
 int pxf_pointto(const double *x, const double *y, const double *z, double *l, double *m, double *n, int64_t num,
@@ -695,9 +723,10 @@ int pxf_indangle(const double *l, const double *m, const double *n, const double
 int pxf_radgrat(const double *x, const double *y, double *l, double *m, double *n, double wave,
                 int64_t num, double dpermm, double order, const uint8_t *mask, pxf_stream_t stream)
 {
-    return launch_op<OpRadgrat>(rows9(const_cast<double *>(x), const_cast<double *>(y), nullptr, l, m, n,
-                                      nullptr, nullptr, nullptr),
-                                num, mask, nullptr, nullptr, make_radgrat(wave, dpermm, order), stream);
+    // (measured: 0.654 / 0.693 / 0.694 / 0.676 / 0.653 ms)
+    return launch_shaped<OpRadgrat>(0, rows9(const_cast<double *>(x), const_cast<double *>(y), nullptr, l, m, n,
+                                             nullptr, nullptr, nullptr),
+                                    num, mask, make_radgrat(wave, dpermm, order), stream);
 }
 
 int pxf_radgratw(const double *x, const double *y, double *l, double *m, double *n, const double *wave,
@@ -740,8 +769,8 @@ int pxf_conic(double *x, double *y, double *z, double *l, double *m, double *n,
               double *ux, double *uy, double *uz, int64_t num, double R, double K,
               const uint8_t *mask, pxf_stream_t stream)
 {
-    return launch_op<OpConic>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
-                              make_conic(R, K, false, 0.), stream);
+    // (measured: 1.165 / 1.163 / 1.281 / 1.422 / 1.160 ms)
+    return launch_shaped<OpConic>(0, rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, make_conic(R, K, false, 0.), stream);
 }
 
 int pxf_conicopd(double *opd, double *x, double *y, double *z, double *l, double *m, double *n,
@@ -773,8 +802,9 @@ int pxf_woltersecondary(double *x, double *y, double *z, double *l, double *m, d
                         double *ux, double *uy, double *uz, int64_t num, double r0, double z0, double psi,
                         const uint8_t *mask, pxf_stream_t stream)
 {
-    return launch_op<OpWolterSecondary>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
-                                        make_wolter(r0, z0, psi, false, 0.), stream);
+    // (measured: 0.893 / 0.900 / 0.900 / 0.865 / 0.897 ms)
+    return launch_shaped<OpWolterSecondary>(3, rows9(x, y, z, l, m, n, ux, uy, uz), num, mask,
+                                            make_wolter(r0, z0, psi, false, 0.), stream);
 }
 
 int pxf_woltersine(double *x, double *y, double *z, double *l, double *m, double *n,
@@ -782,8 +812,9 @@ int pxf_woltersine(double *x, double *y, double *z, double *l, double *m, double
                    double r0, double z0, double amp, double freq,
                    const uint8_t *mask, pxf_stream_t stream)
 {
-    return launch_op<OpWolterSine>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
-                                   make_woltersine(r0, z0, amp, freq), stream);
+    // (measured: 1.596 / 1.610 / 1.613 / 1.636 / 1.597 ms -- bound by the two sin/cos evaluations per Newton step)
+    return launch_shaped<OpWolterSine>(0, rows9(x, y, z, l, m, n, ux, uy, uz), num, mask,
+                                       make_woltersine(r0, z0, amp, freq), stream);
 }
 
 int pxf_wsprimary(double *x, double *y, double *z, double *l, double *m, double *n,
@@ -822,8 +853,8 @@ int pxf_spocone(double *x, double *y, double *z, double *l, double *m, double *n
                 double *ux, double *uy, double *uz, int64_t num, double R0, double tg,
                 const uint8_t *mask, pxf_stream_t stream)
 {
-    return launch_op<OpSpoCone>(rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, nullptr, nullptr,
-                                make_spo(R0, tg), stream);
+    // (measured: 1.199 / 1.001 / 1.049 / 1.137 / 1.215 ms)
+    return launch_shaped<OpSpoCone>(1, rows9(x, y, z, l, m, n, ux, uy, uz), num, mask, make_spo(R0, tg), stream);
 }
 
 int pxf_wolterprimll(double *x, double *y, double *z, double *l, double *m, double *n,

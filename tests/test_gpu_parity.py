@@ -1552,3 +1552,30 @@ def test_pointto_applyt_indangle_kernels(pxf):
     got = A.indAngle(dev, ind=mask, normal=(0., .6, .8)).cpu().numpy()
     assert np.allclose(got, np.arccos(.6 * rays[5][mask] + .8 * rays[6][mask]), rtol=0, atol=1e-14)
     assert A.indAngle(dev, ind=np.zeros(5003, dtype=bool)).shape[0] == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 3072, 3073, 100_000, 2_000_003])
+def test_argsort_sizes_and_degenerate_keys(pxf, n):
+    """The one-sweep radix sort (analyses.py:76 argsort): sizes around the tile, all-equal keys (no pass runs), keys
+    that differ in one byte only, heavy ties (stability), negative / signed-zero / inf / NaN keys."""
+    import torch
+    rng = np.random.default_rng(n)
+    cases = {
+        "uniform": rng.uniform(0, 1e-3, n),
+        "equal": np.full(n, 3.25),
+        "one_byte": np.float64(1.) + rng.integers(0, 256, n) * 2. ** -52,
+        "ties": rng.integers(-3, 4, n).astype(np.float64),
+        "mixed": rng.normal(0, 1, n) * 10. ** rng.integers(-300, 300, n),
+    }
+    cases["mixed"][::7] = -0.
+    cases["mixed"][3::11] = 0.
+    cases["mixed"][5::13] = np.inf
+    cases["mixed"][6::17] = -np.inf
+    cases["mixed"][1::19] = np.nan
+    for name, kc in cases.items():
+        ks, idx = pxf.analyses.argsort(torch.from_numpy(kc).cuda())
+        kn, ii = ks.cpu().numpy(), idx.cpu().numpy()
+        want = np.argsort(kc, kind="stable")
+        assert np.array_equal(ii, want), name
+        assert np.array_equal(kn.view(np.int64)[~np.isnan(kn)], kc[want].view(np.int64)[~np.isnan(kc[want])]), name
+        assert np.isnan(kn).sum() == np.isnan(kc).sum(), name
