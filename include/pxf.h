@@ -626,6 +626,26 @@ int pxf_southwellbin(const double *x, const double *y, const double *l, const do
                      double *xang, double *yang, double *phase, int32_t xdim, int32_t ydim, void *scratch,
                      pxf_stream_t stream);
 
+/* ======================= scattered-data interpolation =================== */
+/* scipy.interpolate.griddata((x, y), v, (qx, qy), method) as analyses.interpolateVec / wavefront call it
+ * (analyses.py:189-230, 305-334; scipy is a third-party dependency of the reference).  method 0 = 'nearest', 1 = 'linear'
+ * (barycentric interpolation inside the Delaunay triangle that contains the query; NaN outside the convex hull).  The
+ * triangle is found from the query's own natural neighbours (Voronoi cell clipped over a uniform cell grid), no global
+ * triangulation is built.  All arrays on the device; out[nq].  *nfail_host (may be NULL; reading it synchronises)
+ * receives the number of queries whose cell could not be resolved (degenerate input; they are NaN).
+ * scratch: pxf_griddata_scratch_bytes(num). */
+size_t pxf_griddata_scratch_bytes(int64_t num);
+int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
+                 double *out, int64_t nq, int32_t method, int64_t *nfail_host, void *scratch, pxf_stream_t stream);
+
+/* Helpers of analyses.interpolateVec: the bounding box of the ray positions (xr = [x.min(), x.max()], analyses.py:206-208;
+ * box_host[4] = xmin, xmax, ymin, ymax; scratch: pxf_bbox_scratch_bytes()), the polar coordinates of its polar=True
+ * branch (rho, rho*arctan2(y,x), rho*arctan2(x,y); analyses.py:219-226) and np.nanmedian of two arrays (:227). */
+size_t pxf_bbox_scratch_bytes(void);
+int pxf_bbox(const double *x, const double *y, int64_t num, double *box_host, void *scratch, pxf_stream_t stream);
+int pxf_polar_coords(const double *x, const double *y, int64_t num, double *rho, double *az1, double *az2, pxf_stream_t stream);
+int pxf_nanmedian2(const double *a, const double *b, int64_t num, double *out, pxf_stream_t stream);
+
 /* ======================= sources ======================================== */
 /* Device-side ray generation for bundles too large for host MT19937 (SURVEY 7 "RNG parity").
  * Counter-based Philox4x32-10, key=(seed lo,hi), counter=(global ray index, stream id);

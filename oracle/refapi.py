@@ -216,6 +216,64 @@ def grazeAngle(rays, ind=None):
     return np.pi / 2 - indAngle(rays, ind=ind)
 
 
+def interpolateVec(rays, I, Nx, Ny, xr=None, yr=None, method='linear', polar=False, interpVec=None):
+    """analyses.py:189-230 with scipy's own griddata (the reference's third-party dependency; scipy is present on the
+    GPU box too, so this oracle travels)."""
+    from scipy.interpolate import griddata
+    x, y = rays[1:3]
+    if interpVec is None:
+        interpVec = rays[I]
+    if xr is None:
+        xr = [x.min(), x.max()]
+        yr = [y.min(), y.max()]
+    gridx, gridy = np.meshgrid(np.linspace(xr[0], xr[1], Nx), np.linspace(yr[0], yr[1], Ny))
+    dx = np.diff(gridx)[0][0]
+    dy = np.diff(np.transpose(gridy))[0][0]
+    if polar is True:
+        rho = np.sqrt(x ** 2 + y ** 2)
+        theta1 = np.arctan2(y, x)
+        theta2 = np.arctan2(x, y)
+        rhog = np.sqrt(gridx ** 2 + gridy ** 2)
+        azg1 = rhog * np.arctan2(gridy, gridx)
+        azg2 = rhog * np.arctan2(gridx, gridy)
+        res1 = griddata((rho, theta1 * rho), interpVec, (rhog, azg1), method=method)
+        res2 = griddata((rho, theta2 * rho), interpVec, (rhog, azg2), method=method)
+        with np.errstate(all="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = np.nanmedian([res1, res2], axis=0)
+    else:
+        res = griddata((x, y), interpVec, (gridx, gridy), method=method)
+    return res, dx, dy
+
+
+def wavefront(rays, Nx, Ny, method='cubic', polar=False, maxiter=10000):
+    """analyses.py:305-334.  PARITY UNPINNED at two points the reference itself cannot execute: ``man.padRect`` is in the
+    un-vendored ``utilities.imaging`` package (taken as a one-pixel NaN frame: the function strips ``[1:-1,1:-1]`` at
+    the end) and ``reconstruct.reconstruct`` is called without its required ``maxiter`` (:327)."""
+    y, dx, dy = interpolateVec(rays, 5, Nx, Ny, method=method, polar=polar)
+    x, dx, dy = interpolateVec(rays, 4, Nx, Ny, method=method, polar=polar)
+
+    def padRect(img):
+        out = np.full((img.shape[0] + 2, img.shape[1] + 2), np.nan)
+        out[1:-1, 1:-1] = img
+        return out
+    x = padRect(x)
+    y = padRect(y)
+    phase = np.zeros(np.shape(x), order='F')
+    phase[np.isnan(x)] = 100.
+    x[np.isnan(x)] = 100.
+    y[np.isnan(y)] = 100.
+    y = np.array(y, order='F')
+    x = np.array(x, order='F')
+    phase = _f.reconstruct.reconstruct(y, x, 1e-12, dx, phase, maxiter)
+    phase[phase == 100] = np.nan
+    x[x == 100] = np.nan
+    y[y == 100] = np.nan
+    return phase[1:-1, 1:-1], x[1:-1, 1:-1], y[1:-1, 1:-1]
+
+
 # ------------------------------------------------------------------ conicsolve.py
 def primrad(z, r0, z0, psi=1.):
     """conicsolve.py:7-15"""

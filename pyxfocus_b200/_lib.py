@@ -174,6 +174,13 @@ SIGNATURES = {
     "pxf_reconstruct": (_c.c_int, [_dp, _dp, _i32, _i32, _d, _d, _dp, _dp, _i32, _vp, _st]),
     "pxf_southwellbin_scratch_bytes": (_sz, [_i64, _i32, _i32]),
     "pxf_southwellbin": (_c.c_int, [_dp, _dp, _dp, _dp, _i64, _d, _dp, _dp, _dp, _i32, _i32, _vp, _st]),
+    # scattered-data interpolation
+    "pxf_griddata_scratch_bytes": (_sz, [_i64]),
+    "pxf_bbox_scratch_bytes": (_sz, []),
+    "pxf_bbox": (_c.c_int, [_dp, _dp, _i64, _vp, _vp, _st]),
+    "pxf_polar_coords": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _dp, _st]),
+    "pxf_nanmedian2": (_c.c_int, [_dp, _dp, _i64, _dp, _st]),
+    "pxf_griddata": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _i32, _vp, _vp, _st]),
     # sources
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),
     "pxf_source_segmented": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _i32, _vp, _dp, _st]),

@@ -300,3 +300,108 @@ def indAngle(rays, ind=None, normal=None):
 def grazeAngle(rays, ind=None):
     """Graze angle against the current surface normal (analyses.py:184-187)."""
     return np.pi / 2 - indAngle(rays, ind=ind)
+
+
+# ---- OPD-map pipeline: scattered-data interpolation and wavefront integration (analyses.py:189-230, 305-334) ----
+def griddata(px, py, values, qx, qy, method="linear"):
+    """``scipy.interpolate.griddata((px, py), values, (qx, qy), method)`` for 'nearest' / 'linear' on the device
+    (``pxf_griddata``: the Delaunay triangle of every query point from its natural neighbours; NaN outside the convex
+    hull).  All five arguments are equally long (points) / equally shaped (queries) float64 CUDA tensors."""
+    if method not in ("nearest", "linear"):
+        raise NotImplementedError(
+            "method=%r: only 'nearest' and 'linear' are built ('cubic' is scipy's Clough-Tocher scheme, whose global "
+            "gradient estimate is an iteration to a tolerance inside a third-party library)" % (method,))
+    dev = px.device
+    shape = qx.shape
+    px, py, values = (t.contiguous() for t in (px, py, values))
+    fx, fy = qx.reshape(-1).contiguous(), qy.reshape(-1).contiguous()
+    out = torch.empty_like(fx)
+    L = _lib.lib()
+    nfail = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        scratch = torch.empty(int(L.pxf_griddata_scratch_bytes(px.shape[0])), dtype=torch.uint8, device=dev)
+        _lib.check(L.pxf_griddata(px.data_ptr(), py.data_ptr(), values.data_ptr(), px.shape[0], fx.data_ptr(), fy.data_ptr(),
+                                  out.data_ptr(), fx.shape[0], 1 if method == "linear" else 0, ctypes.byref(nfail),
+                                  scratch.data_ptr(), stream_ptr(dev)))
+    if nfail.value:
+        raise _lib.PxfError("griddata: %d query points have no unique Delaunay triangle (degenerate point set: "
+                            "duplicate, collinear or exactly cocircular points) -- %s"
+                            % (nfail.value, (L.pxf_last_error() or b"").decode()))
+    return out.reshape(shape)
+
+
+def _bbox(x, y):
+    L = _lib.lib()
+    box = (ctypes.c_double * 4)()
+    with torch.cuda.device(x.device):
+        scratch = torch.empty(int(L.pxf_bbox_scratch_bytes()), dtype=torch.uint8, device=x.device)
+        _lib.check(L.pxf_bbox(x.data_ptr(), y.data_ptr(), x.shape[0], box, scratch.data_ptr(), stream_ptr(x.device)))
+    return list(box)
+
+
+def interpolateVec(rays, I, Nx, Ny, xr=None, yr=None, method='linear', polar=False, interpVec=None):
+    """Interpolate ray vector ``I`` (or ``interpVec``) onto an Nx x Ny grid spanning the rays' x/y range
+    (analyses.py:189-230).  Returns ``(res, dx, dy)``; ``res`` is a (Ny, Nx) CUDA tensor."""
+    flush(rays)
+    x, y = rays[1:3]
+    dev = x.device
+    vec = rays[I] if interpVec is None else torch.as_tensor(interpVec, dtype=torch.float64, device=dev)
+    if xr is None:
+        box = _bbox(x, y)
+        xr, yr = box[0:2], box[2:4]
+    gx, gy = np.meshgrid(np.linspace(xr[0], xr[1], Nx), np.linspace(yr[0], yr[1], Ny))
+    dx = np.diff(gx)[0][0]
+    dy = np.diff(np.transpose(gy))[0][0]
+    qx, qy = torch.from_numpy(gx).to(dev), torch.from_numpy(gy).to(dev)
+    if polar is not True:
+        return griddata(x, y, vec, qx, qy, method=method), dx, dy
+    # two polar charts (cut along -x and along -y), then the median of the two maps
+    L = _lib.lib()
+
+    def chart(px, py):
+        flat_x, flat_y = px.reshape(-1).contiguous(), py.reshape(-1).contiguous()
+        rho, a1, a2 = (torch.empty_like(flat_x) for _ in range(3))
+        with torch.cuda.device(dev):
+            _lib.check(L.pxf_polar_coords(flat_x.data_ptr(), flat_y.data_ptr(), flat_x.shape[0], rho.data_ptr(),
+                                          a1.data_ptr(), a2.data_ptr(), stream_ptr(dev)))
+        return rho.reshape(px.shape), a1.reshape(px.shape), a2.reshape(px.shape)
+    rho, t1, t2 = chart(x, y)
+    rhog, g1, g2 = chart(qx, qy)
+    res1 = griddata(rho, t1, vec, rhog, g1, method=method)
+    res2 = griddata(rho, t2, vec, rhog, g2, method=method)
+    res = torch.empty_like(res1)
+    with torch.cuda.device(dev):
+        _lib.check(L.pxf_nanmedian2(res1.data_ptr(), res2.data_ptr(), res1.numel(), res.data_ptr(), stream_ptr(dev)))
+    return res, dx, dy
+
+
+def wavefront(rays, Nx, Ny, method='cubic', polar=False, maxiter=10000):
+    """Interpolate the beam slopes onto a grid and integrate the wavefront (analyses.py:305-334): ``interpolateVec`` of
+    m and l, a one-pixel border, missing data -> 100., Southwell reconstruction (criterion 1e-12, step dx).  Returns
+    ``(phase, x, y)`` without the border, as numpy arrays like the reference (NaN where there is no data).
+
+    As shipped the reference cannot run this function: ``man.padRect`` lives in the un-vendored ``utilities.imaging``
+    package (taken here as a one-pixel NaN frame, which is what the ``[1:-1,1:-1]`` at the end strips), and
+    ``reconstruct.reconstruct`` is called without its required ``maxiter`` (here a keyword, default as in
+    ``southwell.southwell``).  ``method='cubic'`` (the default) needs scipy's Clough-Tocher interpolant and raises
+    ``NotImplementedError``; pass ``method='linear'``."""
+    from . import reconstruct as _rec
+    ys, dx, dy = interpolateVec(rays, 5, Nx, Ny, method=method, polar=polar)
+    xs, dx, dy = interpolateVec(rays, 4, Nx, Ny, method=method, polar=polar)
+
+    def framed(t):
+        a = np.full((t.shape[0] + 2, t.shape[1] + 2), np.nan, order='F')
+        a[1:-1, 1:-1] = t.cpu().numpy()
+        return a
+    xs, ys = framed(xs), framed(ys)
+    hole = np.isnan(xs)
+    phase = np.zeros(xs.shape, order='F')
+    phase[hole] = 100.
+    xs[hole] = 100.
+    ys[np.isnan(ys)] = 100.
+    phase = _rec.reconstruct(ys, xs, 1e-12, dx, phase, maxiter)
+    phase[phase == 100] = np.nan
+    xs[xs == 100] = np.nan
+    ys[ys == 100] = np.nan
+    return phase[1:-1, 1:-1], xs[1:-1, 1:-1], ys[1:-1, 1:-1]
+

@@ -1,0 +1,451 @@
+// Scattered-data interpolation of a per-ray quantity onto query points: analyses.interpolateVec / wavefront
+// (analyses.py:189-230, 305-334), which call scipy.interpolate.griddata (Delaunay triangulation + barycentric
+// interpolation for 'linear', nearest neighbour for 'nearest').  SURVEY.md 8(f) rank 4.
+//
+// No global triangulation is built.  The Delaunay triangle that contains a query point q is the optimum of a
+// three-variable linear programme (the facet of the lifted points' lower hull under q), reached by pivoting, one
+// thread per query, with O(1) state:
+//   1. the points are binned into a uniform cell grid (counting sort by cell through pxf_argsort);
+//   2. a start triangle that contains q: the nearest point of each quadrant about q gives four points whose hull
+//      holds q, and one of their triangles does.  If a quadrant is empty (q near or outside the hull) one pass over
+//      all points finds the extreme directions on both sides of a first point: either they close a triangle
+//      around q, or a half-plane through q holds every point and q is outside the convex hull -> NaN (griddata's
+//      fill value);
+//   3. while some point lies inside the triangle's circumcircle, the deepest such point replaces the vertex that
+//      keeps q inside (q's height on the lifted plane falls monotonically, so this ends); only the cells under the
+//      circumcircle are scanned.  The final triangle contains q and has an empty circumcircle: it is the triangle
+//      of the Delaunay triangulation (unique in general position) that scipy/Qhull interpolates in;
+//   4. barycentric interpolation inside that triangle.
+#include <vector>
+#include "pxf_internal.h"
+#include "pxf_ray.cuh"
+
+namespace pxf {
+
+#define GI_THREADS 128
+#define GI_MAX_PIVOTS 512
+
+struct GridCells {
+    double x0, y0, x1, y1, h, box;   // bounding box, cell size, half-size of the start square (relative to the query)
+    int gx, gy;
+};
+
+// ---------------------------------------------------------------- bounding box (two-stage, deterministic)
+__global__ void __launch_bounds__(256)
+k_bbox_partial(const double *__restrict__ x, const double *__restrict__ y, int64_t num, double *__restrict__ part /*[grid][4]*/)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double xl = inf, xh = -inf, yl = inf, yh = -inf;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y[i];
+        xl = fmin(xl, a); xh = fmax(xh, a); yl = fmin(yl, b); yh = fmax(yh, b);
+    }
+    __shared__ double sh[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xl = fmin(xl, __shfl_down_sync(0xffffffffu, xl, o)); xh = fmax(xh, __shfl_down_sync(0xffffffffu, xh, o));
+        yl = fmin(yl, __shfl_down_sync(0xffffffffu, yl, o)); yh = fmax(yh, __shfl_down_sync(0xffffffffu, yh, o));
+    }
+    if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; sh[0][w] = xl; sh[1][w] = xh; sh[2][w] = yl; sh[3][w] = yh; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { xl = fmin(xl, sh[0][w]); xh = fmax(xh, sh[1][w]); yl = fmin(yl, sh[2][w]); yh = fmax(yh, sh[3][w]); }
+        part[blockIdx.x * 4 + 0] = xl; part[blockIdx.x * 4 + 1] = xh; part[blockIdx.x * 4 + 2] = yl; part[blockIdx.x * 4 + 3] = yh;
+    }
+}
+
+// one thread: fold the partial boxes and lay out the cell grid (about two points per cell)
+__global__ void k_grid_setup(const double *__restrict__ part, int nblk, int64_t num, int max_cells, GridCells *g)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double xl = part[0], xh = part[1], yl = part[2], yh = part[3];
+    for (int b = 1; b < nblk; b++) {
+        xl = fmin(xl, part[4 * b]); xh = fmax(xh, part[4 * b + 1]); yl = fmin(yl, part[4 * b + 2]); yh = fmax(yh, part[4 * b + 3]);
+    }
+    double W = xh - xl, H = yh - yl;
+    const double diag = sqrt(W * W + H * H);
+    if (!(W > 0.)) W = diag > 0. ? diag * 1e-6 : 1.;
+    if (!(H > 0.)) H = diag > 0. ? diag * 1e-6 : 1.;
+    double cells = (double)num / 2.;
+    if (cells < 1.) cells = 1.;
+    if (cells > (double)max_cells) cells = (double)max_cells;
+    double h = sqrt(W * H / cells);
+    // a very elongated box: never more than max_cells cells in total
+    int gx = (int)ceil(W / h), gy = (int)ceil(H / h);
+    while ((double)gx * (double)gy > (double)max_cells) { h *= 1.1; gx = (int)ceil(W / h); gy = (int)ceil(H / h); }
+    if (gx < 1) gx = 1;
+    if (gy < 1) gy = 1;
+    g->x0 = xl; g->y0 = yl; g->x1 = xh; g->y1 = yh; g->h = h; g->gx = gx; g->gy = gy;
+    g->box = 1e6 * (diag > 0. ? diag : 1.);
+}
+
+PXF_DEV int cell_of(const GridCells &g, double x, double y, int &cx, int &cy)
+{
+    cx = (int)floor((x - g.x0) / g.h);
+    cy = (int)floor((y - g.y0) / g.h);
+    cx = cx < 0 ? 0 : (cx >= g.gx ? g.gx - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= g.gy ? g.gy - 1 : cy);
+    return cy * g.gx + cx;
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t num, const GridCells *__restrict__ gp,
+            double *__restrict__ key)
+{
+    const GridCells g = *gp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
+        int cx, cy;
+        key[i] = (double)cell_of(g, x[i], y[i], cx, cy);
+    }
+}
+
+// start[c] = first sorted position of cell c (start[ncell] = num); also the points in cell order
+__global__ void __launch_bounds__(256)
+k_cell_starts(const double *__restrict__ skey, const long long *__restrict__ perm, int64_t num, const GridCells *__restrict__ gp,
+              const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ v,
+              int *__restrict__ start, double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sv)
+{
+    const int ncell = gp->gx * gp->gy;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)skey[i];
+        const int prev = i > 0 ? (int)skey[i - 1] : -1;
+        for (int k = prev + 1; k <= c; k++) start[k] = (int)i;
+        if (i == num - 1)
+            for (int k = c + 1; k <= ncell; k++) start[k] = (int)num;
+        const long long p = perm[i];
+        sx[i] = x[p]; sy[i] = y[p]; sv[i] = v[p];
+    }
+}
+
+// ---------------------------------------------------------------- the query kernel
+// lower bound of the distance from q to any point in a cell outside the (2r+1)^2 block around cell (cx, cy);
+// +inf when the block covers the whole grid
+PXF_DEV double ring_clearance(const GridCells &g, double qx, double qy, int cx, int cy, int r)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double d = inf;
+    if (cx - r > 0) d = fmin(d, fmax(0., qx - (g.x0 + (cx - r) * g.h)));
+    if (cx + r < g.gx - 1) d = fmin(d, fmax(0., (g.x0 + (cx + r + 1) * g.h) - qx));
+    if (cy - r > 0) d = fmin(d, fmax(0., qy - (g.y0 + (cy - r) * g.h)));
+    if (cy + r < g.gy - 1) d = fmin(d, fmax(0., (g.y0 + (cy + r + 1) * g.h) - qy));
+    return d;
+}
+
+// 2 x signed area: > 0 when a, b, c turn left
+PXF_DEV double orient2(double ax, double ay, double bx, double by, double cx, double cy)
+{
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+
+// > 0 when p is inside the circle through a, b, c (counter-clockwise)
+PXF_DEV double incircle(double ax, double ay, double bx, double by, double cx, double cy, double px, double py)
+{
+    const double adx = ax - px, ady = ay - py, bdx = bx - px, bdy = by - py, cdx = cx - px, cdy = cy - py;
+    const double ad = adx * adx + ady * ady, bd = bdx * bdx + bdy * bdy, cd = cdx * cdx + cdy * cdy;
+    return adx * (bdy * cd - bd * cdy) - ady * (bdx * cd - bd * cdx) + ad * (bdx * cdy - bdy * cdx);
+}
+
+// status per query: 0 interpolated, 1 outside the hull (NaN), 2 failed (NaN; counted)
+template <int METHOD>
+__global__ void __launch_bounds__(GI_THREADS)
+k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
+           const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
+           const double *__restrict__ qys, int64_t nq, double *__restrict__ out, unsigned long long *__restrict__ nfail)
+{
+    const int64_t iq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (iq >= nq) return;
+    const GridCells g = *gp;
+    const double qx = qxs[iq], qy = qys[iq];
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    if (!(qx == qx) || !(qy == qy)) { out[iq] = nanv; return; }
+    int cx, cy;
+    cell_of(g, qx, qy, cx, cy);
+    const int rcap = g.gx > g.gy ? g.gx : g.gy;
+
+    if (METHOD == 0) {
+        // nearest neighbour: rings until no unvisited point can be closer
+        double best = __longlong_as_double(0x7ff0000000000000ll), val = nanv;
+        for (int r = 0; r <= rcap; r++) {
+            for (int j = cy - r; j <= cy + r; j++) {
+                if (j < 0 || j >= g.gy) continue;
+                const bool edge_row = j == cy - r || j == cy + r;
+                for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
+                    if (i < 0 || i >= g.gx) continue;
+                    const int c = j * g.gx + i;
+                    for (int p = start[c]; p < start[c + 1]; p++) {
+                        const double dx = sx[p] - qx, dy = sy[p] - qy, d2 = dx * dx + dy * dy;
+                        if (d2 < best) { best = d2; val = sv[p]; }
+                    }
+                }
+            }
+            const double clr = ring_clearance(g, qx, qy, cx, cy, r);
+            if (clr * clr > best) break;
+        }
+        out[iq] = val;
+        return;
+    }
+
+    // ---- linear
+    // outside the points' bounding box: outside their convex hull
+    if (qx < g.x0 || qx > g.x1 || qy < g.y0 || qy > g.y1) { out[iq] = nanv; return; }
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    // 2. the nearest point of each half-open quadrant about q
+    double qd[4] = {inf, inf, inf, inf};
+    int qi[4] = {-1, -1, -1, -1};
+    for (int r = 0; r <= rcap; r++) {
+        for (int j = cy - r; j <= cy + r; j++) {
+            if (j < 0 || j >= g.gy) continue;
+            const bool edge_row = j == cy - r || j == cy + r;
+            for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
+                if (i < 0 || i >= g.gx) continue;
+                const int c = j * g.gx + i;
+                for (int p = start[c]; p < start[c + 1]; p++) {
+                    const double dx = sx[p] - qx, dy = sy[p] - qy, d2 = dx * dx + dy * dy;
+                    if (d2 == 0.) { out[iq] = sv[p]; return; }        // the query is a data point
+                    const int quad = dx > 0. ? (dy >= 0. ? 0 : 3) : (dx < 0. ? (dy > 0. ? 1 : 2) : (dy > 0. ? 1 : 3));
+                    if (d2 < qd[quad]) { qd[quad] = d2; qi[quad] = p; }
+                }
+            }
+        }
+        if (qi[0] >= 0 && qi[1] >= 0 && qi[2] >= 0 && qi[3] >= 0) break;
+    }
+    double ax, ay, bx, by, cx_, cy_;       // the triangle, relative to q, counter-clockwise
+    int ia = -1, ib = -1, ic = -1;
+    if (qi[0] >= 0 && qi[1] >= 0 && qi[2] >= 0 && qi[3] >= 0) {
+        // q is in the hull of the four points (no half-plane through q meets all four quadrants): take the triple
+        // that holds it best
+        double bestm = -inf;
+        for (int skip = 0; skip < 4; skip++) {
+            int t[3], n = 0;
+            for (int k = 0; k < 4; k++) if (k != skip) t[n++] = qi[k];       // still in counter-clockwise quadrant order
+            const double x0 = sx[t[0]] - qx, y0 = sy[t[0]] - qy, x1 = sx[t[1]] - qx, y1 = sy[t[1]] - qy,
+                         x2 = sx[t[2]] - qx, y2 = sy[t[2]] - qy;
+            const double area = orient2(x0, y0, x1, y1, x2, y2);
+            if (!(area > 0.)) continue;
+            const double m = fmin(fmin(x0 * y1 - y0 * x1, x1 * y2 - y1 * x2), x2 * y0 - y2 * x0) / area;
+            if (m > bestm) { bestm = m; ia = t[0]; ib = t[1]; ic = t[2]; }
+        }
+        if (ia < 0 || bestm < -1e-12) { out[iq] = nanv; atomicAdd(nfail, 1ull); atomicAdd(nfail + 1, 1ull); return; }
+    } else {
+        // a quadrant is empty.  With a = the first point as the zero direction, b = the point turned farthest
+        // counter-clockwise (by less than pi) and c = farthest clockwise: if b and c are less than pi apart on the far
+        // side the triangle a, b, c holds q; otherwise an empty half-plane through q exists: q is outside the hull
+        const int64_t np = start[g.gx * g.gy];
+        const double a0x = sx[0] - qx, a0y = sy[0] - qy;
+        int jb = -1, jc = -1;
+        double bxx = 0., byy = 0., cxx = 0., cyy = 0.;
+        for (int64_t p = 1; p < np; p++) {
+            const double dx = sx[p] - qx, dy = sy[p] - qy;
+            const double cr = a0x * dy - a0y * dx;                   // > 0: counter-clockwise of a
+            if (cr > 0. || (cr == 0. && a0x * dx + a0y * dy < 0.)) {  // (a point exactly opposite counts on this side)
+                if (jb < 0 || bxx * dy - byy * dx > 0.) { jb = (int)p; bxx = dx; byy = dy; }
+            }
+            if (cr < 0. || (cr == 0. && a0x * dx + a0y * dy < 0.)) {
+                if (jc < 0 || cxx * dy - cyy * dx < 0.) { jc = (int)p; cxx = dx; cyy = dy; }
+            }
+        }
+        // b counter-clockwise to c through the far side is less than pi  <=>  c is counter-clockwise of b
+        if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { out[iq] = nanv; return; }
+        ia = 0; ib = jb; ic = jc;
+    }
+    ax = sx[ia] - qx; ay = sy[ia] - qy; bx = sx[ib] - qx; by = sy[ib] - qy; cx_ = sx[ic] - qx; cy_ = sy[ic] - qy;
+
+    // 3. pivot until the circumcircle is empty
+    bool settled = false;
+    for (int it = 0; it < GI_MAX_PIVOTS; it++) {
+        const double area = orient2(ax, ay, bx, by, cx_, cy_);
+        if (!(area > 0.)) break;
+        // circumcentre (relative to a), radius
+        const double ux_ = bx - ax, uy_ = by - ay, vx_ = cx_ - ax, vy_ = cy_ - ay;
+        const double ul = ux_ * ux_ + uy_ * uy_, vl = vx_ * vx_ + vy_ * vy_;
+        const double ox = ax + (vy_ * ul - uy_ * vl) / (2. * area), oy = ay + (ux_ * vl - vx_ * ul) / (2. * area);
+        const double R = sqrt((ox - ax) * (ox - ax) + (oy - ay) * (oy - ay));
+        const double tol = 1e-12 * area * R * R;
+        // cells under the circle
+        int i0 = (int)floor((qx + ox - R - g.x0) / g.h), i1 = (int)floor((qx + ox + R - g.x0) / g.h);
+        int j0 = (int)floor((qy + oy - R - g.y0) / g.h), j1 = (int)floor((qy + oy + R - g.y0) / g.h);
+        // (a huge circle: floor() of a huge quotient saturates; clamp in floating point first)
+        if (!((qx + ox - R - g.x0) / g.h > 0.)) i0 = 0;
+        if (!((qx + ox + R - g.x0) / g.h < (double)g.gx)) i1 = g.gx - 1;
+        if (!((qy + oy - R - g.y0) / g.h > 0.)) j0 = 0;
+        if (!((qy + oy + R - g.y0) / g.h < (double)g.gy)) j1 = g.gy - 1;
+        double worst = tol;
+        int iw = -1;
+        for (int j = j0; j <= j1; j++) {
+            const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];      // cells of one row are contiguous
+            for (int p = p0; p < p1; p++) {
+                if (p == ia || p == ib || p == ic) continue;
+                const double v = incircle(ax, ay, bx, by, cx_, cy_, sx[p] - qx, sy[p] - qy);
+                if (v > worst) { worst = v; iw = p; }
+            }
+        }
+        if (iw < 0) { settled = true; break; }
+        // the deepest point replaces the vertex that keeps q inside: of (p,b,c), (a,p,c), (a,b,p) the one that holds q best
+        const double px = sx[iw] - qx, py = sy[iw] - qy;
+        double bestm = -inf;
+        int which = -1;
+        for (int k = 0; k < 3; k++) {
+            const double x0 = k == 0 ? px : ax, y0 = k == 0 ? py : ay, x1 = k == 1 ? px : bx, y1 = k == 1 ? py : by,
+                         x2 = k == 2 ? px : cx_, y2 = k == 2 ? py : cy_;
+            const double ar = orient2(x0, y0, x1, y1, x2, y2);
+            if (!(ar > 0.)) continue;
+            const double m = fmin(fmin(x0 * y1 - y0 * x1, x1 * y2 - y1 * x2), x2 * y0 - y2 * x0) / ar;
+            if (m > bestm) { bestm = m; which = k; }
+        }
+        if (which < 0 || bestm < -1e-9) break;
+        if (which == 0) { ax = px; ay = py; ia = iw; }
+        else if (which == 1) { bx = px; by = py; ib = iw; }
+        else { cx_ = px; cy_ = py; ic = iw; }
+    }
+    if (!settled) { out[iq] = nanv; atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); return; }
+    {
+        // 4. barycentric coordinates of q (the origin): areas of the sub-triangles
+        const double area = orient2(ax, ay, bx, by, cx_, cy_);
+        const double oab = ax * by - ay * bx, obc = bx * cy_ - by * cx_, oca = cx_ * ay - cy_ * ax;
+        out[iq] = obc / area * sv[ia] + oca / area * sv[ib] + oab / area * sv[ic];
+    }
+}
+
+// analyses.py:219-226 (polar=True): rho, rho*arctan2(y,x), rho*arctan2(x,y)
+__global__ void __launch_bounds__(256)
+k_polar_coords(const double *__restrict__ x, const double *__restrict__ y, int64_t num, double *__restrict__ rho,
+               double *__restrict__ az1, double *__restrict__ az2)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y[i];
+        const double r = sqrt(a * a + b * b);
+        rho[i] = r;
+        az1[i] = atan2(b, a) * r;
+        az2[i] = atan2(a, b) * r;
+    }
+}
+
+// np.nanmedian([a, b], axis=0): the mean of two numbers, the other one if one is NaN (analyses.py:227)
+__global__ void __launch_bounds__(256)
+k_nanmedian2(const double *__restrict__ a, const double *__restrict__ b, int64_t num, double *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
+        const double u = a[i], v = b[i];
+        out[i] = u != u ? v : (v != v ? u : (u + v) / 2.);      // numpy's mean of the two: (u+v)/2
+    }
+}
+
+static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+#define GI_MAX_CELLS (1 << 24)
+#define GI_BBOX_BLOCKS 512
+
+}  // namespace pxf
+
+using namespace pxf;
+
+extern "C" {
+
+size_t pxf_griddata_scratch_bytes(int64_t num)
+{
+    const size_t n = (size_t)(num > 0 ? num : 1);
+    size_t cells = n / 2 + 2;
+    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
+    return 5 * a256(n * 8) + a256(n * 8) + a256((cells + 2) * 4) + a256(GI_BBOX_BLOCKS * 4 * 8) + a256(sizeof(GridCells)) + 256 +
+           pxf_sort_scratch_bytes(num) + 1024;
+}
+
+int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
+                 double *out, int64_t nq, int32_t method, int64_t *nfail_host, void *scratch, pxf_stream_t stream)
+{
+    if (num < 0 || nq < 0 || !x || !y || !v || !scratch || (nq > 0 && (!qx || !qy || !out)) || method < 0 || method > 1 ||
+        num > 0x7fffffffll) {
+        set_error("pxf_griddata: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    if (nfail_host) *nfail_host = 0;
+    if (nq == 0) return PXF_OK;
+    if (num < (method == 1 ? 3 : 1)) { set_error("pxf_griddata: needs at least %d points", method == 1 ? 3 : 1); return PXF_ERR_INVALID; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)num;
+    size_t cells = n / 2 + 2;
+    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
+    char *p = static_cast<char *>(scratch);
+    double *key = (double *)p; p += a256(n * 8);
+    double *skey = (double *)p; p += a256(n * 8);
+    long long *perm = (long long *)p; p += a256(n * 8);
+    double *sx = (double *)p; p += a256(n * 8);
+    double *sy = (double *)p; p += a256(n * 8);
+    double *sv = (double *)p; p += a256(n * 8);
+    int *start = (int *)p; p += a256((cells + 2) * 4);
+    double *part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
+    GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
+    unsigned long long *nfail = (unsigned long long *)p; p += 256;
+    void *sort_scr = p;
+    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
+    PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
+    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
+    k_grid_setup<<<1, 32, 0, s>>>(part, nb, num, (int)(cells - 2), g);
+    k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, g, key);
+    count_launch(3);
+    int rc = pxf_argsort(key, num, skey, reinterpret_cast<int64_t *>(perm), sort_scr, stream);
+    if (rc) return rc;
+    k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, v, start, sx, sy, sv);
+    const unsigned qb = (unsigned)((nq + GI_THREADS - 1) / GI_THREADS);
+    if (method == 0) k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx, qy, nq, out, nfail);
+    else k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx, qy, nq, out, nfail);
+    count_launch(2);
+    if ((rc = check_launch("pxf_griddata"))) return rc;
+    if (nfail_host) {
+        unsigned long long h[4] = {0, 0, 0, 0};
+        PXF_CUDA(cudaMemcpyAsync(h, nfail, 32, cudaMemcpyDeviceToHost, s));
+        PXF_CUDA(cudaStreamSynchronize(s));
+        *nfail_host = (int64_t)h[0];
+        if (h[0])
+            set_error("pxf_griddata: %llu queries unresolved (%llu: no start triangle, %llu: pivoting did not settle)", h[0], h[1],
+                      h[3]);
+    }
+    return PXF_OK;
+}
+
+int pxf_bbox(const double *x, const double *y, int64_t num, double *box_host /*[4]: xmin, xmax, ymin, ymax*/, void *scratch,
+             pxf_stream_t stream)
+{
+    if (num <= 0 || !x || !y || !box_host || !scratch) { set_error("pxf_bbox: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    double *part = static_cast<double *>(scratch);
+    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
+    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
+    count_launch();
+    int rc = check_launch("k_bbox_partial");
+    if (rc) return rc;
+    std::vector<double> h((size_t)nb * 4);
+    PXF_CUDA(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    box_host[0] = h[0]; box_host[1] = h[1]; box_host[2] = h[2]; box_host[3] = h[3];
+    for (int b = 1; b < nb; b++) {
+        box_host[0] = fmin(box_host[0], h[4 * b]); box_host[1] = fmax(box_host[1], h[4 * b + 1]);
+        box_host[2] = fmin(box_host[2], h[4 * b + 2]); box_host[3] = fmax(box_host[3], h[4 * b + 3]);
+    }
+    return PXF_OK;
+}
+
+size_t pxf_bbox_scratch_bytes(void) { return (size_t)GI_BBOX_BLOCKS * 4 * 8; }
+
+int pxf_polar_coords(const double *x, const double *y, int64_t num, double *rho, double *az1, double *az2, pxf_stream_t stream)
+{
+    if (num < 0 || (num > 0 && (!x || !y || !rho || !az1 || !az2))) { set_error("pxf_polar_coords: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    if (num == 0) return PXF_OK;
+    k_polar_coords<<<grid_for(num, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, num, rho, az1, az2);
+    count_launch();
+    return check_launch("k_polar_coords");
+}
+
+int pxf_nanmedian2(const double *a, const double *b, int64_t num, double *out, pxf_stream_t stream)
+{
+    if (num < 0 || (num > 0 && (!a || !b || !out))) { set_error("pxf_nanmedian2: bad argument"); return PXF_ERR_INVALID; }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    if (num == 0) return PXF_OK;
+    k_nanmedian2<<<grid_for(num, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, num, out);
+    count_launch();
+    return check_launch("k_nanmedian2");
+}
+
+}  // extern "C"

@@ -143,3 +143,43 @@ def test_golden_southwell_reproduced_by_the_oracle(golden):
         xd, yd, bs = g["bin_%s_dims" % tag]
         xa, ya, ph = of.reconstruct.southwellbin(g["bin_x"], g["bin_y"], g["bin_l"], g["bin_m"], bs, int(xd), int(yd))
         assert np.array_equal(xa, g["bin_%s_xang" % tag]) and np.array_equal(ph, g["bin_%s_phase" % tag])
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_interpolatevec_and_wavefront_restatements_match_the_live_reference():
+    """oracle/refapi.py interpolateVec against the reference's own function (analyses.py:189-230; both call scipy's
+    griddata) bit for bit, and wavefront (:305-334) against the reference's text run with the two things it lacks as
+    shipped supplied from outside: ``man.padRect`` (un-vendored; a one-pixel NaN frame) and a ``reconstruct`` whose
+    ``maxiter`` has a default (the reference omits the required argument, :327)."""
+    pytest.importorskip("scipy.interpolate")
+    from oracle import f2py as of, refapi
+    ref = refload.load()
+    anal = ref.analyses
+    rng = np.random.default_rng(4)
+    n = 3000
+    r, t = 12.5 * np.sqrt(rng.uniform(0, 1, n)), rng.uniform(0, 2 * np.pi, n)
+    x, y = r * np.cos(t), r * np.sin(t)
+    l, m = 1e-3 * np.sin(x / 5.) + 1e-5 * rng.normal(size=n), 1e-3 * np.cos(y / 7.) + 1e-5 * rng.normal(size=n)
+    zero = np.zeros(n)
+    rays = [zero.copy(), x, y, zero.copy(), l, m, np.sqrt(1 - l ** 2 - m ** 2), zero.copy(), zero.copy(), zero + 1.]
+    for kw in (dict(method="linear"), dict(method="nearest"), dict(method="cubic"), dict(method="linear", polar=True),
+               dict(method="linear", xr=[-3., 9.], yr=[-14., 2.], interpVec=x * y)):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = anal.interpolateVec(copy(rays), 4, 31, 23, **kw)
+        b = refapi.interpolateVec(copy(rays), 4, 31, 23, **kw)
+        assert np.array_equal(a[0], b[0], equal_nan=True) and a[1] == b[1] and a[2] == b[2], kw
+
+    def pad_rect(img):
+        out = np.full((img.shape[0] + 2, img.shape[1] + 2), np.nan)
+        out[1:-1, 1:-1] = img
+        return out
+    anal.man.padRect = pad_rect
+    anal.reconstruct.reconstruct = lambda xa, ya, crit, h, ph, maxiter=500: of.reconstruct.reconstruct(xa, ya, crit, h, ph, maxiter)
+    for method in ("linear", "cubic"):
+        a = anal.wavefront(copy(rays), 20, 16, method=method)
+        b = refapi.wavefront(copy(rays), 20, 16, method=method, maxiter=500)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v, equal_nan=True), method
+        assert np.isfinite(a[0]).sum() > 50
