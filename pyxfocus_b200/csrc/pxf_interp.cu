@@ -25,9 +25,15 @@ namespace pxf {
 #define GI_THREADS 128
 #define GI_MAX_PIVOTS 512
 
+#define GI_NDIR 64          // support directions of the outer hull approximation
+#define GI_DIR_SLICES 32
 struct GridCells {
-    double x0, y0, x1, y1, h, box;   // bounding box, cell size, half-size of the start square (relative to the query)
+    double x0, y0, x1, y1, h;   // bounding box, cell size
     int gx, gy;
+    // the points' support function in GI_NDIR directions: max_i p_i . u_k.  A query with q . u_k above it is outside
+    // the convex hull (an exact certificate); only the thin band between this polygon and the hull pays for the
+    // all-points pass of step 2
+    double ux[GI_NDIR], uy[GI_NDIR], sup[GI_NDIR];
 };
 
 // ---------------------------------------------------------------- bounding box (two-stage, deterministic)
@@ -54,10 +60,40 @@ k_bbox_partial(const double *__restrict__ x, const double *__restrict__ y, int64
     }
 }
 
-// one thread: fold the partial boxes and lay out the cell grid (about two points per cell)
-__global__ void k_grid_setup(const double *__restrict__ part, int nblk, int64_t num, int max_cells, GridCells *g)
+// block (k, s): max over slice s of the points of p . u_k
+__global__ void __launch_bounds__(256)
+k_support_partial(const double *__restrict__ x, const double *__restrict__ y, int64_t num, double *__restrict__ part /*[NDIR][SLICES]*/)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    const int k = blockIdx.x % GI_NDIR, sl = blockIdx.x / GI_NDIR;
+    double sn, cs;
+    sincospi(2. * k / GI_NDIR, &sn, &cs);
+    double best = -__longlong_as_double(0x7ff0000000000000ll);
+    for (int64_t i = (int64_t)sl * blockDim.x + threadIdx.x; i < num; i += (int64_t)GI_DIR_SLICES * blockDim.x)
+        best = fmax(best, x[i] * cs + y[i] * sn);
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_down_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) best = fmax(best, sh[w]);
+        part[k * GI_DIR_SLICES + sl] = best;
+    }
+}
+
+// one warp: fold the partial boxes and supports and lay out the cell grid (about two points per cell)
+__global__ void k_grid_setup(const double *__restrict__ part, int nblk, int64_t num, int max_cells, GridCells *g,
+                             const double *__restrict__ spart)
+{
+    if (blockIdx.x) return;
+    for (int k = threadIdx.x; k < GI_NDIR; k += blockDim.x) {
+        double sn, cs;
+        sincospi(2. * k / GI_NDIR, &sn, &cs);
+        double b = spart[k * GI_DIR_SLICES];
+        for (int sl = 1; sl < GI_DIR_SLICES; sl++) b = fmax(b, spart[k * GI_DIR_SLICES + sl]);
+        g->ux[k] = cs; g->uy[k] = sn; g->sup[k] = b;
+    }
+    if (threadIdx.x) return;
     double xl = part[0], xh = part[1], yl = part[2], yh = part[3];
     for (int b = 1; b < nblk; b++) {
         xl = fmin(xl, part[4 * b]); xh = fmax(xh, part[4 * b + 1]); yl = fmin(yl, part[4 * b + 2]); yh = fmax(yh, part[4 * b + 3]);
@@ -76,7 +112,6 @@ __global__ void k_grid_setup(const double *__restrict__ part, int nblk, int64_t 
     if (gx < 1) gx = 1;
     if (gy < 1) gy = 1;
     g->x0 = xl; g->y0 = yl; g->x1 = xh; g->y1 = yh; g->h = h; g->gx = gx; g->gy = gy;
-    g->box = 1e6 * (diag > 0. ? diag : 1.);
 }
 
 PXF_DEV int cell_of(const GridCells &g, double x, double y, int &cx, int &cy)
@@ -92,7 +127,7 @@ __global__ void __launch_bounds__(256)
 k_cell_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t num, const GridCells *__restrict__ gp,
             double *__restrict__ key)
 {
-    const GridCells g = *gp;
+    const GridCells &g = *gp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num; i += (int64_t)gridDim.x * blockDim.x) {
         int cx, cy;
         key[i] = (double)cell_of(g, x[i], y[i], cx, cy);
@@ -145,16 +180,94 @@ PXF_DEV double incircle(double ax, double ay, double bx, double by, double cx, d
     return adx * (bdy * cd - bd * cdy) - ady * (bdx * cd - bd * cdx) + ad * (bdx * cdy - bdy * cdx);
 }
 
-// status per query: 0 interpolated, 1 outside the hull (NaN), 2 failed (NaN; counted)
+#define GI_RQ 12               // rings searched for the quadrant points before a query is handed to the warp kernel
+#define GI_CELL_BUDGET 4096    // cells under one circumcircle a single thread may scan
+
+// Steps 3 and 4 for one query from a start triangle (ia, ib, ic: counter-clockwise, holds q).  COOP: the 32 lanes of a
+// warp work on the SAME query: the rows of cells under the circumcircle are dealt out to the lanes and the deepest
+// point is agreed on by shuffles.  Returns 0: *res holds the value, 1: over the single-thread budget (not COOP), 2: failed.
+template <bool COOP>
+PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
+                                   const double *__restrict__ sv, const int *__restrict__ start, double qx, double qy,
+                                   int ia, int ib, int ic, double *res)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const int lane = COOP ? (threadIdx.x & 31) : 0;
+    double ax = sx[ia] - qx, ay = sy[ia] - qy, bx = sx[ib] - qx, by = sy[ib] - qy, cx_ = sx[ic] - qx, cy_ = sy[ic] - qy;
+    bool settled = false;
+    for (int it = 0; it < GI_MAX_PIVOTS; it++) {
+        const double area = orient2(ax, ay, bx, by, cx_, cy_);
+        if (!(area > 0.)) break;
+        // circumcentre (relative to q), radius
+        const double ux_ = bx - ax, uy_ = by - ay, vx_ = cx_ - ax, vy_ = cy_ - ay;
+        const double ul = ux_ * ux_ + uy_ * uy_, vl = vx_ * vx_ + vy_ * vy_;
+        const double ox = ax + (vy_ * ul - uy_ * vl) / (2. * area), oy = ay + (ux_ * vl - vx_ * ul) / (2. * area);
+        const double R = sqrt((ox - ax) * (ox - ax) + (oy - ay) * (oy - ay));
+        const double tol = 1e-12 * area * R * R;
+        // cells under the circle (a huge circle: clamp in floating point, floor() of a huge quotient saturates)
+        const double fi0 = (qx + ox - R - g.x0) / g.h, fi1 = (qx + ox + R - g.x0) / g.h;
+        const double fj0 = (qy + oy - R - g.y0) / g.h, fj1 = (qy + oy + R - g.y0) / g.h;
+        const int i0 = fi0 > 0. ? (fi0 < (double)g.gx ? (int)fi0 : g.gx - 1) : 0;
+        const int i1 = fi1 < (double)g.gx ? (fi1 > 0. ? (int)fi1 : 0) : g.gx - 1;
+        const int j0 = fj0 > 0. ? (fj0 < (double)g.gy ? (int)fj0 : g.gy - 1) : 0;
+        const int j1 = fj1 < (double)g.gy ? (fj1 > 0. ? (int)fj1 : 0) : g.gy - 1;
+        if (!COOP && (int64_t)(i1 - i0 + 1) * (j1 - j0 + 1) > GI_CELL_BUDGET) return 1;
+        double worst = tol;
+        int iw = -1;
+        for (int j = j0 + lane; j <= j1; j += COOP ? 32 : 1) {
+            const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];      // cells of one row are contiguous
+            for (int p = p0; p < p1; p++) {
+                if (p == ia || p == ib || p == ic) continue;
+                const double v = incircle(ax, ay, bx, by, cx_, cy_, sx[p] - qx, sy[p] - qy);
+                if (v > worst) { worst = v; iw = p; }
+            }
+        }
+        if (COOP) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, worst, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, iw, o);
+                if (oi >= 0 && (iw < 0 || ov > worst || (ov == worst && oi < iw))) { worst = ov; iw = oi; }
+            }
+        }
+        if (iw < 0) { settled = true; break; }
+        // the deepest point replaces the vertex that keeps q inside: of (p,b,c), (a,p,c), (a,b,p) the one that holds q best
+        const double px = sx[iw] - qx, py = sy[iw] - qy;
+        double bestm = -inf;
+        int which = -1;
+        for (int k = 0; k < 3; k++) {
+            const double x0 = k == 0 ? px : ax, y0 = k == 0 ? py : ay, x1 = k == 1 ? px : bx, y1 = k == 1 ? py : by,
+                         x2 = k == 2 ? px : cx_, y2 = k == 2 ? py : cy_;
+            const double ar = orient2(x0, y0, x1, y1, x2, y2);
+            if (!(ar > 0.)) continue;
+            const double m = fmin(fmin(x0 * y1 - y0 * x1, x1 * y2 - y1 * x2), x2 * y0 - y2 * x0) / ar;
+            if (m > bestm) { bestm = m; which = k; }
+        }
+        if (which < 0 || bestm < -1e-9) break;
+        if (which == 0) { ax = px; ay = py; ia = iw; }
+        else if (which == 1) { bx = px; by = py; ib = iw; }
+        else { cx_ = px; cy_ = py; ic = iw; }
+    }
+    if (!settled) return 2;
+    // 4. barycentric coordinates of q (the origin): areas of the sub-triangles
+    const double area = orient2(ax, ay, bx, by, cx_, cy_);
+    const double oab = ax * by - ay * bx, obc = bx * cy_ - by * cx_, oca = cx_ * ay - cy_ * ax;
+    *res = obc / area * sv[ia] + oca / area * sv[ib] + oab / area * sv[ic];
+    return 0;
+}
+
+// One thread per query.  Queries that need a pass over all points (an empty quadrant nearby: near or outside the hull)
+// or a very large circumcircle are appended to `slow` for k_griddata_warp.
 template <int METHOD>
 __global__ void __launch_bounds__(GI_THREADS)
 k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
            const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
-           const double *__restrict__ qys, int64_t nq, double *__restrict__ out, unsigned long long *__restrict__ nfail)
+           const double *__restrict__ qys, int64_t nq, double *__restrict__ out, unsigned long long *__restrict__ nfail,
+           unsigned *__restrict__ slow)
 {
     const int64_t iq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (iq >= nq) return;
-    const GridCells g = *gp;
+    const GridCells &g = *gp;
     const double qx = qxs[iq], qy = qys[iq];
     const double nanv = __longlong_as_double(0x7ff8000000000000ll);
     if (!(qx == qx) || !(qy == qy)) { out[iq] = nanv; return; }
@@ -186,13 +299,20 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
     }
 
     // ---- linear
-    // outside the points' bounding box: outside their convex hull
+    // outside the points' bounding box or beyond their support in some direction: outside their convex hull
     if (qx < g.x0 || qx > g.x1 || qy < g.y0 || qy > g.y1) { out[iq] = nanv; return; }
+    {
+        const double slack = 1e-12 * (fabs(g.x0) + fabs(g.x1) + fabs(g.y0) + fabs(g.y1));
+        bool outside = false;
+        for (int k = 0; k < GI_NDIR; k++) outside = outside || (qx * g.ux[k] + qy * g.uy[k] > g.sup[k] + slack);
+        if (outside) { out[iq] = nanv; return; }
+    }
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     // 2. the nearest point of each half-open quadrant about q
     double qd[4] = {inf, inf, inf, inf};
     int qi[4] = {-1, -1, -1, -1};
-    for (int r = 0; r <= rcap; r++) {
+    const int rq = rcap < GI_RQ ? rcap : GI_RQ;
+    for (int r = 0; r <= rq; r++) {
         for (int j = cy - r; j <= cy + r; j++) {
             if (j < 0 || j >= g.gy) continue;
             const bool edge_row = j == cy - r || j == cy + r;
@@ -209,7 +329,6 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
         }
         if (qi[0] >= 0 && qi[1] >= 0 && qi[2] >= 0 && qi[3] >= 0) break;
     }
-    double ax, ay, bx, by, cx_, cy_;       // the triangle, relative to q, counter-clockwise
     int ia = -1, ib = -1, ic = -1;
     if (qi[0] >= 0 && qi[1] >= 0 && qi[2] >= 0 && qi[3] >= 0) {
         // q is in the hull of the four points (no half-plane through q meets all four quadrants): take the triple
@@ -225,84 +344,72 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
             const double m = fmin(fmin(x0 * y1 - y0 * x1, x1 * y2 - y1 * x2), x2 * y0 - y2 * x0) / area;
             if (m > bestm) { bestm = m; ia = t[0]; ib = t[1]; ic = t[2]; }
         }
-        if (ia < 0 || bestm < -1e-12) { out[iq] = nanv; atomicAdd(nfail, 1ull); atomicAdd(nfail + 1, 1ull); return; }
-    } else {
-        // a quadrant is empty.  With a = the first point as the zero direction, b = the point turned farthest
-        // counter-clockwise (by less than pi) and c = farthest clockwise: if b and c are less than pi apart on the far
-        // side the triangle a, b, c holds q; otherwise an empty half-plane through q exists: q is outside the hull
-        const int64_t np = start[g.gx * g.gy];
+        if (ia < 0 || bestm < -1e-12) ia = -1;        // (points exactly on the axes through q: let the warp kernel decide)
+    }
+    int rc = 1;
+    double val = nanv;
+    if (ia >= 0) rc = settle_and_interpolate<false>(g, sx, sy, sv, start, qx, qy, ia, ib, ic, &val);
+    if (rc == 1) {
+        out[iq] = nanv;
+        slow[1 + atomicAdd(slow, 1u)] = (unsigned)iq;
+        return;
+    }
+    out[iq] = val;
+    if (rc == 2) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
+}
+
+// One warp per deferred query: a start triangle from a pass over ALL points -- with a = the first point as the zero
+// direction, b = the point turned farthest counter-clockwise (by less than pi) and c = farthest clockwise: if b and c
+// are less than pi apart on the far side the triangle a, b, c holds q, otherwise an empty half-plane through q exists
+// and q is outside the hull -- then the same pivoting with the scans dealt out to the lanes.
+__global__ void __launch_bounds__(GI_THREADS)
+k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
+                const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
+                const double *__restrict__ qys, double *__restrict__ out, unsigned long long *__restrict__ nfail,
+                const unsigned *__restrict__ slow)
+{
+    const GridCells &g = *gp;
+    const unsigned nslow = slow[0];
+    const int lane = threadIdx.x & 31;
+    const unsigned wpb = blockDim.x >> 5;
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    const int np = start[g.gx * g.gy];
+    for (unsigned w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nslow; w += gridDim.x * wpb) {
+        const int64_t iq = slow[1 + w];
+        const double qx = qxs[iq], qy = qys[iq];
         const double a0x = sx[0] - qx, a0y = sy[0] - qy;
         int jb = -1, jc = -1;
         double bxx = 0., byy = 0., cxx = 0., cyy = 0.;
-        for (int64_t p = 1; p < np; p++) {
+        for (int p = 1 + lane; p < np; p += 32) {
             const double dx = sx[p] - qx, dy = sy[p] - qy;
             const double cr = a0x * dy - a0y * dx;                   // > 0: counter-clockwise of a
-            if (cr > 0. || (cr == 0. && a0x * dx + a0y * dy < 0.)) {  // (a point exactly opposite counts on this side)
-                if (jb < 0 || bxx * dy - byy * dx > 0.) { jb = (int)p; bxx = dx; byy = dy; }
+            const bool opposite = cr == 0. && a0x * dx + a0y * dy < 0.;   // (a point exactly opposite counts on both sides)
+            if ((cr > 0. || opposite) && (jb < 0 || bxx * dy - byy * dx > 0.)) { jb = p; bxx = dx; byy = dy; }
+            if ((cr < 0. || opposite) && (jc < 0 || cxx * dy - cyy * dx < 0.)) { jc = p; cxx = dx; cyy = dy; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, jb, o), oc = __shfl_xor_sync(0xffffffffu, jc, o);
+            const double obx = __shfl_xor_sync(0xffffffffu, bxx, o), oby = __shfl_xor_sync(0xffffffffu, byy, o);
+            const double ocx = __shfl_xor_sync(0xffffffffu, cxx, o), ocy = __shfl_xor_sync(0xffffffffu, cyy, o);
+            // (the same direction from two lanes: the lower index, so that both partners keep the same point)
+            if (ob >= 0) {
+                const double t = bxx * oby - byy * obx;
+                if (jb < 0 || t > 0. || (t == 0. && ob < jb)) { jb = ob; bxx = obx; byy = oby; }
             }
-            if (cr < 0. || (cr == 0. && a0x * dx + a0y * dy < 0.)) {
-                if (jc < 0 || cxx * dy - cyy * dx < 0.) { jc = (int)p; cxx = dx; cyy = dy; }
+            if (oc >= 0) {
+                const double t = cxx * ocy - cyy * ocx;
+                if (jc < 0 || t < 0. || (t == 0. && oc < jc)) { jc = oc; cxx = ocx; cyy = ocy; }
             }
         }
         // b counter-clockwise to c through the far side is less than pi  <=>  c is counter-clockwise of b
-        if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { out[iq] = nanv; return; }
-        ia = 0; ib = jb; ic = jc;
-    }
-    ax = sx[ia] - qx; ay = sy[ia] - qy; bx = sx[ib] - qx; by = sy[ib] - qy; cx_ = sx[ic] - qx; cy_ = sy[ic] - qy;
-
-    // 3. pivot until the circumcircle is empty
-    bool settled = false;
-    for (int it = 0; it < GI_MAX_PIVOTS; it++) {
-        const double area = orient2(ax, ay, bx, by, cx_, cy_);
-        if (!(area > 0.)) break;
-        // circumcentre (relative to a), radius
-        const double ux_ = bx - ax, uy_ = by - ay, vx_ = cx_ - ax, vy_ = cy_ - ay;
-        const double ul = ux_ * ux_ + uy_ * uy_, vl = vx_ * vx_ + vy_ * vy_;
-        const double ox = ax + (vy_ * ul - uy_ * vl) / (2. * area), oy = ay + (ux_ * vl - vx_ * ul) / (2. * area);
-        const double R = sqrt((ox - ax) * (ox - ax) + (oy - ay) * (oy - ay));
-        const double tol = 1e-12 * area * R * R;
-        // cells under the circle
-        int i0 = (int)floor((qx + ox - R - g.x0) / g.h), i1 = (int)floor((qx + ox + R - g.x0) / g.h);
-        int j0 = (int)floor((qy + oy - R - g.y0) / g.h), j1 = (int)floor((qy + oy + R - g.y0) / g.h);
-        // (a huge circle: floor() of a huge quotient saturates; clamp in floating point first)
-        if (!((qx + ox - R - g.x0) / g.h > 0.)) i0 = 0;
-        if (!((qx + ox + R - g.x0) / g.h < (double)g.gx)) i1 = g.gx - 1;
-        if (!((qy + oy - R - g.y0) / g.h > 0.)) j0 = 0;
-        if (!((qy + oy + R - g.y0) / g.h < (double)g.gy)) j1 = g.gy - 1;
-        double worst = tol;
-        int iw = -1;
-        for (int j = j0; j <= j1; j++) {
-            const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];      // cells of one row are contiguous
-            for (int p = p0; p < p1; p++) {
-                if (p == ia || p == ib || p == ic) continue;
-                const double v = incircle(ax, ay, bx, by, cx_, cy_, sx[p] - qx, sy[p] - qy);
-                if (v > worst) { worst = v; iw = p; }
-            }
+        if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { if (lane == 0) out[iq] = nanv; continue; }
+        double val = nanv;
+        const int rc = settle_and_interpolate<true>(g, sx, sy, sv, start, qx, qy, 0, jb, jc, &val);
+        if (lane == 0) {
+            out[iq] = val;
+            if (rc) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
         }
-        if (iw < 0) { settled = true; break; }
-        // the deepest point replaces the vertex that keeps q inside: of (p,b,c), (a,p,c), (a,b,p) the one that holds q best
-        const double px = sx[iw] - qx, py = sy[iw] - qy;
-        double bestm = -inf;
-        int which = -1;
-        for (int k = 0; k < 3; k++) {
-            const double x0 = k == 0 ? px : ax, y0 = k == 0 ? py : ay, x1 = k == 1 ? px : bx, y1 = k == 1 ? py : by,
-                         x2 = k == 2 ? px : cx_, y2 = k == 2 ? py : cy_;
-            const double ar = orient2(x0, y0, x1, y1, x2, y2);
-            if (!(ar > 0.)) continue;
-            const double m = fmin(fmin(x0 * y1 - y0 * x1, x1 * y2 - y1 * x2), x2 * y0 - y2 * x0) / ar;
-            if (m > bestm) { bestm = m; which = k; }
-        }
-        if (which < 0 || bestm < -1e-9) break;
-        if (which == 0) { ax = px; ay = py; ia = iw; }
-        else if (which == 1) { bx = px; by = py; ib = iw; }
-        else { cx_ = px; cy_ = py; ic = iw; }
-    }
-    if (!settled) { out[iq] = nanv; atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); return; }
-    {
-        // 4. barycentric coordinates of q (the origin): areas of the sub-triangles
-        const double area = orient2(ax, ay, bx, by, cx_, cy_);
-        const double oab = ax * by - ay * bx, obc = bx * cy_ - by * cx_, oca = cx_ * ay - cy_ * ax;
-        out[iq] = obc / area * sv[ia] + oca / area * sv[ib] + oab / area * sv[ic];
     }
 }
 
@@ -331,6 +438,8 @@ k_nanmedian2(const double *__restrict__ a, const double *__restrict__ b, int64_t
 }
 
 static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+#define GI_QUERY_BATCH (1 << 22)                          // queries per launch pair (bounds the deferred list)
+#define GI_SLOW_CAP_BYTES ((size_t)(GI_QUERY_BATCH + 64) * 4)
 #define GI_MAX_CELLS (1 << 24)
 #define GI_BBOX_BLOCKS 512
 
@@ -346,6 +455,8 @@ size_t pxf_griddata_scratch_bytes(int64_t num)
     size_t cells = n / 2 + 2;
     if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
     return 5 * a256(n * 8) + a256(n * 8) + a256((cells + 2) * 4) + a256(GI_BBOX_BLOCKS * 4 * 8) + a256(sizeof(GridCells)) + 256 +
+           GI_SLOW_CAP_BYTES +
+           a256(GI_NDIR * GI_DIR_SLICES * 8) +
            pxf_sort_scratch_bytes(num) + 1024;
 }
 
@@ -376,20 +487,34 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     double *part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
     GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
     unsigned long long *nfail = (unsigned long long *)p; p += 256;
+    double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
+    unsigned *slow = (unsigned *)p; p += GI_SLOW_CAP_BYTES;
     void *sort_scr = p;
     const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
     PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
     k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
-    k_grid_setup<<<1, 32, 0, s>>>(part, nb, num, (int)(cells - 2), g);
+    k_support_partial<<<GI_NDIR * GI_DIR_SLICES, 256, 0, s>>>(x, y, num, spart);
+    k_grid_setup<<<1, 64, 0, s>>>(part, nb, num, (int)(cells - 2), g, spart);
+    count_launch();
     k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, g, key);
     count_launch(3);
     int rc = pxf_argsort(key, num, skey, reinterpret_cast<int64_t *>(perm), sort_scr, stream);
     if (rc) return rc;
     k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, v, start, sx, sy, sv);
-    const unsigned qb = (unsigned)((nq + GI_THREADS - 1) / GI_THREADS);
-    if (method == 0) k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx, qy, nq, out, nfail);
-    else k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx, qy, nq, out, nfail);
-    count_launch(2);
+    count_launch();
+    for (int64_t q0 = 0; q0 < nq; q0 += GI_QUERY_BATCH) {
+        const int64_t nb_q = nq - q0 < GI_QUERY_BATCH ? nq - q0 : GI_QUERY_BATCH;
+        const unsigned qb = (unsigned)((nb_q + GI_THREADS - 1) / GI_THREADS);
+        if (method == 0) {
+            k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow);
+            count_launch();
+            continue;
+        }
+        PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
+        k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow);
+        k_griddata_warp<<<grid_for(nb_q, 1, 8), GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, out + q0, nfail, slow);
+        count_launch(2);
+    }
     if ((rc = check_launch("pxf_griddata"))) return rc;
     if (nfail_host) {
         unsigned long long h[4] = {0, 0, 0, 0};

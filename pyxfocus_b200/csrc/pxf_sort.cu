@@ -213,13 +213,11 @@ PXF_DEV void onesweep_tile(OsSmem<OS_THREADS, OS_ITEMS> &sm, const double *__res
             peers &= bit ? m : ~m;
         }
         if (!FULL && !valid) peers = 1u << lane;
-        const int leader = __ffs(peers) - 1;
-        u32 base = 0;
-        if (valid && lane == leader) {
-            base = wh[dd];
-            wh[dd] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
+        // every lane reads its digit's running count (lanes of one digit read one word: a broadcast), then the first
+        // lane of each group adds the group's size -- the load precedes the store in the warp's instruction order
+        const u32 base = wh[dd];
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) wh[dd] = base + __popc(peers);
         rank[j] = base + __popc(peers & ((1u << lane) - 1));
         __syncwarp();
     }
