@@ -629,15 +629,24 @@ int pxf_southwellbin(const double *x, const double *y, const double *l, const do
 /* ======================= scattered-data interpolation =================== */
 /* scipy.interpolate.griddata((x, y), v, (qx, qy), method) as analyses.interpolateVec / wavefront call it
  * (analyses.py:189-230, 305-334; scipy is a third-party dependency of the reference).  method 0 = 'nearest', 1 = 'linear'
- * (barycentric interpolation inside the Delaunay triangle that contains the query; NaN outside the convex hull).  The
- * triangle is found from the query's own natural neighbours (Voronoi cell clipped over a uniform cell grid), no global
- * triangulation is built.  All arrays on the device; out[nq].  *nfail_host (may be NULL; reading it synchronises)
+ * (barycentric interpolation inside the Delaunay triangle that contains the query; NaN outside the convex hull), 2 =
+ * 'cubic' (scipy's CloughTocher2DInterpolator: Gauss-Seidel vertex gradients in input order to 1e-6, reproduced sweep for
+ * sweep by level scheduling, then the Clough-Tocher patch of the containing triangle).  The triangle is found by pivoting
+ * to the empty circumcircle over a uniform cell grid; no global triangulation is built.  All arrays on the device; out[nq].  *nfail_host (may be NULL; reading it synchronises)
  * receives the number of queries whose cell could not be resolved (degenerate input; they are NaN).
  * scratch: pxf_griddata_scratch_bytes(num). */
 size_t pxf_griddata_scratch_bytes(int64_t num);
 int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
                  double *out, int64_t nq, int32_t method, int64_t *nfail_host, void *scratch, pxf_stream_t stream);
 
+/* The Delaunay neighbours of every point, counter-clockwise (the structure scipy's 'cubic' griddata takes its vertex
+ * gradients over; gift wrapping about each point over the same cell grid, no triangulation stored).  ring_out:
+ * device int32 [num][pxf_delaunay_max_degree()], unused slots -1; deg_out, open_out: device uint8 [num] (open = 1: a hull
+ * vertex, its ring is the chain from the clockwise to the counter-clockwise hull neighbour).  scratch:
+ * pxf_griddata_scratch_bytes(num). */
+int pxf_delaunay_max_degree(void);
+int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_t *ring_out, uint8_t *deg_out,
+                           uint8_t *open_out, void *scratch, pxf_stream_t stream);
 /* Helpers of analyses.interpolateVec: the bounding box of the ray positions (xr = [x.min(), x.max()], analyses.py:206-208;
  * box_host[4] = xmin, xmax, ymin, ymax; scratch: pxf_bbox_scratch_bytes()), the polar coordinates of its polar=True
  * branch (rho, rho*arctan2(y,x), rho*arctan2(x,y); analyses.py:219-226) and np.nanmedian of two arrays (:227). */

@@ -23,7 +23,7 @@ def main():
     zero = np.zeros(n)
     rays = [zero, x, y, zero, l, zero, zero, zero, zero, zero]
     dev = [torch.from_numpy(a).cuda() for a in rays]
-    for method in ("linear", "nearest"):
+    for method in ("linear", "nearest", "cubic"):
         best = 1e30
         for rep in range(3):
             torch.cuda.synchronize()

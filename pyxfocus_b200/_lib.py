@@ -180,6 +180,8 @@ SIGNATURES = {
     "pxf_bbox": (_c.c_int, [_dp, _dp, _i64, _vp, _vp, _st]),
     "pxf_polar_coords": (_c.c_int, [_dp, _dp, _i64, _dp, _dp, _dp, _st]),
     "pxf_nanmedian2": (_c.c_int, [_dp, _dp, _i64, _dp, _st]),
+    "pxf_delaunay_max_degree": (_c.c_int, []),
+    "pxf_delaunay_neighbors": (_c.c_int, [_dp, _dp, _i64, _vp, _vp, _vp, _vp, _st]),
     "pxf_griddata": (_c.c_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _i32, _vp, _vp, _st]),
     # sources
     "pxf_source": (_c.c_int, [_i32, _vp, _i64, _i64, _u64, _d, _d, _d, _d, _st]),

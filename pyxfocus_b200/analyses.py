@@ -303,14 +303,16 @@ def grazeAngle(rays, ind=None):
 
 
 # ---- OPD-map pipeline: scattered-data interpolation and wavefront integration (analyses.py:189-230, 305-334) ----
+_GRID_METHODS = {"nearest": 0, "linear": 1, "cubic": 2}
+
+
 def griddata(px, py, values, qx, qy, method="linear"):
-    """``scipy.interpolate.griddata((px, py), values, (qx, qy), method)`` for 'nearest' / 'linear' on the device
-    (``pxf_griddata``: the Delaunay triangle of every query point from its natural neighbours; NaN outside the convex
-    hull).  All five arguments are equally long (points) / equally shaped (queries) float64 CUDA tensors."""
-    if method not in ("nearest", "linear"):
-        raise NotImplementedError(
-            "method=%r: only 'nearest' and 'linear' are built ('cubic' is scipy's Clough-Tocher scheme, whose global "
-            "gradient estimate is an iteration to a tolerance inside a third-party library)" % (method,))
+    """``scipy.interpolate.griddata((px, py), values, (qx, qy), method)`` for 'nearest' / 'linear' / 'cubic' on the
+    device (``pxf_griddata``: the Delaunay triangle of every query point by pivoting to the empty circumcircle; 'cubic' is
+    scipy's Clough-Tocher interpolant with its global gradient estimate; NaN outside the convex hull).  All five
+    arguments are equally long (points) / equally shaped (queries) float64 CUDA tensors."""
+    if method not in _GRID_METHODS:
+        raise ValueError("Unknown interpolation method %r for 2 dimensional data" % (method,))
     dev = px.device
     shape = qx.shape
     px, py, values = (t.contiguous() for t in (px, py, values))
@@ -321,13 +323,30 @@ def griddata(px, py, values, qx, qy, method="linear"):
     with torch.cuda.device(dev):
         scratch = torch.empty(int(L.pxf_griddata_scratch_bytes(px.shape[0])), dtype=torch.uint8, device=dev)
         _lib.check(L.pxf_griddata(px.data_ptr(), py.data_ptr(), values.data_ptr(), px.shape[0], fx.data_ptr(), fy.data_ptr(),
-                                  out.data_ptr(), fx.shape[0], 1 if method == "linear" else 0, ctypes.byref(nfail),
+                                  out.data_ptr(), fx.shape[0], _GRID_METHODS[method], ctypes.byref(nfail),
                                   scratch.data_ptr(), stream_ptr(dev)))
     if nfail.value:
         raise _lib.PxfError("griddata: %d query points have no unique Delaunay triangle (degenerate point set: "
                             "duplicate, collinear or exactly cocircular points) -- %s"
                             % (nfail.value, (L.pxf_last_error() or b"").decode()))
     return out.reshape(shape)
+
+
+def delaunay_neighbors(px, py):
+    """Delaunay neighbours of every point, counter-clockwise: ``(ring, degree, is_hull_vertex)`` -- an int32
+    ``[N, max_degree]`` tensor padded with -1, and two uint8 ``[N]`` tensors."""
+    dev = px.device
+    n = px.shape[0]
+    L = _lib.lib()
+    ring = torch.empty((n, int(L.pxf_delaunay_max_degree())), dtype=torch.int32, device=dev)
+    deg = torch.empty(n, dtype=torch.uint8, device=dev)
+    hull = torch.empty(n, dtype=torch.uint8, device=dev)
+    px, py = px.contiguous(), py.contiguous()
+    with torch.cuda.device(dev):
+        scratch = torch.empty(int(L.pxf_griddata_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+        _lib.check(L.pxf_delaunay_neighbors(px.data_ptr(), py.data_ptr(), n, ring.data_ptr(), deg.data_ptr(), hull.data_ptr(),
+                                            scratch.data_ptr(), stream_ptr(dev)))
+    return ring, deg, hull
 
 
 def _bbox(x, y):
@@ -383,8 +402,7 @@ def wavefront(rays, Nx, Ny, method='cubic', polar=False, maxiter=10000):
     As shipped the reference cannot run this function: ``man.padRect`` lives in the un-vendored ``utilities.imaging``
     package (taken here as a one-pixel NaN frame, which is what the ``[1:-1,1:-1]`` at the end strips), and
     ``reconstruct.reconstruct`` is called without its required ``maxiter`` (here a keyword, default as in
-    ``southwell.southwell``).  ``method='cubic'`` (the default) needs scipy's Clough-Tocher interpolant and raises
-    ``NotImplementedError``; pass ``method='linear'``."""
+    ``southwell.southwell``)."""
     from . import reconstruct as _rec
     ys, dx, dy = interpolateVec(rays, 5, Nx, Ny, method=method, polar=polar)
     xs, dx, dy = interpolateVec(rays, 4, Nx, Ny, method=method, polar=polar)

@@ -16,6 +16,8 @@
 //      circumcircle are scanned.  The final triangle contains q and has an empty circumcircle: it is the triangle
 //      of the Delaunay triangulation (unique in general position) that scipy/Qhull interpolates in;
 //   4. barycentric interpolation inside that triangle.
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "pxf_internal.h"
 #include "pxf_ray.cuh"
@@ -180,6 +182,350 @@ PXF_DEV double incircle(double ax, double ay, double bx, double by, double cx, d
     return adx * (bdy * cd - bd * cdy) - ady * (bdx * cd - bd * cdx) + ad * (bdx * cdy - bdy * cdx);
 }
 
+// ================================================================= 'cubic': scipy's CloughTocher2DInterpolator
+// (what griddata(method='cubic') constructs for 2-D data; scipy/interpolate/interpnd.pyx).  Three ingredients:
+//   (a) the Delaunay neighbours of every data point, in counter-clockwise order (k_dt_rings): gift wrapping about the
+//       point -- the nearest neighbour is a Delaunay neighbour, and the apex of the Delaunay triangle on one side of an
+//       edge p-n is the point of that side that minimises the centre offset t of the circle through p, n and it;
+//   (b) the gradient at every data point from scipy's global estimate: Gauss-Seidel sweeps IN INPUT ORDER to a relative
+//       change below tol (estimate_gradients_2d_global).  The sequential sweep is reproduced exactly in parallel by
+//       level scheduling: a vertex's level is one more than the highest level among its neighbours that come earlier in
+//       the input, vertices of one level are mutually non-adjacent, and levels run in order;
+//   (c) the Clough-Tocher cubic on the triangle that holds the query (same triangle search as 'linear'), with the
+//       cross-edge derivative taken towards the centroid of the neighbouring triangle (read off the rings).
+#define GI_DEG 48              // Delaunay neighbours kept per point (a degenerate set -- a thin arc -- can exceed it)
+
+struct Rings {
+    int *ring;                 // [num][GI_DEG] neighbours, counter-clockwise
+    unsigned char *deg;        // [num]
+    unsigned char *open;       // [num] 1: hull vertex, the ring is a chain from its clockwise end to its counter-clockwise end
+};
+
+// Apex of the Delaunay triangle on one side (side = +1: left, -1: right) of the edge from point ip to point in_:
+// the point x of that side with the smallest t = x.(x - e) / (2 side cross(e, x)) (positions relative to ip; the circle
+// through ip, in_, x has its centre at e/2 + t * side-normal(e)).  -1: no point on that side (a hull edge); -2: not
+// settled within GI_RQ_DT rings of cells (a hull edge or a sliver beside the hull: the warp kernel takes the vertex).
+#define GI_RQ_DT 24
+PXF_DEV int apex_of_edge(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
+                         const int *__restrict__ start, int ip, int in_, double side, int rq_dt)
+{
+    const double px = sx[ip], py = sy[ip];
+    const double ex = sx[in_] - px, ey = sy[in_] - py;
+    const double e2 = ex * ex + ey * ey;
+    int cx, cy;
+    cell_of(g, px, py, cx, cy);
+    const int rcap = g.gx > g.gy ? g.gx : g.gy;
+    double tbest = __longlong_as_double(0x7ff0000000000000ll), r2best = tbest;
+    int best = -1;
+    bool settled = false;
+    for (int r = 0; r <= rcap && r <= rq_dt; r++) {
+        for (int j = cy - r; j <= cy + r; j++) {
+            if (j < 0 || j >= g.gy) continue;
+            const bool edge_row = j == cy - r || j == cy + r;
+            for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
+                if (i < 0 || i >= g.gx) continue;
+                const int c = j * g.gx + i;
+                for (int q = start[c]; q < start[c + 1]; q++) {
+                    if (q == ip || q == in_) continue;
+                    const double x = sx[q] - px, y = sy[q] - py;
+                    const double cr = side * (ex * y - ey * x);
+                    if (!(cr > 1e-14 * sqrt(e2 * (x * x + y * y)))) continue;
+                    const double t = (x * (x - ex) + y * (y - ey)) / (2. * cr);
+                    if (t < tbest || (t == tbest && q < best)) { tbest = t; best = q; r2best = e2 * (.25 + t * t); }
+                }
+            }
+        }
+        if (best >= 0) {
+            // any better apex lies inside the best circle so far, i.e. within its diameter of ip
+            const double clr = ring_clearance(g, px, py, cx, cy, r);
+            if (clr * clr > 4. * r2best) { settled = true; break; }
+        }
+        if (r == rcap) settled = true;
+    }
+    return settled ? best : -2;
+}
+
+// the same by the 32 lanes of a warp over ALL points (every lane returns the result)
+PXF_DEV int apex_of_edge_warp(const double *__restrict__ sx, const double *__restrict__ sy, int np, int ip, int in_, double side)
+{
+    const int lane = threadIdx.x & 31;
+    const double px = sx[ip], py = sy[ip];
+    const double ex = sx[in_] - px, ey = sy[in_] - py;
+    const double e2 = ex * ex + ey * ey;
+    double tbest = __longlong_as_double(0x7ff0000000000000ll);
+    int best = -1;
+    for (int q = lane; q < np; q += 32) {
+        if (q == ip || q == in_) continue;
+        const double x = sx[q] - px, y = sy[q] - py;
+        const double cr = side * (ex * y - ey * x);
+        if (!(cr > 1e-14 * sqrt(e2 * (x * x + y * y)))) continue;
+        const double t = (x * (x - ex) + y * (y - ey)) / (2. * cr);
+        if (t < tbest || (t == tbest && q < best)) { tbest = t; best = q; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ot = __shfl_xor_sync(0xffffffffu, tbest, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ob >= 0 && (best < 0 || ot < tbest || (ot == tbest && ob < best))) { tbest = ot; best = ob; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(GI_THREADS)
+k_dt_rings(const double *__restrict__ sx, const double *__restrict__ sy, const int *__restrict__ start,
+           const GridCells *__restrict__ gp, int num, Rings R, unsigned long long *__restrict__ nfail,
+           unsigned *__restrict__ slow, int rq_dt)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= num) return;
+    const GridCells &g = *gp;
+    const double px = sx[ip], py = sy[ip];
+    int cx, cy;
+    cell_of(g, px, py, cx, cy);
+    const int rcap = g.gx > g.gy ? g.gx : g.gy;
+    // the nearest neighbour
+    double best = __longlong_as_double(0x7ff0000000000000ll);
+    int n0 = -1;
+    for (int r = 0; r <= rcap; r++) {
+        for (int j = cy - r; j <= cy + r; j++) {
+            if (j < 0 || j >= g.gy) continue;
+            const bool edge_row = j == cy - r || j == cy + r;
+            for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
+                if (i < 0 || i >= g.gx) continue;
+                const int c = j * g.gx + i;
+                for (int q = start[c]; q < start[c + 1]; q++) {
+                    if (q == ip) continue;
+                    const double x = sx[q] - px, y = sy[q] - py, d2 = x * x + y * y;
+                    if (d2 < best || (d2 == best && q < n0)) { best = d2; n0 = q; }
+                }
+            }
+        }
+        const double clr = ring_clearance(g, px, py, cx, cy, r);
+        if (clr * clr > best) break;
+    }
+    int ccw[GI_DEG], cw[GI_DEG];
+    int nccw = 0, ncw = 0;
+    bool ok = n0 >= 0 && best > 0., open = false, defer = false;
+    if (ok) {
+        ccw[nccw++] = n0;
+        for (int cur = n0;;) {
+            const int d = apex_of_edge(g, sx, sy, start, ip, cur, 1., rq_dt);
+            if (d == -2) { defer = true; break; }
+            if (d < 0) { open = true; break; }
+            if (d == n0) break;
+            if (nccw >= GI_DEG) { ok = false; break; }
+            ccw[nccw++] = d;
+            cur = d;
+        }
+        if (ok && open && !defer)
+            for (int cur = n0;;) {
+                const int d = apex_of_edge(g, sx, sy, start, ip, cur, -1., rq_dt);
+                if (d == -2) { defer = true; break; }
+                if (d < 0) break;
+                if (nccw + ncw >= GI_DEG) { ok = false; break; }
+                cw[ncw++] = d;
+                cur = d;
+            }
+    }
+    if (!ok) { R.deg[ip] = 0; R.open[ip] = 1; atomicAdd(nfail, 1ull); atomicAdd(nfail + 2, 1ull); return; }
+    if (defer) { R.deg[ip] = 0; slow[1 + atomicAdd(slow, 1u)] = (unsigned)ip; return; }
+    int *out = R.ring + (size_t)ip * GI_DEG;
+    for (int k = 0; k < ncw; k++) out[k] = cw[ncw - 1 - k];
+    for (int k = 0; k < nccw; k++) out[ncw + k] = ccw[k];
+    R.deg[ip] = (unsigned char)(ncw + nccw);
+    R.open[ip] = open ? 1 : 0;
+}
+
+// One warp per deferred vertex (beside the hull): the same gift wrapping with every apex taken over all points.
+__global__ void __launch_bounds__(GI_THREADS)
+k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, int num, Rings R,
+                unsigned long long *__restrict__ nfail, const unsigned *__restrict__ slow)
+{
+    const unsigned nslow = slow[0];
+    const int lane = threadIdx.x & 31;
+    const unsigned wpb = blockDim.x >> 5;
+    for (unsigned w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nslow; w += gridDim.x * wpb) {
+        const int ip = (int)slow[1 + w];
+        const double px = sx[ip], py = sy[ip];
+        double best = __longlong_as_double(0x7ff0000000000000ll);
+        int n0 = -1;
+        for (int q = lane; q < num; q += 32) {
+            if (q == ip) continue;
+            const double x = sx[q] - px, y = sy[q] - py, d2 = x * x + y * y;
+            if (d2 < best || (d2 == best && q < n0)) { best = d2; n0 = q; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best, o);
+            const int on = __shfl_xor_sync(0xffffffffu, n0, o);
+            if (on >= 0 && (n0 < 0 || od < best || (od == best && on < n0))) { best = od; n0 = on; }
+        }
+        int *out = R.ring + (size_t)ip * GI_DEG;       // assembled in place: clockwise part reversed at the end
+        int nccw = 0, ncw = 0;
+        bool ok = n0 >= 0 && best > 0., open = false;
+        int cwbuf[GI_DEG];
+        if (ok) {
+            if (lane == 0) out[0] = n0;
+            nccw = 1;
+            for (int cur = n0;;) {
+                const int d = apex_of_edge_warp(sx, sy, num, ip, cur, 1.);
+                if (d < 0) { open = true; break; }
+                if (d == n0) break;
+                if (nccw >= GI_DEG) { ok = false; break; }
+                if (lane == 0) out[nccw] = d;
+                nccw++;
+                cur = d;
+            }
+            if (ok && open)
+                for (int cur = n0;;) {
+                    const int d = apex_of_edge_warp(sx, sy, num, ip, cur, -1.);
+                    if (d < 0) break;
+                    if (nccw + ncw >= GI_DEG) { ok = false; break; }
+                    cwbuf[ncw++] = d;
+                    cur = d;
+                }
+        }
+        if (lane == 0) {
+            if (!ok) { R.deg[ip] = 0; R.open[ip] = 1; atomicAdd(nfail, 1ull); atomicAdd(nfail + 2, 1ull); }
+            else {
+                // shift the counter-clockwise part up and put the clockwise part, reversed, in front
+                for (int k = nccw - 1; k >= 0; k--) out[ncw + k] = out[k];
+                for (int k = 0; k < ncw; k++) out[k] = cwbuf[ncw - 1 - k];
+                R.deg[ip] = (unsigned char)(ncw + nccw);
+                R.open[ip] = open ? 1 : 0;
+            }
+        }
+    }
+}
+
+// rings in the caller's point numbering: row orig[i] of the output holds the neighbours of sorted point i
+__global__ void __launch_bounds__(256)
+k_rings_export(const Rings R, const long long *__restrict__ orig, int num, int *__restrict__ ring_out,
+               unsigned char *__restrict__ deg_out, unsigned char *__restrict__ open_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num) return;
+    const long long o = orig[i];
+    const int *ring = R.ring + (size_t)i * GI_DEG;
+    for (int k = 0; k < GI_DEG; k++) ring_out[o * GI_DEG + k] = k < R.deg[i] ? (int)orig[ring[k]] : -1;
+    deg_out[o] = R.deg[i];
+    open_out[o] = R.open[i];
+}
+
+// one relaxation of level[i] = 1 + max{ level[j] : j a neighbour that comes before i in the input }
+__global__ void __launch_bounds__(256)
+k_gs_levels(const Rings R, const long long *__restrict__ orig, int num, int *__restrict__ level, int *__restrict__ changed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num) return;
+    const long long oi = orig[i];
+    int L = 0;
+    const int *ring = R.ring + (size_t)i * GI_DEG;
+    for (int k = 0; k < R.deg[i]; k++) {
+        const int j = ring[k];
+        if (orig[j] < oi) { const int lj = level[j] + 1; L = lj > L ? lj : L; }
+    }
+    // (changed[1]: the highest level so far -- one launch can raise a chain of vertices by several levels)
+    if (L > level[i]) { level[i] = L; changed[0] = 1; atomicMax(changed + 1, L); }
+}
+
+// One Gauss-Seidel update of the vertices of level `lv` (scipy _estimate_gradients_2d_global, the body of its loop over
+// points).  err: the sweep's largest relative change, as the bits of a non-negative double.
+__global__ void __launch_bounds__(256)
+k_gs_update(const Rings R, const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
+            const int *__restrict__ level, int lv, int num, double *__restrict__ grad, unsigned long long *__restrict__ err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num || level[i] != lv) return;
+    double Q0 = 0., Q1 = 0., Q3 = 0., s0 = 0., s1 = 0.;
+    const int *ring = R.ring + (size_t)i * GI_DEG;
+    const double f1 = sv[i], px = sx[i], py = sy[i];
+    for (int k = 0; k < R.deg[i]; k++) {
+        const int j = ring[k];
+        const double ex = sx[j] - px, ey = sy[j] - py;
+        const double L = sqrt(ex * ex + ey * ey), L3 = L * L * L;
+        const double f2 = sv[j];
+        const double df2 = -ex * grad[2 * j] - ey * grad[2 * j + 1];
+        Q0 += 4 * ex * ex / L3; Q1 += 4 * ex * ey / L3; Q3 += 4 * ey * ey / L3;
+        s0 += (6 * (f1 - f2) - 2 * df2) * ex / L3;
+        s1 += (6 * (f1 - f2) - 2 * df2) * ey / L3;
+    }
+    const double det = Q0 * Q3 - Q1 * Q1;
+    const double r0 = (Q3 * s0 - Q1 * s1) / det, r1 = (-Q1 * s0 + Q0 * s1) / det;
+    double change = fmax(fabs(grad[2 * i] + r0), fabs(grad[2 * i + 1] + r1));
+    grad[2 * i] = -r0; grad[2 * i + 1] = -r1;
+    change /= fmax(1., fmax(fabs(r0), fabs(r1)));
+    if (change == change) atomicMax(err, (unsigned long long)__double_as_longlong(change));
+    else atomicMax(err, 0x7ff0000000000000ull);
+}
+
+// the third vertex of the triangle across the edge u -> v of a counter-clockwise triangle (u, v, w): the neighbour that
+// precedes v counter-clockwise about u.  -1: a hull edge.
+PXF_DEV int across_edge(const Rings &R, int u, int v)
+{
+    const int *ring = R.ring + (size_t)u * GI_DEG;
+    const int deg = R.deg[u];
+    for (int k = 0; k < deg; k++)
+        if (ring[k] == v) {
+            if (k > 0) return ring[k - 1];
+            return R.open[u] ? -1 : ring[deg - 1];
+        }
+    return -2;      // v is not a neighbour of u: the rings and the triangle search disagree
+}
+
+// scipy _clough_tocher_2d_single on the counter-clockwise triangle (i0, i1, i2) holding the query; b: its barycentric
+// coordinates.  Returns false when the rings do not know an edge of the triangle.
+PXF_DEV bool clough_tocher(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
+                           const double *__restrict__ grad, const Rings &R, int i0, int i1, int i2, const double b[3],
+                           double *res)
+{
+    const int v[3] = {i0, i1, i2};
+    const double X0 = sx[i0], Y0 = sy[i0], X1 = sx[i1], Y1 = sy[i1], X2 = sx[i2], Y2 = sy[i2];
+    const double e12x = X1 - X0, e12y = Y1 - Y0, e23x = X2 - X1, e23y = Y2 - Y1, e31x = X0 - X2, e31y = Y0 - Y2;
+    const double f1 = sv[i0], f2 = sv[i1], f3 = sv[i2];
+    const double df12 = +(grad[2 * i0] * e12x + grad[2 * i0 + 1] * e12y), df21 = -(grad[2 * i1] * e12x + grad[2 * i1 + 1] * e12y);
+    const double df23 = +(grad[2 * i1] * e23x + grad[2 * i1 + 1] * e23y), df32 = -(grad[2 * i2] * e23x + grad[2 * i2 + 1] * e23y);
+    const double df31 = +(grad[2 * i2] * e31x + grad[2 * i2 + 1] * e31y), df13 = -(grad[2 * i0] * e31x + grad[2 * i0 + 1] * e31y);
+    const double c3000 = f1, c2100 = (df12 + 3 * c3000) / 3, c2010 = (df13 + 3 * c3000) / 3;
+    const double c0300 = f2, c1200 = (df21 + 3 * c0300) / 3, c0210 = (df23 + 3 * c0300) / 3;
+    const double c0030 = f3, c1020 = (df31 + 3 * c0030) / 3, c0120 = (df32 + 3 * c0030) / 3;
+    const double c2001 = (c2100 + c2010 + c3000) / 3, c0201 = (c1200 + c0300 + c0210) / 3, c0021 = (c1020 + c0120 + c0030) / 3;
+    // the gradient of the spline towards the neighbouring triangle's centroid is linear along each edge
+    const double area = orient2(X0, Y0, X1, Y1, X2, Y2);
+    double gk[3];
+    for (int k = 0; k < 3; k++) {
+        // neighbour opposite vertex k: across the edge v[k+1] -> v[k+2]
+        const int u = v[(k + 1) % 3], w = v[(k + 2) % 3];
+        const int d = across_edge(R, u, w);
+        if (d == -2) return false;
+        if (d < 0) { gk[k] = -.5; continue; }
+        const double yx = (sx[u] + sx[w] + sx[d]) / 3, yy = (sy[u] + sy[w] + sy[d]) / 3;
+        double c[3];
+        c[0] = orient2(yx, yy, X1, Y1, X2, Y2) / area;
+        c[1] = orient2(X0, Y0, yx, yy, X2, Y2) / area;
+        c[2] = 1. - c[0] - c[1];
+        if (k == 0) gk[k] = (2 * c[2] + c[1] - 1) / (2 - 3 * c[2] - 3 * c[1]);
+        else if (k == 1) gk[k] = (2 * c[0] + c[2] - 1) / (2 - 3 * c[0] - 3 * c[2]);
+        else gk[k] = (2 * c[1] + c[0] - 1) / (2 - 3 * c[1] - 3 * c[0]);
+    }
+    const double c0111 = (gk[0] * (-c0300 + 3 * c0210 - 3 * c0120 + c0030) + (-c0300 + 2 * c0210 - c0120 + c0021 + c0201)) / 2;
+    const double c1011 = (gk[1] * (-c0030 + 3 * c1020 - 3 * c2010 + c3000) + (-c0030 + 2 * c1020 - c2010 + c2001 + c0021)) / 2;
+    const double c1101 = (gk[2] * (-c3000 + 3 * c2100 - 3 * c1200 + c0300) + (-c3000 + 2 * c2100 - c1200 + c2001 + c0201)) / 2;
+    const double c1002 = (c1101 + c1011 + c2001) / 3, c0102 = (c1101 + c0111 + c0201) / 3, c0012 = (c1011 + c0111 + c0021) / 3;
+    const double c0003 = (c1002 + c0102 + c0012) / 3;
+    // extended barycentric coordinates
+    const double mn = fmin(b[0], fmin(b[1], b[2]));
+    const double b1 = b[0] - mn, b2 = b[1] - mn, b3 = b[2] - mn, b4 = 3 * mn;
+    *res = b1 * b1 * b1 * c3000 + 3 * b1 * b1 * b2 * c2100 + 3 * b1 * b1 * b3 * c2010 + 3 * b1 * b1 * b4 * c2001 +
+           3 * b1 * b2 * b2 * c1200 + 6 * b1 * b2 * b4 * c1101 + 3 * b1 * b3 * b3 * c1020 + 6 * b1 * b3 * b4 * c1011 +
+           3 * b1 * b4 * b4 * c1002 + b2 * b2 * b2 * c0300 + 3 * b2 * b2 * b3 * c0210 + 3 * b2 * b2 * b4 * c0201 +
+           3 * b2 * b3 * b3 * c0120 + 6 * b2 * b3 * b4 * c0111 + 3 * b2 * b4 * b4 * c0102 + b3 * b3 * b3 * c0030 +
+           3 * b3 * b3 * b4 * c0021 + 3 * b3 * b4 * b4 * c0012 + b4 * b4 * b4 * c0003;
+    return true;
+}
+
+struct Cubic { const double *grad; Rings R; };     // grad == nullptr: linear
+
 #define GI_RQ 12               // rings searched for the quadrant points before a query is handed to the warp kernel
 #define GI_CELL_BUDGET 4096    // cells under one circumcircle a single thread may scan
 
@@ -189,7 +535,7 @@ PXF_DEV double incircle(double ax, double ay, double bx, double by, double cx, d
 template <bool COOP>
 PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
                                    const double *__restrict__ sv, const int *__restrict__ start, double qx, double qy,
-                                   int ia, int ib, int ic, double *res)
+                                   int ia, int ib, int ic, double *res, const Cubic &cub)
 {
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const int lane = COOP ? (threadIdx.x & 31) : 0;
@@ -252,6 +598,11 @@ PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict_
     // 4. barycentric coordinates of q (the origin): areas of the sub-triangles
     const double area = orient2(ax, ay, bx, by, cx_, cy_);
     const double oab = ax * by - ay * bx, obc = bx * cy_ - by * cx_, oca = cx_ * ay - cy_ * ax;
+    if (cub.grad) {
+        const double bb[3] = {obc / area, oca / area, oab / area};
+        if (COOP && lane != 0) return 0;
+        return clough_tocher(sx, sy, sv, cub.grad, cub.R, ia, ib, ic, bb, res) ? 0 : 2;
+    }
     *res = obc / area * sv[ia] + oca / area * sv[ib] + oab / area * sv[ic];
     return 0;
 }
@@ -263,7 +614,7 @@ __global__ void __launch_bounds__(GI_THREADS)
 k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
            const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
            const double *__restrict__ qys, int64_t nq, double *__restrict__ out, unsigned long long *__restrict__ nfail,
-           unsigned *__restrict__ slow)
+           unsigned *__restrict__ slow, const Cubic cub)
 {
     const int64_t iq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (iq >= nq) return;
@@ -348,7 +699,7 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
     }
     int rc = 1;
     double val = nanv;
-    if (ia >= 0) rc = settle_and_interpolate<false>(g, sx, sy, sv, start, qx, qy, ia, ib, ic, &val);
+    if (ia >= 0) rc = settle_and_interpolate<false>(g, sx, sy, sv, start, qx, qy, ia, ib, ic, &val, cub);
     if (rc == 1) {
         out[iq] = nanv;
         slow[1 + atomicAdd(slow, 1u)] = (unsigned)iq;
@@ -366,7 +717,7 @@ __global__ void __launch_bounds__(GI_THREADS)
 k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
                 const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
                 const double *__restrict__ qys, double *__restrict__ out, unsigned long long *__restrict__ nfail,
-                const unsigned *__restrict__ slow)
+                const unsigned *__restrict__ slow, const Cubic cub)
 {
     const GridCells &g = *gp;
     const unsigned nslow = slow[0];
@@ -405,7 +756,8 @@ k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
         // b counter-clockwise to c through the far side is less than pi  <=>  c is counter-clockwise of b
         if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { if (lane == 0) out[iq] = nanv; continue; }
         double val = nanv;
-        const int rc = settle_and_interpolate<true>(g, sx, sy, sv, start, qx, qy, 0, jb, jc, &val);
+        int rc = settle_and_interpolate<true>(g, sx, sy, sv, start, qx, qy, 0, jb, jc, &val, cub);
+        rc = __shfl_sync(0xffffffffu, rc, 0);
         if (lane == 0) {
             out[iq] = val;
             if (rc) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
@@ -455,7 +807,8 @@ size_t pxf_griddata_scratch_bytes(int64_t num)
     size_t cells = n / 2 + 2;
     if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
     return 5 * a256(n * 8) + a256(n * 8) + a256((cells + 2) * 4) + a256(GI_BBOX_BLOCKS * 4 * 8) + a256(sizeof(GridCells)) + 256 +
-           GI_SLOW_CAP_BYTES +
+           GI_SLOW_CAP_BYTES + /* cubic: rings, degrees, levels, gradients */ a256(n * GI_DEG * 4) + 2 * a256(n) + a256(n * 4) +
+           a256(n * 16) + 256 +
            a256(GI_NDIR * GI_DIR_SLICES * 8) +
            pxf_sort_scratch_bytes(num) + 1024;
 }
@@ -463,7 +816,7 @@ size_t pxf_griddata_scratch_bytes(int64_t num)
 int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
                  double *out, int64_t nq, int32_t method, int64_t *nfail_host, void *scratch, pxf_stream_t stream)
 {
-    if (num < 0 || nq < 0 || !x || !y || !v || !scratch || (nq > 0 && (!qx || !qy || !out)) || method < 0 || method > 1 ||
+    if (num < 0 || nq < 0 || !x || !y || !v || !scratch || (nq > 0 && (!qx || !qy || !out)) || method < 0 || method > 2 ||
         num > 0x7fffffffll) {
         set_error("pxf_griddata: bad argument");
         return PXF_ERR_INVALID;
@@ -471,7 +824,7 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     if (nfail_host) *nfail_host = 0;
     if (nq == 0) return PXF_OK;
-    if (num < (method == 1 ? 3 : 1)) { set_error("pxf_griddata: needs at least %d points", method == 1 ? 3 : 1); return PXF_ERR_INVALID; }
+    if (num < (method >= 1 ? 3 : 1)) { set_error("pxf_griddata: needs at least %d points", method >= 1 ? 3 : 1); return PXF_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const size_t n = (size_t)num;
     size_t cells = n / 2 + 2;
@@ -489,6 +842,13 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     unsigned long long *nfail = (unsigned long long *)p; p += 256;
     double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
     unsigned *slow = (unsigned *)p; p += GI_SLOW_CAP_BYTES;
+    Rings R;
+    R.ring = (int *)p; p += a256(n * GI_DEG * 4);
+    R.deg = (unsigned char *)p; p += a256(n);
+    R.open = (unsigned char *)p; p += a256(n);
+    int *level = (int *)p; p += a256(n * 4);
+    double *grad = (double *)p; p += a256(n * 16);
+    int *flag = (int *)p; p += 256;          // [0]: levels changed; [2..3]: the sweep's error
     void *sort_scr = p;
     const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
     PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
@@ -502,17 +862,70 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     if (rc) return rc;
     k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, v, start, sx, sy, sv);
     count_launch();
+    Cubic cub;
+    cub.grad = nullptr; cub.R = R;
+    if (method == 2) {
+        // (a) the Delaunay neighbour rings
+        if (n > (size_t)GI_QUERY_BATCH) { set_error("pxf_griddata: 'cubic' takes at most %d points", GI_QUERY_BATCH); return PXF_ERR_UNSUPPORTED; }
+        PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
+        int rq_dt = GI_RQ_DT;
+        if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
+        k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow,
+                                                                                           rq_dt);
+        k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, (int)num, R, nfail, slow);
+        count_launch(2);
+        unsigned long long hf[4] = {0, 0, 0, 0};
+        PXF_CUDA(cudaMemcpyAsync(hf, nfail, 32, cudaMemcpyDeviceToHost, s));
+        PXF_CUDA(cudaStreamSynchronize(s));
+        if (hf[0]) {
+            set_error("pxf_griddata: %llu points have no Delaunay neighbour ring (duplicate points, or more than %d neighbours)",
+                      hf[0], GI_DEG);
+            if (nfail_host) *nfail_host = (int64_t)hf[0];
+            return PXF_ERR_UNSUPPORTED;
+        }
+        // (b) levels of the input-order Gauss-Seidel sweep, then the sweeps (scipy: maxiter 400, tol 1e-6)
+        const unsigned vb = (unsigned)((num + 255) / 256);
+        PXF_CUDA(cudaMemsetAsync(level, 0, n * 4, s));
+        PXF_CUDA(cudaMemsetAsync(grad, 0, n * 16, s));
+        int nlev = 0;
+        PXF_CUDA(cudaMemsetAsync(flag, 0, 8, s));
+        for (int it = 0;; it++) {
+            if (it > 1 << 20) { set_error("pxf_griddata: the Gauss-Seidel levels did not settle"); return PXF_ERR_UNSUPPORTED; }
+            int h[2] = {0, 0};
+            PXF_CUDA(cudaMemsetAsync(flag, 0, 4, s));
+            k_gs_levels<<<vb, 256, 0, s>>>(R, perm, (int)num, level, flag);
+            count_launch();
+            PXF_CUDA(cudaMemcpyAsync(h, flag, 8, cudaMemcpyDeviceToHost, s));
+            PXF_CUDA(cudaStreamSynchronize(s));
+            nlev = h[1];                       // the highest level assigned
+            if (!h[0]) break;
+        }
+        if (nlev > 65536) { set_error("pxf_griddata: the input order gives %d Gauss-Seidel levels", nlev); return PXF_ERR_UNSUPPORTED; }
+        unsigned long long *err = reinterpret_cast<unsigned long long *>(flag + 2);
+        for (int sweep = 0; sweep < 400; sweep++) {
+            PXF_CUDA(cudaMemsetAsync(err, 0, 8, s));
+            for (int lv = 0; lv <= nlev; lv++) k_gs_update<<<vb, 256, 0, s>>>(R, sx, sy, sv, level, lv, (int)num, grad, err);
+            count_launch(nlev + 1);
+            unsigned long long he = 0;
+            PXF_CUDA(cudaMemcpyAsync(&he, err, 8, cudaMemcpyDeviceToHost, s));
+            PXF_CUDA(cudaStreamSynchronize(s));
+            double e;
+            memcpy(&e, &he, 8);
+            if (e < 1e-6) break;
+        }
+        cub.grad = grad;
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += GI_QUERY_BATCH) {
         const int64_t nb_q = nq - q0 < GI_QUERY_BATCH ? nq - q0 : GI_QUERY_BATCH;
         const unsigned qb = (unsigned)((nb_q + GI_THREADS - 1) / GI_THREADS);
         if (method == 0) {
-            k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow);
+            k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow, cub);
             count_launch();
             continue;
         }
         PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
-        k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow);
-        k_griddata_warp<<<grid_for(nb_q, 1, 8), GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, out + q0, nfail, slow);
+        k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow, cub);
+        k_griddata_warp<<<grid_for(nb_q, 1, 8), GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, out + q0, nfail, slow, cub);
         count_launch(2);
     }
     if ((rc = check_launch("pxf_griddata"))) return rc;
@@ -571,6 +984,67 @@ int pxf_nanmedian2(const double *a, const double *b, int64_t num, double *out, p
     k_nanmedian2<<<grid_for(num, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, num, out);
     count_launch();
     return check_launch("k_nanmedian2");
+}
+
+int pxf_delaunay_max_degree(void) { return GI_DEG; }
+
+int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_t *ring_out, uint8_t *deg_out,
+                           uint8_t *open_out, void *scratch, pxf_stream_t stream)
+{
+    if (num < 3 || !x || !y || !ring_out || !deg_out || !open_out || !scratch || num > (int64_t)GI_QUERY_BATCH) {
+        set_error("pxf_delaunay_neighbors: bad argument");
+        return PXF_ERR_INVALID;
+    }
+    if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)num;
+    size_t cells = n / 2 + 2;
+    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
+    char *p = static_cast<char *>(scratch);
+    double *key = (double *)p; p += a256(n * 8);
+    double *skey = (double *)p; p += a256(n * 8);
+    long long *perm = (long long *)p; p += a256(n * 8);
+    double *sx = (double *)p; p += a256(n * 8);
+    double *sy = (double *)p; p += a256(n * 8);
+    double *sv = (double *)p; p += a256(n * 8);
+    int *start = (int *)p; p += a256((cells + 2) * 4);
+    double *part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
+    GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
+    unsigned long long *nfail = (unsigned long long *)p; p += 256;
+    double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
+    unsigned *slow = (unsigned *)p; p += GI_SLOW_CAP_BYTES;
+    Rings R;
+    R.ring = (int *)p; p += a256(n * GI_DEG * 4);
+    R.deg = (unsigned char *)p; p += a256(n);
+    R.open = (unsigned char *)p; p += a256(n);
+    p += a256(n * 4) + a256(n * 16) + 256;
+    void *sort_scr = p;
+    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
+    PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
+    PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
+    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
+    k_support_partial<<<GI_NDIR * GI_DIR_SLICES, 256, 0, s>>>(x, y, num, spart);
+    k_grid_setup<<<1, 64, 0, s>>>(part, nb, num, (int)(cells - 2), g, spart);
+    k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, g, key);
+    count_launch(4);
+    int rc = pxf_argsort(key, num, skey, reinterpret_cast<int64_t *>(perm), sort_scr, stream);
+    if (rc) return rc;
+    k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, x, start, sx, sy, sv);
+    int rq_dt = GI_RQ_DT;
+    if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);
+    k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow, rq_dt);
+    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, (int)num, R, nfail, slow);
+    k_rings_export<<<(unsigned)((num + 255) / 256), 256, 0, s>>>(R, perm, (int)num, ring_out, deg_out, open_out);
+    count_launch(4);
+    if ((rc = check_launch("pxf_delaunay_neighbors"))) return rc;
+    unsigned long long hf[4] = {0, 0, 0, 0};
+    PXF_CUDA(cudaMemcpyAsync(hf, nfail, 32, cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    if (hf[0]) {
+        set_error("pxf_delaunay_neighbors: %llu points have no neighbour ring (duplicate points, or more than %d neighbours)", hf[0], GI_DEG);
+        return PXF_ERR_UNSUPPORTED;
+    }
+    return PXF_OK;
 }
 
 }  // extern "C"

@@ -85,8 +85,23 @@ def test_interpolatevec_linear_and_nearest(pxf, name):
     want, _, _ = refapi.interpolateVec(copy(rays), 1, 33, 21, xr=xr, yr=yr, interpVec=vec)
     got, _, _ = pxf.analyses.interpolateVec(dev, 1, 33, 21, xr=xr, yr=yr, interpVec=vec)
     compare(got, want, np.abs(vec).max(), name + " xr/yr/interpVec")
-    with pytest.raises(NotImplementedError):
-        pxf.analyses.interpolateVec(dev, 4, 8, 8, method="cubic")
+    with pytest.raises(ValueError):
+        pxf.analyses.interpolateVec(dev, 4, 8, 8, method="quintic")
+
+
+@pytest.mark.parametrize("name", ["square", "annulus_sector", "disc", "clustered", "tiny"])
+def test_interpolatevec_cubic(pxf, name):
+    """method='cubic': scipy's Clough-Tocher interpolant.  Its vertex gradients are Gauss-Seidel sweeps in input order to
+    a relative change of 1e-6; the device runs the same sweeps level by level, so the maps agree to rounding (1e-9 of
+    the data's scale leaves room for the different order of the neighbour sums), not merely to the 1e-6 tolerance."""
+    x, y = footprints()[name]
+    rays = bundle(x, y, 9)
+    dev = to_dev(rays)
+    Nx, Ny = (64, 48) if name != "tiny" else (9, 7)
+    for I in (4, 5):
+        want, _, _ = refapi.interpolateVec(copy(rays), I, Nx, Ny, method="cubic")
+        got, _, _ = pxf.analyses.interpolateVec(dev, I, Nx, Ny, method="cubic")
+        assert compare(got, want, np.abs(rays[I]).max(), "%s I=%d cubic" % (name, I), tol=1e-9) > 0
 
 
 @pytest.mark.parametrize("name", ["annulus_sector", "disc"])
@@ -134,5 +149,37 @@ def test_interpolatevec_on_a_traced_bundle_and_wavefront(pxf):
     # the reconstruction amplifies slope differences of 1e-16 through a few hundred SOR sweeps
     compare(pg, pw, np.nanmax(np.abs(pw)), "wavefront phase", tol=1e-8)
     assert np.isfinite(pg).sum() > 100
-    with pytest.raises(NotImplementedError):
-        pxf.analyses.wavefront(dev, 30, 24)                       # the default 'cubic' is not built
+    # the default method ('cubic') on a filled footprint
+    x, y = footprints()["disc"]
+    rays = bundle(x, y, 11)
+    dev = to_dev(rays)
+    pw, xw, yw = refapi.wavefront(copy(rays), 40, 32, maxiter=3000)
+    pg, xg, yg = pxf.analyses.wavefront(dev, 40, 32, maxiter=3000)
+    compare(xg, xw, np.nanmax(np.abs(xw)), "wavefront (cubic) x slopes", tol=1e-9)
+    compare(yg, yw, np.nanmax(np.abs(yw)), "wavefront (cubic) y slopes", tol=1e-9)
+    compare(pg, pw, np.nanmax(np.abs(pw)), "wavefront (cubic) phase", tol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["square", "annulus_sector", "disc", "clustered", "tiny"])
+def test_delaunay_neighbor_rings(pxf, name):
+    """The gift-wrapped neighbour rings against Qhull's triangulation: same neighbour SETS for every vertex, hull flags
+    equal, and each ring counter-clockwise."""
+    import torch
+    from scipy.spatial import Delaunay
+    x, y = footprints()[name]
+    tri = Delaunay(np.column_stack([x, y]))
+    indptr, indices = tri.vertex_neighbor_vertices
+    ring, deg, hull = (t.cpu().numpy() for t in pxf.analyses.delaunay_neighbors(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()))
+    on_hull = np.zeros(x.size, dtype=bool)
+    on_hull[np.unique(tri.convex_hull)] = True
+    bad = 0
+    for i in range(x.size):
+        want = set(indices[indptr[i]:indptr[i + 1]].tolist())
+        got = ring[i, :deg[i]].tolist()
+        if set(got) != want or len(got) != len(want):
+            bad += 1
+            continue
+        ang = np.unwrap(np.arctan2(y[got] - y[i], x[got] - x[i]))
+        assert np.all(np.diff(ang) > 0), "ring of vertex %d is not counter-clockwise" % i
+    assert bad == 0, "%d of %d vertices have a different neighbour set" % (bad, x.size)
+    assert np.array_equal(hull.astype(bool), on_hull)
