@@ -84,6 +84,9 @@ int pxf_refract(double *l, double *m, double *n, double *ux, double *uy, double 
 /* transformations.pointTo (transformations.py:91-100): l,m,n = reverse*(r - p0)/|r - p0|. */
 int pxf_pointto(const double *x, const double *y, const double *z, double *l, double *m, double *n, int64_t num,
                 double x0, double y0, double z0, double reverse, const uint8_t *mask, pxf_stream_t stream);
+/* analyses.measureOPD (analyses.py:232-244): dist[i] = |r_i - p0|. */
+int pxf_distance(const double *x, const double *y, const double *z, double *dist, int64_t num, double x0, double y0, double z0,
+                 const uint8_t *mask, pxf_stream_t stream);
 /* transformations.applyT (transformations.py:257-280), in place: positions through the first three rows of the 4x4
  * point matrix, direction cosines and normals through those of the 4x4 rotation matrix (HOST row-major double[>=12],
  * i.e. coords[i+1] and coords[i]). */

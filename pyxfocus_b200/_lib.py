@@ -49,6 +49,7 @@ SIGNATURES = {
     "pxf_reflect": (_c.c_int, [_dp] * 6 + [_i64, _vp, _st]),
     "pxf_refract": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _vp, _st]),
     "pxf_pointto": (_c.c_int, [_dp] * 6 + [_i64, _d, _d, _d, _d, _vp, _st]),
+    "pxf_distance": (_c.c_int, [_dp] * 4 + [_i64, _d, _d, _d, _vp, _st]),
     "pxf_applyt": (_c.c_int, _NINE + [_i64, _vp, _vp, _st]),
     "pxf_indangle": (_c.c_int, [_dp] * 7 + [_i64, _vp, _vp, _st]),
     "pxf_radgrat": (_c.c_int, [_dp] * 5 + [_d, _i64, _d, _d, _vp, _st]),

@@ -277,6 +277,19 @@ def rmsPoint(rays, point, weights=None):
     return out.value
 
 
+def measureOPD(rays, point):
+    """Distance of every ray from a point -- a ten-row ray or an (x,y,z) triple (analyses.py:232-244); a device tensor."""
+    flush(rays)
+    off = 1 if len(point) == 10 else 0
+    px, py, pz = (float(point[off + k]) for k in range(3))
+    x, y, z = rays[1:4]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pxf_distance(x.data_ptr(), y.data_ptr(), z.data_ptr(), out.data_ptr(), x.shape[0], px, py, pz,
+                                           None, stream_ptr(x.device)))
+    return out
+
+
 def indAngle(rays, ind=None, normal=None):
     """Incidence angle against the current or a given surface normal (analyses.py:164-182); returns a
     device tensor (one pxf_indangle launch; ``ind`` -- bool mask or index array -- selects rays like numpy
@@ -422,4 +435,25 @@ def wavefront(rays, Nx, Ny, method='cubic', polar=False, maxiter=10000):
     xs[xs == 100] = np.nan
     ys[ys == 100] = np.nan
     return phase[1:-1, 1:-1], xs[1:-1, 1:-1], ys[1:-1, 1:-1]
+
+
+# ---- scalar set-up formulas of analyses.py that do not touch a ray bundle (host numpy, as in the reference) ----
+def radialGrad(x, y, hubscale, yaw, hubdist):
+    """x and y derivatives of a radial grating's phase function at the points (x, y) (analyses.py:402-428).  As in the
+    reference the hub shift is applied to the UNROTATED y (``y2 = y + hubdist``, :415)."""
+    x2 = x * np.cos(yaw) + y * np.sin(yaw)
+    y2 = y + hubdist
+    rho = np.sqrt(x2 ** 2 + y2 ** 2)
+    theta = np.arctan2(-x2, y2)
+    gx = hubscale * (np.cos(theta) / rho)
+    gy = -hubscale * (np.sin(theta) / rho)
+    return gx * np.cos(-yaw) + gy * np.sin(-yaw), -gx * np.sin(-yaw) + gy * np.cos(-yaw)
+
+
+def sellmeier(wave, B, C):
+    """Refractive index from Sellmeier coefficients, one value per wavelength (analyses.py:430-446)."""
+    w2 = np.reshape(wave, [np.size(wave), 1]) ** 2
+    B = np.reshape(B, [1, np.size(B)])
+    C = np.reshape(C, [1, np.size(C)])
+    return np.sqrt(1 + np.sum(np.dot(w2, B) / (w2 - C), axis=1))
 

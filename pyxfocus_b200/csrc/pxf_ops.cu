@@ -237,6 +237,17 @@ struct OpIndAngle {
         r.opd = acos(d);
     }
 };
+// analyses.measureOPD (analyses.py:232-244): distance of every ray from a point, written to the row in the opd slot
+struct OpDistance {
+    using Params = PointToP;
+    static constexpr unsigned LOAD = R_POS, STORE = R_OPD;
+    static constexpr int AUX = 0, SMEM = 0;
+    PXF_DEV static void apply(Ray &r, const Params &p, const double *, double, double)
+    {
+        const double dx = r.x - p.x0, dy = r.y - p.y0, dz = r.z - p.z0;
+        r.opd = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+};
 struct OpIndAngleFixed {
     using Params = IndAngleP;
     static constexpr unsigned LOAD = R_DIR, STORE = R_OPD;
@@ -693,6 +704,14 @@ int pxf_pointto(const double *x, const double *y, const double *z, double *l, do
     PointToP p{x0, y0, z0, reverse};
     return launch_op<OpPointTo>(rows9(const_cast<double *>(x), const_cast<double *>(y), const_cast<double *>(z), l, m, n,
                                       nullptr, nullptr, nullptr), num, mask, nullptr, nullptr, p, stream);
+}
+
+int pxf_distance(const double *x, const double *y, const double *z, double *dist, int64_t num, double x0, double y0, double z0,
+                 const uint8_t *mask, pxf_stream_t stream)
+{
+    PointToP p{x0, y0, z0, 0.};
+    return launch_op<OpDistance>(rows9(const_cast<double *>(x), const_cast<double *>(y), const_cast<double *>(z), nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, dist), num, mask, nullptr, nullptr, p, stream);
 }
 
 int pxf_applyt(double *x, double *y, double *z, double *l, double *m, double *n, double *ux, double *uy, double *uz,

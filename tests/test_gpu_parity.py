@@ -1552,6 +1552,10 @@ def test_pointto_applyt_indangle_kernels(pxf):
     got = A.indAngle(dev, ind=mask, normal=(0., .6, .8)).cpu().numpy()
     assert np.allclose(got, np.arccos(.6 * rays[5][mask] + .8 * rays[6][mask]), rtol=0, atol=1e-14)
     assert A.indAngle(dev, ind=np.zeros(5003, dtype=bool)).shape[0] == 0
+    # measureOPD (analyses.py:232-244): an (x,y,z) triple or a ten-row ray
+    want = np.sqrt((rays[1] - 3.) ** 2 + (rays[2] + 4.) ** 2 + (rays[3] - 8000.) ** 2)
+    assert np.array_equal(A.measureOPD(dev, (3., -4., 8000.)).cpu().numpy(), want)
+    assert np.array_equal(A.measureOPD(dev, [0., 3., -4., 8000., 0., 0., 1., 0., 0., 1.]).cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 3072, 3073, 100_000, 2_000_003])

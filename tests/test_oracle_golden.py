@@ -96,6 +96,13 @@ def test_restatement_matches_live_reference_python():
     a, b = copy(good), copy(good)
     assert pyref.focusI(a) == surf.focusI(b)
     assert_bit_equal(a, b, what="focusI")
+    # the two scalar set-up formulas of analyses.py
+    from pyxfocus_b200 import analyses as panal
+    xs, ys = np.linspace(-3., 4., 11), np.linspace(1., 9., 11)
+    for u, v in zip(panal.radialGrad(xs, ys, 2e-4, .03, 11832.), anal.radialGrad(xs, ys, 2e-4, .03, 11832.)):
+        assert np.array_equal(u, v)
+    assert np.array_equal(panal.sellmeier([.5, .6, .7], [1.03, .23, 1.01], [6e-3, 2e-2, 103.]),
+                          anal.sellmeier([.5, .6, .7], [1.03, .23, 1.01], [6e-3, 2e-2, 103.]))
     # the mirrored host-side helpers of the product package
     import importlib
     import sys
