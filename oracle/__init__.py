@@ -3,9 +3,12 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline
 legs may import this package.  ``pyxfocus_b200`` never does.
 
-Parity status: **unpinned** by the reference (it ships no tests or golden
-vectors and its Fortran cannot be compiled in the build container); see the
-header of ``pxf_oracle.c`` and DESIGN.md.
+Parity status: the reference ships no tests or golden vectors and its Fortran cannot be compiled
+in the build container (no Fortran compiler), so there is no ``oracle/_ref``.  The C restatement is
+pinned against the Fortran SOURCE TEXT instead: ``oracle.f95run`` executes the ``.f95`` files
+themselves (a translator with gfortran's arithmetic rules) and ``pxf_oracle.c`` reproduces every
+routine's output bit for bit (``tests/test_f95_source.py``); see the header of ``pxf_oracle.c`` and
+DESIGN.md.
 
 ``oracle.f2py`` exposes four namespaces named after the reference's f2py
 extension modules (``transformationsf``, ``surfacesf``, ``woltsurf``,

@@ -6,12 +6,20 @@
  * cpu_baseline / --impl reference legs).  The product path never links,
  * imports or executes anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no tests, golden
- * vectors or fixtures, and no Fortran compiler exists in the build container,
- * so the Fortran itself could not be run.  Every routine below follows the
- * cited .f95 lines statement by statement (evaluation order, implicit typing,
- * REAL*4 literals) and is pinned only by (a) physics known-answer checks
- * (tests/test_oracle_kat.py) and (b) golden vectors produced by the
+ * PARITY STATUS: pinned against the Fortran SOURCE TEXT, not against a compiled
+ * build of it.  The reference ships no tests, golden vectors or fixtures, and no
+ * Fortran compiler exists in the build container, so there is no oracle/_ref.
+ * Instead oracle/f95run.py EXECUTES the reference's .f95 files: a translator for
+ * the Fortran subset they use with gfortran's arithmetic rules (REAL*4 literals
+ * and implicit typing, kind promotion, truncating integer division, __powidf2
+ * powers, glibc libm, by-reference arguments).  tests/golden/make_f95_golden.py
+ * ran every subroutine of transformationsf / surfacesf / woltsurf / zernsurf /
+ * reconstruct (59 cases, on- and off-axis) through it and this file reproduces
+ * every output bit for bit (tests/test_f95_source.py; fixture
+ * tests/golden/f95_source.npz).  What that does NOT cover: a compiler-specific
+ * deviation of a real gfortran build from those rules (none is known for
+ * baseline x86-64 without -ffast-math).  Further pins: (a) physics known-answer
+ * checks (tests/test_oracle_kat.py) and (b) golden vectors produced by the
  * reference's own *Python* layer driving this file (tests/golden/).
  *
  * Conventions restated from the Fortran (all citations relative to the
