@@ -14,7 +14,7 @@
  * and implicit typing, kind promotion, truncating integer division, __powidf2
  * powers, glibc libm, by-reference arguments).  tests/golden/make_f95_golden.py
  * ran every subroutine of transformationsf / surfacesf / woltsurf / zernsurf /
- * reconstruct (59 cases, on- and off-axis) through it and this file reproduces
+ * reconstruct (57 cases, on- and off-axis) through it and this file reproduces
  * every output bit for bit (tests/test_f95_source.py; fixture
  * tests/golden/f95_source.npz).  What that does NOT cover: a compiler-specific
  * deviation of a real gfortran build from those rules (none is known for
