@@ -183,3 +183,29 @@ def test_delaunay_neighbor_rings(pxf, name):
         assert np.all(np.diff(ang) > 0), "ring of vertex %d is not counter-clockwise" % i
     assert bad == 0, "%d of %d vertices have a different neighbour set" % (bad, x.size)
     assert np.array_equal(hull.astype(bool), on_hull)
+
+
+def test_interpolatevec_cubic_polar_and_degenerate_inputs(pxf):
+    import torch
+    x, y = footprints()["disc"]
+    rays = bundle(x, y, 12)
+    dev = to_dev(rays)
+    want, _, _ = refapi.interpolateVec(copy(rays), 4, 30, 24, method="cubic", polar=True)
+    got, _, _ = pxf.analyses.interpolateVec(dev, 4, 30, 24, method="cubic", polar=True)
+    compare(got, want, np.abs(rays[4]).max(), "cubic polar", tol=1e-6)          # (chart coordinates: see the linear test)
+    # three points: one triangle
+    t = [torch.tensor(v, dtype=torch.float64).cuda() for v in ([0., 1., 0.], [0., 0., 1.], [1., 2., 3.])]
+    q = [torch.tensor(v, dtype=torch.float64).cuda() for v in ([.25, .9, .2], [.25, .9, .2])]
+    for method in ("linear", "cubic", "nearest"):
+        got = pxf.analyses.griddata(*t, *q, method=method).cpu().numpy()
+        want = scipy_interpolate.griddata((t[0].cpu().numpy(), t[1].cpu().numpy()), t[2].cpu().numpy(),
+                                          (q[0].cpu().numpy(), q[1].cpu().numpy()), method=method)
+        assert np.allclose(got, want, rtol=0, atol=1e-12, equal_nan=True), method
+    # collinear points have no triangulation (Qhull raises): every query is outside the (flat) hull here, never a hang
+    line = [torch.linspace(0, 1, 50, dtype=torch.float64).cuda() for _ in range(2)]
+    got = pxf.analyses.griddata(line[0], line[1], line[0], q[0], q[1] + .05, method="linear").cpu().numpy()
+    assert np.isnan(got).all()
+    # duplicate points: a loud error for the methods that need the triangulation
+    dup = [torch.tensor(v, dtype=torch.float64).cuda() for v in ([0., 1., 0., 1., .5, .5], [0., 0., 1., 1., .5, .5], [1., 2., 3., 4., 5., 5.])]
+    with pytest.raises(pxf.PxfError):
+        pxf.analyses.griddata(*dup, q[0], q[1], method="cubic")
