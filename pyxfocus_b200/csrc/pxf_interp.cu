@@ -791,7 +791,8 @@ k_nanmedian2(const double *__restrict__ a, const double *__restrict__ b, int64_t
 
 static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 #define GI_QUERY_BATCH (1 << 22)                          // queries per launch pair (bounds the deferred list)
-#define GI_SLOW_CAP_BYTES ((size_t)(GI_QUERY_BATCH + 64) * 4)
+// the deferred list holds query indices of one batch or, for 'cubic', vertex indices: sized for the larger
+static size_t slow_cap_bytes(size_t n) { return (((n > (size_t)GI_QUERY_BATCH ? n : (size_t)GI_QUERY_BATCH) + 64) * 4 + 255) & ~(size_t)255; }
 #define GI_MAX_CELLS (1 << 24)
 #define GI_BBOX_BLOCKS 512
 
@@ -807,7 +808,7 @@ size_t pxf_griddata_scratch_bytes(int64_t num)
     size_t cells = n / 2 + 2;
     if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
     return 5 * a256(n * 8) + a256(n * 8) + a256((cells + 2) * 4) + a256(GI_BBOX_BLOCKS * 4 * 8) + a256(sizeof(GridCells)) + 256 +
-           GI_SLOW_CAP_BYTES + /* cubic: rings, degrees, levels, gradients */ a256(n * GI_DEG * 4) + 2 * a256(n) + a256(n * 4) +
+           slow_cap_bytes(n) + /* cubic: rings, degrees, levels, gradients */ a256(n * GI_DEG * 4) + 2 * a256(n) + a256(n * 4) +
            a256(n * 16) + 256 +
            a256(GI_NDIR * GI_DIR_SLICES * 8) +
            pxf_sort_scratch_bytes(num) + 1024;
@@ -841,7 +842,7 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
     unsigned long long *nfail = (unsigned long long *)p; p += 256;
     double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
-    unsigned *slow = (unsigned *)p; p += GI_SLOW_CAP_BYTES;
+    unsigned *slow = (unsigned *)p; p += slow_cap_bytes(n);
     Rings R;
     R.ring = (int *)p; p += a256(n * GI_DEG * 4);
     R.deg = (unsigned char *)p; p += a256(n);
@@ -866,7 +867,6 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     cub.grad = nullptr; cub.R = R;
     if (method == 2) {
         // (a) the Delaunay neighbour rings
-        if (n > (size_t)GI_QUERY_BATCH) { set_error("pxf_griddata: 'cubic' takes at most %d points", GI_QUERY_BATCH); return PXF_ERR_UNSUPPORTED; }
         PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
         int rq_dt = GI_RQ_DT;
         if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
@@ -991,7 +991,7 @@ int pxf_delaunay_max_degree(void) { return GI_DEG; }
 int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_t *ring_out, uint8_t *deg_out,
                            uint8_t *open_out, void *scratch, pxf_stream_t stream)
 {
-    if (num < 3 || !x || !y || !ring_out || !deg_out || !open_out || !scratch || num > (int64_t)GI_QUERY_BATCH) {
+    if (num < 3 || !x || !y || !ring_out || !deg_out || !open_out || !scratch || num > 0x7fffffffll) {
         set_error("pxf_delaunay_neighbors: bad argument");
         return PXF_ERR_INVALID;
     }
@@ -1012,7 +1012,7 @@ int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_
     GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
     unsigned long long *nfail = (unsigned long long *)p; p += 256;
     double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
-    unsigned *slow = (unsigned *)p; p += GI_SLOW_CAP_BYTES;
+    unsigned *slow = (unsigned *)p; p += slow_cap_bytes(n);
     Rings R;
     R.ring = (int *)p; p += a256(n * GI_DEG * 4);
     R.deg = (unsigned char *)p; p += a256(n);
