@@ -135,6 +135,27 @@ def main():
     rows.append(("argsort (stable LSD radix, 64-bit keys)", "analyses.py:76", 24,
                  *(lambda ms: (ms, n / (ms * 1e-3), 24 * n / (ms * 1e-3) / 1e9, 24 * n / (ms * 1e-3) / 1e9 / peak))(
                      timed_b2b(lambda: pxf.analyses.argsort(rad), calls=5))))
+    # the step either side of the path (round 2)
+    def row(name, ref, b, ms):
+        rows.append((name, ref, b, ms, n / (ms * 1e-3), b * n / (ms * 1e-3) / 1e9, b * n / (ms * 1e-3) / 1e9 / peak))
+    A, T, S = pxf.analyses, pxf.transformations, pxf.sources
+    tmp = bundle_alloc(n, dev)
+    row("rectbeam (Philox)", "sources.py:348-379", 80, timed_b2b(lambda: S.rectbeam(12., 7., n, rng="philox", out=tmp), calls=10))
+    row("convergingbeam (Philox)", "sources.py:250-296", 80,
+        timed_b2b(lambda: S.convergingbeam(8400., 200., 230., -.1, .3, n, 1.5, rng="philox", out=tmp), calls=10))
+    row("gaussianBeam (Philox + Box-Muller)", "sources.py:381-416", 80, timed_b2b(lambda: S.gaussianBeam(.01, n, rng="philox", out=tmp), calls=10))
+    side = int(np.sqrt(n))
+    grid_rows = bundle_alloc(side * side, dev)
+    ms = timed_b2b(lambda: S.rectArray(4., 2.5, side, out=grid_rows), calls=10)
+    rows.append(("rectArray (%d^2)" % side, "sources.py:210-247", 80, ms, side * side / (ms * 1e-3), 80 * side * side / (ms * 1e-3) / 1e9,
+                 80 * side * side / (ms * 1e-3) / 1e9 / peak))
+    for k in range(10):
+        tmp[k].copy_(st3[k])
+    row("pointTo", "transformations.py:91-100", 48, timed_b2b(lambda: T.pointTo(tmp, 0., 0., -100.), calls=10))
+    row("indAngle", "analyses.py:164-182", 56, timed_b2b(lambda: A.indAngle(st3), calls=10))
+    row("measureOPD", "analyses.py:232-244", 32, timed_b2b(lambda: A.measureOPD(st3, (0., 0., 1.)), calls=10))
+    row("rmsPoint", "analyses.py:33-45", 24, timed_b2b(lambda: A.rmsPoint(st3, (0., 0., 1.)), calls=10))
+    del tmp, grid_rows
     print("rays per launch: %d; HBM peak (measured copy rate): %.1f GB/s" % (n, peak))
     print("%-40s %-30s %7s %9s %11s %9s %6s" % ("routine", "reference", "B/ray", "ms", "Grays/s", "GB/s", "frac"))
     for r in rows:

@@ -140,7 +140,7 @@ struct Lin { double start, stop, step, delta, div; long long n; int step_zero; }
 PXF_DEV double lin_at(const Lin &q, long long i)
 {
     if (q.n > 1 && i == q.n - 1) return q.stop;
-    const double t = (double)i;
+    const double t = (i >> 31) ? (double)i : (double)(int)i;      // (the 64-bit conversion is a slow instruction)
     if (q.n <= 1) return t * q.delta + q.start;
     if (q.step_zero) return (t / q.div) * q.delta + q.start;
     return t * q.step + q.start;
@@ -153,7 +153,11 @@ k_source_grid(const RowPtrs P, int64_t num, int64_t first, const GridP p)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tid; i < num; i += nthr) {
+    // (row, column) of the meshgrid carried along the grid stride: one 64-bit division per thread, not per ray
+    long long c = (first + tid) % p.nu, r = (first + tid) / p.nu;
+    const long long dc = nthr % p.nu, dr = nthr / p.nu;
+    for (int64_t i = tid; i < num; i += nthr, c += dc, r += dr) {
+        if (c >= p.nu) { c -= p.nu; r++; }
         const long long g = first + i;
         double x = 0., y = 0., l = 0., m = 0., n;
         if (p.kind == PXF_SRC_XSLIT) {                 // sources.py:173-207
@@ -161,7 +165,6 @@ k_source_grid(const RowPtrs P, int64_t num, int64_t first, const GridP p)
             n = p.zhat;
         } else {
             // np.meshgrid(u, v) flattened row-major: column index runs fastest
-            const long long c = g % p.nu, r = g / p.nu;
             const double a = lin_at(p.u, c), b = lin_at(p.v, r);
             if (p.kind == PXF_SRC_RECTARRAY) {         // sources.py:210-247
                 x = a; y = b; n = 1.;
