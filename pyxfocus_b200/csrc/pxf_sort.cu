@@ -2,13 +2,16 @@
 // gathered inclusive scan, and the weighted-HPD reduction built on them
 // (analyses.rhocdf / hpd weighted branch, analyses.py:73-97: argsort -> cumsum -> argmin).
 //
-// Layout: the array is cut into G contiguous chunks, one persistent CTA per chunk
-// (G = SM count x 4).  Per pass: (1) every CTA histograms the digit over its chunk,
-// (2) one CTA turns the digit-major [256][G] table into exclusive offsets, (3) every CTA
-// re-reads its chunk tile by tile and scatters; ranks inside a tile come from
-// __match_any_sync per 32-key slice (stable), running digit offsets live in shared memory.
-// Passes whose digit is constant over the whole array (typically the sign/exponent byte)
-// are skipped after one up-front 8-digit histogram pass.
+// Sort: one-sweep passes.  k_sort_hist_all histograms all eight key bytes in one read of the
+// input; k_sort_plan (one CTA) turns the histograms into per-pass digit bases, drops the passes
+// on constant bytes and fixes the ping-pong order on the device (nothing is read back); every
+// remaining pass is ONE kernel, k_onesweep: a tile of keys is ranked in shared memory (ranks
+// inside a 32-key slice from eight ballots, stable), its digit counts are published and the
+// counts of all earlier tiles are summed by a decoupled look-back, and the tile is written out
+// digit run by digit run.  The first pass converts the doubles and synthesises the indices, the
+// last pass writes doubles and int64 indices.
+// Scan: the array is cut into G contiguous chunks, one CTA per chunk: chunk sums, one-CTA scan,
+// rescan.
 #include "pxf_internal.h"
 #include "pxf_ray.cuh"
 
