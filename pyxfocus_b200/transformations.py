@@ -310,11 +310,21 @@ def applyT(rays, coords, inverse=False):
     return out
 
 
+def _mean_tilts(rays):
+    """(mean l, mean m) of the bundle by the library's deterministic tree reduction (pxf_centroid on rows 4, 5)."""
+    l, m = rays[4], rays[5]
+    a, b = ctypes.c_double(), ctypes.c_double()
+    with torch.cuda.device(l.device):
+        _lib.check(_lib.lib().pxf_centroid(l.data_ptr(), m.data_ptr(), None, l.shape[0], ctypes.byref(a), ctypes.byref(b),
+                                           stream_ptr(l.device)))
+    return a.value, b.value
+
+
 def steerY(rays, coords=None):
     """Rotate the reference frame until the mean y tilt vanishes (transformations.py:78-82)."""
     flush(rays)
-    while abs(float(rays[5].mean())) > 1e-6:
-        transform(rays, 0, 0, 0, -float(rays[5].mean()), 0, 0, coords=coords)
+    while abs(_mean_tilts(rays)[1]) > 1e-6:
+        transform(rays, 0, 0, 0, -_mean_tilts(rays)[1], 0, 0, coords=coords)
         flush(rays)          # inside `with fused(rays)` the transform is only recorded: run it before re-reading the mean
     return
 
@@ -322,8 +332,8 @@ def steerY(rays, coords=None):
 def steerX(rays, coords=None):
     """Rotate the reference frame until the mean x tilt vanishes (transformations.py:84-88)."""
     flush(rays)
-    while abs(float(rays[4].mean())) > 1e-6:
-        transform(rays, 0, 0, 0, 0, -float(rays[4].mean()), 0, coords=coords)
+    while abs(_mean_tilts(rays)[0]) > 1e-6:
+        transform(rays, 0, 0, 0, 0, -_mean_tilts(rays)[0], 0, coords=coords)
         flush(rays)
     return
 
