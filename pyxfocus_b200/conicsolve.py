@@ -67,3 +67,61 @@ def ellipsoidFunction(S, psi, R, F):
     b = sqrt(a ** 2 - f ** 2)
     e = f / a
     return P, a, b, e, f
+
+
+# ---- the remaining closed-form prescription helpers (design-time scalars; conicsolve.py:17-27, 39-49, 85-89, 283-325) ----
+def _sag(z, r, z0, z1):
+    """Sag of a mirror segment: the quadratic term of a parabola fitted to its radius profile, over half its length."""
+    import numpy as np
+    return np.abs(np.polyfit(z, r, 2)[0] * ((z1 - z0) / 2.) ** 2)
+
+
+def primsag(z1, r0, z0):
+    """Sag of a primary that runs from the node z0 to z1 (conicsolve.py:17-27)."""
+    import numpy as np
+    z = np.linspace(z0, z1, 100)
+    return _sag(z, primrad(z, r0, z0), z0, z1)
+
+
+def secsag(z1, z0, r0, F, psi=1.):
+    """Sag of a secondary that runs from z0 to z1 for the prescription (r0, F) (conicsolve.py:39-49)."""
+    import numpy as np
+    z = np.linspace(z0, z1, 100)
+    return _sag(z, secrad(z, r0, F, psi=psi), z0, z1)
+
+
+def rGoal_to_rMax(rgoal, z0, zmax):
+    """The node radius r0 whose primary reaches radius rgoal at zmax: a 10000-point scan below rgoal (conicsolve.py:85-89)."""
+    import numpy as np
+    rguess = np.linspace(rgoal - 2., rgoal, 10000)
+    return rguess[np.argmin(np.abs(rgoal - primrad(zmax, rguess, z0)))]
+
+
+def ellipsoidRad(S, psi, R, F, z):
+    """Radius of an ellipsoid primary at height z above the two-mirror focus (conicsolve.py:283-290)."""
+    P, a, b, e, f = ellipsoidFunction(S, psi, R, F)
+    return sqrt(1 - (z - (f - P + F)) ** 2 / a ** 2) * b
+
+
+def ehSecRad(S, psi, R, F, z):
+    """Radius of the hyperboloid secondary of an ellipsoid-hyperboloid pair at height z (conicsolve.py:292-300)."""
+    P, a, b, e, f = ellipsoidFunction(S, psi, R, F)
+    psi_eff = arctan(R / P) / (arctan(R / F) - arctan(R / P))
+    return secrad(z, R, F, psi=psi_eff)
+
+
+def ellipsoidSag(S, psi, R0, F, z1, z0):
+    """Sag of an ellipsoid primary between z0 and z1 (conicsolve.py:302-309)."""
+    import numpy as np
+    z = np.linspace(z0, z1, 100)
+    return _sag(z, ellipsoidRad(S, psi, R0, F, z), z0, z1)
+
+
+def solveS(P, a, b, e, f, x, y, z, l, m, n):
+    """Analytic ray / conic intersection: the two path lengths and their quadratic's coefficients (conicsolve.py:311-325)."""
+    K = -e ** 2
+    R = b ** 2 / a
+    denom = l ** 2 + m ** 2 + (K + 1) * n ** 2
+    b2 = (l * x + m * y - R * n + (K + 1) * n * z) / denom
+    c2 = (x ** 2 + y ** 2 - 2 * R * z + (K + 1) * z ** 2) / denom
+    return b2, c2, -b2 + sqrt(b2 ** 2 - c2), -b2 - sqrt(b2 ** 2 - c2)
