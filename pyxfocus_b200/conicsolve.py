@@ -1,8 +1,9 @@
 """Scalar mirror-prescription helpers mirrored from the reference's ``conicsolve.py``
-(host-side numpy; nothing here touches rays).  Only the functions the hot-path wrappers and
-the known-answer tests need: ``primrad`` (conicsolve.py:7-15), ``secrad`` (:29-37),
+(host-side numpy; nothing here touches rays): ``primrad`` (conicsolve.py:7-15), ``secrad`` (:29-37),
 ``woltparam`` (:51-59), ``primfocus`` (:62-64), ``wsRMS`` (:250-254), ``wsFoc`` (:257-261),
-``ellipsoidFunction`` (:263-281).
+``ellipsoidFunction`` (:263-281) and, at the end of the file, the sag / radius / intersection helpers.  Not mirrored:
+the reference's debugging scratch (``mathraytrace``, ``wsPrimFunction*``, ``wsSecFunction*`` stop in ``pdb.set_trace()``;
+``primaryintercept`` only prints).
 """
 from numpy import arcsin, arctan, cos, sin, sqrt, tan
 
