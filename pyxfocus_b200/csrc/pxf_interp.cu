@@ -26,6 +26,7 @@ namespace pxf {
 
 #define GI_THREADS 128
 #define GI_MAX_PIVOTS 512
+#define GI_ILP 8              // independent point loads in flight per lane in the all-points passes
 
 #define GI_NDIR 64          // support directions of the outer hull approximation
 #define GI_DIR_SLICES 32
@@ -246,7 +247,46 @@ PXF_DEV int apex_of_edge(const GridCells &g, const double *__restrict__ sx, cons
 }
 
 // the same by the 32 lanes of a warp over ALL points (every lane returns the result)
-PXF_DEV int apex_of_edge_warp(const double *__restrict__ sx, const double *__restrict__ sy, int np, int ip, int in_, double side)
+// one lane-strided pass over the points [p0, p1) of the apex search: keeps the smallest t
+PXF_DEV void apex_scan_range(const double *__restrict__ sx, const double *__restrict__ sy, int p0, int p1, int lane, int ip, int in_,
+                             double px, double py, double ex, double ey, double e2, double side, double &tbest, int &best)
+{
+    for (int q0 = p0 + lane; q0 < p1; q0 += 32 * GI_ILP) {
+        double xs[GI_ILP], ys[GI_ILP];
+#pragma unroll
+        for (int u = 0; u < GI_ILP; u++) {
+            const int q = q0 + 32 * u;
+            xs[u] = q < p1 ? sx[q] : px; ys[u] = q < p1 ? sy[q] : py;
+        }
+#pragma unroll
+        for (int u = 0; u < GI_ILP; u++) {
+            const int q = q0 + 32 * u;
+            if (q >= p1) break;
+            if (q == ip || q == in_) continue;
+            const double x = xs[u] - px, y = ys[u] - py;
+            const double cr = side * (ex * y - ey * x);
+            if (!(cr > 1e-14 * sqrt(e2 * (x * x + y * y)))) continue;
+            const double t = (x * (x - ex) + y * (y - ey)) / (2. * cr);
+            if (t < tbest || (t == tbest && q < best)) { tbest = t; best = q; }
+        }
+    }
+}
+
+PXF_DEV void apex_agree(double &tbest, int &best)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ot = __shfl_xor_sync(0xffffffffu, tbest, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ob >= 0 && (best < 0 || ot < tbest || (ot == tbest && ob < best))) { tbest = ot; best = ob; }
+    }
+}
+
+// the same by the 32 lanes of a warp (every lane returns the result): a candidate from the block of cells the thread
+// kernel gave up on, then every cell under the candidate's circle (any better apex lies inside it); only an edge
+// with no candidate nearby -- a hull edge -- takes a pass over ALL points
+PXF_DEV int apex_of_edge_warp(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
+                              const int *__restrict__ start, int np, int ip, int in_, double side)
 {
     const int lane = threadIdx.x & 31;
     const double px = sx[ip], py = sy[ip];
@@ -254,20 +294,32 @@ PXF_DEV int apex_of_edge_warp(const double *__restrict__ sx, const double *__res
     const double e2 = ex * ex + ey * ey;
     double tbest = __longlong_as_double(0x7ff0000000000000ll);
     int best = -1;
-    for (int q = lane; q < np; q += 32) {
-        if (q == ip || q == in_) continue;
-        const double x = sx[q] - px, y = sy[q] - py;
-        const double cr = side * (ex * y - ey * x);
-        if (!(cr > 1e-14 * sqrt(e2 * (x * x + y * y)))) continue;
-        const double t = (x * (x - ex) + y * (y - ey)) / (2. * cr);
-        if (t < tbest || (t == tbest && q < best)) { tbest = t; best = q; }
+    int cx, cy;
+    cell_of(g, px, py, cx, cy);
+    {
+        const int i0 = cx - GI_RQ_DT < 0 ? 0 : cx - GI_RQ_DT, i1 = cx + GI_RQ_DT >= g.gx ? g.gx - 1 : cx + GI_RQ_DT;
+        for (int j = cy - GI_RQ_DT; j <= cy + GI_RQ_DT; j++) {
+            if (j < 0 || j >= g.gy) continue;
+            apex_scan_range(sx, sy, start[j * g.gx + i0], start[j * g.gx + i1 + 1], lane, ip, in_, px, py, ex, ey, e2, side, tbest, best);
+        }
+        apex_agree(tbest, best);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ot = __shfl_xor_sync(0xffffffffu, tbest, o);
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-        if (ob >= 0 && (best < 0 || ot < tbest || (ot == tbest && ob < best))) { tbest = ot; best = ob; }
+    if (best < 0) {
+        apex_scan_range(sx, sy, 0, np, lane, ip, in_, px, py, ex, ey, e2, side, tbest, best);
+        apex_agree(tbest, best);
+        return best;
     }
+    // centre of the candidate's circle: e/2 + t * side * (-ey, ex); radius^2 = e2 (1/4 + t^2)
+    const double ox = px + .5 * ex - tbest * side * ey, oy = py + .5 * ey + tbest * side * ex;
+    const double R = sqrt(e2 * (.25 + tbest * tbest));
+    const double fi0 = (ox - R - g.x0) / g.h, fi1 = (ox + R - g.x0) / g.h, fj0 = (oy - R - g.y0) / g.h, fj1 = (oy + R - g.y0) / g.h;
+    const int i0 = fi0 > 0. ? (fi0 < (double)g.gx ? (int)fi0 : g.gx - 1) : 0;
+    const int i1 = fi1 < (double)g.gx ? (fi1 > 0. ? (int)fi1 : 0) : g.gx - 1;
+    const int j0 = fj0 > 0. ? (fj0 < (double)g.gy ? (int)fj0 : g.gy - 1) : 0;
+    const int j1 = fj1 < (double)g.gy ? (fj1 > 0. ? (int)fj1 : 0) : g.gy - 1;
+    for (int j = j0; j <= j1; j++)
+        apex_scan_range(sx, sy, start[j * g.gx + i0], start[j * g.gx + i1 + 1], lane, ip, in_, px, py, ex, ey, e2, side, tbest, best);
+    apex_agree(tbest, best);
     return best;
 }
 
@@ -338,9 +390,11 @@ k_dt_rings(const double *__restrict__ sx, const double *__restrict__ sy, const i
 
 // One warp per deferred vertex (beside the hull): the same gift wrapping with every apex taken over all points.
 __global__ void __launch_bounds__(GI_THREADS)
-k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, int num, Rings R,
-                unsigned long long *__restrict__ nfail, const unsigned *__restrict__ slow)
+k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, const int *__restrict__ start,
+                const GridCells *__restrict__ gp, int num, Rings R, unsigned long long *__restrict__ nfail,
+                const unsigned *__restrict__ slow)
 {
+    const GridCells &g = *gp;
     const unsigned nslow = slow[0];
     const int lane = threadIdx.x & 31;
     const unsigned wpb = blockDim.x >> 5;
@@ -349,10 +403,20 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, in
         const double px = sx[ip], py = sy[ip];
         double best = __longlong_as_double(0x7ff0000000000000ll);
         int n0 = -1;
-        for (int q = lane; q < num; q += 32) {
-            if (q == ip) continue;
-            const double x = sx[q] - px, y = sy[q] - py, d2 = x * x + y * y;
-            if (d2 < best || (d2 == best && q < n0)) { best = d2; n0 = q; }
+        for (int q0 = lane; q0 < num; q0 += 32 * GI_ILP) {
+            double xs[GI_ILP], ys[GI_ILP];
+#pragma unroll
+            for (int u = 0; u < GI_ILP; u++) {
+                const int q = q0 + 32 * u;
+                xs[u] = q < num ? sx[q] : px; ys[u] = q < num ? sy[q] : py;
+            }
+#pragma unroll
+            for (int u = 0; u < GI_ILP; u++) {
+                const int q = q0 + 32 * u;
+                if (q >= num || q == ip) continue;
+                const double x = xs[u] - px, y = ys[u] - py, d2 = x * x + y * y;
+                if (d2 < best || (d2 == best && q < n0)) { best = d2; n0 = q; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -368,7 +432,7 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, in
             if (lane == 0) out[0] = n0;
             nccw = 1;
             for (int cur = n0;;) {
-                const int d = apex_of_edge_warp(sx, sy, num, ip, cur, 1.);
+                const int d = apex_of_edge_warp(g, sx, sy, start, num, ip, cur, 1.);
                 if (d < 0) { open = true; break; }
                 if (d == n0) break;
                 if (nccw >= GI_DEG) { ok = false; break; }
@@ -378,7 +442,7 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, in
             }
             if (ok && open)
                 for (int cur = n0;;) {
-                    const int d = apex_of_edge_warp(sx, sy, num, ip, cur, -1.);
+                    const int d = apex_of_edge_warp(g, sx, sy, start, num, ip, cur, -1.);
                     if (d < 0) break;
                     if (nccw + ncw >= GI_DEG) { ok = false; break; }
                     cwbuf[ncw++] = d;
@@ -560,12 +624,35 @@ PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict_
         if (!COOP && (int64_t)(i1 - i0 + 1) * (j1 - j0 + 1) > GI_CELL_BUDGET) return 1;
         double worst = tol;
         int iw = -1;
-        for (int j = j0 + lane; j <= j1; j += COOP ? 32 : 1) {
-            const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];      // cells of one row are contiguous
-            for (int p = p0; p < p1; p++) {
-                if (p == ia || p == ib || p == ic) continue;
-                const double v = incircle(ax, ay, bx, by, cx_, cy_, sx[p] - qx, sy[p] - qy);
-                if (v > worst) { worst = v; iw = p; }
+        if (COOP) {
+            // the lanes share each row's point range, GI_ILP independent loads in flight per lane
+            for (int j = j0; j <= j1; j++) {
+                const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];  // cells of one row are contiguous
+                for (int pb = p0 + lane; pb < p1; pb += 32 * GI_ILP) {
+                    double xs[GI_ILP], ys[GI_ILP];
+#pragma unroll
+                    for (int u = 0; u < GI_ILP; u++) {
+                        const int p = pb + 32 * u;
+                        xs[u] = p < p1 ? sx[p] : 0.; ys[u] = p < p1 ? sy[p] : 0.;
+                    }
+#pragma unroll
+                    for (int u = 0; u < GI_ILP; u++) {
+                        const int p = pb + 32 * u;
+                        if (p >= p1) break;
+                        if (p == ia || p == ib || p == ic) continue;
+                        const double v = incircle(ax, ay, bx, by, cx_, cy_, xs[u] - qx, ys[u] - qy);
+                        if (v > worst) { worst = v; iw = p; }
+                    }
+                }
+            }
+        } else {
+            for (int j = j0; j <= j1; j++) {
+                const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];  // cells of one row are contiguous
+                for (int p = p0; p < p1; p++) {
+                    if (p == ia || p == ib || p == ic) continue;
+                    const double v = incircle(ax, ay, bx, by, cx_, cy_, sx[p] - qx, sy[p] - qy);
+                    if (v > worst) { worst = v; iw = p; }
+                }
             }
         }
         if (COOP) {
@@ -697,6 +784,33 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
         }
         if (ia < 0 || bestm < -1e-12) ia = -1;        // (points exactly on the axes through q: let the warp kernel decide)
     }
+    if (ia < 0) {
+        // A quadrant is empty nearby (q beside the hull).  The same closure test the warp kernel applies to ALL points,
+        // on the points of the rings just searched: a = the nearest one as the zero direction, b / c = the ones turned
+        // farthest counter-clockwise / clockwise by less than pi; if c is counter-clockwise of b the triangle holds q.
+        // (If it does not close q is outside the hull of the NEARBY points only: the warp kernel decides.)
+        int na = -1;
+        double nd = inf;
+        for (int k = 0; k < 4; k++) if (qi[k] >= 0 && qd[k] < nd) { nd = qd[k]; na = qi[k]; }
+        if (na >= 0) {
+            const double a0x = sx[na] - qx, a0y = sy[na] - qy;
+            int jb = -1, jc = -1;
+            double bxx = 0., byy = 0., cxx = 0., cyy = 0.;
+            for (int j = cy - rq; j <= cy + rq; j++) {
+                if (j < 0 || j >= g.gy) continue;
+                const int i0 = cx - rq < 0 ? 0 : cx - rq, i1 = cx + rq >= g.gx ? g.gx - 1 : cx + rq;
+                for (int p = start[j * g.gx + i0]; p < start[j * g.gx + i1 + 1]; p++) {
+                    if (p == na) continue;
+                    const double dx = sx[p] - qx, dy = sy[p] - qy;
+                    const double cr = a0x * dy - a0y * dx;
+                    const bool opposite = cr == 0. && a0x * dx + a0y * dy < 0.;
+                    if ((cr > 0. || opposite) && (jb < 0 || bxx * dy - byy * dx > 0.)) { jb = p; bxx = dx; byy = dy; }
+                    if ((cr < 0. || opposite) && (jc < 0 || cxx * dy - cyy * dx < 0.)) { jc = p; cxx = dx; cyy = dy; }
+                }
+            }
+            if (jb >= 0 && jc >= 0 && bxx * cyy - byy * cxx > 0.) { ia = na; ib = jb; ic = jc; }
+        }
+    }
     int rc = 1;
     double val = nanv;
     if (ia >= 0) rc = settle_and_interpolate<false>(g, sx, sy, sv, start, qx, qy, ia, ib, ic, &val, cub);
@@ -731,12 +845,24 @@ k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
         const double a0x = sx[0] - qx, a0y = sy[0] - qy;
         int jb = -1, jc = -1;
         double bxx = 0., byy = 0., cxx = 0., cyy = 0.;
-        for (int p = 1 + lane; p < np; p += 32) {
-            const double dx = sx[p] - qx, dy = sy[p] - qy;
-            const double cr = a0x * dy - a0y * dx;                   // > 0: counter-clockwise of a
-            const bool opposite = cr == 0. && a0x * dx + a0y * dy < 0.;   // (a point exactly opposite counts on both sides)
-            if ((cr > 0. || opposite) && (jb < 0 || bxx * dy - byy * dx > 0.)) { jb = p; bxx = dx; byy = dy; }
-            if ((cr < 0. || opposite) && (jc < 0 || cxx * dy - cyy * dx < 0.)) { jc = p; cxx = dx; cyy = dy; }
+        // (eight independent loads in flight per lane: one warp per query is otherwise bound by load latency)
+        for (int p0 = 1 + lane; p0 < np; p0 += 32 * GI_ILP) {
+            double xs[GI_ILP], ys[GI_ILP];
+#pragma unroll
+            for (int u = 0; u < GI_ILP; u++) {
+                const int p = p0 + 32 * u;
+                xs[u] = p < np ? sx[p] : qx; ys[u] = p < np ? sy[p] : qy;
+            }
+#pragma unroll
+            for (int u = 0; u < GI_ILP; u++) {
+                const int p = p0 + 32 * u;
+                if (p >= np) break;
+                const double dx = xs[u] - qx, dy = ys[u] - qy;
+                const double cr = a0x * dy - a0y * dx;                   // > 0: counter-clockwise of a
+                const bool opposite = cr == 0. && a0x * dx + a0y * dy < 0.;   // (a point exactly opposite counts on both sides)
+                if ((cr > 0. || opposite) && (jb < 0 || bxx * dy - byy * dx > 0.)) { jb = p; bxx = dx; byy = dy; }
+                if ((cr < 0. || opposite) && (jc < 0 || cxx * dy - cyy * dx < 0.)) { jc = p; cxx = dx; cyy = dy; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -872,7 +998,7 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
         if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
         k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow,
                                                                                            rq_dt);
-        k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, (int)num, R, nfail, slow);
+        k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow);
         count_launch(2);
         unsigned long long hf[4] = {0, 0, 0, 0};
         PXF_CUDA(cudaMemcpyAsync(hf, nfail, 32, cudaMemcpyDeviceToHost, s));
@@ -1033,7 +1159,7 @@ int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_
     int rq_dt = GI_RQ_DT;
     if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);
     k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow, rq_dt);
-    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, (int)num, R, nfail, slow);
+    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow);
     k_rings_export<<<(unsigned)((num + 255) / 256), 256, 0, s>>>(R, perm, (int)num, ring_out, deg_out, open_out);
     count_launch(4);
     if ((rc = check_launch("pxf_delaunay_neighbors"))) return rc;
