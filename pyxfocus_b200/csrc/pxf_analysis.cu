@@ -1673,12 +1673,6 @@ static inline unsigned int *ccnt(const void *scratch, int64_t ntiles)
 {
     return (unsigned int *)((char *)scratch + (size_t)(ntiles + 1) * 8);
 }
-static inline RowTable *ctab(const void *scratch, int64_t ntiles)
-{
-    size_t off = (size_t)(ntiles + 1) * 8 + (size_t)ntiles * 4;
-    off = (off + 15) & ~(size_t)15;
-    return (RowTable *)((char *)scratch + off);
-}
 
 int pxf_vignette_flags(const double *l, const double *m, const double *n, int64_t num,
                        uint8_t *flags, pxf_stream_t stream)
