@@ -252,6 +252,22 @@ struct SelectState {
 
 PXF_DEV unsigned long long key_of(double r) { return (unsigned long long)__double_as_longlong(r); }
 
+
+// Warp-aggregated shared-memory histogram update (bin < 0: nothing to add; every lane of the warp must call).
+// The early select passes see almost every key in ONE bin: the lanes that share lane 0's bin are counted by a ballot and
+// added once, the rest add themselves.  (__match_any_sync would aggregate every bin, but it runs at a few hundred
+// cycles per warp on this part -- it bounded this kernel at 2.4 TB/s, profiles/r02_notes.md.)
+PXF_DEV void hist_add_warp(unsigned int *sh, int bin)
+{
+    const int b0 = __shfl_sync(0xffffffffu, bin, 0);
+    const unsigned same = __ballot_sync(0xffffffffu, bin == b0);
+    if (bin == b0) {
+        if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(&sh[bin], (unsigned)__popc(same));
+    } else if (bin >= 0) {
+        atomicAdd(&sh[bin], 1u);
+    }
+}
+
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(PXF_BLOCK)
 k_select_hist(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ keys,
@@ -293,9 +309,7 @@ k_select_hist(const double *__restrict__ x, const double *__restrict__ y, const 
                 else if (np == 2 && top == p1) bin = nbins + d;
             }
         }
-        // warp-aggregated shared-memory histogram: one atomic per distinct bin per warp
-        unsigned peers = __match_any_sync(0xffffffffu, bin);
-        if (bin >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[bin], __popc(peers));
+        hist_add_warp(sh, bin);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < np * nbins; t += blockDim.x) {
@@ -707,8 +721,7 @@ k_small_select(const double *__restrict__ keys, const int *__restrict__ seg_coun
                     if (top == p0) bin = d;
                     else if (npl == 2 && top == p1) bin = NB + d;
                 }
-                const unsigned peers = __match_any_sync(0xffffffffu, bin);
-                if (bin >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[bin], __popc(peers));
+                hist_add_warp(sh, bin);
             }
         }
         __syncthreads();
