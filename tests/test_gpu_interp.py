@@ -209,3 +209,16 @@ def test_interpolatevec_cubic_polar_and_degenerate_inputs(pxf):
     dup = [torch.tensor(v, dtype=torch.float64).cuda() for v in ([0., 1., 0., 1., .5, .5], [0., 0., 1., 1., .5, .5], [1., 2., 3., 4., 5., 5.])]
     with pytest.raises(pxf.PxfError):
         pxf.analyses.griddata(*dup, q[0], q[1], method="cubic")
+
+
+def test_interpolatevec_at_scale(pxf):
+    """2e5 points -> 128 x 128 grid, all three methods against scipy (the largest size scipy finishes in seconds)."""
+    rng = np.random.default_rng(21)
+    n = 200_000
+    r, t = 12.5 * np.sqrt(rng.uniform(0, 1, n)), rng.uniform(0, 2 * np.pi, n)
+    rays = bundle(r * np.cos(t), r * np.sin(t), 22)
+    dev = to_dev(rays)
+    for method, tol in (("linear", 1e-10), ("cubic", 1e-9), ("nearest", 0.)):
+        want, _, _ = refapi.interpolateVec(copy(rays), 5, 128, 128, method=method)
+        got, _, _ = pxf.analyses.interpolateVec(dev, 5, 128, 128, method=method)
+        assert compare(got, want, np.abs(rays[5]).max(), "2e5 points " + method, tol=tol) > 10_000

@@ -1583,3 +1583,22 @@ def test_argsort_sizes_and_degenerate_keys(pxf, n):
         assert np.array_equal(ii, want), name
         assert np.array_equal(kn.view(np.int64)[~np.isnan(kn)], kc[want].view(np.int64)[~np.isnan(kc[want])]), name
         assert np.isnan(kn).sum() == np.isnan(kc).sum(), name
+
+
+def test_argsort_at_bench_scale(pxf):
+    """1e8 keys (the radii of a config-5 shard): size-independent properties of the one-sweep sort -- sorted, a permutation,
+    keys[idx] == sorted keys bit for bit, equal keys in input order."""
+    import torch
+    n = 100_000_000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    keys = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    keys[::1000] = keys[0]                                   # 1e5 exact ties
+    keys.mul_(1e-3)
+    ks, idx = pxf.analyses.argsort(keys)
+    assert bool((ks[1:] >= ks[:-1]).all())
+    assert bool((keys[idx] == ks).all())
+    seen = torch.zeros(n, dtype=torch.bool, device="cuda")
+    seen[idx] = True
+    assert bool(seen.all())
+    tie = ks[1:] == ks[:-1]
+    assert int(tie.sum()) >= 99_000 and bool((idx[1:][tie] > idx[:-1][tie]).all())
