@@ -20,9 +20,11 @@ def stream_ptr(device):
 
 
 def bundle_alloc(num, device, nrows=10, zero=False):
-    """Rows of one [nrows, N] fp64 allocation, each row 16-byte aligned (double2 path)."""
-    pad = (int(num) + 1) & ~1
-    base = (torch.zeros if zero else torch.empty)((nrows, max(pad, 2)), dtype=torch.float64, device=device)
+    """Rows of one [nrows, N] fp64 allocation, every row starting on a 128-byte boundary: the double2 path needs 16,
+    and a warp's 256-byte access then covers whole 32-byte sectors (rows of an odd ray count ran at 0.6 of the rate of
+    aligned ones: partial-sector writes, profiles/r02_notes.md)."""
+    pad = (int(num) + 15) & ~15
+    base = (torch.zeros if zero else torch.empty)((nrows, max(pad, 16)), dtype=torch.float64, device=device)
     return [base[i, :num] for i in range(nrows)]
 
 

@@ -137,10 +137,11 @@ struct Lin { double start, stop, step, delta, div; long long n; int step_zero; }
 
 // numpy.linspace(start, stop, n)[i]: i*step + start with step = (stop-start)/(n-1), the last point pinned to stop;
 // when the step underflows to zero numpy divides first ((i/div)*delta + start); n == 1 gives start.
-PXF_DEV double lin_at(const Lin &q, long long i)
+template <class Int>
+PXF_DEV double lin_at(const Lin &q, Int i)
 {
-    if (q.n > 1 && i == q.n - 1) return q.stop;
-    const double t = (i >> 31) ? (double)i : (double)(int)i;      // (the 64-bit conversion is a slow instruction)
+    if (q.n > 1 && (long long)i == q.n - 1) return q.stop;
+    const double t = (double)i;
     if (q.n <= 1) return t * q.delta + q.start;
     if (q.step_zero) return (t / q.div) * q.delta + q.start;
     return t * q.step + q.start;
@@ -154,10 +155,12 @@ k_source_grid(const RowPtrs P, int64_t num, int64_t first, const GridP p)
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     // (row, column) of the meshgrid carried along the grid stride: one 64-bit division per thread, not per ray
-    long long c = (first + tid) % p.nu, r = (first + tid) / p.nu;
-    const long long dc = nthr % p.nu, dr = nthr / p.nu;
+    // (32-bit: the host refuses meshgrids with 2^31 or more rows or columns; 64-bit integer -> double conversions and
+    // compares are slow instructions)
+    int c = (int)((first + tid) % p.nu), r = (int)((first + tid) / p.nu);
+    const int nu = (int)p.nu, dc = (int)(nthr % p.nu), dr = (int)(nthr / p.nu);
     for (int64_t i = tid; i < num; i += nthr, c += dc, r += dr) {
-        if (c >= p.nu) { c -= p.nu; r++; }
+        if (c >= nu) { c -= nu; r++; }
         const long long g = first + i;
         double x = 0., y = 0., l = 0., m = 0., n;
         if (p.kind == PXF_SRC_XSLIT) {                 // sources.py:173-207
@@ -397,6 +400,10 @@ int pxf_source_grid(int32_t kind, double *const rays[10], int64_t num, int64_t f
         break;
     }
     default: set_error("pxf_source_grid: bad kind %d", kind); return PXF_ERR_INVALID;
+    }
+    if (kind != PXF_SRC_XSLIT && (n1 >= (1ll << 31) - 1 || n2 >= (1ll << 31) - 2)) {
+        set_error("pxf_source_grid: grid too large");
+        return PXF_ERR_INVALID;
     }
     if (n1 < 0 || n2 < 0 || num < 0 || first < 0 || first + num > total) {
         set_error("pxf_source_grid: rays [%lld, %lld) are not inside the %lld-ray source", (long long)first,
