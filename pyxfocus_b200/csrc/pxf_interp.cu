@@ -922,6 +922,90 @@ static size_t slow_cap_bytes(size_t n) { return (((n > (size_t)GI_QUERY_BATCH ? 
 #define GI_MAX_CELLS (1 << 24)
 #define GI_BBOX_BLOCKS 512
 
+// the scratch buffer of pxf_griddata / pxf_delaunay_neighbors, carved up
+struct InterpScratch {
+    double *key, *skey, *sx, *sy, *sv, *part, *spart, *grad;
+    long long *perm;
+    int *start, *level, *flag;          // flag[0]: levels changed, flag[1]: highest level, flag[2..3]: the sweep's error
+    GridCells *g;
+    unsigned long long *nfail;
+    unsigned *slow;
+    Rings R;
+    void *sort_scr;
+    size_t cells;
+};
+
+static size_t interp_cells(size_t n)
+{
+    const size_t cells = n / 2 + 2;
+    return cells > GI_MAX_CELLS ? GI_MAX_CELLS : cells;
+}
+
+static InterpScratch interp_carve(void *scratch, size_t n)
+{
+    InterpScratch w;
+    w.cells = interp_cells(n);
+    char *p = static_cast<char *>(scratch);
+    w.key = (double *)p; p += a256(n * 8);
+    w.skey = (double *)p; p += a256(n * 8);
+    w.perm = (long long *)p; p += a256(n * 8);
+    w.sx = (double *)p; p += a256(n * 8);
+    w.sy = (double *)p; p += a256(n * 8);
+    w.sv = (double *)p; p += a256(n * 8);
+    w.start = (int *)p; p += a256((w.cells + 2) * 4);
+    w.part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
+    w.g = (GridCells *)p; p += a256(sizeof(GridCells));
+    w.nfail = (unsigned long long *)p; p += 256;
+    w.spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
+    w.slow = (unsigned *)p; p += slow_cap_bytes(n);
+    w.R.ring = (int *)p; p += a256(n * GI_DEG * 4);
+    w.R.deg = (unsigned char *)p; p += a256(n);
+    w.R.open = (unsigned char *)p; p += a256(n);
+    w.level = (int *)p; p += a256(n * 4);
+    w.grad = (double *)p; p += a256(n * 16);
+    w.flag = (int *)p; p += 256;
+    w.sort_scr = p;
+    return w;
+}
+
+// bounding box, support function and cell grid of the points; the points (and their values) in cell order
+static int interp_bin(const InterpScratch &w, const double *x, const double *y, const double *v, int64_t num, pxf_stream_t stream)
+{
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
+    PXF_CUDA(cudaMemsetAsync(w.nfail, 0, 32, s));
+    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, w.part);
+    k_support_partial<<<GI_NDIR * GI_DIR_SLICES, 256, 0, s>>>(x, y, num, w.spart);
+    k_grid_setup<<<1, 64, 0, s>>>(w.part, nb, num, (int)(w.cells - 2), w.g, w.spart);
+    k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, w.g, w.key);
+    count_launch(4);
+    const int rc = pxf_argsort(w.key, num, w.skey, reinterpret_cast<int64_t *>(w.perm), w.sort_scr, stream);
+    if (rc) return rc;
+    k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(w.skey, w.perm, num, w.g, x, y, v, w.start, w.sx, w.sy, w.sv);
+    count_launch();
+    return check_launch("interp_bin");
+}
+
+// the Delaunay neighbour rings of the binned points
+static int interp_rings(const InterpScratch &w, int64_t num, cudaStream_t s)
+{
+    PXF_CUDA(cudaMemsetAsync(w.slow, 0, 4, s));
+    int rq_dt = GI_RQ_DT;
+    if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
+    k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(w.sx, w.sy, w.start, w.g, (int)num, w.R, w.nfail,
+                                                                                       w.slow, rq_dt);
+    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(w.sx, w.sy, w.start, w.g, (int)num, w.R, w.nfail, w.slow);
+    count_launch(2);
+    unsigned long long hf[4] = {0, 0, 0, 0};
+    PXF_CUDA(cudaMemcpyAsync(hf, w.nfail, 32, cudaMemcpyDeviceToHost, s));
+    PXF_CUDA(cudaStreamSynchronize(s));
+    if (hf[0]) {
+        set_error("%llu points have no Delaunay neighbour ring (duplicate points, or more than %d neighbours)", hf[0], GI_DEG);
+        return PXF_ERR_UNSUPPORTED;
+    }
+    return PXF_OK;
+}
+
 }  // namespace pxf
 
 using namespace pxf;
@@ -931,13 +1015,9 @@ extern "C" {
 size_t pxf_griddata_scratch_bytes(int64_t num)
 {
     const size_t n = (size_t)(num > 0 ? num : 1);
-    size_t cells = n / 2 + 2;
-    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
-    return 5 * a256(n * 8) + a256(n * 8) + a256((cells + 2) * 4) + a256(GI_BBOX_BLOCKS * 4 * 8) + a256(sizeof(GridCells)) + 256 +
-           slow_cap_bytes(n) + /* cubic: rings, degrees, levels, gradients */ a256(n * GI_DEG * 4) + 2 * a256(n) + a256(n * 4) +
-           a256(n * 16) + 256 +
-           a256(GI_NDIR * GI_DIR_SLICES * 8) +
-           pxf_sort_scratch_bytes(num) + 1024;
+    char probe[1];                                           // (only the offsets are used)
+    const InterpScratch w = interp_carve(probe, n);
+    return (size_t)((char *)w.sort_scr - probe) + pxf_sort_scratch_bytes(num) + 1024;
 }
 
 int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
@@ -954,61 +1034,21 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     if (num < (method >= 1 ? 3 : 1)) { set_error("pxf_griddata: needs at least %d points", method >= 1 ? 3 : 1); return PXF_ERR_INVALID; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const size_t n = (size_t)num;
-    size_t cells = n / 2 + 2;
-    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
-    char *p = static_cast<char *>(scratch);
-    double *key = (double *)p; p += a256(n * 8);
-    double *skey = (double *)p; p += a256(n * 8);
-    long long *perm = (long long *)p; p += a256(n * 8);
-    double *sx = (double *)p; p += a256(n * 8);
-    double *sy = (double *)p; p += a256(n * 8);
-    double *sv = (double *)p; p += a256(n * 8);
-    int *start = (int *)p; p += a256((cells + 2) * 4);
-    double *part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
-    GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
-    unsigned long long *nfail = (unsigned long long *)p; p += 256;
-    double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
-    unsigned *slow = (unsigned *)p; p += slow_cap_bytes(n);
-    Rings R;
-    R.ring = (int *)p; p += a256(n * GI_DEG * 4);
-    R.deg = (unsigned char *)p; p += a256(n);
-    R.open = (unsigned char *)p; p += a256(n);
-    int *level = (int *)p; p += a256(n * 4);
-    double *grad = (double *)p; p += a256(n * 16);
-    int *flag = (int *)p; p += 256;          // [0]: levels changed; [2..3]: the sweep's error
-    void *sort_scr = p;
-    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
-    PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
-    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
-    k_support_partial<<<GI_NDIR * GI_DIR_SLICES, 256, 0, s>>>(x, y, num, spart);
-    k_grid_setup<<<1, 64, 0, s>>>(part, nb, num, (int)(cells - 2), g, spart);
-    count_launch();
-    k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, g, key);
-    count_launch(3);
-    int rc = pxf_argsort(key, num, skey, reinterpret_cast<int64_t *>(perm), sort_scr, stream);
+    const InterpScratch w = interp_carve(scratch, n);
+    int rc = interp_bin(w, x, y, v, num, stream);
     if (rc) return rc;
-    k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, v, start, sx, sy, sv);
-    count_launch();
+    double *const sx = w.sx, *const sy = w.sy, *const sv = w.sv, *const grad = w.grad;
+    int *const start = w.start, *const level = w.level, *const flag = w.flag;
+    GridCells *const g = w.g;
+    unsigned long long *const nfail = w.nfail;
+    unsigned *const slow = w.slow;
+    const long long *const perm = w.perm;
+    const Rings R = w.R;
     Cubic cub;
     cub.grad = nullptr; cub.R = R;
     if (method == 2) {
         // (a) the Delaunay neighbour rings
-        PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
-        int rq_dt = GI_RQ_DT;
-        if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
-        k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow,
-                                                                                           rq_dt);
-        k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow);
-        count_launch(2);
-        unsigned long long hf[4] = {0, 0, 0, 0};
-        PXF_CUDA(cudaMemcpyAsync(hf, nfail, 32, cudaMemcpyDeviceToHost, s));
-        PXF_CUDA(cudaStreamSynchronize(s));
-        if (hf[0]) {
-            set_error("pxf_griddata: %llu points have no Delaunay neighbour ring (duplicate points, or more than %d neighbours)",
-                      hf[0], GI_DEG);
-            if (nfail_host) *nfail_host = (int64_t)hf[0];
-            return PXF_ERR_UNSUPPORTED;
-        }
+        if ((rc = interp_rings(w, num, s))) { if (nfail_host) *nfail_host = 1; return rc; }
         // (b) levels of the input-order Gauss-Seidel sweep, then the sweeps (scipy: maxiter 400, tol 1e-6)
         const unsigned vb = (unsigned)((num + 255) / 256);
         PXF_CUDA(cudaMemsetAsync(level, 0, n * 4, s));
@@ -1123,53 +1163,13 @@ int pxf_delaunay_neighbors(const double *x, const double *y, int64_t num, int32_
     }
     if (sm_count() <= 0) { set_error("no CUDA device available (libpxf has no CPU fallback)"); return PXF_ERR_CUDA; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const size_t n = (size_t)num;
-    size_t cells = n / 2 + 2;
-    if (cells > GI_MAX_CELLS) cells = GI_MAX_CELLS;
-    char *p = static_cast<char *>(scratch);
-    double *key = (double *)p; p += a256(n * 8);
-    double *skey = (double *)p; p += a256(n * 8);
-    long long *perm = (long long *)p; p += a256(n * 8);
-    double *sx = (double *)p; p += a256(n * 8);
-    double *sy = (double *)p; p += a256(n * 8);
-    double *sv = (double *)p; p += a256(n * 8);
-    int *start = (int *)p; p += a256((cells + 2) * 4);
-    double *part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
-    GridCells *g = (GridCells *)p; p += a256(sizeof(GridCells));
-    unsigned long long *nfail = (unsigned long long *)p; p += 256;
-    double *spart = (double *)p; p += a256(GI_NDIR * GI_DIR_SLICES * 8);
-    unsigned *slow = (unsigned *)p; p += slow_cap_bytes(n);
-    Rings R;
-    R.ring = (int *)p; p += a256(n * GI_DEG * 4);
-    R.deg = (unsigned char *)p; p += a256(n);
-    R.open = (unsigned char *)p; p += a256(n);
-    p += a256(n * 4) + a256(n * 16) + 256;
-    void *sort_scr = p;
-    const int nb = grid_for(num, 256 * 4, 4) < GI_BBOX_BLOCKS ? grid_for(num, 256 * 4, 4) : GI_BBOX_BLOCKS;
-    PXF_CUDA(cudaMemsetAsync(nfail, 0, 32, s));
-    PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
-    k_bbox_partial<<<nb, 256, 0, s>>>(x, y, num, part);
-    k_support_partial<<<GI_NDIR * GI_DIR_SLICES, 256, 0, s>>>(x, y, num, spart);
-    k_grid_setup<<<1, 64, 0, s>>>(part, nb, num, (int)(cells - 2), g, spart);
-    k_cell_keys<<<grid_for(num, 256, 8), 256, 0, s>>>(x, y, num, g, key);
-    count_launch(4);
-    int rc = pxf_argsort(key, num, skey, reinterpret_cast<int64_t *>(perm), sort_scr, stream);
+    const InterpScratch w = interp_carve(scratch, (size_t)num);
+    int rc = interp_bin(w, x, y, x, num, stream);
     if (rc) return rc;
-    k_cell_starts<<<grid_for(num, 256, 8), 256, 0, s>>>(skey, perm, num, g, x, y, x, start, sx, sy, sv);
-    int rq_dt = GI_RQ_DT;
-    if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);
-    k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow, rq_dt);
-    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(sx, sy, start, g, (int)num, R, nfail, slow);
-    k_rings_export<<<(unsigned)((num + 255) / 256), 256, 0, s>>>(R, perm, (int)num, ring_out, deg_out, open_out);
-    count_launch(4);
+    if ((rc = interp_rings(w, num, s))) return rc;
+    k_rings_export<<<(unsigned)((num + 255) / 256), 256, 0, s>>>(w.R, w.perm, (int)num, ring_out, deg_out, open_out);
+    count_launch();
     if ((rc = check_launch("pxf_delaunay_neighbors"))) return rc;
-    unsigned long long hf[4] = {0, 0, 0, 0};
-    PXF_CUDA(cudaMemcpyAsync(hf, nfail, 32, cudaMemcpyDeviceToHost, s));
-    PXF_CUDA(cudaStreamSynchronize(s));
-    if (hf[0]) {
-        set_error("pxf_delaunay_neighbors: %llu points have no neighbour ring (duplicate points, or more than %d neighbours)", hf[0], GI_DEG);
-        return PXF_ERR_UNSUPPORTED;
-    }
     return PXF_OK;
 }
 
