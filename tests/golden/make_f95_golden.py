@@ -249,6 +249,29 @@ def main():
             same = all(np.array_equal(u, v, equal_nan=True) for u, v in zip(o, (xa, ya, ph)))
             print("%-44s %s" % (tag, "== oracle" if same else "DIFFERS"))
             bad += not same
+    # specialFunctions.f95 called directly: Legendre polynomials and derivatives, radial Zernike polynomials, zernset
+    sp = f95run.load(os.path.join(REF, "specialFunctions.f95"))
+    xs = g.uniform(-1., 1., 6)
+    leg = np.array([[[sp["legendre"](x, n), sp["legendrep"](x, n)] for x in xs] for n in range(9)], dtype=np.float64)
+    rhos = np.concatenate([[0.], g.uniform(0., 1., 4)])
+    nm = [(n, m) for n in range(9) for m in range(n % 2, n + 1, 2)]
+    rad = np.array([[sp["radialpoly"](r_, n, m) for r_ in rhos] for n, m in nm], dtype=np.float64)
+    ro, ao = np.array([n for n in range(5) for _ in range(n + 1)], dtype=np.int32), np.array([m for n in range(5) for m in range(-n, n + 1, 2)], dtype=np.int32)
+    zs = []
+    for r_, th in ((.3, .7), (0., .2), (.99, -2.)):
+        po, dr, dt = (np.zeros(len(ro)) for _ in range(3))
+        sp["zernset"](r_, th, ro, ao, len(ro), po, dr, dt)
+        zs.append([po, dr, dt])
+    store.update(sf_x=xs, sf_legendre=leg, sf_rho=rhos, sf_nm=np.array(nm), sf_radialpoly=rad, sf_rorder=ro, sf_aorder=ao,
+                 sf_zernset_args=np.array([(.3, .7), (0., .2), (.99, -2.)]), sf_zernset=np.array(zs))
+    if check:
+        ok = all(of.specialfunctions.legendre(x, n) == leg[n, i, 0] and of.specialfunctions.legendrep(x, n) == leg[n, i, 1]
+                 for n in range(9) for i, x in enumerate(xs))
+        ok = ok and all(of.specialfunctions.radialpoly(r_, n, m) == rad[k, i] for k, (n, m) in enumerate(nm) for i, r_ in enumerate(rhos))
+        for (r_, th), want in zip(((.3, .7), (0., .2), (.99, -2.)), zs):
+            ok = ok and all(np.array_equal(u, v) for u, v in zip(of.specialfunctions.zernset(r_, th, ro, ao), want))
+        print("%-44s %s" % ("specialFunctions (legendre, radialpoly, zernset)", "== oracle" if ok else "DIFFERS"))
+        bad += not ok
     if "--no-write" not in sys.argv:
         np.savez_compressed(os.path.join(HERE, "f95_source.npz"), **store)
     print("%d cases, %d differ from the C oracle" % (len(store) and k + 1, bad) if check else "%d cases written" % (k + 1))

@@ -89,6 +89,22 @@ def test_c_oracle_reproduces_the_fortran_source(fixture):
             assert np.array_equal(got, fixture[tag + "__" + k], equal_nan=True), tag
 
 
+def test_c_oracle_special_functions_against_the_fortran_source(fixture):
+    """specialFunctions.f95 called directly: legendre / legendrep (:337-388), radialpoly (:17-40), zernset (:142-234)."""
+    fx = fixture
+    for n in range(9):
+        for i, x in enumerate(fx["sf_x"]):
+            assert of.specialfunctions.legendre(x, n) == fx["sf_legendre"][n, i, 0]
+            assert of.specialfunctions.legendrep(x, n) == fx["sf_legendre"][n, i, 1]
+    for k, (n, m) in enumerate(fx["sf_nm"]):
+        for i, rho in enumerate(fx["sf_rho"]):
+            assert of.specialfunctions.radialpoly(rho, int(n), int(m)) == fx["sf_radialpoly"][k, i]
+    for (rho, th), want in zip(fx["sf_zernset_args"], fx["sf_zernset"]):
+        got = of.specialfunctions.zernset(rho, th, fx["sf_rorder"], fx["sf_aorder"])
+        for u, v in zip(got, want):
+            assert np.array_equal(u, v)
+
+
 @pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
 def test_translated_fortran_reproduces_the_fixture(fixture):
     """Re-run the translator on a third of the cases (the whole set takes a few minutes in Python)."""
