@@ -205,6 +205,18 @@ def _logical_lines(path, seen=None):
     return lines
 
 
+def _logical_lines_no_include(path):
+    """The file's own lines (its ``include`` lines dropped): which units a file DEFINES rather than pulls in."""
+    import tempfile
+    text = "\n".join(ln for ln in open(path, errors="replace").read().splitlines() if not re.match(r"\s*include\s+'", ln, re.I))
+    with tempfile.NamedTemporaryFile("w", suffix=".f95", delete=False) as f:
+        f.write(text)
+    try:
+        return _logical_lines(f.name)
+    finally:
+        os.unlink(f.name)
+
+
 _TYPE = re.compile(r"^(real\*8|real\*4|double precision|real|integer|logical)\b(.*)$")
 _UNIT = re.compile(r"^(?:recursive\s+)?(?:(real\*8|real\*4|real|integer|double precision)\s+)?(subroutine|function)\s+(\w+)\s*"
                    r"\(([^)]*)\)\s*(?:result\s*\((\w+)\))?$")

@@ -3,6 +3,8 @@
 Run in the BUILD container only (needs /root/reference):
 
     python tests/golden/make_golden.py
+    python tests/golden/make_golden.py --fortran-source     # re-derive every fixture from the reference's Fortran TEXT
+                                                            # (oracle/f95run.py in the f2py slots) and compare, writing nothing
 
 It imports the reference's *unmodified* Python layer (sources / transformations / surfaces /
 analyses) through ``oracle.refload`` -- with the C oracle standing in for the four f2py
@@ -31,7 +33,23 @@ def pack(prefix, rays):
 
 
 def main():
-    ref = refload.load()
+    fortran = "--fortran-source" in sys.argv
+    if fortran:
+        # the unmodified Python layer over the unmodified Fortran source text: the whole reference.  Nothing is written;
+        # every array the script would store is compared with the committed fixture instead.
+        from oracle import f95mods
+        ref = refload.load(f2py_modules=f95mods.modules())
+        report = []
+
+        def compare(path, **g):
+            old = np.load(path)
+            bad = [k for k in g if k not in old.files or not np.array_equal(np.asarray(g[k]), old[k], equal_nan=True)]
+            report.append((os.path.basename(path), len(g), bad))
+            print("%-18s %3d arrays: %s" % (os.path.basename(path), len(g), "identical" if not bad else "DIFFER: " + ", ".join(bad)),
+                  flush=True)
+        np.savez_compressed = compare
+    else:
+        ref = refload.load()
     src, tran, surf, anal = ref.sources, ref.transformations, ref.surfaces, ref.analyses
     out = {}
 

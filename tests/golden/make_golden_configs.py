@@ -28,7 +28,12 @@ def stack(rays, rows):
 
 
 def main():
-    api = ex.make_api(refload.load(), ex.NumpyXP, "reference")
+    fortran = "--fortran-source" in sys.argv      # the reference's Fortran TEXT in the f2py slots: compare, write nothing
+    if fortran:
+        from oracle import f95mods
+        api = ex.make_api(refload.load(f2py_modules=f95mods.modules()), ex.NumpyXP, "reference over its own Fortran")
+    else:
+        api = ex.make_api(refload.load(), ex.NumpyXP, "reference")
     g = {}
     ap = ex.ws_aperture(api)
     g["c2_aperture"] = np.array(ap)
@@ -51,6 +56,11 @@ def main():
     g["c5_rows"] = stack(r["rays"], range(1, 10))
     g["c5_weights"] = np.asarray(r["weights"])
     g["c5_scalars"] = np.array([r["kept"], r["hpd"], r["rms"], r["cx"], r["cy"], r["area"]])
+    if fortran:
+        old = np.load(os.path.join(HERE, "configs.npz"))
+        bad = [k for k in g if k not in old.files or not np.array_equal(np.asarray(g[k]), old[k], equal_nan=True)]
+        print("%-18s %3d arrays: %s" % ("configs.npz", len(g), "identical" if not bad else "DIFFER: " + ", ".join(bad)))
+        return
     np.savez_compressed(os.path.join(HERE, "configs.npz"), **g)
     print("wrote configs.npz:", sum(v.nbytes for v in g.values()), "bytes raw")
 

@@ -200,3 +200,37 @@ def test_libpxf_reproduces_the_fortran_source(fixture):
             assert_close(got, rout, pos_scale=scale, tol=1e-12, what=tag)
         n += 1
     assert n >= 53
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_whole_reference_runs_here_and_equals_the_oracle_driven_reference():
+    """The reference ITSELF, end to end, in a container without a Fortran compiler: its unmodified Python layer
+    (sources / surfaces / transformations / analyses, imported from /root/reference) over its unmodified Fortran text
+    executed by oracle/f95run.py (``oracle.f95mods`` in the f2py slots) -- against the same layer over the C oracle,
+    which is how every golden fixture under tests/golden/ was produced.  All five BASELINE configurations at small
+    sizes: every ray row, surviving-index set and merit figure bit for bit."""
+    from oracle import f95mods
+    from pyxfocus_b200 import examples as ex
+    src_api = ex.make_api(refload.load(f2py_modules=f95mods.modules()), ex.NumpyXP, "reference over its own Fortran")
+    runs_src = [ex.config1(src_api, 400, 3),
+                ex.config2_point(src_api, 150, 5. / 60. * np.pi / 180., ex.ws_aperture(src_api), 5),
+                ex.config2_point(src_api, 60, 24. / 60. * np.pi / 180., ex.ws_aperture(src_api), 6),
+                ex.config3(src_api, 300, 2),
+                ex.config4(src_api, 6, 20, order=-2, wave=2.4, rng_seed=4, offX=1e-4, offY=-2e-4),
+                ex.config5(src_api, 12, 20, offaxis=2e-4, rng_seed=7)]
+    orc_api = ex.make_api(refload.load(), ex.NumpyXP, "reference over the C oracle")
+    runs_orc = [ex.config1(orc_api, 400, 3),
+                ex.config2_point(orc_api, 150, 5. / 60. * np.pi / 180., ex.ws_aperture(orc_api), 5),
+                ex.config2_point(orc_api, 60, 24. / 60. * np.pi / 180., ex.ws_aperture(orc_api), 6),
+                ex.config3(orc_api, 300, 2),
+                ex.config4(orc_api, 6, 20, order=-2, wave=2.4, rng_seed=4, offX=1e-4, offY=-2e-4),
+                ex.config5(orc_api, 12, 20, offaxis=2e-4, rng_seed=7)]
+
+    def same(a, b):
+        return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+    for k, (a, b) in enumerate(zip(runs_src, runs_orc)):
+        for key in a:
+            if isinstance(a[key], list):
+                assert all(same(x, y) for x, y in zip(a[key], b[key])), (k, key)
+            else:
+                assert same(a[key], b[key]), (k, key)
