@@ -20,7 +20,9 @@
  * deviation of a real gfortran build from those rules (none is known for
  * baseline x86-64 without -ffast-math).  Further pins: (a) physics known-answer
  * checks (tests/test_oracle_kat.py) and (b) golden vectors produced by the
- * reference's own *Python* layer driving this file (tests/golden/).
+ * reference's own *Python* layer driving this file (tests/golden/) -- every
+ * one of which re-derives identically with the Fortran text itself in the
+ * f2py slots (oracle/f95mods.py; make_golden.py --fortran-source).
  *
  * Conventions restated from the Fortran (all citations relative to the
  * reference tree):
