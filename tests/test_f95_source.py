@@ -234,3 +234,75 @@ def test_whole_reference_runs_here_and_equals_the_oracle_driven_reference():
                 assert all(same(x, y) for x, y in zip(a[key], b[key])), (k, key)
             else:
                 assert same(a[key], b[key]), (k, key)
+
+
+def test_translator_control_flow_and_precedence():
+    """More rules of the translator: ** is right associative and binds tighter than unary minus, logical operators,
+    zero-trip and negative-step do loops, do while / exit / cycle, recursive functions with a result variable, integer
+    mod / sign, 2-D arrays in (row, column) order, ';'-separated statements and '&' continuations."""
+    import tempfile
+    src = '''
+subroutine rules(out)
+  implicit none
+  real*8, intent(inout) :: out(12)
+  integer :: i, k, grid(2,3)
+  real*8 :: acc
+  real*8 :: fact
+  out(1) = 2**3**2
+  out(2) = -2**2
+  out(3) = 2*3 + 4*5 - &
+           6/4
+  k = 0
+  do i = 5, 1
+    k = k + 1
+  end do
+  out(4) = k
+  k = 0
+  do i = 10, 1, -3
+    k = k + i
+  end do
+  out(5) = k
+  k = 0 ; i = 0
+  do while (.true.)
+    i = i + 1
+    if (i > 10) exit
+    if (mod(i,2) == 0) cycle
+    k = k + i
+  end do
+  out(6) = k
+  out(7) = fact(5)
+  out(8) = sign(3, -2) + mod(-7, 3)
+  if (.not. (1 > 2) .and. (3 >= 3 .or. 1 == 2)) then
+    out(9) = 1
+  else
+    out(9) = 0
+  end if
+  grid(2,3) = 7 ; grid(1,1) = 1
+  out(10) = grid(2,3) - grid(1,1)
+  acc = 1.d0/3
+  out(11) = acc
+  out(12) = 1./3
+end subroutine rules
+
+recursive function fact(n) result(f)
+  implicit none
+  integer, intent(in) :: n
+  real*8 :: f
+  real*8 :: fact
+  if (n <= 1) then
+    f = 1
+    return
+  end if
+  f = n*fact(n-1)
+end function fact
+'''
+    with tempfile.NamedTemporaryFile("w", suffix=".f95", delete=False) as f:
+        f.write(src)
+    try:
+        U = f95run.load(f.name)
+    finally:
+        os.unlink(f.name)
+    out = np.zeros(12)
+    U["rules"](out)
+    assert out[:10].tolist() == [512., -4., 25., 0., 22., 25., 120., -4., 1., 6.]
+    assert out[10] == 1. / 3. and out[11] == np.float64(np.float32(1.) / np.float32(3.))
