@@ -28,7 +28,7 @@ namespace pxf {
 #define GI_MAX_PIVOTS 512
 #define GI_ILP 8              // independent point loads in flight per lane in the all-points passes
 
-#define GI_NDIR 64          // support directions of the outer hull approximation
+#define GI_NDIR 256         // support directions of the outer hull approximation (the band between hull and polygon shrinks as 1/NDIR^2)
 #define GI_DIR_SLICES 32
 struct GridCells {
     double x0, y0, x1, y1, h;   // bounding box, cell size
