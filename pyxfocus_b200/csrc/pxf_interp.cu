@@ -593,16 +593,20 @@ struct Cubic { const double *grad; Rings R; };     // grad == nullptr: linear
 #define GI_RQ 12               // rings searched for the quadrant points before a query is handed to the warp kernel
 #define GI_CELL_BUDGET 4096    // cells under one circumcircle a single thread may scan
 
-// Steps 3 and 4 for one query from a start triangle (ia, ib, ic: counter-clockwise, holds q).  COOP: the 32 lanes of a
-// warp work on the SAME query: the rows of cells under the circumcircle are dealt out to the lanes and the deepest
-// point is agreed on by shuffles.  Returns 0: *res holds the value, 1: over the single-thread budget (not COOP), 2: failed.
+// Steps 3 and 4 for one query from a start triangle (ia, ib, ic: counter-clockwise, holds q).  COOP: ALL threads of the
+// CTA work on the SAME query (identical control flow): the points of the cells under the circumcircle are dealt out to
+// the threads and the deepest one is agreed on by shuffles and a shared-memory round.  Returns 0: *res holds the value
+// (thread 0 when COOP), 1: over the single-thread budget (not COOP), 2: failed.
 template <bool COOP>
 PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
                                    const double *__restrict__ sv, const int *__restrict__ start, double qx, double qy,
                                    int ia, int ib, int ic, double *res, const Cubic &cub)
 {
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    const int lane = COOP ? (threadIdx.x & 31) : 0;
+    const int lane = COOP ? (int)threadIdx.x : 0;             // position among the cooperating threads
+    const int nco = COOP ? (int)blockDim.x : 1;
+    __shared__ double co_w[32];
+    __shared__ int co_i[32];
     double ax = sx[ia] - qx, ay = sy[ia] - qy, bx = sx[ib] - qx, by = sy[ib] - qy, cx_ = sx[ic] - qx, cy_ = sy[ic] - qy;
     bool settled = false;
     for (int it = 0; it < GI_MAX_PIVOTS; it++) {
@@ -628,16 +632,16 @@ PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict_
             // the lanes share each row's point range, GI_ILP independent loads in flight per lane
             for (int j = j0; j <= j1; j++) {
                 const int p0 = start[j * g.gx + i0], p1 = start[j * g.gx + i1 + 1];  // cells of one row are contiguous
-                for (int pb = p0 + lane; pb < p1; pb += 32 * GI_ILP) {
+                for (int pb = p0 + lane; pb < p1; pb += nco * GI_ILP) {
                     double xs[GI_ILP], ys[GI_ILP];
 #pragma unroll
                     for (int u = 0; u < GI_ILP; u++) {
-                        const int p = pb + 32 * u;
+                        const int p = pb + nco * u;
                         xs[u] = p < p1 ? sx[p] : 0.; ys[u] = p < p1 ? sy[p] : 0.;
                     }
 #pragma unroll
                     for (int u = 0; u < GI_ILP; u++) {
-                        const int p = pb + 32 * u;
+                        const int p = pb + nco * u;
                         if (p >= p1) break;
                         if (p == ia || p == ib || p == ic) continue;
                         const double v = incircle(ax, ay, bx, by, cx_, cy_, xs[u] - qx, ys[u] - qy);
@@ -661,6 +665,17 @@ PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict_
                 const double ov = __shfl_xor_sync(0xffffffffu, worst, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, iw, o);
                 if (oi >= 0 && (iw < 0 || ov > worst || (ov == worst && oi < iw))) { worst = ov; iw = oi; }
+            }
+            if (nco > 32) {
+                if ((lane & 31) == 0) { co_w[lane >> 5] = worst; co_i[lane >> 5] = iw; }
+                __syncthreads();
+                worst = tol; iw = -1;
+                for (int k = 0; k < (nco >> 5); k++) {
+                    const double ov = co_w[k];
+                    const int oi = co_i[k];
+                    if (oi >= 0 && (iw < 0 || ov > worst || (ov == worst && oi < iw))) { worst = ov; iw = oi; }
+                }
+                __syncthreads();
             }
         }
         if (iw < 0) { settled = true; break; }
@@ -687,7 +702,7 @@ PXF_DEV int settle_and_interpolate(const GridCells &g, const double *__restrict_
     const double oab = ax * by - ay * bx, obc = bx * cy_ - by * cx_, oca = cx_ * ay - cy_ * ax;
     if (cub.grad) {
         const double bb[3] = {obc / area, oca / area, oab / area};
-        if (COOP && lane != 0) return 0;
+        if (COOP && lane != 0) return 0;                        // (thread 0 evaluates the patch)
         return clough_tocher(sx, sy, sv, cub.grad, cub.R, ia, ib, ic, bb, res) ? 0 : 2;
     }
     *res = obc / area * sv[ia] + oca / area * sv[ib] + oab / area * sv[ic];
@@ -823,11 +838,13 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
     if (rc == 2) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
 }
 
-// One warp per deferred query: a start triangle from a pass over ALL points -- with a = the first point as the zero
+// One CTA per deferred query: a start triangle from a pass over ALL points -- with a = the first point as the zero
 // direction, b = the point turned farthest counter-clockwise (by less than pi) and c = farthest clockwise: if b and c
 // are less than pi apart on the far side the triangle a, b, c holds q, otherwise an empty half-plane through q exists
-// and q is outside the hull -- then the same pivoting with the scans dealt out to the lanes.
-__global__ void __launch_bounds__(GI_THREADS)
+// and q is outside the hull -- then the same pivoting with the scans dealt out to the threads.  (The deferred queries
+// are few, so what counts is the latency of ONE of them: 256 threads with eight loads in flight each.)
+#define GI_COOP_THREADS 256
+__global__ void __launch_bounds__(GI_COOP_THREADS)
 k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
                 const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
                 const double *__restrict__ qys, double *__restrict__ out, unsigned long long *__restrict__ nfail,
@@ -835,27 +852,27 @@ k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
 {
     const GridCells &g = *gp;
     const unsigned nslow = slow[0];
-    const int lane = threadIdx.x & 31;
-    const unsigned wpb = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const double nanv = __longlong_as_double(0x7ff8000000000000ll);
     const int np = start[g.gx * g.gy];
-    for (unsigned w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nslow; w += gridDim.x * wpb) {
+    __shared__ int s_jb[32], s_jc[32], s_rc;
+    __shared__ double s_bx[32], s_by[32], s_cx[32], s_cy[32];
+    for (unsigned w = blockIdx.x; w < nslow; w += gridDim.x) {
         const int64_t iq = slow[1 + w];
         const double qx = qxs[iq], qy = qys[iq];
         const double a0x = sx[0] - qx, a0y = sy[0] - qy;
         int jb = -1, jc = -1;
         double bxx = 0., byy = 0., cxx = 0., cyy = 0.;
-        // (eight independent loads in flight per lane: one warp per query is otherwise bound by load latency)
-        for (int p0 = 1 + lane; p0 < np; p0 += 32 * GI_ILP) {
+        for (int p0 = 1 + tid; p0 < np; p0 += (int)blockDim.x * GI_ILP) {
             double xs[GI_ILP], ys[GI_ILP];
 #pragma unroll
             for (int u = 0; u < GI_ILP; u++) {
-                const int p = p0 + 32 * u;
+                const int p = p0 + (int)blockDim.x * u;
                 xs[u] = p < np ? sx[p] : qx; ys[u] = p < np ? sy[p] : qy;
             }
 #pragma unroll
             for (int u = 0; u < GI_ILP; u++) {
-                const int p = p0 + 32 * u;
+                const int p = p0 + (int)blockDim.x * u;
                 if (p >= np) break;
                 const double dx = xs[u] - qx, dy = ys[u] - qy;
                 const double cr = a0x * dy - a0y * dx;                   // > 0: counter-clockwise of a
@@ -864,12 +881,12 @@ k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
                 if ((cr < 0. || opposite) && (jc < 0 || cxx * dy - cyy * dx < 0.)) { jc = p; cxx = dx; cyy = dy; }
             }
         }
+        // (the same direction from two threads: the lower index, so that all of them keep the same point)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const int ob = __shfl_xor_sync(0xffffffffu, jb, o), oc = __shfl_xor_sync(0xffffffffu, jc, o);
             const double obx = __shfl_xor_sync(0xffffffffu, bxx, o), oby = __shfl_xor_sync(0xffffffffu, byy, o);
             const double ocx = __shfl_xor_sync(0xffffffffu, cxx, o), ocy = __shfl_xor_sync(0xffffffffu, cyy, o);
-            // (the same direction from two lanes: the lower index, so that both partners keep the same point)
             if (ob >= 0) {
                 const double t = bxx * oby - byy * obx;
                 if (jb < 0 || t > 0. || (t == 0. && ob < jb)) { jb = ob; bxx = obx; byy = oby; }
@@ -879,15 +896,31 @@ k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
                 if (jc < 0 || t < 0. || (t == 0. && oc < jc)) { jc = oc; cxx = ocx; cyy = ocy; }
             }
         }
-        // b counter-clockwise to c through the far side is less than pi  <=>  c is counter-clockwise of b
-        if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { if (lane == 0) out[iq] = nanv; continue; }
-        double val = nanv;
-        int rc = settle_and_interpolate<true>(g, sx, sy, sv, start, qx, qy, 0, jb, jc, &val, cub);
-        rc = __shfl_sync(0xffffffffu, rc, 0);
-        if (lane == 0) {
-            out[iq] = val;
-            if (rc) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
+        if (lane == 0) { s_jb[warp] = jb; s_bx[warp] = bxx; s_by[warp] = byy; s_jc[warp] = jc; s_cx[warp] = cxx; s_cy[warp] = cyy; }
+        __syncthreads();
+        jb = -1; jc = -1;
+        for (int k = 0; k < nwarp; k++) {
+            if (s_jb[k] >= 0) {
+                const double t = bxx * s_by[k] - byy * s_bx[k];
+                if (jb < 0 || t > 0. || (t == 0. && s_jb[k] < jb)) { jb = s_jb[k]; bxx = s_bx[k]; byy = s_by[k]; }
+            }
+            if (s_jc[k] >= 0) {
+                const double t = cxx * s_cy[k] - cyy * s_cx[k];
+                if (jc < 0 || t < 0. || (t == 0. && s_jc[k] < jc)) { jc = s_jc[k]; cxx = s_cx[k]; cyy = s_cy[k]; }
+            }
         }
+        __syncthreads();
+        // b counter-clockwise to c through the far side is less than pi  <=>  c is counter-clockwise of b
+        if (jb < 0 || jc < 0 || !(bxx * cyy - byy * cxx > 0.)) { if (tid == 0) out[iq] = nanv; continue; }
+        double val = nanv;
+        const int rc = settle_and_interpolate<true>(g, sx, sy, sv, start, qx, qy, 0, jb, jc, &val, cub);
+        if (tid == 0) s_rc = rc;
+        __syncthreads();
+        if (tid == 0) {
+            out[iq] = val;
+            if (s_rc) { atomicAdd(nfail, 1ull); atomicAdd(nfail + 3, 1ull); }
+        }
+        __syncthreads();
     }
 }
 
@@ -1091,7 +1124,7 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
         }
         PXF_CUDA(cudaMemsetAsync(slow, 0, 4, s));
         k_griddata<1><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow, cub);
-        k_griddata_warp<<<grid_for(nb_q, 1, 8), GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, out + q0, nfail, slow, cub);
+        k_griddata_warp<<<grid_for(nb_q, 1, 4), GI_COOP_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, out + q0, nfail, slow, cub);
         count_launch(2);
     }
     if ((rc = check_launch("pxf_griddata"))) return rc;
