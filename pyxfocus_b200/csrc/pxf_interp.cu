@@ -25,6 +25,7 @@
 namespace pxf {
 
 #define GI_THREADS 128
+#define GI_COOP_THREADS 256    // threads of a CTA that share ONE deferred query / vertex
 #define GI_MAX_PIVOTS 512
 #define GI_ILP 8              // independent point loads in flight per lane in the all-points passes
 
@@ -251,16 +252,17 @@ PXF_DEV int apex_of_edge(const GridCells &g, const double *__restrict__ sx, cons
 PXF_DEV void apex_scan_range(const double *__restrict__ sx, const double *__restrict__ sy, int p0, int p1, int lane, int ip, int in_,
                              double px, double py, double ex, double ey, double e2, double side, double &tbest, int &best)
 {
-    for (int q0 = p0 + lane; q0 < p1; q0 += 32 * GI_ILP) {
+    const int nco = (int)blockDim.x;                  // `lane`: position among the CTA's threads, which share the search
+    for (int q0 = p0 + lane; q0 < p1; q0 += nco * GI_ILP) {
         double xs[GI_ILP], ys[GI_ILP];
 #pragma unroll
         for (int u = 0; u < GI_ILP; u++) {
-            const int q = q0 + 32 * u;
+            const int q = q0 + nco * u;
             xs[u] = q < p1 ? sx[q] : px; ys[u] = q < p1 ? sy[q] : py;
         }
 #pragma unroll
         for (int u = 0; u < GI_ILP; u++) {
-            const int q = q0 + 32 * u;
+            const int q = q0 + nco * u;
             if (q >= p1) break;
             if (q == ip || q == in_) continue;
             const double x = xs[u] - px, y = ys[u] - py;
@@ -272,23 +274,38 @@ PXF_DEV void apex_scan_range(const double *__restrict__ sx, const double *__rest
     }
 }
 
+// every thread of the CTA ends up with the same (smallest t, lowest index) pair
 PXF_DEV void apex_agree(double &tbest, int &best)
 {
+    __shared__ double a_t[32];
+    __shared__ int a_b[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ot = __shfl_xor_sync(0xffffffffu, tbest, o);
         const int ob = __shfl_xor_sync(0xffffffffu, best, o);
         if (ob >= 0 && (best < 0 || ot < tbest || (ot == tbest && ob < best))) { tbest = ot; best = ob; }
     }
+    const int nw = blockDim.x >> 5;
+    if (nw > 1) {
+        if ((threadIdx.x & 31) == 0) { a_t[threadIdx.x >> 5] = tbest; a_b[threadIdx.x >> 5] = best; }
+        __syncthreads();
+        tbest = __longlong_as_double(0x7ff0000000000000ll); best = -1;
+        for (int k = 0; k < nw; k++) {
+            const double ot = a_t[k];
+            const int ob = a_b[k];
+            if (ob >= 0 && (best < 0 || ot < tbest || (ot == tbest && ob < best))) { tbest = ot; best = ob; }
+        }
+        __syncthreads();
+    }
 }
 
-// the same by the 32 lanes of a warp (every lane returns the result): a candidate from the block of cells the thread
+// the same by all threads of a CTA (every thread returns the result): a candidate from the block of cells the thread
 // kernel gave up on, then every cell under the candidate's circle (any better apex lies inside it); only an edge
 // with no candidate nearby -- a hull edge -- takes a pass over ALL points
 PXF_DEV int apex_of_edge_warp(const GridCells &g, const double *__restrict__ sx, const double *__restrict__ sy,
                               const int *__restrict__ start, int np, int ip, int in_, double side)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x;
     const double px = sx[ip], py = sy[ip];
     const double ex = sx[in_] - px, ey = sy[in_] - py;
     const double e2 = ex * ex + ey * ey;
@@ -388,31 +405,32 @@ k_dt_rings(const double *__restrict__ sx, const double *__restrict__ sy, const i
     R.open[ip] = open ? 1 : 0;
 }
 
-// One warp per deferred vertex (beside the hull): the same gift wrapping with every apex taken over all points.
-__global__ void __launch_bounds__(GI_THREADS)
+// One CTA per deferred vertex (beside the hull): the same gift wrapping with every apex searched by all threads.
+__global__ void __launch_bounds__(GI_COOP_THREADS)
 k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, const int *__restrict__ start,
                 const GridCells *__restrict__ gp, int num, Rings R, unsigned long long *__restrict__ nfail,
                 const unsigned *__restrict__ slow)
 {
     const GridCells &g = *gp;
     const unsigned nslow = slow[0];
-    const int lane = threadIdx.x & 31;
-    const unsigned wpb = blockDim.x >> 5;
-    for (unsigned w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nslow; w += gridDim.x * wpb) {
+    const int tid = threadIdx.x;
+    __shared__ double n_d[32];
+    __shared__ int n_i[32];
+    for (unsigned w = blockIdx.x; w < nslow; w += gridDim.x) {
         const int ip = (int)slow[1 + w];
         const double px = sx[ip], py = sy[ip];
         double best = __longlong_as_double(0x7ff0000000000000ll);
         int n0 = -1;
-        for (int q0 = lane; q0 < num; q0 += 32 * GI_ILP) {
+        for (int q0 = tid; q0 < num; q0 += (int)blockDim.x * GI_ILP) {
             double xs[GI_ILP], ys[GI_ILP];
 #pragma unroll
             for (int u = 0; u < GI_ILP; u++) {
-                const int q = q0 + 32 * u;
+                const int q = q0 + (int)blockDim.x * u;
                 xs[u] = q < num ? sx[q] : px; ys[u] = q < num ? sy[q] : py;
             }
 #pragma unroll
             for (int u = 0; u < GI_ILP; u++) {
-                const int q = q0 + 32 * u;
+                const int q = q0 + (int)blockDim.x * u;
                 if (q >= num || q == ip) continue;
                 const double x = xs[u] - px, y = ys[u] - py, d2 = x * x + y * y;
                 if (d2 < best || (d2 == best && q < n0)) { best = d2; n0 = q; }
@@ -424,19 +442,25 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
             const int on = __shfl_xor_sync(0xffffffffu, n0, o);
             if (on >= 0 && (n0 < 0 || od < best || (od == best && on < n0))) { best = od; n0 = on; }
         }
+        if ((tid & 31) == 0) { n_d[tid >> 5] = best; n_i[tid >> 5] = n0; }
+        __syncthreads();
+        best = __longlong_as_double(0x7ff0000000000000ll); n0 = -1;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++)
+            if (n_i[k] >= 0 && (n0 < 0 || n_d[k] < best || (n_d[k] == best && n_i[k] < n0))) { best = n_d[k]; n0 = n_i[k]; }
+        __syncthreads();
         int *out = R.ring + (size_t)ip * GI_DEG;       // assembled in place: clockwise part reversed at the end
         int nccw = 0, ncw = 0;
         bool ok = n0 >= 0 && best > 0., open = false;
         int cwbuf[GI_DEG];
         if (ok) {
-            if (lane == 0) out[0] = n0;
+            if (tid == 0) out[0] = n0;
             nccw = 1;
             for (int cur = n0;;) {
                 const int d = apex_of_edge_warp(g, sx, sy, start, num, ip, cur, 1.);
                 if (d < 0) { open = true; break; }
                 if (d == n0) break;
                 if (nccw >= GI_DEG) { ok = false; break; }
-                if (lane == 0) out[nccw] = d;
+                if (tid == 0) out[nccw] = d;
                 nccw++;
                 cur = d;
             }
@@ -449,7 +473,7 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
                     cur = d;
                 }
         }
-        if (lane == 0) {
+        if (tid == 0) {
             if (!ok) { R.deg[ip] = 0; R.open[ip] = 1; atomicAdd(nfail, 1ull); atomicAdd(nfail + 2, 1ull); }
             else {
                 // shift the counter-clockwise part up and put the clockwise part, reversed, in front
@@ -459,6 +483,7 @@ k_dt_rings_warp(const double *__restrict__ sx, const double *__restrict__ sy, co
                 R.open[ip] = open ? 1 : 0;
             }
         }
+        __syncthreads();
     }
 }
 
@@ -843,7 +868,6 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
 // are less than pi apart on the far side the triangle a, b, c holds q, otherwise an empty half-plane through q exists
 // and q is outside the hull -- then the same pivoting with the scans dealt out to the threads.  (The deferred queries
 // are few, so what counts is the latency of ONE of them: 256 threads with eight loads in flight each.)
-#define GI_COOP_THREADS 256
 __global__ void __launch_bounds__(GI_COOP_THREADS)
 k_griddata_warp(const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
                 const int *__restrict__ start, const GridCells *__restrict__ gp, const double *__restrict__ qxs,
@@ -1027,7 +1051,7 @@ static int interp_rings(const InterpScratch &w, int64_t num, cudaStream_t s)
     if (const char *e = getenv("PXF_GRID_RQ")) rq_dt = atoi(e);          // (tuning / debugging)
     k_dt_rings<<<(unsigned)((num + GI_THREADS - 1) / GI_THREADS), GI_THREADS, 0, s>>>(w.sx, w.sy, w.start, w.g, (int)num, w.R, w.nfail,
                                                                                        w.slow, rq_dt);
-    k_dt_rings_warp<<<grid_for(num, 1, 8), GI_THREADS, 0, s>>>(w.sx, w.sy, w.start, w.g, (int)num, w.R, w.nfail, w.slow);
+    k_dt_rings_warp<<<grid_for(num, 1, 4), GI_COOP_THREADS, 0, s>>>(w.sx, w.sy, w.start, w.g, (int)num, w.R, w.nfail, w.slow);
     count_launch(2);
     unsigned long long hf[4] = {0, 0, 0, 0};
     PXF_CUDA(cudaMemcpyAsync(hf, w.nfail, 32, cudaMemcpyDeviceToHost, s));
