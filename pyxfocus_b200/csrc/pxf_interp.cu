@@ -157,6 +157,28 @@ k_cell_starts(const double *__restrict__ skey, const long long *__restrict__ per
 }
 
 // ---------------------------------------------------------------- the query kernel
+// per row of cells: the next non-empty cell at or after each cell, and the previous one at or before it (-1: none).
+// One thread per row.  (For the nearest-neighbour search of queries far from the data.)
+__global__ void __launch_bounds__(128)
+k_row_links(const int *__restrict__ start, const GridCells *__restrict__ gp, int *__restrict__ nxt, int *__restrict__ prv)
+{
+    const int gx = gp->gx, gy = gp->gy;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= gy) return;
+    int last = -1;
+    for (int i = gx - 1; i >= 0; i--) {
+        const int c = j * gx + i;
+        if (start[c + 1] > start[c]) last = c;
+        nxt[c] = last;
+    }
+    last = -1;
+    for (int i = 0; i < gx; i++) {
+        const int c = j * gx + i;
+        if (start[c + 1] > start[c]) last = c;
+        prv[c] = last;
+    }
+}
+
 // lower bound of the distance from q to any point in a cell outside the (2r+1)^2 block around cell (cx, cy);
 // +inf when the block covers the whole grid
 PXF_DEV double ring_clearance(const GridCells &g, double qx, double qy, int cx, int cy, int r)
@@ -613,7 +635,7 @@ PXF_DEV bool clough_tocher(const double *__restrict__ sx, const double *__restri
     return true;
 }
 
-struct Cubic { const double *grad; Rings R; };     // grad == nullptr: linear
+struct Cubic { const double *grad; Rings R; const int *nxt, *prv; };     // grad == nullptr: linear; nxt / prv: row links ('nearest')
 
 #define GI_RQ 12               // rings searched for the quadrant points before a query is handed to the warp kernel
 #define GI_CELL_BUDGET 4096    // cells under one circumcircle a single thread may scan
@@ -754,23 +776,44 @@ k_griddata(const double *__restrict__ sx, const double *__restrict__ sy, const d
     const int rcap = g.gx > g.gy ? g.gx : g.gy;
 
     if (METHOD == 0) {
-        // nearest neighbour: rings until no unvisited point can be closer
+        // nearest neighbour, row by row of cells outwards from q's row: in each row the non-empty cells nearest to q's
+        // column (per-row links: no walk over empty cells), as long as their lower bound can beat the best so far.  A
+        // query in a corner of the grid, far outside a round aperture, costs O(rows) look-ups instead of O(cells).
         double best = __longlong_as_double(0x7ff0000000000000ll), val = nanv;
-        for (int r = 0; r <= rcap; r++) {
-            for (int j = cy - r; j <= cy + r; j++) {
+        const int *nxt = cub.nxt, *prv = cub.prv;
+        for (int dj = 0; dj < g.gy; dj++) {
+            bool any = false;
+            for (int sgn = 0; sgn < (dj ? 2 : 1); sgn++) {
+                const int j = sgn ? cy - dj : cy + dj;
                 if (j < 0 || j >= g.gy) continue;
-                const bool edge_row = j == cy - r || j == cy + r;
-                for (int i = cx - r; i <= cx + r; i += (edge_row ? 1 : 2 * r > 0 ? 2 * r : 1)) {
-                    if (i < 0 || i >= g.gx) continue;
-                    const int c = j * g.gx + i;
+                // vertical distance from q to the band of row j
+                const double ylo = g.y0 + j * g.h, yhi = ylo + g.h;
+                const double dyb = qy < ylo ? ylo - qy : (qy > yhi ? qy - yhi : 0.);
+                if (dyb * dyb > best) continue;
+                any = true;
+                for (int c = nxt[j * g.gx + cx]; c >= 0;) {            // q's column and to the right
+                    const double xlo = g.x0 + (c - j * g.gx) * g.h;
+                    const double dxb = qx < xlo ? xlo - qx : 0.;
+                    if (dxb * dxb + dyb * dyb > best) break;
                     for (int p = start[c]; p < start[c + 1]; p++) {
                         const double dx = sx[p] - qx, dy = sy[p] - qy, d2 = dx * dx + dy * dy;
                         if (d2 < best) { best = d2; val = sv[p]; }
                     }
+                    c = (c + 1 < (j + 1) * g.gx) ? nxt[c + 1] : -1;
+                }
+                for (int c = cx > 0 ? prv[j * g.gx + cx - 1] : -1; c >= 0;) {      // to the left
+                    const double xhi = g.x0 + (c - j * g.gx + 1) * g.h;
+                    const double dxb = qx > xhi ? qx - xhi : 0.;
+                    if (dxb * dxb + dyb * dyb > best) break;
+                    for (int p = start[c]; p < start[c + 1]; p++) {
+                        const double dx = sx[p] - qx, dy = sy[p] - qy, d2 = dx * dx + dy * dy;
+                        if (d2 < best) { best = d2; val = sv[p]; }
+                    }
+                    c = (c - 1 >= j * g.gx) ? prv[c - 1] : -1;
                 }
             }
-            const double clr = ring_clearance(g, qx, qy, cx, cy, r);
-            if (clr * clr > best) break;
+            // neither row at this distance is inside the grid and within reach; farther rows are farther still
+            if (!any && dj > 0) break;
         }
         out[iq] = val;
         return;
@@ -983,7 +1026,7 @@ static size_t slow_cap_bytes(size_t n) { return (((n > (size_t)GI_QUERY_BATCH ? 
 struct InterpScratch {
     double *key, *skey, *sx, *sy, *sv, *part, *spart, *grad;
     long long *perm;
-    int *start, *level, *flag;          // flag[0]: levels changed, flag[1]: highest level, flag[2..3]: the sweep's error
+    int *start, *level, *flag, *nxt, *prv;   // flag[0]: levels changed, flag[1]: highest level, flag[2..3]: the sweep's error
     GridCells *g;
     unsigned long long *nfail;
     unsigned *slow;
@@ -1010,6 +1053,8 @@ static InterpScratch interp_carve(void *scratch, size_t n)
     w.sy = (double *)p; p += a256(n * 8);
     w.sv = (double *)p; p += a256(n * 8);
     w.start = (int *)p; p += a256((w.cells + 2) * 4);
+    w.nxt = (int *)p; p += a256((w.cells + 2) * 4);
+    w.prv = (int *)p; p += a256((w.cells + 2) * 4);
     w.part = (double *)p; p += a256(GI_BBOX_BLOCKS * 4 * 8);
     w.g = (GridCells *)p; p += a256(sizeof(GridCells));
     w.nfail = (unsigned long long *)p; p += 256;
@@ -1102,7 +1147,7 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
     const long long *const perm = w.perm;
     const Rings R = w.R;
     Cubic cub;
-    cub.grad = nullptr; cub.R = R;
+    cub.grad = nullptr; cub.R = R; cub.nxt = w.nxt; cub.prv = w.prv;
     if (method == 2) {
         // (a) the Delaunay neighbour rings
         if ((rc = interp_rings(w, num, s))) { if (nfail_host) *nfail_host = 1; return rc; }
@@ -1142,6 +1187,10 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
         const int64_t nb_q = nq - q0 < GI_QUERY_BATCH ? nq - q0 : GI_QUERY_BATCH;
         const unsigned qb = (unsigned)((nb_q + GI_THREADS - 1) / GI_THREADS);
         if (method == 0) {
+            if (q0 == 0) {
+                k_row_links<<<(unsigned)(((int)(w.cells) + 127) / 128), 128, 0, s>>>(start, g, w.nxt, w.prv);     // (one thread per row; rows <= cells)
+                count_launch();
+            }
             k_griddata<0><<<qb, GI_THREADS, 0, s>>>(sx, sy, sv, start, g, qx + q0, qy + q0, nb_q, out + q0, nfail, slow, cub);
             count_launch();
             continue;
