@@ -540,14 +540,35 @@ k_gs_levels(const Rings R, const long long *__restrict__ orig, int num, int *__r
     if (L > level[i]) { level[i] = L; changed[0] = 1; atomicMax(changed + 1, L); }
 }
 
-// One Gauss-Seidel update of the vertices of level `lv` (scipy _estimate_gradients_2d_global, the body of its loop over
+// level of every vertex as a sort key, and the first sorted position of every level (lstart[nlev + 1] = num)
+__global__ void __launch_bounds__(256)
+k_level_keys(const int *__restrict__ level, int num, double *__restrict__ key)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num) key[i] = (double)level[i];
+}
+__global__ void __launch_bounds__(256)
+k_level_starts(const double *__restrict__ skey, int num, int nlev, int *__restrict__ lstart)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num) return;
+    const int c = (int)skey[i];
+    const int prev = i > 0 ? (int)skey[i - 1] : -1;
+    for (int k = prev + 1; k <= c; k++) lstart[k] = i;
+    if (i == num - 1)
+        for (int k = c + 1; k <= nlev + 1; k++) lstart[k] = num;
+}
+
+// One Gauss-Seidel update of the vertices of one level (scipy _estimate_gradients_2d_global, the body of its loop over
 // points).  err: the sweep's largest relative change, as the bits of a non-negative double.
 __global__ void __launch_bounds__(256)
 k_gs_update(const Rings R, const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sv,
-            const int *__restrict__ level, int lv, int num, double *__restrict__ grad, unsigned long long *__restrict__ err)
+            const long long *__restrict__ members, int count, double *__restrict__ grad, unsigned long long *__restrict__ err)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= num || level[i] != lv) return;
+    // members: the vertices of this level (the vertices sorted by level, cut at the level's range)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int i = (int)members[t];
     double Q0 = 0., Q1 = 0., Q3 = 0., s0 = 0., s1 = 0.;
     const int *ring = R.ring + (size_t)i * GI_DEG;
     const double f1 = sv[i], px = sx[i], py = sy[i];
@@ -1021,12 +1042,13 @@ static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t slow_cap_bytes(size_t n) { return (((n > (size_t)GI_QUERY_BATCH ? n : (size_t)GI_QUERY_BATCH) + 64) * 4 + 255) & ~(size_t)255; }
 #define GI_MAX_CELLS (1 << 24)
 #define GI_BBOX_BLOCKS 512
+#define GI_MAX_LEVELS 65536
 
 // the scratch buffer of pxf_griddata / pxf_delaunay_neighbors, carved up
 struct InterpScratch {
     double *key, *skey, *sx, *sy, *sv, *part, *spart, *grad;
-    long long *perm;
-    int *start, *level, *flag, *nxt, *prv;   // flag[0]: levels changed, flag[1]: highest level, flag[2..3]: the sweep's error
+    long long *perm, *lorder;   // lorder: the vertices sorted by Gauss-Seidel level
+    int *start, *level, *flag, *nxt, *prv, *lstart;   // flag[0]: levels changed, flag[1]: highest level, flag[2..3]: the sweep's error
     GridCells *g;
     unsigned long long *nfail;
     unsigned *slow;
@@ -1066,6 +1088,8 @@ static InterpScratch interp_carve(void *scratch, size_t n)
     w.level = (int *)p; p += a256(n * 4);
     w.grad = (double *)p; p += a256(n * 16);
     w.flag = (int *)p; p += 256;
+    w.lorder = (long long *)p; p += a256(n * 8);
+    w.lstart = (int *)p; p += a256((GI_MAX_LEVELS + 4) * 4);
     w.sort_scr = p;
     return w;
 }
@@ -1168,11 +1192,25 @@ int pxf_griddata(const double *x, const double *y, const double *v, int64_t num,
             nlev = h[1];                       // the highest level assigned
             if (!h[0]) break;
         }
-        if (nlev > 65536) { set_error("pxf_griddata: the input order gives %d Gauss-Seidel levels", nlev); return PXF_ERR_UNSUPPORTED; }
+        if (nlev > GI_MAX_LEVELS) { set_error("pxf_griddata: the input order gives %d Gauss-Seidel levels", nlev); return PXF_ERR_UNSUPPORTED; }
+        // the vertices bucketed by level (a sort by level: the binning's key / sorted-key / sort scratch are free again), so
+        // that a level's launch touches its own vertices only
+        k_level_keys<<<vb, 256, 0, s>>>(level, (int)num, w.key);
+        count_launch();
+        if ((rc = pxf_argsort(w.key, num, w.skey, reinterpret_cast<int64_t *>(w.lorder), w.sort_scr, stream))) return rc;
+        k_level_starts<<<vb, 256, 0, s>>>(w.skey, (int)num, nlev, w.lstart);
+        count_launch();
+        std::vector<int> lstart((size_t)nlev + 2);
+        PXF_CUDA(cudaMemcpyAsync(lstart.data(), w.lstart, lstart.size() * 4, cudaMemcpyDeviceToHost, s));
+        PXF_CUDA(cudaStreamSynchronize(s));
         unsigned long long *err = reinterpret_cast<unsigned long long *>(flag + 2);
         for (int sweep = 0; sweep < 400; sweep++) {
             PXF_CUDA(cudaMemsetAsync(err, 0, 8, s));
-            for (int lv = 0; lv <= nlev; lv++) k_gs_update<<<vb, 256, 0, s>>>(R, sx, sy, sv, level, lv, (int)num, grad, err);
+            for (int lv = 0; lv <= nlev; lv++) {
+                const int cnt = lstart[lv + 1] - lstart[lv];
+                if (cnt <= 0) continue;
+                k_gs_update<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(R, sx, sy, sv, w.lorder + lstart[lv], cnt, grad, err);
+            }
             count_launch(nlev + 1);
             unsigned long long he = 0;
             PXF_CUDA(cudaMemcpyAsync(&he, err, 8, cudaMemcpyDeviceToHost, s));
