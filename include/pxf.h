@@ -637,7 +637,8 @@ int pxf_southwellbin(const double *x, const double *y, const double *l, const do
  * sweep by level scheduling, then the Clough-Tocher patch of the containing triangle).  The triangle is found by pivoting
  * to the empty circumcircle over a uniform cell grid; no global triangulation is built.  All arrays on the device; out[nq].  *nfail_host (may be NULL; reading it synchronises)
  * receives the number of queries whose cell could not be resolved (degenerate input; they are NaN).
- * scratch: pxf_griddata_scratch_bytes(num). */
+ * scratch: pxf_griddata_scratch_bytes(num) -- about 300 bytes per point (cell-ordered copies, sort scratch and, for 'cubic',
+ * 48 neighbour slots, the level order and the gradient of every point). */
 size_t pxf_griddata_scratch_bytes(int64_t num);
 int pxf_griddata(const double *x, const double *y, const double *v, int64_t num, const double *qx, const double *qy,
                  double *out, int64_t nq, int32_t method, int64_t *nfail_host, void *scratch, pxf_stream_t stream);
